@@ -1,0 +1,209 @@
+/*
+ * pyxu_b200 -- C ABI of the B200-native hot path (libpyxu_b200.so).
+ *
+ * Drop-in boundary for the inner loop of Pyxu's PD3O / CondatVu / PGD solvers on stencil-based
+ * imaging problems.  Plain pointers and sizes only: every array argument is a DEVICE pointer
+ * (what a DLPack capsule's `data + byte_offset` holds), C-contiguous, dtype given by
+ * `dtype` (PXB_F32 / PXB_F64); `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *
+ * Every entry point returns 0 on success, a negative PXB_E* code otherwise; pxb_last_error()
+ * returns a thread-local human-readable message.  No call synchronises the device.
+ *
+ * Array convention (same as the reference): an array of shape (..., N) with N = prod(arg_shape)
+ * is seen as (batch, n0, n1, n2) with batch = prod(leading dims); arg_shapes of rank < 3 are
+ * left-padded with 1 (kernel extent 1, center 0, mode constant along the padded axes).
+ *
+ * Each declaration cites the reference interface it replaces (file:line in AdriaJ/pyxu).
+ */
+#ifndef PYXU_B200_H
+#define PYXU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PXB_ABI_VERSION 1
+
+enum pxb_dtype { PXB_F32 = 0, PXB_F64 = 1 };
+
+/* boundary modes: numpy.pad names used by Pad/Stencil (reference: src/pyxu/operator/linop/pad.py:158-172) */
+enum pxb_mode { PXB_CONSTANT = 0, PXB_WRAP = 1, PXB_REFLECT = 2, PXB_SYMMETRIC = 3, PXB_EDGE = 4 };
+
+enum pxb_error {
+    PXB_OK = 0,
+    PXB_EINVAL = -1,   /* bad argument (message says which) */
+    PXB_ECUDA = -2,    /* CUDA runtime error (message carries cudaGetErrorString) */
+    PXB_ENOSUP = -3    /* valid request outside the compiled kernel envelope */
+};
+
+#define PXB_MAX_DIRS 3   /* directions of a Gradient stack (<= spatial rank) */
+#define PXB_MAX_GTAP 16  /* taps of one 1-D derivative kernel carried by value */
+
+/* ------------------------------------------------------------------------------------------ */
+/* Domain decomposition along axis 0 (z-slabs).  The arrays handed to a call hold the planes    */
+/* this rank owns; `halo_lo` / `halo_hi` planes of valid neighbour data sit immediately before  */
+/* / after them in memory when the corresponding side is "open".  A closed side is a true       */
+/* domain boundary and gets the boundary mode.  Single-GPU: both closed (all zeros).            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct pxb_slab {
+    int32_t open_lo; /* 1: planes [-halo, 0) hold the lower neighbour's data */
+    int32_t open_hi; /* 1: planes [n0, n0+halo) hold the upper neighbour's data */
+} pxb_slab;
+
+/* ------------------------------------------------------------------------------------------ */
+/* Stencil / Convolve  (reference: src/pyxu/operator/linop/stencil/stencil.py:356-461,         */
+/* _stencil.py:139-198).  One dense correlation kernel of extent ksize[] whose entry            */
+/* center[] sits on the output sample; out-of-domain reads follow mode[] per axis.              */
+/* Separable stencils are issued by the host as one call per axis with ksize = 1 elsewhere.     */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct pxb_stencil_desc {
+    int32_t dtype;
+    int32_t _pad;
+    int64_t batch;
+    int64_t shape[3];
+    int32_t ksize[3];
+    int32_t center[3];
+    int32_t mode[3];
+    pxb_slab slab;
+    const void* coef; /* DEVICE pointer: prod(ksize) coefficients of `dtype`, C-order */
+} pxb_stencil_desc;
+
+/* y = S x  (Stencil.apply, stencil.py:441-450)  /  x = S^T y  (Stencil.adjoint, stencil.py:452-461).
+ * `in` and `out` must not alias. */
+int pxb_stencil_apply(const pxb_stencil_desc* d, const void* in, void* out, void* stream);
+int pxb_stencil_adjoint(const pxb_stencil_desc* d, const void* in, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Gradient stack: ndir first-order 1-D derivative stencils, direction k acting along           */
+/* axis[k] (reference: src/pyxu/operator/linop/diff.py:1113-1265 Gradient,                      */
+/* :952-1056 _stack_diff_ops, :157-261 finite-difference coefficients).                         */
+/* Output layout (batch, ndir, n0, n1, n2) == vstack of the per-direction operators.            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct pxb_grad_desc {
+    int32_t dtype;
+    int32_t ndir;
+    int64_t batch;
+    int64_t shape[3];
+    int32_t mode[3];              /* per AXIS */
+    int32_t axis[PXB_MAX_DIRS];   /* per direction: axis in [0,3) of the left-padded shape */
+    int32_t ntap[PXB_MAX_DIRS];
+    int32_t center[PXB_MAX_DIRS];
+    double coef[PXB_MAX_DIRS][PXB_MAX_GTAP];
+    pxb_slab slab;
+} pxb_grad_desc;
+
+int pxb_gradient_apply(const pxb_grad_desc* d, const void* x, void* z, void* stream);   /* z = K x   */
+int pxb_gradient_adjoint(const pxb_grad_desc* d, const void* z, void* x, void* stream); /* x = K^T z */
+
+/* ------------------------------------------------------------------------------------------ */
+/* Proximal maps of the primal term g (reference: src/pyxu/operator/func/norm.py:47-52 L1Norm, */
+/* :100-104 SquaredL2Norm, :400-403 PositiveL1Norm; func/indicator.py:203-206 PositiveOrthant, */
+/* :58-69 LInfinityBall; ScaleRule abc/arithmetic.py:182).  prox_{tau*g}.                      */
+/* ------------------------------------------------------------------------------------------ */
+enum pxb_prox_kind {
+    PXB_PROX_NONE = 0,  /* g = 0                      : v                                   */
+    PXB_PROX_POS = 1,   /* g = i_{x>=0}               : max(v, 0)                           */
+    PXB_PROX_BOX = 2,   /* g = i_{p0<=x<=p1}          : clip(v, p0, p1)                     */
+    PXB_PROX_L1 = 3,    /* g = p0*||x||_1             : soft(v, p0*tau)                     */
+    PXB_PROX_POSL1 = 4, /* g = p0*(||x||_1 + i_+)     : max(v - p0*tau, 0)                  */
+    PXB_PROX_SQL2 = 5   /* g = p0*||x||_2^2           : v / (2*p0*tau + 1)                  */
+};
+typedef struct pxb_prox_spec {
+    int32_t kind;
+    int32_t _pad;
+    double p0, p1;
+} pxb_prox_spec;
+
+/* out[i] = prox_{tau g}( a*x[i] + b*y[i % ny] + c*z[i % nz] );  y, z may be NULL (term dropped).
+ * One pass: the linear combination every solver forms before calling g.prox
+ * (pds.py:431-434, :750-753; pgd.py:179-191).  out may alias x. */
+int pxb_prox_lincomb(int dtype, const pxb_prox_spec* g, double tau, int64_t n, void* out,
+                     double a, const void* x, double b, const void* y, int64_t ny,
+                     double c, const void* z, int64_t nz, void* stream);
+
+/* out[i] = a*x[i] + b*y[i % ny] + c*z[i % nz]  (ScaleRule / ArgShiftRule / relaxation algebra). */
+int pxb_lincomb(int dtype, int64_t n, void* out, double a, const void* x, double b, const void* y,
+                int64_t ny, double c, const void* z, int64_t nz, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Dual term h (reference: src/pyxu/operator/func/norm.py:352-364 L21Norm.prox, :47-52 L1Norm;  */
+/* fenchel_prox abc/operator.py:906-944).  Arrays are (outer, group, inner); the l2 norm runs   */
+/* over `group` (for TV: outer = batch, group = ndir, inner = voxels).                          */
+/* ------------------------------------------------------------------------------------------ */
+enum pxb_dual_kind { PXB_DUAL_NONE = 0, PXB_DUAL_L21 = 1, PXB_DUAL_L1 = 2 };
+
+/* out = prox_{tau*lam*||.||_{2,1}}(x)                (L21Norm.prox through ScaleRule) */
+int pxb_prox_l21(int dtype, int64_t outer, int64_t group, int64_t inner, double lam, double tau,
+                 const void* x, void* out, void* stream);
+
+/* Dual update of CondatVu / PD3O (pds.py:437-441, :756-760):
+ *   p = z + sigma*t ;  z <- (1-rho)*z + rho*prox_{sigma h*}(p),  h = lam*L21 | lam*L1.
+ * norms (nullable): per `outer` row, += { sum (z_new-z_old)^2, sum z_old^2 }  (RelError[z]). */
+int pxb_dual_update(int dtype, int kind, int64_t outer, int64_t group, int64_t inner, double lam,
+                    double sigma, double rho, void* z, const void* t, double* norms, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Fused primal / dual half-iterations for h o K with K a Gradient stack (TV-type problems).    */
+/* One pass over every voxel each.                                                              */
+/* ------------------------------------------------------------------------------------------ */
+enum pxb_algo { PXB_PD3O = 0, PXB_CV = 1 };
+
+enum pxb_fterm_kind {
+    PXB_F_NONE = 0,    /* f = 0 */
+    PXB_F_SQL2 = 1,    /* f = alpha*||x + shift||^2, grad = 2*alpha*(x + shift)  (SquaredL2Norm + ArgShift + Scale) */
+    PXB_F_GRADARR = 2  /* CV only: grad f(x_k) precomputed in `garr` (non-local f, e.g. blur data term) */
+};
+typedef struct pxb_fterm {
+    int32_t kind;
+    int32_t _pad;
+    double alpha;
+    const void* shift;    /* DEVICE, nullable (zero shift) */
+    int64_t shift_period; /* shift[i % shift_period] (broadcast over stacked problems) */
+    const void* garr;     /* DEVICE, PXB_F_GRADARR */
+} pxb_fterm;
+
+typedef struct pxb_pds_params {
+    double tau, sigma, rho;
+    pxb_prox_spec g;
+    pxb_fterm f;
+    int32_t hkind; /* pxb_dual_kind */
+    int32_t _pad;
+    double lam;
+} pxb_pds_params;
+
+/* Primal half-step, per voxel s (K^T z gathered in-kernel from z unless `ktz` is given):
+ *  PD3O (pds.py:747-761):  x = prox_g(u - tau*K^T z);  ut = x - tau*grad f(x);
+ *                          w = x + ut - u;  u <- (1-rho)*u + rho*ut
+ *        `xu` holds u (in/out), `x_out` receives x, `w` receives w.
+ *  CV   (pds.py:429-442):  xt = prox_g(x - tau*grad f(x) - tau*K^T z);  w = 2*xt - x;
+ *                          x <- rho*xt + (1-rho)*x
+ *        `xu` holds x (in/out), `x_out` unused (may be NULL), `w` receives 2*xt - x.
+ *  norms (nullable): per batch row += { sum (x_new-x_old)^2, sum x_old^2 } where x_old is the
+ *  previous content of x_out (PD3O) / xu (CV)  -> RelError[x] without an extra pass. */
+int pxb_pds_primal(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu,
+                   const void* z, const void* ktz, void* x_out, void* w, double* norms, void* stream);
+
+/* Dual half-step:  z <- (1-rho)*z + rho*prox_{sigma h*}(z + sigma*K w)  with K w gathered in-kernel.
+ * norms as in pxb_dual_update. */
+int pxb_pds_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w, void* z,
+                 double* norms, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Stopping-criterion norms (reference: src/pyxu/opt/stop.py:273-284 AbsError, :353-382         */
+/* RelError).  Per row r of a (rows, n) array:  out[2r] += sum (x-y)^2 (y NULL -> sum x^2),     */
+/* out[2r+1] += sum y^2.  `out` is a DEVICE double[2*rows] the caller zeroes.                   */
+/* ------------------------------------------------------------------------------------------ */
+int pxb_sqnorms(int dtype, int64_t rows, int64_t n, const void* x, const void* y, double* out, void* stream);
+
+/* misc */
+int pxb_abi_version(void);
+const char* pxb_last_error(void);
+/* number of kernels this library has launched in the calling process (bench's gpu_launches) */
+int64_t pxb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYXU_B200_H */
