@@ -50,6 +50,10 @@ enum pxb_error {
 typedef struct pxb_slab {
     int32_t open_lo; /* 1: planes [-halo, 0) hold the lower neighbour's data */
     int32_t open_hi; /* 1: planes [n0, n0+halo) hold the upper neighbour's data */
+    int32_t halo;    /* planes allocated on EACH side of the owned planes (0 on a single GPU).  Arrays are
+                        (halo + n0 + halo, n1, n2) per component; pointers passed to a call address owned
+                        plane 0.  halo > 0 requires batch == 1. */
+    int32_t _pad;
 } pxb_slab;
 
 /* ------------------------------------------------------------------------------------------ */

@@ -1,0 +1,340 @@
+"""
+Solver / StoppingCriterion base classes
+(reference: src/pyxu/abc/solver.py -- Mode:27, StoppingCriterion:37, Solver:119).
+
+Same user-facing protocol: `fit(**kwargs, stop_crit=..., mode=..., track_objective=...)`,
+`steps()`, `stats()`, `solution()`, `busy()`, `stop()`, `writeback()`, `workdir / logfile /
+datafile`; sub-classes implement `m_init()` / `m_step()`.  The mathematical state `_mstate` holds
+device buffers; `stats()` hands arrays back in the memory space `fit()` received them in
+(NumPy in -> NumPy out).  Stopping criteria are tested before each step, as in the reference
+(solver.py:588-652).
+"""
+import datetime as dt
+import enum
+import logging
+import operator
+import pathlib as plib
+import shutil
+import sys
+import tempfile
+import threading
+
+import numpy as np
+
+from .. import _array as A
+
+
+@enum.unique
+class Mode(enum.Enum):
+    BLOCK = enum.auto()
+    MANUAL = enum.auto()
+    ASYNC = enum.auto()
+
+
+class StoppingCriterion:
+    def stop(self, state):
+        raise NotImplementedError
+
+    def info(self):
+        raise NotImplementedError
+
+    def clear(self):
+        pass
+
+    def __or__(self, other):
+        return _Composition(self, other, operator.or_)
+
+    def __and__(self, other):
+        return _Composition(self, other, operator.and_)
+
+    # variables whose ||x_k - x_{k-1}||, ||x_{k-1}|| the solver may accumulate inside its update kernels
+    def _fused_vars(self):
+        return frozenset()
+
+    def _needs_host_sync(self):
+        return True
+
+
+class _Composition(StoppingCriterion):
+    def __init__(self, lhs, rhs, op):
+        self._lhs, self._rhs, self._op = lhs, rhs, op
+
+    def stop(self, state):
+        return self._op(self._lhs.stop(state), self._rhs.stop(state))
+
+    def info(self):
+        return {**self._lhs.info(), **self._rhs.info()}
+
+    def clear(self):
+        self._lhs.clear()
+        self._rhs.clear()
+
+    def _fused_vars(self):
+        return self._lhs._fused_vars() | self._rhs._fused_vars()
+
+    def _needs_host_sync(self):
+        return self._lhs._needs_host_sync() or self._rhs._needs_host_sync()
+
+
+class Solver:
+    def __init__(self, *, folder=None, exist_ok=False, stop_rate=1, writeback_rate=None, verbosity=None,
+                 show_progress=True, log_var=frozenset()):
+        self._mstate = dict()
+        self._astate = dict(history=None, idx=0, log_rate=None, log_var=None, logger=None, stdout=None, stop_crit=None,
+                            stop_rate=None, track_objective=None, wb_rate=None, workdir=None, mode=None, active=None,
+                            worker=None, origin=A.DEVICE)
+        try:
+            if folder is None:
+                folder = plib.Path(tempfile.mkdtemp(prefix="pyxu_"))
+            elif (folder := plib.Path(folder).expanduser().resolve()).exists() and (not exist_ok):
+                raise FileExistsError(f"{folder} already exists.")
+            else:
+                shutil.rmtree(folder, ignore_errors=True)
+                folder.mkdir(parents=True)
+            self._astate["workdir"] = folder
+        except FileExistsError:
+            raise
+        except Exception:
+            raise Exception(f"folder: expected path-like, got {type(folder)}.")
+
+        try:
+            assert stop_rate >= 1
+            self._astate["stop_rate"] = int(stop_rate)
+        except Exception:
+            raise ValueError(f"stop_rate must be positive, got {stop_rate}.")
+        try:
+            self._astate["wb_rate"] = writeback_rate
+            if writeback_rate is not None:
+                assert writeback_rate % self._astate["stop_rate"] == 0
+                self._astate["wb_rate"] = int(writeback_rate)
+        except Exception:
+            raise ValueError(f"writeback_rate must be a multiple of stop_rate({stop_rate}), got {writeback_rate}.")
+        try:
+            if verbosity is None:
+                verbosity = self._astate["stop_rate"]
+            assert verbosity % self._astate["stop_rate"] == 0
+            self._astate["log_rate"] = int(verbosity)
+            self._astate["stdout"] = bool(show_progress)
+        except Exception:
+            raise ValueError(f"verbosity must be a multiple of stop_rate({stop_rate}), got {verbosity}.")
+        try:
+            if isinstance(log_var, str):
+                log_var = (log_var,)
+            self._astate["log_var"] = frozenset(log_var)
+        except Exception:
+            raise ValueError(f"log_var: expected collection, got {type(log_var)}.")
+
+    # -- user API ---------------------------------------------------------------------------
+    def fit(self, **kwargs):
+        self._fit_init(
+            mode=kwargs.pop("mode", Mode.BLOCK),
+            stop_crit=kwargs.pop("stop_crit", None),
+            track_objective=kwargs.pop("track_objective", False),
+        )
+        self.m_init(**kwargs)
+        self._fit_run()
+
+    def m_init(self, **kwargs):
+        raise NotImplementedError
+
+    def m_step(self):
+        raise NotImplementedError
+
+    def steps(self, n=None):
+        self._check_mode(Mode.MANUAL)
+        i = 0
+        while (n is None) or (i < n):
+            if self._step():
+                data, _ = self.stats()
+                yield data
+                i += 1
+            else:
+                self._astate["mode"] = None
+                self._cleanup_logger()
+                return
+
+    def _materialize(self, name):
+        """Hook: bring a lazily-maintained state variable up to date (fused solvers override)."""
+        return self._mstate.get(name)
+
+    def stats(self):
+        history = self._astate["history"]
+        if history is not None:
+            history = np.concatenate(history, dtype=history[0].dtype, axis=0) if len(history) > 0 else None
+        data = {}
+        for k in self._astate["log_var"]:
+            v = self._materialize(k)
+            if v is not None and hasattr(v, "is_cuda"):
+                v = A.restore(v, self._astate["origin"])
+            data[k] = v
+        return data, history
+
+    @property
+    def workdir(self):
+        return self._astate["workdir"]
+
+    @property
+    def logfile(self):
+        return self.workdir / "solver.log"
+
+    @property
+    def datafile(self):
+        return self.workdir / "data.npz"
+
+    def busy(self):
+        self._check_mode(Mode.ASYNC, Mode.BLOCK)
+        return self._astate["active"].is_set()
+
+    def solution(self):
+        raise NotImplementedError
+
+    def stop(self):
+        self._check_mode(Mode.ASYNC, Mode.BLOCK)
+        self._astate["active"].clear()
+        self._astate["worker"].join()
+        self._astate.update(mode=None, active=None, worker=None)
+        self._cleanup_logger()
+
+    def writeback(self):
+        data, history = self.stats()
+        kwargs = {}
+        for k, v in dict(history=history, **data).items():
+            if v is None:
+                continue
+            kwargs[k] = v.cpu().numpy() if hasattr(v, "is_cuda") else np.asarray(v)
+        np.savez(self.datafile, **kwargs)
+
+    def default_stop_crit(self):
+        raise NotImplementedError("No default stopping criterion defined.")
+
+    def objective_func(self):
+        raise NotImplementedError("No objective function defined.")
+
+    # -- internals --------------------------------------------------------------------------
+    def _fit_init(self, mode, stop_crit, track_objective):
+        def _init_logger():
+            logger = logging.getLogger(str(self.workdir))
+            logger.handlers.clear()
+            logger.setLevel("DEBUG")
+            fmt = logging.Formatter(fmt="{levelname} -- {message}", style="{")
+            handlers = [logging.FileHandler(self.logfile, mode="w")]
+            if (mode is Mode.BLOCK) and self._astate["stdout"]:
+                handlers.append(logging.StreamHandler(sys.stdout))
+            for h in handlers:
+                h.setLevel("DEBUG")
+                h.setFormatter(fmt)
+                logger.addHandler(h)
+            return logger
+
+        self._mstate.clear()
+        if stop_crit is None:
+            stop_crit = self.default_stop_crit()
+        stop_crit.clear()
+        if track_objective:
+            from ..opt.stop import Memorize
+
+            stop_crit |= Memorize(var="objective_func")
+        self._astate.update(history=[], idx=0, logger=_init_logger(), stop_crit=stop_crit, track_objective=track_objective,
+                            mode=mode, active=None, worker=None)
+
+    def _fit_run(self):
+        mode = self._astate["mode"]
+        if mode is Mode.MANUAL:
+            return
+        if mode is Mode.BLOCK:
+            # The reference runs BLOCK mode in a worker thread it immediately joins (solver.py:541-560); the
+            # loop is run inline here so that CUDA's thread-local current device / stream stay the caller's.
+            while self._step():
+                pass
+            self._astate.update(mode=None, active=None, worker=None)
+            self._cleanup_logger()
+            return
+        import torch
+
+        self._astate["device"] = torch.cuda.current_device() if torch.cuda.is_available() else None
+        self._astate.update(active=threading.Event(), worker=Solver._Worker(self))
+        self._astate["active"].set()
+        self._astate["worker"].start()
+
+    def _check_mode(self, *modes):
+        m = self._astate["mode"]
+        if m in modes:
+            return
+        if m is None:
+            msg = "Illegal method call: invoke Solver.fit() first."
+        else:
+            msg = " ".join(["Illegal method call: can only be used if Solver.fit() invoked with",
+                            "mode=Any[" + ", ".join(map(lambda _: str(_.name), modes)) + "]"])
+        raise ValueError(msg)
+
+    def _step(self):
+        ast = self._astate
+        must_stop = ast["idx"] % ast["stop_rate"] == 0
+        must_log = ast["idx"] % ast["log_rate"] == 0
+        must_wb = (ast["wb_rate"] is not None) and (ast["idx"] % ast["wb_rate"] == 0)
+
+        def _log(msg=None):
+            if msg is None:
+                h = ast["history"][-1][0]
+                msg = [f"[{dt.datetime.now()}] Iteration {ast['idx']:>_d}"]
+                for field, value in zip(h.dtype.names, h):
+                    msg.append(f"\t{field}: {value}")
+                msg = "\n".join(msg)
+            ast["logger"].info(msg)
+
+        def _update_history():
+            data = ast["stop_crit"].info()
+            dtype = np.dtype([("iteration", np.int64)] + [(k, np.float64) for k in data])
+            rec = np.zeros(1, dtype=dtype)
+            rec["iteration"] = ast["idx"]
+            for k, v in data.items():
+                rec[k] = v
+            ast["history"].append(rec)
+
+        try:
+            if must_stop and ast["track_objective"]:
+                self._mstate["objective_func"] = self.objective_func().reshape(-1)
+            if must_stop and ast["stop_crit"].stop(self._mstate):
+                _update_history()
+                _log()
+                _log(msg=f"[{dt.datetime.now()}] Stopping Criterion satisfied -> END")
+                self.writeback()
+                return False
+            if must_stop:
+                _update_history()
+            if must_log:
+                _log()
+            if must_wb:
+                self.writeback()
+            ast["idx"] += 1
+            self.m_step()
+            return True
+        except Exception as e:
+            msg = f"[{dt.datetime.now()}] Something went wrong -> EXCEPTION RAISED"
+            print("\n".join([msg, f"More information: {self.logfile}."]), file=sys.stderr)
+            if ast["wb_rate"] is not None:
+                _, r = divmod(ast["idx"], ast["wb_rate"])
+                msg = "\n".join([msg, f"Last valid checkpoint done at iteration={ast['idx'] - r}."])
+            ast["logger"].exception(msg, exc_info=e)
+            ast["error"] = e
+            return False
+
+    def _cleanup_logger(self):
+        logger = logging.getLogger(str(self.workdir))
+        for handler in logger.handlers:
+            handler.close()
+
+    class _Worker(threading.Thread):
+        def __init__(self, solver):
+            super().__init__()
+            self.slvr = solver
+
+        def run(self):
+            import torch
+
+            dev = self.slvr._astate.get("device")
+            if dev is not None:
+                torch.cuda.set_device(dev)  # worker threads start on device 0
+            while self.slvr.busy() and self.slvr._step():
+                pass
+            self.slvr._astate["active"].clear()

@@ -87,6 +87,12 @@ PXB_HD void pxb_preimage(int s, int n, int mode, int p, int open_lo, int open_hi
     P.cnt = c;
 }
 
+// true when sample s has no folded pre-image (conservative for every mode): only e == s maps onto it.
+PXB_HD bool pxb_no_fold(int s, int n, int mode, int p, int open_lo, int open_hi) {
+    if (mode == PXB_CONSTANT || p <= 0) return true;
+    return (open_lo || s > p) && (open_hi || s < n - 1 - p);
+}
+
 PXB_HD int pxb_imax(int a, int b) { return a > b ? a : b; }
 PXB_HD int pxb_imin(int a, int b) { return a < b ? a : b; }
 
@@ -119,7 +125,7 @@ PXB_HD T pxb_corr1d_adj_at(const T* __restrict__ line, int64_t stride, int n, in
     const int p = nt - 1;
     // rows i that exist: [ilo, ihi]; halo rows count when the side is open.
     const int ilo = open_lo ? -p : 0, ihi = open_hi ? n - 1 + p : n - 1;
-    if (s - (nt - 1 - cen) >= 0 && s + cen <= n - 1) {  // interior: single pre-image, all rows valid
+    if (s - (nt - 1 - cen) >= 0 && s + cen <= n - 1 && pxb_no_fold(s, n, mode, p, open_lo, open_hi)) {  // interior: single pre-image, all rows valid
         for (int q = 0; q < nt; ++q) acc += T(coef[q]) * line[(int64_t)(s + cen - q) * stride];
         return acc;
     }
@@ -194,7 +200,9 @@ PXB_HD T pxb_stencil_adj_at(const pxb_stencil_desc& d, const PxbGeom& g, const T
     const int k0 = d.ksize[0], k1 = d.ksize[1], k2 = d.ksize[2];
     const int c0 = d.center[0], c1 = d.center[1], c2 = d.center[2];
     const bool interior = s0 - (k0 - 1 - c0) >= 0 && s0 + c0 <= g.n0 - 1 && s1 - (k1 - 1 - c1) >= 0 &&
-                          s1 + c1 <= g.n1 - 1 && s2 - (k2 - 1 - c2) >= 0 && s2 + c2 <= g.n2 - 1;
+                          s1 + c1 <= g.n1 - 1 && s2 - (k2 - 1 - c2) >= 0 && s2 + c2 <= g.n2 - 1 &&
+                          pxb_no_fold(s0, g.n0, d.mode[0], k0 - 1, d.slab.open_lo, d.slab.open_hi) &&
+                          pxb_no_fold(s1, g.n1, d.mode[1], k1 - 1, 0, 0) && pxb_no_fold(s2, g.n2, d.mode[2], k2 - 1, 0, 0);
     if (interior) {
         for (int q0 = 0; q0 < k0; ++q0)
             for (int q1 = 0; q1 < k1; ++q1) {
@@ -340,4 +348,141 @@ PXB_HD void pxb_primal_at(int algo, const pxb_pds_params& P, T ktz, T xu_old, in
         xu_new = rho * xt + (T(1) - rho) * xu_old;
         x_out = xu_new;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-voxel kernel bodies.  (b, i0, i1, i2) is the voxel; array base pointers address owned plane 0
+// of batch item 0.  `vol` = elements per component incl. halo planes = (n0 + 2*halo)*n1*n2.
+// ---------------------------------------------------------------------------------------------
+PXB_HD int64_t pxb_vol(const PxbGeom& g, const pxb_slab& s) { return (int64_t)(g.n0 + 2 * s.halo) * g.s0; }
+
+template <class T>
+PXB_HD void pxb_body_stencil(const pxb_stencil_desc& d, const PxbGeom& g, bool adjoint, const T* __restrict__ in,
+                             T* __restrict__ out, int64_t b, int i0, int i1, int i2) {
+    const int64_t vol = pxb_vol(g, d.slab);
+    const T* img = in + b * vol;
+    const int64_t o = b * vol + (int64_t)i0 * g.s0 + (int64_t)i1 * g.s1 + i2;
+    out[o] = adjoint ? pxb_stencil_adj_at<T>(d, g, img, (const T*)d.coef, i0, i1, i2)
+                     : pxb_stencil_at<T>(d, g, img, (const T*)d.coef, i0, i1, i2);
+}
+
+template <class T>
+PXB_HD void pxb_body_grad_apply(const pxb_grad_desc& d, const PxbGeom& g, const T* __restrict__ x, T* __restrict__ z,
+                                int64_t b, int i0, int i1, int i2) {
+    const int64_t vol = pxb_vol(g, d.slab);
+    const int64_t v = (int64_t)i0 * g.s0 + (int64_t)i1 * g.s1 + i2;
+    for (int k = 0; k < d.ndir; ++k) z[(b * d.ndir + k) * vol + v] = pxb_grad_dir_at<T>(d, g, k, x + b * vol, i0, i1, i2);
+}
+
+template <class T>
+PXB_HD void pxb_body_grad_adjoint(const pxb_grad_desc& d, const PxbGeom& g, const T* __restrict__ z, T* __restrict__ x,
+                                  int64_t b, int i0, int i1, int i2) {
+    const int64_t vol = pxb_vol(g, d.slab);
+    const int64_t v = (int64_t)i0 * g.s0 + (int64_t)i1 * g.s1 + i2;
+    x[b * vol + v] = pxb_grad_adj_at<T>(d, g, z + b * d.ndir * vol, vol, i0, i1, i2);
+}
+
+// primal half-step; n0/n1 accumulate sum (x_new - x_old)^2, sum x_old^2 when `want_norms`.
+template <class T>
+PXB_HD void pxb_body_primal(int algo, const pxb_grad_desc& d, const PxbGeom& g, const pxb_pds_params& P,
+                            T* __restrict__ xu, const T* __restrict__ z, const T* __restrict__ ktz, T* __restrict__ x_out,
+                            T* __restrict__ w, bool want_norms, double& n0, double& n1, int64_t b, int i0, int i1, int i2) {
+    const int64_t vol = pxb_vol(g, d.slab);
+    const int64_t lin = b * vol + (int64_t)i0 * g.s0 + (int64_t)i1 * g.s1 + i2;
+    T kz = T(0);
+    if (ktz) kz = ktz[lin];
+    else if (P.hkind != PXB_DUAL_NONE) kz = pxb_grad_adj_at<T>(d, g, z + b * d.ndir * vol, vol, i0, i1, i2);
+    const T old = xu[lin];
+    T xu_new, xo, wo;
+    pxb_primal_at<T>(algo, P, kz, old, lin, xu_new, xo, wo);
+    if (want_norms) {
+        const T xprev = (algo == PXB_PD3O) ? x_out[lin] : old;
+        const double dd = (double)xo - (double)xprev;
+        n0 += dd * dd;
+        n1 += (double)xprev * (double)xprev;
+    }
+    xu[lin] = xu_new;
+    w[lin] = wo;
+    if (algo == PXB_PD3O) x_out[lin] = xo;
+}
+
+// dual half-step with in-kernel K w.
+template <class T>
+PXB_HD void pxb_body_dual(const pxb_grad_desc& d, const PxbGeom& g, const pxb_pds_params& P, const T* __restrict__ w,
+                          T* __restrict__ z, bool want_norms, double& n0, double& n1, int64_t b, int i0, int i1, int i2) {
+    const int64_t vol = pxb_vol(g, d.slab);
+    const int64_t v = (int64_t)i0 * g.s0 + (int64_t)i1 * g.s1 + i2;
+    T zo[PXB_MAX_DIRS], p[PXB_MAX_DIRS];
+    const T sigma = T(P.sigma), rho = T(P.rho);
+    for (int k = 0; k < d.ndir; ++k) {
+        zo[k] = z[(b * d.ndir + k) * vol + v];
+        p[k] = zo[k] + sigma * pxb_grad_dir_at<T>(d, g, k, w + b * vol, i0, i1, i2);
+    }
+    pxb_dual_prox_group<T>(P.hkind, d.ndir, T(P.lam), sigma, p);
+    for (int k = 0; k < d.ndir; ++k) {
+        const T zn = (T(1) - rho) * zo[k] + rho * p[k];
+        if (want_norms) {
+            const double dd = (double)zn - (double)zo[k];
+            n0 += dd * dd;
+            n1 += (double)zo[k] * (double)zo[k];
+        }
+        z[(b * d.ndir + k) * vol + v] = zn;
+    }
+}
+
+// dual update from a precomputed t = K w, arbitrary group size (outer, group, inner).
+template <class T>
+PXB_HD void pxb_body_dual_update(int kind, int64_t group, int64_t inner, T lam, T sigma, T rho, T* __restrict__ z,
+                                 const T* __restrict__ t, bool want_norms, double& n0, double& n1, int64_t o, int64_t i) {
+    const int64_t base = o * group * inner + i;
+    const T tp = (T(1) / sigma) * lam;
+    T sc = T(0);
+    if (kind == PXB_DUAL_L21) {
+        T nn = T(0);
+        for (int64_t k = 0; k < group; ++k) {
+            const T a = (z[base + k * inner] + sigma * t[base + k * inner]) / sigma;
+            nn += a * a;
+        }
+        const T nrm = sqrt(nn);
+        sc = T(1) - tp / (nrm > tp ? nrm : tp);
+    }
+    for (int64_t k = 0; k < group; ++k) {
+        const T zo = z[base + k * inner];
+        const T p = zo + sigma * t[base + k * inner];
+        const T a = p / sigma;
+        T pr;
+        if (kind == PXB_DUAL_L21) pr = p - sigma * (a * sc);
+        else if (kind == PXB_DUAL_L1) {
+            const T m = fabs(a) - tp;
+            pr = p - sigma * (m > T(0) ? (a < T(0) ? -m : m) : T(0));
+        } else pr = p;
+        const T zn = (T(1) - rho) * zo + rho * pr;
+        if (want_norms) {
+            const double dd = (double)zn - (double)zo;
+            n0 += dd * dd;
+            n1 += (double)zo * (double)zo;
+        }
+        z[base + k * inner] = zn;
+    }
+}
+
+// out = prox_{tau*lam*L21}(x) on (outer, group, inner)   (norm.py:352-364)
+template <class T>
+PXB_HD void pxb_body_prox_l21(int64_t group, int64_t inner, T lam, T tau, const T* __restrict__ x, T* __restrict__ out,
+                              int64_t o, int64_t i) {
+    const int64_t base = o * group * inner + i;
+    const T t = tau * lam;
+    T nn = T(0);
+    for (int64_t k = 0; k < group; ++k) { const T a = x[base + k * inner]; nn += a * a; }
+    const T nrm = sqrt(nn);
+    const T sc = T(1) - t / (nrm > t ? nrm : t);
+    for (int64_t k = 0; k < group; ++k) out[base + k * inner] = x[base + k * inner] * sc;
+}
+
+template <class T>
+PXB_HD T pxb_lincomb_at(T a, const T* x, T b, const T* y, int64_t ny, T c, const T* z, int64_t nz, int64_t i) {
+    T v = a * x[i];
+    if (y) v += b * y[ny ? i % ny : i];
+    if (z) v += c * z[nz ? i % nz : i];
+    return v;
 }

@@ -1,0 +1,487 @@
+// pxb_kernels.cu -- CUDA kernels (sm_100a) + C ABI of libpyxu_b200.so.
+//
+// Every kernel on this path is HBM-bound integer-free streaming work (a handful of FMAs per byte
+// moved), so the design rules are: one pass per voxel, coalesced accesses along the fastest axis,
+// neighbour taps served by L1/L2 (a z-plane of 1024^2 fp32 is 4 MiB, the L2 is 126 MB), grid sized
+// from the volume, fp64 accumulation of the stopping-criterion norms with one atomic per block.
+// Tensor cores are deliberately unused: nothing here is a dense contraction.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "pxb_core.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define PXB_CHECK_LAUNCH(name)                                                         \
+    do {                                                                               \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                            \
+        cudaError_t e_ = cudaGetLastError();                                           \
+        if (e_ != cudaSuccess) return fail(PXB_ECUDA, "%s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Thread -> voxel mapping.  A block is TX x TY threads: TX consecutive samples of a row (axis 2,
+// unit stride => coalesced) times TY rows.  Rows are the flattened (batch, i0, i1) index.
+// ------------------------------------------------------------------------------------------
+constexpr int kBlock = 256;
+
+struct VoxMap {
+    int tx_log2;      // TX = 1 << tx_log2
+    int nxt;          // x-tiles per row
+    int64_t rows;     // batch * n0 * n1
+    int n0, n1, n2;
+    unsigned grid;
+};
+
+inline bool make_map(int64_t batch, const int64_t shape[3], VoxMap& m) {
+    m.n0 = (int)shape[0]; m.n1 = (int)shape[1]; m.n2 = (int)shape[2];
+    int l = 5;  // TX in [32, 256]: a warp never straddles rows
+    while ((1 << l) < m.n2 && l < 8) ++l;
+    m.tx_log2 = l;
+    const int TX = 1 << l, TY = kBlock / TX;
+    m.nxt = (m.n2 + TX - 1) / TX;
+    m.rows = batch * shape[0] * shape[1];
+    const int64_t nblk = (int64_t)m.nxt * ((m.rows + TY - 1) / TY);
+    if (nblk <= 0 || nblk > 0x7fffffffLL) return false;
+    m.grid = (unsigned)nblk;
+    return true;
+}
+
+struct Vox {
+    int64_t b;
+    int i0, i1, i2;
+    bool ok;
+};
+
+__device__ __forceinline__ Vox vox_of_thread(const VoxMap& m) {
+    const int TX = 1 << m.tx_log2;
+    const int tx = threadIdx.x & (TX - 1), ty = threadIdx.x >> m.tx_log2;
+    const unsigned bx = blockIdx.x % (unsigned)m.nxt, by = blockIdx.x / (unsigned)m.nxt;
+    Vox v;
+    v.i2 = (int)bx * TX + tx;
+    const int64_t r = (int64_t)by * (kBlock >> m.tx_log2) + ty;
+    v.ok = (v.i2 < m.n2) && (r < m.rows);
+    if (m.rows <= 0xffffffffLL) {  // 32-bit divisions on the common path
+        const unsigned r32 = (unsigned)r, n1 = (unsigned)m.n1, n0 = (unsigned)m.n0;
+        const unsigned q = r32 / n1;
+        v.i1 = (int)(r32 - q * n1);
+        const unsigned bb = q / n0;
+        v.i0 = (int)(q - bb * n0);
+        v.b = bb;
+    } else {
+        const int64_t q = r / m.n1;
+        v.i1 = (int)(r - q * m.n1);
+        v.b = q / m.n0;
+        v.i0 = (int)(q - v.b * m.n0);
+    }
+    return v;
+}
+
+// Block-wide sum of two doubles, then one atomicAdd pair per block into out[2*b], out[2*b+1].
+// Fast path requires every thread of the block to belong to the same batch row `b` (true whenever
+// n0*n1 >= TY, i.e. always except toy sizes); otherwise each thread adds on its own.
+__device__ __forceinline__ void block_accumulate(double a0, double a1, int64_t b, bool ok, double* out) {
+    __shared__ double sh[2][kBlock / 32];
+    __shared__ long long sb_min, sb_max;
+    if (threadIdx.x == 0) { sb_min = 0x7fffffffffffffffLL; sb_max = -1; }
+    __syncthreads();
+    if (ok) { atomicMin(&sb_min, (long long)b); atomicMax(&sb_max, (long long)b); }
+    __syncthreads();
+    if (sb_max < 0) return;
+    if (sb_min != sb_max) {
+        if (ok) { atomicAdd(out + 2 * b, a0); atomicAdd(out + 2 * b + 1, a1); }
+        return;
+    }
+    if (!ok) { a0 = 0.0; a1 = 0.0; }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = a0; sh[1][w] = a1; }
+    __syncthreads();
+    if (w == 0) {
+        a0 = l < kBlock / 32 ? sh[0][l] : 0.0;
+        a1 = l < kBlock / 32 ? sh[1][l] : 0.0;
+        for (int o = 4; o > 0; o >>= 1) {
+            a0 += __shfl_down_sync(0xffffffffu, a0, o);
+            a1 += __shfl_down_sync(0xffffffffu, a1, o);
+        }
+        if (l == 0) { atomicAdd(out + 2 * sb_min, a0); atomicAdd(out + 2 * sb_min + 1, a1); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernels
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_stencil(pxb_stencil_desc d, VoxMap m, int adjoint, const T* __restrict__ in, T* __restrict__ out) {
+    const Vox v = vox_of_thread(m);
+    if (!v.ok) return;
+    const PxbGeom g = pxb_geom(d.shape);
+    pxb_body_stencil<T>(d, g, adjoint != 0, in, out, v.b, v.i0, v.i1, v.i2);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_grad_apply(pxb_grad_desc d, VoxMap m, const T* __restrict__ x, T* __restrict__ z) {
+    const Vox v = vox_of_thread(m);
+    if (!v.ok) return;
+    const PxbGeom g = pxb_geom(d.shape);
+    pxb_body_grad_apply<T>(d, g, x, z, v.b, v.i0, v.i1, v.i2);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_grad_adjoint(pxb_grad_desc d, VoxMap m, const T* __restrict__ z, T* __restrict__ x) {
+    const Vox v = vox_of_thread(m);
+    if (!v.ok) return;
+    const PxbGeom g = pxb_geom(d.shape);
+    pxb_body_grad_adjoint<T>(d, g, z, x, v.b, v.i0, v.i1, v.i2);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_pds_primal(int algo, pxb_grad_desc d, pxb_pds_params P, VoxMap m, T* __restrict__ xu,
+                                                       const T* __restrict__ z, const T* __restrict__ ktz, T* __restrict__ x_out,
+                                                       T* __restrict__ w, double* __restrict__ norms) {
+    const Vox v = vox_of_thread(m);
+    const PxbGeom g = pxb_geom(d.shape);
+    double a0 = 0.0, a1 = 0.0;
+    if (v.ok) pxb_body_primal<T>(algo, d, g, P, xu, z, ktz, x_out, w, norms != nullptr, a0, a1, v.b, v.i0, v.i1, v.i2);
+    if (norms) block_accumulate(a0, a1, v.b, v.ok, norms);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_pds_dual(pxb_grad_desc d, pxb_pds_params P, VoxMap m, const T* __restrict__ w,
+                                                     T* __restrict__ z, double* __restrict__ norms) {
+    const Vox v = vox_of_thread(m);
+    const PxbGeom g = pxb_geom(d.shape);
+    double a0 = 0.0, a1 = 0.0;
+    if (v.ok) pxb_body_dual<T>(d, g, P, w, z, norms != nullptr, a0, a1, v.b, v.i0, v.i1, v.i2);
+    if (norms) block_accumulate(a0, a1, v.b, v.ok, norms);
+}
+
+// (outer, group, inner) kernels: one thread per (outer, inner) pair, `inner` fastest.
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_dual_update(int kind, int64_t outer, int64_t group, int64_t inner, T lam, T sigma, T rho,
+                                                        T* __restrict__ z, const T* __restrict__ t, double* __restrict__ norms) {
+    const int64_t per = (inner + kBlock - 1) / kBlock;  // blocks per outer row
+    const int64_t o = blockIdx.x / per;
+    const int64_t i = (blockIdx.x % per) * kBlock + threadIdx.x;
+    const bool ok = i < inner;
+    double a0 = 0.0, a1 = 0.0;
+    if (ok) pxb_body_dual_update<T>(kind, group, inner, lam, sigma, rho, z, t, norms != nullptr, a0, a1, o, i);
+    if (norms) block_accumulate(a0, a1, o, ok, norms);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_prox_l21(int64_t outer, int64_t group, int64_t inner, T lam, T tau, const T* __restrict__ x,
+                                                     T* __restrict__ out) {
+    const int64_t per = (inner + kBlock - 1) / kBlock;
+    const int64_t o = blockIdx.x / per;
+    const int64_t i = (blockIdx.x % per) * kBlock + threadIdx.x;
+    if (i < inner) pxb_body_prox_l21<T>(group, inner, lam, tau, x, out, o, i);
+}
+
+template <class T, bool PROX>
+__global__ void __launch_bounds__(kBlock) k_lincomb(pxb_prox_spec g, T tau, int64_t n, T* out, T a, const T* x, T b, const T* y,
+                                                    int64_t ny, T c, const T* z, int64_t nz) {
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        T v = pxb_lincomb_at<T>(a, x, b, y, ny, c, z, nz, i);
+        if (PROX) v = pxb_prox_eval<T>(g.kind, T(g.p0), T(g.p1), v, tau);
+        out[i] = v;
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_sqnorms(int64_t rows, int64_t n, const T* __restrict__ x, const T* __restrict__ y,
+                                                    double* __restrict__ out, int64_t per) {
+    const int64_t r = blockIdx.x / per;
+    const int64_t chunk = blockIdx.x % per;
+    double a0 = 0.0, a1 = 0.0;
+    // each block strides over its row: chunk c covers i = c*kBlock + t, + per*kBlock, ...
+    for (int64_t i = chunk * kBlock + threadIdx.x; i < n; i += per * kBlock) {
+        const double xv = (double)x[r * n + i];
+        if (y) {
+            const double yv = (double)y[r * n + i];
+            a0 += (xv - yv) * (xv - yv);
+            a1 += yv * yv;
+        } else {
+            a0 += xv * xv;
+        }
+    }
+    block_accumulate(a0, a1, r, true, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// Argument validation
+// ------------------------------------------------------------------------------------------
+int check_shape(const int64_t shape[3], int64_t batch, const char* who) {
+    if (batch < 1) return fail(PXB_EINVAL, "%s: batch must be >= 1", who);
+    for (int a = 0; a < 3; ++a)
+        if (shape[a] < 1 || shape[a] > 0x3fffffff) return fail(PXB_EINVAL, "%s: shape[%d]=%lld out of range", who, a, (long long)shape[a]);
+    return 0;
+}
+
+// pad-width limits of the reference (pad.py:217-229): a boundary coordinate must fold at most once.
+int check_mode(int mode, int64_t n, int p, int open_lo, int open_hi, const char* who, int axis) {
+    if (mode < PXB_CONSTANT || mode > PXB_EDGE) return fail(PXB_EINVAL, "%s: unknown mode %d on axis %d", who, mode, axis);
+    if (open_lo && open_hi) return 0;
+    int64_t lim = 0x7fffffff;
+    if (mode == PXB_WRAP || mode == PXB_SYMMETRIC) lim = n;
+    if (mode == PXB_REFLECT) lim = n - 1;
+    if (p > lim) return fail(PXB_EINVAL, "%s: pad width %d along axis %d is limited to %lld for this mode", who, p, axis, (long long)lim);
+    return 0;
+}
+
+int check_slab(const pxb_slab& s, int64_t batch, int need, const char* who) {
+    if (s.halo < 0) return fail(PXB_EINVAL, "%s: negative halo", who);
+    if ((s.open_lo || s.open_hi) && s.halo < need) return fail(PXB_EINVAL, "%s: halo=%d planes < stencil reach %d", who, s.halo, need);
+    if (s.halo > 0 && batch != 1) return fail(PXB_EINVAL, "%s: slab halos require batch == 1", who);
+    return 0;
+}
+
+int check_stencil(const pxb_stencil_desc* d, const void* in, const void* out, const char* who) {
+    if (!d || !in || !out) return fail(PXB_EINVAL, "%s: null argument", who);
+    if (in == out) return fail(PXB_EINVAL, "%s: in and out must not alias", who);
+    if (d->dtype != PXB_F32 && d->dtype != PXB_F64) return fail(PXB_EINVAL, "%s: bad dtype %d", who, d->dtype);
+    if (!d->coef) return fail(PXB_EINVAL, "%s: null coefficient pointer", who);
+    if (int e = check_shape(d->shape, d->batch, who)) return e;
+    for (int a = 0; a < 3; ++a) {
+        if (d->ksize[a] < 1) return fail(PXB_EINVAL, "%s: ksize[%d] < 1", who, a);
+        if (d->center[a] < 0 || d->center[a] >= d->ksize[a]) return fail(PXB_EINVAL, "%s: center[%d] outside kernel", who, a);
+        const int p = d->mode[a] == PXB_CONSTANT ? 0 : d->ksize[a] - 1;
+        if (int e = check_mode(d->mode[a], d->shape[a], p, a == 0 ? d->slab.open_lo : 0, a == 0 ? d->slab.open_hi : 0, who, a)) return e;
+    }
+    return check_slab(d->slab, d->batch, d->ksize[0] - 1, who);
+}
+
+int check_grad(const pxb_grad_desc* d, const char* who) {
+    if (!d) return fail(PXB_EINVAL, "%s: null descriptor", who);
+    if (d->dtype != PXB_F32 && d->dtype != PXB_F64) return fail(PXB_EINVAL, "%s: bad dtype %d", who, d->dtype);
+    if (d->ndir < 1 || d->ndir > PXB_MAX_DIRS) return fail(PXB_ENOSUP, "%s: ndir=%d outside [1,%d]", who, d->ndir, PXB_MAX_DIRS);
+    if (int e = check_shape(d->shape, d->batch, who)) return e;
+    int reach0 = 0;
+    for (int k = 0; k < d->ndir; ++k) {
+        const int ax = d->axis[k];
+        if (ax < 0 || ax > 2) return fail(PXB_EINVAL, "%s: axis[%d]=%d", who, k, ax);
+        if (d->ntap[k] < 1 || d->ntap[k] > PXB_MAX_GTAP) return fail(PXB_ENOSUP, "%s: ntap[%d]=%d outside [1,%d]", who, k, d->ntap[k], PXB_MAX_GTAP);
+        if (d->center[k] < 0 || d->center[k] >= d->ntap[k]) return fail(PXB_EINVAL, "%s: center[%d] outside kernel", who, k);
+        const int p = d->mode[ax] == PXB_CONSTANT ? 0 : d->ntap[k] - 1;
+        if (int e = check_mode(d->mode[ax], d->shape[ax], p, ax == 0 ? d->slab.open_lo : 0, ax == 0 ? d->slab.open_hi : 0, who, ax)) return e;
+        if (ax == 0 && d->ntap[k] - 1 > reach0) reach0 = d->ntap[k] - 1;
+    }
+    return check_slab(d->slab, d->batch, reach0, who);
+}
+
+unsigned flat_grid(int64_t n) {
+    int64_t b = (n + kBlock - 1) / kBlock;
+    const int64_t cap = 148LL * 32;  // grid-stride: a few waves of the 148 SMs
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int pxb_abi_version(void) { return PXB_ABI_VERSION; }
+const char* pxb_last_error(void) { return g_err.c_str(); }
+int64_t pxb_launch_count(void) { return g_launches.load(); }
+
+static int stencil_launch(const pxb_stencil_desc* d, const void* in, void* out, void* stream, int adjoint, const char* who) {
+    if (int e = check_stencil(d, in, out, who)) return e;
+    VoxMap m;
+    if (!make_map(d->batch, d->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->dtype == PXB_F32) k_stencil<float><<<m.grid, kBlock, 0, s>>>(*d, m, adjoint, (const float*)in, (float*)out);
+    else k_stencil<double><<<m.grid, kBlock, 0, s>>>(*d, m, adjoint, (const double*)in, (double*)out);
+    PXB_CHECK_LAUNCH(who);
+    return 0;
+}
+
+int pxb_stencil_apply(const pxb_stencil_desc* d, const void* in, void* out, void* stream) {
+    return stencil_launch(d, in, out, stream, 0, "pxb_stencil_apply");
+}
+int pxb_stencil_adjoint(const pxb_stencil_desc* d, const void* in, void* out, void* stream) {
+    return stencil_launch(d, in, out, stream, 1, "pxb_stencil_adjoint");
+}
+
+int pxb_gradient_apply(const pxb_grad_desc* d, const void* x, void* z, void* stream) {
+    const char* who = "pxb_gradient_apply";
+    if (int e = check_grad(d, who)) return e;
+    if (!x || !z || x == z) return fail(PXB_EINVAL, "%s: null or aliased arrays", who);
+    VoxMap m;
+    if (!make_map(d->batch, d->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->dtype == PXB_F32) k_grad_apply<float><<<m.grid, kBlock, 0, s>>>(*d, m, (const float*)x, (float*)z);
+    else k_grad_apply<double><<<m.grid, kBlock, 0, s>>>(*d, m, (const double*)x, (double*)z);
+    PXB_CHECK_LAUNCH(who);
+    return 0;
+}
+
+int pxb_gradient_adjoint(const pxb_grad_desc* d, const void* z, void* x, void* stream) {
+    const char* who = "pxb_gradient_adjoint";
+    if (int e = check_grad(d, who)) return e;
+    if (!x || !z || x == z) return fail(PXB_EINVAL, "%s: null or aliased arrays", who);
+    VoxMap m;
+    if (!make_map(d->batch, d->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->dtype == PXB_F32) k_grad_adjoint<float><<<m.grid, kBlock, 0, s>>>(*d, m, (const float*)z, (float*)x);
+    else k_grad_adjoint<double><<<m.grid, kBlock, 0, s>>>(*d, m, (const double*)z, (double*)x);
+    PXB_CHECK_LAUNCH(who);
+    return 0;
+}
+
+static int lincomb_launch(bool prox, int dtype, const pxb_prox_spec* g, double tau, int64_t n, void* out, double a, const void* x,
+                          double b, const void* y, int64_t ny, double c, const void* z, int64_t nz, void* stream, const char* who) {
+    if (dtype != PXB_F32 && dtype != PXB_F64) return fail(PXB_EINVAL, "%s: bad dtype %d", who, dtype);
+    if (n < 0 || !out || !x) return fail(PXB_EINVAL, "%s: null array or negative size", who);
+    if (ny < 0 || nz < 0) return fail(PXB_EINVAL, "%s: negative broadcast period", who);
+    if (prox && (!g || g->kind < PXB_PROX_NONE || g->kind > PXB_PROX_SQL2)) return fail(PXB_EINVAL, "%s: bad prox spec", who);
+    if (n == 0) return 0;
+    pxb_prox_spec gs = prox ? *g : pxb_prox_spec{PXB_PROX_NONE, 0, 0.0, 0.0};
+    if (ny >= n) ny = 0;
+    if (nz >= n) nz = 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = flat_grid(n);
+    if (dtype == PXB_F32) {
+        if (prox) k_lincomb<float, true><<<grid, kBlock, 0, s>>>(gs, (float)tau, n, (float*)out, (float)a, (const float*)x, (float)b, (const float*)y, ny, (float)c, (const float*)z, nz);
+        else k_lincomb<float, false><<<grid, kBlock, 0, s>>>(gs, (float)tau, n, (float*)out, (float)a, (const float*)x, (float)b, (const float*)y, ny, (float)c, (const float*)z, nz);
+    } else {
+        if (prox) k_lincomb<double, true><<<grid, kBlock, 0, s>>>(gs, tau, n, (double*)out, a, (const double*)x, b, (const double*)y, ny, c, (const double*)z, nz);
+        else k_lincomb<double, false><<<grid, kBlock, 0, s>>>(gs, tau, n, (double*)out, a, (const double*)x, b, (const double*)y, ny, c, (const double*)z, nz);
+    }
+    PXB_CHECK_LAUNCH(who);
+    return 0;
+}
+
+int pxb_prox_lincomb(int dtype, const pxb_prox_spec* g, double tau, int64_t n, void* out, double a, const void* x, double b,
+                     const void* y, int64_t ny, double c, const void* z, int64_t nz, void* stream) {
+    return lincomb_launch(true, dtype, g, tau, n, out, a, x, b, y, ny, c, z, nz, stream, "pxb_prox_lincomb");
+}
+
+int pxb_lincomb(int dtype, int64_t n, void* out, double a, const void* x, double b, const void* y, int64_t ny, double c,
+                const void* z, int64_t nz, void* stream) {
+    return lincomb_launch(false, dtype, nullptr, 0.0, n, out, a, x, b, y, ny, c, z, nz, stream, "pxb_lincomb");
+}
+
+static int ogi_grid(int64_t outer, int64_t inner, unsigned& grid, const char* who) {
+    if (outer < 1 || inner < 1) return fail(PXB_EINVAL, "%s: outer/inner must be >= 1", who);
+    const int64_t nb = outer * ((inner + kBlock - 1) / kBlock);
+    if (nb > 0x7fffffffLL) return fail(PXB_ENOSUP, "%s: grid too large", who);
+    grid = (unsigned)nb;
+    return 0;
+}
+
+int pxb_prox_l21(int dtype, int64_t outer, int64_t group, int64_t inner, double lam, double tau, const void* x, void* out, void* stream) {
+    const char* who = "pxb_prox_l21";
+    if (dtype != PXB_F32 && dtype != PXB_F64) return fail(PXB_EINVAL, "%s: bad dtype %d", who, dtype);
+    if (!x || !out || group < 1) return fail(PXB_EINVAL, "%s: null array or empty group", who);
+    unsigned grid;
+    if (int e = ogi_grid(outer, inner, grid, who)) return e;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == PXB_F32) k_prox_l21<float><<<grid, kBlock, 0, s>>>(outer, group, inner, (float)lam, (float)tau, (const float*)x, (float*)out);
+    else k_prox_l21<double><<<grid, kBlock, 0, s>>>(outer, group, inner, lam, tau, (const double*)x, (double*)out);
+    PXB_CHECK_LAUNCH(who);
+    return 0;
+}
+
+int pxb_dual_update(int dtype, int kind, int64_t outer, int64_t group, int64_t inner, double lam, double sigma, double rho, void* z,
+                    const void* t, double* norms, void* stream) {
+    const char* who = "pxb_dual_update";
+    if (dtype != PXB_F32 && dtype != PXB_F64) return fail(PXB_EINVAL, "%s: bad dtype %d", who, dtype);
+    if (!z || !t || group < 1) return fail(PXB_EINVAL, "%s: null array or empty group", who);
+    if (kind < PXB_DUAL_NONE || kind > PXB_DUAL_L1) return fail(PXB_EINVAL, "%s: bad kind %d", who, kind);
+    if (!(sigma > 0)) return fail(PXB_EINVAL, "%s: sigma must be > 0", who);
+    unsigned grid;
+    if (int e = ogi_grid(outer, inner, grid, who)) return e;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == PXB_F32) k_dual_update<float><<<grid, kBlock, 0, s>>>(kind, outer, group, inner, (float)lam, (float)sigma, (float)rho, (float*)z, (const float*)t, norms);
+    else k_dual_update<double><<<grid, kBlock, 0, s>>>(kind, outer, group, inner, lam, sigma, rho, (double*)z, (const double*)t, norms);
+    PXB_CHECK_LAUNCH(who);
+    return 0;
+}
+
+static int check_pds(const pxb_grad_desc* K, const pxb_pds_params* p, const char* who) {
+    if (int e = check_grad(K, who)) return e;
+    if (!p) return fail(PXB_EINVAL, "%s: null params", who);
+    if (p->g.kind < PXB_PROX_NONE || p->g.kind > PXB_PROX_SQL2) return fail(PXB_EINVAL, "%s: bad g kind", who);
+    if (p->f.kind < PXB_F_NONE || p->f.kind > PXB_F_GRADARR) return fail(PXB_EINVAL, "%s: bad f kind", who);
+    if (p->hkind < PXB_DUAL_NONE || p->hkind > PXB_DUAL_L1) return fail(PXB_EINVAL, "%s: bad h kind", who);
+    if (p->f.kind == PXB_F_SQL2 && p->f.shift && p->f.shift_period < 1) return fail(PXB_EINVAL, "%s: shift_period < 1", who);
+    if (p->f.kind == PXB_F_GRADARR && !p->f.garr) return fail(PXB_EINVAL, "%s: null gradient array", who);
+    return 0;
+}
+
+int pxb_pds_primal(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu, const void* z, const void* ktz, void* x_out,
+                   void* w, double* norms, void* stream) {
+    const char* who = "pxb_pds_primal";
+    if (int e = check_pds(K, p, who)) return e;
+    if (algo != PXB_PD3O && algo != PXB_CV) return fail(PXB_EINVAL, "%s: bad algo %d", who, algo);
+    if (!xu || !w) return fail(PXB_EINVAL, "%s: null xu/w", who);
+    if (algo == PXB_PD3O && !x_out) return fail(PXB_EINVAL, "%s: PD3O needs x_out", who);
+    if (algo == PXB_PD3O && p->f.kind == PXB_F_GRADARR) return fail(PXB_EINVAL, "%s: PD3O evaluates grad f at the new x; PXB_F_GRADARR is CV-only", who);
+    if (p->hkind != PXB_DUAL_NONE && !z && !ktz) return fail(PXB_EINVAL, "%s: need z or ktz", who);
+    VoxMap m;
+    if (!make_map(K->batch, K->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (K->dtype == PXB_F32)
+        k_pds_primal<float><<<m.grid, kBlock, 0, s>>>(algo, *K, *p, m, (float*)xu, (const float*)z, (const float*)ktz, (float*)x_out, (float*)w, norms);
+    else
+        k_pds_primal<double><<<m.grid, kBlock, 0, s>>>(algo, *K, *p, m, (double*)xu, (const double*)z, (const double*)ktz, (double*)x_out, (double*)w, norms);
+    PXB_CHECK_LAUNCH(who);
+    return 0;
+}
+
+int pxb_pds_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w, void* z, double* norms, void* stream) {
+    const char* who = "pxb_pds_dual";
+    if (int e = check_pds(K, p, who)) return e;
+    if (!w || !z) return fail(PXB_EINVAL, "%s: null w/z", who);
+    if (p->hkind == PXB_DUAL_NONE) return fail(PXB_EINVAL, "%s: h is null, nothing to do", who);
+    if (!(p->sigma > 0)) return fail(PXB_EINVAL, "%s: sigma must be > 0", who);
+    VoxMap m;
+    if (!make_map(K->batch, K->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (K->dtype == PXB_F32) k_pds_dual<float><<<m.grid, kBlock, 0, s>>>(*K, *p, m, (const float*)w, (float*)z, norms);
+    else k_pds_dual<double><<<m.grid, kBlock, 0, s>>>(*K, *p, m, (const double*)w, (double*)z, norms);
+    PXB_CHECK_LAUNCH(who);
+    return 0;
+}
+
+int pxb_sqnorms(int dtype, int64_t rows, int64_t n, const void* x, const void* y, double* out, void* stream) {
+    const char* who = "pxb_sqnorms";
+    if (dtype != PXB_F32 && dtype != PXB_F64) return fail(PXB_EINVAL, "%s: bad dtype %d", who, dtype);
+    if (!x || !out || rows < 1 || n < 1) return fail(PXB_EINVAL, "%s: null array or empty size", who);
+    int64_t per = (n + kBlock - 1) / kBlock;
+    const int64_t cap = (148LL * 16 + rows - 1) / rows;  // ~16 blocks per SM overall
+    if (per > cap) per = cap;
+    if (per < 1) per = 1;
+    if (rows * per > 0x7fffffffLL) return fail(PXB_ENOSUP, "%s: grid too large", who);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == PXB_F32) k_sqnorms<float><<<(unsigned)(rows * per), kBlock, 0, s>>>(rows, n, (const float*)x, (const float*)y, out, per);
+    else k_sqnorms<double><<<(unsigned)(rows * per), kBlock, 0, s>>>(rows, n, (const double*)x, (const double*)y, out, per);
+    PXB_CHECK_LAUNCH(who);
+    return 0;
+}
+
+}  // extern "C"

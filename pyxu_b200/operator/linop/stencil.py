@@ -1,0 +1,257 @@
+"""
+Stencil / Correlate / Convolve
+(reference: src/pyxu/operator/linop/stencil/stencil.py -- Stencil:26, Convolve:794;
+low-level JIT stencil: stencil/_stencil.py:62).
+
+Same constructor and semantics as the reference: `S = Trim o S0 o Pad`, i.e. a correlation of the
+boundary-extended input with `kernel` overlaid at `center`, boundary conditions per axis as in
+numpy.pad, and `adjoint` the exact matrix transpose.  The reference materialises the padded array,
+JIT-compiles a Numba stencil and trims; here both directions are single gather passes over the
+un-padded array (boundary handled by index maps, adjoint by pre-image gathering), one pass per
+separable factor.
+"""
+import collections.abc as cabc
+import ctypes as C
+import functools
+import operator as _op
+
+import numpy as np
+
+from ... import _array as A
+from ... import _cabi as K
+from ...abc import operator as pxo
+from ...abc.operator import device_io
+
+_PAD_LIMIT = dict(constant=np.inf, wrap=lambda n: n, reflect=lambda n: n - 1, symmetric=lambda n: n, edge=np.inf)
+
+
+def canonical_mode(mode, ndim):
+    """tuple[str] of length ndim (reference: pad.py:190-205)."""
+    if isinstance(mode, str):
+        mode = (mode,) * ndim
+    elif isinstance(mode, cabc.Sequence):
+        assert len(mode) == ndim, "arg_shape/mode are length-mismatched."
+        mode = tuple(mode)
+    else:
+        raise ValueError(f"Unkwown mode encountered: {mode}.")
+    mode = tuple(m.strip().lower() for m in mode)
+    assert set(mode) <= set(K.MODES), "Unknown mode(s) encountered."
+    return mode
+
+
+def _as_host_kernel(k):
+    """Kernel coefficients are tiny: keep a host (NumPy) copy whatever the input array type."""
+    if isinstance(k, np.ndarray):
+        return k
+    if hasattr(k, "detach"):
+        return k.detach().cpu().numpy()
+    if hasattr(k, "__dlpack__"):
+        import torch
+
+        return torch.from_dlpack(k).cpu().numpy()
+    return np.asarray(k)
+
+
+class Stencil(pxo.SquareOp):
+    KernelSpec = object
+    MAX_NDIM = 3
+
+    def __init__(self, arg_shape, kernel, center, mode="constant", enable_warnings=True):
+        if not isinstance(arg_shape, cabc.Sequence):
+            arg_shape = (arg_shape,)
+        arg_shape = tuple(int(n) for n in arg_shape)
+        D = len(arg_shape)
+        assert len(center) == D
+        if D > self.MAX_NDIM:
+            raise NotImplementedError(f"Stencil: rank-{D} arrays; kernels are compiled for rank <= {self.MAX_NDIM}")
+        dim = int(np.prod(arg_shape))
+        super().__init__((dim, dim))
+
+        # canonical representation (reference: stencil.py:497-538)
+        sep = not (hasattr(kernel, "ndim") and not isinstance(kernel, (list, tuple)))
+        if not sep:
+            k = _as_host_kernel(kernel)
+            assert k.ndim == D
+            kernels = [k]
+            centers = [np.array(center, dtype=int)]
+        else:
+            assert len(kernel) == D
+            kernels, centers = [], []
+            for i in range(D):
+                sh = [1] * D
+                sh[i] = -1
+                kernels.append(_as_host_kernel(kernel[i]).reshape(sh))
+                c = np.zeros(D, dtype=int)
+                c[i] = center[i]
+                centers.append(c)
+        dt = kernels[0].dtype
+        if dt not in (np.float32, np.float64):
+            dt = np.dtype(np.float64)  # reference coerces to the current precision (default double)
+        self._dtype = np.dtype(dt)
+        self._kernels = [np.ascontiguousarray(k, dtype=self._dtype) for k in kernels]
+        self._centers = centers
+        for k, c in zip(self._kernels, self._centers):
+            assert np.all(0 <= c) and np.all(c < k.shape)  # reference: _stencil.py:123-125
+        self._separable = sep
+        self._arg_shape = arg_shape
+        self._mode = canonical_mode(mode, D)
+        self._enable_warnings = bool(enable_warnings)
+        self._flip = False  # Convolve swaps forward/backward
+
+        # pad widths the reference would use; they bound what the boundary maps must support
+        # (reference: stencil.py:540-561, pad.py:217-229)
+        self._pad_width = []
+        for i in range(D):
+            if not sep:
+                c, n = int(self._centers[0][i]), self._kernels[0].shape[i]
+            else:
+                c, n = int(self._centers[i][i]), self._kernels[i].size
+            p = max(c, n - c - 1) if self._mode[i] == "constant" else n - 1
+            lim = _PAD_LIMIT[self._mode[i]]
+            lim = lim if not callable(lim) else lim(arg_shape[i])
+            assert p <= lim, f"pad_width along dim-{i} is limited to {lim}."
+            self._pad_width.append((p, p))
+        self._pad_width = tuple(self._pad_width)
+
+        self._dev_coef = {}  # (dtype, device, pass, flipped) -> device tensor
+        self.lipschitz = self.estimate_lipschitz(__rule=True)
+
+    # -- descriptors ---------------------------------------------------------------------
+    def _passes(self, adjoint):
+        """Sequence of (kernel ndarray (k0,k1,k2), center (3,)) dense passes, in application order."""
+        use_flipped = self._flip  # Convolve: forward correlates with the flipped kernel
+        out = []
+        D = len(self._arg_shape)
+        for k, c in zip(self._kernels, self._centers):
+            if use_flipped:
+                k = np.flip(k)
+                c = np.array(k.shape) - c - 1
+            k3 = np.ascontiguousarray(k.reshape((1,) * (3 - D) + k.shape))
+            c3 = np.concatenate([np.zeros(3 - D, dtype=int), c])
+            out.append((k3, c3))
+        # 1-tap unit factors (what PartialDerivative puts on the non-differentiated axes, diff.py:715) are identities
+        kept = [(k3, c3) for (k3, c3) in out if not (k3.size == 1 and k3.reshape(-1)[0] == 1)]
+        out = kept if kept else out[:1]
+        # A = P_last ... P_first  =>  A^T = P_first^T ... P_last^T
+        return out[::-1] if adjoint else out
+
+    def _desc(self, k3, c3, batch, dtype_code, coef_ptr, slab=None):
+        D = len(self._arg_shape)
+        d = K.StencilDesc()
+        d.dtype = dtype_code
+        d.batch = batch
+        shape3 = (1,) * (3 - D) + self._arg_shape
+        mode3 = ("constant",) * (3 - D) + self._mode
+        for a in range(3):
+            d.shape[a] = shape3[a]
+            d.ksize[a] = k3.shape[a]
+            d.center[a] = int(c3[a])
+            d.mode[a] = K.MODES[mode3[a]]
+        d.slab = slab if slab is not None else K.Slab(0, 0, 0, 0)
+        d.coef = coef_ptr
+        return d
+
+    def _coef_on_device(self, idx, k3, like):
+        key = (like.dtype, like.device, idx, self._flip)
+        t = self._dev_coef.get(key)
+        if t is None:
+            t, _ = A.asdevice(k3.reshape(-1), dtype=like.dtype)
+            self._dev_coef[key] = t
+        return t
+
+    def _run(self, arr, adjoint):
+        if arr.shape[-1] != self.dim:
+            raise ValueError(f"{self}: expected (..., {self.dim}) input, got {tuple(arr.shape)}")
+        if A.np_dtype(arr.dtype) != self._dtype and self._enable_warnings:
+            import warnings
+
+            from ...info import PrecisionWarning
+
+            warnings.warn("Computation may not be performed at the requested precision.", PrecisionWarning)
+        batch = max(1, arr.numel() // self.dim)
+        fn = K.lib().pxb_stencil_adjoint if adjoint else K.lib().pxb_stencil_apply
+        cur = arr
+        passes = self._passes(adjoint)
+        for n, (k3, c3) in enumerate(passes):
+            idx = (len(passes) - 1 - n) if adjoint else n
+            coef = self._coef_on_device(idx, k3, arr)
+            d = self._desc(k3, c3, batch, A.dcode(arr), coef.data_ptr())
+            out = A.empty_like(arr)
+            K.check(fn(C.byref(d), A.ptr(cur), A.ptr(out), A.stream()), "Stencil")
+            cur = out
+        return cur
+
+    # -- LinOp interface -------------------------------------------------------------------
+    @device_io
+    def apply(self, arr):
+        return self._run(arr, adjoint=False)
+
+    @device_io
+    def adjoint(self, arr):
+        return self._run(arr, adjoint=True)
+
+    def estimate_lipschitz(self, **kwargs):
+        if "__rule" in kwargs:
+            # Young's inequality bound ||h||_1 times the Pad bound (reference: stencil.py:639-656, pad.py:377-391)
+            full = functools.reduce(_op.mul, self._kernels, 1)
+            L_st = float(np.abs(np.asarray(full, dtype=np.float64)).sum())
+            L_pad = 1.0
+            for n, m, (l, r) in zip(self._arg_shape, self._mode, self._pad_width):
+                if m == "constant":
+                    L = 1.0
+                elif m in ("wrap", "symmetric"):
+                    L = np.sqrt(1 + np.ceil((l + r) / n))
+                elif m == "reflect":
+                    L = np.sqrt(1 + np.ceil((l + r) / (n - 2)))
+                else:
+                    L = np.sqrt(1 + max(l, r))
+                L_pad *= L
+            return float(L_st * L_pad)
+        kwargs.setdefault("dtype", A.torch_dtype(self._dtype))
+        return super().estimate_lipschitz(**kwargs)
+
+    def asarray(self, **kwargs):
+        out = super().asarray(dtype=self._dtype)
+        return out.astype(kwargs.get("dtype", np.float64))
+
+    def trace(self, **kwargs):
+        if all(m == "constant" for m in self._mode):
+            tr = functools.reduce(_op.mul, [k[tuple(c)] for k, c in zip(self._kernels, self._centers)], 1.0)
+            return float(tr * self.dim)
+        return float(np.trace(self.asarray()))
+
+    # -- introspection (reference: stencil.py:691-788) ----------------------------------------
+    @property
+    def kernel(self):
+        return self._kernels[0] if not self._separable else list(self._kernels)
+
+    @property
+    def center(self):
+        if not self._separable:
+            return tuple(int(c) for c in self._centers[0])
+        return tuple(int(c[d]) for d, c in enumerate(self._centers))
+
+    @property
+    def relative_indices(self):
+        if not self._separable:
+            return [np.arange(s) - c for c, s in zip(self.center, self.kernel.shape)]
+        return [np.arange(k.size) - c for c, k in zip(self.center, self.kernel)]
+
+    def visualize(self):
+        kernel = functools.reduce(_op.mul, self._kernels, 1).astype(str)
+        kernel[self.center] = "(" + kernel[self.center] + ")"
+        return np.array2string(kernel).replace("'", "")
+
+
+Correlate = Stencil
+
+
+class Convolve(Stencil):
+    """Convolution = correlation with flipped kernel and mirrored center (reference: stencil.py:794-887)."""
+
+    def __init__(self, arg_shape, kernel, center, mode="constant", enable_warnings=True):
+        super().__init__(arg_shape=arg_shape, kernel=kernel, center=center, mode=mode, enable_warnings=enable_warnings)
+        self._flip = True
+
+
+__all__ = ["Stencil", "Correlate", "Convolve"]

@@ -1,0 +1,466 @@
+"""
+Primal-dual splitting solvers
+(reference: src/pyxu/opt/solver/pds.py -- _PrimalDualSplitting:26, CondatVu:210, PD3O:523,
+ChambollePock:867, LorisVerhoeven:970, DavisYin:1115, ForwardBackward:1698, ProximalPoint:1788).
+
+Problem:  min_x f(x) + g(x) + h(Kx).  Constructor / fit() arguments, automatic step-size selection,
+default stopping criterion and logged variables follow the reference.  What differs is how an
+iteration executes: `m_step()` asks a planner (``_Plan``) which of three execution paths applies:
+
+* ``fused``  -- h o K is a (scaled) L21 / L1 norm of a Gradient stack, g has a pointwise prox and f is
+                 null / a shifted squared-l2 data term (or, for CondatVu, anything differentiable):
+                 one iteration = pxb_pds_primal + pxb_pds_dual, two passes over the volume, with the
+                 RelError norms accumulated in the same passes.
+* ``semi``   -- same h o K, but PD3O with a non-local f (e.g. a blur in the data term): K^T z and the
+                 prox are separate passes, the dual half-step stays fused.
+* ``generic``-- any other composition: the reference's formulas evaluated through the operators'
+                 own methods, glued by fused elementwise kernels (pxb_lincomb / pxb_prox_lincomb /
+                 pxb_dual_update).
+"""
+import ctypes as C
+import math
+import warnings
+
+import numpy as np
+
+from ... import _array as A
+from ... import _cabi as K
+from ... import _kernels as kr
+from ...abc import operator as pxo
+from ...abc.solver import Solver
+from ...operator.linop.base import IdentityOp, NullFunc, NullOp
+from .. import stop as pxs
+
+__all__ = ["CondatVu", "CV", "PD3O", "ChambollePock", "CP", "LorisVerhoeven", "LV", "DavisYin", "DY",
+           "ForwardBackward", "FB", "ProximalPoint", "PP"]
+
+
+def _is_null(op):
+    return getattr(op, "_name", "") == "NullFunc"
+
+
+class _Plan:
+    """Decides how one iteration is executed and owns the descriptors / work buffers."""
+
+    def __init__(self, solver, algo, x0):
+        f, g, h, Kop = solver._f, solver._g, solver._h, solver._K
+        self.algo = algo
+        self.kind = "generic"
+        self.batch = max(1, x0.numel() // x0.shape[-1])
+        self.gspec = g._prox_spec()
+        self.hspec = None if _is_null(h) else h._dual_spec()
+        self.h_null = _is_null(h)
+        self.fkind, self.falpha, self.fshift = None, 0.0, None
+        if _is_null(f):
+            self.fkind = K.F_NONE
+        else:
+            s = f._sql2_spec()
+            if s is not None:
+                self.fkind, self.falpha = K.F_SQL2, float(s[0])
+                if s[1] is not None:
+                    if isinstance(s[1], float):
+                        import torch
+
+                        self.fshift = torch.full((1,), s[1], dtype=x0.dtype, device=x0.device)
+                    else:
+                        self.fshift, _ = A.asdevice(s[1], dtype=x0.dtype)
+                        self.fshift = self.fshift.reshape(-1)
+                        if x0.numel() % self.fshift.numel() != 0:
+                            self.fkind = None
+
+        from ...operator.linop.diff import _DiffStack
+
+        tv = isinstance(Kop, _DiffStack) and Kop._fusable and self.gspec is not None
+        if tv and not self.h_null:
+            hs = self.hspec
+            N, nd = Kop.dim, len(Kop._dirs)
+            ok_l21 = hs is not None and hs[0] == K.DUAL_L21 and tuple(hs[2]) == (1, nd, N)
+            ok_l1 = hs is not None and hs[0] == K.DUAL_L1 and h.dim == nd * N
+            tv = ok_l21 or ok_l1
+        elif self.h_null:
+            tv = False
+        if tv:
+            if self.fkind is not None:
+                self.kind = "fused"
+            elif algo == K.ALGO_CV:
+                self.kind = "fused"
+                self.fkind = K.F_GRADARR
+            else:
+                self.kind = "semi"
+        self.K = Kop
+        if self.kind != "generic":
+            self.gdesc = Kop._desc(self.batch, A.dcode(x0))
+            self.w = A.empty_like(x0)
+
+    def params(self, mst, garr=None):
+        p = K.PdsParams()
+        p.tau, p.sigma, p.rho = float(mst["tau"]), float(mst["sigma"]), float(mst["rho"])
+        p.g = K.ProxSpec(int(self.gspec[0]), 0, float(self.gspec[1]), float(self.gspec[2]))
+        fk = self.fkind if self.fkind is not None else K.F_NONE
+        f = K.FTerm()
+        f.kind, f.alpha = fk, self.falpha
+        if fk == K.F_SQL2 and self.fshift is not None:
+            f.shift, f.shift_period = self.fshift.data_ptr(), self.fshift.numel()
+        if fk == K.F_GRADARR:
+            f.garr = garr.data_ptr()
+        p.f = f
+        p.hkind, p.lam = int(self.hspec[0]), float(self.hspec[1])
+        return p
+
+
+class _PrimalDualSplitting(Solver):
+    _ALGO = None
+
+    def __init__(self, f=None, g=None, h=None, K=None, beta=None, **kwargs):
+        kwargs.update(log_var=kwargs.get("log_var", ("x", "z")))
+        super().__init__(**kwargs)
+        if (f is None) and (g is None) and (h is None):
+            raise ValueError("Cannot minimize always-0 functional. At least one of Parameter[f, g, h] must be specified.")
+        primal_dim = f.dim if f is not None else (g.dim if g is not None else h.dim)
+        if h is not None:
+            dual_dim = h.dim
+        elif K is not None:
+            dual_dim = K.shape[0]
+        else:
+            dual_dim = primal_dim
+        self._f = NullFunc(dim=primal_dim) if (f is None) else f
+        self._g = NullFunc(dim=primal_dim) if (g is None) else g
+        self._h = NullFunc(dim=dual_dim) if (h is None) else h
+        self._beta = self._set_beta(beta)
+        if h is not None:
+            self._K = IdentityOp(dim=h.dim) if (K is None) else K
+        else:
+            if K is None:
+                K_dim = f.dim if f is not None else g.dim
+                self._K = NullOp(shape=(K_dim, K_dim))
+            else:
+                raise ValueError("Optional argument ``h`` mut be specified if ``K`` is not None.")
+        self._plan = None
+
+    # ---------------------------------------------------------------------------------------
+    def m_init(self, x0, z0=None, tau=None, sigma=None, rho=None, tuning_strategy=1):
+        mst = self._mstate
+        x0d, origin = A.asdevice(x0)
+        self._astate["origin"] = origin
+        mst["x"] = x0d.clone()  # never write into the caller's buffer
+        if z0 is None:
+            mst["z"] = self._K(mst["x"])
+            if mst["z"].data_ptr() == mst["x"].data_ptr():
+                mst["z"] = mst["z"].clone()
+        else:
+            z0d, _ = A.asdevice(z0, dtype=x0d.dtype)
+            mst["z"] = z0d.clone()
+        self._tuning_strategy = int(tuning_strategy)
+        gamma = self._set_gamma(tuning_strategy)
+        mst["tau"], mst["sigma"], delta = self._set_step_sizes(tau, sigma, gamma)
+        mst["rho"] = self._set_momentum_term(rho, delta)
+        self._plan = _Plan(self, self._ALGO, mst["x"])
+        self._setup_fused_norms()
+
+    def _setup_fused_norms(self):
+        """If the stopping criterion is RelError on x / z evaluated every iteration, let the update kernels
+        accumulate its norms (no extra pass, no x_prev copy)."""
+        import torch
+
+        mst, ast = self._mstate, self._astate
+        want = ast["stop_crit"]._fused_vars() if ast["stop_crit"] is not None else frozenset()
+        self._nx = self._nz = None
+        if self._plan.kind == "generic" or ast["stop_rate"] != 1 or not want <= {"x", "z"}:
+            return
+        if self._plan.kind == "semi":
+            want = want - {"x"}
+        rows = self._plan.batch
+        fused = {}
+        if "x" in want:
+            self._nx = torch.zeros((rows, 2), dtype=torch.float64, device=mst["x"].device)
+            fused["x"] = self._nx
+        if "z" in want and not self._plan.h_null:
+            self._nz = torch.zeros((rows, 2), dtype=torch.float64, device=mst["x"].device)
+            fused["z"] = self._nz
+        if fused:
+            mst["_fused_norms"] = fused
+
+    def default_stop_crit(self):
+        stop_crit_x = pxs.RelError(eps=1e-4, var="x", f=None, norm=2, satisfy_all=True)
+        stop_crit_z = pxs.RelError(eps=1e-4, var="z", f=None, norm=2, satisfy_all=True)
+        return stop_crit_x & stop_crit_z if self._h._name != "NullFunc" else stop_crit_x
+
+    def solution(self, which="primal"):
+        data, _ = self.stats()
+        if which == "primal":
+            assert "x" in data.keys(), "Primal variable x was not logged (declare it in log_var to log it)."
+        elif which == "dual":
+            assert "z" in data.keys(), "Dual variable z was not logged (declare it in log_var to log it)."
+        else:
+            raise ValueError(f"Parameter which must be one of ['primal', 'dual'] got: {which}.")
+        return data.get("x") if which == "primal" else data.get("z")
+
+    def objective_func(self):
+        x = self._mstate["x"]
+        out = self._f(x) + self._g(x)
+        if not _is_null(self._h):
+            out = out + self._h(self._K(x))
+        return out
+
+    def _set_beta(self, beta):
+        if beta is None:
+            dl = self._f.diff_lipschitz
+            if math.isfinite(dl):
+                return float(dl)
+            raise ValueError("beta: automatic inference not supported for operators with unbounded Lipschitz gradients.")
+        return float(beta)
+
+    def _set_gamma(self, tuning_strategy):
+        return float(self._beta) if tuning_strategy != 2 else float(self._beta / 1.9)
+
+    def _set_step_sizes(self, tau, sigma, gamma):
+        raise NotImplementedError
+
+    def _set_momentum_term(self, rho, delta):
+        if rho is None:
+            rho = 1.0 if self._tuning_strategy != 3 else delta - 0.1
+        else:
+            assert rho <= delta, f"Parameter rho must be smaller than delta: {rho} > {delta}."
+        return float(rho)
+
+    def _K_lipschitz(self):
+        if math.isfinite(self._K.lipschitz):
+            return self._K.lipschitz
+        raise ValueError("Please compute the Lipschitz constant of the linear operator K by calling its method 'estimate_lipschitz()'")
+
+    def _check_K_linear(self):
+        if not isinstance(self._K, pxo.LinOp):
+            raise ValueError("Automatic selection of parameters is only supported in the case in which K is a linear operator. "
+                             f"Got operator of type {self._K.__class__}.")
+
+    # -- shared kernels ---------------------------------------------------------------------
+    def _dual_fused(self, w):
+        mst, pl = self._mstate, self._plan
+        if self._nz is not None:
+            self._nz.zero_()
+        p = pl.params(mst, garr=w)  # garr unused by the dual kernel
+        rc = K.lib().pxb_pds_dual(C.byref(pl.gdesc), C.byref(p), A.ptr(w), A.ptr(mst["z"]), A.ptr(self._nz), A.stream())
+        K.check(rc, "pxb_pds_dual")
+
+    def _dual_generic(self, w):
+        """z <- (1-rho) z + rho prox_{sigma h*}(z + sigma K w) through operator methods."""
+        mst, pl = self._mstate, self._plan
+        t = self._K(w)
+        hs = pl.hspec
+        if hs is not None and hs[0] == K.DUAL_L21:
+            outer, group, inner = hs[2]
+            kr.dual_update(K.DUAL_L21, mst["z"], t, pl.batch * outer, group, inner, hs[1], mst["sigma"], mst["rho"])
+        elif hs is not None and hs[0] == K.DUAL_L1:
+            kr.dual_update(K.DUAL_L1, mst["z"], t, pl.batch, 1, self._h.dim, hs[1], mst["sigma"], mst["rho"])
+        else:
+            p = kr.lincomb(1.0, mst["z"], mst["sigma"], t, out=t)
+            z_temp = self._h.fenchel_prox(p, sigma=mst["sigma"])
+            kr.lincomb(1.0 - mst["rho"], mst["z"], mst["rho"], z_temp, out=mst["z"])
+
+    def _prox_g(self, a, x, b=0.0, y=None, c=0.0, z=None, out=None):
+        """prox_{tau g}(a x + b y + c z): one pass when g is pointwise, else lincomb + g.prox."""
+        mst, pl = self._mstate, self._plan
+        if pl.gspec is not None:
+            return kr.prox_lincomb(pl.gspec, mst["tau"], a, x, b, y, c, z, out=out)
+        return self._g.prox(kr.lincomb(a, x, b, y, c, z), tau=mst["tau"])
+
+
+_PDS = _PrimalDualSplitting
+
+
+class CondatVu(_PrimalDualSplitting):
+    r"""Condat-Vu primal-dual splitting (reference: pds.py:210-517, iteration pds.py:429-442)."""
+
+    _ALGO = K.ALGO_CV
+
+    def m_step(self):
+        mst, pl = self._mstate, self._plan
+        if pl.kind == "fused":
+            garr = self._f.grad(mst["x"]) if pl.fkind == K.F_GRADARR else None
+            if self._nx is not None:
+                self._nx.zero_()
+            p = pl.params(mst, garr=garr)
+            rc = K.lib().pxb_pds_primal(K.ALGO_CV, C.byref(pl.gdesc), C.byref(p), A.ptr(mst["x"]), A.ptr(mst["z"]), None, None,
+                                        A.ptr(pl.w), A.ptr(self._nx), A.stream())
+            K.check(rc, "pxb_pds_primal")
+            self._dual_fused(pl.w)
+            return
+        # generic: x_temp = prox_g(x - tau grad f(x) - tau K^T z)
+        x = mst["x"]
+        gf = None if _is_null(self._f) else self._f.grad(x)
+        ktz = None if pl.h_null else self._K.jacobian(x).adjoint(mst["z"])
+        x_temp = self._prox_g(1.0, x, -mst["tau"], gf, -mst["tau"], ktz)
+        if not pl.h_null:
+            u = kr.lincomb(2.0, x_temp, -1.0, x)
+            self._dual_generic(u)
+        mst["x"] = kr.lincomb(mst["rho"], x_temp, 1.0 - mst["rho"], x, out=x_temp)
+
+    def _set_step_sizes(self, tau, sigma, gamma):
+        self._check_K_linear()
+        tau = None if tau == 0 else tau
+        sigma = None if sigma == 0 else sigma
+        h_null = _is_null(self._h)
+        if (tau is not None) and (sigma is None):
+            assert tau > 0, f"Parameter tau must be positive, got {tau}."
+            if h_null:
+                assert tau <= 1 / gamma, f"Parameter tau must be smaller than 1/gamma: {tau} > {1 / gamma}."
+                sigma = 0
+            else:
+                sigma = ((1 / tau) - gamma) * (1 / self._K_lipschitz() ** 2)
+        elif (tau is None) and (sigma is not None):
+            assert sigma > 0
+            tau = 1 / gamma if h_null else 1 / (gamma + (sigma * self._K_lipschitz() ** 2))
+        elif (tau is None) and (sigma is None):
+            if self._beta > 0:
+                if h_null:
+                    tau, sigma = 1 / gamma, 0
+                else:
+                    L = self._K_lipschitz()
+                    tau = sigma = (1 / L**2) * ((-gamma / 2) + math.sqrt((gamma**2 / 4) + L**2))
+            else:
+                if h_null:
+                    tau, sigma = 1, 0
+                else:
+                    tau = sigma = 1 / self._K_lipschitz()
+        delta = 2 if (self._beta == 0 or (isinstance(self._f, pxo.QuadraticFunc) and gamma <= self._beta)) else 2 - self._beta / (2 * gamma)
+        return float(tau), float(sigma), float(delta)
+
+
+CV = CondatVu
+
+
+class PD3O(_PrimalDualSplitting):
+    r"""Primal-dual three-operator splitting (reference: pds.py:523-864, iteration pds.py:747-761)."""
+
+    _ALGO = K.ALGO_PD3O
+
+    def m_init(self, x0, z0=None, tau=None, sigma=None, rho=None, tuning_strategy=1):
+        super().m_init(x0=x0, z0=z0, tau=tau, sigma=sigma, rho=rho, tuning_strategy=tuning_strategy)
+        mst = self._mstate
+        # if x0 == u0 the first step would not move x when g = h = 0 (reference: pds.py:741-745)
+        if _is_null(self._g) and _is_null(self._h):
+            mst["u"] = kr.lincomb(1.01, mst["x"])
+        else:
+            mst["u"] = mst["x"].clone()
+
+    def m_step(self):
+        mst, pl = self._mstate, self._plan
+        tau, rho = mst["tau"], mst["rho"]
+        if pl.kind == "fused":
+            if self._nx is not None:
+                self._nx.zero_()
+            p = pl.params(mst)
+            rc = K.lib().pxb_pds_primal(K.ALGO_PD3O, C.byref(pl.gdesc), C.byref(p), A.ptr(mst["u"]), A.ptr(mst["z"]), None,
+                                        A.ptr(mst["x"]), A.ptr(pl.w), A.ptr(self._nx), A.stream())
+            K.check(rc, "pxb_pds_primal")
+            self._dual_fused(pl.w)
+            return
+        u = mst["u"]
+        ktz = None if pl.h_null else self._K.jacobian(u).adjoint(mst["z"])
+        x = self._prox_g(1.0, u, -tau, ktz, out=mst["x"] if pl.gspec is not None else None)
+        mst["x"] = x
+        gf = None if _is_null(self._f) else self._f.grad(x)
+        if not pl.h_null:
+            # w = x + u_temp - u = 2x - tau grad f(x) - u
+            w = kr.lincomb(2.0, x, -tau, gf, -1.0, u, out=getattr(pl, "w", None))
+            if pl.kind == "semi":
+                self._dual_fused(w)
+            else:
+                self._dual_generic(w)
+        # u <- (1-rho) u + rho (x - tau grad f(x))
+        kr.lincomb(1.0 - rho, u, rho, x, -rho * tau, gf, out=u)
+
+    def _set_step_sizes(self, tau, sigma, gamma):
+        self._check_K_linear()
+        tau = None if tau == 0 else tau
+        sigma = None if sigma == 0 else sigma
+        h_null = _is_null(self._h)
+        if (tau is not None) and (sigma is None):
+            assert 0 < tau <= 1 / gamma, "tau must be positive and smaller than 1/gamma."
+            sigma = 0 if h_null else 1 / (tau * self._K_lipschitz() ** 2)
+        elif (tau is None) and (sigma is not None):
+            assert sigma > 0, f"sigma must be positive, got {sigma}."
+            tau = 1 / gamma if h_null else min(1 / (sigma * self._K_lipschitz() ** 2), 1 / gamma)
+        elif (tau is None) and (sigma is None):
+            if self._beta > 0:
+                if h_null:
+                    tau, sigma = 1 / gamma, 0
+                else:
+                    self._K_lipschitz()
+                    tau, sigma = self._optimize_step_sizes(gamma)
+            else:
+                if h_null:
+                    tau, sigma = 1, 0
+                else:
+                    tau = sigma = 1 / self._K_lipschitz()
+        delta = 2 if self._beta == 0 else 2 - self._beta * tau / 2
+        return float(tau), float(sigma), float(delta)
+
+    def _optimize_step_sizes(self, gamma):
+        """Same linear program as the reference (pds.py:831-864), solved with scipy's HiGHS."""
+        from scipy.optimize import linprog
+
+        c = np.array([-1, -1])
+        A_ub = np.array([[1, 1], [1, 0]])
+        b_ub = np.array([np.log(0.99) - 2 * np.log(self._K.lipschitz), np.log(1 / gamma)])
+        A_eq = np.array([[1, -1]])
+        b_eq = np.array([0])
+        result = linprog(c=c, A_ub=A_ub, b_ub=b_ub, A_eq=A_eq, b_eq=b_eq, bounds=(None, None))
+        if not result.success:
+            warnings.warn("Automatic parameter selection has not converged.", UserWarning)
+        return np.exp(result.x)
+
+
+def ChambollePock(g=None, h=None, K=None, base=CondatVu, **kwargs):
+    """Chambolle-Pock / PDHG: f = 0 in CondatVu or PD3O (reference: pds.py:867-964)."""
+    kwargs.update(log_var=kwargs.get("log_var", ("x", "z")))
+    obj = base(f=None, g=g, h=h, K=K, beta=0, **kwargs)
+    obj.__repr__ = lambda _: "ChambollePock"
+    return obj
+
+
+CP = ChambollePock
+
+
+class LorisVerhoeven(PD3O):
+    """min f(x) + h(Kx): PD3O with g = 0 (reference: pds.py:970-1109)."""
+
+    def __init__(self, f=None, h=None, K=None, beta=None, **kwargs):
+        kwargs.update(log_var=kwargs.get("log_var", ("x", "z")))
+        super().__init__(f=f, g=None, h=h, K=K, beta=beta, **kwargs)
+
+
+LV = LorisVerhoeven
+
+
+class DavisYin(PD3O):
+    """min f(x) + g(x) + h(x): PD3O with K = Id (reference: pds.py:1115-1237)."""
+
+    def __init__(self, f, g=None, h=None, beta=None, **kwargs):
+        kwargs.update(log_var=kwargs.get("log_var", ("x", "z")))
+        super().__init__(f=f, g=g, h=h, K=None, beta=beta, **kwargs)
+
+
+DY = DavisYin
+
+
+def ForwardBackward(f=None, g=None, beta=None, **kwargs):
+    """Forward-backward splitting: CondatVu with h = 0 (reference: pds.py:1698-1782)."""
+    kwargs.update(log_var=kwargs.get("log_var", ("x",)))
+    obj = CondatVu(f=f, g=g, h=None, K=None, beta=beta, **kwargs)
+    obj.__repr__ = lambda _: "ForwardBackward"
+    return obj
+
+
+FB = ForwardBackward
+
+
+def ProximalPoint(g=None, base=CondatVu, **kwargs):
+    """Proximal-point method: f = h = 0 (reference: pds.py:1788-1862)."""
+    kwargs.update(log_var=kwargs.get("log_var", ("x",)))
+    obj = base(f=None, g=g, h=None, K=None, beta=None if False else 0, **kwargs)
+    obj.__repr__ = lambda _: "ProximalPoint"
+    return obj
+
+
+PP = ProximalPoint

@@ -1,0 +1,108 @@
+// tests/emu/pxb_emu.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the per-voxel bodies of pyxu_b200/csrc/pxb_core.cuh (the exact functions the CUDA
+// kernels call) for the host and drives them with plain loops, so that index handling (boundary
+// maps, adjoint pre-images, slab halos, fused half-steps) can be checked against the oracle on the
+// GPU-less build container.  Never loaded by the pyxu_b200 package; pointers here are HOST pointers.
+#include <cstdint>
+#include <cstring>
+
+#include "../../pyxu_b200/csrc/pxb_core.cuh"
+
+#define FOR_VOX(batch, g)                              \
+    for (int64_t b = 0; b < (batch); ++b)              \
+        for (int i0 = 0; i0 < (g).n0; ++i0)            \
+            for (int i1 = 0; i1 < (g).n1; ++i1)        \
+                for (int i2 = 0; i2 < (g).n2; ++i2)
+
+template <class T>
+static void t_stencil(const pxb_stencil_desc* d, bool adj, const void* in, void* out) {
+    const PxbGeom g = pxb_geom(d->shape);
+    FOR_VOX(d->batch, g) pxb_body_stencil<T>(*d, g, adj, (const T*)in, (T*)out, b, i0, i1, i2);
+}
+template <class T>
+static void t_grad(const pxb_grad_desc* d, bool adj, const void* in, void* out) {
+    const PxbGeom g = pxb_geom(d->shape);
+    FOR_VOX(d->batch, g) {
+        if (adj) pxb_body_grad_adjoint<T>(*d, g, (const T*)in, (T*)out, b, i0, i1, i2);
+        else pxb_body_grad_apply<T>(*d, g, (const T*)in, (T*)out, b, i0, i1, i2);
+    }
+}
+template <class T>
+static void t_primal(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu, const void* z, const void* ktz, void* x_out,
+                     void* w, double* norms) {
+    const PxbGeom g = pxb_geom(K->shape);
+    // kernels read z / x_out(old) / xu(old) of *other or same* voxels while writing xu, x_out, w: only z has
+    // neighbour reads and z is never written here, so a sequential sweep is equivalent to the parallel one.
+    FOR_VOX(K->batch, g) {
+        double a0 = 0, a1 = 0;
+        pxb_body_primal<T>(algo, *K, g, *p, (T*)xu, (const T*)z, (const T*)ktz, (T*)x_out, (T*)w, norms != nullptr, a0, a1, b, i0, i1, i2);
+        if (norms) { norms[2 * b] += a0; norms[2 * b + 1] += a1; }
+    }
+}
+template <class T>
+static void t_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w, void* z, double* norms) {
+    const PxbGeom g = pxb_geom(K->shape);
+    FOR_VOX(K->batch, g) {
+        double a0 = 0, a1 = 0;
+        pxb_body_dual<T>(*K, g, *p, (const T*)w, (T*)z, norms != nullptr, a0, a1, b, i0, i1, i2);
+        if (norms) { norms[2 * b] += a0; norms[2 * b + 1] += a1; }
+    }
+}
+
+extern "C" {
+int emu_stencil(const pxb_stencil_desc* d, int adjoint, const void* in, void* out) {
+    if (d->dtype == PXB_F32) t_stencil<float>(d, adjoint, in, out); else t_stencil<double>(d, adjoint, in, out);
+    return 0;
+}
+int emu_gradient(const pxb_grad_desc* d, int adjoint, const void* in, void* out) {
+    if (d->dtype == PXB_F32) t_grad<float>(d, adjoint, in, out); else t_grad<double>(d, adjoint, in, out);
+    return 0;
+}
+int emu_pds_primal(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu, const void* z, const void* ktz, void* x_out,
+                   void* w, double* norms) {
+    if (K->dtype == PXB_F32) t_primal<float>(algo, K, p, xu, z, ktz, x_out, w, norms);
+    else t_primal<double>(algo, K, p, xu, z, ktz, x_out, w, norms);
+    return 0;
+}
+int emu_pds_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w, void* z, double* norms) {
+    if (K->dtype == PXB_F32) t_dual<float>(K, p, w, z, norms); else t_dual<double>(K, p, w, z, norms);
+    return 0;
+}
+int emu_dual_update(int dtype, int kind, int64_t outer, int64_t group, int64_t inner, double lam, double sigma, double rho, void* z,
+                    const void* t, double* norms) {
+    for (int64_t o = 0; o < outer; ++o)
+        for (int64_t i = 0; i < inner; ++i) {
+            double a0 = 0, a1 = 0;
+            if (dtype == PXB_F32) pxb_body_dual_update<float>(kind, group, inner, (float)lam, (float)sigma, (float)rho, (float*)z, (const float*)t, norms != nullptr, a0, a1, o, i);
+            else pxb_body_dual_update<double>(kind, group, inner, lam, sigma, rho, (double*)z, (const double*)t, norms != nullptr, a0, a1, o, i);
+            if (norms) { norms[2 * o] += a0; norms[2 * o + 1] += a1; }
+        }
+    return 0;
+}
+int emu_prox_l21(int dtype, int64_t outer, int64_t group, int64_t inner, double lam, double tau, const void* x, void* out) {
+    for (int64_t o = 0; o < outer; ++o)
+        for (int64_t i = 0; i < inner; ++i) {
+            if (dtype == PXB_F32) pxb_body_prox_l21<float>(group, inner, (float)lam, (float)tau, (const float*)x, (float*)out, o, i);
+            else pxb_body_prox_l21<double>(group, inner, lam, tau, (const double*)x, (double*)out, o, i);
+        }
+    return 0;
+}
+int emu_prox_lincomb(int dtype, const pxb_prox_spec* g, double tau, int64_t n, void* out, double a, const void* x, double b,
+                     const void* y, int64_t ny, double c, const void* z, int64_t nz) {
+    if (ny >= n) ny = 0;
+    if (nz >= n) nz = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (dtype == PXB_F32) {
+            float v = pxb_lincomb_at<float>((float)a, (const float*)x, (float)b, (const float*)y, ny, (float)c, (const float*)z, nz, i);
+            if (g) v = pxb_prox_eval<float>(g->kind, (float)g->p0, (float)g->p1, v, (float)tau);
+            ((float*)out)[i] = v;
+        } else {
+            double v = pxb_lincomb_at<double>(a, (const double*)x, b, (const double*)y, ny, c, (const double*)z, nz, i);
+            if (g) v = pxb_prox_eval<double>(g->kind, g->p0, g->p1, v, tau);
+            ((double*)out)[i] = v;
+        }
+    }
+    return 0;
+}
+}

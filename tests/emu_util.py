@@ -1,0 +1,75 @@
+"""Helpers to drive tests/emu/libpxb_emu.so (host build of the kernel bodies) with NumPy arrays."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from pyxu_b200 import _build, _cabi as K
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.build_emu()
+        h = C.CDLL(path)
+        vp, i, i64, d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+        P = C.POINTER
+        h.emu_stencil.argtypes = [P(K.StencilDesc), i, vp, vp]
+        h.emu_gradient.argtypes = [P(K.GradDesc), i, vp, vp]
+        h.emu_pds_primal.argtypes = [i, P(K.GradDesc), P(K.PdsParams), vp, vp, vp, vp, vp, vp]
+        h.emu_pds_dual.argtypes = [P(K.GradDesc), P(K.PdsParams), vp, vp, vp]
+        h.emu_dual_update.argtypes = [i, i, i64, i64, i64, d, d, d, vp, vp, vp]
+        h.emu_prox_l21.argtypes = [i, i64, i64, i64, d, d, vp, vp]
+        h.emu_prox_lincomb.argtypes = [i, P(K.ProxSpec), d, i64, vp, d, vp, d, vp, i64, d, vp, i64]
+        _lib = h
+    return _lib
+
+
+def p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def dcode(a):
+    return K.F32 if a.dtype == np.float32 else K.F64
+
+
+def stencil_run(op, x, adjoint):
+    """Mirror of pyxu_b200.operator.linop.stencil.Stencil._run on host arrays."""
+    x = np.ascontiguousarray(x)
+    batch = max(1, x.size // op.dim)
+    cur = x
+    for k3, c3 in op._passes(adjoint):
+        coef = np.ascontiguousarray(k3.reshape(-1), dtype=x.dtype)
+        d = op._desc(k3, c3, batch, dcode(x), coef.ctypes.data)
+        out = np.empty_like(x)
+        lib().emu_stencil(C.byref(d), int(adjoint), p(cur), p(out))
+        cur = out
+    return cur
+
+
+def gradient_run(op, x, adjoint, slab=None, shape0=None):
+    x = np.ascontiguousarray(x)
+    n_in = op.codim if adjoint else op.dim
+    batch = max(1, x.size // n_in)
+    d = op._desc(batch, dcode(x), slab=slab, shape0=shape0)
+    out = np.empty((*x.shape[:-1], op.dim if adjoint else op.codim), dtype=x.dtype)
+    lib().emu_gradient(C.byref(d), int(adjoint), p(x), p(out))
+    return out
+
+
+def pds_params(tau, sigma, rho, gspec=(K.PROX_NONE, 0.0, 0.0), fkind=K.F_NONE, alpha=0.0, shift=None, garr=None,
+               hkind=K.DUAL_L21, lam=0.0):
+    P = K.PdsParams()
+    P.tau, P.sigma, P.rho = tau, sigma, rho
+    P.g = K.ProxSpec(gspec[0], 0, gspec[1], gspec[2])
+    f = K.FTerm()
+    f.kind, f.alpha = fkind, alpha
+    if shift is not None:
+        f.shift, f.shift_period = shift.ctypes.data, shift.size
+    if garr is not None:
+        f.garr = garr.ctypes.data
+    P.f = f
+    P.hkind, P.lam = hkind, lam
+    return P

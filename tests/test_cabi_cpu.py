@@ -1,0 +1,63 @@
+"""CPU checks of the C-ABI boundary: the library loads and exports every symbol include/pyxu_b200.h
+declares; the ctypes prototypes cover the same set; struct layouts agree with the C compiler."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+from conftest import ROOT
+from pyxu_b200 import _build, _cabi as K
+
+HEADER = os.path.join(ROOT, "include", "pyxu_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pxb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    _build.build_cuda()
+    h = C.CDLL(K.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(h, n), f"{n} declared in include/pyxu_b200.h but not exported"
+    assert set(names) == set(K.PROTOTYPES), set(names) ^ set(K.PROTOTYPES)
+    assert K.lib().pxb_abi_version() == K.ABI_VERSION
+
+
+def test_struct_layouts_match_the_c_compiler():
+    prog = r"""
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "pyxu_b200.h"
+    int main(void){
+      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(pxb_slab), sizeof(pxb_stencil_desc), sizeof(pxb_grad_desc),
+             sizeof(pxb_prox_spec), sizeof(pxb_fterm), sizeof(pxb_pds_params));
+      printf("%zu %zu %zu %zu\n", offsetof(pxb_stencil_desc, coef), offsetof(pxb_grad_desc, coef),
+             offsetof(pxb_grad_desc, slab), offsetof(pxb_pds_params, lam));
+      return 0; }
+    """
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "t.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(td, "t")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    sizes = [C.sizeof(s) for s in (K.Slab, K.StencilDesc, K.GradDesc, K.ProxSpec, K.FTerm, K.PdsParams)]
+    offs = [K.StencilDesc.coef.offset, K.GradDesc.coef.offset, K.GradDesc.slab.offset, K.PdsParams.lam.offset]
+    assert [int(v) for v in out] == sizes + offs
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    lib = K.lib()
+    d = K.StencilDesc()
+    rc = lib.pxb_stencil_apply(C.byref(d), None, None, None)
+    assert rc == -1 and b"null" in lib.pxb_last_error()
+    g = K.GradDesc()
+    g.ndir = 7
+    rc = lib.pxb_gradient_apply(C.byref(g), C.c_void_p(8), C.c_void_p(16), None)
+    assert rc in (-1, -3)

@@ -1,0 +1,180 @@
+"""
+CPU checks of the CUDA kernels' per-voxel bodies (pyxu_b200/csrc/pxb_core.cuh compiled for the host,
+see tests/emu) driven by the descriptors the Python host layer builds, against fixtures produced by
+the real reference.  This validates boundary maps, adjoint pre-image gathering, the fused PD3O / CV
+half-steps and the host->C-ABI translation without a GPU.  (The GPU tests repeat all of this through
+the real library.)
+"""
+import ctypes as C
+import types
+
+import numpy as np
+import pytest
+
+import cases
+import emu_util as E
+import pyxu_b200.operator as pxo
+from conftest import golden
+from pyxu_b200 import _cabi as K
+
+ns = types.SimpleNamespace(operator=pxo)
+
+
+def relerr(a, b):
+    d = np.linalg.norm(np.asarray(b, dtype=np.float64).ravel())
+    return np.linalg.norm((np.asarray(a, dtype=np.float64) - b).ravel()) / (d if d else 1.0)
+
+
+@pytest.mark.parametrize("case", cases.STENCIL_CASES, ids=lambda c: c["name"])
+def test_stencil_bodies(case):
+    g, n = golden("stencil.npz"), case["name"]
+    op = cases.make_stencil(ns, case)
+    assert relerr(E.stencil_run(op, g[f"{n}/x"], False), g[f"{n}/apply"]) < 1e-13
+    assert relerr(E.stencil_run(op, g[f"{n}/y"], True), g[f"{n}/adjoint"]) < 1e-13
+    assert abs(op.lipschitz - float(g[f"{n}/lipschitz"])) <= 1e-12 * op.lipschitz
+
+
+@pytest.mark.parametrize("case", cases.STENCIL_CASES[:8], ids=lambda c: c["name"])
+def test_stencil_bodies_f32(case):
+    g, n = golden("stencil.npz"), case["name"]
+    op = cases.make_stencil(ns, case, dtype=np.float32)
+    assert relerr(E.stencil_run(op, g[f"{n}/x"].astype(np.float32), False), g[f"{n}/apply"]) < 2e-6
+    assert relerr(E.stencil_run(op, g[f"{n}/y"].astype(np.float32), True), g[f"{n}/adjoint"]) < 2e-6
+
+
+@pytest.mark.parametrize("case", cases.GRADIENT_CASES, ids=lambda c: c["name"])
+def test_gradient_bodies(case):
+    g, n = golden("gradient.npz"), case["name"]
+    op = cases.make_gradient(ns, case)
+    assert relerr(E.gradient_run(op, g[f"{n}/x"], False), g[f"{n}/apply"]) < 1e-13
+    assert relerr(E.gradient_run(op, g[f"{n}/y"], True), g[f"{n}/adjoint"]) < 1e-13
+    assert abs(op.lipschitz - float(g[f"{n}/lipschitz"])) <= 1e-12 * op.lipschitz
+
+
+def test_adjoint_is_transpose_random_modes():
+    """<Ax, y> == <x, A^T y> for every mode combination, kernel bigger than needed, tiny arrays."""
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        D = rng.integers(1, 4)
+        shape = tuple(int(rng.integers(3, 7)) for _ in range(D))
+        modes = tuple(rng.choice(list(K.MODES)) for _ in range(D))
+        ks = []
+        for n, m in zip(shape, modes):
+            lim = {"constant": 5, "edge": 5, "wrap": n + 1, "symmetric": n + 1, "reflect": n}[m]
+            ks.append(int(rng.integers(1, min(5, lim) + 1)))
+        kern = rng.standard_normal(ks)
+        cen = tuple(int(rng.integers(0, k)) for k in ks)
+        op = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode=modes)
+        x, y = rng.standard_normal(op.dim), rng.standard_normal(op.dim)
+        lhs = np.dot(E.stencil_run(op, x, False), y)
+        rhs = np.dot(x, E.stencil_run(op, y, True))
+        assert abs(lhs - rhs) < 1e-10 * (1 + abs(lhs)), (shape, modes, ks, cen)
+
+
+def _fused_run(name, algo, shape, n_iter, lam, gspec, y, x0, mode="constant", dtype=np.float64):
+    g = golden("solvers.npz")
+    tau, sigma, rho = (float(g[f"{name}/{k}"]) for k in ("tau", "sigma", "rho"))
+    Kop = pxo.Gradient(arg_shape=shape, mode=mode)
+    D, N = len(shape), int(np.prod(shape))
+    shift = np.ascontiguousarray(-y.reshape(-1), dtype=dtype)
+    P = E.pds_params(tau, sigma, rho, gspec=gspec, fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L21, lam=lam)
+    d = Kop._desc(1, K.F32 if dtype == np.float32 else K.F64)
+    x = np.ascontiguousarray(x0, dtype=dtype).copy()
+    z = E.gradient_run(Kop, x, False)
+    u, w = x.copy(), np.empty_like(x)
+    nx, nz = np.zeros(2), np.zeros(2)
+    for _ in range(n_iter):
+        nx[:] = 0
+        nz[:] = 0
+        if algo == K.ALGO_PD3O:
+            E.lib().emu_pds_primal(algo, C.byref(d), C.byref(P), E.p(u), E.p(z), None, E.p(x), E.p(w), E.p(nx))
+        else:
+            E.lib().emu_pds_primal(algo, C.byref(d), C.byref(P), E.p(x), E.p(z), None, None, E.p(w), E.p(nx))
+        E.lib().emu_pds_dual(C.byref(d), C.byref(P), E.p(w), E.p(z), E.p(nz))
+    return x, z, nx, nz, g
+
+
+POS = (K.PROX_POS, 0.0, 0.0)
+NONE = (K.PROX_NONE, 0.0, 0.0)
+
+
+@pytest.mark.parametrize("strat", [1, 2, 3])
+def test_fused_pd3o_tv2d(strat):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    x, z, *_ = _fused_run(f"pd3o_tv2d/s{strat}", K.ALGO_PD3O, (32, 40), 60, 0.1, POS, y, y.reshape(-1))
+    assert relerr(x, g[f"pd3o_tv2d/s{strat}/x"]) < 1e-10
+    assert relerr(z, g[f"pd3o_tv2d/s{strat}/z"]) < 1e-10
+
+
+@pytest.mark.parametrize("mode", ["reflect", "wrap", "symmetric", "edge"])
+def test_fused_pd3o_tv2d_modes(mode):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    x, z, *_ = _fused_run(f"pd3o_tv2d/{mode}", K.ALGO_PD3O, (32, 40), 40, 0.15, NONE, y, np.zeros(y.size), mode=mode)
+    assert relerr(x, g[f"pd3o_tv2d/{mode}/x"]) < 1e-10
+    assert relerr(z, g[f"pd3o_tv2d/{mode}/z"]) < 1e-10
+
+
+def test_fused_cv_tv2d():
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    x, z, *_ = _fused_run("cv_tv2d", K.ALGO_CV, (32, 40), 60, 0.1, POS, y, y.reshape(-1))
+    assert relerr(x, g["cv_tv2d/x"]) < 1e-10
+    assert relerr(z, g["cv_tv2d/z"]) < 1e-10
+
+
+def test_fused_pd3o_tv3d_and_norms():
+    g = golden("solvers.npz")
+    y = g["pd3o_tv3d/y"]
+    x, z, nx, nz, _ = _fused_run("pd3o_tv3d", K.ALGO_PD3O, (10, 12, 14), 50, 0.08, POS, y, y.reshape(-1))
+    assert relerr(x, g["pd3o_tv3d/x"]) < 1e-10
+    assert relerr(z, g["pd3o_tv3d/z"]) < 1e-10
+    x2, z2, *_ = _fused_run("pd3o_tv3d/mixed", K.ALGO_PD3O, (10, 12, 14), 30, 0.08, POS, y, y.reshape(-1),
+                            mode=("reflect", "wrap", "constant"))
+    assert relerr(x2, g["pd3o_tv3d/mixed/x"]) < 1e-10
+    # fused RelError norms of the last iteration == norms recomputed from iterates 49 -> 50
+    xa, za, *_ = _fused_run("pd3o_tv3d", K.ALGO_PD3O, (10, 12, 14), 49, 0.08, POS, y, y.reshape(-1))
+    assert abs(nx[0] - np.sum((x - xa) ** 2)) < 1e-12 * (1 + nx[0]) and abs(nx[1] - np.sum(xa**2)) < 1e-9 * nx[1]
+    assert abs(nz[0] - np.sum((z - za) ** 2)) < 1e-12 * (1 + nz[0]) and abs(nz[1] - np.sum(za**2)) < 1e-9 * nz[1]
+
+
+def test_fused_pd3o_f32_tolerance():
+    """fp32 kernels vs the reference's float64 solver: rel. L2 error <= 1e-4 (north-star tolerance)."""
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    x, z, *_ = _fused_run("pd3o_tv2d/s1", K.ALGO_PD3O, (32, 40), 60, 0.1, POS, y, y.reshape(-1), dtype=np.float32)
+    assert relerr(x, g["pd3o_tv2d/s1/x"]) < 1e-4
+
+
+def test_funcs_bodies():
+    g = golden("funcs.npz")
+    x = g["x"]
+    lib = E.lib()
+
+    def prox(spec, tau):
+        out = np.empty_like(x)
+        s = K.ProxSpec(spec[0], 0, spec[1], spec[2])
+        lib.emu_prox_lincomb(K.F64, C.byref(s), tau, x.size, E.p(out), 1.0, E.p(x), 0.0, None, 0, 0.0, None, 0)
+        return out
+
+    for tau in (0.3, 1.7):
+        t = f"{tau}"
+        assert relerr(prox((K.PROX_L1, 1.0, 0), tau), g[f"l1/prox/{t}"]) < 1e-14
+        assert relerr(prox((K.PROX_L1, 0.4, 0), tau), g[f"l1s/prox/{t}"]) < 1e-14
+        assert relerr(prox((K.PROX_POSL1, 1.0, 0), tau), g[f"posl1/prox/{t}"]) < 1e-14
+        assert relerr(prox((K.PROX_POS, 0, 0), tau), g[f"pos/prox/{t}"]) < 1e-14
+        assert relerr(prox((K.PROX_BOX, -0.8, 0.8), tau), g[f"linfball/prox/{t}"]) < 1e-14
+        assert relerr(prox((K.PROX_SQL2, 1.0, 0), tau), g[f"sql2/prox/{t}"]) < 1e-14
+        out = np.empty_like(x)
+        lib.emu_prox_l21(K.F64, 3, 3, 20, 1.0, tau, E.p(x), E.p(out))
+        assert relerr(out, g[f"l21/prox/{t}"]) < 1e-14
+        lib.emu_prox_l21(K.F64, 9, 20, 1, 1.0, tau, E.p(x), E.p(out))
+        assert relerr(out, g[f"l21ax12/prox/{t}"]) < 1e-14
+        # fenchel prox of 0.7*L21 at x == dual_update with z=0... use z = x, t = 0, rho = 1: prox_{sigma h*}(x)
+        z, tt = x.copy(), np.zeros_like(x)
+        lib.emu_dual_update(K.F64, K.DUAL_L21, 3, 3, 20, 0.7, tau, 1.0, E.p(z), E.p(tt), None)
+        assert relerr(z, g[f"l21s/fprox/{t}"]) < 1e-14
+        z = x.copy()
+        lib.emu_dual_update(K.F64, K.DUAL_L1, 3, 1, 60, 1.0, tau, 1.0, E.p(z), E.p(tt), None)
+        assert relerr(z, g[f"l1/fprox/{t}"]) < 1e-14

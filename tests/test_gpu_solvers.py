@@ -1,0 +1,235 @@
+"""
+GPU parity tests of the solvers through Solver.fit(): every fixture the real reference produced
+(tests/golden/solvers.npz, config0.npz) is re-run through pyxu_b200 with the same problem builders
+(tests/golden/cases.py).  Tolerance after N iterations: rel. L2 <= 1e-10 (fp64), <= 1e-4 (fp32)
+-- the north-star's bar.  Iteration counts under the default RelError criterion must match exactly.
+"""
+import types
+
+import numpy as np
+import pytest
+
+import cases
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+TOL64, TOL32 = 1e-10, 1e-4
+
+
+@pytest.fixture(scope="module")
+def px():
+    import pyxu_b200.operator as pxo
+    import pyxu_b200.opt.solver as pxs
+    import pyxu_b200.opt.stop as pxst
+
+    assert torch.cuda.is_available()
+    return types.SimpleNamespace(operator=pxo, solver=pxs, stop=pxst)
+
+
+def relerr(a, b):
+    a = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    return np.linalg.norm((a.astype(np.float64) - b).ravel()) / np.linalg.norm(b.ravel())
+
+
+def check(slv, g, prefix, keys=("x", "z"), tol=TOL64, steps=True):
+    assert slv._astate.get("error") is None, slv._astate.get("error")
+    data, hist = slv.stats()
+    for k in keys:
+        assert relerr(data[k], g[f"{prefix}/{k}"]) < tol, (prefix, k, relerr(data[k], g[f"{prefix}/{k}"]))
+    if steps:
+        for k in ("tau", "sigma", "rho"):
+            if f"{prefix}/{k}" in g:
+                assert abs(float(slv._mstate[k]) - float(g[f"{prefix}/{k}"])) < 1e-8
+    assert len(hist) == int(g[f"{prefix}/n_hist"])
+    return data, hist
+
+
+@pytest.mark.parametrize("strat", [1, 2, 3])
+def test_pd3o_tv2d(px, strat):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.1)
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=px.stop.MaxIter(60), tuning_strategy=strat)
+    assert slv._plan.kind == "fused"
+    data, _ = check(slv, g, f"pd3o_tv2d/s{strat}")
+    assert isinstance(data["x"], np.ndarray)
+
+
+def test_pd3o_tv2d_default_stop_iteration_count(px):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.1)
+    slv.fit(x0=y.reshape(-1).copy())  # RelError[x] & RelError[z], fused into the update kernels
+    assert "_fused_norms" in slv._mstate
+    data, hist = check(slv, g, "pd3o_tv2d/default_stop", tol=1e-9)
+    last = np.array([float(hist[-1][n]) for n in hist.dtype.names])
+    assert np.allclose(last, g["pd3o_tv2d/default_stop/hist_last"], rtol=1e-6)
+    # same run with the generic (non-fused) criterion path: stop_rate=1 but criterion on a transformed variable
+    slv2 = cases.build_tv_denoise(px, y, (32, 40), lam=0.1)
+    sc = px.stop.RelError(eps=1e-4, var="x", f=lambda v: v) & px.stop.RelError(eps=1e-4, var="z", f=lambda v: v)
+    slv2.fit(x0=y.reshape(-1).copy(), stop_crit=sc)
+    _, hist2 = slv2.stats()
+    assert len(hist2) == len(hist)
+
+
+@pytest.mark.parametrize("mode", ["reflect", "wrap", "symmetric", "edge"])
+def test_pd3o_tv2d_modes(px, mode):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.15, mode=mode, positivity=False)
+    slv.fit(x0=np.zeros(y.size), stop_crit=px.stop.MaxIter(40))
+    check(slv, g, f"pd3o_tv2d/{mode}")
+
+
+def test_cv_tv2d(px):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.1, solver="CondatVu")
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=px.stop.MaxIter(60))
+    assert slv._plan.kind == "fused"
+    check(slv, g, "cv_tv2d")
+
+
+def test_pd3o_tv3d(px):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv3d/y"]
+    slv = cases.build_tv_denoise(px, y, (10, 12, 14), lam=0.08)
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=px.stop.MaxIter(50))
+    check(slv, g, "pd3o_tv3d")
+    slv = cases.build_tv_denoise(px, y, (10, 12, 14), lam=0.08, mode=("reflect", "wrap", "constant"))
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=px.stop.MaxIter(30), tuning_strategy=3)
+    check(slv, g, "pd3o_tv3d/mixed")
+    # fp32 run against the float64 reference result
+    slv = cases.build_tv_denoise(px, y.astype(np.float32), (10, 12, 14), lam=0.08, dtype=np.float32)
+    slv.fit(x0=y.reshape(-1).astype(np.float32), stop_crit=px.stop.MaxIter(50))
+    data, _ = slv.stats()
+    assert data["x"].dtype == np.float32 and relerr(data["x"], g["pd3o_tv3d/x"]) < TOL32
+
+
+@pytest.mark.parametrize("tag", ["dense", "sep"])
+def test_cv_deblur2d(px, tag):
+    g = golden("solvers.npz")
+    g9 = cases.gaussian_1d(9, 1.5)
+    kern = np.outer(g9, g9) if tag == "dense" else [g9, g9]
+    yb = g[f"cv_deblur2d/{tag}/y"]
+    slv, A = cases.build_tv_deblur(px, yb, (28, 24), kern, (4, 4), lam=0.02)
+    slv.fit(x0=np.zeros(yb.size), stop_crit=px.stop.MaxIter(40))
+    assert slv._plan.kind == "fused"
+    check(slv, g, f"cv_deblur2d/{tag}")
+
+
+def test_pd3o_deblur2d_semi_fused(px):
+    g = golden("solvers.npz")
+    g9 = cases.gaussian_1d(9, 1.5)
+    yb = g["cv_deblur2d/sep/y"]
+    slv, A = cases.build_tv_deblur(px, yb, (28, 24), np.outer(g9, g9), (4, 4), lam=0.02, blur_mode="reflect",
+                                   positivity=True, solver="PD3O")
+    slv.fit(x0=np.zeros(yb.size), stop_crit=px.stop.MaxIter(40))
+    assert slv._plan.kind == "semi"
+    check(slv, g, "pd3o_deblur2d")
+
+
+def test_cv_deblur3d(px):
+    g = golden("solvers.npz")
+    g3 = cases.gaussian_1d(3, 0.8)
+    psf = np.einsum("i,j,k->ijk", g3, g3, g3)
+    yb = g["cv_deblur3d/y"]
+    slv, A = cases.build_tv_deblur(px, yb, (9, 10, 11), psf, (1, 1, 1), lam=0.01, positivity=True)
+    slv.fit(x0=np.zeros(yb.size), stop_crit=px.stop.MaxIter(30))
+    check(slv, g, "cv_deblur3d")
+
+
+@pytest.mark.parametrize("acc", [True, False])
+def test_pgd_l1_deconv(px, acc):
+    g = golden("solvers.npz")
+    B, shape = 3, (20, 22)
+    k5 = np.outer(cases.gaussian_1d(5, 1.0), cases.gaussian_1d(5, 1.0))[None]
+    yb = g["pgd_l1/y"]
+    slv, A = cases.build_l1_deconv(px, yb, (B,) + shape, k5, (0, 2, 2), lam=0.02)
+    slv.fit(x0=np.zeros(yb.size), stop_crit=px.stop.MaxIter(50), acceleration=acc, tau=1 / A.lipschitz**2)
+    check(slv, g, f"pgd_l1/acc{int(acc)}", keys=("x",), steps=False)
+
+
+def test_pgd_default_stop_iteration_count(px):
+    g = golden("solvers.npz")
+    B, shape = 3, (20, 22)
+    k5 = np.outer(cases.gaussian_1d(5, 1.0), cases.gaussian_1d(5, 1.0))[None]
+    yb = g["pgd_l1/y"]
+    slv, A = cases.build_l1_deconv(px, yb, (B,) + shape, k5, (0, 2, 2), lam=0.02)
+    slv.fit(x0=np.zeros(yb.size), tau=1 / A.lipschitz**2)
+    check(slv, g, "pgd_l1/default_stop", keys=("x",), tol=1e-9, steps=False)
+
+
+def test_pgd_stacked_images_equal_per_image_solves(px):
+    """config[2] layout: a stack (B, N) of independent images with per-image data (stacked argshift)."""
+    pxo = px.operator
+    B, shape = 4, (24, 20)
+    N = shape[0] * shape[1]
+    rng = np.random.default_rng(3)
+    ys = rng.random((B, N))
+    k5 = np.outer(cases.gaussian_1d(5, 1.0), cases.gaussian_1d(5, 1.0))
+    A = pxo.Stencil(arg_shape=shape, kernel=k5, center=(2, 2), mode="reflect")
+    outs = []
+    for data in (ys, *[ys[b] for b in range(B)]):
+        f = (0.5 * pxo.SquaredL2Norm(dim=N).argshift(-data)) * A
+        slv = px.solver.PGD(f=f, g=0.02 * pxo.L1Norm(dim=N), show_progress=False)
+        slv.fit(x0=np.zeros_like(data), stop_crit=px.stop.MaxIter(30), tau=1 / A.lipschitz**2)
+        outs.append(slv.solution())
+    assert outs[0].shape == (B, N)
+    for b in range(B):
+        assert relerr(outs[0][b], outs[1 + b]) < 1e-13
+
+
+def test_generic_path_equals_fused_path(px):
+    """Same PD3O-TV problem with K wrapped so the planner cannot recognise it -> generic execution."""
+    pxo = px.operator
+    g = golden("solvers.npz")
+    y = g["pd3o_tv3d/y"]
+    shape, N = (10, 12, 14), 10 * 12 * 14
+    Kop = pxo.Gradient(arg_shape=shape)
+    Kw = (2.0 * Kop) * 0.5 if False else (Kop * pxo.HomothetyOp(dim=N, cst=1.0 + 0.0))  # opaque composition
+    f = 0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y.reshape(-1))
+    h = 0.08 * pxo.L21Norm(arg_shape=(3, *shape), l2_axis=(0,))
+    slv = px.solver.PD3O(f=f, g=pxo.PositiveOrthant(dim=N), h=h, K=Kw, show_progress=False)
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=px.stop.MaxIter(50), tau=float(g["pd3o_tv3d/tau"]), sigma=float(g["pd3o_tv3d/sigma"]))
+    assert slv._plan.kind == "generic"
+    check(slv, g, "pd3o_tv3d", steps=False)
+
+
+def test_config0_full_size(px):
+    """BASELINE.json configs[0]: 512x512 float64 PD3O TV denoising + positivity, 200 iterations."""
+    g = golden("config0.npz")
+    shape = (512, 512)
+    _, y = cases.phantom(shape, seed=11, noise=0.15)
+    slv = cases.build_tv_denoise(px, y, shape, lam=0.1)
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=px.stop.MaxIter(200))
+    assert slv._astate.get("error") is None
+    d, _ = slv.stats()
+    x, z = d["x"], d["z"]
+    assert relerr(x[::37], g["x_sub"]) < TOL64 and relerr(z[::41], g["z_sub"]) < TOL64
+    assert abs(np.linalg.norm(x) - float(g["x_norm"])) < 1e-10 * float(g["x_norm"])
+    assert abs(x.sum() - float(g["x_sum"])) < 1e-9 * abs(float(g["x_sum"]))
+    assert abs(slv._mstate["tau"] - float(g["tau"])) < 1e-9
+
+
+def test_manual_and_async_modes(px):
+    import time
+
+    from pyxu_b200.abc import Mode
+
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.1)
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=px.stop.MaxIter(60), mode=Mode.MANUAL)
+    n = sum(1 for _ in slv.steps())
+    assert n == 60
+    check(slv, g, "pd3o_tv2d/s1")
+    slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.1)
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=px.stop.MaxIter(60), mode=Mode.ASYNC)
+    while slv.busy():
+        time.sleep(0.01)
+    slv.stop()
+    check(slv, g, "pd3o_tv2d/s1")
+    assert slv.datafile.exists()

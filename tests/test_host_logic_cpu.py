@@ -1,0 +1,114 @@
+"""Host-side logic that needs no GPU: operator arithmetic (class inference, Lipschitz propagation),
+descriptor construction, step-size selection, solver argument validation."""
+import math
+import types
+
+import numpy as np
+import pytest
+
+import cases
+import pyxu_b200.abc as pxa
+import pyxu_b200.operator as pxo
+import pyxu_b200.opt.solver as pxs
+import pyxu_b200.opt.stop as pxst
+from conftest import golden
+from oracle import pyxu_oracle as orc
+from pyxu_b200 import _cabi as K
+
+
+def test_arithmetic_class_inference_and_constants():
+    N = 12
+    sq = pxo.SquaredL2Norm(dim=N)
+    f = 0.5 * sq.argshift(-np.arange(N, dtype=float))
+    assert isinstance(f, pxa.QuadraticFunc) and f.diff_lipschitz == 1.0
+    assert f._sql2_spec()[0] == 0.5 and np.array_equal(f._sql2_spec()[1], -np.arange(N))
+    A = pxo.Stencil(arg_shape=(3, 4), kernel=np.ones((3, 3)), center=(1, 1))
+    fA = f * A
+    assert isinstance(fA, pxa.QuadraticFunc) and fA.shape == (1, N)
+    assert math.isclose(fA.diff_lipschitz, A.lipschitz**2)
+    h = 0.3 * pxo.L21Norm(arg_shape=(2, 3, 4))
+    assert isinstance(h, pxa.ProxFunc) and not isinstance(h, pxa.DiffFunc)
+    assert h._dual_spec() == (K.DUAL_L21, 0.3, (1, 2, 12))
+    g = 2.0 * pxo.L1Norm(dim=N)
+    assert g._prox_spec() == (K.PROX_L1, 2.0, 0.0) and math.isclose(g.lipschitz, 2 * math.sqrt(N))
+    assert (3 * pxo.PositiveOrthant(dim=N))._prox_spec()[0] == K.PROX_POS
+    assert (-1 * pxo.L1Norm(dim=N)).can_prox is False  # negative scaling loses proximability
+    s = pxo.L1Norm(dim=N) + f
+    assert isinstance(s, pxa.Func) and not s.can_prox
+    AT = A.T
+    assert AT.shape == (N, N) and AT.T is A and AT.lipschitz == A.lipschitz
+    AA = A.T * A
+    assert isinstance(AA, pxa.SquareOp) and math.isclose(AA.lipschitz, A.lipschitz**2)
+    assert (A * 0).__class__.__name__ == "NullOp" and (A * 1) is A
+    with pytest.raises(ValueError):
+        f.argshift(np.zeros(N + 1))
+    with pytest.raises(ValueError):
+        A + pxo.Stencil(arg_shape=(5,), kernel=np.ones(2), center=(0,))
+
+
+def test_stencil_constructor_validation_matches_reference():
+    with pytest.raises(AssertionError):  # center outside kernel (reference: _stencil.py:123-125)
+        pxo.Stencil(arg_shape=(8,), kernel=np.ones(3), center=(3,))
+    with pytest.raises(AssertionError):  # reflect pad width limited to N-1 (reference: pad.py:217-229)
+        pxo.Stencil(arg_shape=(4,), kernel=np.ones(6), center=(0,), mode="reflect")
+    with pytest.raises(AssertionError):
+        pxo.Stencil(arg_shape=(4, 4), kernel=np.ones(3), center=(0, 0))
+    op = pxo.Stencil(arg_shape=(5, 6, 9), kernel=[np.r_[1, -1], np.r_[3, 2, 1], np.r_[2, -1, 3, 1]], center=(1, 0, 3))
+    assert [r.tolist() for r in op.relative_indices] == [[-1, 0], [0, 1, 2], [-3, -2, -1, 0]]  # stencil.py:740-749
+    assert op.center == (1, 0, 3)
+
+
+@pytest.mark.parametrize("case", cases.GRADIENT_CASES, ids=lambda c: c["name"])
+def test_fd_coefficients_match_reference(case):
+    ns = types.SimpleNamespace(operator=pxo)
+    op = cases.make_gradient(ns, case)
+    ref = orc.Gradient(case["arg_shape"], mode=case["mode"], **case["diff_kwargs"])
+    for t, c, rop, d in zip(op._taps, op._centers, ref.ops, op._dirs):
+        assert np.allclose(t, rop._k[d].reshape(-1), rtol=0, atol=0) and c == rop._c[d][d]
+
+
+def test_step_sizes_match_reference_fixture():
+    g = golden("solvers.npz")
+    ns = types.SimpleNamespace(operator=pxo, solver=pxs, stop=pxst)
+    y = g["pd3o_tv2d/y"]
+    for strat in (1, 2, 3):
+        slv = cases.build_tv_denoise(ns, y, (32, 40), lam=0.1)
+        slv._tuning_strategy = strat
+        gamma = slv._set_gamma(strat)
+        tau, sigma, delta = slv._set_step_sizes(None, None, gamma)
+        rho = slv._set_momentum_term(None, delta)
+        for k, v in (("tau", tau), ("sigma", sigma), ("rho", rho)):
+            assert abs(v - float(g[f"pd3o_tv2d/s{strat}/{k}"])) < 1e-9, (strat, k)
+        # closed form used by the oracle agrees with the LP
+        t2, s2, r2 = orc.pd3o_step_sizes(slv._beta, slv._K.lipschitz, True, tuning_strategy=strat)
+        assert abs(t2 - tau) < 1e-8 and abs(r2 - rho) < 1e-8
+    slv = cases.build_tv_denoise(ns, y, (32, 40), lam=0.1, solver="CondatVu")
+    slv._tuning_strategy = 1
+    tau, sigma, delta = slv._set_step_sizes(None, None, slv._set_gamma(1))
+    assert abs(tau - float(g["cv_tv2d/tau"])) < 1e-12 and abs(sigma - float(g["cv_tv2d/sigma"])) < 1e-12
+    t2, s2, _ = orc.cv_step_sizes(slv._beta, slv._K.lipschitz, True, True)
+    assert abs(t2 - tau) < 1e-14
+
+
+def test_solver_argument_validation():
+    with pytest.raises(ValueError):
+        pxs.PD3O()
+    with pytest.raises(ValueError):
+        pxs.PGD()
+    N = 6
+    with pytest.raises(ValueError):  # K without h (reference: pds.py:72-77)
+        pxs.CV(f=pxo.SquaredL2Norm(dim=N), K=pxo.Gradient(arg_shape=(N,)))
+    with pytest.raises(ValueError):  # unbounded diff-Lipschitz (reference: pds.py:141-146)
+        pxs.PD3O(f=pxo.L1Norm(dim=N).moreau_envelope(1.0) * 1.0 if False else _Unbounded(N))
+    with pytest.raises(ValueError):
+        pxst.MaxIter(0)
+    with pytest.raises(ValueError):
+        pxst.RelError(eps=-1)
+    sc = pxst.MaxIter(3) & pxst.RelError(1e-3)
+    assert sc._fused_vars() == {"x"} and sc._needs_host_sync()
+    assert not pxst.MaxIter(3)._needs_host_sync()
+
+
+class _Unbounded(pxa.DiffFunc):
+    def __init__(self, n):
+        super().__init__((1, n))
