@@ -53,7 +53,9 @@ typedef struct pxb_slab {
     int32_t halo;    /* planes allocated on EACH side of the owned planes (0 on a single GPU).  Arrays are
                         (halo + n0 + halo, n1, n2) per component; pointers passed to a call address owned
                         plane 0.  halo > 0 requires batch == 1. */
-    int32_t _pad;
+    int32_t plane_alloc; /* planes allocated per component (stride between components / batch items, in planes);
+                            0 means n0 + 2*halo.  Lets a call address a sub-range of planes of a larger slab
+                            (boundary planes first, interior while the halo exchange is in flight). */
 } pxb_slab;
 
 /* ------------------------------------------------------------------------------------------ */

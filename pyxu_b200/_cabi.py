@@ -26,7 +26,7 @@ class NativeLibraryError(RuntimeError):
 
 
 class Slab(C.Structure):
-    _fields_ = [("open_lo", C.c_int32), ("open_hi", C.c_int32), ("halo", C.c_int32), ("_pad", C.c_int32)]
+    _fields_ = [("open_lo", C.c_int32), ("open_hi", C.c_int32), ("halo", C.c_int32), ("plane_alloc", C.c_int32)]
 
 
 class StencilDesc(C.Structure):

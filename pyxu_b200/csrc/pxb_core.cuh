@@ -354,7 +354,9 @@ PXB_HD void pxb_primal_at(int algo, const pxb_pds_params& P, T ktz, T xu_old, in
 // Per-voxel kernel bodies.  (b, i0, i1, i2) is the voxel; array base pointers address owned plane 0
 // of batch item 0.  `vol` = elements per component incl. halo planes = (n0 + 2*halo)*n1*n2.
 // ---------------------------------------------------------------------------------------------
-PXB_HD int64_t pxb_vol(const PxbGeom& g, const pxb_slab& s) { return (int64_t)(g.n0 + 2 * s.halo) * g.s0; }
+PXB_HD int64_t pxb_vol(const PxbGeom& g, const pxb_slab& s) {
+    return (int64_t)(s.plane_alloc > 0 ? s.plane_alloc : g.n0 + 2 * s.halo) * g.s0;
+}
 
 template <class T>
 PXB_HD void pxb_body_stencil(const pxb_stencil_desc& d, const PxbGeom& g, bool adjoint, const T* __restrict__ in,

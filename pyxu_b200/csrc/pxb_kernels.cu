@@ -253,6 +253,7 @@ int check_slab(const pxb_slab& s, int64_t batch, int need, const char* who) {
     if (s.halo < 0) return fail(PXB_EINVAL, "%s: negative halo", who);
     if ((s.open_lo || s.open_hi) && s.halo < need) return fail(PXB_EINVAL, "%s: halo=%d planes < stencil reach %d", who, s.halo, need);
     if (s.halo > 0 && batch != 1) return fail(PXB_EINVAL, "%s: slab halos require batch == 1", who);
+    if (s.plane_alloc < 0) return fail(PXB_EINVAL, "%s: negative plane_alloc", who);
     return 0;
 }
 

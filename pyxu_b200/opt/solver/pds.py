@@ -110,6 +110,7 @@ class _Plan:
 
 class _PrimalDualSplitting(Solver):
     _ALGO = None
+    _probe = None  # optional callable(tag) invoked around the fused kernels (bench.py records CUDA events with it)
 
     def __init__(self, f=None, g=None, h=None, K=None, beta=None, **kwargs):
         kwargs.update(log_var=kwargs.get("log_var", ("x", "z")))
@@ -350,10 +351,16 @@ class PD3O(_PrimalDualSplitting):
             if self._nx is not None:
                 self._nx.zero_()
             p = pl.params(mst)
+            if self._probe:
+                self._probe("primal_begin")
             rc = K.lib().pxb_pds_primal(K.ALGO_PD3O, C.byref(pl.gdesc), C.byref(p), A.ptr(mst["u"]), A.ptr(mst["z"]), None,
                                         A.ptr(mst["x"]), A.ptr(pl.w), A.ptr(self._nx), A.stream())
             K.check(rc, "pxb_pds_primal")
+            if self._probe:
+                self._probe("primal_end")
             self._dual_fused(pl.w)
+            if self._probe:
+                self._probe("dual_end")
             return
         u = mst["u"]
         ktz = None if pl.h_null else self._K.jacobian(u).adjoint(mst["z"])
