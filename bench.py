@@ -340,7 +340,7 @@ def main():
         t0 = time.perf_counter()
         f2 = 0.5 * pxo.SquaredL2Norm(dim=nvox).argshift(shift_np)
         slv2 = pxs.PD3O(f=f2, g=pxo.PositiveOrthant(dim=nvox), h=LAM * pxo.L21Norm(arg_shape=(3, *shape), l2_axis=(0,)),
-                        K=Kop, show_progress=False)
+                        K=Kop, show_progress=False, final_writeback=False)
         # K iterations; the RelError metric is read back from the device every iteration (eps tiny: never triggers)
         slv2.fit(x0=x0_np, stop_crit=pxst.MaxIter(K) | pxst.RelError(eps=1e-30, var="x"))
         x_host = slv2.solution()

@@ -78,7 +78,11 @@ class _Composition(StoppingCriterion):
 
 class Solver:
     def __init__(self, *, folder=None, exist_ok=False, stop_rate=1, writeback_rate=None, verbosity=None,
-                 show_progress=True, log_var=frozenset()):
+                 show_progress=True, log_var=frozenset(), final_writeback=True):
+        """Same parameters as the reference (solver.py:188-236) plus `final_writeback`: the reference always dumps
+        the logged variables to <workdir>/data.npz when the solver stops; for multi-GiB volumes that disk write
+        dominates everything else, so it can be switched off here (default: on, as in the reference)."""
+        self._final_writeback = bool(final_writeback)
         self._mstate = dict()
         self._astate = dict(history=None, idx=0, log_rate=None, log_var=None, logger=None, stdout=None, stop_crit=None,
                             stop_rate=None, track_objective=None, wb_rate=None, workdir=None, mode=None, active=None,
@@ -157,16 +161,20 @@ class Solver:
         """Hook: bring a lazily-maintained state variable up to date (fused solvers override)."""
         return self._mstate.get(name)
 
+    def _logged(self, k):
+        """Logged variable `k` in the memory space fit() received its arrays in (None if unknown)."""
+        if k not in self._astate["log_var"]:
+            return None
+        v = self._materialize(k)
+        if v is not None and hasattr(v, "is_cuda"):
+            v = A.restore(v, self._astate["origin"])
+        return v
+
     def stats(self):
         history = self._astate["history"]
         if history is not None:
             history = np.concatenate(history, dtype=history[0].dtype, axis=0) if len(history) > 0 else None
-        data = {}
-        for k in self._astate["log_var"]:
-            v = self._materialize(k)
-            if v is not None and hasattr(v, "is_cuda"):
-                v = A.restore(v, self._astate["origin"])
-            data[k] = v
+        data = {k: self._logged(k) for k in self._astate["log_var"]}
         return data, history
 
     @property
@@ -298,7 +306,8 @@ class Solver:
                 _update_history()
                 _log()
                 _log(msg=f"[{dt.datetime.now()}] Stopping Criterion satisfied -> END")
-                self.writeback()
+                if self._final_writeback:
+                    self.writeback()
                 return False
             if must_stop:
                 _update_history()

@@ -12,7 +12,10 @@
 #include <cstdio>
 #include <string>
 
+#include <initializer_list>
+
 #include "pxb_core.cuh"
+#include "pxb_tv_fast.cuh"
 
 namespace {
 
@@ -176,6 +179,72 @@ __global__ void __launch_bounds__(kBlock) k_pds_dual(pxb_grad_desc d, pxb_pds_pa
     if (norms) block_accumulate(a0, a1, v.b, v.ok, norms);
 }
 
+// ------------------------------------------------------------------------------------------
+// Fast TV half-steps (pxb_tv_fast.cuh): one thread = VEC consecutive voxels (128-bit accesses).
+// The VoxMap is built on the row length n2/VEC; i2 is scaled back by VEC here.
+// ------------------------------------------------------------------------------------------
+template <class T, int NDIR, int VEC>
+__global__ void __launch_bounds__(kBlock) k_tv_primal(int algo, pxb_grad_desc d, PxbTvCoef cf, pxb_pds_params P, VoxMap m,
+                                                      T* __restrict__ xu, const T* __restrict__ z, T* __restrict__ x_out,
+                                                      T* __restrict__ w, double* __restrict__ norms) {
+    const Vox v = vox_of_thread(m);
+    const PxbGeom g = pxb_geom(d.shape);
+    double a0 = 0.0, a1 = 0.0;
+    if (v.ok) pxb_tv_primal_vec<T, NDIR, VEC>(algo, d, g, cf, P, xu, z, x_out, w, norms != nullptr, a0, a1, v.b, v.i0, v.i1, v.i2 * VEC);
+    if (norms) block_accumulate(a0, a1, v.b, v.ok, norms);
+}
+
+template <class T, int NDIR, int VEC>
+__global__ void __launch_bounds__(kBlock) k_tv_dual(pxb_grad_desc d, PxbTvCoef cf, pxb_pds_params P, VoxMap m,
+                                                    const T* __restrict__ w, T* __restrict__ z, double* __restrict__ norms) {
+    const Vox v = vox_of_thread(m);
+    const PxbGeom g = pxb_geom(d.shape);
+    double a0 = 0.0, a1 = 0.0;
+    if (v.ok) pxb_tv_dual_vec<T, NDIR, VEC>(d, g, cf, P, w, z, norms != nullptr, a0, a1, v.b, v.i0, v.i1, v.i2 * VEC);
+    if (norms) block_accumulate(a0, a1, v.b, v.ok, norms);
+}
+
+// widest vector (<= 16 bytes) that divides the row length and matches every pointer's alignment
+template <class T>
+int pick_vec(int64_t n2, std::initializer_list<const void*> ptrs) {
+    int vec = 16 / (int)sizeof(T);
+    while (vec > 1) {
+        bool ok = (n2 % vec) == 0;
+        for (const void* p : ptrs)
+            if (p && (reinterpret_cast<uintptr_t>(p) % (vec * sizeof(T))) != 0) ok = false;
+        if (ok) break;
+        vec >>= 1;
+    }
+    return vec;
+}
+
+inline bool make_map_vec(int64_t batch, const int64_t shape[3], int vec, VoxMap& m) {
+    int64_t sh[3] = {shape[0], shape[1], shape[2] / vec};
+    return make_map(batch, sh, m);
+}
+
+template <class T, int NDIR>
+void launch_tv_primal(int vec, unsigned grid, cudaStream_t s, int algo, const pxb_grad_desc& d, const PxbTvCoef& cf,
+                      const pxb_pds_params& P, const VoxMap& m, void* xu, const void* z, void* x_out, void* w, double* norms) {
+    T* a = (T*)xu; const T* b = (const T*)z; T* c = (T*)x_out; T* e = (T*)w;
+    if constexpr (sizeof(T) == 4) {
+        if (vec == 4) { k_tv_primal<T, NDIR, 4><<<grid, kBlock, 0, s>>>(algo, d, cf, P, m, a, b, c, e, norms); return; }
+    }
+    if (vec == 2) k_tv_primal<T, NDIR, 2><<<grid, kBlock, 0, s>>>(algo, d, cf, P, m, a, b, c, e, norms);
+    else k_tv_primal<T, NDIR, 1><<<grid, kBlock, 0, s>>>(algo, d, cf, P, m, a, b, c, e, norms);
+}
+
+template <class T, int NDIR>
+void launch_tv_dual(int vec, unsigned grid, cudaStream_t s, const pxb_grad_desc& d, const PxbTvCoef& cf, const pxb_pds_params& P,
+                    const VoxMap& m, const void* w, void* z, double* norms) {
+    const T* a = (const T*)w; T* b = (T*)z;
+    if constexpr (sizeof(T) == 4) {
+        if (vec == 4) { k_tv_dual<T, NDIR, 4><<<grid, kBlock, 0, s>>>(d, cf, P, m, a, b, norms); return; }
+    }
+    if (vec == 2) k_tv_dual<T, NDIR, 2><<<grid, kBlock, 0, s>>>(d, cf, P, m, a, b, norms);
+    else k_tv_dual<T, NDIR, 1><<<grid, kBlock, 0, s>>>(d, cf, P, m, a, b, norms);
+}
+
 // (outer, group, inner) kernels: one thread per (outer, inner) pair, `inner` fastest.
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_dual_update(int kind, int64_t outer, int64_t group, int64_t inner, T lam, T sigma, T rho,
@@ -241,7 +310,7 @@ int check_shape(const int64_t shape[3], int64_t batch, const char* who) {
 // pad-width limits of the reference (pad.py:217-229): a boundary coordinate must fold at most once.
 int check_mode(int mode, int64_t n, int p, int open_lo, int open_hi, const char* who, int axis) {
     if (mode < PXB_CONSTANT || mode > PXB_EDGE) return fail(PXB_EINVAL, "%s: unknown mode %d on axis %d", who, mode, axis);
-    if (open_lo && open_hi) return 0;
+    if (open_lo || open_hi) return 0;  // slab / sub-range launch: the caller guarantees the halo covers the reach
     int64_t lim = 0x7fffffff;
     if (mode == PXB_WRAP || mode == PXB_SYMMETRIC) lim = n;
     if (mode == PXB_REFLECT) lim = n - 1;
@@ -444,8 +513,24 @@ int pxb_pds_primal(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, vo
     if (algo == PXB_PD3O && p->f.kind == PXB_F_GRADARR) return fail(PXB_EINVAL, "%s: PD3O evaluates grad f at the new x; PXB_F_GRADARR is CV-only", who);
     if (p->hkind != PXB_DUAL_NONE && !z && !ktz) return fail(PXB_EINVAL, "%s: need z or ktz", who);
     VoxMap m;
-    if (!make_map(K->batch, K->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     cudaStream_t s = (cudaStream_t)stream;
+    PxbTvCoef cf;
+    if (!ktz && z && p->hkind != PXB_DUAL_NONE && pxb_tv_fast_coefs(*K, cf)) {  // specialised 128-bit path
+        const int vec = K->dtype == PXB_F32 ? pick_vec<float>(K->shape[2], {xu, z, x_out, w}) : pick_vec<double>(K->shape[2], {xu, z, x_out, w});
+        if (!make_map_vec(K->batch, K->shape, vec, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
+        if (K->dtype == PXB_F32) {
+            if (K->ndir == 3) launch_tv_primal<float, 3>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
+            else if (K->ndir == 2) launch_tv_primal<float, 2>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
+            else launch_tv_primal<float, 1>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
+        } else {
+            if (K->ndir == 3) launch_tv_primal<double, 3>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
+            else if (K->ndir == 2) launch_tv_primal<double, 2>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
+            else launch_tv_primal<double, 1>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
+        }
+        PXB_CHECK_LAUNCH(who);
+        return 0;
+    }
+    if (!make_map(K->batch, K->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     if (K->dtype == PXB_F32)
         k_pds_primal<float><<<m.grid, kBlock, 0, s>>>(algo, *K, *p, m, (float*)xu, (const float*)z, (const float*)ktz, (float*)x_out, (float*)w, norms);
     else
@@ -461,8 +546,24 @@ int pxb_pds_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w,
     if (p->hkind == PXB_DUAL_NONE) return fail(PXB_EINVAL, "%s: h is null, nothing to do", who);
     if (!(p->sigma > 0)) return fail(PXB_EINVAL, "%s: sigma must be > 0", who);
     VoxMap m;
-    if (!make_map(K->batch, K->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     cudaStream_t s = (cudaStream_t)stream;
+    PxbTvCoef cf;
+    if (pxb_tv_fast_coefs(*K, cf)) {  // specialised 128-bit path
+        const int vec = K->dtype == PXB_F32 ? pick_vec<float>(K->shape[2], {w, z}) : pick_vec<double>(K->shape[2], {w, z});
+        if (!make_map_vec(K->batch, K->shape, vec, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
+        if (K->dtype == PXB_F32) {
+            if (K->ndir == 3) launch_tv_dual<float, 3>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
+            else if (K->ndir == 2) launch_tv_dual<float, 2>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
+            else launch_tv_dual<float, 1>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
+        } else {
+            if (K->ndir == 3) launch_tv_dual<double, 3>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
+            else if (K->ndir == 2) launch_tv_dual<double, 2>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
+            else launch_tv_dual<double, 1>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
+        }
+        PXB_CHECK_LAUNCH(who);
+        return 0;
+    }
+    if (!make_map(K->batch, K->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     if (K->dtype == PXB_F32) k_pds_dual<float><<<m.grid, kBlock, 0, s>>>(*K, *p, m, (const float*)w, (float*)z, norms);
     else k_pds_dual<double><<<m.grid, kBlock, 0, s>>>(*K, *p, m, (const double*)w, (double*)z, norms);
     PXB_CHECK_LAUNCH(who);

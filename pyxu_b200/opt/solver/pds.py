@@ -187,14 +187,14 @@ class _PrimalDualSplitting(Solver):
         return stop_crit_x & stop_crit_z if self._h._name != "NullFunc" else stop_crit_x
 
     def solution(self, which="primal"):
-        data, _ = self.stats()
+        logged = self._astate["log_var"]
         if which == "primal":
-            assert "x" in data.keys(), "Primal variable x was not logged (declare it in log_var to log it)."
+            assert "x" in logged, "Primal variable x was not logged (declare it in log_var to log it)."
         elif which == "dual":
-            assert "z" in data.keys(), "Dual variable z was not logged (declare it in log_var to log it)."
+            assert "z" in logged, "Dual variable z was not logged (declare it in log_var to log it)."
         else:
             raise ValueError(f"Parameter which must be one of ['primal', 'dual'] got: {which}.")
-        return data.get("x") if which == "primal" else data.get("z")
+        return self._logged("x" if which == "primal" else "z")  # only the requested variable leaves the device
 
     def objective_func(self):
         x = self._mstate["x"]

@@ -89,5 +89,4 @@ class PGD(Solver):
         return self._f.apply(x) + self._g.apply(x)
 
     def solution(self):
-        data, _ = self.stats()
-        return data.get("x")
+        return self._logged("x")

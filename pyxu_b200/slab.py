@@ -1,0 +1,251 @@
+"""
+z-slab domain decomposition of large 3-D volumes across the GPUs of one node.
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  The volume is cut along axis 0
+into `world` contiguous slabs; every rank stores its slab with `halo` ghost planes on each side:
+
+    component layout  (halo + n0_local + halo, n1, n2)      <- pointers handed to kernels address owned plane 0
+
+Per PD3O-TV iteration two planes cross each slab interface:
+    * before the primal half-step: the dual component along z, z_0, last owned plane  -> upper neighbour
+      (K^T z at a slab's first plane needs z_0 of the plane below),
+    * before the dual half-step:   w, first owned plane                              -> lower neighbour
+      (forward difference of w at a slab's last plane needs w of the plane above),
+through NCCL send/recv (`torch.distributed.batch_isend_irecv`).  The stopping-criterion norms of all
+ranks are combined by ONE all-reduce of a 4-double vector per evaluation.  Independent images of a
+batch need none of this: they are simply dealt out to the ranks (see `split_batch`).
+
+With `overlap=True` the exchange runs on a side stream while the interior planes are being computed: each
+half-step is issued as [interior planes] on the main stream and [boundary plane] after the halo arrived.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _array as A
+from . import _cabi as K
+
+
+def partition(n0, world):
+    """Balanced contiguous split of n0 planes into `world` slabs: list of (start, stop)."""
+    base, rem = divmod(int(n0), int(world))
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def split_batch(n_items, world):
+    """Independent images of a batch: contiguous shares, no communication."""
+    return partition(n_items, world)
+
+
+class HaloExchanger:
+    """Moves boundary planes between neighbouring slabs.  Works on any torch.distributed backend
+    (NCCL on GPUs; gloo on CPU tensors in the unit tests of the plumbing)."""
+
+    def __init__(self, rank=None, world=None, group=None, periodic=False):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.periodic = bool(periodic) and self.world > 1
+        self.lo = self.rank - 1 if self.rank > 0 else (self.world - 1 if self.periodic else None)
+        self.hi = self.rank + 1 if self.rank < self.world - 1 else (0 if self.periodic else None)
+
+    def exchange(self, buf, halo, n_owned, up=True, down=True):
+        """buf: (halo + n_owned + halo, n1, n2) tensor.
+        up:   my last `halo` owned planes  -> upper neighbour's lower ghost planes;
+        down: my first `halo` owned planes -> lower neighbour's upper ghost planes.
+        Returns the list of outstanding requests (call .wait() on each)."""
+        ops = []
+        h = halo
+        if up:
+            if self.hi is not None:
+                ops.append(dist.P2POp(dist.isend, buf[n_owned : n_owned + h], self.hi, self.group))
+            if self.lo is not None:
+                ops.append(dist.P2POp(dist.irecv, buf[0:h], self.lo, self.group))
+        if down:
+            if self.lo is not None:
+                ops.append(dist.P2POp(dist.isend, buf[h : 2 * h], self.lo, self.group))
+            if self.hi is not None:
+                ops.append(dist.P2POp(dist.irecv, buf[h + n_owned : 2 * h + n_owned], self.hi, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+
+class SlabPD3OTV:
+    """PD3O on  min 1/2||x - y||^2 + i_+(x) + lam*||grad x||_{2,1}  for a volume decomposed in z-slabs.
+
+    Same iteration as pyxu_b200.opt.solver.PD3O on the fused path (pxb_pds_primal + pxb_pds_dual), issued
+    per rank on its slab with `open_lo/open_hi` set where a neighbour exists.  Step sizes follow
+    PD3O._set_step_sizes for beta = 1 and the Gradient's Lipschitz bound.
+    """
+
+    HALO = 1
+
+    def __init__(self, shape, y_full=None, y_local=None, lam=0.08, positivity=True, dtype=torch.float32, mode="constant",
+                 rho=1.0, tau=None, sigma=None, group=None, overlap=True):
+        from .operator.linop.diff import Gradient
+
+        A.require_cuda()
+        assert len(shape) == 3
+        self.shape = tuple(int(s) for s in shape)
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.dev = A.current_device()
+        self.dtype = dtype
+        modes = (mode,) * 3 if isinstance(mode, str) else tuple(mode)
+        self.hx = HaloExchanger(self.rank, self.world, group, periodic=(modes[0] == "wrap"))
+        self.start, self.stop = partition(self.shape[0], self.world)[self.rank]
+        self.n0 = self.stop - self.start
+        n1, n2 = self.shape[1:]
+        self.plane = n1 * n2
+        self.local_voxels = self.n0 * self.plane
+        h = self.HALO
+        assert self.n0 >= 2 * h + 1, "slabs thinner than 3 planes are not supported"
+        self.K = Gradient(arg_shape=self.shape, mode=modes, dtype=A.np_dtype(dtype))
+        alloc = self.n0 + 2 * h
+
+        def field(ncomp=1):
+            return torch.zeros((ncomp, alloc, n1, n2), dtype=dtype, device=self.dev)
+
+        self.u, self.x, self.w, self.z = field(), field(), field(), field(3)
+        if y_local is None:
+            y_local = y_full.reshape(self.shape)[self.start : self.stop]
+        self.shift = (-y_local).to(dtype).contiguous()  # f = 1/2 ||x + shift||^2
+        own = slice(h, h + self.n0)
+        self.u[0, own].copy_(y_local)
+        self.x[0, own].copy_(y_local)
+        # step sizes: PD3O defaults (reference: pds.py:807-829, 849-864) for beta = 1
+        L = self.K.lipschitz
+        t = math.exp(min(0.5 * (math.log(0.99) - 2 * math.log(L)), 0.0))
+        self.tau = t if tau is None else tau
+        self.sigma = t if sigma is None else sigma
+        self.rho = rho
+        self.lam, self.positivity = lam, positivity
+        # Sub-range launches treat the cut as an open side, which is only exact when no boundary fold reaches across
+        # it: 'constant' (nothing folds) or 'wrap' (ring exchange: every side is open).  Other modes along z run
+        # whole-slab launches after the exchange.
+        self.overlap = bool(overlap) and self.world > 1 and modes[0] in ("constant", "wrap")
+        self.comm = torch.cuda.Stream(device=self.dev) if self.overlap else None
+        self.event_log = []   # (tag, cuda event) pairs, filled when `record_events`
+        self.record_events = True
+        # z0 = K x0 needs x0's upper ghost plane
+        self._wait(self.hx.exchange(self.x[0], h, self.n0, up=False, down=True))
+        d = self._desc(0, self.n0)
+        K.check(K.lib().pxb_gradient_apply(C.byref(d), self._p(self.x, 0, 0), self._p(self.z, 0, 0), A.stream()), "gradient_apply")
+        torch.cuda.synchronize()
+
+    # -- helpers ----------------------------------------------------------------------------------
+    @staticmethod
+    def _wait(reqs):
+        for r in reqs:
+            r.wait()
+
+    def _p(self, t, comp, plane):
+        """Device pointer to owned plane `plane` of component `comp`."""
+        h = self.HALO
+        return C.c_void_p(t.data_ptr() + t.element_size() * ((comp * t.shape[1] + h + plane) * self.plane))
+
+    def _desc(self, p0, p1):
+        """Gradient descriptor for owned planes [p0, p1) of this slab."""
+        h = self.HALO
+        open_lo = 1 if (p0 > 0 or self.hx.lo is not None) else 0
+        open_hi = 1 if (p1 < self.n0 or self.hx.hi is not None) else 0
+        slab = K.Slab(open_lo, open_hi, h, self.n0 + 2 * h)
+        return self.K._desc(1, A.dcode(self.u), slab=slab, shape0=p1 - p0)
+
+    def _params(self):
+        p = K.PdsParams()
+        p.tau, p.sigma, p.rho = self.tau, self.sigma, self.rho
+        p.g = K.ProxSpec(K.PROX_POS if self.positivity else K.PROX_NONE, 0, 0.0, 0.0)
+        f = K.FTerm()
+        f.kind, f.alpha = K.F_SQL2, 0.5
+        p.f = f
+        p.hkind, p.lam = K.DUAL_L21, self.lam
+        return p
+
+    def _primal(self, p0, p1, norms=None):
+        d, p = self._desc(p0, p1), self._params()
+        # the shift (= -y) is stored without ghost planes: address its plane p0 directly
+        p.f.shift = self.shift.data_ptr() + self.shift.element_size() * p0 * self.plane
+        p.f.shift_period = (self.n0 - p0) * self.plane
+        rc = K.lib().pxb_pds_primal(K.ALGO_PD3O, C.byref(d), C.byref(p), self._p(self.u, 0, p0), self._p(self.z, 0, p0), None,
+                                    self._p(self.x, 0, p0), self._p(self.w, 0, p0), A.ptr(norms), A.stream())
+        K.check(rc, "pxb_pds_primal")
+
+    def _dual(self, p0, p1, norms=None):
+        d, p = self._desc(p0, p1), self._params()
+        rc = K.lib().pxb_pds_dual(C.byref(d), C.byref(p), self._p(self.w, 0, p0), self._p(self.z, 0, p0), A.ptr(norms), A.stream())
+        K.check(rc, "pxb_pds_dual")
+
+    def _tick(self, tag):
+        if self.record_events:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.event_log.append((tag, ev))
+
+    # -- one PD3O iteration ------------------------------------------------------------------------
+    def step(self, want_norms=False):
+        h, n0 = self.HALO, self.n0
+        nx = nz = None
+        if want_norms:  # kernels accumulate into (rows, 2) buffers
+            nx = torch.zeros((1, 2), dtype=torch.float64, device=self.dev)
+            nz = torch.zeros((1, 2), dtype=torch.float64, device=self.dev)
+        main = torch.cuda.current_stream()
+        if not self.overlap:
+            if self.world > 1:
+                self._wait(self.hx.exchange(self.z[0], h, n0, up=True, down=False))
+            self._tick("primal_begin")
+            self._primal(0, n0, nx)
+            self._tick("primal_end")
+            if self.world > 1:
+                self._wait(self.hx.exchange(self.w[0], h, n0, up=False, down=True))
+            self._dual(0, n0, nz)
+            self._tick("dual_end")
+        else:
+            comm = self.comm
+            # (1) z_0 ghost plane travels while planes [1, n0) take their primal half-step
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):
+                self._wait(self.hx.exchange(self.z[0], h, n0, up=True, down=False))
+            self._tick("primal_begin")
+            self._primal(1, n0, nx)
+            main.wait_stream(comm)
+            self._primal(0, 1, nx)
+            self._tick("primal_end")
+            # (2) w's first plane travels while planes [0, n0-1) take their dual half-step
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):
+                self._wait(self.hx.exchange(self.w[0], h, n0, up=False, down=True))
+            self._dual(0, n0 - 1, nz)
+            main.wait_stream(comm)
+            self._dual(n0 - 1, n0, nz)
+            self._tick("dual_end")
+        if want_norms:
+            v = torch.cat([nx.reshape(-1), nz.reshape(-1)])
+            dist.all_reduce(v, group=self.group)  # the single fused scalar all-reduce of the stopping criterion
+            return v.cpu().numpy()
+        return None
+
+    def rel_errors(self, v):
+        """(RelError[x], RelError[z]) from the all-reduced norm vector returned by step(want_norms=True)."""
+        import numpy as np
+
+        with np.errstate(all="ignore"):
+            rx, rz = np.sqrt(v[0]) / np.sqrt(v[1]), np.sqrt(v[2]) / np.sqrt(v[3])
+        return float(np.nan_to_num(rx)), float(np.nan_to_num(rz))
+
+    def gather_x(self):
+        """Full primal iterate on every rank (tests / small volumes only)."""
+        h = self.HALO
+        parts = partition(self.shape[0], self.world)
+        nmax = max(b - a for a, b in parts)
+        mine = torch.zeros((nmax, *self.shape[1:]), dtype=self.dtype, device=self.dev)
+        mine[: self.n0].copy_(self.x[0, h : h + self.n0])
+        bufs = [torch.empty_like(mine) for _ in parts]
+        dist.all_gather(bufs, mine, group=self.group)
+        return torch.cat([b_[: e - a] for b_, (a, e) in zip(bufs, parts)], dim=0)

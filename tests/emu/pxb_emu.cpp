@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "../../pyxu_b200/csrc/pxb_core.cuh"
+#include "../../pyxu_b200/csrc/pxb_tv_fast.cuh"
 
 #define FOR_VOX(batch, g)                              \
     for (int64_t b = 0; b < (batch); ++b)              \
@@ -50,7 +51,50 @@ static void t_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* 
     }
 }
 
+// fast (vectorised) TV bodies: loop over vectors of VEC voxels exactly like the CUDA thread map does
+template <class T, int NDIR, int VEC>
+static void t_tv(int which, int algo, const pxb_grad_desc* K, const PxbTvCoef& cf, const pxb_pds_params* p, void* xu, const void* z,
+                 void* x_out, void* w, double* norms) {
+    const PxbGeom g = pxb_geom(K->shape);
+    for (int64_t b = 0; b < K->batch; ++b)
+        for (int i0 = 0; i0 < g.n0; ++i0)
+            for (int i1 = 0; i1 < g.n1; ++i1)
+                for (int i2 = 0; i2 < g.n2; i2 += VEC) {
+                    double a0 = 0, a1 = 0;
+                    if (which == 0)
+                        pxb_tv_primal_vec<T, NDIR, VEC>(algo, *K, g, cf, *p, (T*)xu, (const T*)z, (T*)x_out, (T*)w, norms != nullptr, a0, a1, b, i0, i1, i2);
+                    else
+                        pxb_tv_dual_vec<T, NDIR, VEC>(*K, g, cf, *p, (const T*)w, (T*)z, norms != nullptr, a0, a1, b, i0, i1, i2);
+                    if (norms) { norms[2 * b] += a0; norms[2 * b + 1] += a1; }
+                }
+}
+template <class T, int NDIR>
+static int t_tv_vec(int vec, int which, int algo, const pxb_grad_desc* K, const PxbTvCoef& cf, const pxb_pds_params* p, void* xu,
+                    const void* z, void* x_out, void* w, double* norms) {
+    if (K->shape[2] % vec) return -1;
+    if (vec == 4) t_tv<T, NDIR, 4>(which, algo, K, cf, p, xu, z, x_out, w, norms);
+    else if (vec == 2) t_tv<T, NDIR, 2>(which, algo, K, cf, p, xu, z, x_out, w, norms);
+    else if (vec == 1) t_tv<T, NDIR, 1>(which, algo, K, cf, p, xu, z, x_out, w, norms);
+    else return -1;
+    return 0;
+}
+template <class T>
+static int t_tv_dir(int vec, int which, int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu, const void* z, void* x_out,
+                    void* w, double* norms) {
+    PxbTvCoef cf;
+    if (!pxb_tv_fast_coefs(*K, cf)) return -2;
+    if (K->ndir == 3) return t_tv_vec<T, 3>(vec, which, algo, K, cf, p, xu, z, x_out, w, norms);
+    if (K->ndir == 2) return t_tv_vec<T, 2>(vec, which, algo, K, cf, p, xu, z, x_out, w, norms);
+    return t_tv_vec<T, 1>(vec, which, algo, K, cf, p, xu, z, x_out, w, norms);
+}
+
 extern "C" {
+// which: 0 primal, 1 dual.  Returns -2 when the descriptor is not eligible for the fast bodies.
+int emu_tv_fast(int vec, int which, int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu, const void* z, void* x_out,
+                void* w, double* norms) {
+    if (K->dtype == PXB_F32) return t_tv_dir<float>(vec, which, algo, K, p, xu, z, x_out, w, norms);
+    return t_tv_dir<double>(vec, which, algo, K, p, xu, z, x_out, w, norms);
+}
 int emu_stencil(const pxb_stencil_desc* d, int adjoint, const void* in, void* out) {
     if (d->dtype == PXB_F32) t_stencil<float>(d, adjoint, in, out); else t_stencil<double>(d, adjoint, in, out);
     return 0;

@@ -1,0 +1,64 @@
+"""torchrun worker: z-slab PD3O-TV on WORLD_SIZE GPUs must reproduce the single-GPU PD3O solver.
+Usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/slab_worker.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import pyxu_b200.operator as pxo
+    import pyxu_b200.opt.solver as pxs
+    import pyxu_b200.opt.stop as pxst
+    from pyxu_b200.slab import SlabPD3OTV
+
+    ok = True
+    for shape, mode, overlap, dtype, tol in [((37, 24, 32), "constant", True, torch.float64, 1e-13),
+                                             ((37, 24, 32), "constant", False, torch.float64, 1e-13),
+                                             ((40, 20, 28), ("reflect", "wrap", "edge"), True, torch.float64, 1e-13),
+                                             ((32, 16, 24), "wrap", True, torch.float64, 1e-13),
+                                             ((64, 48, 64), "constant", True, torch.float32, 1e-5)]:
+        n_iter, lam = 25, 0.08
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        y = torch.rand(shape, device="cuda", dtype=dtype, generator=gen)
+        slab = SlabPD3OTV(shape, y_full=y, lam=lam, positivity=True, dtype=dtype, mode=mode, overlap=overlap, rho=1.2)
+        v = None
+        for _ in range(n_iter):
+            v = slab.step(want_norms=True)
+        x_slab = slab.gather_x().reshape(-1)
+        # single-GPU reference through the public solver, same step sizes
+        N = int(np.prod(shape))
+        f = 0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y.reshape(-1))
+        Kop = pxo.Gradient(arg_shape=shape, mode=mode, dtype=np.float64 if dtype == torch.float64 else np.float32)
+        h = lam * pxo.L21Norm(arg_shape=(3, *shape), l2_axis=(0,))
+        slv = pxs.PD3O(f=f, g=pxo.PositiveOrthant(dim=N), h=h, K=Kop, show_progress=False, final_writeback=False)
+        sc = pxst.MaxIter(n_iter) | pxst.RelError(eps=1e-30, var="x") | pxst.RelError(eps=1e-30, var="z")
+        slv.fit(x0=y.reshape(-1), stop_crit=sc, tau=slab.tau, sigma=slab.sigma, rho=1.2)
+        assert slv._astate.get("error") is None, slv._astate.get("error")
+        x_ref = slv._mstate["x"]
+        err = float((x_slab - x_ref).norm() / x_ref.norm())
+        _, hist = slv.stats()
+        rx, rz = slab.rel_errors(v)
+        e_rx = abs(rx - float(hist[-1]["RelError[x]"])) / max(rx, 1e-300)
+        e_rz = abs(rz - float(hist[-1]["RelError[z]"])) / max(rz, 1e-300)
+        good = err < tol and e_rx < 1e-6 and e_rz < 1e-6
+        ok &= good
+        if rank == 0:
+            print(f"[slab] world={world} shape={shape} mode={mode} overlap={slab.overlap} {dtype}: rel.err={err:.2e} "
+                  f"relerr-norms dev=({e_rx:.1e},{e_rz:.1e}) {'OK' if good else 'FAIL'}", flush=True)
+    t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

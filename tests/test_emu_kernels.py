@@ -71,7 +71,8 @@ def test_adjoint_is_transpose_random_modes():
         assert abs(lhs - rhs) < 1e-10 * (1 + abs(lhs)), (shape, modes, ks, cen)
 
 
-def _fused_run(name, algo, shape, n_iter, lam, gspec, y, x0, mode="constant", dtype=np.float64):
+def _fused_run(name, algo, shape, n_iter, lam, gspec, y, x0, mode="constant", dtype=np.float64, vec=0):
+    """vec = 0: generic per-voxel bodies; vec in {1, 2, 4}: vectorised fast bodies (pxb_tv_fast.cuh)."""
     g = golden("solvers.npz")
     tau, sigma, rho = (float(g[f"{name}/{k}"]) for k in ("tau", "sigma", "rho"))
     Kop = pxo.Gradient(arg_shape=shape, mode=mode)
@@ -86,11 +87,13 @@ def _fused_run(name, algo, shape, n_iter, lam, gspec, y, x0, mode="constant", dt
     for _ in range(n_iter):
         nx[:] = 0
         nz[:] = 0
-        if algo == K.ALGO_PD3O:
-            E.lib().emu_pds_primal(algo, C.byref(d), C.byref(P), E.p(u), E.p(z), None, E.p(x), E.p(w), E.p(nx))
+        xu, xo = (u, x) if algo == K.ALGO_PD3O else (x, None)
+        if vec:
+            assert E.lib().emu_tv_fast(vec, 0, algo, C.byref(d), C.byref(P), E.p(xu), E.p(z), E.p(xo), E.p(w), E.p(nx)) == 0
+            assert E.lib().emu_tv_fast(vec, 1, algo, C.byref(d), C.byref(P), None, E.p(z), None, E.p(w), E.p(nz)) == 0
         else:
-            E.lib().emu_pds_primal(algo, C.byref(d), C.byref(P), E.p(x), E.p(z), None, None, E.p(w), E.p(nx))
-        E.lib().emu_pds_dual(C.byref(d), C.byref(P), E.p(w), E.p(z), E.p(nz))
+            E.lib().emu_pds_primal(algo, C.byref(d), C.byref(P), E.p(xu), E.p(z), None, E.p(xo), E.p(w), E.p(nx))
+            E.lib().emu_pds_dual(C.byref(d), C.byref(P), E.p(w), E.p(z), E.p(nz))
     return x, z, nx, nz, g
 
 
@@ -178,3 +181,63 @@ def test_funcs_bodies():
         z = x.copy()
         lib.emu_dual_update(K.F64, K.DUAL_L1, 3, 1, 60, 1.0, tau, 1.0, E.p(z), E.p(tt), None)
         assert relerr(z, g[f"l1/fprox/{t}"]) < 1e-14
+
+
+# ---- vectorised fast bodies (what the B200 runs for first-order-FD TV problems) ------------------------
+@pytest.mark.parametrize("vec", [1, 2, 4])
+@pytest.mark.parametrize("mode", ["constant", "reflect", "wrap", "symmetric", "edge"])
+def test_fast_bodies_pd3o_2d_all_modes(vec, mode):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    if mode == "constant":
+        name, lam, gspec, x0, it = "pd3o_tv2d/s3", 0.1, POS, y.reshape(-1), 60
+    else:
+        name, lam, gspec, x0, it = f"pd3o_tv2d/{mode}", 0.15, NONE, np.zeros(y.size), 40
+    x, z, nx, nz, _ = _fused_run(name, K.ALGO_PD3O, (32, 40), it, lam, gspec, y, x0, mode=mode, vec=vec)
+    assert relerr(x, g[f"{name}/x"]) < 1e-10 and relerr(z, g[f"{name}/z"]) < 1e-10
+    # identical to the generic bodies up to rounding, including the fused norms
+    x2, z2, nx2, nz2, _ = _fused_run(name, K.ALGO_PD3O, (32, 40), it, lam, gspec, y, x0, mode=mode, vec=0)
+    assert relerr(x, x2) < 1e-13 and relerr(z, z2) < 1e-13
+    assert np.allclose(nx, nx2, rtol=1e-9, atol=1e-30) and np.allclose(nz, nz2, rtol=1e-9, atol=1e-30)
+
+
+@pytest.mark.parametrize("vec", [1, 2])
+def test_fast_bodies_3d_and_cv(vec):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv3d/y"]
+    x, z, *_ = _fused_run("pd3o_tv3d", K.ALGO_PD3O, (10, 12, 14), 50, 0.08, POS, y, y.reshape(-1), vec=vec)
+    assert relerr(x, g["pd3o_tv3d/x"]) < 1e-10 and relerr(z, g["pd3o_tv3d/z"]) < 1e-10
+    x, z, *_ = _fused_run("pd3o_tv3d/mixed", K.ALGO_PD3O, (10, 12, 14), 30, 0.08, POS, y, y.reshape(-1),
+                          mode=("reflect", "wrap", "constant"), vec=vec)
+    assert relerr(x, g["pd3o_tv3d/mixed/x"]) < 1e-10 and relerr(z, g["pd3o_tv3d/mixed/z"]) < 1e-10
+    y2 = g["pd3o_tv2d/y"]
+    x, z, *_ = _fused_run("cv_tv2d", K.ALGO_CV, (32, 40), 60, 0.1, POS, y2, y2.reshape(-1), vec=2 * vec)
+    assert relerr(x, g["cv_tv2d/x"]) < 1e-10 and relerr(z, g["cv_tv2d/z"]) < 1e-10
+
+
+@pytest.mark.parametrize("scheme", ["backward", "central"])
+def test_fast_bodies_other_schemes_equal_generic(scheme):
+    """backward / central differences (taps at -1 / +-1) under every mode: fast == generic bodies."""
+    rng = np.random.default_rng(2)
+    shape = (6, 8, 12)
+    for mode in ("constant", ("reflect", "symmetric", "wrap"), "edge"):
+        Kop = pxo.Gradient(arg_shape=shape, mode=mode, scheme=scheme, sampling=(1.0, 0.5, 2.0))
+        d = Kop._desc(1, K.F64)
+        shift = rng.standard_normal(Kop.dim)
+        P = E.pds_params(0.21, 0.19, 1.2, gspec=(K.PROX_L1, 0.05, 0.0), fkind=K.F_SQL2, alpha=0.7, shift=shift, hkind=K.DUAL_L1, lam=0.3)
+        outs = []
+        for vec in (0, 1, 2, 4):
+            r = np.random.default_rng(3)
+            u, x, w = r.standard_normal(Kop.dim), r.standard_normal(Kop.dim), np.zeros(Kop.dim)
+            z = r.standard_normal(Kop.codim)
+            for _ in range(3):
+                if vec:
+                    assert E.lib().emu_tv_fast(vec, 0, K.ALGO_PD3O, C.byref(d), C.byref(P), E.p(u), E.p(z), E.p(x), E.p(w), None) == 0
+                    assert E.lib().emu_tv_fast(vec, 1, 0, C.byref(d), C.byref(P), None, E.p(z), None, E.p(w), None) == 0
+                else:
+                    E.lib().emu_pds_primal(K.ALGO_PD3O, C.byref(d), C.byref(P), E.p(u), E.p(z), None, E.p(x), E.p(w), None)
+                    E.lib().emu_pds_dual(C.byref(d), C.byref(P), E.p(w), E.p(z), None)
+            outs.append((u.copy(), x.copy(), z.copy()))
+        for o in outs[1:]:
+            for a, b in zip(o, outs[0]):
+                assert relerr(a, b) < 1e-13, (scheme, mode)

@@ -1,0 +1,207 @@
+"""
+CPU coverage of the multi-GPU path:
+ (1) kernel-side slab semantics (open sides, ghost planes, sub-range launches) -- the kernel bodies compiled
+     for the host (tests/emu) run a z-slab-decomposed PD3O-TV iteration with the halo exchange done in NumPy,
+     and must reproduce the single-domain iterates bit for bit;
+ (2) host-side plumbing -- partition() and HaloExchanger over torch.distributed (gloo, world_size 2 and 3).
+"""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import emu_util as E
+import pyxu_b200.operator as pxo
+from pyxu_b200 import _cabi as K
+from pyxu_b200.slab import HaloExchanger, partition
+
+
+def test_partition():
+    assert partition(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert partition(1024, 8)[-1] == (896, 1024)
+    for n, w in ((17, 4), (5, 5), (100, 7)):
+        p = partition(n, w)
+        assert p[0][0] == 0 and p[-1][1] == n and all(a[1] == b[0] for a, b in zip(p, p[1:]))
+        assert max(e - s for s, e in p) - min(e - s for s, e in p) <= 1
+
+
+def _single_domain(shape, y, mode, n_iter, tau, sigma, rho, lam):
+    Kop = pxo.Gradient(arg_shape=shape, mode=mode)
+    shift = np.ascontiguousarray(-y.reshape(-1))
+    P = E.pds_params(tau, sigma, rho, gspec=(K.PROX_POS, 0, 0), fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L21, lam=lam)
+    d = Kop._desc(1, K.F64)
+    x = y.reshape(-1).copy()
+    z = E.gradient_run(Kop, x, False)
+    u, w = x.copy(), np.empty_like(x)
+    for _ in range(n_iter):
+        E.lib().emu_pds_primal(K.ALGO_PD3O, C.byref(d), C.byref(P), E.p(u), E.p(z), None, E.p(x), E.p(w), None)
+        E.lib().emu_pds_dual(C.byref(d), C.byref(P), E.p(w), E.p(z), None)
+    return x.reshape(shape), z.reshape((3,) + shape)
+
+
+class _Rank:
+    """One simulated rank: same buffer layout / descriptors as pyxu_b200.slab.SlabPD3OTV."""
+
+    H = 1
+
+    def __init__(self, shape, y, a, b, rank, world, mode, periodic):
+        self.n0, self.plane = b - a, shape[1] * shape[2]
+        self.a, self.b, self.rank, self.world = a, b, rank, world
+        alloc = self.n0 + 2 * self.H
+        self.K = pxo.Gradient(arg_shape=shape, mode=mode)
+        self.has_lo = rank > 0 or periodic
+        self.has_hi = rank < world - 1 or periodic
+        f = lambda c=1: np.zeros((c, alloc) + shape[1:])
+        self.u, self.x, self.w, self.z = f(), f(), f(), f(3)
+        self.shift = np.ascontiguousarray(-y[a:b])
+        self.u[0, 1:-1] = y[a:b]
+        self.x[0, 1:-1] = y[a:b]
+
+    def ptr(self, t, comp, plane):
+        return C.c_void_p(t.ctypes.data + 8 * ((comp * t.shape[1] + self.H + plane) * self.plane))
+
+    def desc(self, p0, p1):
+        lo = 1 if (p0 > 0 or self.has_lo) else 0
+        hi = 1 if (p1 < self.n0 or self.has_hi) else 0
+        return self.K._desc(1, K.F64, slab=K.Slab(lo, hi, self.H, self.n0 + 2 * self.H), shape0=p1 - p0)
+
+    def params(self, tau, sigma, rho, lam, p0):
+        P = E.pds_params(tau, sigma, rho, gspec=(K.PROX_POS, 0, 0), fkind=K.F_SQL2, alpha=0.5, hkind=K.DUAL_L21, lam=lam)
+        P.f.shift = self.shift.ctypes.data + 8 * p0 * self.plane
+        P.f.shift_period = (self.n0 - p0) * self.plane
+        return P
+
+    fast = 0  # 0: generic bodies; 1: vectorised fast bodies (VEC=1; the shape's row length is odd)
+
+    def primal(self, p0, p1, prm):
+        d, P = self.desc(p0, p1), self.params(*prm, p0)
+        a = (self.ptr(self.u, 0, p0), self.ptr(self.z, 0, p0))
+        b = (self.ptr(self.x, 0, p0), self.ptr(self.w, 0, p0))
+        if self.fast:
+            assert E.lib().emu_tv_fast(self.fast, 0, K.ALGO_PD3O, C.byref(d), C.byref(P), *a, *b, None) == 0
+        else:
+            E.lib().emu_pds_primal(K.ALGO_PD3O, C.byref(d), C.byref(P), *a, None, *b, None)
+
+    def dual(self, p0, p1, prm):
+        d, P = self.desc(p0, p1), self.params(*prm, p0)
+        if self.fast:
+            assert E.lib().emu_tv_fast(self.fast, 1, 0, C.byref(d), C.byref(P), None, self.ptr(self.z, 0, p0), None, self.ptr(self.w, 0, p0), None) == 0
+        else:
+            E.lib().emu_pds_dual(C.byref(d), C.byref(P), self.ptr(self.w, 0, p0), self.ptr(self.z, 0, p0), None)
+
+
+def _exchange(ranks, name, comp, up, down, periodic):
+    W = len(ranks)
+    for r, rk in enumerate(ranks):
+        arr = getattr(rk, name)[comp]
+        if up:
+            dst = r + 1 if r + 1 < W else (0 if periodic else None)
+            if dst is not None:
+                getattr(ranks[dst], name)[comp][0] = arr[rk.n0]  # last owned plane -> lower ghost
+        if down:
+            dst = r - 1 if r > 0 else (W - 1 if periodic else None)
+            if dst is not None:
+                getattr(ranks[dst], name)[comp][-1] = arr[1]  # first owned plane -> upper ghost
+
+
+@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("mode,subrange", [("constant", True), ("constant", False), ("wrap", True),
+                                           (("reflect", "wrap", "symmetric"), False), (("edge", "constant", "reflect"), False)])
+def test_slab_decomposed_iteration_equals_single_domain(world, mode, subrange, fast):
+    shape, n_iter, lam = (11, 6, 7), 12, 0.08
+    tau = sigma = 0.28
+    rho = 1.3
+    y = np.random.default_rng(0).random(shape)
+    x_ref, z_ref = _single_domain(shape, y, mode, n_iter, tau, sigma, rho, lam)
+
+    periodic = (mode if isinstance(mode, str) else mode[0]) == "wrap"
+    parts = partition(shape[0], world)
+    ranks = [_Rank(shape, y, a, b, r, world, mode, periodic) for r, (a, b) in enumerate(parts)]
+    for rk in ranks:
+        rk.fast = fast
+    prm = (tau, sigma, rho, lam)
+    _exchange(ranks, "x", 0, False, True, periodic)
+    for rk in ranks:  # z0 = K x0
+        d = rk.desc(0, rk.n0)
+        E.lib().emu_gradient(C.byref(d), 0, rk.ptr(rk.x, 0, 0), rk.ptr(rk.z, 0, 0))
+    for _ in range(n_iter):
+        _exchange(ranks, "z", 0, True, False, periodic)
+        for rk in ranks:
+            if subrange:  # interior first, boundary plane after "the halo arrived" (same order as SlabPD3OTV.step)
+                rk.primal(1, rk.n0, prm)
+                rk.primal(0, 1, prm)
+            else:
+                rk.primal(0, rk.n0, prm)
+        _exchange(ranks, "w", 0, False, True, periodic)
+        for rk in ranks:
+            if subrange:
+                rk.dual(0, rk.n0 - 1, prm)
+                rk.dual(rk.n0 - 1, rk.n0, prm)
+            else:
+                rk.dual(0, rk.n0, prm)
+    x = np.concatenate([rk.x[0, 1:-1] for rk in ranks], axis=0)
+    z = np.concatenate([rk.z[:, 1:-1] for rk in ranks], axis=1)
+    if fast:  # fast bodies sum the taps in the same order: equal up to FMA contraction
+        assert np.allclose(x, x_ref, rtol=1e-13, atol=1e-15) and np.allclose(z, z_ref, rtol=1e-13, atol=1e-15)
+    else:
+        assert np.array_equal(x, x_ref) and np.array_equal(z, z_ref)
+
+
+# ---- torch.distributed plumbing over gloo --------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, periodic, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n0s = [e - s for s, e in partition(11, world)]
+        n0, h = n0s[rank], 1
+        buf = torch.full((n0 + 2 * h, 3, 4), -1.0, dtype=torch.float64)
+        buf[h : h + n0] = torch.arange(n0, dtype=torch.float64).reshape(-1, 1, 1) + 100 * rank
+        hx = HaloExchanger(periodic=periodic)
+        for r in hx.exchange(buf, h, n0, up=True, down=True):
+            r.wait()
+        lo = rank - 1 if rank > 0 else (world - 1 if periodic else None)
+        hi = rank + 1 if rank < world - 1 else (0 if periodic else None)
+        ok = True
+        ok &= bool((buf[0] == (-1.0 if lo is None else 100 * lo + n0s[lo] - 1)).all())
+        ok &= bool((buf[-1] == (-1.0 if hi is None else 100 * hi)).all())
+        ok &= bool((buf[h] == 100 * rank).all())  # owned planes untouched
+        # one-directional exchange leaves the other ghost alone
+        buf[0], buf[-1] = -2.0, -2.0
+        for r in hx.exchange(buf, h, n0, up=False, down=True):
+            r.wait()
+        ok &= bool((buf[0] == -2.0).all()) and bool((buf[-1] == (-2.0 if hi is None else 100 * hi)).all())
+        # the stopping criterion's single fused all-reduce
+        v = torch.tensor([1.0 + rank, 2.0, 3.0, 4.0 * rank], dtype=torch.float64)
+        dist.all_reduce(v)
+        ok &= bool(torch.allclose(v, torch.tensor([world * (world + 1) / 2, 2.0 * world, 3.0 * world, 2.0 * world * (world - 1)], dtype=torch.float64)))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,periodic", [(2, False), (3, False), (3, True)])
+def test_halo_exchanger_gloo(world, periodic):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, periodic, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]
