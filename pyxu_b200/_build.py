@@ -17,8 +17,7 @@ LIB = os.path.join(LIBDIR, "libpyxu_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-    "--cudart", "static",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -39,10 +38,26 @@ def _nvcc():
 def build_cuda(force=False, verbose=False):
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [os.path.join(ROOT, "include", "pyxu_b200.h")]
-    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
     if force or _newer(LIB, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *srcs]
-        subprocess.run(cmd, check=True, cwd=CSRC)
+        from concurrent.futures import ThreadPoolExecutor
+
+        nvcc = _nvcc()
+
+        def compile_one(src):  # one translation unit -> one object, all units in parallel
+            obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+            cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", obj, src]
+            r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+            if verbose:
+                print(r.stderr)
+            return obj
+
+        with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+            objs = list(ex.map(compile_one, srcs))
+        subprocess.run([nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs], check=True)
     return LIB
 
 

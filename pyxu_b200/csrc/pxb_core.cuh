@@ -293,26 +293,25 @@ PXB_HD T pxb_prox_eval(int kind, T p0, T p1, T v, T tau) {
     }
 }
 
-// prox_{sigma h*}(p) for one l2-group p[0..G) (G <= PXB_MAX_DIRS here), h = lam*L21 | lam*L1, following
-// the reference's order of operations: Moreau identity (abc/operator.py:940-944) around
-// L21Norm.prox (norm.py:352-364) / L1Norm.prox with tau' = lam/sigma (ScaleRule, arithmetic.py:182).
+// prox_{sigma h*}(p) for one l2-group p[0..G), h = lam*L21 | lam*L1.
+// Reference: Moreau identity (abc/operator.py:940-944)  p - sigma * prox_{h/sigma}(p / sigma)  around
+// L21Norm.prox (norm.py:352-364) / L1Norm.prox (norm.py:47-52) with tau' = lam/sigma (ScaleRule).  Substituting,
+//   L21:  p - sigma*(p/sigma)*(1 - (lam/sigma)/max(||p||/sigma, lam/sigma))  ==  p * lam / max(||p||, lam)
+//   L1 :  p - sigma*soft(p/sigma, lam/sigma)                                 ==  clip(p, -lam, lam)
+// i.e. the projections onto the dual balls; evaluated in this closed form (one sqrt + one division per group
+// instead of 2G+2 divisions: the unfused arithmetic made the kernels issue-bound).  The results differ from the
+// reference's operation order by a few ulps, far inside the 1e-10 / 1e-4 parity tolerance.
 template <class T>
 PXB_HD void pxb_dual_prox_group(int kind, int G, T lam, T sigma, T* p) {
-    const T tp = (T(1) / sigma) * lam;
+    (void)sigma;
     if (kind == PXB_DUAL_L21) {
-        T a[PXB_MAX_DIRS];
         T nn = T(0);
-        for (int k = 0; k < G; ++k) { a[k] = p[k] / sigma; nn += a[k] * a[k]; }
+        for (int k = 0; k < G; ++k) nn += p[k] * p[k];
         const T nrm = sqrt(nn);
-        const T sc = T(1) - tp / (nrm > tp ? nrm : tp);
-        for (int k = 0; k < G; ++k) p[k] = p[k] - sigma * (a[k] * sc);
+        const T sc = lam / (nrm > lam ? nrm : lam);
+        for (int k = 0; k < G; ++k) p[k] = p[k] * sc;
     } else if (kind == PXB_DUAL_L1) {
-        for (int k = 0; k < G; ++k) {
-            const T a = p[k] / sigma;
-            const T m = fabs(a) - tp;
-            const T s = m > T(0) ? (a < T(0) ? -m : m) : T(0);
-            p[k] = p[k] - sigma * s;
-        }
+        for (int k = 0; k < G; ++k) p[k] = p[k] < -lam ? -lam : (p[k] > lam ? lam : p[k]);
     }
 }
 
@@ -432,32 +431,28 @@ PXB_HD void pxb_body_dual(const pxb_grad_desc& d, const PxbGeom& g, const pxb_pd
     }
 }
 
-// dual update from a precomputed t = K w, arbitrary group size (outer, group, inner).
+// dual update from a precomputed t = K w, arbitrary group size (outer, group, inner); same closed forms as above.
 template <class T>
 PXB_HD void pxb_body_dual_update(int kind, int64_t group, int64_t inner, T lam, T sigma, T rho, T* __restrict__ z,
                                  const T* __restrict__ t, bool want_norms, double& n0, double& n1, int64_t o, int64_t i) {
     const int64_t base = o * group * inner + i;
-    const T tp = (T(1) / sigma) * lam;
-    T sc = T(0);
+    T sc = T(1);
     if (kind == PXB_DUAL_L21) {
         T nn = T(0);
         for (int64_t k = 0; k < group; ++k) {
-            const T a = (z[base + k * inner] + sigma * t[base + k * inner]) / sigma;
-            nn += a * a;
+            const T p = z[base + k * inner] + sigma * t[base + k * inner];
+            nn += p * p;
         }
         const T nrm = sqrt(nn);
-        sc = T(1) - tp / (nrm > tp ? nrm : tp);
+        sc = lam / (nrm > lam ? nrm : lam);
     }
     for (int64_t k = 0; k < group; ++k) {
         const T zo = z[base + k * inner];
         const T p = zo + sigma * t[base + k * inner];
-        const T a = p / sigma;
         T pr;
-        if (kind == PXB_DUAL_L21) pr = p - sigma * (a * sc);
-        else if (kind == PXB_DUAL_L1) {
-            const T m = fabs(a) - tp;
-            pr = p - sigma * (m > T(0) ? (a < T(0) ? -m : m) : T(0));
-        } else pr = p;
+        if (kind == PXB_DUAL_L21) pr = p * sc;
+        else if (kind == PXB_DUAL_L1) pr = p < -lam ? -lam : (p > lam ? lam : p);
+        else pr = p;
         const T zn = (T(1) - rho) * zo + rho * pr;
         if (want_norms) {
             const double dd = (double)zn - (double)zo;

@@ -5,24 +5,19 @@
 // neighbour taps served by L1/L2 (a z-plane of 1024^2 fp32 is 4 MiB, the L2 is 126 MB), grid sized
 // from the volume, fp64 accumulation of the stopping-criterion norms with one atomic per block.
 // Tensor cores are deliberately unused: nothing here is a dense contraction.
-#include <cuda_runtime.h>
-
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
 
-#include <initializer_list>
-
-#include "pxb_core.cuh"
-#include "pxb_tv_fast.cuh"
+#include "pxb_launch.cuh"
 
 namespace {
-
 thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
+}  // namespace
 
-int fail(int code, const char* fmt, ...) {
+int pxb_fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -31,105 +26,10 @@ int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
+void pxb_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+#define fail pxb_fail
 
-#define PXB_CHECK_LAUNCH(name)                                                         \
-    do {                                                                               \
-        g_launches.fetch_add(1, std::memory_order_relaxed);                            \
-        cudaError_t e_ = cudaGetLastError();                                           \
-        if (e_ != cudaSuccess) return fail(PXB_ECUDA, "%s: %s", name, cudaGetErrorString(e_)); \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------
-// Thread -> voxel mapping.  A block is TX x TY threads: TX consecutive samples of a row (axis 2,
-// unit stride => coalesced) times TY rows.  Rows are the flattened (batch, i0, i1) index.
-// ------------------------------------------------------------------------------------------
-constexpr int kBlock = 256;
-
-struct VoxMap {
-    int tx_log2;      // TX = 1 << tx_log2
-    int nxt;          // x-tiles per row
-    int64_t rows;     // batch * n0 * n1
-    int n0, n1, n2;
-    unsigned grid;
-};
-
-inline bool make_map(int64_t batch, const int64_t shape[3], VoxMap& m) {
-    m.n0 = (int)shape[0]; m.n1 = (int)shape[1]; m.n2 = (int)shape[2];
-    int l = 5;  // TX in [32, 256]: a warp never straddles rows
-    while ((1 << l) < m.n2 && l < 8) ++l;
-    m.tx_log2 = l;
-    const int TX = 1 << l, TY = kBlock / TX;
-    m.nxt = (m.n2 + TX - 1) / TX;
-    m.rows = batch * shape[0] * shape[1];
-    const int64_t nblk = (int64_t)m.nxt * ((m.rows + TY - 1) / TY);
-    if (nblk <= 0 || nblk > 0x7fffffffLL) return false;
-    m.grid = (unsigned)nblk;
-    return true;
-}
-
-struct Vox {
-    int64_t b;
-    int i0, i1, i2;
-    bool ok;
-};
-
-__device__ __forceinline__ Vox vox_of_thread(const VoxMap& m) {
-    const int TX = 1 << m.tx_log2;
-    const int tx = threadIdx.x & (TX - 1), ty = threadIdx.x >> m.tx_log2;
-    const unsigned bx = blockIdx.x % (unsigned)m.nxt, by = blockIdx.x / (unsigned)m.nxt;
-    Vox v;
-    v.i2 = (int)bx * TX + tx;
-    const int64_t r = (int64_t)by * (kBlock >> m.tx_log2) + ty;
-    v.ok = (v.i2 < m.n2) && (r < m.rows);
-    if (m.rows <= 0xffffffffLL) {  // 32-bit divisions on the common path
-        const unsigned r32 = (unsigned)r, n1 = (unsigned)m.n1, n0 = (unsigned)m.n0;
-        const unsigned q = r32 / n1;
-        v.i1 = (int)(r32 - q * n1);
-        const unsigned bb = q / n0;
-        v.i0 = (int)(q - bb * n0);
-        v.b = bb;
-    } else {
-        const int64_t q = r / m.n1;
-        v.i1 = (int)(r - q * m.n1);
-        v.b = q / m.n0;
-        v.i0 = (int)(q - v.b * m.n0);
-    }
-    return v;
-}
-
-// Block-wide sum of two doubles, then one atomicAdd pair per block into out[2*b], out[2*b+1].
-// Fast path requires every thread of the block to belong to the same batch row `b` (true whenever
-// n0*n1 >= TY, i.e. always except toy sizes); otherwise each thread adds on its own.
-__device__ __forceinline__ void block_accumulate(double a0, double a1, int64_t b, bool ok, double* out) {
-    __shared__ double sh[2][kBlock / 32];
-    __shared__ long long sb_min, sb_max;
-    if (threadIdx.x == 0) { sb_min = 0x7fffffffffffffffLL; sb_max = -1; }
-    __syncthreads();
-    if (ok) { atomicMin(&sb_min, (long long)b); atomicMax(&sb_max, (long long)b); }
-    __syncthreads();
-    if (sb_max < 0) return;
-    if (sb_min != sb_max) {
-        if (ok) { atomicAdd(out + 2 * b, a0); atomicAdd(out + 2 * b + 1, a1); }
-        return;
-    }
-    if (!ok) { a0 = 0.0; a1 = 0.0; }
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_down_sync(0xffffffffu, a0, o);
-        a1 += __shfl_down_sync(0xffffffffu, a1, o);
-    }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { sh[0][w] = a0; sh[1][w] = a1; }
-    __syncthreads();
-    if (w == 0) {
-        a0 = l < kBlock / 32 ? sh[0][l] : 0.0;
-        a1 = l < kBlock / 32 ? sh[1][l] : 0.0;
-        for (int o = 4; o > 0; o >>= 1) {
-            a0 += __shfl_down_sync(0xffffffffu, a0, o);
-            a1 += __shfl_down_sync(0xffffffffu, a1, o);
-        }
-        if (l == 0) { atomicAdd(out + 2 * sb_min, a0); atomicAdd(out + 2 * sb_min + 1, a1); }
-    }
-}
+namespace {
 
 // ------------------------------------------------------------------------------------------
 // Kernels
@@ -177,72 +77,6 @@ __global__ void __launch_bounds__(kBlock) k_pds_dual(pxb_grad_desc d, pxb_pds_pa
     double a0 = 0.0, a1 = 0.0;
     if (v.ok) pxb_body_dual<T>(d, g, P, w, z, norms != nullptr, a0, a1, v.b, v.i0, v.i1, v.i2);
     if (norms) block_accumulate(a0, a1, v.b, v.ok, norms);
-}
-
-// ------------------------------------------------------------------------------------------
-// Fast TV half-steps (pxb_tv_fast.cuh): one thread = VEC consecutive voxels (128-bit accesses).
-// The VoxMap is built on the row length n2/VEC; i2 is scaled back by VEC here.
-// ------------------------------------------------------------------------------------------
-template <class T, int NDIR, int VEC>
-__global__ void __launch_bounds__(kBlock) k_tv_primal(int algo, pxb_grad_desc d, PxbTvCoef cf, pxb_pds_params P, VoxMap m,
-                                                      T* __restrict__ xu, const T* __restrict__ z, T* __restrict__ x_out,
-                                                      T* __restrict__ w, double* __restrict__ norms) {
-    const Vox v = vox_of_thread(m);
-    const PxbGeom g = pxb_geom(d.shape);
-    double a0 = 0.0, a1 = 0.0;
-    if (v.ok) pxb_tv_primal_vec<T, NDIR, VEC>(algo, d, g, cf, P, xu, z, x_out, w, norms != nullptr, a0, a1, v.b, v.i0, v.i1, v.i2 * VEC);
-    if (norms) block_accumulate(a0, a1, v.b, v.ok, norms);
-}
-
-template <class T, int NDIR, int VEC>
-__global__ void __launch_bounds__(kBlock) k_tv_dual(pxb_grad_desc d, PxbTvCoef cf, pxb_pds_params P, VoxMap m,
-                                                    const T* __restrict__ w, T* __restrict__ z, double* __restrict__ norms) {
-    const Vox v = vox_of_thread(m);
-    const PxbGeom g = pxb_geom(d.shape);
-    double a0 = 0.0, a1 = 0.0;
-    if (v.ok) pxb_tv_dual_vec<T, NDIR, VEC>(d, g, cf, P, w, z, norms != nullptr, a0, a1, v.b, v.i0, v.i1, v.i2 * VEC);
-    if (norms) block_accumulate(a0, a1, v.b, v.ok, norms);
-}
-
-// widest vector (<= 16 bytes) that divides the row length and matches every pointer's alignment
-template <class T>
-int pick_vec(int64_t n2, std::initializer_list<const void*> ptrs) {
-    int vec = 16 / (int)sizeof(T);
-    while (vec > 1) {
-        bool ok = (n2 % vec) == 0;
-        for (const void* p : ptrs)
-            if (p && (reinterpret_cast<uintptr_t>(p) % (vec * sizeof(T))) != 0) ok = false;
-        if (ok) break;
-        vec >>= 1;
-    }
-    return vec;
-}
-
-inline bool make_map_vec(int64_t batch, const int64_t shape[3], int vec, VoxMap& m) {
-    int64_t sh[3] = {shape[0], shape[1], shape[2] / vec};
-    return make_map(batch, sh, m);
-}
-
-template <class T, int NDIR>
-void launch_tv_primal(int vec, unsigned grid, cudaStream_t s, int algo, const pxb_grad_desc& d, const PxbTvCoef& cf,
-                      const pxb_pds_params& P, const VoxMap& m, void* xu, const void* z, void* x_out, void* w, double* norms) {
-    T* a = (T*)xu; const T* b = (const T*)z; T* c = (T*)x_out; T* e = (T*)w;
-    if constexpr (sizeof(T) == 4) {
-        if (vec == 4) { k_tv_primal<T, NDIR, 4><<<grid, kBlock, 0, s>>>(algo, d, cf, P, m, a, b, c, e, norms); return; }
-    }
-    if (vec == 2) k_tv_primal<T, NDIR, 2><<<grid, kBlock, 0, s>>>(algo, d, cf, P, m, a, b, c, e, norms);
-    else k_tv_primal<T, NDIR, 1><<<grid, kBlock, 0, s>>>(algo, d, cf, P, m, a, b, c, e, norms);
-}
-
-template <class T, int NDIR>
-void launch_tv_dual(int vec, unsigned grid, cudaStream_t s, const pxb_grad_desc& d, const PxbTvCoef& cf, const pxb_pds_params& P,
-                    const VoxMap& m, const void* w, void* z, double* norms) {
-    const T* a = (const T*)w; T* b = (T*)z;
-    if constexpr (sizeof(T) == 4) {
-        if (vec == 4) { k_tv_dual<T, NDIR, 4><<<grid, kBlock, 0, s>>>(d, cf, P, m, a, b, norms); return; }
-    }
-    if (vec == 2) k_tv_dual<T, NDIR, 2><<<grid, kBlock, 0, s>>>(d, cf, P, m, a, b, norms);
-    else k_tv_dual<T, NDIR, 1><<<grid, kBlock, 0, s>>>(d, cf, P, m, a, b, norms);
 }
 
 // (outer, group, inner) kernels: one thread per (outer, inner) pair, `inner` fastest.
@@ -383,8 +217,8 @@ static int stencil_launch(const pxb_stencil_desc* d, const void* in, void* out, 
     VoxMap m;
     if (!make_map(d->batch, d->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     cudaStream_t s = (cudaStream_t)stream;
-    if (d->dtype == PXB_F32) k_stencil<float><<<m.grid, kBlock, 0, s>>>(*d, m, adjoint, (const float*)in, (float*)out);
-    else k_stencil<double><<<m.grid, kBlock, 0, s>>>(*d, m, adjoint, (const double*)in, (double*)out);
+    if (d->dtype == PXB_F32) k_stencil<float><<<grid_of(m), kBlock, 0, s>>>(*d, m, adjoint, (const float*)in, (float*)out);
+    else k_stencil<double><<<grid_of(m), kBlock, 0, s>>>(*d, m, adjoint, (const double*)in, (double*)out);
     PXB_CHECK_LAUNCH(who);
     return 0;
 }
@@ -403,8 +237,8 @@ int pxb_gradient_apply(const pxb_grad_desc* d, const void* x, void* z, void* str
     VoxMap m;
     if (!make_map(d->batch, d->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     cudaStream_t s = (cudaStream_t)stream;
-    if (d->dtype == PXB_F32) k_grad_apply<float><<<m.grid, kBlock, 0, s>>>(*d, m, (const float*)x, (float*)z);
-    else k_grad_apply<double><<<m.grid, kBlock, 0, s>>>(*d, m, (const double*)x, (double*)z);
+    if (d->dtype == PXB_F32) k_grad_apply<float><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const float*)x, (float*)z);
+    else k_grad_apply<double><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const double*)x, (double*)z);
     PXB_CHECK_LAUNCH(who);
     return 0;
 }
@@ -416,8 +250,8 @@ int pxb_gradient_adjoint(const pxb_grad_desc* d, const void* z, void* x, void* s
     VoxMap m;
     if (!make_map(d->batch, d->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     cudaStream_t s = (cudaStream_t)stream;
-    if (d->dtype == PXB_F32) k_grad_adjoint<float><<<m.grid, kBlock, 0, s>>>(*d, m, (const float*)z, (float*)x);
-    else k_grad_adjoint<double><<<m.grid, kBlock, 0, s>>>(*d, m, (const double*)z, (double*)x);
+    if (d->dtype == PXB_F32) k_grad_adjoint<float><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const float*)z, (float*)x);
+    else k_grad_adjoint<double><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const double*)z, (double*)x);
     PXB_CHECK_LAUNCH(who);
     return 0;
 }
@@ -514,27 +348,15 @@ int pxb_pds_primal(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, vo
     if (p->hkind != PXB_DUAL_NONE && !z && !ktz) return fail(PXB_EINVAL, "%s: need z or ktz", who);
     VoxMap m;
     cudaStream_t s = (cudaStream_t)stream;
-    PxbTvCoef cf;
-    if (!ktz && z && p->hkind != PXB_DUAL_NONE && pxb_tv_fast_coefs(*K, cf)) {  // specialised 128-bit path
-        const int vec = K->dtype == PXB_F32 ? pick_vec<float>(K->shape[2], {xu, z, x_out, w}) : pick_vec<double>(K->shape[2], {xu, z, x_out, w});
-        if (!make_map_vec(K->batch, K->shape, vec, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
-        if (K->dtype == PXB_F32) {
-            if (K->ndir == 3) launch_tv_primal<float, 3>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
-            else if (K->ndir == 2) launch_tv_primal<float, 2>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
-            else launch_tv_primal<float, 1>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
-        } else {
-            if (K->ndir == 3) launch_tv_primal<double, 3>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
-            else if (K->ndir == 2) launch_tv_primal<double, 2>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
-            else launch_tv_primal<double, 1>(vec, m.grid, s, algo, *K, cf, *p, m, xu, z, x_out, w, norms);
-        }
-        PXB_CHECK_LAUNCH(who);
-        return 0;
+    if (!ktz && z && p->hkind != PXB_DUAL_NONE) {  // specialised 128-bit path (pxb_tv_kernels.cu)
+        int rc = 0;
+        if (pxb_tv_try_primal(algo, K, p, xu, z, x_out, w, norms, s, &rc)) return rc;
     }
     if (!make_map(K->batch, K->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     if (K->dtype == PXB_F32)
-        k_pds_primal<float><<<m.grid, kBlock, 0, s>>>(algo, *K, *p, m, (float*)xu, (const float*)z, (const float*)ktz, (float*)x_out, (float*)w, norms);
+        k_pds_primal<float><<<grid_of(m), kBlock, 0, s>>>(algo, *K, *p, m, (float*)xu, (const float*)z, (const float*)ktz, (float*)x_out, (float*)w, norms);
     else
-        k_pds_primal<double><<<m.grid, kBlock, 0, s>>>(algo, *K, *p, m, (double*)xu, (const double*)z, (const double*)ktz, (double*)x_out, (double*)w, norms);
+        k_pds_primal<double><<<grid_of(m), kBlock, 0, s>>>(algo, *K, *p, m, (double*)xu, (const double*)z, (const double*)ktz, (double*)x_out, (double*)w, norms);
     PXB_CHECK_LAUNCH(who);
     return 0;
 }
@@ -547,25 +369,13 @@ int pxb_pds_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w,
     if (!(p->sigma > 0)) return fail(PXB_EINVAL, "%s: sigma must be > 0", who);
     VoxMap m;
     cudaStream_t s = (cudaStream_t)stream;
-    PxbTvCoef cf;
-    if (pxb_tv_fast_coefs(*K, cf)) {  // specialised 128-bit path
-        const int vec = K->dtype == PXB_F32 ? pick_vec<float>(K->shape[2], {w, z}) : pick_vec<double>(K->shape[2], {w, z});
-        if (!make_map_vec(K->batch, K->shape, vec, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
-        if (K->dtype == PXB_F32) {
-            if (K->ndir == 3) launch_tv_dual<float, 3>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
-            else if (K->ndir == 2) launch_tv_dual<float, 2>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
-            else launch_tv_dual<float, 1>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
-        } else {
-            if (K->ndir == 3) launch_tv_dual<double, 3>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
-            else if (K->ndir == 2) launch_tv_dual<double, 2>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
-            else launch_tv_dual<double, 1>(vec, m.grid, s, *K, cf, *p, m, w, z, norms);
-        }
-        PXB_CHECK_LAUNCH(who);
-        return 0;
+    {
+        int rc = 0;
+        if (pxb_tv_try_dual(K, p, w, z, norms, s, &rc)) return rc;
     }
     if (!make_map(K->batch, K->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
-    if (K->dtype == PXB_F32) k_pds_dual<float><<<m.grid, kBlock, 0, s>>>(*K, *p, m, (const float*)w, (float*)z, norms);
-    else k_pds_dual<double><<<m.grid, kBlock, 0, s>>>(*K, *p, m, (const double*)w, (double*)z, norms);
+    if (K->dtype == PXB_F32) k_pds_dual<float><<<grid_of(m), kBlock, 0, s>>>(*K, *p, m, (const float*)w, (float*)z, norms);
+    else k_pds_dual<double><<<grid_of(m), kBlock, 0, s>>>(*K, *p, m, (const double*)w, (double*)z, norms);
     PXB_CHECK_LAUNCH(who);
     return 0;
 }

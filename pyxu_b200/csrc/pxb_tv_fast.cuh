@@ -4,12 +4,23 @@
 //
 // One thread owns VEC consecutive voxels of a row (16 bytes: 4 fp32 / 2 fp64): all row-aligned operands move
 // as 128-bit vector loads/stores; the +-1 neighbours along the row are one extra scalar (L1-resident) load.
-// Rows at a domain face whose mode is not 'constant' -- where the reference's boundary extension folds samples
-// back -- are delegated, per voxel, to the generic bodies of pxb_core.cuh, so every mode stays exact.
+// Voxels next to a domain face whose mode is not 'constant' -- where the reference's boundary extension folds
+// samples back -- are delegated, per voxel, to the generic bodies of pxb_core.cuh, so every mode stays exact.
+//
+// The first version of these bodies was issue-bound, not HBM-bound (ncu, profiles/r01_a_*: 74 % issue-active,
+// ~150 instructions per voxel): all scalars are therefore converted to T and folded on the host (PxbTvP<T>), the
+// dual prox is evaluated in its closed form (one sqrt + one division per voxel), and the shift / gradient
+// arrays of the data term are vector-loaded.
 //
 // Like pxb_core.cuh these bodies are __host__ __device__: tests/emu runs them on the CPU.
 #pragma once
 #include "pxb_core.cuh"
+
+#if defined(__CUDACC__)
+#define PXB_NOINLINE __host__ __device__ __noinline__
+#else
+#define PXB_NOINLINE inline
+#endif
 
 struct PxbTvCoef {  // per direction k: taps at offsets -1 / 0 / +1 (0.0 when absent)
     double cm[PXB_MAX_DIRS], c0[PXB_MAX_DIRS], cp[PXB_MAX_DIRS];
@@ -30,6 +41,48 @@ PXB_HD bool pxb_tv_fast_coefs(const pxb_grad_desc& d, PxbTvCoef& c) {
         }
     }
     return true;
+}
+
+// how the shift of the data term f = alpha*||x + shift||^2 is addressed
+enum { PXB_SHIFT_NONE = 0, PXB_SHIFT_SCALAR = 1, PXB_SHIFT_LIN = 2 /* shift[lin] */, PXB_SHIFT_VOL = 3 /* shift[v] */, PXB_SHIFT_MOD = 4 };
+
+// Everything the fast bodies need, typed and folded on the host.
+template <class T>
+struct PxbTvP {
+    T cm[PXB_MAX_DIRS], c0[PXB_MAX_DIRS], cp[PXB_MAX_DIRS];
+    T tau, sigma, rho, one_m_rho, lam, two_alpha, gp0, gp1;
+    int gkind, fkind, hkind, shift_mode;
+    const T* shift;
+    const T* garr;
+    int64_t shift_period;
+    int n0, n1, n2;
+    int64_t s0, s1, vol;  // vol: elements between components / batch items
+    int mode[3];
+    int open_lo, open_hi;
+};
+
+template <class T>
+PXB_HD void pxb_tv_prepare(const pxb_grad_desc& d, const PxbTvCoef& cf, const pxb_pds_params& P, PxbTvP<T>& q) {
+    for (int k = 0; k < PXB_MAX_DIRS; ++k) {
+        q.cm[k] = T(cf.cm[k]); q.c0[k] = T(cf.c0[k]); q.cp[k] = T(cf.cp[k]);
+    }
+    q.tau = T(P.tau); q.sigma = T(P.sigma); q.rho = T(P.rho); q.one_m_rho = T(1) - q.rho;
+    q.lam = T(P.lam); q.two_alpha = T(2 * P.f.alpha); q.gp0 = T(P.g.p0); q.gp1 = T(P.g.p1);
+    q.gkind = P.g.kind; q.fkind = P.f.kind; q.hkind = P.hkind;
+    const PxbGeom g = pxb_geom(d.shape);
+    q.n0 = g.n0; q.n1 = g.n1; q.n2 = g.n2; q.s0 = g.s0; q.s1 = g.s1;
+    q.vol = pxb_vol(g, d.slab);
+    for (int a = 0; a < 3; ++a) q.mode[a] = d.mode[a];
+    q.open_lo = d.slab.open_lo; q.open_hi = d.slab.open_hi;
+    q.shift = (const T*)P.f.shift; q.garr = (const T*)P.f.garr; q.shift_period = P.f.shift_period;
+    q.shift_mode = PXB_SHIFT_NONE;
+    if (P.f.kind == PXB_F_SQL2 && P.f.shift) {
+        const int64_t span = (d.batch - 1) * q.vol + (int64_t)g.n0 * g.s0;  // largest lin + 1
+        if (P.f.shift_period == 1) q.shift_mode = PXB_SHIFT_SCALAR;
+        else if (P.f.shift_period >= span) q.shift_mode = PXB_SHIFT_LIN;
+        else if (P.f.shift_period == q.vol) q.shift_mode = PXB_SHIFT_VOL;
+        else q.shift_mode = PXB_SHIFT_MOD;
+    }
 }
 
 template <class T, int VEC>
@@ -73,188 +126,197 @@ PXB_HD void pxb_vstore(T* __restrict__ p, const PxbVec<T, VEC>& r) {
 // its mode is not 'constant' (and, for axis 0, the side is not an open slab cut).  With radius-1 taps the
 // boundary extension folds samples onto the face voxel itself (wrap / symmetric / edge) or onto its neighbour
 // ('reflect': m(-1) = 1, m(n) = n-2), hence a band of two voxels per face.
-template <int NDIR>
-PXB_HD bool pxb_tv_needs_generic(const pxb_grad_desc& d, const PxbGeom& g, int i0, int i1, int i2, int vec) {
-    if (NDIR >= 3 && d.mode[0] != PXB_CONSTANT)
-        if ((i0 <= 1 && !d.slab.open_lo) || (i0 >= g.n0 - 2 && !d.slab.open_hi)) return true;
-    if (NDIR >= 2 && d.mode[1] != PXB_CONSTANT)
-        if (i1 <= 1 || i1 >= g.n1 - 2) return true;
-    if (d.mode[2] != PXB_CONSTANT)
-        if (i2 <= 1 || i2 + vec >= g.n2 - 1) return true;
+template <class T, int NDIR>
+PXB_HD bool pxb_tv_needs_generic(const PxbTvP<T>& q, int i0, int i1, int i2, int vec) {
+    if (NDIR >= 3 && q.mode[0] != PXB_CONSTANT)
+        if ((i0 <= 1 && !q.open_lo) || (i0 >= q.n0 - 2 && !q.open_hi)) return true;
+    if (NDIR >= 2 && q.mode[1] != PXB_CONSTANT)
+        if (i1 <= 1 || i1 >= q.n1 - 2) return true;
+    if (q.mode[2] != PXB_CONSTANT)
+        if (i2 <= 1 || i2 + vec >= q.n2 - 1) return true;
     return false;
 }
 
-// shift value for the data term at linear index lin = b*vol + v  (see pxb_fterm)
+// The folding-aware generic bodies are kept out of line on the device so that their register needs do not
+// dictate the occupancy of the fast path (they run for a vanishing fraction of the voxels).
 template <class T>
-PXB_HD T pxb_shift_at(const pxb_fterm& f, int64_t lin, int64_t v, int64_t vol) {
-    const T* s = (const T*)f.shift;
-    if (!s) return T(0);
-    if (f.shift_period == 1) return s[0];
-    if (f.shift_period == vol) return s[v];
-    if (lin < f.shift_period) return s[lin];
-    return s[lin % f.shift_period];
+PXB_NOINLINE void pxb_tv_primal_generic(int algo, const pxb_grad_desc& d, const pxb_pds_params& P, T* xu, const T* z, T* x_out, T* w,
+                                        bool want_norms, double* nrm, int64_t b, int i0, int i1, int i2, int vec) {
+    const PxbGeom g = pxb_geom(d.shape);
+    double n0 = 0.0, n1 = 0.0;
+    for (int j = 0; j < vec; ++j)
+        pxb_body_primal<T>(algo, d, g, P, xu, z, (const T*)nullptr, x_out, w, want_norms, n0, n1, b, i0, i1, i2 + j);
+    nrm[0] += n0;
+    nrm[1] += n1;
+}
+
+template <class T>
+PXB_NOINLINE void pxb_tv_dual_generic(const pxb_grad_desc& d, const pxb_pds_params& P, const T* w, T* z, bool want_norms, double* nrm,
+                                      int64_t b, int i0, int i1, int i2, int vec) {
+    const PxbGeom g = pxb_geom(d.shape);
+    double n0 = 0.0, n1 = 0.0;
+    for (int j = 0; j < vec; ++j) pxb_body_dual<T>(d, g, P, w, z, want_norms, n0, n1, b, i0, i1, i2 + j);
+    nrm[0] += n0;
+    nrm[1] += n1;
+}
+
+// taps of one direction along the row itself:  out[j] = c_hi * f[j+1] + c_0 * f[j] + c_lo * f[j-1]
+// (the vector's own elements serve as neighbours, the two ends come from one scalar load each)
+template <class T, int VEC>
+PXB_HD void pxb_tv_taps_row(const T* __restrict__ f, const PxbVec<T, VEC>& c, T c_hi, T c_0, T c_lo, bool has_lo, bool has_hi, T* out) {
+    T lo = T(0), hi = T(0);
+    if (c_lo != T(0) && has_lo) lo = f[-1];
+    if (c_hi != T(0) && has_hi) hi = f[VEC];
+    for (int j = 0; j < VEC; ++j) {
+        const T up = (j + 1 < VEC) ? c.v[j + 1 < VEC ? j + 1 : 0] : hi;
+        const T dn = (j > 0) ? c.v[j > 0 ? j - 1 : 0] : lo;
+        T a = c_0 * c.v[j];
+        if (c_hi != T(0)) a += c_hi * up;
+        if (c_lo != T(0)) a += c_lo * dn;
+        out[j] = a;
+    }
+}
+
+// taps of one direction across rows / planes:  out[j] = c_hi * f[s + st] + c_0 * f[s] + c_lo * f[s - st]
+template <class T, int VEC>
+PXB_HD void pxb_tv_taps_col(const T* __restrict__ f, int64_t st, const PxbVec<T, VEC>& c, T c_hi, T c_0, T c_lo, bool has_lo, bool has_hi,
+                            T* out) {
+    for (int j = 0; j < VEC; ++j) out[j] = c_0 * c.v[j];
+    if (c_hi != T(0) && has_hi) {
+        const PxbVec<T, VEC> up = pxb_vload<T, VEC>(f + st);
+        for (int j = 0; j < VEC; ++j) out[j] += c_hi * up.v[j];
+    }
+    if (c_lo != T(0) && has_lo) {
+        const PxbVec<T, VEC> dn = pxb_vload<T, VEC>(f - st);
+        for (int j = 0; j < VEC; ++j) out[j] += c_lo * dn.v[j];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// primal half-step for VEC voxels (b, i0, i1, i2 .. i2+VEC)
+// primal half-step for VEC voxels (b, i0, i1, i2 .. i2+VEC).  nrm[0..1] += RelError[x] partial sums.
 // ---------------------------------------------------------------------------------------------------------
-template <class T, int NDIR, int VEC>
-PXB_HD void pxb_tv_primal_vec(int algo, const pxb_grad_desc& d, const PxbGeom& g, const PxbTvCoef& cf, const pxb_pds_params& P,
-                              T* __restrict__ xu, const T* __restrict__ z, T* __restrict__ x_out, T* __restrict__ w,
-                              bool want_norms, double& n0, double& n1, int64_t b, int i0, int i1, int i2) {
-    if (pxb_tv_needs_generic<NDIR>(d, g, i0, i1, i2, VEC)) {
-        for (int j = 0; j < VEC; ++j)
-            pxb_body_primal<T>(algo, d, g, P, xu, z, (const T*)nullptr, x_out, w, want_norms, n0, n1, b, i0, i1, i2 + j);
+template <class T, int NDIR, int VEC, int ALGO, bool NORMS>
+PXB_HD void pxb_tv_primal_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const pxb_pds_params& P, T* __restrict__ xu,
+                              const T* __restrict__ z, T* __restrict__ x_out, T* __restrict__ w, double* nrm, int64_t b, int i0,
+                              int i1, int i2) {
+    if (pxb_tv_needs_generic<T, NDIR>(q, i0, i1, i2, VEC)) {
+        pxb_tv_primal_generic<T>(ALGO, d, P, xu, z, x_out, w, NORMS, nrm, b, i0, i1, i2, VEC);
         return;
     }
-    const int64_t vol = pxb_vol(g, d.slab);
-    const int64_t v = (int64_t)i0 * g.s0 + (int64_t)i1 * g.s1 + i2;
-    const int64_t lin = b * vol + v;
-    const T* __restrict__ zb = z + b * NDIR * vol + v;
+    const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2;
+    const int64_t lin = b * q.vol + v;
+    const T* __restrict__ zb = z + b * NDIR * q.vol + v;
     T kz[VEC];
     for (int j = 0; j < VEC; ++j) kz[j] = T(0);
     // (K_k^T z)[s] = cm*z_k[s+st] + c0*z_k[s] + cp*z_k[s-st]   (rows outside the domain contribute nothing)
     for (int k = 0; k < NDIR; ++k) {
         const int ax = 3 - NDIR + k;
-        const T cm = T(cf.cm[k]), c0 = T(cf.c0[k]), cp = T(cf.cp[k]);
-        const T* __restrict__ zk = zb + k * vol;
+        const T* __restrict__ zk = zb + k * q.vol;
+        const PxbVec<T, VEC> c = pxb_vload<T, VEC>(zk);
+        T t[VEC];
         if (ax == 2) {
-            const PxbVec<T, VEC> c = pxb_vload<T, VEC>(zk);
-            T lo = T(0), hi = T(0);
-            if (cp != T(0) && i2 > 0) lo = zk[-1];
-            if (cm != T(0) && i2 + VEC < g.n2) hi = zk[VEC];
-            for (int j = 0; j < VEC; ++j) {
-                const T up = (j + 1 < VEC) ? c.v[j + 1 < VEC ? j + 1 : 0] : hi;
-                const T dn = (j > 0) ? c.v[j > 0 ? j - 1 : 0] : lo;
-                T a = T(0);
-                if (cm != T(0)) a += cm * up;
-                a += c0 * c.v[j];
-                if (cp != T(0)) a += cp * dn;
-                kz[j] += a;
-            }
+            pxb_tv_taps_row<T, VEC>(zk, c, q.cm[k], q.c0[k], q.cp[k], i2 > 0, i2 + VEC < q.n2, t);
         } else {
-            const int64_t st = ax == 0 ? g.s0 : g.s1;
-            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? g.n0 : g.n1;
-            const bool has_lo = i > 0 || (ax == 0 && d.slab.open_lo), has_hi = i < n - 1 || (ax == 0 && d.slab.open_hi);
-            const PxbVec<T, VEC> c = pxb_vload<T, VEC>(zk);
-            PxbVec<T, VEC> up, dn;
-            for (int j = 0; j < VEC; ++j) up.v[j] = dn.v[j] = T(0);
-            if (cm != T(0) && has_hi) up = pxb_vload<T, VEC>(zk + st);
-            if (cp != T(0) && has_lo) dn = pxb_vload<T, VEC>(zk - st);
-            for (int j = 0; j < VEC; ++j) {
-                T a = T(0);
-                if (cm != T(0)) a += cm * up.v[j];
-                a += c0 * c.v[j];
-                if (cp != T(0)) a += cp * dn.v[j];
-                kz[j] += a;
-            }
+            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? q.n0 : q.n1;
+            const bool has_lo = i > 0 || (ax == 0 && q.open_lo), has_hi = i < n - 1 || (ax == 0 && q.open_hi);
+            pxb_tv_taps_col<T, VEC>(zk, ax == 0 ? q.s0 : q.s1, c, q.cm[k], q.c0[k], q.cp[k], has_lo, has_hi, t);
         }
+        for (int j = 0; j < VEC; ++j) kz[j] += t[j];
     }
     const PxbVec<T, VEC> old = pxb_vload<T, VEC>(xu + lin);
-    PxbVec<T, VEC> xprev;
-    if (want_norms && algo == PXB_PD3O) xprev = pxb_vload<T, VEC>(x_out + lin);
+    PxbVec<T, VEC> sh;
+    for (int j = 0; j < VEC; ++j) sh.v[j] = T(0);
+    if (q.fkind == PXB_F_SQL2) {
+        if (q.shift_mode == PXB_SHIFT_LIN) sh = pxb_vload<T, VEC>(q.shift + lin);
+        else if (q.shift_mode == PXB_SHIFT_VOL) sh = pxb_vload<T, VEC>(q.shift + v);
+        else if (q.shift_mode == PXB_SHIFT_SCALAR) { for (int j = 0; j < VEC; ++j) sh.v[j] = q.shift[0]; }
+        else if (q.shift_mode == PXB_SHIFT_MOD) { for (int j = 0; j < VEC; ++j) sh.v[j] = q.shift[(lin + j) % q.shift_period]; }
+    }
     PxbVec<T, VEC> xn, xo, wo;
-    for (int j = 0; j < VEC; ++j) {
-        // same algebra as pxb_primal_at, with the shift fetched without a modulo on the common layouts
-        const T tau = T(P.tau), rho = T(P.rho);
-        const T sh = (P.f.kind == PXB_F_SQL2) ? pxb_shift_at<T>(P.f, lin + j, v + j, vol) : T(0);
-        if (algo == PXB_PD3O) {
-            const T x = pxb_prox_eval<T>(P.g.kind, T(P.g.p0), T(P.g.p1), old.v[j] - tau * kz[j], tau);
-            const T gf = (P.f.kind == PXB_F_SQL2) ? (x + sh) * T(2 * P.f.alpha) : T(0);
-            const T ut = x - tau * gf;
+    double a0 = 0.0, a1 = 0.0;
+    if (ALGO == PXB_PD3O) {
+        PxbVec<T, VEC> xprev;
+        if (NORMS) xprev = pxb_vload<T, VEC>(x_out + lin);
+        for (int j = 0; j < VEC; ++j) {
+            const T x = pxb_prox_eval<T>(q.gkind, q.gp0, q.gp1, old.v[j] - q.tau * kz[j], q.tau);
+            const T gf = (q.fkind == PXB_F_SQL2) ? (x + sh.v[j]) * q.two_alpha : T(0);
+            const T ut = x - q.tau * gf;
             wo.v[j] = x + ut - old.v[j];
-            xn.v[j] = (T(1) - rho) * old.v[j] + rho * ut;
+            xn.v[j] = q.one_m_rho * old.v[j] + q.rho * ut;
             xo.v[j] = x;
-        } else {
-            T gf = T(0);
-            if (P.f.kind == PXB_F_SQL2) gf = (old.v[j] + sh) * T(2 * P.f.alpha);
-            else if (P.f.kind == PXB_F_GRADARR) gf = ((const T*)P.f.garr)[lin + j];
-            const T vv = old.v[j] - tau * gf - tau * kz[j];
-            const T xt = pxb_prox_eval<T>(P.g.kind, T(P.g.p0), T(P.g.p1), vv, tau);
-            wo.v[j] = T(2) * xt - old.v[j];
-            xn.v[j] = rho * xt + (T(1) - rho) * old.v[j];
-            xo.v[j] = xn.v[j];
+            if (NORMS) {
+                const double dd = (double)x - (double)xprev.v[j];
+                a0 += dd * dd;
+                a1 += (double)xprev.v[j] * (double)xprev.v[j];
+            }
         }
-        if (want_norms) {
-            const T xp = (algo == PXB_PD3O) ? xprev.v[j] : old.v[j];
-            const double dd = (double)xo.v[j] - (double)xp;
-            n0 += dd * dd;
-            n1 += (double)xp * (double)xp;
+        pxb_vstore<T, VEC>(x_out + lin, xo);
+    } else {
+        PxbVec<T, VEC> ga;
+        if (q.fkind == PXB_F_GRADARR) ga = pxb_vload<T, VEC>(q.garr + lin);
+        for (int j = 0; j < VEC; ++j) {
+            T gf = T(0);
+            if (q.fkind == PXB_F_SQL2) gf = (old.v[j] + sh.v[j]) * q.two_alpha;
+            else if (q.fkind == PXB_F_GRADARR) gf = ga.v[j];
+            const T vv = old.v[j] - q.tau * gf - q.tau * kz[j];
+            const T xt = pxb_prox_eval<T>(q.gkind, q.gp0, q.gp1, vv, q.tau);
+            wo.v[j] = T(2) * xt - old.v[j];
+            xn.v[j] = q.rho * xt + q.one_m_rho * old.v[j];
+            if (NORMS) {
+                const double dd = (double)xn.v[j] - (double)old.v[j];
+                a0 += dd * dd;
+                a1 += (double)old.v[j] * (double)old.v[j];
+            }
         }
     }
     pxb_vstore<T, VEC>(xu + lin, xn);
     pxb_vstore<T, VEC>(w + lin, wo);
-    if (algo == PXB_PD3O) pxb_vstore<T, VEC>(x_out + lin, xo);
+    if (NORMS) { nrm[0] += a0; nrm[1] += a1; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // dual half-step for VEC voxels:  z <- (1-rho) z + rho prox_{sigma h*}(z + sigma K w)
 // ---------------------------------------------------------------------------------------------------------
-template <class T, int NDIR, int VEC>
-PXB_HD void pxb_tv_dual_vec(const pxb_grad_desc& d, const PxbGeom& g, const PxbTvCoef& cf, const pxb_pds_params& P,
-                            const T* __restrict__ w, T* __restrict__ z, bool want_norms, double& n0, double& n1, int64_t b,
-                            int i0, int i1, int i2) {
-    if (pxb_tv_needs_generic<NDIR>(d, g, i0, i1, i2, VEC)) {
-        for (int j = 0; j < VEC; ++j) pxb_body_dual<T>(d, g, P, w, z, want_norms, n0, n1, b, i0, i1, i2 + j);
+template <class T, int NDIR, int VEC, bool NORMS>
+PXB_HD void pxb_tv_dual_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const pxb_pds_params& P, const T* __restrict__ w,
+                            T* __restrict__ z, double* nrm, int64_t b, int i0, int i1, int i2) {
+    if (pxb_tv_needs_generic<T, NDIR>(q, i0, i1, i2, VEC)) {
+        pxb_tv_dual_generic<T>(d, P, w, z, NORMS, nrm, b, i0, i1, i2, VEC);
         return;
     }
-    const int64_t vol = pxb_vol(g, d.slab);
-    const int64_t v = (int64_t)i0 * g.s0 + (int64_t)i1 * g.s1 + i2;
-    const T* __restrict__ wb = w + b * vol + v;
-    T* __restrict__ zb = z + b * NDIR * vol + v;
+    const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2;
+    const T* __restrict__ wb = w + b * q.vol + v;
+    T* __restrict__ zb = z + b * NDIR * q.vol + v;
     const PxbVec<T, VEC> wc = pxb_vload<T, VEC>(wb);
     T p[NDIR][VEC], zo[NDIR][VEC];
-    const T sigma = T(P.sigma), rho = T(P.rho);
     // (K_k w)[s] = cm*w[s-st] + c0*w[s] + cp*w[s+st]
     for (int k = 0; k < NDIR; ++k) {
         const int ax = 3 - NDIR + k;
-        const T cm = T(cf.cm[k]), c0 = T(cf.c0[k]), cp = T(cf.cp[k]);
-        const PxbVec<T, VEC> zc = pxb_vload<T, VEC>(zb + k * vol);
+        const PxbVec<T, VEC> zc = pxb_vload<T, VEC>(zb + k * q.vol);
         T kw[VEC];
         if (ax == 2) {
-            T lo = T(0), hi = T(0);
-            if (cm != T(0) && i2 > 0) lo = wb[-1];
-            if (cp != T(0) && i2 + VEC < g.n2) hi = wb[VEC];
-            for (int j = 0; j < VEC; ++j) {
-                const T up = (j + 1 < VEC) ? wc.v[j + 1 < VEC ? j + 1 : 0] : hi;
-                const T dn = (j > 0) ? wc.v[j > 0 ? j - 1 : 0] : lo;
-                T a = T(0);
-                if (cm != T(0)) a += cm * dn;
-                a += c0 * wc.v[j];
-                if (cp != T(0)) a += cp * up;
-                kw[j] = a;
-            }
+            pxb_tv_taps_row<T, VEC>(wb, wc, q.cp[k], q.c0[k], q.cm[k], i2 > 0, i2 + VEC < q.n2, kw);
         } else {
-            const int64_t st = ax == 0 ? g.s0 : g.s1;
-            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? g.n0 : g.n1;
-            const bool has_lo = i > 0 || (ax == 0 && d.slab.open_lo), has_hi = i < n - 1 || (ax == 0 && d.slab.open_hi);
-            PxbVec<T, VEC> up, dn;
-            for (int j = 0; j < VEC; ++j) up.v[j] = dn.v[j] = T(0);
-            if (cp != T(0) && has_hi) up = pxb_vload<T, VEC>(wb + st);
-            if (cm != T(0) && has_lo) dn = pxb_vload<T, VEC>(wb - st);
-            for (int j = 0; j < VEC; ++j) {
-                T a = T(0);
-                if (cm != T(0)) a += cm * dn.v[j];
-                a += c0 * wc.v[j];
-                if (cp != T(0)) a += cp * up.v[j];
-                kw[j] = a;
-            }
+            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? q.n0 : q.n1;
+            const bool has_lo = i > 0 || (ax == 0 && q.open_lo), has_hi = i < n - 1 || (ax == 0 && q.open_hi);
+            pxb_tv_taps_col<T, VEC>(wb, ax == 0 ? q.s0 : q.s1, wc, q.cp[k], q.c0[k], q.cm[k], has_lo, has_hi, kw);
         }
         for (int j = 0; j < VEC; ++j) {
             zo[k][j] = zc.v[j];
-            p[k][j] = zc.v[j] + sigma * kw[j];
+            p[k][j] = zc.v[j] + q.sigma * kw[j];
         }
     }
+    double a0 = 0.0, a1 = 0.0;
     for (int j = 0; j < VEC; ++j) {
         T grp[PXB_MAX_DIRS];
         for (int k = 0; k < NDIR; ++k) grp[k] = p[k][j];
-        pxb_dual_prox_group<T>(P.hkind, NDIR, T(P.lam), sigma, grp);
+        pxb_dual_prox_group<T>(q.hkind, NDIR, q.lam, q.sigma, grp);
         for (int k = 0; k < NDIR; ++k) {
-            const T zn = (T(1) - rho) * zo[k][j] + rho * grp[k];
-            if (want_norms) {
+            const T zn = q.one_m_rho * zo[k][j] + q.rho * grp[k];
+            if (NORMS) {
                 const double dd = (double)zn - (double)zo[k][j];
-                n0 += dd * dd;
-                n1 += (double)zo[k][j] * (double)zo[k][j];
+                a0 += dd * dd;
+                a1 += (double)zo[k][j] * (double)zo[k][j];
             }
             p[k][j] = zn;
         }
@@ -262,6 +324,7 @@ PXB_HD void pxb_tv_dual_vec(const pxb_grad_desc& d, const PxbGeom& g, const PxbT
     for (int k = 0; k < NDIR; ++k) {
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = p[k][j];
-        pxb_vstore<T, VEC>(zb + k * vol, o);
+        pxb_vstore<T, VEC>(zb + k * q.vol, o);
     }
+    if (NORMS) { nrm[0] += a0; nrm[1] += a1; }
 }

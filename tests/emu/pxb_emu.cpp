@@ -56,16 +56,26 @@ template <class T, int NDIR, int VEC>
 static void t_tv(int which, int algo, const pxb_grad_desc* K, const PxbTvCoef& cf, const pxb_pds_params* p, void* xu, const void* z,
                  void* x_out, void* w, double* norms) {
     const PxbGeom g = pxb_geom(K->shape);
+    PxbTvP<T> q;
+    pxb_tv_prepare<T>(*K, cf, *p, q);
     for (int64_t b = 0; b < K->batch; ++b)
         for (int i0 = 0; i0 < g.n0; ++i0)
             for (int i1 = 0; i1 < g.n1; ++i1)
                 for (int i2 = 0; i2 < g.n2; i2 += VEC) {
-                    double a0 = 0, a1 = 0;
-                    if (which == 0)
-                        pxb_tv_primal_vec<T, NDIR, VEC>(algo, *K, g, cf, *p, (T*)xu, (const T*)z, (T*)x_out, (T*)w, norms != nullptr, a0, a1, b, i0, i1, i2);
-                    else
-                        pxb_tv_dual_vec<T, NDIR, VEC>(*K, g, cf, *p, (const T*)w, (T*)z, norms != nullptr, a0, a1, b, i0, i1, i2);
-                    if (norms) { norms[2 * b] += a0; norms[2 * b + 1] += a1; }
+                    double a[2] = {0, 0};
+                    if (which == 0) {
+                        if (algo == PXB_PD3O) {
+                            if (norms) pxb_tv_primal_vec<T, NDIR, VEC, PXB_PD3O, true>(q, *K, *p, (T*)xu, (const T*)z, (T*)x_out, (T*)w, a, b, i0, i1, i2);
+                            else pxb_tv_primal_vec<T, NDIR, VEC, PXB_PD3O, false>(q, *K, *p, (T*)xu, (const T*)z, (T*)x_out, (T*)w, a, b, i0, i1, i2);
+                        } else {
+                            if (norms) pxb_tv_primal_vec<T, NDIR, VEC, PXB_CV, true>(q, *K, *p, (T*)xu, (const T*)z, (T*)x_out, (T*)w, a, b, i0, i1, i2);
+                            else pxb_tv_primal_vec<T, NDIR, VEC, PXB_CV, false>(q, *K, *p, (T*)xu, (const T*)z, (T*)x_out, (T*)w, a, b, i0, i1, i2);
+                        }
+                    } else {
+                        if (norms) pxb_tv_dual_vec<T, NDIR, VEC, true>(q, *K, *p, (const T*)w, (T*)z, a, b, i0, i1, i2);
+                        else pxb_tv_dual_vec<T, NDIR, VEC, false>(q, *K, *p, (const T*)w, (T*)z, a, b, i0, i1, i2);
+                    }
+                    if (norms) { norms[2 * b] += a[0]; norms[2 * b + 1] += a[1]; }
                 }
 }
 template <class T, int NDIR>
