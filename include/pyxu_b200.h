@@ -196,6 +196,22 @@ int pxb_pds_primal(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, vo
 int pxb_pds_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w, void* z,
                  double* norms, void* stream);
 
+/* One whole iteration in ONE pass (primal half-step + dual half-step + both RelError norms), out of place:
+ *   reads  xu_in (PD3O: u, CV: x), z_in      -- left untouched (they become the next call's output buffers)
+ *   writes xu_out, z_out, and for PD3O x_out (nullable: x is then not materialised)
+ * Same algebra as pxb_pds_primal followed by pxb_pds_dual (pds.py:429-442, :747-761); w never leaves the SM.
+ * norms_x / norms_z (nullable): per batch row += { sum (new-old)^2, sum old^2 } for x (PD3O: against the previous
+ * content of x_out) and z.
+ * Envelope: K a 2- or 3-direction first-order Gradient with 'constant' boundaries, 16-byte aligned arrays, last
+ * axis a multiple of 4 (fp32) / 2 (fp64) samples, h = lam*L21 | lam*L1, f pointwise (PD3O) or any (CV, garr).
+ * Returns PXB_ENOSUP outside the envelope: callers fall back to the two-pass form.
+ * With an open slab side the ghost planes of xu_in, z_in (and of the shift array) must hold the neighbour's data. */
+int pxb_pds_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in,
+                 void* xu_out, void* z_out, void* x_out, double* norms_x, double* norms_z, void* stream);
+/* same, with the number of planes one thread block marches through fixed by the caller (tuning / tests) */
+int pxb_pds_iter_chunked(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in,
+                         void* xu_out, void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Stopping-criterion norms (reference: src/pyxu/opt/stop.py:273-284 AbsError, :353-382         */
 /* RelError).  Per row r of a (rows, n) array:  out[2r] += sum (x-y)^2 (y NULL -> sum x^2),     */

@@ -65,7 +65,7 @@ def build_emu(force=False):
     """Host build of the per-voxel kernel bodies (tests/emu): CPU test infrastructure only."""
     src = os.path.join(ROOT, "tests", "emu", "pxb_emu.cpp")
     out = os.path.join(ROOT, "tests", "emu", "libpxb_emu.so")
-    deps = [src, os.path.join(CSRC, "pxb_core.cuh"), os.path.join(ROOT, "include", "pyxu_b200.h")]
+    deps = [src, os.path.join(ROOT, "include", "pyxu_b200.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     if force or _newer(out, deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", out, src], check=True)
     return out

@@ -104,6 +104,8 @@ PROTOTYPES = {
     "pxb_dual_update": (_i, [_i, _i, _i64, _i64, _i64, _d, _d, _d, _vp, _vp, _vp, _vp]),
     "pxb_pds_primal": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pxb_pds_dual": (_i, [_P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp]),
+    "pxb_pds_iter": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pxb_pds_iter_chunked": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pxb_sqnorms": (_i, [_i, _i64, _i64, _vp, _vp, _vp, _vp]),
 }
 

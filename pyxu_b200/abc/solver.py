@@ -54,6 +54,10 @@ class StoppingCriterion:
     def _needs_host_sync(self):
         return True
 
+    # keys of the solver's mathematical state this criterion reads; None = unknown (assume all of them)
+    def _state_vars(self):
+        return None
+
 
 class _Composition(StoppingCriterion):
     def __init__(self, lhs, rhs, op):
@@ -74,6 +78,10 @@ class _Composition(StoppingCriterion):
 
     def _needs_host_sync(self):
         return self._lhs._needs_host_sync() or self._rhs._needs_host_sync()
+
+    def _state_vars(self):
+        a, b = self._lhs._state_vars(), self._rhs._state_vars()
+        return None if (a is None or b is None) else (a | b)
 
 
 class Solver:

@@ -380,6 +380,26 @@ int pxb_pds_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w,
     return 0;
 }
 
+int pxb_pds_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out,
+                 void* z_out, void* x_out, double* norms_x, double* norms_z, void* stream) {
+    const char* who = "pxb_pds_iter";
+    if (int e = check_pds(K, p, who)) return e;
+    if (algo != PXB_PD3O && algo != PXB_CV) return fail(PXB_EINVAL, "%s: bad algo %d", who, algo);
+    if (!xu_in || !z_in || !xu_out || !z_out) return fail(PXB_EINVAL, "%s: null xu/z", who);
+    if (xu_in == xu_out || z_in == z_out) return fail(PXB_EINVAL, "%s: the update is out of place (ping-pong buffers)", who);
+    if (!(p->sigma > 0)) return fail(PXB_EINVAL, "%s: sigma must be > 0", who);
+    return pxb_tv_iter_launch(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, 0, (cudaStream_t)stream);
+}
+
+int pxb_pds_iter_chunked(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out,
+                         void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk, void* stream) {
+    const char* who = "pxb_pds_iter_chunked";
+    if (int e = check_pds(K, p, who)) return e;
+    if (!xu_in || !z_in || !xu_out || !z_out || xu_in == xu_out || z_in == z_out) return fail(PXB_EINVAL, "%s: bad buffers", who);
+    if (chunk < 1) return fail(PXB_EINVAL, "%s: chunk must be >= 1", who);
+    return pxb_tv_iter_launch(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, chunk, (cudaStream_t)stream);
+}
+
 int pxb_sqnorms(int dtype, int64_t rows, int64_t n, const void* x, const void* y, double* out, void* stream) {
     const char* who = "pxb_sqnorms";
     if (dtype != PXB_F32 && dtype != PXB_F64) return fail(PXB_EINVAL, "%s: bad dtype %d", who, dtype);

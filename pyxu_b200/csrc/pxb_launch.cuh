@@ -139,3 +139,7 @@ static __device__ __forceinline__ void block_accumulate(double a0, double a1, in
 bool pxb_tv_try_primal(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu, const void* z, void* x_out, void* w,
                        double* norms, cudaStream_t s, int* rc);
 bool pxb_tv_try_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w, void* z, double* norms, cudaStream_t s, int* rc);
+
+// single-kernel iteration (pxb_tv_iter.cu); PXB_ENOSUP when the descriptor is outside its envelope
+int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out,
+                       void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s);

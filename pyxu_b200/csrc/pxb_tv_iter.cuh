@@ -1,0 +1,352 @@
+// pxb_tv_iter.cuh -- ONE kernel per PD3O / CondatVu iteration of a TV-type problem (K = first-order Gradient,
+// 'constant' boundaries): primal half-step, dual half-step and both RelError norms in a single sweep.
+//
+// Why: the two-kernel form (pxb_tv_kernels.cu) moves 60 B/voxel (fp32, 3-D) because w = 2x - tau grad f - u makes a
+// round trip through HBM and z is read twice.  Here a CTA owns a tile of TY rows x T2 columns and MARCHES along the
+// slowest axis with a direction ("M"): per plane it computes w for its tile plus a one-sample rim (phase A), keeps
+// the last four w planes in shared memory, and -- one plane behind -- finishes the dual update of its tile from
+// shared memory and from the z values it still holds in registers (phase C).  HBM traffic per voxel:
+//      read u, shift, z0, z1, z2  +  write u, z0, z1, z2   = 36 B      (+4 B when x is written, +4 B for x_prev)
+// The update is out of place (u_in/z_in -> u_out/z_out, ping-pong buffers on the host side): the rim of a tile is
+// another CTA's interior, so the old iterate must stay readable while the new one is written.
+//
+//   geometry      NDIR == 3: M = axis 0, rows = axis 1, columns = axis 2     (component k acts along axis k)
+//                 NDIR == 2: M = axis 1, no row axis (TY == 1), columns = axis 2; axis 0 and the batch index
+//                            enumerate independent images
+//   work item     (image, chunk of planes along M, tile); blockIdx.x enumerates them, tiles fastest, so CTAs that
+//                 run together march through the same planes and share their rims through L2
+//   ring          w(m) lives in slot m & 3;  phase A of plane m+1 / m+2 never touches a slot phase C of plane m
+//                 still reads, hence ONE __syncthreads per plane
+//
+// Like the other bodies these are __host__ __device__ so that tests/emu can run the exact per-thread code on the
+// CPU (phase A for every thread, then phase C for every thread: the same order the barrier enforces).
+#pragma once
+#include "pxb_tv_fast.cuh"
+
+struct PxbIterGeom {
+    int nM, nR, nC;       // extents along M, rows (1 when NDIR == 2), columns
+    int64_t sM, sR;       // strides in elements (columns: 1)
+    int chunk, nchunk;    // planes per work item, work items per image along M
+    int ntR, ntC;         // tiles per plane
+    int sub;              // images per batch item (n0 when NDIR == 2, else 1)
+    int64_t sub_stride;   // elements between those images
+    int64_t nimg;         // batch * sub
+    int64_t vol;          // elements between components / batch items
+    int ndir;
+    int open_lo, open_hi; // slab cuts along M (NDIR == 3): ghost planes hold the neighbour's u, z, shift
+    int64_t nblocks;
+};
+
+template <class T>
+struct PxbIterPtr {
+    const T* u_in;   // PD3O: u     CV: x
+    const T* z_in;
+    T* u_out;
+    T* z_out;
+    T* x_out;        // PD3O only, nullable: x is then not materialised (36 B/voxel form)
+    double* norms_x; // nullable pair per batch row (RelError[x])
+    double* norms_z;
+};
+
+struct PxbIterItem {
+    int64_t lin_base;  // offset of the image in u-like arrays
+    int64_t z_base;    // offset of component 0 of the image in z-like arrays
+    int64_t v_base;    // offset of the image inside its batch item
+    int64_t b;         // batch row
+    int m0, m1, r0, c0;
+};
+
+template <class T, int VEC, int TXL, int TY, int NDIR>
+struct PxbIterCfg {
+    static constexpr bool HASR = NDIR == 3;
+    static constexpr int NT = TXL * TY, T2 = TXL * VEC, RS = T2 + 2 * VEC;
+    static constexpr int R0 = HASR ? 1 : 0, ROWS = HASR ? TY + 2 : TY, SLOT = ROWS * RS, NSLOT = 4;
+    static constexpr int KM = 0, KR = HASR ? 1 : 0 /*unused when !HASR*/, KC = NDIR - 1;
+    static constexpr size_t SMEM = sizeof(T) * NSLOT * SLOT;
+};
+
+template <class T, int VEC>
+struct PxbIterThread {
+    T zc[3][VEC];     // z_in of the plane phase A just visited (this thread's own samples)
+    T zprev[3][VEC];  // ... of the plane before
+    double acc[4];    // RelError partial sums: x (num, den), z (num, den)
+};
+
+PXB_HD PxbIterItem pxb_iter_item(const PxbIterGeom& g, int64_t blk, int ty, int t2) {
+    PxbIterItem it;
+    const int tC = (int)(blk % g.ntC); blk /= g.ntC;
+    const int tR = (int)(blk % g.ntR); blk /= g.ntR;
+    const int ch = (int)(blk % g.nchunk); blk /= g.nchunk;
+    const int64_t b = blk / g.sub;
+    const int si = (int)(blk - b * g.sub);
+    it.b = b;
+    it.v_base = (int64_t)si * g.sub_stride;
+    it.lin_base = b * g.vol + it.v_base;
+    it.z_base = b * g.ndir * g.vol + it.v_base;
+    it.m0 = ch * g.chunk;
+    it.m1 = it.m0 + g.chunk < g.nM ? it.m0 + g.chunk : g.nM;
+    it.r0 = tR * ty;
+    it.c0 = tC * t2;
+    return it;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// w (and, when `store`, the new primal iterate) for W consecutive samples starting at (m, r, c).
+// The samples lie inside the domain or on a ghost plane of an open slab side.
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int W, int NDIR, int ALGO, bool NORMS>
+PXB_HD void pxb_iter_w(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int m, int r, int c,
+                       bool store, T* wv, T (*zc)[W], double* acc) {
+    constexpr bool HASR = NDIR == 3;
+    constexpr int KM = 0, KR = 1, KC = NDIR - 1;
+    const int64_t off = (int64_t)m * g.sM + (int64_t)r * g.sR + c;
+    const T* __restrict__ zb = a.z_in + it.z_base + off;
+    T kz[W], t[W];
+    // (K_k^T z)[s] = cm*z_k[s+e] + c0*z_k[s] + cp*z_k[s-e]
+    {
+        const T* __restrict__ zk = zb + KM * g.vol;
+        const PxbVec<T, W> cv = pxb_vload<T, W>(zk);
+        if (zc) for (int j = 0; j < W; ++j) zc[KM][j] = cv.v[j];
+        pxb_tv_taps_col<T, W>(zk, g.sM, cv, q.cm[KM], q.c0[KM], q.cp[KM], m > 0 || g.open_lo, m < g.nM - 1 || g.open_hi, kz);
+    }
+    if (HASR) {
+        const T* __restrict__ zk = zb + KR * g.vol;
+        const PxbVec<T, W> cv = pxb_vload<T, W>(zk);
+        if (zc) for (int j = 0; j < W; ++j) zc[KR][j] = cv.v[j];
+        pxb_tv_taps_col<T, W>(zk, g.sR, cv, q.cm[KR], q.c0[KR], q.cp[KR], r > 0, r < g.nR - 1, t);
+        for (int j = 0; j < W; ++j) kz[j] += t[j];
+    }
+    {
+        const T* __restrict__ zk = zb + KC * g.vol;
+        const PxbVec<T, W> cv = pxb_vload<T, W>(zk);
+        if (zc) for (int j = 0; j < W; ++j) zc[KC][j] = cv.v[j];
+        pxb_tv_taps_row<T, W>(zk, cv, q.cm[KC], q.c0[KC], q.cp[KC], c > 0, c + W < g.nC, t);
+        for (int j = 0; j < W; ++j) kz[j] += t[j];
+    }
+    const int64_t lin = it.lin_base + off;
+    const PxbVec<T, W> old = pxb_vload<T, W>(a.u_in + lin);
+    PxbVec<T, W> sh;
+    for (int j = 0; j < W; ++j) sh.v[j] = T(0);
+    if (q.fkind == PXB_F_SQL2) {
+        if (q.shift_mode == PXB_SHIFT_LIN) sh = pxb_vload<T, W>(q.shift + lin);
+        else if (q.shift_mode == PXB_SHIFT_VOL) sh = pxb_vload<T, W>(q.shift + it.v_base + off);
+        else if (q.shift_mode == PXB_SHIFT_SCALAR) { for (int j = 0; j < W; ++j) sh.v[j] = q.shift[0]; }
+        else if (q.shift_mode == PXB_SHIFT_MOD) { for (int j = 0; j < W; ++j) sh.v[j] = q.shift[(lin + j) % q.shift_period]; }
+    }
+    PxbVec<T, W> un, xo;
+    if (ALGO == PXB_PD3O) {
+        for (int j = 0; j < W; ++j) {
+            const T x = pxb_prox_eval<T>(q.gkind, q.gp0, q.gp1, old.v[j] - q.tau * kz[j], q.tau);
+            const T gf = (q.fkind == PXB_F_SQL2) ? (x + sh.v[j]) * q.two_alpha : T(0);
+            const T ut = x - q.tau * gf;
+            wv[j] = x + ut - old.v[j];
+            un.v[j] = q.one_m_rho * old.v[j] + q.rho * ut;
+            xo.v[j] = x;
+        }
+        if (store) {
+            if (NORMS && a.norms_x) {
+                const PxbVec<T, W> xprev = pxb_vload<T, W>(a.x_out + lin);
+                for (int j = 0; j < W; ++j) {
+                    const double dd = (double)xo.v[j] - (double)xprev.v[j];
+                    acc[0] += dd * dd;
+                    acc[1] += (double)xprev.v[j] * (double)xprev.v[j];
+                }
+            }
+            if (a.x_out) pxb_vstore<T, W>(a.x_out + lin, xo);
+        }
+    } else {
+        PxbVec<T, W> ga;
+        if (q.fkind == PXB_F_GRADARR) ga = pxb_vload<T, W>(q.garr + lin);
+        for (int j = 0; j < W; ++j) {
+            T gf = T(0);
+            if (q.fkind == PXB_F_SQL2) gf = (old.v[j] + sh.v[j]) * q.two_alpha;
+            else if (q.fkind == PXB_F_GRADARR) gf = ga.v[j];
+            const T vv = old.v[j] - q.tau * gf - q.tau * kz[j];
+            const T xt = pxb_prox_eval<T>(q.gkind, q.gp0, q.gp1, vv, q.tau);
+            wv[j] = T(2) * xt - old.v[j];
+            un.v[j] = q.rho * xt + q.one_m_rho * old.v[j];
+            if (NORMS && store && a.norms_x) {
+                const double dd = (double)un.v[j] - (double)old.v[j];
+                acc[0] += dd * dd;
+                acc[1] += (double)old.v[j] * (double)old.v[j];
+            }
+        }
+    }
+    if (store) pxb_vstore<T, W>(a.u_out + lin, un);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// phase A of plane m: w(m) of the tile (+ rim on planes the work item updates) -> ring slot m & 3
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int VEC, int TXL, int TY, int NDIR, int ALGO, bool NORMS>
+PXB_HD void pxb_iter_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid, int m,
+                            T* smem, PxbIterThread<T, VEC>& st) {
+    using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
+    T* __restrict__ slot = smem + (m & 3) * C::SLOT;
+    const bool plane_in = (m >= 0 || g.open_lo) && (m < g.nM || g.open_hi);
+    const bool own = m >= it.m0 && m < it.m1;
+    const int rl = tid / TXL, cx = tid - rl * TXL, cl = cx * VEC;
+    {
+        const int r = it.r0 + rl, c = it.c0 + cl;
+        PxbVec<T, VEC> wv;
+        if (plane_in && r < g.nR && c < g.nC) pxb_iter_w<T, VEC, NDIR, ALGO, NORMS>(q, g, it, a, m, r, c, own, wv.v, st.zc, st.acc);
+        else for (int j = 0; j < VEC; ++j) wv.v[j] = T(0);
+        pxb_vstore<T, VEC>(slot + (rl + C::R0) * C::RS + cl + VEC, wv);
+    }
+    if (!own) return;  // planes of the neighbouring chunks are only needed at the tile's own positions
+    if (C::HASR && tid < 2 * TXL) {  // rim rows r0-1 (needed when cm != 0) and r0+TY (cp != 0):  (K w)[s] = cm w[s-e] + c0 w[s] + cp w[s+e]
+        const bool top = tid < TXL;
+        const T coef = top ? q.cm[C::KR] : q.cp[C::KR];
+        if (coef != T(0)) {
+            const int r = top ? it.r0 - 1 : it.r0 + TY, c = it.c0 + cl;
+            PxbVec<T, VEC> wv;
+            if (r >= 0 && r < g.nR && c < g.nC) pxb_iter_w<T, VEC, NDIR, ALGO, false>(q, g, it, a, m, r, c, false, wv.v, (T(*)[VEC]) nullptr, st.acc);
+            else for (int j = 0; j < VEC; ++j) wv.v[j] = T(0);
+            pxb_vstore<T, VEC>(slot + (top ? 0 : TY + 1) * C::RS + cl + VEC, wv);
+        }
+    }
+    if (tid >= C::NT - 2 * TY) {  // rim columns c0-1 (cm != 0) and c0+T2 (cp != 0), one sample per row
+        const int h = tid - (C::NT - 2 * TY);
+        const bool left = h < TY;
+        const int hl = left ? h : h - TY;
+        const T coef = left ? q.cm[C::KC] : q.cp[C::KC];
+        if (coef != T(0)) {
+            const int r = it.r0 + hl, c = left ? it.c0 - 1 : it.c0 + C::T2;
+            T w1[1];
+            if (r < g.nR && c >= 0 && c < g.nC) pxb_iter_w<T, 1, NDIR, ALGO, false>(q, g, it, a, m, r, c, false, w1, (T(*)[1]) nullptr, st.acc);
+            else w1[0] = T(0);
+            slot[(hl + C::R0) * C::RS + (left ? VEC - 1 : VEC + C::T2)] = w1[0];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// phase C of plane mm: z_out(mm) = (1-rho) z + rho prox_{sigma h*}(z + sigma K w) for the tile, w from the ring,
+// z (old) from `zo` (registers).
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int VEC, int TXL, int TY, int NDIR, bool NORMS>
+PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid, int mm,
+                            const T* smem, const T (*zo)[VEC], double* acc) {
+    using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
+    const int rl = tid / TXL, cx = tid - rl * TXL, cl = cx * VEC;
+    const int r = it.r0 + rl, c = it.c0 + cl;
+    if (r >= g.nR || c >= g.nC) return;
+    const int cell = (rl + C::R0) * C::RS + cl + VEC;
+    const T* __restrict__ s1 = smem + (mm & 3) * C::SLOT + cell;
+    const PxbVec<T, VEC> wc = pxb_vload<T, VEC>(s1);
+    T p[NDIR][VEC];
+    {  // along M: neighbouring ring slots
+        T kw[VEC];
+        for (int j = 0; j < VEC; ++j) kw[j] = q.c0[C::KM] * wc.v[j];
+        if (q.cm[C::KM] != T(0)) {
+            const PxbVec<T, VEC> n = pxb_vload<T, VEC>(smem + ((mm - 1) & 3) * C::SLOT + cell);
+            for (int j = 0; j < VEC; ++j) kw[j] += q.cm[C::KM] * n.v[j];
+        }
+        if (q.cp[C::KM] != T(0)) {
+            const PxbVec<T, VEC> n = pxb_vload<T, VEC>(smem + ((mm + 1) & 3) * C::SLOT + cell);
+            for (int j = 0; j < VEC; ++j) kw[j] += q.cp[C::KM] * n.v[j];
+        }
+        for (int j = 0; j < VEC; ++j) p[C::KM][j] = zo[C::KM][j] + q.sigma * kw[j];
+    }
+    if (C::HASR) {  // along the rows of the slot
+        T kw[VEC];
+        for (int j = 0; j < VEC; ++j) kw[j] = q.c0[C::KR] * wc.v[j];
+        if (q.cm[C::KR] != T(0)) {
+            const PxbVec<T, VEC> n = pxb_vload<T, VEC>(s1 - C::RS);
+            for (int j = 0; j < VEC; ++j) kw[j] += q.cm[C::KR] * n.v[j];
+        }
+        if (q.cp[C::KR] != T(0)) {
+            const PxbVec<T, VEC> n = pxb_vload<T, VEC>(s1 + C::RS);
+            for (int j = 0; j < VEC; ++j) kw[j] += q.cp[C::KR] * n.v[j];
+        }
+        for (int j = 0; j < VEC; ++j) p[C::KR][j] = zo[C::KR][j] + q.sigma * kw[j];
+    }
+    {  // along the row (rim cells hold w of the neighbouring tile, or 0 outside the domain)
+        T kw[VEC];
+        pxb_tv_taps_row<T, VEC>(s1, wc, q.cp[C::KC], q.c0[C::KC], q.cm[C::KC], true, true, kw);
+        for (int j = 0; j < VEC; ++j) p[C::KC][j] = zo[C::KC][j] + q.sigma * kw[j];
+    }
+    double a0 = 0.0, a1 = 0.0;
+    for (int j = 0; j < VEC; ++j) {
+        T grp[PXB_MAX_DIRS];
+        for (int k = 0; k < NDIR; ++k) grp[k] = p[k][j];
+        pxb_dual_prox_group<T>(q.hkind, NDIR, q.lam, q.sigma, grp);
+        for (int k = 0; k < NDIR; ++k) {
+            const T zn = q.one_m_rho * zo[k][j] + q.rho * grp[k];
+            if (NORMS) {
+                const double dd = (double)zn - (double)zo[k][j];
+                a0 += dd * dd;
+                a1 += (double)zo[k][j] * (double)zo[k][j];
+            }
+            p[k][j] = zn;
+        }
+    }
+    T* __restrict__ zb = a.z_out + it.z_base + (int64_t)mm * g.sM + (int64_t)r * g.sR + c;
+    for (int k = 0; k < NDIR; ++k) {
+        PxbVec<T, VEC> o;
+        for (int j = 0; j < VEC; ++j) o.v[j] = p[k][j];
+        pxb_vstore<T, VEC>(zb + k * g.vol, o);
+    }
+    if (NORMS) { acc[2] += a0; acc[3] += a1; }
+}
+
+// The marching loop of one thread between barriers (`sync` is __syncthreads on the device; the host emulation
+// runs the two phases as separate sweeps over the threads instead of calling this).
+//   lag = 1 when (K w)[m] needs w[m+1] (cp != 0 along M): phase C then trails phase A by one plane.
+struct PxbIterRange {
+    int mlo, mhi, lag;
+};
+template <class T>
+PXB_HD PxbIterRange pxb_iter_range(const PxbTvP<T>& q, const PxbIterItem& it) {
+    PxbIterRange R;
+    R.lag = q.cp[0] != T(0) ? 1 : 0;
+    R.mlo = it.m0 - (q.cm[0] != T(0) ? 1 : 0);
+    R.mhi = it.m1 + R.lag;
+    return R;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: eligibility + geometry (shared by the launcher and by tests/emu)
+// ---------------------------------------------------------------------------------------------------------
+// returns 0 when the single-kernel iteration applies, else a reason code (> 0)
+inline int pxb_iter_setup(const pxb_grad_desc& d, const pxb_pds_params& P, int vec, int ty, int t2, int chunk_hint, PxbTvCoef& cf,
+                          PxbIterGeom& g) {
+    if (!pxb_tv_fast_coefs(d, cf)) return 1;
+    if (d.ndir != 2 && d.ndir != 3) return 2;
+    if (P.hkind != PXB_DUAL_L21 && P.hkind != PXB_DUAL_L1) return 3;
+    for (int k = 0; k < d.ndir; ++k)
+        if (d.mode[3 - d.ndir + k] != PXB_CONSTANT) return 4;
+    if (d.shape[2] % vec) return 5;
+    const PxbGeom gg = pxb_geom(d.shape);
+    g.ndir = d.ndir;
+    g.vol = pxb_vol(gg, d.slab);
+    g.nC = gg.n2;
+    if (d.ndir == 3) {
+        g.nM = gg.n0; g.nR = gg.n1; g.sM = gg.s0; g.sR = gg.s1;
+        g.sub = 1; g.sub_stride = 0;
+        g.open_lo = d.slab.open_lo; g.open_hi = d.slab.open_hi;
+        // a ghost w plane needs z one plane further out when the stencil along M is two-sided
+        const bool two_sided = cf.cm[0] != 0.0 && cf.cp[0] != 0.0;
+        if ((g.open_lo || g.open_hi) && d.slab.halo < (two_sided ? 2 : 1)) return 6;
+    } else {
+        if (d.slab.halo != 0 || d.slab.open_lo || d.slab.open_hi) return 7;
+        g.nM = gg.n1; g.nR = 1; g.sM = gg.s1; g.sR = 0;
+        g.sub = gg.n0; g.sub_stride = gg.s0;
+        g.open_lo = g.open_hi = 0;
+    }
+    g.nimg = d.batch * g.sub;
+    g.ntR = (g.nR + ty - 1) / ty;
+    g.ntC = (g.nC + t2 - 1) / t2;
+    const int64_t tiles = (int64_t)g.ntR * g.ntC * g.nimg;
+    int chunk = chunk_hint;
+    if (chunk <= 0) {  // enough work items for ~16 CTAs per SM, chunks no shorter than 16 planes (rim-plane overhead 1/chunk)
+        chunk = g.nM < 128 ? g.nM : 128;
+        while (chunk > 16 && tiles * ((g.nM + chunk - 1) / chunk) < 148 * 16) chunk = (chunk + 1) / 2;
+    }
+    if (chunk > g.nM) chunk = g.nM;
+    g.chunk = chunk;
+    g.nchunk = (g.nM + chunk - 1) / chunk;
+    g.nblocks = tiles * g.nchunk;
+    if (g.nblocks <= 0 || g.nblocks > 0x7fffffffLL) return 8;
+    return 0;
+}

@@ -9,8 +9,10 @@ iteration executes: `m_step()` asks a planner (``_Plan``) which of three executi
 
 * ``fused``  -- h o K is a (scaled) L21 / L1 norm of a Gradient stack, g has a pointwise prox and f is
                  null / a shifted squared-l2 data term (or, for CondatVu, anything differentiable):
-                 one iteration = pxb_pds_primal + pxb_pds_dual, two passes over the volume, with the
-                 RelError norms accumulated in the same passes.
+                 one iteration = ONE kernel (pxb_pds_iter: primal + dual half-steps + RelError norms in a
+                 single sweep, ping-pong buffers) when the Gradient is a 2-/3-direction first-order scheme
+                 with 'constant' boundaries; otherwise pxb_pds_primal + pxb_pds_dual (two sweeps).  PD3O's
+                 x is then only materialised when something reads it (stopping criterion, log, solution).
 * ``semi``   -- same h o K, but PD3O with a non-local f (e.g. a blur in the data term): K^T z and the
                  prox are separate passes, the dual half-step stays fused.
 * ``generic``-- any other composition: the reference's formulas evaluated through the operators'
@@ -45,6 +47,7 @@ class _Plan:
     def __init__(self, solver, algo, x0):
         f, g, h, Kop = solver._f, solver._g, solver._h, solver._K
         self.algo = algo
+        self._x0_like = x0
         self.kind = "generic"
         self.batch = max(1, x0.numel() // x0.shape[-1])
         self.gspec = g._prox_spec()
@@ -90,7 +93,15 @@ class _Plan:
         self.K = Kop
         if self.kind != "generic":
             self.gdesc = Kop._desc(self.batch, A.dcode(x0))
-            self.w = A.empty_like(x0)
+        self._w = None
+        self.iter_ok = None if self.kind == "fused" else False  # single-kernel iteration: None = not tried yet
+        self.alt = None  # (primal, dual) spare buffers of the ping-pong
+
+    @property
+    def w(self):  # work array of the two-sweep form, allocated on first use
+        if self._w is None:
+            self._w = A.empty_like(self._x0_like)
+        return self._w
 
     def params(self, mst, garr=None):
         p = K.PdsParams()
@@ -160,26 +171,81 @@ class _PrimalDualSplitting(Solver):
 
     def _setup_fused_norms(self):
         """If the stopping criterion is RelError on x / z evaluated every iteration, let the update kernels
-        accumulate its norms (no extra pass, no x_prev copy)."""
+        accumulate its norms (no extra pass, no x_prev copy).  Also decides whether PD3O's x must be written by
+        every iteration or only when somebody asks for it (`_materialize`)."""
         import torch
 
         mst, ast = self._mstate, self._astate
-        want = ast["stop_crit"]._fused_vars() if ast["stop_crit"] is not None else frozenset()
-        self._nx = self._nz = None
-        if self._plan.kind == "generic" or ast["stop_rate"] != 1 or not want <= {"x", "z"}:
-            return
-        if self._plan.kind == "semi":
-            want = want - {"x"}
-        rows = self._plan.batch
-        fused = {}
-        if "x" in want:
-            self._nx = torch.zeros((rows, 2), dtype=torch.float64, device=mst["x"].device)
-            fused["x"] = self._nx
-        if "z" in want and not self._plan.h_null:
-            self._nz = torch.zeros((rows, 2), dtype=torch.float64, device=mst["x"].device)
-            fused["z"] = self._nz
-        if fused:
-            mst["_fused_norms"] = fused
+        crit = ast["stop_crit"]
+        want = crit._fused_vars() if crit is not None else frozenset()
+        self._nx = self._nz = self._nrm = None
+        self._x_stale = False
+        reads = crit._state_vars() if crit is not None else None
+        fusable = self._plan.kind != "generic" and ast["stop_rate"] == 1 and want <= {"x", "z"}
+        if fusable:
+            if self._plan.kind == "semi":
+                want = want - {"x"}
+            if self._plan.h_null:
+                want = want - {"z"}
+            rows = self._plan.batch
+            if want:
+                # one (2, rows, 2) buffer: a single memset per iteration and a single 32-byte readback
+                self._nrm = torch.zeros((2, rows, 2), dtype=torch.float64, device=mst["x"].device)
+                fused = {"_all": self._nrm, "_host": None, "_stamp": -1}
+                if "x" in want:
+                    self._nx = fused["x"] = self._nrm[0]
+                if "z" in want:
+                    self._nz = fused["z"] = self._nrm[1]
+                mst["_fused_norms"] = fused
+        else:
+            want = frozenset()
+        # x is read behind the solver's back by: an unknown criterion, a criterion on "x" that is not served by the
+        # fused norms, or objective tracking
+        self._x_every = bool(ast["track_objective"]) or reads is None or ("x" in reads and "x" not in want)
+
+    def _zero_norms(self):
+        if self._nrm is not None:
+            self._nrm.zero_()
+            self._mstate["_fused_norms"]["_stamp"] = -1
+
+    def _iter_fused(self, algo, garr=None):
+        """One iteration as a single kernel (pxb_pds_iter).  Returns False when the problem is outside the kernel's
+        envelope (decided once, on the first call: nothing was launched) -- the caller then runs the two-sweep form."""
+        mst, pl = self._mstate, self._plan
+        key = "u" if algo == K.ALGO_PD3O else "x"
+        if pl.alt is None:
+            pl.alt = (A.empty_like(mst[key]), A.empty_like(mst["z"]))
+        want_x = algo == K.ALGO_PD3O and (self._nx is not None or self._x_every)
+        self._zero_norms()
+        p = pl.params(mst, garr=garr)
+        if self._probe:
+            self._probe("iter_begin")
+        rc = K.lib().pxb_pds_iter(algo, C.byref(pl.gdesc), C.byref(p), A.ptr(mst[key]), A.ptr(mst["z"]), A.ptr(pl.alt[0]), A.ptr(pl.alt[1]),
+                                  A.ptr(mst["x"]) if want_x else None, A.ptr(self._nx), A.ptr(self._nz), A.stream())
+        if rc == -3 and pl.iter_ok is None:  # PXB_ENOSUP
+            pl.iter_ok, pl.alt = False, None
+            return False
+        K.check(rc, "pxb_pds_iter")
+        if self._probe:
+            self._probe("iter_end")
+        pl.iter_ok = True
+        new_primal, new_dual = pl.alt
+        pl.alt = (mst[key], mst["z"])  # the previous iterate: next call's output buffers (and what a lazy x is rebuilt from)
+        mst[key], mst["z"] = new_primal, new_dual
+        if algo == K.ALGO_PD3O and not want_x:
+            self._x_stale = True
+        return True
+
+    def _materialize(self, name):
+        """x of PD3O is not written by the single-kernel iteration unless something needs it every step; rebuild it
+        on demand from the previous iterate: x_k = prox_{tau g}(u_{k-1} - tau K^T z_{k-1})  (pds.py:747-750)."""
+        mst = self._mstate
+        if name == "x" and getattr(self, "_x_stale", False):
+            u_prev, z_prev = self._plan.alt
+            ktz = self._K.jacobian(u_prev).adjoint(z_prev)
+            mst["x"] = self._prox_g(1.0, u_prev, -mst["tau"], ktz, out=mst["x"])
+            self._x_stale = False
+        return mst.get(name)
 
     def default_stop_crit(self):
         stop_crit_x = pxs.RelError(eps=1e-4, var="x", f=None, norm=2, satisfy_all=True)
@@ -197,7 +263,7 @@ class _PrimalDualSplitting(Solver):
         return self._logged("x" if which == "primal" else "z")  # only the requested variable leaves the device
 
     def objective_func(self):
-        x = self._mstate["x"]
+        x = self._materialize("x")
         out = self._f(x) + self._g(x)
         if not _is_null(self._h):
             out = out + self._h(self._K(x))
@@ -237,8 +303,6 @@ class _PrimalDualSplitting(Solver):
     # -- shared kernels ---------------------------------------------------------------------
     def _dual_fused(self, w):
         mst, pl = self._mstate, self._plan
-        if self._nz is not None:
-            self._nz.zero_()
         p = pl.params(mst, garr=w)  # garr unused by the dual kernel
         rc = K.lib().pxb_pds_dual(C.byref(pl.gdesc), C.byref(p), A.ptr(w), A.ptr(mst["z"]), A.ptr(self._nz), A.stream())
         K.check(rc, "pxb_pds_dual")
@@ -278,8 +342,9 @@ class CondatVu(_PrimalDualSplitting):
         mst, pl = self._mstate, self._plan
         if pl.kind == "fused":
             garr = self._f.grad(mst["x"]) if pl.fkind == K.F_GRADARR else None
-            if self._nx is not None:
-                self._nx.zero_()
+            if pl.iter_ok is not False and self._iter_fused(K.ALGO_CV, garr=garr):
+                return
+            self._zero_norms()
             p = pl.params(mst, garr=garr)
             rc = K.lib().pxb_pds_primal(K.ALGO_CV, C.byref(pl.gdesc), C.byref(p), A.ptr(mst["x"]), A.ptr(mst["z"]), None, None,
                                         A.ptr(pl.w), A.ptr(self._nx), A.stream())
@@ -348,8 +413,9 @@ class PD3O(_PrimalDualSplitting):
         mst, pl = self._mstate, self._plan
         tau, rho = mst["tau"], mst["rho"]
         if pl.kind == "fused":
-            if self._nx is not None:
-                self._nx.zero_()
+            if pl.iter_ok is not False and self._iter_fused(K.ALGO_PD3O):
+                return
+            self._zero_norms()
             p = pl.params(mst)
             if self._probe:
                 self._probe("primal_begin")
@@ -371,6 +437,7 @@ class PD3O(_PrimalDualSplitting):
             # w = x + u_temp - u = 2x - tau grad f(x) - u
             w = kr.lincomb(2.0, x, -tau, gf, -1.0, u, out=getattr(pl, "w", None))
             if pl.kind == "semi":
+                self._zero_norms()
                 self._dual_fused(w)
             else:
                 self._dual_generic(w)

@@ -39,6 +39,9 @@ class MaxIter(StoppingCriterion):
     def clear(self):
         self._i = 0
 
+    def _state_vars(self):
+        return frozenset()
+
     def _needs_host_sync(self):
         return False
 
@@ -49,6 +52,9 @@ class ManualStop(StoppingCriterion):
 
     def info(self):
         return dict()
+
+    def _state_vars(self):
+        return frozenset()
 
     def _needs_host_sync(self):
         return False
@@ -74,6 +80,9 @@ class MaxDuration(StoppingCriterion):
     def clear(self):
         self._t_start = dt.datetime.now()
         self._t_now = self._t_start
+
+    def _state_vars(self):
+        return frozenset()
 
     def _needs_host_sync(self):
         return False
@@ -102,6 +111,9 @@ class Memorize(StoppingCriterion):
     def clear(self):
         self._val = np.r_[0]
 
+    def _state_vars(self):
+        return frozenset([self._var])
+
 
 def _device_norm(x, ord):
     """(rows, 1) host array of L`ord` norms of the rows of device array x."""
@@ -111,6 +123,17 @@ def _device_norm(x, ord):
     import torch  # non-Euclidean norms: rare, off the hot path
 
     return torch.linalg.vector_norm(x.reshape(rows, -1).double(), ord=ord, dim=-1, keepdim=True).cpu().numpy()
+
+
+def _fused_host(fused, var):
+    """Host copy of the (rows, 2) sums of `var`; all fused sums of an iteration cross the bus in ONE readback
+    (the solver resets `_stamp` when it zeroes the buffer for the next iteration)."""
+    if "_all" not in fused:
+        return fused[var].cpu().numpy()
+    if fused["_stamp"] != 0:
+        fused["_host"] = fused["_all"].cpu().numpy()
+        fused["_stamp"] = 0
+    return fused["_host"][0 if var == "x" else 1]
 
 
 class _NormCriterion(StoppingCriterion):
@@ -132,6 +155,9 @@ class _NormCriterion(StoppingCriterion):
 
     def _label(self):
         return f"{type(self).__name__}[{self._var}]"
+
+    def _state_vars(self):
+        return frozenset([self._var])
 
     def info(self):
         if self._val.size == 1:
@@ -176,7 +202,7 @@ class RelError(_NormCriterion):
                 self._started = True
                 self._val = np.zeros((fused.shape[0], 1))
                 return False
-            sq = fused.cpu().numpy()
+            sq = _fused_host(state["_fused_norms"], self._var)
             num, den = np.sqrt(sq[:, :1]), np.sqrt(sq[:, 1:2])
             return self._decide(num, den)
 

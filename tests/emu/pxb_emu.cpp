@@ -9,6 +9,8 @@
 
 #include "../../pyxu_b200/csrc/pxb_core.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_fast.cuh"
+#include "../../pyxu_b200/csrc/pxb_tv_iter.cuh"
+#include <vector>
 
 #define FOR_VOX(batch, g)                              \
     for (int64_t b = 0; b < (batch); ++b)              \
@@ -98,7 +100,69 @@ static int t_tv_dir(int vec, int which, int algo, const pxb_grad_desc* K, const 
     return t_tv_vec<T, 1>(vec, which, algo, K, cf, p, xu, z, x_out, w, norms);
 }
 
+// single-kernel iteration (pxb_tv_iter.cuh): every CTA is replayed as "phase A for all threads, then phase C for
+// all threads" per plane -- the order the device's one barrier per plane enforces -- with the CTA's shared-memory
+// ring as a host array.  Same template instances as the launcher in pxb_tv_iter.cu.
+template <class T, int VEC, int TXL, int TY, int NDIR, int ALGO, bool NORMS>
+static int t_iter_cfg(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, int chunk) {
+    using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
+    PxbTvCoef cf;
+    PxbIterGeom g;
+    if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, cf, g)) return -100 - why;
+    PxbTvP<T> q;
+    pxb_tv_prepare<T>(*K, cf, *p, q);
+    std::vector<T> smem(C::NSLOT * C::SLOT);
+    std::vector<PxbIterThread<T, VEC>> st(C::NT);
+    for (int64_t blk = 0; blk < g.nblocks; ++blk) {
+        const PxbIterItem it = pxb_iter_item(g, blk, TY, C::T2);
+        const PxbIterRange R = pxb_iter_range<T>(q, it);
+        for (auto& s : st) std::memset(&s, 0, sizeof(s));
+        for (auto& v : smem) v = T(12345);  // poison: cells that are read must have been written
+        for (int m = R.mlo; m < R.mhi; ++m) {
+            for (int tid = 0; tid < C::NT; ++tid) pxb_iter_phaseA<T, VEC, TXL, TY, NDIR, ALGO, NORMS>(q, g, it, a, tid, m, smem.data(), st[tid]);
+            const int mm = m - R.lag;
+            for (int tid = 0; tid < C::NT; ++tid) {
+                if (mm >= it.m0 && mm < it.m1)
+                    pxb_iter_phaseC<T, VEC, TXL, TY, NDIR, NORMS>(q, g, it, a, tid, mm, smem.data(), R.lag ? st[tid].zprev : st[tid].zc, st[tid].acc);
+                std::memcpy(st[tid].zprev, st[tid].zc, sizeof(st[tid].zc));
+            }
+        }
+        if (NORMS)
+            for (int tid = 0; tid < C::NT; ++tid) {
+                if (a.norms_x) { a.norms_x[2 * it.b] += st[tid].acc[0]; a.norms_x[2 * it.b + 1] += st[tid].acc[1]; }
+                if (a.norms_z) { a.norms_z[2 * it.b] += st[tid].acc[2]; a.norms_z[2 * it.b + 1] += st[tid].acc[3]; }
+            }
+    }
+    return 0;
+}
+template <class T, int NDIR, int ALGO, bool NORMS>
+static int t_iter_tile(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, int chunk) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (NDIR == 3) return t_iter_cfg<T, VEC, 32, 8, 3, ALGO, NORMS>(K, p, a, chunk);
+    if (K->shape[2] <= 128 * VEC) return t_iter_cfg<T, VEC, 128, 1, 2, ALGO, NORMS>(K, p, a, chunk);
+    return t_iter_cfg<T, VEC, 256, 1, 2, ALGO, NORMS>(K, p, a, chunk);
+}
+template <class T>
+static int t_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
+                  void* x_out, double* nx, double* nz, int chunk) {
+    PxbIterPtr<T> a{(const T*)u_in, (const T*)z_in, (T*)u_out, (T*)z_out, (T*)x_out, nx, nz};
+    const bool norms = nx || nz;
+#define EMU_ITER_CASE(ND, AL) \
+    if (K->ndir == ND && algo == AL) return norms ? t_iter_tile<T, ND, AL, true>(K, p, a, chunk) : t_iter_tile<T, ND, AL, false>(K, p, a, chunk);
+    EMU_ITER_CASE(3, PXB_PD3O)
+    EMU_ITER_CASE(3, PXB_CV)
+    EMU_ITER_CASE(2, PXB_PD3O)
+    EMU_ITER_CASE(2, PXB_CV)
+#undef EMU_ITER_CASE
+    return -102;
+}
+
 extern "C" {
+int emu_tv_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
+                void* x_out, double* nx, double* nz, int chunk) {
+    if (K->dtype == PXB_F32) return t_iter<float>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);
+    return t_iter<double>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);
+}
 // which: 0 primal, 1 dual.  Returns -2 when the descriptor is not eligible for the fast bodies.
 int emu_tv_fast(int vec, int which, int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu, const void* z, void* x_out,
                 void* w, double* norms) {

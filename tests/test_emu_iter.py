@@ -1,0 +1,169 @@
+"""
+CPU checks of the single-kernel PD3O / CondatVu iteration (pyxu_b200/csrc/pxb_tv_iter.cuh).
+
+The per-thread phases of the CUDA kernel are compiled for the host (tests/emu) and replayed CTA by CTA with the
+shared-memory ring as a host array.  They must reproduce (a) the two-pass kernel bodies on random states for
+every finite-difference scheme, tile / chunk / batch layout, and (b) the fixtures produced by the real reference.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import emu_util as E
+import pyxu_b200.operator as pxo
+from conftest import golden
+from pyxu_b200 import _cabi as K
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(np.asarray(a, dtype=np.float64).ravel() - np.asarray(b, dtype=np.float64).ravel()) / max(np.linalg.norm(np.asarray(b, dtype=np.float64).ravel()), 1e-300))
+
+
+def two_pass(algo, d, P, u, z, x, nx=None, nz=None):
+    """reference for the emulation: generic per-voxel bodies, primal pass then dual pass (in place)."""
+    w = np.zeros_like(u)
+    E.lib().emu_pds_primal(algo, C.byref(d), C.byref(P), E.p(u), E.p(z), None, E.p(x) if algo == K.ALGO_PD3O else None, E.p(w), E.p(nx))
+    E.lib().emu_pds_dual(C.byref(d), C.byref(P), E.p(w), E.p(z), E.p(nz))
+
+
+def one_pass(algo, d, P, u, z, x, nx=None, nz=None, chunk=0):
+    u2, z2 = np.full_like(u, np.nan), np.full_like(z, np.nan)
+    rc = E.lib().emu_tv_iter(algo, C.byref(d), C.byref(P), E.p(u), E.p(z), E.p(u2), E.p(z2), E.p(x) if algo == K.ALGO_PD3O else None,
+                             E.p(nx), E.p(nz), chunk)
+    assert rc == 0, rc
+    return u2, z2
+
+
+SCHEMES = ["forward", "backward", "central"]
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("algo", [K.ALGO_PD3O, K.ALGO_CV])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_iter_equals_two_pass_3d(scheme, algo, dtype):
+    rng = np.random.default_rng(5)
+    vec = 2 if dtype == np.float64 else 4
+    # > 1 tile along rows (8) and columns (32*vec), ragged in both, several chunks of planes
+    shape = (7, 19, 32 * vec * 2 + 3 * vec)
+    Kop = pxo.Gradient(arg_shape=shape, scheme=scheme, sampling=(1.0, 0.5, 2.0))
+    d = Kop._desc(1, E.dcode(np.zeros(1, dtype=dtype)))
+    shift = rng.standard_normal(Kop.dim).astype(dtype)
+    for hkind, gspec in ((K.DUAL_L21, (K.PROX_POS, 0.0, 0.0)), (K.DUAL_L1, (K.PROX_BOX, 0.2, 0.9))):
+        P = E.pds_params(0.21, 0.19, 0.9, gspec=gspec, fkind=K.F_SQL2, alpha=0.7, shift=shift, hkind=hkind, lam=0.3)
+        for chunk in (0, 3, 1):
+            u = rng.standard_normal(Kop.dim).astype(dtype)
+            x = rng.standard_normal(Kop.dim).astype(dtype)
+            z = rng.standard_normal(Kop.codim).astype(dtype)
+            ua, za, xa = u.copy(), z.copy(), x.copy()
+            nxa, nza, nxb, nzb = np.zeros(2), np.zeros(2), np.zeros(2), np.zeros(2)
+            two_pass(algo, d, P, ua, za, xa, nxa, nza)
+            xb = x.copy()
+            ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=chunk)
+            tol = 1e-13 if dtype == np.float64 else 2e-6
+            assert relerr(ub, ua) < tol and relerr(zb, za) < tol, (scheme, algo, chunk)
+            if algo == K.ALGO_PD3O:
+                assert relerr(xb, xa) < tol
+            assert np.allclose(nxa, nxb, rtol=1e-5 if dtype == np.float32 else 1e-10) and np.allclose(nza, nzb, rtol=1e-5 if dtype == np.float32 else 1e-10)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("width", [40, 300, 1100])
+def test_iter_equals_two_pass_2d_batched(scheme, width):
+    """2-D images (marching along the rows), a batch of them, narrow and wide tile variants."""
+    rng = np.random.default_rng(7)
+    shape, batch = (13, width), 3
+    Kop = pxo.Gradient(arg_shape=shape, scheme=scheme)
+    d = Kop._desc(batch, K.F32)
+    shift = rng.standard_normal(Kop.dim).astype(np.float32)  # broadcast over the batch (period = one image)
+    P = E.pds_params(0.3, 0.25, 1.0, gspec=(K.PROX_L1, 0.05, 0.0), fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L21, lam=0.2)
+    u = rng.standard_normal((batch, Kop.dim)).astype(np.float32)
+    x = rng.standard_normal((batch, Kop.dim)).astype(np.float32)
+    z = rng.standard_normal((batch, Kop.codim)).astype(np.float32)
+    for algo in (K.ALGO_PD3O, K.ALGO_CV):
+        for chunk in (0, 4):
+            ua, za, xa = u.copy(), z.copy(), x.copy()
+            nxa, nza, nxb, nzb = (np.zeros(2 * batch) for _ in range(4))
+            two_pass(algo, d, P, ua, za, xa, nxa, nza)
+            xb = x.copy()
+            ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=chunk)
+            assert relerr(ub, ua) < 2e-6 and relerr(zb, za) < 2e-6
+            assert np.allclose(nxa, nxb, rtol=1e-5) and np.allclose(nza, nzb, rtol=1e-5)
+
+
+def test_iter_cv_gradarr_and_stacked_2d():
+    """CondatVu with a precomputed grad f array; 2-D gradient over the last two axes of a 3-D arg_shape."""
+    rng = np.random.default_rng(9)
+    shape = (3, 11, 24)
+    Kop = pxo.Gradient(arg_shape=shape, directions=(1, 2))
+    d = Kop._desc(2, K.F64)
+    garr = rng.standard_normal((2, Kop.dim))
+    P = E.pds_params(0.3, 0.25, 0.8, gspec=(K.PROX_POS, 0.0, 0.0), fkind=K.F_GRADARR, garr=garr, hkind=K.DUAL_L21, lam=0.2)
+    u, z = rng.standard_normal((2, Kop.dim)), rng.standard_normal((2, Kop.codim))
+    ua, za = u.copy(), z.copy()
+    two_pass(K.ALGO_CV, d, P, ua, za, None)
+    ub, zb = one_pass(K.ALGO_CV, d, P, u, z, None, chunk=5)
+    assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13
+
+
+def test_iter_not_eligible():
+    Kop = pxo.Gradient(arg_shape=(8, 16), mode="reflect")
+    d = Kop._desc(1, K.F64)
+    P = E.pds_params(0.3, 0.25, 1.0, hkind=K.DUAL_L21, lam=0.2)
+    a = np.zeros(Kop.dim)
+    z = np.zeros(Kop.codim)
+    assert E.lib().emu_tv_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), E.p(a), E.p(z), E.p(a.copy()), E.p(z.copy()), None, None, None, 0) == -104
+    Kop = pxo.Gradient(arg_shape=(8, 15))  # last axis not a multiple of the vector width
+    d = Kop._desc(1, K.F64)
+    assert E.lib().emu_tv_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), E.p(a), E.p(z), E.p(a.copy()), E.p(z.copy()), None, None, None, 0) == -105
+
+
+def _solve(name, algo, shape, n_iter, lam, gspec, y, x0, dtype=np.float64):
+    g = golden("solvers.npz")
+    tau, sigma, rho = (float(g[f"{name}/{k}"]) for k in ("tau", "sigma", "rho"))
+    Kop = pxo.Gradient(arg_shape=shape)
+    shift = np.ascontiguousarray(-y.reshape(-1), dtype=dtype)
+    P = E.pds_params(tau, sigma, rho, gspec=gspec, fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L21, lam=lam)
+    d = Kop._desc(1, E.dcode(shift))
+    x = np.ascontiguousarray(x0, dtype=dtype).copy()
+    z = E.gradient_run(Kop, x, False)
+    u = x.copy()
+    nx, nz = np.zeros(2), np.zeros(2)
+    hist = []
+    for _ in range(n_iter):
+        nx[:] = 0
+        nz[:] = 0
+        if algo == K.ALGO_PD3O:
+            u, z = one_pass(algo, d, P, u, z, x, nx, nz)
+        else:
+            x, z = one_pass(algo, d, P, x, z, None, nx, nz)
+        hist.append((nx.copy(), nz.copy()))
+    return x, z, hist, g
+
+
+POS = (K.PROX_POS, 0.0, 0.0)
+
+
+def test_iter_golden_pd3o_2d_3d_cv():
+    """N iterations of the single-kernel form against the real reference's NumPy float64 solver (<= 1e-10)."""
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    x, z, *_ = _solve("pd3o_tv2d/s1", K.ALGO_PD3O, (32, 40), 60, 0.1, POS, y, y.reshape(-1))
+    assert relerr(x, g["pd3o_tv2d/s1/x"]) < 1e-10 and relerr(z, g["pd3o_tv2d/s1/z"]) < 1e-10
+    x, z, *_ = _solve("cv_tv2d", K.ALGO_CV, (32, 40), 60, 0.1, POS, y, y.reshape(-1))
+    assert relerr(x, g["cv_tv2d/x"]) < 1e-10 and relerr(z, g["cv_tv2d/z"]) < 1e-10
+    y3 = g["pd3o_tv3d/y"]
+    x, z, hist, _ = _solve("pd3o_tv3d", K.ALGO_PD3O, (10, 12, 14), 50, 0.08, POS, y3, y3.reshape(-1))
+    assert relerr(x, g["pd3o_tv3d/x"]) < 1e-10 and relerr(z, g["pd3o_tv3d/z"]) < 1e-10
+    # fused RelError sums of the last iteration == recomputed from iterates 49 -> 50
+    xa, za, *_ = _solve("pd3o_tv3d", K.ALGO_PD3O, (10, 12, 14), 49, 0.08, POS, y3, y3.reshape(-1))
+    nx, nz = hist[-1]
+    assert abs(nx[0] - np.sum((x - xa) ** 2)) < 1e-12 * (1 + nx[0]) and abs(nx[1] - np.sum(xa**2)) < 1e-9 * nx[1]
+    assert abs(nz[0] - np.sum((z - za) ** 2)) < 1e-12 * (1 + nz[0]) and abs(nz[1] - np.sum(za**2)) < 1e-9 * nz[1]
+
+
+def test_iter_golden_f32():
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    x, z, *_ = _solve("pd3o_tv2d/s1", K.ALGO_PD3O, (32, 40), 60, 0.1, POS, y, y.reshape(-1), dtype=np.float32)
+    assert relerr(x, g["pd3o_tv2d/s1/x"]) < 1e-4
