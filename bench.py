@@ -31,8 +31,9 @@ sys.path.insert(0, ROOT)
 METRIC, UNIT = "pd3o_tv_gvoxel_iter_per_s", "Gvoxel-iter/s"
 LAM = 0.08
 # algorithmic HBM bytes per voxel per launch (fp32; DESIGN.md "Kernels"):
-#   primal: read u, z0, z1, z2, y  + write x, w, u  = 8 floats;   dual: read w, z0..2 + write z0..2 = 7 floats
-BYTES_PER_VOXEL = {"pxb_pds_primal": 8 * 4, "pxb_pds_dual": 7 * 4}
+#   single-kernel iteration: read u, y, z0, z1, z2 + write u, z0, z1, z2 = 9 floats (x is materialised on demand)
+#   two-sweep form:  primal: read u, z0, z1, z2, y + write x, w, u = 8 floats;   dual: read w, z0..2 + write z0..2 = 7 floats
+BYTES_PER_VOXEL = {"pxb_pds_iter": 9 * 4, "pxb_pds_primal": 8 * 4, "pxb_pds_dual": 7 * 4}
 
 
 def parse():
@@ -45,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-size", type=int, default=320, help="cube edge of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--two-sweep", action="store_true", help="force the two-kernel form of the iteration (A/B comparison)")
     return ap.parse_args()
 
 
@@ -272,6 +274,8 @@ def main():
         slv = pxs.PD3O(f=f, g=g, h=h, K=Kop, show_progress=False)
         slv.fit(x0=y.reshape(-1), mode=Mode.MANUAL, stop_crit=pxst.ManualStop())
         assert slv._plan.kind == "fused"
+        if args.two_sweep:
+            slv._plan.iter_ok = False
         step = slv.m_step
         pending = []
 
@@ -318,6 +322,8 @@ def main():
             tags.setdefault("pxb_pds_primal", []).append(a.elapsed_time(b))
         if t0 == "primal_end" and t1 == "dual_end":
             tags.setdefault("pxb_pds_dual", []).append(a.elapsed_time(b))
+        if t0 == "iter_begin" and t1 == "iter_end":
+            tags.setdefault("pxb_pds_iter", []).append(a.elapsed_time(b))
     peak, peak_src = measured_peak()
     roof = {}
     for kname, ts in tags.items():

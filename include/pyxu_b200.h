@@ -208,6 +208,10 @@ int pxb_pds_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w,
  * With an open slab side the ghost planes of xu_in, z_in (and of the shift array) must hold the neighbour's data. */
 int pxb_pds_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in,
                  void* xu_out, void* z_out, void* x_out, double* norms_x, double* norms_z, void* stream);
+/* Which implementation pxb_pds_iter uses: 0 = automatic (3-D: TMA-staged pipeline, 2-D: direct loads),
+ * 1 = direct-load form only, 2 = TMA form only (PXB_ENOSUP when it does not apply).  Environment variable
+ * PXB_TV_ITER=direct|tma sets the initial value.  For A/B measurements and tests. */
+int pxb_set_iter_path(int path);
 /* same, with the number of planes one thread block marches through fixed by the caller (tuning / tests) */
 int pxb_pds_iter_chunked(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in,
                          void* xu_out, void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk, void* stream);

@@ -8,6 +8,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "pxb_launch.cuh"
@@ -206,7 +208,23 @@ unsigned flat_grid(int64_t n) {
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
+static std::atomic<int> g_iter_path{-1};
+int pxb_iter_path() {
+    int v = g_iter_path.load();
+    if (v < 0) {  // first use: PXB_TV_ITER=direct|tma overrides the automatic choice
+        const char* e = getenv("PXB_TV_ITER");
+        v = (e && !strcmp(e, "direct")) ? 1 : (e && !strcmp(e, "tma")) ? 2 : 0;
+        g_iter_path.store(v);
+    }
+    return v;
+}
+
 extern "C" {
+int pxb_set_iter_path(int path) {
+    if (path < 0 || path > 2) return fail(PXB_EINVAL, "pxb_set_iter_path: 0 (auto), 1 (direct loads) or 2 (TMA)");
+    g_iter_path.store(path);
+    return 0;
+}
 
 int pxb_abi_version(void) { return PXB_ABI_VERSION; }
 const char* pxb_last_error(void) { return g_err.c_str(); }

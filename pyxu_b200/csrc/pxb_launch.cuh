@@ -143,3 +143,6 @@ bool pxb_tv_try_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void
 // single-kernel iteration (pxb_tv_iter.cu); PXB_ENOSUP when the descriptor is outside its envelope
 int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out,
                        void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s);
+int pxb_tv_tma_try(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out, void* z_out,
+                   void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, cudaError_t* err);
+int pxb_iter_path();  // 0 auto, 1 direct-load form only, 2 TMA form only

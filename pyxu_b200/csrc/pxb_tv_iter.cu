@@ -134,6 +134,18 @@ int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p
     if (algo == PXB_PD3O && norms_x && !x_out) return pxb_fail(PXB_EINVAL, "pxb_pds_iter: RelError[x] needs x_out (it holds the previous x)");
     cudaError_t err = cudaSuccess;
     int why;
+    // 3-D volumes: TMA-staged pipeline (pxb_tv_tma.cu) unless the direct-load form is forced or the TMA form declines
+    if (K->ndir == 3 && pxb_iter_path() != 1) {
+        why = pxb_tv_tma_try(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, chunk_hint, s, &err);
+        if (why == 0) {
+            pxb_count_launch();
+            if (err != cudaSuccess) return pxb_fail(PXB_ECUDA, "pxb_pds_iter (tma): %s", cudaGetErrorString(err));
+            return 0;
+        }
+        if (pxb_iter_path() == 2) return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: TMA form not applicable (reason %d)", why);
+    } else if (pxb_iter_path() == 2) {
+        return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: TMA form is 3-D only");
+    }
     if (K->dtype == PXB_F32) {
         PxbIterPtr<float> a{(const float*)xu_in, (const float*)z_in, (float*)xu_out, (float*)z_out, (float*)x_out, norms_x, norms_z};
         why = dispatch<float>(algo, *K, *p, a, chunk_hint, s, &err);

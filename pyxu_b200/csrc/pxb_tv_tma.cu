@@ -1,0 +1,213 @@
+// pxb_tv_tma.cu -- TMA + mbarrier pipelined single-kernel iteration for 3-D volumes (design: pxb_tv_tma.cuh).
+//
+//   thread 0 of each CTA:  cp.async.bulk.tensor.5d (SASS UTMALDG) x5 per plane into a 3-stage shared-memory ring,
+//                          completion counted in bytes on one mbarrier per stage
+//   all 256 threads:       wait(stage m) -> phase A out of shared memory -> __syncthreads -> [thread 0 refills the
+//                          stage just consumed with plane m+3] -> phase C of plane m-1
+// Shared memory per CTA (fp32): 3 x 28.5 KB stages + 21.8 KB w ring = 107 KB  -> 2 CTAs per SM.
+#include <cuda.h>
+
+#include "pxb_launch.cuh"
+#include "pxb_tv_tma.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Spin on the phase parity; a bounded number of polls, then trap: a wrong transaction count must fail the launch
+// loudly instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+template <class T, int VEC, int TY, int ALGO, bool NORMS>
+__global__ void __launch_bounds__(32 * TY, 2)
+    k_tv_iter_tma(const __grid_constant__ PxbTvP<T> q, const __grid_constant__ PxbIterGeom g, const __grid_constant__ PxbTmaGeom tg,
+                  const __grid_constant__ PxbIterPtr<T> a, const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s,
+                  const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_z1) {
+    using C = PxbTmaCfg<T, VEC, TY>;
+    extern __shared__ __align__(128) unsigned char pxb_tma_smem[];
+    T* stages = reinterpret_cast<T*>(pxb_tma_smem);
+    T* ring = reinterpret_cast<T*>(pxb_tma_smem + C::SMEM_STAGES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(pxb_tma_smem + C::SMEM_STAGES + C::SMEM_RING);
+
+    const PxbIterItem it = pxb_iter_item(g, (int64_t)blockIdx.x, TY, C::T2);
+    const PxbIterRange R = pxb_iter_range<T>(q, it);
+    const int tid = threadIdx.x;
+    const bool need_next = q.cm[0] != T(0);              // phase A of plane m reads z0 of plane m+1
+    const int mload_hi = R.mhi + (need_next ? 1 : 0);    // planes [mlo, mload_hi) are staged
+    const int b = (int)it.b;
+
+    // one plane -> one stage: 4 or 5 boxes, all signalling the stage's mbarrier
+    auto issue = [&](int m) {
+        const int s = (m - R.mlo) % C::NSTAGE;
+        T* st = stages + s * C::STAGE;
+        uint64_t* bar = full + s;
+        const uint32_t bytes = C::BYTES_BOX * (3 + (tg.has_shift ? 1 : 0)) + C::BYTES_BOX1;
+        mbar_expect_tx(bar, bytes);
+        const int cc = it.c0 - VEC, cr = it.r0 - 1, cp = m + tg.gl;
+        tma_load_5d(st + C::OFF_U, &map_u, bar, cc, cr, cp, 0, b);
+        if (tg.has_shift) tma_load_5d(st + C::OFF_S, &map_s, bar, cc, cr, cp, 0, tg.sh_batched ? b : 0);
+        tma_load_5d(st + C::OFF_Z0, &map_z, bar, cc, cr, cp, 0, b);
+        tma_load_5d(st + C::OFF_Z2, &map_z, bar, cc, cr, cp, 2, b);
+        tma_load_5d(st + C::OFF_Z1, &map_z1, bar, cc, cr - 1, cp, 1, b);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < C::NSTAGE; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int m = R.mlo; m < R.mlo + C::NSTAGE && m < mload_hi; ++m) issue(m);
+
+    PxbTmaThread<T, VEC> th;
+    for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < VEC; ++j) th.zc[k][j] = th.zprev[k][j] = T(0);
+    for (int k = 0; k < 4; ++k) th.acc[k] = 0.0;
+    pxb_tma_prologue<T, VEC, TY>(q, g, it, a, tid, R.mlo, th);
+
+    for (int m = R.mlo; m < R.mhi; ++m) {
+        const int k = m - R.mlo, s = k % C::NSTAGE;
+        mbar_wait(full + s, (uint32_t)(k / C::NSTAGE) & 1u);
+        const T* st = stages + s * C::STAGE;
+        const T* st_next = st;
+        if (need_next) {
+            const int k1 = k + 1, s1 = k1 % C::NSTAGE;
+            mbar_wait(full + s1, (uint32_t)(k1 / C::NSTAGE) & 1u);
+            st_next = stages + s1 * C::STAGE;
+        }
+        pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS>(q, g, tg, it, a, tid, m, st, st_next, ring, th);
+        __syncthreads();  // w(m) complete; every thread is done with stage s
+        if (tid == 0 && m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
+        const int mm = m - R.lag;
+        if (mm >= it.m0 && mm < it.m1) {
+            T zo[3][VEC];
+            for (int kk = 0; kk < 3; ++kk)
+                for (int j = 0; j < VEC; ++j) zo[kk][j] = R.lag ? th.zprev[kk][j] : th.zc[kk][j];
+            pxb_iter_phaseC<T, VEC, C::TXL, TY, 3, NORMS>(q, g, it, a, tid, mm, ring, zo, th.acc);
+        }
+        for (int kk = 0; kk < 3; ++kk)
+            for (int j = 0; j < VEC; ++j) th.zprev[kk][j] = th.zc[kk][j];
+    }
+    // a stage filled for `need_next` beyond the last plane has been waited on above (k1), nothing is in flight here
+
+    if (NORMS) {
+        __shared__ double red[4][C::NT / 32];
+        double v[4] = {th.acc[0], th.acc[1], th.acc[2], th.acc[3]};
+        for (int o = 16; o > 0; o >>= 1)
+            for (int kk = 0; kk < 4; ++kk) v[kk] += __shfl_down_sync(0xffffffffu, v[kk], o);
+        const int w = tid >> 5, l = tid & 31;
+        if (l == 0)
+            for (int kk = 0; kk < 4; ++kk) red[kk][w] = v[kk];
+        __syncthreads();
+        if (tid == 0) {
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int i = 0; i < C::NT / 32; ++i)
+                for (int kk = 0; kk < 4; ++kk) s4[kk] += red[kk][i];
+            if (a.norms_x) { atomicAdd(a.norms_x + 2 * it.b, s4[0]); atomicAdd(a.norms_x + 2 * it.b + 1, s4[1]); }
+            if (a.norms_z) { atomicAdd(a.norms_z + 2 * it.b, s4[2]); atomicAdd(a.norms_z + 2 * it.b + 1, s4[3]); }
+        }
+    }
+}
+
+// ---- tensor maps ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+template <class T>
+bool encode(const PxbTmaBoxDesc& m, CUtensorMap* out) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < 5; ++i) { dims[i] = m.dim[i]; box[i] = m.box[i]; }
+    for (int i = 1; i < 5; ++i) strides[i - 1] = m.stride[i] * sizeof(T);
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    return fn(out, dt, 5, const_cast<void*>(m.base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <class T, int ALGO, bool NORMS>
+int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a, int chunk_hint, cudaStream_t s, cudaError_t* err) {
+    constexpr int VEC = 16 / (int)sizeof(T), TY = 8;
+    using C = PxbTmaCfg<T, VEC, TY>;
+    PxbTvCoef cf;
+    PxbIterGeom g;
+    PxbTvP<T> q;
+    if (int why = pxb_iter_setup(d, P, VEC, TY, C::T2, chunk_hint, cf, g)) return why;
+    pxb_tv_prepare<T>(d, cf, P, q);
+    PxbTmaGeom tg;
+    PxbTmaBoxDesc mu, ms, mz;
+    if (int why = pxb_tma_setup<T, VEC, TY>(d, P, cf, g, q, a.u_in, a.z_in, tg, mu, ms, mz)) return why;
+    PxbTmaBoxDesc mz1 = mz;
+    mz1.box[1] = C::BR1;
+    alignas(64) CUtensorMap tu, ts, tz, tz1;
+    if (!encode<T>(mu, &tu) || !encode<T>(ms, &ts) || !encode<T>(mz, &tz) || !encode<T>(mz1, &tz1)) return 23;
+    auto kern = k_tv_iter_tma<T, VEC, TY, ALGO, NORMS>;
+    static bool attr_set = false;  // per template instance
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) { *err = e; return 0; }
+        attr_set = true;
+    }
+    kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, tg, a, tu, ts, tz, tz1);
+    *err = cudaGetLastError();
+    return 0;
+}
+
+template <class T>
+int dispatch(int algo, const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a, int chunk_hint, cudaStream_t s, cudaError_t* err) {
+    const bool norms = a.norms_x || a.norms_z;
+    if (algo == PXB_PD3O) return norms ? run<T, PXB_PD3O, true>(d, P, a, chunk_hint, s, err) : run<T, PXB_PD3O, false>(d, P, a, chunk_hint, s, err);
+    return norms ? run<T, PXB_CV, true>(d, P, a, chunk_hint, s, err) : run<T, PXB_CV, false>(d, P, a, chunk_hint, s, err);
+}
+
+}  // namespace
+
+// > 0: not eligible (reason), 0: launched (or *err set)
+int pxb_tv_tma_try(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out, void* z_out,
+                   void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, cudaError_t* err) {
+    if (K->ndir != 3) return 20;
+    if (K->dtype == PXB_F32) {
+        PxbIterPtr<float> a{(const float*)xu_in, (const float*)z_in, (float*)xu_out, (float*)z_out, (float*)x_out, norms_x, norms_z};
+        return dispatch<float>(algo, *K, *p, a, chunk_hint, s, err);
+    }
+    PxbIterPtr<double> a{(const double*)xu_in, (const double*)z_in, (double*)xu_out, (double*)z_out, (double*)x_out, norms_x, norms_z};
+    return dispatch<double>(algo, *K, *p, a, chunk_hint, s, err);
+}

@@ -1,0 +1,253 @@
+// pxb_tv_tma.cuh -- TMA-staged form of the single-kernel PD3O / CondatVu iteration for 3-D volumes.
+//
+// Same algorithm, tiles, shared-memory w ring and phase C as pxb_tv_iter.cuh, but phase A no longer issues global
+// loads: one thread per CTA asks the Tensor Memory Accelerator for the boxes of plane m+3
+//        u, shift (or grad f), z0, z2 : rows [r0-1, r0+TY+1) x columns [c0-VEC, c0+T2+VEC)
+//        z1                           : rows [r0-2, r0+TY+2) x the same columns
+// while the CTA computes plane m out of shared memory (3-stage ring, one mbarrier per stage, completion by
+// transaction bytes).  Out-of-domain rows / columns / planes are ZERO-FILLED by the TMA unit, which is exactly the
+// reference's 'constant' boundary, so phase A carries no boundary branches for its operands; only w itself is masked
+// outside the domain.  DRAM latency is hidden by the ring instead of by occupancy (the direct-load form exposed two
+// dependent DRAM round trips per plane: 46 % of the HBM roofline).
+//
+// The arithmetic below is __host__ __device__ and is replayed on the CPU by tests/emu with the box loads emulated
+// by a plain gather with zero fill (pxb_tma_box_desc is what both the tensor-map encoder and the emulation consume).
+#pragma once
+#include "pxb_tv_iter.cuh"
+
+template <class T, int VEC, int TY>
+struct PxbTmaCfg {
+    static constexpr int TXL = 32, NT = TXL * TY, T2 = TXL * VEC;
+    static constexpr int BW = T2 + 2 * VEC;         // box width (elements): one vector of rim on each side
+    static constexpr int BR = TY + 2, BR1 = TY + 4;  // box rows: +-1 (u, shift, z0, z2), +-2 (z1)
+    static constexpr int PADE = 128 / (int)sizeof(T);
+    static constexpr int BOX = (BW * BR + PADE - 1) / PADE * PADE;    // elements, 128-byte multiples (TMA destination alignment)
+    static constexpr int BOX1 = (BW * BR1 + PADE - 1) / PADE * PADE;
+    static constexpr int OFF_U = 0, OFF_S = BOX, OFF_Z0 = 2 * BOX, OFF_Z2 = 3 * BOX, OFF_Z1 = 4 * BOX, STAGE = 4 * BOX + BOX1;
+    static constexpr int NSTAGE = 3;
+    using Ring = PxbIterCfg<T, VEC, TXL, TY, 3>;     // w ring: identical layout to the direct-load form (RS == BW)
+    static constexpr size_t SMEM_STAGES = sizeof(T) * NSTAGE * STAGE, SMEM_RING = Ring::SMEM;
+    static constexpr size_t SMEM = SMEM_STAGES + SMEM_RING + 64;      // + mbarriers
+    static constexpr uint32_t BYTES_BOX = BW * BR * sizeof(T), BYTES_BOX1 = BW * BR1 * sizeof(T);
+};
+
+// One tensor map = one 5-D view (columns, rows, planes, component, batch) of an array.
+struct PxbTmaBoxDesc {
+    const void* base;
+    uint64_t dim[5];
+    uint64_t stride[5];  // elements; stride[0] == 1
+    uint32_t box[5];
+};
+
+struct PxbTmaGeom {
+    int gl;         // ghost planes below owned plane 0 that the maps cover (plane coordinate = m + gl)
+    int has_shift;  // 1: a per-voxel array (shift of the data term, or grad f for CondatVu) is staged in OFF_S
+    int sh_batched; // 1: that array has one volume per batch item, 0: one volume broadcast over the batch
+};
+
+template <class T, int VEC, int TY>
+inline int pxb_tma_setup(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbTvCoef& cf, const PxbIterGeom& g, const PxbTvP<T>& q,
+                         const void* u_in, const void* z_in, PxbTmaGeom& tg, PxbTmaBoxDesc& mu, PxbTmaBoxDesc& ms, PxbTmaBoxDesc& mz) {
+    using C = PxbTmaCfg<T, VEC, TY>;
+    if (g.ndir != 3) return 20;
+    const bool two_sided = cf.cm[0] != 0.0 && cf.cp[0] != 0.0;
+    const int gdepth = two_sided ? 2 : 1;
+    tg.gl = g.open_lo ? gdepth : 0;
+    const int gh = g.open_hi ? gdepth : 0;
+    const uint64_t planes = (uint64_t)(g.nM + tg.gl + gh);
+    auto fill = [&](PxbTmaBoxDesc& m, const void* base, uint64_t ncomp, uint64_t comp_stride, uint64_t nbatch, uint64_t batch_stride, int rows) {
+        m.base = (const void*)((const T*)base - (int64_t)tg.gl * g.sM);
+        m.dim[0] = g.nC; m.dim[1] = g.nR; m.dim[2] = planes; m.dim[3] = ncomp; m.dim[4] = nbatch;
+        m.stride[0] = 1; m.stride[1] = g.sR; m.stride[2] = g.sM; m.stride[3] = comp_stride; m.stride[4] = batch_stride;
+        m.box[0] = C::BW; m.box[1] = rows; m.box[2] = m.box[3] = m.box[4] = 1;
+    };
+    const uint64_t batch = (uint64_t)g.nimg;
+    fill(mu, u_in, 1, g.vol, batch, g.vol, C::BR);
+    fill(mz, z_in, 3, g.vol, batch, 3 * (uint64_t)g.vol, C::BR);  // box rows: BR for z0 / z2, BR1 for z1 -> z1 has its own map copy
+    tg.has_shift = 0;
+    tg.sh_batched = 0;
+    ms = mu;
+    if (q.fkind == PXB_F_GRADARR) {
+        tg.has_shift = 1; tg.sh_batched = 1;
+        fill(ms, q.garr, 1, g.vol, batch, g.vol, C::BR);
+    } else if (q.fkind == PXB_F_SQL2) {
+        if (q.shift_mode == PXB_SHIFT_LIN) { tg.has_shift = 1; tg.sh_batched = 1; fill(ms, q.shift, 1, g.vol, batch, g.vol, C::BR); }
+        else if (q.shift_mode == PXB_SHIFT_VOL) { tg.has_shift = 1; fill(ms, q.shift, 1, g.vol, 1, g.vol, C::BR); }
+        else if (q.shift_mode == PXB_SHIFT_MOD) return 21;
+    }
+    // TMA limits: strides in bytes multiples of 16 (rows are, since nC % VEC == 0), boxes <= 256 per dimension
+    if ((g.sR * sizeof(T)) % 16 || (g.vol * sizeof(T)) % 16) return 22;
+    return 0;
+}
+
+template <class T, int VEC>
+struct PxbTmaThread {
+    T zc[3][VEC];     // z_in at this thread's own samples, plane just visited
+    T zprev[3][VEC];  // plane before (phase C with lag 1)
+    T z0p[VEC];       // z0 of the previous plane at: own samples ...
+    T z0p_rim[VEC];   //   ... the rim-row samples this thread computes (warps 0, 1)
+    T z0p_col;        //   ... the rim-column sample (last 2*TY threads)
+    double acc[4];
+};
+
+// w / new primal iterate for W samples whose box position is (row br, column bc) -- everything from shared memory.
+template <class T, int VEC, int TY, int W, int ALGO>
+PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restrict__ st, const T* __restrict__ st_next, int br, int bc,
+                      const T* z0p, T* wv, T* z0c, T* z1c, T* z2c, T* xo, T* un, T* uold) {
+    using C = PxbTmaCfg<T, VEC, TY>;
+    const int i = br * C::BW + bc, i1 = (br + 1) * C::BW + bc;
+    T kz[W], t[W];
+    {   // along M: (K^T z)[s] = cm z[s+e] + c0 z[s] + cp z[s-e]
+        const PxbVec<T, W> c = pxb_vload<T, W>(st + C::OFF_Z0 + i);
+        for (int j = 0; j < W; ++j) { z0c[j] = c.v[j]; kz[j] = q.c0[0] * c.v[j]; }
+        if (q.cp[0] != T(0)) for (int j = 0; j < W; ++j) kz[j] += q.cp[0] * z0p[j];
+        if (q.cm[0] != T(0)) {
+            const PxbVec<T, W> n = pxb_vload<T, W>(st_next + C::OFF_Z0 + i);
+            for (int j = 0; j < W; ++j) kz[j] += q.cm[0] * n.v[j];
+        }
+    }
+    {   // along the rows (z1 box starts one row earlier)
+        const T* __restrict__ z1 = st + C::OFF_Z1 + i1;
+        const PxbVec<T, W> c = pxb_vload<T, W>(z1);
+        for (int j = 0; j < W; ++j) z1c[j] = c.v[j];
+        pxb_tv_taps_col<T, W>(z1, C::BW, c, q.cm[1], q.c0[1], q.cp[1], true, true, t);
+        for (int j = 0; j < W; ++j) kz[j] += t[j];
+    }
+    {   // along the row
+        const T* __restrict__ z2 = st + C::OFF_Z2 + i;
+        const PxbVec<T, W> c = pxb_vload<T, W>(z2);
+        for (int j = 0; j < W; ++j) z2c[j] = c.v[j];
+        pxb_tv_taps_row<T, W>(z2, c, q.cm[2], q.c0[2], q.cp[2], true, true, t);
+        for (int j = 0; j < W; ++j) kz[j] += t[j];
+    }
+    const PxbVec<T, W> old = pxb_vload<T, W>(st + C::OFF_U + i);
+    PxbVec<T, W> sh;
+    for (int j = 0; j < W; ++j) sh.v[j] = T(0);
+    if (tg.has_shift) sh = pxb_vload<T, W>(st + C::OFF_S + i);
+    else if (q.fkind == PXB_F_SQL2 && q.shift_mode == PXB_SHIFT_SCALAR) { for (int j = 0; j < W; ++j) sh.v[j] = q.shift[0]; }
+    for (int j = 0; j < W; ++j) {
+        uold[j] = old.v[j];
+        if (ALGO == PXB_PD3O) {
+            const T x = pxb_prox_eval<T>(q.gkind, q.gp0, q.gp1, old.v[j] - q.tau * kz[j], q.tau);
+            const T gf = (q.fkind == PXB_F_SQL2) ? (x + sh.v[j]) * q.two_alpha : T(0);
+            const T ut = x - q.tau * gf;
+            wv[j] = x + ut - old.v[j];
+            un[j] = q.one_m_rho * old.v[j] + q.rho * ut;
+            xo[j] = x;
+        } else {
+            T gf = T(0);
+            if (q.fkind == PXB_F_SQL2) gf = (old.v[j] + sh.v[j]) * q.two_alpha;
+            else if (q.fkind == PXB_F_GRADARR) gf = sh.v[j];
+            const T vv = old.v[j] - q.tau * gf - q.tau * kz[j];
+            const T xt = pxb_prox_eval<T>(q.gkind, q.gp0, q.gp1, vv, q.tau);
+            wv[j] = T(2) * xt - old.v[j];
+            un[j] = q.rho * xt + q.one_m_rho * old.v[j];
+            xo[j] = un[j];
+        }
+    }
+}
+
+// z0 of plane mlo-1 at the samples whose previous-plane value this thread carries (start of a work item)
+template <class T, int VEC, int TY>
+PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid, int mlo,
+                             PxbTmaThread<T, VEC>& st) {
+    using C = PxbTmaCfg<T, VEC, TY>;
+    for (int j = 0; j < VEC; ++j) st.z0p[j] = st.z0p_rim[j] = T(0);
+    st.z0p_col = T(0);
+    if (q.cp[0] == T(0)) return;
+    const int mp = mlo - 1;
+    if (!((mp >= 0 || g.open_lo) && (mp < g.nM || g.open_hi))) return;
+    const T* __restrict__ z0 = a.z_in + it.z_base + (int64_t)mp * g.sM;
+    const int rl = tid / C::TXL, cl = (tid - rl * C::TXL) * VEC;
+    {
+        const int r = it.r0 + rl, c = it.c0 + cl;
+        if (r < g.nR && c < g.nC) { const PxbVec<T, VEC> v = pxb_vload<T, VEC>(z0 + (int64_t)r * g.sR + c); for (int j = 0; j < VEC; ++j) st.z0p[j] = v.v[j]; }
+    }
+    if (tid < 2 * C::TXL) {
+        const int r = tid < C::TXL ? it.r0 - 1 : it.r0 + TY, c = it.c0 + cl;
+        if (r >= 0 && r < g.nR && c < g.nC) { const PxbVec<T, VEC> v = pxb_vload<T, VEC>(z0 + (int64_t)r * g.sR + c); for (int j = 0; j < VEC; ++j) st.z0p_rim[j] = v.v[j]; }
+    }
+    if (tid >= C::NT - 2 * TY) {
+        const int h = tid - (C::NT - 2 * TY);
+        const bool left = h < TY;
+        const int r = it.r0 + (left ? h : h - TY), c = left ? it.c0 - 1 : it.c0 + C::T2;
+        if (r < g.nR && c >= 0 && c < g.nC) st.z0p_col = z0[(int64_t)r * g.sR + c];
+    }
+}
+
+// phase A of plane m out of stage `st` (plane m) and, for two-sided / backward schemes, `st_next` (plane m+1).
+template <class T, int VEC, int TY, int ALGO, bool NORMS>
+PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTmaGeom& tg, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid,
+                           int m, const T* __restrict__ st, const T* __restrict__ st_next, T* ring, PxbTmaThread<T, VEC>& th) {
+    using C = PxbTmaCfg<T, VEC, TY>;
+    using R = typename C::Ring;
+    T* __restrict__ slot = ring + (m & 3) * R::SLOT;
+    const bool plane_in = (m >= 0 || g.open_lo) && (m < g.nM || g.open_hi);
+    const bool own = m >= it.m0 && m < it.m1;
+    const int rl = tid / C::TXL, cl = (tid - rl * C::TXL) * VEC;
+    {
+        const int r = it.r0 + rl, c = it.c0 + cl;
+        const bool in = plane_in && r < g.nR && c < g.nC;
+        T wv[VEC], z0c[VEC], xo[VEC], un[VEC], uo[VEC];
+        pxb_tma_w<T, VEC, TY, VEC, ALGO>(q, tg, st, st_next, rl + 1, cl + VEC, th.z0p, wv, z0c, th.zc[1], th.zc[2], xo, un, uo);
+        for (int j = 0; j < VEC; ++j) { th.zc[0][j] = z0c[j]; th.z0p[j] = z0c[j]; }
+        PxbVec<T, VEC> o;
+        for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
+        pxb_vstore<T, VEC>(slot + (rl + 1) * R::RS + cl + VEC, o);
+        if (own && in) {
+            const int64_t lin = it.lin_base + (int64_t)m * g.sM + (int64_t)r * g.sR + c;
+            if (ALGO == PXB_PD3O) {
+                if (NORMS && a.norms_x) {
+                    const PxbVec<T, VEC> xp = pxb_vload<T, VEC>(a.x_out + lin);
+                    for (int j = 0; j < VEC; ++j) {
+                        const double dd = (double)xo[j] - (double)xp.v[j];
+                        th.acc[0] += dd * dd;
+                        th.acc[1] += (double)xp.v[j] * (double)xp.v[j];
+                    }
+                }
+                if (a.x_out) { for (int j = 0; j < VEC; ++j) o.v[j] = xo[j]; pxb_vstore<T, VEC>(a.x_out + lin, o); }
+            } else if (NORMS && a.norms_x) {
+                for (int j = 0; j < VEC; ++j) {
+                    const double dd = (double)un[j] - (double)uo[j];
+                    th.acc[0] += dd * dd;
+                    th.acc[1] += (double)uo[j] * (double)uo[j];
+                }
+            }
+            for (int j = 0; j < VEC; ++j) o.v[j] = un[j];
+            pxb_vstore<T, VEC>(a.u_out + lin, o);
+        }
+    }
+    // rims: w of the neighbouring tiles' border samples (only on planes this work item updates); the carried z0 of
+    // the previous plane is refreshed on every plane
+    if (tid < 2 * C::TXL) {
+        const bool top = tid < C::TXL;
+        const int br = top ? 0 : TY + 1;
+        const T coef = top ? q.cm[1] : q.cp[1];
+        if (own && coef != T(0)) {
+            const int r = top ? it.r0 - 1 : it.r0 + TY, c = it.c0 + cl;
+            T wv[VEC], z0c[VEC], z1c[VEC], z2c[VEC], xo[VEC], un[VEC], uo[VEC];
+            pxb_tma_w<T, VEC, TY, VEC, ALGO>(q, tg, st, st_next, br, cl + VEC, th.z0p_rim, wv, z0c, z1c, z2c, xo, un, uo);
+            const bool in = r >= 0 && r < g.nR && c < g.nC;
+            PxbVec<T, VEC> o;
+            for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
+            pxb_vstore<T, VEC>(slot + br * R::RS + cl + VEC, o);
+        }
+        const PxbVec<T, VEC> z = pxb_vload<T, VEC>(st + C::OFF_Z0 + br * C::BW + cl + VEC);
+        for (int j = 0; j < VEC; ++j) th.z0p_rim[j] = z.v[j];
+    }
+    if (tid >= C::NT - 2 * TY) {
+        const int h = tid - (C::NT - 2 * TY);
+        const bool left = h < TY;
+        const int hl = left ? h : h - TY;
+        const int bc = left ? VEC - 1 : VEC + C::T2;
+        const T coef = left ? q.cm[2] : q.cp[2];
+        if (own && coef != T(0)) {
+            const int r = it.r0 + hl, c = left ? it.c0 - 1 : it.c0 + C::T2;
+            T wv[1], z0c[1], z1c[1], z2c[1], xo[1], un[1], uo[1];
+            pxb_tma_w<T, VEC, TY, 1, ALGO>(q, tg, st, st_next, hl + 1, bc, &th.z0p_col, wv, z0c, z1c, z2c, xo, un, uo);
+            const bool in = r < g.nR && c >= 0 && c < g.nC;
+            slot[(hl + 1) * R::RS + bc] = in ? wv[0] : T(0);
+        }
+        th.z0p_col = st[C::OFF_Z0 + (hl + 1) * C::BW + bc];
+    }
+}

@@ -10,6 +10,7 @@
 #include "../../pyxu_b200/csrc/pxb_core.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_fast.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_iter.cuh"
+#include "../../pyxu_b200/csrc/pxb_tv_tma.cuh"
 #include <vector>
 
 #define FOR_VOX(batch, g)                              \
@@ -157,7 +158,98 @@ static int t_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, con
     return -102;
 }
 
+// TMA-staged form (pxb_tv_tma.cuh): the box loads the device issues as cp.async.bulk.tensor are replayed as a
+// gather with zero fill from the same PxbTmaBoxDesc the tensor-map encoder consumes; the rest is the device's
+// per-thread code.  Stage reuse follows the kernel: plane m lives in stage (m - mlo) % 3.
+template <class T>
+static void emu_tma_box(const PxbTmaBoxDesc& m, uint32_t rows, const int c[5], T* dst) {
+    const T* base = (const T*)m.base;
+    for (uint32_t i1 = 0; i1 < rows; ++i1)
+        for (uint32_t i0 = 0; i0 < m.box[0]; ++i0) {
+            const int64_t x0 = (int64_t)c[0] + i0, x1 = (int64_t)c[1] + i1;
+            bool in = x0 >= 0 && x0 < (int64_t)m.dim[0] && x1 >= 0 && x1 < (int64_t)m.dim[1];
+            for (int k = 2; k < 5; ++k) in = in && c[k] >= 0 && c[k] < (int64_t)m.dim[k];
+            T v = T(0);
+            if (in) v = base[x0 + x1 * (int64_t)m.stride[1] + c[2] * (int64_t)m.stride[2] + c[3] * (int64_t)m.stride[3] + c[4] * (int64_t)m.stride[4]];
+            dst[i1 * m.box[0] + i0] = v;
+        }
+}
+template <class T, int ALGO, bool NORMS>
+static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, int chunk) {
+    constexpr int VEC = 16 / (int)sizeof(T), TY = 8;
+    using C = PxbTmaCfg<T, VEC, TY>;
+    using R = typename C::Ring;
+    PxbTvCoef cf;
+    PxbIterGeom g;
+    if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, cf, g)) return -100 - why;
+    PxbTvP<T> q;
+    pxb_tv_prepare<T>(*K, cf, *p, q);
+    PxbTmaGeom tg;
+    PxbTmaBoxDesc mu, ms, mz;
+    if (int why = pxb_tma_setup<T, VEC, TY>(*K, *p, cf, g, q, a.u_in, a.z_in, tg, mu, ms, mz)) return -100 - why;
+    std::vector<T> stages(C::NSTAGE * C::STAGE), ring(R::NSLOT * R::SLOT);
+    std::vector<PxbTmaThread<T, VEC>> th(C::NT);
+    for (int64_t blk = 0; blk < g.nblocks; ++blk) {
+        const PxbIterItem it = pxb_iter_item(g, blk, TY, C::T2);
+        const PxbIterRange Rg = pxb_iter_range<T>(q, it);
+        const bool need_next = q.cm[0] != T(0);
+        const int mload_hi = Rg.mhi + (need_next ? 1 : 0);
+        for (auto& v : stages) v = T(777);
+        for (auto& v : ring) v = T(12345);
+        auto issue = [&](int m) {
+            T* st = stages.data() + ((m - Rg.mlo) % C::NSTAGE) * C::STAGE;
+            const int b = (int)it.b;
+            int cu[5] = {it.c0 - VEC, it.r0 - 1, m + tg.gl, 0, b};
+            emu_tma_box<T>(mu, C::BR, cu, st + C::OFF_U);
+            if (tg.has_shift) { int cs[5] = {cu[0], cu[1], cu[2], 0, tg.sh_batched ? b : 0}; emu_tma_box<T>(ms, C::BR, cs, st + C::OFF_S); }
+            emu_tma_box<T>(mz, C::BR, cu, st + C::OFF_Z0);
+            int c2[5] = {cu[0], cu[1], cu[2], 2, b};
+            emu_tma_box<T>(mz, C::BR, c2, st + C::OFF_Z2);
+            int c1[5] = {cu[0], cu[1] - 1, cu[2], 1, b};
+            emu_tma_box<T>(mz, C::BR1, c1, st + C::OFF_Z1);
+        };
+        for (int m = Rg.mlo; m < Rg.mlo + C::NSTAGE && m < mload_hi; ++m) issue(m);
+        for (int tid = 0; tid < C::NT; ++tid) {
+            std::memset(&th[tid], 0, sizeof(th[tid]));
+            pxb_tma_prologue<T, VEC, TY>(q, g, it, a, tid, Rg.mlo, th[tid]);
+        }
+        for (int m = Rg.mlo; m < Rg.mhi; ++m) {
+            const int k = m - Rg.mlo;
+            const T* st = stages.data() + (k % C::NSTAGE) * C::STAGE;
+            const T* st_next = need_next ? stages.data() + ((k + 1) % C::NSTAGE) * C::STAGE : st;
+            for (int tid = 0; tid < C::NT; ++tid) pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS>(q, g, tg, it, a, tid, m, st, st_next, ring.data(), th[tid]);
+            if (m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
+            const int mm = m - Rg.lag;
+            for (int tid = 0; tid < C::NT; ++tid) {
+                if (mm >= it.m0 && mm < it.m1)
+                    pxb_iter_phaseC<T, VEC, C::TXL, TY, 3, NORMS>(q, g, it, a, tid, mm, ring.data(), Rg.lag ? th[tid].zprev : th[tid].zc, th[tid].acc);
+                std::memcpy(th[tid].zprev, th[tid].zc, sizeof(th[tid].zc));
+            }
+        }
+        if (NORMS)
+            for (int tid = 0; tid < C::NT; ++tid) {
+                if (a.norms_x) { a.norms_x[2 * it.b] += th[tid].acc[0]; a.norms_x[2 * it.b + 1] += th[tid].acc[1]; }
+                if (a.norms_z) { a.norms_z[2 * it.b] += th[tid].acc[2]; a.norms_z[2 * it.b + 1] += th[tid].acc[3]; }
+            }
+    }
+    return 0;
+}
+template <class T>
+static int t_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
+                 void* x_out, double* nx, double* nz, int chunk) {
+    if (K->ndir != 3) return -120;
+    PxbIterPtr<T> a{(const T*)u_in, (const T*)z_in, (T*)u_out, (T*)z_out, (T*)x_out, nx, nz};
+    const bool norms = nx || nz;
+    if (algo == PXB_PD3O) return norms ? t_tma_run<T, PXB_PD3O, true>(K, p, a, chunk) : t_tma_run<T, PXB_PD3O, false>(K, p, a, chunk);
+    return norms ? t_tma_run<T, PXB_CV, true>(K, p, a, chunk) : t_tma_run<T, PXB_CV, false>(K, p, a, chunk);
+}
+
 extern "C" {
+int emu_tv_iter_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
+                    void* x_out, double* nx, double* nz, int chunk) {
+    if (K->dtype == PXB_F32) return t_tma<float>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);
+    return t_tma<double>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);
+}
 int emu_tv_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
                 void* x_out, double* nx, double* nz, int chunk) {
     if (K->dtype == PXB_F32) return t_iter<float>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);

@@ -22,6 +22,7 @@ def lib():
         h.emu_pds_dual.argtypes = [P(K.GradDesc), P(K.PdsParams), vp, vp, vp]
         h.emu_tv_fast.argtypes = [i, i, i, P(K.GradDesc), P(K.PdsParams), vp, vp, vp, vp, vp]
         h.emu_tv_iter.argtypes = [i, P(K.GradDesc), P(K.PdsParams), vp, vp, vp, vp, vp, vp, vp, i]
+        h.emu_tv_iter_tma.argtypes = h.emu_tv_iter.argtypes
         h.emu_dual_update.argtypes = [i, i, i64, i64, i64, d, d, d, vp, vp, vp]
         h.emu_prox_l21.argtypes = [i, i64, i64, i64, d, d, vp, vp]
         h.emu_prox_lincomb.argtypes = [i, P(K.ProxSpec), d, i64, vp, d, vp, d, vp, i64, d, vp, i64]

@@ -27,9 +27,10 @@ def two_pass(algo, d, P, u, z, x, nx=None, nz=None):
     E.lib().emu_pds_dual(C.byref(d), C.byref(P), E.p(w), E.p(z), E.p(nz))
 
 
-def one_pass(algo, d, P, u, z, x, nx=None, nz=None, chunk=0):
+def one_pass(algo, d, P, u, z, x, nx=None, nz=None, chunk=0, form="direct"):
     u2, z2 = np.full_like(u, np.nan), np.full_like(z, np.nan)
-    rc = E.lib().emu_tv_iter(algo, C.byref(d), C.byref(P), E.p(u), E.p(z), E.p(u2), E.p(z2), E.p(x) if algo == K.ALGO_PD3O else None,
+    fn = E.lib().emu_tv_iter if form == "direct" else E.lib().emu_tv_iter_tma
+    rc = fn(algo, C.byref(d), C.byref(P), E.p(u), E.p(z), E.p(u2), E.p(z2), E.p(x) if algo == K.ALGO_PD3O else None,
                              E.p(nx), E.p(nz), chunk)
     assert rc == 0, rc
     return u2, z2
@@ -41,7 +42,8 @@ SCHEMES = ["forward", "backward", "central"]
 @pytest.mark.parametrize("scheme", SCHEMES)
 @pytest.mark.parametrize("algo", [K.ALGO_PD3O, K.ALGO_CV])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_iter_equals_two_pass_3d(scheme, algo, dtype):
+@pytest.mark.parametrize("form", ["direct", "tma"])
+def test_iter_equals_two_pass_3d(scheme, algo, dtype, form):
     rng = np.random.default_rng(5)
     vec = 2 if dtype == np.float64 else 4
     # > 1 tile along rows (8) and columns (32*vec), ragged in both, several chunks of planes
@@ -59,7 +61,7 @@ def test_iter_equals_two_pass_3d(scheme, algo, dtype):
             nxa, nza, nxb, nzb = np.zeros(2), np.zeros(2), np.zeros(2), np.zeros(2)
             two_pass(algo, d, P, ua, za, xa, nxa, nza)
             xb = x.copy()
-            ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=chunk)
+            ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=chunk, form=form)
             tol = 1e-13 if dtype == np.float64 else 2e-6
             assert relerr(ub, ua) < tol and relerr(zb, za) < tol, (scheme, algo, chunk)
             if algo == K.ALGO_PD3O:
@@ -167,3 +169,46 @@ def test_iter_golden_f32():
     y = g["pd3o_tv2d/y"]
     x, z, *_ = _solve("pd3o_tv2d/s1", K.ALGO_PD3O, (32, 40), 60, 0.1, POS, y, y.reshape(-1), dtype=np.float32)
     assert relerr(x, g["pd3o_tv2d/s1/x"]) < 1e-4
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_tma_form_batched_shift_modes_gradarr(scheme):
+    """TMA-staged form: batch > 1 with a broadcast shift (one volume) and a per-item shift, CondatVu with grad f array."""
+    rng = np.random.default_rng(11)
+    shape, batch = (5, 11, 24), 2
+    Kop = pxo.Gradient(arg_shape=shape, scheme=scheme)
+    d = Kop._desc(batch, K.F64)
+    u, x = rng.standard_normal((batch, Kop.dim)), rng.standard_normal((batch, Kop.dim))
+    z = rng.standard_normal((batch, Kop.codim))
+    for shift in (rng.standard_normal(Kop.dim), rng.standard_normal((batch, Kop.dim)), np.r_[0.3]):
+        P = E.pds_params(0.21, 0.19, 0.9, gspec=(K.PROX_POS, 0.0, 0.0), fkind=K.F_SQL2, alpha=0.7, shift=shift, hkind=K.DUAL_L21, lam=0.3)
+        for algo in (K.ALGO_PD3O, K.ALGO_CV):
+            ua, za, xa = u.copy(), z.copy(), x.copy()
+            nxa, nza, nxb, nzb = (np.zeros(2 * batch) for _ in range(4))
+            two_pass(algo, d, P, ua, za, xa, nxa, nza)
+            xb = x.copy()
+            ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=2, form="tma")
+            assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13, (scheme, algo, shift.shape)
+            assert np.allclose(nxa, nxb, rtol=1e-10) and np.allclose(nza, nzb, rtol=1e-10)
+    garr = rng.standard_normal((batch, Kop.dim))
+    P = E.pds_params(0.3, 0.25, 0.8, gspec=(K.PROX_L1, 0.1, 0.0), fkind=K.F_GRADARR, garr=garr, hkind=K.DUAL_L1, lam=0.2)
+    ua, za = u.copy(), z.copy()
+    two_pass(K.ALGO_CV, d, P, ua, za, None)
+    ub, zb = one_pass(K.ALGO_CV, d, P, u, z, None, chunk=0, form="tma")
+    assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13
+
+
+def test_tma_form_golden_3d():
+    g = golden("solvers.npz")
+    y3 = g["pd3o_tv3d/y"]
+    tau, sigma, rho = (float(g[f"pd3o_tv3d/{k}"]) for k in ("tau", "sigma", "rho"))
+    Kop = pxo.Gradient(arg_shape=(10, 12, 14))
+    shift = np.ascontiguousarray(-y3.reshape(-1))
+    P = E.pds_params(tau, sigma, rho, gspec=POS, fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L21, lam=0.08)
+    d = Kop._desc(1, K.F64)
+    x = y3.reshape(-1).copy()
+    z = E.gradient_run(Kop, x, False)
+    u = x.copy()
+    for _ in range(50):
+        u, z = one_pass(K.ALGO_PD3O, d, P, u, z, x, form="tma")
+    assert relerr(x, g["pd3o_tv3d/x"]) < 1e-10 and relerr(z, g["pd3o_tv3d/z"]) < 1e-10

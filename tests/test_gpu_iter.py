@@ -1,0 +1,240 @@
+"""
+GPU parity of the single-kernel PD3O / CondatVu iteration (pxb_pds_iter) called through the C ABI:
+
+* against the two-sweep kernels (pxb_pds_primal + pxb_pds_dual) on random states -- every finite-difference scheme,
+  2-D / 3-D, ragged tiles, several chunks, batches, fp32 / fp64;
+* against the NumPy oracle (oracle/pyxu_oracle.py, pinned on the real reference) after N iterations through
+  Solver.fit(), including the lazily materialised x and the iteration count under the default RelError criterion;
+* at a large size through size-independent properties (two-sweep agreement on a 256^3 volume, chunk invariance).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def env():
+    import types
+
+    import pyxu_b200.operator as pxo
+    import pyxu_b200.opt.solver as pxs
+    import pyxu_b200.opt.stop as pxst
+    from pyxu_b200 import _array as A
+    from pyxu_b200 import _cabi as K
+
+    assert torch.cuda.is_available()
+    return types.SimpleNamespace(operator=pxo, solver=pxs, stop=pxst, A=A, K=K, lib=K.lib())
+
+
+@pytest.fixture
+def iter_path(env):
+    """select the implementation behind pxb_pds_iter for one test (1 direct loads, 2 TMA), restore 'auto' after"""
+    yield lambda p: env.K.check(env.lib.pxb_set_iter_path(p), "pxb_set_iter_path")
+    env.lib.pxb_set_iter_path(0)
+
+
+def rel(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b).clamp_min(1e-300))
+
+
+def params(K, tau, sigma, rho, gspec, fkind, alpha, shift, garr, hkind, lam):
+    P = K.PdsParams()
+    P.tau, P.sigma, P.rho = tau, sigma, rho
+    P.g = K.ProxSpec(gspec[0], 0, gspec[1], gspec[2])
+    f = K.FTerm()
+    f.kind, f.alpha = fkind, alpha
+    if shift is not None:
+        f.shift, f.shift_period = shift.data_ptr(), shift.numel()
+    if garr is not None:
+        f.garr = garr.data_ptr()
+    P.f = f
+    P.hkind, P.lam = hkind, lam
+    return P
+
+
+def both_forms(env, algo, Kop, batch, dtype, P, seed=0, chunk=0, norms=True):
+    """Runs one iteration in both forms from the same random state; returns ((u, z, x, nx, nz) two-sweep, same single-kernel)."""
+    K, lib, A = env.K, env.lib, env.A
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    rnd = lambda *s: torch.randn(*s, device="cuda", dtype=dtype, generator=gen)
+    d = Kop._desc(batch, K.F32 if dtype == torch.float32 else K.F64)
+    u, x, z = rnd(batch, Kop.dim), rnd(batch, Kop.dim), rnd(batch, Kop.codim)
+    st = A.stream()
+    # two sweeps (in place)
+    ua, xa, za, w = u.clone(), x.clone(), z.clone(), torch.empty_like(u)
+    na = torch.zeros((2, batch, 2), dtype=torch.float64, device="cuda")
+    pd3o = algo == K.ALGO_PD3O
+    K.check(lib.pxb_pds_primal(algo, C.byref(d), C.byref(P), ua.data_ptr(), za.data_ptr(), None, xa.data_ptr() if pd3o else None, w.data_ptr(),
+                               na[0].data_ptr() if norms else None, st), "primal")
+    K.check(lib.pxb_pds_dual(C.byref(d), C.byref(P), w.data_ptr(), za.data_ptr(), na[1].data_ptr() if norms else None, st), "dual")
+    # one sweep (out of place)
+    ub, zb, xb = torch.full_like(u, float("nan")), torch.full_like(z, float("nan")), x.clone()
+    nb = torch.zeros((2, batch, 2), dtype=torch.float64, device="cuda")
+    args = (algo, C.byref(d), C.byref(P), u.data_ptr(), z.data_ptr(), ub.data_ptr(), zb.data_ptr(), xb.data_ptr() if pd3o else None,
+            nb[0].data_ptr() if norms else None, nb[1].data_ptr() if norms else None)
+    rc = lib.pxb_pds_iter_chunked(*args, chunk, st) if chunk else lib.pxb_pds_iter(*args, st)
+    K.check(rc, "pxb_pds_iter")
+    torch.cuda.synchronize()
+    return (ua, za, xa, na), (ub, zb, xb, nb)
+
+
+def assert_same(env, algo, a, b, tol):
+    (ua, za, xa, na), (ub, zb, xb, nb) = a, b
+    assert torch.isfinite(ub).all() and torch.isfinite(zb).all()
+    assert rel(ub, ua) < tol and rel(zb, za) < tol, (rel(ub, ua), rel(zb, za))
+    if algo == env.K.ALGO_PD3O:
+        assert rel(xb, xa) < tol
+    assert torch.allclose(na, nb, rtol=1e-9 if tol < 1e-9 else 1e-5), (na, nb)
+
+
+@pytest.mark.parametrize("scheme", ["forward", "backward", "central"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("form", ["direct", "tma"])
+def test_iter_vs_two_sweeps_3d(env, scheme, dtype, form, iter_path):
+    K = env.K
+    iter_path(1 if form == "direct" else 2)
+    vec = 4 if dtype == torch.float32 else 2
+    shape = (21, 19, 32 * vec * 2 + 3 * vec)  # 3 row tiles (ragged), 3 column tiles (ragged)
+    Kop = env.operator.Gradient(arg_shape=shape, scheme=scheme, sampling=(1.0, 0.5, 2.0), dtype=np.float32 if dtype == torch.float32 else np.float64)
+    shift = torch.randn(Kop.dim, device="cuda", dtype=dtype)
+    tol = 1e-13 if dtype == torch.float64 else 2e-6
+    for algo in (K.ALGO_PD3O, K.ALGO_CV):
+        for hkind, gspec in ((K.DUAL_L21, (K.PROX_POS, 0.0, 0.0)), (K.DUAL_L1, (K.PROX_BOX, 0.2, 0.9))):
+            P = params(K, 0.21, 0.19, 0.9, gspec, K.F_SQL2, 0.7, shift, None, hkind, 0.3)
+            for chunk in (0, 5, 1):
+                a, b = both_forms(env, algo, Kop, 1, dtype, P, seed=chunk, chunk=chunk)
+                assert_same(env, algo, a, b, tol)
+
+
+@pytest.mark.parametrize("scheme", ["forward", "backward", "central"])
+@pytest.mark.parametrize("width", [40, 300, 1100])
+def test_iter_vs_two_sweeps_2d_batched(env, scheme, width):
+    K = env.K
+    Kop = env.operator.Gradient(arg_shape=(37, width), scheme=scheme, dtype=np.float32)
+    shift = torch.randn(Kop.dim, device="cuda", dtype=torch.float32)  # one image: broadcast over the batch
+    P = params(K, 0.3, 0.25, 1.0, (K.PROX_L1, 0.05, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L21, 0.2)
+    for algo in (K.ALGO_PD3O, K.ALGO_CV):
+        for chunk in (0, 4):
+            a, b = both_forms(env, algo, Kop, 5, torch.float32, P, seed=width + chunk, chunk=chunk)
+            assert_same(env, algo, a, b, 2e-6)
+
+
+def test_iter_cv_gradarr_stacked(env):
+    K = env.K
+    Kop = env.operator.Gradient(arg_shape=(3, 33, 24), directions=(1, 2))
+    garr = torch.randn(2, Kop.dim, device="cuda", dtype=torch.float64)
+    P = params(K, 0.3, 0.25, 0.8, (K.PROX_POS, 0.0, 0.0), K.F_GRADARR, 0.0, None, garr, K.DUAL_L21, 0.2)
+    a, b = both_forms(env, K.ALGO_CV, Kop, 2, torch.float64, P, chunk=7)
+    assert_same(env, K.ALGO_CV, a, b, 1e-13)
+
+
+def test_iter_envelope_errors(env):
+    K, lib = env.K, env.lib
+    Kop = env.operator.Gradient(arg_shape=(8, 16), mode="reflect")
+    d = Kop._desc(1, K.F64)
+    P = params(K, 0.3, 0.25, 1.0, (K.PROX_NONE, 0.0, 0.0), K.F_NONE, 0.0, None, None, K.DUAL_L21, 0.2)
+    u, z = torch.zeros(Kop.dim, device="cuda", dtype=torch.float64), torch.zeros(Kop.codim, device="cuda", dtype=torch.float64)
+    u2, z2 = u.clone(), z.clone()
+    n0 = lib.pxb_launch_count()
+    assert lib.pxb_pds_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), u.data_ptr(), z.data_ptr(), u2.data_ptr(), z2.data_ptr(), None, None, None, None) == -3
+    assert b"reason 4" in lib.pxb_last_error()
+    assert lib.pxb_pds_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), u.data_ptr(), z.data_ptr(), u.data_ptr(), z2.data_ptr(), None, None, None, None) == -1
+    assert lib.pxb_launch_count() == n0  # nothing was launched
+
+
+@pytest.mark.parametrize("scheme", ["forward", "central"])
+def test_tma_form_batched_shift_modes(env, scheme, iter_path):
+    """TMA form with batch > 1: shift broadcast over the batch (one volume), per-item shift, scalar shift; CV + grad f array."""
+    K = env.K
+    iter_path(2)
+    Kop = env.operator.Gradient(arg_shape=(9, 21, 136), scheme=scheme, dtype=np.float32)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for shape in ((Kop.dim,), (3, Kop.dim), (1,)):
+        shift = torch.randn(*shape, device="cuda", dtype=torch.float32, generator=gen)
+        P = params(K, 0.21, 0.19, 0.9, (K.PROX_POS, 0.0, 0.0), K.F_SQL2, 0.7, shift, None, K.DUAL_L21, 0.3)
+        for algo in (K.ALGO_PD3O, K.ALGO_CV):
+            a, b = both_forms(env, algo, Kop, 3, torch.float32, P, seed=len(shape), chunk=4)
+            assert_same(env, algo, a, b, 2e-6)
+    garr = torch.randn(3, Kop.dim, device="cuda", dtype=torch.float32, generator=gen)
+    P = params(K, 0.3, 0.25, 0.8, (K.PROX_L1, 0.1, 0.0), K.F_GRADARR, 0.0, None, garr, K.DUAL_L1, 0.2)
+    a, b = both_forms(env, K.ALGO_CV, Kop, 3, torch.float32, P)
+    assert_same(env, K.ALGO_CV, a, b, 2e-6)
+
+
+@pytest.mark.parametrize("form", ["direct", "tma"])
+def test_iter_large_volume_properties(env, form, iter_path):
+    """256^3 fp32 (every SM busy, many chunks): agreement with the two-sweep form and chunk invariance."""
+    K = env.K
+    iter_path(1 if form == "direct" else 2)
+    Kop = env.operator.Gradient(arg_shape=(256, 256, 256), dtype=np.float32)
+    shift = torch.randn(Kop.dim, device="cuda", dtype=torch.float32)
+    P = params(K, 0.28, 0.28, 1.0, (K.PROX_POS, 0.0, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L21, 0.08)
+    a, b = both_forms(env, K.ALGO_PD3O, Kop, 1, torch.float32, P, seed=1)
+    assert_same(env, K.ALGO_PD3O, a, b, 2e-6)
+    _, c = both_forms(env, K.ALGO_PD3O, Kop, 1, torch.float32, P, seed=1, chunk=37)
+    assert torch.equal(b[0], c[0]) and torch.equal(b[1], c[1]) and torch.equal(b[2], c[2])  # bitwise: same arithmetic per voxel
+
+
+# ---- through Solver.fit(): the oracle / the real reference's fixtures ------------------------------------
+def relnp(a, b):
+    a = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    return np.linalg.norm((a.astype(np.float64) - b).ravel()) / np.linalg.norm(b.ravel())
+
+
+def test_solver_uses_single_kernel_and_lazy_x(env):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv3d/y"]
+    slv = cases.build_tv_denoise(env, y, (10, 12, 14), lam=0.08, final_writeback=False)  # the final dump would materialise x
+    n0 = env.lib.pxb_launch_count()
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=env.stop.MaxIter(50))
+    assert slv._plan.kind == "fused" and slv._plan.iter_ok is True
+    assert slv._x_stale  # MaxIter never reads x: no iteration wrote it
+    launches = env.lib.pxb_launch_count() - n0
+    data, _ = slv.stats()  # materialises x from the previous iterate
+    assert not slv._x_stale
+    assert relnp(data["x"], g["pd3o_tv3d/x"]) < 1e-10 and relnp(data["z"], g["pd3o_tv3d/z"]) < 1e-10
+    assert launches <= 50 + 8, launches  # one kernel per iteration (+ set-up: K x0, clones)
+
+
+def test_solver_default_stop_fused_norms_single_kernel(env):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    slv = cases.build_tv_denoise(env, y, (32, 40), lam=0.1)
+    slv.fit(x0=y.reshape(-1).copy())
+    assert slv._plan.iter_ok is True and "_fused_norms" in slv._mstate and not slv._x_stale
+    data, hist = slv.stats()
+    assert len(hist) == int(g["pd3o_tv2d/default_stop/n_hist"])
+    assert relnp(data["x"], g["pd3o_tv2d/default_stop/x"]) < 1e-9
+    last = np.array([float(hist[-1][n]) for n in hist.dtype.names])
+    assert np.allclose(last, g["pd3o_tv2d/default_stop/hist_last"], rtol=1e-6)
+
+
+def test_solver_cv_single_kernel(env):
+    g = golden("solvers.npz")
+    y = g["pd3o_tv2d/y"]
+    slv = cases.build_tv_denoise(env, y, (32, 40), lam=0.1, solver="CondatVu")
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=env.stop.MaxIter(60))
+    assert slv._plan.iter_ok is True
+    data, _ = slv.stats()
+    assert relnp(data["x"], g["cv_tv2d/x"]) < 1e-10 and relnp(data["z"], g["cv_tv2d/z"]) < 1e-10
+
+
+def test_solver_fp32_tolerance_256cube_vs_oracle_property(env):
+    """fp32 run of a 96^3 problem against the fp64 run of the same solver (<= 1e-4, the north-star tolerance)."""
+    rng = np.random.default_rng(0)
+    y = rng.random((96, 96, 96))
+    outs = []
+    for dt in (np.float64, np.float32):
+        slv = cases.build_tv_denoise(env, y.astype(dt), (96, 96, 96), lam=0.08, dtype=dt)
+        slv.fit(x0=y.reshape(-1).astype(dt), stop_crit=env.stop.MaxIter(40))
+        assert slv._plan.iter_ok is True
+        outs.append(slv.solution())
+    assert relnp(outs[1], np.asarray(outs[0], dtype=np.float64)) < 1e-4
