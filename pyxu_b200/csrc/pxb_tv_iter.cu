@@ -88,12 +88,12 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
     PxbTvP<T> q;
     if (NDIR == 3) {
         constexpr int TXL = 32, TY = 8;
-        if (int why = pxb_iter_setup(d, P, VEC, TY, TXL * VEC, chunk_hint, cf, g)) return why;
+        if (int why = pxb_iter_setup(d, P, VEC, TY, TXL * VEC, chunk_hint, 148 * 3, cf, g)) return why;
         pxb_tv_prepare<T>(d, cf, P, q);
         *err = launch_cfg<T, VEC, TXL, TY, 3, ALGO, NORMS>(q, g, a, s);
     } else {
         const bool narrow = d.shape[2] <= 128 * VEC;
-        if (int why = pxb_iter_setup(d, P, VEC, 1, (narrow ? 128 : 256) * VEC, chunk_hint, cf, g)) return why;
+        if (int why = pxb_iter_setup(d, P, VEC, 1, (narrow ? 128 : 256) * VEC, chunk_hint, 148 * 3, cf, g)) return why;
         pxb_tv_prepare<T>(d, cf, P, q);
         *err = narrow ? launch_cfg<T, VEC, 128, 1, 2, ALGO, NORMS>(q, g, a, s) : launch_cfg<T, VEC, 256, 1, 2, ALGO, NORMS>(q, g, a, s);
     }

@@ -44,7 +44,7 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-template <class T, int VEC, int TY, int ALGO, bool NORMS>
+template <class T, int VEC, int TY, int ALGO, bool NORMS, class S>
 __global__ void __launch_bounds__(32 * TY, 2)
     k_tv_iter_tma(const __grid_constant__ PxbTvP<T> q, const __grid_constant__ PxbIterGeom g, const __grid_constant__ PxbTmaGeom tg,
                   const __grid_constant__ PxbIterPtr<T> a, const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s,
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(32 * TY, 2)
     const PxbIterItem it = pxb_iter_item(g, (int64_t)blockIdx.x, TY, C::T2);
     const PxbIterRange R = pxb_iter_range<T>(q, it);
     const int tid = threadIdx.x;
-    const bool need_next = q.cm[0] != T(0);              // phase A of plane m reads z0 of plane m+1
+    const bool need_next = pxb_has_cm<S>(q, 0);          // phase A of plane m reads z0 of plane m+1
     const int mload_hi = R.mhi + (need_next ? 1 : 0);    // planes [mlo, mload_hi) are staged
     const int b = (int)it.b;
 
@@ -67,11 +67,12 @@ __global__ void __launch_bounds__(32 * TY, 2)
         const int s = (m - R.mlo) % C::NSTAGE;
         T* st = stages + s * C::STAGE;
         uint64_t* bar = full + s;
-        const uint32_t bytes = C::BYTES_BOX * (3 + (tg.has_shift ? 1 : 0)) + C::BYTES_BOX1;
+        const bool staged_shift = S::FK == 1 || tg.has_shift;
+        const uint32_t bytes = C::BYTES_BOX * (3 + (staged_shift ? 1 : 0)) + C::BYTES_BOX1;
         mbar_expect_tx(bar, bytes);
         const int cc = it.c0 - VEC, cr = it.r0 - 1, cp = m + tg.gl;
         tma_load_5d(st + C::OFF_U, &map_u, bar, cc, cr, cp, 0, b);
-        if (tg.has_shift) tma_load_5d(st + C::OFF_S, &map_s, bar, cc, cr, cp, 0, tg.sh_batched ? b : 0);
+        if (staged_shift) tma_load_5d(st + C::OFF_S, &map_s, bar, cc, cr, cp, 0, tg.sh_batched ? b : 0);
         tma_load_5d(st + C::OFF_Z0, &map_z, bar, cc, cr, cp, 0, b);
         tma_load_5d(st + C::OFF_Z2, &map_z, bar, cc, cr, cp, 2, b);
         tma_load_5d(st + C::OFF_Z1, &map_z1, bar, cc, cr - 1, cp, 1, b);
@@ -92,28 +93,32 @@ __global__ void __launch_bounds__(32 * TY, 2)
     for (int k = 0; k < 4; ++k) th.acc[k] = 0.0;
     pxb_tma_prologue<T, VEC, TY>(q, g, it, a, tid, R.mlo, th);
 
+    const int lag = S::SCHEME == PXB_SCHEME_FWD ? 1 : R.lag;
+    int s = 0;            // stage of plane m, and the parity of its mbarrier phase
+    uint32_t par = 0;
     for (int m = R.mlo; m < R.mhi; ++m) {
-        const int k = m - R.mlo, s = k % C::NSTAGE;
-        mbar_wait(full + s, (uint32_t)(k / C::NSTAGE) & 1u);
+        mbar_wait(full + s, par);
         const T* st = stages + s * C::STAGE;
         const T* st_next = st;
+        const int s1 = s + 1 == C::NSTAGE ? 0 : s + 1;
         if (need_next) {
-            const int k1 = k + 1, s1 = k1 % C::NSTAGE;
-            mbar_wait(full + s1, (uint32_t)(k1 / C::NSTAGE) & 1u);
+            mbar_wait(full + s1, s1 == 0 ? par ^ 1u : par);
             st_next = stages + s1 * C::STAGE;
         }
-        pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS>(q, g, tg, it, a, tid, m, st, st_next, ring, th);
+        pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S>(q, g, tg, it, a, tid, m, st, st_next, ring, th);
         __syncthreads();  // w(m) complete; every thread is done with stage s
         if (tid == 0 && m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
-        const int mm = m - R.lag;
+        const int mm = m - lag;
         if (mm >= it.m0 && mm < it.m1) {
             T zo[3][VEC];
             for (int kk = 0; kk < 3; ++kk)
-                for (int j = 0; j < VEC; ++j) zo[kk][j] = R.lag ? th.zprev[kk][j] : th.zc[kk][j];
-            pxb_iter_phaseC<T, VEC, C::TXL, TY, 3, NORMS>(q, g, it, a, tid, mm, ring, zo, th.acc);
+                for (int j = 0; j < VEC; ++j) zo[kk][j] = lag ? th.zprev[kk][j] : th.zc[kk][j];
+            pxb_iter_phaseC<T, VEC, C::TXL, TY, 3, NORMS, S>(q, g, it, a, tid, mm, ring, zo, th.acc);
         }
         for (int kk = 0; kk < 3; ++kk)
             for (int j = 0; j < VEC; ++j) th.zprev[kk][j] = th.zc[kk][j];
+        s = s1;
+        if (s == 0) par ^= 1u;
     }
     // a stage filled for `need_next` beyond the last plane has been waited on above (k1), nothing is in flight here
 
@@ -170,7 +175,7 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
     PxbTvCoef cf;
     PxbIterGeom g;
     PxbTvP<T> q;
-    if (int why = pxb_iter_setup(d, P, VEC, TY, C::T2, chunk_hint, cf, g)) return why;
+    if (int why = pxb_iter_setup(d, P, VEC, TY, C::T2, chunk_hint, 148 * 2, cf, g)) return why;
     pxb_tv_prepare<T>(d, cf, P, q);
     PxbTmaGeom tg;
     PxbTmaBoxDesc mu, ms, mz;
@@ -179,15 +184,19 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
     mz1.box[1] = C::BR1;
     alignas(64) CUtensorMap tu, ts, tz, tz1;
     if (!encode<T>(mu, &tu) || !encode<T>(ms, &ts) || !encode<T>(mz, &tz) || !encode<T>(mz1, &tz1)) return 23;
-    auto kern = k_tv_iter_tma<T, VEC, TY, ALGO, NORMS>;
-    static bool attr_set = false;  // per template instance
-    if (!attr_set) {
+    // specialised instances: forward differences + L21 + shifted squared-l2 data term staged per voxel + g in
+    // {positivity, none}; everything else runs the generic instance
+    const int spec = pxb_tma_pick_spec<T>(cf, q, tg);
+    auto go = [&](auto kern) {
+        // (the attribute is per function: set it on every launch path once; cheap enough to repeat)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) { *err = e; return 0; }
-        attr_set = true;
-    }
-    kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, tg, a, tu, ts, tz, tz1);
-    *err = cudaGetLastError();
+        if (e != cudaSuccess) { *err = e; return; }
+        kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, tg, a, tu, ts, tz, tz1);
+        *err = cudaGetLastError();
+    };
+    if (spec == 1) go(k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecFwdPos>);
+    else if (spec == 2) go(k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecFwdNone>);
+    else go(k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecAny>);
     return 0;
 }
 

@@ -80,6 +80,18 @@ inline int pxb_tma_setup(const pxb_grad_desc& d, const pxb_pds_params& P, const 
     return 0;
 }
 
+// which compiled instance serves a problem: 1 / 2 = forward differences + L21 + per-voxel shifted squared-l2 data
+// term with g = positivity / none; 0 = the generic instance
+using PxbSpecFwdPos = PxbSpec<PXB_SCHEME_FWD, PXB_PROX_POS, PXB_DUAL_L21, 1>;
+using PxbSpecFwdNone = PxbSpec<PXB_SCHEME_FWD, PXB_PROX_NONE, PXB_DUAL_L21, 1>;
+template <class T>
+inline int pxb_tma_pick_spec(const PxbTvCoef& cf, const PxbTvP<T>& q, const PxbTmaGeom& tg) {
+    bool fwd = true;
+    for (int k = 0; k < 3; ++k) fwd = fwd && cf.cm[k] == 0.0 && cf.cp[k] != 0.0;
+    if (!(fwd && q.hkind == PXB_DUAL_L21 && q.fkind == PXB_F_SQL2 && tg.has_shift)) return 0;
+    return q.gkind == PXB_PROX_POS ? 1 : (q.gkind == PXB_PROX_NONE ? 2 : 0);
+}
+
 template <class T, int VEC>
 struct PxbTmaThread {
     T zc[3][VEC];     // z_in at this thread's own samples, plane just visited
@@ -91,55 +103,68 @@ struct PxbTmaThread {
 };
 
 // w / new primal iterate for W samples whose box position is (row br, column bc) -- everything from shared memory.
-template <class T, int VEC, int TY, int W, int ALGO>
+template <class T, int VEC, int TY, int W, int ALGO, class S>
 PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restrict__ st, const T* __restrict__ st_next, int br, int bc,
                       const T* z0p, T* wv, T* z0c, T* z1c, T* z2c, T* xo, T* un, T* uold) {
     using C = PxbTmaCfg<T, VEC, TY>;
     const int i = br * C::BW + bc, i1 = (br + 1) * C::BW + bc;
-    T kz[W], t[W];
+    T kz[W];
     {   // along M: (K^T z)[s] = cm z[s+e] + c0 z[s] + cp z[s-e]
         const PxbVec<T, W> c = pxb_vload<T, W>(st + C::OFF_Z0 + i);
         for (int j = 0; j < W; ++j) { z0c[j] = c.v[j]; kz[j] = q.c0[0] * c.v[j]; }
-        if (q.cp[0] != T(0)) for (int j = 0; j < W; ++j) kz[j] += q.cp[0] * z0p[j];
-        if (q.cm[0] != T(0)) {
+        if (pxb_has_cp<S>(q, 0)) for (int j = 0; j < W; ++j) kz[j] += q.cp[0] * z0p[j];
+        if (pxb_has_cm<S>(q, 0)) {
             const PxbVec<T, W> n = pxb_vload<T, W>(st_next + C::OFF_Z0 + i);
             for (int j = 0; j < W; ++j) kz[j] += q.cm[0] * n.v[j];
         }
     }
-    {   // along the rows (z1 box starts one row earlier)
+    {   // along the rows (the z1 box starts one row earlier); zero fill stands in for every boundary test
         const T* __restrict__ z1 = st + C::OFF_Z1 + i1;
         const PxbVec<T, W> c = pxb_vload<T, W>(z1);
-        for (int j = 0; j < W; ++j) z1c[j] = c.v[j];
-        pxb_tv_taps_col<T, W>(z1, C::BW, c, q.cm[1], q.c0[1], q.cp[1], true, true, t);
-        for (int j = 0; j < W; ++j) kz[j] += t[j];
+        for (int j = 0; j < W; ++j) { z1c[j] = c.v[j]; kz[j] += q.c0[1] * c.v[j]; }
+        if (pxb_has_cm<S>(q, 1)) {
+            const PxbVec<T, W> n = pxb_vload<T, W>(z1 + C::BW);
+            for (int j = 0; j < W; ++j) kz[j] += q.cm[1] * n.v[j];
+        }
+        if (pxb_has_cp<S>(q, 1)) {
+            const PxbVec<T, W> n = pxb_vload<T, W>(z1 - C::BW);
+            for (int j = 0; j < W; ++j) kz[j] += q.cp[1] * n.v[j];
+        }
     }
     {   // along the row
         const T* __restrict__ z2 = st + C::OFF_Z2 + i;
         const PxbVec<T, W> c = pxb_vload<T, W>(z2);
-        for (int j = 0; j < W; ++j) z2c[j] = c.v[j];
-        pxb_tv_taps_row<T, W>(z2, c, q.cm[2], q.c0[2], q.cp[2], true, true, t);
-        for (int j = 0; j < W; ++j) kz[j] += t[j];
+        T lo = T(0), hi = T(0);
+        if (pxb_has_cp<S>(q, 2)) lo = z2[-1];
+        if (pxb_has_cm<S>(q, 2)) hi = z2[W];
+        for (int j = 0; j < W; ++j) {
+            z2c[j] = c.v[j];
+            kz[j] += q.c0[2] * c.v[j];
+            if (pxb_has_cm<S>(q, 2)) kz[j] += q.cm[2] * (j + 1 < W ? c.v[j + 1 < W ? j + 1 : 0] : hi);
+            if (pxb_has_cp<S>(q, 2)) kz[j] += q.cp[2] * (j > 0 ? c.v[j > 0 ? j - 1 : 0] : lo);
+        }
     }
     const PxbVec<T, W> old = pxb_vload<T, W>(st + C::OFF_U + i);
     PxbVec<T, W> sh;
     for (int j = 0; j < W; ++j) sh.v[j] = T(0);
-    if (tg.has_shift) sh = pxb_vload<T, W>(st + C::OFF_S + i);
+    if (S::FK == 1 || tg.has_shift) sh = pxb_vload<T, W>(st + C::OFF_S + i);
     else if (q.fkind == PXB_F_SQL2 && q.shift_mode == PXB_SHIFT_SCALAR) { for (int j = 0; j < W; ++j) sh.v[j] = q.shift[0]; }
+    const int gk = pxb_gkind<S>(q);
     for (int j = 0; j < W; ++j) {
         uold[j] = old.v[j];
         if (ALGO == PXB_PD3O) {
-            const T x = pxb_prox_eval<T>(q.gkind, q.gp0, q.gp1, old.v[j] - q.tau * kz[j], q.tau);
-            const T gf = (q.fkind == PXB_F_SQL2) ? (x + sh.v[j]) * q.two_alpha : T(0);
+            const T x = pxb_prox_eval<T>(gk, q.gp0, q.gp1, old.v[j] - q.tau * kz[j], q.tau);
+            const T gf = (S::FK == 1 || q.fkind == PXB_F_SQL2) ? (x + sh.v[j]) * q.two_alpha : T(0);
             const T ut = x - q.tau * gf;
             wv[j] = x + ut - old.v[j];
             un[j] = q.one_m_rho * old.v[j] + q.rho * ut;
             xo[j] = x;
         } else {
             T gf = T(0);
-            if (q.fkind == PXB_F_SQL2) gf = (old.v[j] + sh.v[j]) * q.two_alpha;
+            if (S::FK == 1 || q.fkind == PXB_F_SQL2) gf = (old.v[j] + sh.v[j]) * q.two_alpha;
             else if (q.fkind == PXB_F_GRADARR) gf = sh.v[j];
             const T vv = old.v[j] - q.tau * gf - q.tau * kz[j];
-            const T xt = pxb_prox_eval<T>(q.gkind, q.gp0, q.gp1, vv, q.tau);
+            const T xt = pxb_prox_eval<T>(gk, q.gp0, q.gp1, vv, q.tau);
             wv[j] = T(2) * xt - old.v[j];
             un[j] = q.rho * xt + q.one_m_rho * old.v[j];
             xo[j] = un[j];
@@ -154,7 +179,7 @@ PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const Pxb
     using C = PxbTmaCfg<T, VEC, TY>;
     for (int j = 0; j < VEC; ++j) st.z0p[j] = st.z0p_rim[j] = T(0);
     st.z0p_col = T(0);
-    if (q.cp[0] == T(0)) return;
+    if (q.cp[0] == T(0)) return;  // (run-time test: executed once per work item)
     const int mp = mlo - 1;
     if (!((mp >= 0 || g.open_lo) && (mp < g.nM || g.open_hi))) return;
     const T* __restrict__ z0 = a.z_in + it.z_base + (int64_t)mp * g.sM;
@@ -176,7 +201,7 @@ PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const Pxb
 }
 
 // phase A of plane m out of stage `st` (plane m) and, for two-sided / backward schemes, `st_next` (plane m+1).
-template <class T, int VEC, int TY, int ALGO, bool NORMS>
+template <class T, int VEC, int TY, int ALGO, bool NORMS, class S = PxbSpecAny>
 PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTmaGeom& tg, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid,
                            int m, const T* __restrict__ st, const T* __restrict__ st_next, T* ring, PxbTmaThread<T, VEC>& th) {
     using C = PxbTmaCfg<T, VEC, TY>;
@@ -189,7 +214,7 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         const int r = it.r0 + rl, c = it.c0 + cl;
         const bool in = plane_in && r < g.nR && c < g.nC;
         T wv[VEC], z0c[VEC], xo[VEC], un[VEC], uo[VEC];
-        pxb_tma_w<T, VEC, TY, VEC, ALGO>(q, tg, st, st_next, rl + 1, cl + VEC, th.z0p, wv, z0c, th.zc[1], th.zc[2], xo, un, uo);
+        pxb_tma_w<T, VEC, TY, VEC, ALGO, S>(q, tg, st, st_next, rl + 1, cl + VEC, th.z0p, wv, z0c, th.zc[1], th.zc[2], xo, un, uo);
         for (int j = 0; j < VEC; ++j) { th.zc[0][j] = z0c[j]; th.z0p[j] = z0c[j]; }
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
@@ -222,11 +247,11 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
     if (tid < 2 * C::TXL) {
         const bool top = tid < C::TXL;
         const int br = top ? 0 : TY + 1;
-        const T coef = top ? q.cm[1] : q.cp[1];
-        if (own && coef != T(0)) {
+        const bool need = top ? pxb_has_cm<S>(q, 1) : pxb_has_cp<S>(q, 1);
+        if (own && need) {
             const int r = top ? it.r0 - 1 : it.r0 + TY, c = it.c0 + cl;
             T wv[VEC], z0c[VEC], z1c[VEC], z2c[VEC], xo[VEC], un[VEC], uo[VEC];
-            pxb_tma_w<T, VEC, TY, VEC, ALGO>(q, tg, st, st_next, br, cl + VEC, th.z0p_rim, wv, z0c, z1c, z2c, xo, un, uo);
+            pxb_tma_w<T, VEC, TY, VEC, ALGO, S>(q, tg, st, st_next, br, cl + VEC, th.z0p_rim, wv, z0c, z1c, z2c, xo, un, uo);
             const bool in = r >= 0 && r < g.nR && c < g.nC;
             PxbVec<T, VEC> o;
             for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
@@ -240,11 +265,11 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         const bool left = h < TY;
         const int hl = left ? h : h - TY;
         const int bc = left ? VEC - 1 : VEC + C::T2;
-        const T coef = left ? q.cm[2] : q.cp[2];
-        if (own && coef != T(0)) {
+        const bool need = left ? pxb_has_cm<S>(q, 2) : pxb_has_cp<S>(q, 2);
+        if (own && need) {
             const int r = it.r0 + hl, c = left ? it.c0 - 1 : it.c0 + C::T2;
             T wv[1], z0c[1], z1c[1], z2c[1], xo[1], un[1], uo[1];
-            pxb_tma_w<T, VEC, TY, 1, ALGO>(q, tg, st, st_next, hl + 1, bc, &th.z0p_col, wv, z0c, z1c, z2c, xo, un, uo);
+            pxb_tma_w<T, VEC, TY, 1, ALGO, S>(q, tg, st, st_next, hl + 1, bc, &th.z0p_col, wv, z0c, z1c, z2c, xo, un, uo);
             const bool in = r < g.nR && c >= 0 && c < g.nC;
             slot[(hl + 1) * R::RS + bc] = in ? wv[0] : T(0);
         }

@@ -109,7 +109,7 @@ static int t_iter_cfg(const pxb_grad_desc* K, const pxb_pds_params* p, const Pxb
     using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
     PxbTvCoef cf;
     PxbIterGeom g;
-    if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, cf, g)) return -100 - why;
+    if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, 5, cf, g)) return -100 - why;
     PxbTvP<T> q;
     pxb_tv_prepare<T>(*K, cf, *p, q);
     std::vector<T> smem(C::NSLOT * C::SLOT);
@@ -174,25 +174,27 @@ static void emu_tma_box(const PxbTmaBoxDesc& m, uint32_t rows, const int c[5], T
             dst[i1 * m.box[0] + i0] = v;
         }
 }
-template <class T, int ALGO, bool NORMS>
-static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, int chunk) {
+template <class T, int ALGO, bool NORMS, class S>
+static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, int chunk, int want_spec) {
     constexpr int VEC = 16 / (int)sizeof(T), TY = 8;
     using C = PxbTmaCfg<T, VEC, TY>;
     using R = typename C::Ring;
     PxbTvCoef cf;
     PxbIterGeom g;
-    if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, cf, g)) return -100 - why;
+    if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, 5, cf, g)) return -100 - why;
     PxbTvP<T> q;
     pxb_tv_prepare<T>(*K, cf, *p, q);
     PxbTmaGeom tg;
     PxbTmaBoxDesc mu, ms, mz;
     if (int why = pxb_tma_setup<T, VEC, TY>(*K, *p, cf, g, q, a.u_in, a.z_in, tg, mu, ms, mz)) return -100 - why;
+    if (pxb_tma_pick_spec<T>(cf, q, tg) != want_spec) return -130;  // the caller dispatches on the same rule as the launcher
     std::vector<T> stages(C::NSTAGE * C::STAGE), ring(R::NSLOT * R::SLOT);
     std::vector<PxbTmaThread<T, VEC>> th(C::NT);
     for (int64_t blk = 0; blk < g.nblocks; ++blk) {
         const PxbIterItem it = pxb_iter_item(g, blk, TY, C::T2);
         const PxbIterRange Rg = pxb_iter_range<T>(q, it);
-        const bool need_next = q.cm[0] != T(0);
+        const bool need_next = pxb_has_cm<S>(q, 0);
+        const int lag = S::SCHEME == PXB_SCHEME_FWD ? 1 : Rg.lag;
         const int mload_hi = Rg.mhi + (need_next ? 1 : 0);
         for (auto& v : stages) v = T(777);
         for (auto& v : ring) v = T(12345);
@@ -201,7 +203,7 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
             const int b = (int)it.b;
             int cu[5] = {it.c0 - VEC, it.r0 - 1, m + tg.gl, 0, b};
             emu_tma_box<T>(mu, C::BR, cu, st + C::OFF_U);
-            if (tg.has_shift) { int cs[5] = {cu[0], cu[1], cu[2], 0, tg.sh_batched ? b : 0}; emu_tma_box<T>(ms, C::BR, cs, st + C::OFF_S); }
+            if (S::FK == 1 || tg.has_shift) { int cs[5] = {cu[0], cu[1], cu[2], 0, tg.sh_batched ? b : 0}; emu_tma_box<T>(ms, C::BR, cs, st + C::OFF_S); }
             emu_tma_box<T>(mz, C::BR, cu, st + C::OFF_Z0);
             int c2[5] = {cu[0], cu[1], cu[2], 2, b};
             emu_tma_box<T>(mz, C::BR, c2, st + C::OFF_Z2);
@@ -217,12 +219,12 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
             const int k = m - Rg.mlo;
             const T* st = stages.data() + (k % C::NSTAGE) * C::STAGE;
             const T* st_next = need_next ? stages.data() + ((k + 1) % C::NSTAGE) * C::STAGE : st;
-            for (int tid = 0; tid < C::NT; ++tid) pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS>(q, g, tg, it, a, tid, m, st, st_next, ring.data(), th[tid]);
+            for (int tid = 0; tid < C::NT; ++tid) pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S>(q, g, tg, it, a, tid, m, st, st_next, ring.data(), th[tid]);
             if (m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
-            const int mm = m - Rg.lag;
+            const int mm = m - lag;
             for (int tid = 0; tid < C::NT; ++tid) {
                 if (mm >= it.m0 && mm < it.m1)
-                    pxb_iter_phaseC<T, VEC, C::TXL, TY, 3, NORMS>(q, g, it, a, tid, mm, ring.data(), Rg.lag ? th[tid].zprev : th[tid].zc, th[tid].acc);
+                    pxb_iter_phaseC<T, VEC, C::TXL, TY, 3, NORMS, S>(q, g, it, a, tid, mm, ring.data(), lag ? th[tid].zprev : th[tid].zc, th[tid].acc);
                 std::memcpy(th[tid].zprev, th[tid].zc, sizeof(th[tid].zc));
             }
         }
@@ -240,8 +242,18 @@ static int t_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
     if (K->ndir != 3) return -120;
     PxbIterPtr<T> a{(const T*)u_in, (const T*)z_in, (T*)u_out, (T*)z_out, (T*)x_out, nx, nz};
     const bool norms = nx || nz;
-    if (algo == PXB_PD3O) return norms ? t_tma_run<T, PXB_PD3O, true>(K, p, a, chunk) : t_tma_run<T, PXB_PD3O, false>(K, p, a, chunk);
-    return norms ? t_tma_run<T, PXB_CV, true>(K, p, a, chunk) : t_tma_run<T, PXB_CV, false>(K, p, a, chunk);
+    // try the instances in the launcher's order; exactly one accepts (-130 = "not my problem")
+#define EMU_TMA_TRY(S, id)                                                                                              \
+    {                                                                                                                   \
+        int rc = algo == PXB_PD3O ? (norms ? t_tma_run<T, PXB_PD3O, true, S>(K, p, a, chunk, id) : t_tma_run<T, PXB_PD3O, false, S>(K, p, a, chunk, id)) \
+                                  : (norms ? t_tma_run<T, PXB_CV, true, S>(K, p, a, chunk, id) : t_tma_run<T, PXB_CV, false, S>(K, p, a, chunk, id));       \
+        if (rc != -130) return rc;                                                                                      \
+    }
+    EMU_TMA_TRY(PxbSpecFwdPos, 1)
+    EMU_TMA_TRY(PxbSpecFwdNone, 2)
+    EMU_TMA_TRY(PxbSpecAny, 0)
+#undef EMU_TMA_TRY
+    return -131;
 }
 
 extern "C" {
