@@ -337,6 +337,7 @@ inline int pxb_iter_setup(const pxb_grad_desc& d, const pxb_pds_params& P, int v
     for (int k = 0; k < d.ndir; ++k)
         if (d.mode[3 - d.ndir + k] != PXB_CONSTANT) return 4;
     if (d.shape[2] % vec) return 5;
+    if (d.shape[0] < 1 || d.shape[1] < 1 || d.shape[2] < 1 || d.batch < 1) return 9;
     const PxbGeom gg = pxb_geom(d.shape);
     g.ndir = d.ndir;
     g.vol = pxb_vol(gg, d.slab);

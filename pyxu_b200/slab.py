@@ -6,7 +6,13 @@ into `world` contiguous slabs; every rank stores its slab with `halo` ghost plan
 
     component layout  (halo + n0_local + halo, n1, n2)      <- pointers handed to kernels address owned plane 0
 
-Per PD3O-TV iteration two planes cross each slab interface:
+Single-kernel form (default; 'constant' boundaries): one pxb_pds_iter launch per iteration and slab, ping-pong
+buffers.  The kernel recomputes w on the ghost plane above the slab, so what crosses each interface per iteration is
+the NEW iterate's boundary planes: u, z_0, z_1, z_2 of the first owned plane go down, z_0 of the last owned plane
+goes up (5 planes, 20 MiB at 1024^2 fp32).  The two boundary chunks of a slab are launched first; their planes travel
+on a side stream (NCCL send/recv) while the interior chunks are computed.
+
+Two-sweep form (other boundary modes): per PD3O-TV iteration two planes cross each slab interface:
     * before the primal half-step: the dual component along z, z_0, last owned plane  -> upper neighbour
       (K^T z at a slab's first plane needs z_0 of the plane below),
     * before the dual half-step:   w, first owned plane                              -> lower neighbour
@@ -75,6 +81,23 @@ class HaloExchanger:
                 ops.append(dist.P2POp(dist.irecv, buf[h + n_owned : 2 * h + n_owned], self.hi, self.group))
         return dist.batch_isend_irecv(ops) if ops else []
 
+    def exchange_many(self, items, halo, n_owned):
+        """One batched exchange of several buffers: items = [(buf, up, down), ...] (same order on every rank)."""
+        ops = []
+        h = halo
+        for buf, up, down in items:
+            if up:
+                if self.hi is not None:
+                    ops.append(dist.P2POp(dist.isend, buf[n_owned : n_owned + h], self.hi, self.group))
+                if self.lo is not None:
+                    ops.append(dist.P2POp(dist.irecv, buf[0:h], self.lo, self.group))
+            if down:
+                if self.lo is not None:
+                    ops.append(dist.P2POp(dist.isend, buf[h : 2 * h], self.lo, self.group))
+                if self.hi is not None:
+                    ops.append(dist.P2POp(dist.irecv, buf[h + n_owned : 2 * h + n_owned], self.hi, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
 
 class SlabPD3OTV:
     """PD3O on  min 1/2||x - y||^2 + i_+(x) + lam*||grad x||_{2,1}  for a volume decomposed in z-slabs.
@@ -87,7 +110,7 @@ class SlabPD3OTV:
     HALO = 1
 
     def __init__(self, shape, y_full=None, y_local=None, lam=0.08, positivity=True, dtype=torch.float32, mode="constant",
-                 rho=1.0, tau=None, sigma=None, group=None, overlap=True):
+                 rho=1.0, tau=None, sigma=None, group=None, overlap=True, fused=True, edge=8):
         from .operator.linop.diff import Gradient
 
         A.require_cuda()
@@ -112,11 +135,25 @@ class SlabPD3OTV:
         def field(ncomp=1):
             return torch.zeros((ncomp, alloc, n1, n2), dtype=dtype, device=self.dev)
 
-        self.u, self.x, self.w, self.z = field(), field(), field(), field(3)
+        # single-kernel iteration: 'constant' boundaries (the kernel's envelope); ping-pong (u, z) pairs, no w array
+        self.fused = bool(fused) and all(m == "constant" for m in modes)
+        self.edge = max(1, min(int(edge), self.n0 // 2))  # planes of the boundary launches that precede the exchange
         if y_local is None:
             y_local = y_full.reshape(self.shape)[self.start : self.stop]
-        self.shift = (-y_local).to(dtype).contiguous()  # f = 1/2 ||x + shift||^2
         own = slice(h, h + self.n0)
+        self.x = field()
+        self._x_stale = False
+        if self.fused:
+            self._ub, self._zb, self.cur = [field(), field()], [field(3), field(3)], 0
+            self.w = None
+            self.shift_h = field()  # shift (= -y) WITH ghost planes: the kernel evaluates grad f on the ghost plane too
+            self.shift_h[0, own].copy_(y_local)
+            self.shift_h.neg_()
+            self.shift = self.shift_h[0, own]
+        else:
+            self._ub, self._zb, self.cur = [field()], [field(3)], 0
+            self.w = field()
+            self.shift = (-y_local).to(dtype).contiguous()  # f = 1/2 ||x + shift||^2
         self.u[0, own].copy_(y_local)
         self.x[0, own].copy_(y_local)
         # step sizes: PD3O defaults (reference: pds.py:807-829, 849-864) for beta = 1
@@ -130,14 +167,26 @@ class SlabPD3OTV:
         # it: 'constant' (nothing folds) or 'wrap' (ring exchange: every side is open).  Other modes along z run
         # whole-slab launches after the exchange.
         self.overlap = bool(overlap) and self.world > 1 and modes[0] in ("constant", "wrap")
-        self.comm = torch.cuda.Stream(device=self.dev) if self.overlap else None
+        self.comm = torch.cuda.Stream(device=self.dev) if (self.overlap or self.fused) else None
         self.event_log = []   # (tag, cuda event) pairs, filled when `record_events`
         self.record_events = True
         # z0 = K x0 needs x0's upper ghost plane
         self._wait(self.hx.exchange(self.x[0], h, self.n0, up=False, down=True))
         d = self._desc(0, self.n0)
         K.check(K.lib().pxb_gradient_apply(C.byref(d), self._p(self.x, 0, 0), self._p(self.z, 0, 0), A.stream()), "gradient_apply")
+        if self.fused and self.world > 1:  # ghost planes of the data term (once) and of the initial iterate
+            self._wait(self.hx.exchange(self.shift_h[0], h, self.n0, up=True, down=True))
+            self._wait(self._exchange_state(self.cur))
         torch.cuda.synchronize()
+
+    # current iterate (the ping-pong index flips every fused iteration)
+    @property
+    def u(self):
+        return self._ub[self.cur]
+
+    @property
+    def z(self):
+        return self._zb[self.cur]
 
     # -- helpers ----------------------------------------------------------------------------------
     @staticmethod
@@ -188,8 +237,81 @@ class SlabPD3OTV:
             ev.record()
             self.event_log.append((tag, ev))
 
+    # -- single-kernel form ----------------------------------------------------------------------------
+    def _exchange_state(self, idx):
+        """Boundary planes of iterate `idx` -> the neighbours' ghost planes: u, z_0..2 first plane down, z_0 last plane up."""
+        u, z = self._ub[idx], self._zb[idx]
+        items = [(u[0], False, True), (z[0], True, True), (z[1], False, True), (z[2], False, True)]
+        return self.hx.exchange_many(items, self.HALO, self.n0)
+
+    def _iter(self, p0, p1, src, dst, x_out, nx, nz):
+        """pxb_pds_iter on owned planes [p0, p1): reads iterate `src` (ghost planes valid), writes iterate `dst`."""
+        d, p = self._desc(p0, p1), self._params()
+        sh = self.shift_h
+        p.f.shift = sh.data_ptr() + sh.element_size() * (self.HALO + p0) * self.plane
+        p.f.shift_period = sh.shape[1] * self.plane  # >= the span of the launch: addressed like u (ghost planes included)
+        ptr = lambda t, comp: self._p(t, comp, p0)
+        rc = K.lib().pxb_pds_iter(K.ALGO_PD3O, C.byref(d), C.byref(p), ptr(self._ub[src], 0), ptr(self._zb[src], 0), ptr(self._ub[dst], 0),
+                                  ptr(self._zb[dst], 0), ptr(self.x, 0) if x_out else None, A.ptr(nx), A.ptr(nz), A.stream())
+        K.check(rc, "pxb_pds_iter")
+
+    def _step_fused(self, want_norms):
+        n0, e = self.n0, self.edge
+        src, dst = self.cur, 1 - self.cur
+        nx = nz = None
+        if want_norms:
+            if self._x_stale:
+                self.materialize_x()
+            nrm = torch.zeros((2, 1, 2), dtype=torch.float64, device=self.dev)
+            nx, nz = nrm[0], nrm[1]
+        main = torch.cuda.current_stream()
+        main.wait_stream(self.comm)  # ghost planes of `src` (sent during the previous iteration) have arrived
+        self._tick("iter_begin")
+        if self.world > 1 and self.overlap and n0 >= 4 * e:
+            lo, hi = (e if self.hx.lo is not None else 0), (n0 - e if self.hx.hi is not None else n0)
+            if lo:
+                self._iter(0, lo, src, dst, want_norms, nx, nz)
+            if hi < n0:
+                self._iter(hi, n0, src, dst, want_norms, nx, nz)
+            self.comm.wait_stream(main)
+            with torch.cuda.stream(self.comm):
+                self._wait(self._exchange_state(dst))  # the new boundary planes travel while the interior is computed
+            self._iter(lo, hi, src, dst, want_norms, nx, nz)
+        else:
+            self._iter(0, n0, src, dst, want_norms, nx, nz)
+            if self.world > 1:
+                self.comm.wait_stream(main)
+                with torch.cuda.stream(self.comm):
+                    self._wait(self._exchange_state(dst))
+        self._tick("iter_end")
+        self.cur = dst
+        self._x_stale = not want_norms
+        if want_norms:
+            v = nrm.reshape(-1)
+            dist.all_reduce(v, group=self.group)
+            return v.cpu().numpy()
+        return None
+
+    def materialize_x(self):
+        """x_k = prox_g(u_{k-1} - tau K^T z_{k-1}) from the previous iterate (kept in the other ping-pong pair)."""
+        if not (self.fused and self._x_stale):
+            return
+        prev = 1 - self.cur
+        torch.cuda.current_stream().wait_stream(self.comm)
+        tmp_u, tmp_w = self._ub[prev].clone(), torch.empty_like(self._ub[prev])
+        d, p = self._desc(0, self.n0), self._params()
+        sh = self.shift_h
+        p.f.shift = sh.data_ptr() + sh.element_size() * self.HALO * self.plane
+        p.f.shift_period = sh.shape[1] * self.plane
+        rc = K.lib().pxb_pds_primal(K.ALGO_PD3O, C.byref(d), C.byref(p), self._p(tmp_u, 0, 0), self._p(self._zb[prev], 0, 0), None,
+                                    self._p(self.x, 0, 0), self._p(tmp_w, 0, 0), None, A.stream())
+        K.check(rc, "pxb_pds_primal")
+        self._x_stale = False
+
     # -- one PD3O iteration ------------------------------------------------------------------------
     def step(self, want_norms=False):
+        if self.fused:
+            return self._step_fused(want_norms)
         h, n0 = self.HALO, self.n0
         nx = nz = None
         if want_norms:  # kernels accumulate into (rows, 2) buffers
@@ -241,6 +363,7 @@ class SlabPD3OTV:
 
     def gather_x(self):
         """Full primal iterate on every rank (tests / small volumes only)."""
+        self.materialize_x()
         h = self.HALO
         parts = partition(self.shape[0], self.world)
         nmax = max(b - a for a, b in parts)

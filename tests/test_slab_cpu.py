@@ -205,3 +205,140 @@ def test_halo_exchanger_gloo(world, periodic):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+# ---- single-kernel iteration on slabs (SlabPD3OTV fused path) -------------------------------------------
+class _RankIter:
+    """Simulated rank of the single-kernel slab path: ping-pong (u, z) pairs, shift stored WITH ghost planes."""
+
+    H = 1
+
+    def __init__(self, shape, y, a, b, rank, world, scheme):
+        self.n0, self.plane = b - a, shape[1] * shape[2]
+        self.has_lo, self.has_hi = rank > 0, rank < world - 1
+        alloc = self.n0 + 2 * self.H
+        self.K = pxo.Gradient(arg_shape=shape, scheme=scheme)
+        f = lambda c=1: np.zeros((c, alloc) + shape[1:])
+        self.ub, self.zb, self.x, self.sh = [f(), f()], [f(3), f(3)], f(), f()
+        self.cur = 0
+        self.ub[0][0, 1:-1] = y[a:b]
+        self.x[0, 1:-1] = y[a:b]
+        self.sh[0, 1:-1] = -y[a:b]
+
+    def ptr(self, t, comp, plane):
+        return C.c_void_p(t.ctypes.data + 8 * ((comp * t.shape[1] + self.H + plane) * self.plane))
+
+    def desc(self, p0, p1):
+        lo = 1 if (p0 > 0 or self.has_lo) else 0
+        hi = 1 if (p1 < self.n0 or self.has_hi) else 0
+        return self.K._desc(1, K.F64, slab=K.Slab(lo, hi, self.H, self.n0 + 2 * self.H), shape0=p1 - p0)
+
+    def iterate(self, p0, p1, prm, form, chunk):
+        tau, sigma, rho, lam = prm
+        d = self.desc(p0, p1)
+        P = E.pds_params(tau, sigma, rho, gspec=(K.PROX_POS, 0, 0), fkind=K.F_SQL2, alpha=0.5, hkind=K.DUAL_L21, lam=lam)
+        P.f.shift = self.sh.ctypes.data + 8 * (self.H + p0) * self.plane
+        P.f.shift_period = self.sh.shape[1] * self.plane
+        s, t = self.cur, 1 - self.cur
+        fn = E.lib().emu_tv_iter if form == "direct" else E.lib().emu_tv_iter_tma
+        rc = fn(K.ALGO_PD3O, C.byref(d), C.byref(P), self.ptr(self.ub[s], 0, p0), self.ptr(self.zb[s], 0, p0), self.ptr(self.ub[t], 0, p0),
+                self.ptr(self.zb[t], 0, p0), self.ptr(self.x, 0, p0), None, None, chunk)
+        assert rc == 0, rc
+
+
+def _exchange_iter(ranks, idx):
+    """u, z_0..2 first owned plane -> lower neighbour's upper ghost; z_0 last owned plane -> upper neighbour's lower ghost"""
+    for r, rk in enumerate(ranks):
+        if r > 0:
+            lo = ranks[r - 1]
+            lo.ub[idx][0][-1] = rk.ub[idx][0][1]
+            for c in range(3):
+                lo.zb[idx][c][-1] = rk.zb[idx][c][1]
+        if r + 1 < len(ranks):
+            ranks[r + 1].zb[idx][0][0] = rk.zb[idx][0][rk.n0]
+
+
+@pytest.mark.parametrize("form", ["direct", "tma"])
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("scheme", ["forward"])
+def test_slab_single_kernel_iteration_equals_single_domain(world, form, scheme):
+    shape, n_iter, lam = (13, 6, 8), 10, 0.08
+    tau = sigma = 0.28
+    rho = 1.3
+    y = np.random.default_rng(1).random(shape)
+    # single-domain reference: two-sweep generic bodies
+    Kop = pxo.Gradient(arg_shape=shape, scheme=scheme)
+    shift = np.ascontiguousarray(-y.reshape(-1))
+    P = E.pds_params(tau, sigma, rho, gspec=(K.PROX_POS, 0, 0), fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L21, lam=lam)
+    d = Kop._desc(1, K.F64)
+    x_ref = y.reshape(-1).copy()
+    z_ref = E.gradient_run(Kop, x_ref, False)
+    u_ref, w = x_ref.copy(), np.empty_like(x_ref)
+    for _ in range(n_iter):
+        E.lib().emu_pds_primal(K.ALGO_PD3O, C.byref(d), C.byref(P), E.p(u_ref), E.p(z_ref), None, E.p(x_ref), E.p(w), None)
+        E.lib().emu_pds_dual(C.byref(d), C.byref(P), E.p(w), E.p(z_ref), None)
+
+    parts = partition(shape[0], world)
+    ranks = [_RankIter(shape, y, a, b, r, world, scheme) for r, (a, b) in enumerate(parts)]
+    prm = (tau, sigma, rho, lam)
+    for r, rk in enumerate(ranks):  # ghost planes of x0 and of the shift; z0 = K x0
+        if r > 0:
+            ranks[r - 1].x[0][-1] = rk.x[0][1]
+            ranks[r - 1].sh[0][-1] = rk.sh[0][1]
+        if r + 1 < world:
+            ranks[r + 1].x[0][0] = rk.x[0][rk.n0]
+            ranks[r + 1].sh[0][0] = rk.sh[0][rk.n0]
+    for rk in ranks:
+        dd = rk.desc(0, rk.n0)
+        E.lib().emu_gradient(C.byref(dd), 0, rk.ptr(rk.x, 0, 0), rk.ptr(rk.zb[0], 0, 0))
+    _exchange_iter(ranks, 0)
+    for it in range(n_iter):
+        for rk in ranks:  # boundary chunks first, then the interior (same order as SlabPD3OTV._step_fused)
+            e = 2
+            lo, hi = (e if rk.has_lo else 0), (rk.n0 - e if rk.has_hi else rk.n0)
+            if lo:
+                rk.iterate(0, lo, prm, form, 3)
+            if hi < rk.n0:
+                rk.iterate(hi, rk.n0, prm, form, 3)
+            if lo < hi:
+                rk.iterate(lo, hi, prm, form, 2)
+        for rk in ranks:
+            rk.cur = 1 - rk.cur
+        _exchange_iter(ranks, ranks[0].cur)
+    x = np.concatenate([rk.x[0, 1:-1] for rk in ranks], axis=0).reshape(-1)
+    z = np.concatenate([rk.zb[rk.cur][:, 1:-1] for rk in ranks], axis=1).reshape(-1)
+    assert np.allclose(x, x_ref, rtol=1e-13, atol=1e-15) and np.allclose(z, z_ref, rtol=1e-13, atol=1e-15)
+
+
+def _worker_many(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n0, h = 4, 1
+        mk = lambda v: torch.full((n0 + 2 * h, 2, 3), float(v), dtype=torch.float64)
+        u, z0, z1 = mk(10 + rank), mk(20 + rank), mk(30 + rank)
+        hx = HaloExchanger()
+        for r in hx.exchange_many([(u, False, True), (z0, True, True), (z1, False, True)], h, n0):
+            r.wait()
+        ok = True
+        if rank + 1 < world:  # upper ghosts hold the upper neighbour's first planes
+            ok &= bool((u[-1] == 10 + rank + 1).all() and (z0[-1] == 20 + rank + 1).all() and (z1[-1] == 30 + rank + 1).all())
+        if rank > 0:  # lower ghost: only z0 travels up
+            ok &= bool((z0[0] == 20 + rank - 1).all() and (u[0] == 10 + rank).all() and (z1[0] == 30 + rank).all())
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_many_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 3
+    procs = [ctx.Process(target=_worker_many, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]
