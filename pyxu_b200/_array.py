@@ -62,9 +62,78 @@ def asdevice(arr, dtype=None):
     return t, origin
 
 
+_BIG = 64 << 20      # results above this size leave the device through the pipelined path
+_CHUNK = 32 << 20     # bytes per staging buffer
+_STAGE = None         # pinned staging buffers (allocated once, on first use)
+
+
+def _advise_hugepages(arr):
+    """First touch of a fresh multi-GiB NumPy array is page-fault bound (~2 GB/s with 4 KiB pages): ask for
+    transparent huge pages.  Best effort."""
+    try:
+        libc = C.CDLL(None, use_errno=True)
+        addr, n = arr.ctypes.data, arr.nbytes
+        lo = (addr + (1 << 21) - 1) & ~((1 << 21) - 1)
+        hi = (addr + n) & ~((1 << 21) - 1)
+        if hi > lo:
+            libc.madvise(C.c_void_p(lo), C.c_size_t(hi - lo), 14)  # MADV_HUGEPAGE
+    except Exception:
+        pass
+
+
+def _d2h_pipelined(t):
+    """Device -> pageable host array at PCIe speed: chunks travel into pinned staging buffers on a copy stream while
+    a few host threads move the previous chunk into the result (first-touch faults spread over the threads)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    global _STAGE
+    nb = 3
+    if _STAGE is None:
+        _STAGE = [torch.empty(_CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(nb)]
+    flat = t.reshape(-1).view(torch.uint8)
+    nbytes = flat.numel()
+    out = np.empty(t.numel(), dtype=np_dtype(t.dtype))
+    _advise_hugepages(out)
+    out_b = out.view(np.uint8)
+    nthreads = max(1, min(8, (os.cpu_count() or 2) // 2))
+    copy_stream = torch.cuda.Stream(device=t.device)
+    copy_stream.wait_stream(torch.cuda.current_stream())
+    nchunks = (nbytes + _CHUNK - 1) // _CHUNK
+    events, futures = [None] * nchunks, [[] for _ in range(nb)]
+
+    def move(buf, lo, hi, a, b):  # staging[a:b] -> out[lo+a : lo+b]
+        np.copyto(out_b[lo + a : lo + b], buf[a:b])
+
+    with ThreadPoolExecutor(nthreads) as pool:
+        for k in range(nchunks + 1):
+            if k < nchunks:
+                for f in futures[k % nb]:
+                    f.result()  # the buffer's previous content has been copied out
+                lo, hi = k * _CHUNK, min(nbytes, (k + 1) * _CHUNK)
+                with torch.cuda.stream(copy_stream):
+                    _STAGE[k % nb][: hi - lo].copy_(flat[lo:hi], non_blocking=True)
+                    events[k] = torch.cuda.Event()
+                    events[k].record()
+            if k >= 1:
+                j = k - 1
+                events[j].synchronize()
+                lo, hi = j * _CHUNK, min(nbytes, (j + 1) * _CHUNK)
+                buf = _STAGE[j % nb].numpy()
+                step = -(-(hi - lo) // nthreads)
+                futures[j % nb] = [pool.submit(move, buf, lo, hi, a, min(hi - lo, a + step)) for a in range(0, hi - lo, step)]
+        for fs in futures:
+            for f in fs:
+                f.result()
+    t.record_stream(copy_stream)
+    return out.reshape(tuple(t.shape))
+
+
 def restore(t, origin):
     """Give a result back in the caller's memory space."""
     if origin == HOST:
+        if t.is_cuda and t.is_contiguous() and t.numel() * t.element_size() >= _BIG and t.dtype in (torch.float32, torch.float64):
+            return _d2h_pipelined(t)
         return t.cpu().numpy()
     return t
 

@@ -238,3 +238,14 @@ def test_solver_fp32_tolerance_256cube_vs_oracle_property(env):
         assert slv._plan.iter_ok is True
         outs.append(slv.solution())
     assert relnp(outs[1], np.asarray(outs[0], dtype=np.float64)) < 1e-4
+
+
+def test_large_results_leave_the_device_through_the_pipelined_copy(env):
+    """HOST-origin results above 64 MiB: chunked D2H through pinned staging buffers == plain .cpu()."""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for dt, n in ((torch.float32, (70 << 20) // 4 + 12345), (torch.float64, (97 << 20) // 8 + 1)):
+        t = torch.randn(n, device="cuda", dtype=dt, generator=gen)
+        out = env.A.restore(t, env.A.HOST)
+        assert isinstance(out, np.ndarray) and out.shape == (n,) and np.array_equal(out, t.cpu().numpy())
+    t2 = torch.randn(3, (80 << 20) // 12, device="cuda", generator=gen)
+    assert np.array_equal(env.A.restore(t2, env.A.HOST), t2.cpu().numpy())
