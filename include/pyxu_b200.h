@@ -82,6 +82,34 @@ int pxb_stencil_apply(const pxb_stencil_desc* d, const void* in, void* out, void
 int pxb_stencil_adjoint(const pxb_stencil_desc* d, const void* in, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Tiled 2-D stencil for 'constant' boundaries: the whole correlation over the last two axes in ONE pass, also when */
+/* the kernel is separable (the reference chains one 1-D stencil per axis, stencil.py:497-538, 441-450), with the    */
+/* input window of each tile staged in shared memory by TMA (out-of-image samples zero-filled == numpy.pad           */
+/* 'constant', pad.py:252-258).  Arrays are (nimg, n1, n2); nimg collects every leading dimension.                  */
+/*   out[i] = alpha * S(in)[i] + beta * add[i % add_period]          (add nullable; add_period <= 0: same size)     */
+/* S: dense == 0: taps coef1 (ksize[0], along axis n1) and coef2 (ksize[1], along n2), entry center[] on the output  */
+/*    dense == 1: ksize[0] x ksize[1] coefficients of `dtype` at DEVICE pointer `coef`, C-order.                     */
+/* The transpose of such an S is the same call with both factors reversed and center = ksize - 1 - center            */
+/* (stencil.py:452-461 with zero padding).  Returns PXB_ENOSUP outside the envelope (more than 16 row taps; more     */
+/* than 13 (fp32) / 11 (fp64) column taps; last axis not a multiple of 4 / 2 samples; unaligned arrays).             */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct pxb_stencil2d {
+    int32_t dtype;
+    int32_t dense;
+    int64_t nimg;
+    int64_t shape[2];
+    int32_t ksize[2];
+    int32_t center[2];
+    double coef1[16];
+    double coef2[16];
+    const void* coef;
+    double alpha, beta;
+    const void* add;
+    int64_t add_period;
+} pxb_stencil2d;
+int pxb_stencil2d_apply(const pxb_stencil2d* d, const void* in, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Gradient stack: ndir first-order 1-D derivative stencils, direction k acting along           */
 /* axis[k] (reference: src/pyxu/operator/linop/diff.py:1113-1265 Gradient,                      */
 /* :952-1056 _stack_diff_ops, :157-261 finite-difference coefficients).                         */

@@ -43,6 +43,24 @@ class StencilDesc(C.Structure):
     ]
 
 
+class Stencil2D(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("dense", C.c_int32),
+        ("nimg", C.c_int64),
+        ("shape", C.c_int64 * 2),
+        ("ksize", C.c_int32 * 2),
+        ("center", C.c_int32 * 2),
+        ("coef1", C.c_double * 16),
+        ("coef2", C.c_double * 16),
+        ("coef", C.c_void_p),
+        ("alpha", C.c_double),
+        ("beta", C.c_double),
+        ("add", C.c_void_p),
+        ("add_period", C.c_int64),
+    ]
+
+
 class GradDesc(C.Structure):
     _fields_ = [
         ("dtype", C.c_int32),
@@ -96,6 +114,7 @@ PROTOTYPES = {
     "pxb_launch_count": (_i64, []),
     "pxb_stencil_apply": (_i, [_P(StencilDesc), _vp, _vp, _vp]),
     "pxb_stencil_adjoint": (_i, [_P(StencilDesc), _vp, _vp, _vp]),
+    "pxb_stencil2d_apply": (_i, [_P(Stencil2D), _vp, _vp, _vp]),
     "pxb_gradient_apply": (_i, [_P(GradDesc), _vp, _vp, _vp]),
     "pxb_gradient_adjoint": (_i, [_P(GradDesc), _vp, _vp, _vp]),
     "pxb_prox_lincomb": (_i, [_i, _P(ProxSpec), _d, _i64, _vp, _d, _vp, _d, _vp, _i64, _d, _vp, _i64, _vp]),

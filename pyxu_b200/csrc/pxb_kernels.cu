@@ -248,6 +248,20 @@ int pxb_stencil_adjoint(const pxb_stencil_desc* d, const void* in, void* out, vo
     return stencil_launch(d, in, out, stream, 1, "pxb_stencil_adjoint");
 }
 
+int pxb_stencil2d_apply(const pxb_stencil2d* d, const void* in, void* out, void* stream) {
+    const char* who = "pxb_stencil2d_apply";
+    if (!d || !in || !out) return fail(PXB_EINVAL, "%s: null argument", who);
+    if (d->dtype != PXB_F32 && d->dtype != PXB_F64) return fail(PXB_EINVAL, "%s: bad dtype %d", who, d->dtype);
+    if (in == out) return fail(PXB_EINVAL, "%s: in and out must not alias", who);
+    if (d->nimg < 1 || d->shape[0] < 1 || d->shape[1] < 1) return fail(PXB_EINVAL, "%s: empty array", who);
+    if (d->dense && !d->coef) return fail(PXB_EINVAL, "%s: dense kernel without coefficients", who);
+    cudaError_t err = cudaSuccess;
+    if (int why = pxb_stencil2d_try(d, in, out, (cudaStream_t)stream, &err)) return fail(PXB_ENOSUP, "%s: outside the tiled kernel's envelope (reason %d)", who, why);
+    pxb_count_launch();
+    if (err != cudaSuccess) return fail(PXB_ECUDA, "%s: %s", who, cudaGetErrorString(err));
+    return 0;
+}
+
 int pxb_gradient_apply(const pxb_grad_desc* d, const void* x, void* z, void* stream) {
     const char* who = "pxb_gradient_apply";
     if (int e = check_grad(d, who)) return e;

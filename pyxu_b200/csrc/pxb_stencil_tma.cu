@@ -1,0 +1,111 @@
+// pxb_stencil_tma.cu -- launcher of the TMA-staged 2-D stencil (design: pxb_stencil_tma.cuh).
+//   thread 0:   one cp.async.bulk.tensor.3d box load (SASS UTMALDG) of the tile's input window, mbarrier completion
+//   256 threads: [dense] stage the k1 x k2 coefficients in shared memory while the box is in flight;
+//                wait -> row pass -> __syncthreads -> column pass + epilogue   (separable)
+//                wait -> register-blocked accumulation + epilogue              (dense)
+// No in-CTA pipelining: 22-50 KB of shared memory per CTA leaves 4-8 CTAs per SM, whose loads overlap each other's math.
+#include "pxb_launch.cuh"
+#include "pxb_tma_util.cuh"
+#include "pxb_stencil_tma.cuh"
+
+namespace {
+
+template <class T, int VEC, int NV, bool DENSE>
+__global__ void __launch_bounds__(256) k_stencil2d_tma(const __grid_constant__ PxbSt2P p, const __grid_constant__ CUtensorMap map, T* __restrict__ out) {
+    using C = PxbSt2Cfg<T, VEC>;
+    extern __shared__ __align__(128) unsigned char pxb_st2_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    T* box = reinterpret_cast<T*>(pxb_st2_smem);
+    const int box_elems = (p.bh * p.bw + 31) / 32 * 32;
+    T* mid = box + box_elems;  // separable: bh x TX intermediate; dense: k1*k2 coefficients
+    const int tid = threadIdx.x;
+    unsigned blk = blockIdx.x;
+    const int tx = blk % (unsigned)p.ntx; blk /= (unsigned)p.ntx;
+    const int ty = blk % (unsigned)p.nty;
+    const int64_t img = blk / (unsigned)p.nty;
+    const int x0 = tx * C::TX, y0 = ty * C::TY;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, (uint32_t)(p.bh * p.bw * sizeof(T)));
+        tma_load_3d(box, &map, &bar, x0 - p.c2, y0 - p.c1, (int)img);
+    }
+    if (DENSE) {
+        const T* __restrict__ ck = (const T*)p.coef;
+        for (int i = tid; i < p.k1 * p.k2; i += C::NT) mid[i] = ck[i];
+    }
+    mbar_wait(&bar, 0);
+    const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
+    T acc[C::R][VEC];
+    if (!DENSE) {
+        for (int it = tid; it < p.bh * C::TXL; it += C::NT) pxb_st2_row_item<T, VEC, NV>(p, box, mid, it >> 5, (it & 31) * VEC);
+        __syncthreads();
+        pxb_st2_col_item<T, VEC>(p, mid, yl, xl, acc);
+    } else {
+        __syncthreads();
+        pxb_st2_dense_item<T, VEC, NV>(p, box, mid, yl, xl, acc);
+    }
+    pxb_st2_store<T, VEC>(p, out, img, y0, x0, yl, xl, acc);
+}
+
+template <class T, int VEC, int NV>
+cudaError_t launch_nv(const PxbSt2P& p, const CUtensorMap& map, T* out, cudaStream_t s) {
+    using C = PxbSt2Cfg<T, VEC>;
+    const size_t box_bytes = (size_t)((p.bh * p.bw + 31) / 32 * 32) * sizeof(T);
+    const size_t smem = box_bytes + (p.dense ? (size_t)p.k1 * p.k2 * sizeof(T) : (size_t)p.bh * C::TX * sizeof(T));
+    const unsigned grid = (unsigned)((int64_t)p.ntx * p.nty * p.nimg);
+    cudaError_t e;
+    if (p.dense) {
+        auto k = k_stencil2d_tma<T, VEC, NV, true>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, C::NT, smem, s>>>(p, map, out);
+    } else {
+        auto k = k_stencil2d_tma<T, VEC, NV, false>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, C::NT, smem, s>>>(p, map, out);
+    }
+    return cudaGetLastError();
+}
+
+template <class T>
+int run(PxbSt2P& p, const void* in, void* out, cudaStream_t s, cudaError_t* err) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (int why = pxb_st2_setup<T, VEC>(p)) return why;
+    const uint64_t dim[3] = {(uint64_t)p.n2, (uint64_t)p.n1, (uint64_t)p.nimg};
+    const uint64_t stride[3] = {1, (uint64_t)p.n2, (uint64_t)p.n1 * (uint64_t)p.n2};
+    const uint32_t box[3] = {(uint32_t)p.bw, (uint32_t)p.bh, 1};
+    alignas(64) CUtensorMap map;
+    if (!pxb_tma_encode<T>(3, in, dim, stride, box, &map)) return 10;
+    const int nv = pxb_st2_nv(p.k2, VEC);
+    switch (nv) {
+        case 1: *err = launch_nv<T, VEC, 1>(p, map, (T*)out, s); break;
+        case 2: *err = launch_nv<T, VEC, 2>(p, map, (T*)out, s); break;
+        case 3: *err = launch_nv<T, VEC, 3>(p, map, (T*)out, s); break;
+        case 4: *err = launch_nv<T, VEC, 4>(p, map, (T*)out, s); break;
+        default:
+            if constexpr (VEC == 2) {
+                if (nv == 5) { *err = launch_nv<T, VEC, 5>(p, map, (T*)out, s); break; }
+                if (nv == 6) { *err = launch_nv<T, VEC, 6>(p, map, (T*)out, s); break; }
+            }
+            return 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// > 0: outside the envelope (reason); 0: launched or *err set
+int pxb_stencil2d_try(const pxb_stencil2d* d, const void* in, void* out, cudaStream_t s, cudaError_t* err) {
+    PxbSt2P p;
+    p.n1 = (int)d->shape[0]; p.n2 = (int)d->shape[1]; p.nimg = d->nimg;
+    p.k1 = d->ksize[0]; p.k2 = d->ksize[1]; p.c1 = d->center[0]; p.c2 = d->center[1];
+    p.dense = d->dense;
+    for (int i = 0; i < PXB_ST2_MAXTAP; ++i) { p.coef1[i] = d->coef1[i]; p.coef2[i] = d->coef2[i]; }
+    p.coef = d->coef; p.alpha = d->alpha; p.beta = d->beta; p.add = d->add; p.add_period = d->add_period;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(d->add)) & 15u) return 6;
+    if (d->add && d->add_period > 0 && d->add_period >= d->nimg * d->shape[0] * d->shape[1]) p.add_period = 0;
+    return d->dtype == PXB_F32 ? run<float>(p, in, out, s, err) : run<double>(p, in, out, s, err);
+}

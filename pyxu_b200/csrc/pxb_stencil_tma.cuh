@@ -1,0 +1,142 @@
+// pxb_stencil_tma.cuh -- shared-memory-tiled 2-D stencil ('constant' boundaries) with TMA-staged halos.
+//
+// One CTA = one tile of TY x TX outputs of one image.  A single TMA box load brings the (TY + k1 - 1) x (TX + k2 - 1)
+// input window into shared memory; samples outside the image are ZERO-FILLED by the TMA unit, which is the reference's
+// 'constant' Pad (pad.py:252-258), so no thread ever tests a boundary.  Then either
+//   * separable (k = k1 (x) k2, what the reference runs as a CHAIN of 1-D stencils, one HBM round trip each:
+//     stencil.py:497-538): row pass shared -> shared, column pass shared -> registers: ONE HBM round trip;
+//   * dense k1 x k2: register-blocked accumulation (4 rows x VEC columns per thread) out of shared memory.
+// Epilogue: out = alpha * S(in) + beta * add[i % period]  (fuses the "- y" of a data term A x - y).
+// HBM traffic: 8 B/voxel (fp32) + the halo re-reads, which are L2 hits (neighbouring tiles run together).
+//
+// The per-thread bodies are __host__ __device__; tests/emu replays them with the box load emulated.
+#pragma once
+#include "pxb_tv_fast.cuh"
+
+#define PXB_ST2_MAXTAP 16
+
+struct PxbSt2P {          // by-value kernel parameter
+    int n1, n2;           // image rows, columns
+    int64_t nimg;
+    int k1, k2, c1, c2;   // taps / centers along rows (axis 1) and columns (axis 2)
+    int dense;
+    int bw, bh;           // input box: columns (multiple of VEC), rows = TY + k1 - 1
+    int ntx, nty;         // tiles per image
+    double coef1[PXB_ST2_MAXTAP], coef2[PXB_ST2_MAXTAP];
+    const void* coef;     // dense: device pointer to k1*k2 coefficients
+    double alpha, beta;
+    const void* add;
+    int64_t add_period;
+};
+
+template <class T, int VEC>
+struct PxbSt2Cfg {
+    static constexpr int TXL = 32, TX = TXL * VEC, TY = 32, R = 4, NT = TXL * (TY / R);
+};
+
+// row pass for one vector item: t[y][x..x+VEC) = sum_q c2[q] * in[y][x + q ...]; NV vectors cover the window
+template <class T, int VEC, int NV>
+PXB_HD void pxb_st2_row_item(const PxbSt2P& p, const T* __restrict__ box, T* __restrict__ mid, int y, int xl) {
+    using C = PxbSt2Cfg<T, VEC>;
+    T v[NV * VEC];
+    const T* __restrict__ src = box + y * p.bw + xl;
+    for (int n = 0; n < NV; ++n) {
+        const PxbVec<T, VEC> t = pxb_vload<T, VEC>(src + n * VEC);
+        for (int j = 0; j < VEC; ++j) v[n * VEC + j] = t.v[j];
+    }
+    PxbVec<T, VEC> acc;
+    for (int j = 0; j < VEC; ++j) acc.v[j] = T(0);
+    for (int q = 0; q < NV * VEC - VEC + 1; ++q) {
+        if (q < p.k2) {
+            const T c = T(p.coef2[q]);
+            for (int j = 0; j < VEC; ++j) acc.v[j] += c * v[q + j];
+        }
+    }
+    pxb_vstore<T, VEC>(mid + y * C::TX + xl, acc);
+}
+
+// column pass + epilogue for one thread: R adjacent rows x VEC columns
+template <class T, int VEC>
+PXB_HD void pxb_st2_col_item(const PxbSt2P& p, const T* __restrict__ mid, int yl, int xl, T (*acc)[VEC]) {
+    using C = PxbSt2Cfg<T, VEC>;
+    for (int r = 0; r < C::R; ++r)
+        for (int j = 0; j < VEC; ++j) acc[r][j] = T(0);
+    for (int i = 0; i < C::R + p.k1 - 1; ++i) {
+        const PxbVec<T, VEC> t = pxb_vload<T, VEC>(mid + (yl + i) * C::TX + xl);
+        for (int r = 0; r < C::R; ++r) {
+            const int q = i - r;
+            if (q >= 0 && q < p.k1) {
+                const T c = T(p.coef1[q]);
+                for (int j = 0; j < VEC; ++j) acc[r][j] += c * t.v[j];
+            }
+        }
+    }
+}
+
+// dense k1 x k2 for one thread; `ck`: the coefficients in shared memory (row-major k1 x k2)
+template <class T, int VEC, int NV>
+PXB_HD void pxb_st2_dense_item(const PxbSt2P& p, const T* __restrict__ box, const T* __restrict__ ck, int yl, int xl, T (*acc)[VEC]) {
+    using C = PxbSt2Cfg<T, VEC>;
+    for (int r = 0; r < C::R; ++r)
+        for (int j = 0; j < VEC; ++j) acc[r][j] = T(0);
+    for (int q1 = 0; q1 < p.k1; ++q1) {
+        T c[NV * VEC - VEC + 1];
+        for (int q = 0; q < NV * VEC - VEC + 1; ++q) c[q] = q < p.k2 ? ck[q1 * p.k2 + q] : T(0);
+        for (int r = 0; r < C::R; ++r) {
+            T v[NV * VEC];
+            const T* __restrict__ src = box + (yl + r + q1) * p.bw + xl;
+            for (int n = 0; n < NV; ++n) {
+                const PxbVec<T, VEC> t = pxb_vload<T, VEC>(src + n * VEC);
+                for (int j = 0; j < VEC; ++j) v[n * VEC + j] = t.v[j];
+            }
+            for (int q = 0; q < NV * VEC - VEC + 1; ++q)
+                for (int j = 0; j < VEC; ++j) acc[r][j] += c[q] * v[q + j];
+        }
+    }
+}
+
+// epilogue + store of one thread's R x VEC outputs (tile origin (y0, x0) of image `img`)
+template <class T, int VEC>
+PXB_HD void pxb_st2_store(const PxbSt2P& p, T* __restrict__ out, int64_t img, int y0, int x0, int yl, int xl, T (*acc)[VEC]) {
+    using C = PxbSt2Cfg<T, VEC>;
+    const int x = x0 + xl;
+    if (x >= p.n2) return;
+    const T alpha = T(p.alpha), beta = T(p.beta);
+    const T* __restrict__ add = (const T*)p.add;
+    for (int r = 0; r < C::R; ++r) {
+        const int y = y0 + yl + r;
+        if (y >= p.n1) break;
+        const int64_t lin = (img * p.n1 + y) * (int64_t)p.n2 + x;
+        PxbVec<T, VEC> o;
+        for (int j = 0; j < VEC; ++j) o.v[j] = alpha * acc[r][j];
+        if (add) {
+            if (p.add_period <= 0) {
+                const PxbVec<T, VEC> a = pxb_vload<T, VEC>(add + lin);
+                for (int j = 0; j < VEC; ++j) o.v[j] += beta * a.v[j];
+            } else {
+                for (int j = 0; j < VEC; ++j) o.v[j] += beta * add[(lin + j) % p.add_period];
+            }
+        }
+        pxb_vstore<T, VEC>(out + lin, o);
+    }
+}
+
+// number of VEC-wide vectors that cover a window of k taps starting at a vector boundary
+PXB_HD int pxb_st2_nv(int k, int vec) { return (k - 1 + vec + vec - 1) / vec; }
+
+// host: geometry.  Returns 0 or a reason code when outside the envelope.
+template <class T, int VEC>
+inline int pxb_st2_setup(PxbSt2P& p) {
+    using C = PxbSt2Cfg<T, VEC>;
+    if (p.k1 < 1 || p.k2 < 1 || p.k1 > PXB_ST2_MAXTAP || p.k2 > PXB_ST2_MAXTAP) return 1;
+    if (pxb_st2_nv(p.k2, VEC) > (VEC == 4 ? 4 : 6)) return 1;  // compiled window widths: 13 taps (fp32), 11 taps (fp64)
+    if (p.n2 % VEC) return 2;
+    if (p.c1 < 0 || p.c1 >= p.k1 || p.c2 < 0 || p.c2 >= p.k2) return 3;
+    p.bh = C::TY + p.k1 - 1;
+    p.bw = C::TX + (pxb_st2_nv(p.k2, VEC) - 1) * VEC;
+    if (p.bw > 256 || p.bh > 256) return 4;
+    p.ntx = (p.n2 + C::TX - 1) / C::TX;
+    p.nty = (p.n1 + C::TY - 1) / C::TY;
+    if ((int64_t)p.ntx * p.nty * p.nimg > 0x7fffffffLL) return 5;
+    return 0;
+}

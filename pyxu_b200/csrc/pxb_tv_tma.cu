@@ -5,44 +5,11 @@
 //   all 256 threads:       wait(stage m) -> phase A out of shared memory -> __syncthreads -> [thread 0 refills the
 //                          stage just consumed with plane m+3] -> phase C of plane m-1
 // Shared memory per CTA (fp32): 3 x 28.5 KB stages + 21.8 KB w ring = 107 KB  -> 2 CTAs per SM.
-#include <cuda.h>
-
 #include "pxb_launch.cuh"
+#include "pxb_tma_util.cuh"
 #include "pxb_tv_tma.cuh"
 
 namespace {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Spin on the phase parity; a bounded number of polls, then trap: a wrong transaction count must fail the launch
-// loudly instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
 
 template <class T, int VEC, int TY, int ALGO, bool NORMS, class S>
 __global__ void __launch_bounds__(32 * TY, 2)
@@ -141,33 +108,6 @@ __global__ void __launch_bounds__(32 * TY, 2)
     }
 }
 
-// ---- tensor maps ---------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
-        return (EncodeTiledFn)p;
-    }();
-    return fn;
-}
-
-template <class T>
-bool encode(const PxbTmaBoxDesc& m, CUtensorMap* out) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    cuuint64_t dims[5], strides[4];
-    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
-    for (int i = 0; i < 5; ++i) { dims[i] = m.dim[i]; box[i] = m.box[i]; }
-    for (int i = 1; i < 5; ++i) strides[i - 1] = m.stride[i] * sizeof(T);
-    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
-    return fn(out, dt, 5, const_cast<void*>(m.base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <class T, int ALGO, bool NORMS>
 int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a, int chunk_hint, cudaStream_t s, cudaError_t* err) {
     constexpr int VEC = 16 / (int)sizeof(T), TY = 8;
@@ -183,7 +123,8 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
     PxbTmaBoxDesc mz1 = mz;
     mz1.box[1] = C::BR1;
     alignas(64) CUtensorMap tu, ts, tz, tz1;
-    if (!encode<T>(mu, &tu) || !encode<T>(ms, &ts) || !encode<T>(mz, &tz) || !encode<T>(mz1, &tz1)) return 23;
+    auto enc = [](const PxbTmaBoxDesc& m, CUtensorMap* out) { return pxb_tma_encode<T>(5, m.base, m.dim, m.stride, m.box, out); };
+    if (!enc(mu, &tu) || !enc(ms, &ts) || !enc(mz, &tz) || !enc(mz1, &tz1)) return 23;
     // specialised instances: forward differences + L21 + shifted squared-l2 data term staged per voxel + g in
     // {positivity, none}; everything else runs the generic instance
     const int spec = pxb_tma_pick_spec<T>(cf, q, tg);

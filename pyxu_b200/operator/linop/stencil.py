@@ -114,6 +114,7 @@ class Stencil(pxo.SquareOp):
         self._pad_width = tuple(self._pad_width)
 
         self._dev_coef = {}  # (dtype, device, pass, flipped) -> device tensor
+        self._tiled_ok = None  # TMA-tiled single-pass kernel (pxb_stencil2d_apply): None = not tried yet
         self.lipschitz = self.estimate_lipschitz(__rule=True)
 
     # -- descriptors ---------------------------------------------------------------------
@@ -159,6 +160,96 @@ class Stencil(pxo.SquareOp):
             self._dev_coef[key] = t
         return t
 
+    # -- TMA-tiled path ('constant' boundaries) --------------------------------------------------------
+    def _tiled_plan(self, adjoint):
+        """Splits the stencil into (factor along axis 0 | None, in-plane part) when the tiled kernel applies.
+        In-plane part: ("sep", taps1, c1, taps2, c2) or ("dense", k2d, c1, c2).  None when not applicable."""
+        if any(m != "constant" for m, p in zip(self._mode, self._pad_width) if p[0] > 0):
+            return None
+        passes = self._passes(False)
+        if adjoint:  # zero-padded correlation: transpose = correlation with the reversed kernel, mirrored center
+            passes = [(np.ascontiguousarray(np.flip(k3)), np.array(k3.shape) - c3 - 1) for k3, c3 in passes]
+        axis0, f1, f2, dense, scale = None, None, None, None, 1.0
+        for k3, c3 in passes:
+            nz = [a for a in range(3) if k3.shape[a] > 1]
+            if len(nz) == 0:  # a 1-tap factor is a scalar
+                scale *= float(k3.reshape(-1)[0])
+            elif len(nz) == 1:
+                a = nz[0]
+                if a == 0 and axis0 is None:
+                    axis0 = (k3, c3)
+                elif a == 1 and f1 is None:
+                    f1 = (k3.reshape(-1), int(c3[1]))
+                elif a == 2 and f2 is None:
+                    f2 = (k3.reshape(-1), int(c3[2]))
+                else:
+                    return None
+            elif nz == [1, 2] and len(passes) == 1:
+                dense = (k3[0], int(c3[1]), int(c3[2]))
+            else:
+                return None
+        if dense is not None:
+            return axis0, ("dense",) + dense, scale
+        if f1 is None and f2 is None:
+            return None
+        one = (np.ones(1, dtype=self._dtype), 0)
+        f1, f2 = f1 or one, f2 or one
+        if f1[0].size > 16 or f2[0].size > 16:
+            return None
+        return axis0, ("sep", f1[0], f1[1], f2[0], f2[1]), scale
+
+    def _run_tiled(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
+        """One pass over HBM for the in-plane part (+ one generic pass when there is a factor along axis 0).
+        Returns None when the tiled kernel does not apply."""
+        if self._tiled_ok is False:
+            return None
+        plan = self._tiled_plan(adjoint)
+        if plan is None:
+            self._tiled_ok = False
+            return None
+        axis0, inplane, scale = plan
+        alpha = alpha * scale
+        D = len(self._arg_shape)
+        shape3 = (1,) * (3 - D) + self._arg_shape
+        batch = max(1, arr.numel() // self.dim)
+        d = K.Stencil2D()
+        d.dtype, d.nimg = A.dcode(arr), batch * shape3[0]
+        d.shape[0], d.shape[1] = shape3[1], shape3[2]
+        keep = None
+        if inplane[0] == "dense":
+            _, k2d, c1, c2 = inplane
+            keep, _ = A.asdevice(np.ascontiguousarray(k2d.reshape(-1)), dtype=arr.dtype) if ("tiled", adjoint, arr.dtype) not in self._dev_coef else (self._dev_coef[("tiled", adjoint, arr.dtype)], None)
+            self._dev_coef[("tiled", adjoint, arr.dtype)] = keep
+            d.dense, d.coef = 1, keep.data_ptr()
+            d.ksize[0], d.ksize[1], d.center[0], d.center[1] = k2d.shape[0], k2d.shape[1], c1, c2
+        else:
+            _, t1, c1, t2, c2 = inplane
+            d.dense = 0
+            d.ksize[0], d.ksize[1], d.center[0], d.center[1] = t1.size, t2.size, c1, c2
+            for i, v in enumerate(t1):
+                d.coef1[i] = float(v)
+            for i, v in enumerate(t2):
+                d.coef2[i] = float(v)
+        cur = arr
+        if axis0 is not None:  # the factor along the slowest axis keeps the generic kernel (one more pass)
+            k3, c3 = axis0
+            coef, _ = A.asdevice(np.ascontiguousarray(k3.reshape(-1)), dtype=arr.dtype)
+            dd = self._desc(k3, c3, batch, A.dcode(arr), coef.data_ptr())
+            tmp = A.empty_like(arr)
+            K.check(K.lib().pxb_stencil_apply(C.byref(dd), A.ptr(cur), A.ptr(tmp), A.stream()), "Stencil")
+            cur = tmp
+        d.alpha, d.beta = float(alpha), float(beta)
+        if add is not None:
+            d.add, d.add_period = add.data_ptr(), add.numel()
+        out = A.empty_like(arr)
+        rc = K.lib().pxb_stencil2d_apply(C.byref(d), A.ptr(cur), A.ptr(out), A.stream())
+        if rc == -3:
+            self._tiled_ok = False
+            return None
+        K.check(rc, "pxb_stencil2d_apply")
+        self._tiled_ok = True
+        return out
+
     def _run(self, arr, adjoint):
         if arr.shape[-1] != self.dim:
             raise ValueError(f"{self}: expected (..., {self.dim}) input, got {tuple(arr.shape)}")
@@ -168,6 +259,10 @@ class Stencil(pxo.SquareOp):
             from ...info import PrecisionWarning
 
             warnings.warn("Computation may not be performed at the requested precision.", PrecisionWarning)
+        if arr.is_contiguous():
+            out = self._run_tiled(arr, adjoint)
+            if out is not None:
+                return out
         batch = max(1, arr.numel() // self.dim)
         fn = K.lib().pxb_stencil_adjoint if adjoint else K.lib().pxb_stencil_apply
         cur = arr

@@ -11,6 +11,7 @@
 #include "../../pyxu_b200/csrc/pxb_tv_fast.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_iter.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_tma.cuh"
+#include "../../pyxu_b200/csrc/pxb_stencil_tma.cuh"
 #include <vector>
 
 #define FOR_VOX(batch, g)                              \
@@ -256,7 +257,61 @@ static int t_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
     return -131;
 }
 
+// TMA-tiled 2-D stencil (pxb_stencil_tma.cuh): box load emulated as a zero-filled gather, then the device's
+// per-thread bodies in barrier order.
+template <class T, int VEC, int NV>
+static void t_st2_nv(const PxbSt2P& p, const T* in, T* out) {
+    using C = PxbSt2Cfg<T, VEC>;
+    std::vector<T> box((size_t)p.bh * p.bw), mid((size_t)p.bh * C::TX + (size_t)p.k1 * p.k2);
+    for (int64_t img = 0; img < p.nimg; ++img)
+        for (int ty = 0; ty < p.nty; ++ty)
+            for (int tx = 0; tx < p.ntx; ++tx) {
+                const int x0 = tx * C::TX, y0 = ty * C::TY;
+                for (int i = 0; i < p.bh; ++i)
+                    for (int j = 0; j < p.bw; ++j) {
+                        const int y = y0 - p.c1 + i, x = x0 - p.c2 + j;
+                        box[(size_t)i * p.bw + j] = (y >= 0 && y < p.n1 && x >= 0 && x < p.n2) ? in[(img * p.n1 + y) * (int64_t)p.n2 + x] : T(0);
+                    }
+                if (p.dense)
+                    for (int i = 0; i < p.k1 * p.k2; ++i) mid[i] = ((const T*)p.coef)[i];
+                else
+                    for (int it = 0; it < p.bh * C::TXL; ++it) pxb_st2_row_item<T, VEC, NV>(p, box.data(), mid.data(), it / C::TXL, (it % C::TXL) * VEC);
+                for (int tid = 0; tid < C::NT; ++tid) {
+                    const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
+                    T acc[C::R][VEC];
+                    if (p.dense) pxb_st2_dense_item<T, VEC, NV>(p, box.data(), mid.data(), yl, xl, acc);
+                    else pxb_st2_col_item<T, VEC>(p, mid.data(), yl, xl, acc);
+                    pxb_st2_store<T, VEC>(p, out, img, y0, x0, yl, xl, acc);
+                }
+            }
+}
+template <class T>
+static int t_st2(const pxb_stencil2d* d, const void* in, void* out) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    PxbSt2P p;
+    p.n1 = (int)d->shape[0]; p.n2 = (int)d->shape[1]; p.nimg = d->nimg;
+    p.k1 = d->ksize[0]; p.k2 = d->ksize[1]; p.c1 = d->center[0]; p.c2 = d->center[1];
+    p.dense = d->dense;
+    for (int i = 0; i < PXB_ST2_MAXTAP; ++i) { p.coef1[i] = d->coef1[i]; p.coef2[i] = d->coef2[i]; }
+    p.coef = d->coef; p.alpha = d->alpha; p.beta = d->beta; p.add = d->add; p.add_period = d->add_period;
+    if (d->add && d->add_period > 0 && d->add_period >= d->nimg * d->shape[0] * d->shape[1]) p.add_period = 0;
+    if (int why = pxb_st2_setup<T, VEC>(p)) return -100 - why;
+    switch (pxb_st2_nv(p.k2, VEC)) {
+        case 1: t_st2_nv<T, VEC, 1>(p, (const T*)in, (T*)out); break;
+        case 2: t_st2_nv<T, VEC, 2>(p, (const T*)in, (T*)out); break;
+        case 3: t_st2_nv<T, VEC, 3>(p, (const T*)in, (T*)out); break;
+        case 4: t_st2_nv<T, VEC, 4>(p, (const T*)in, (T*)out); break;
+        case 5: t_st2_nv<T, VEC, 5>(p, (const T*)in, (T*)out); break;
+        case 6: t_st2_nv<T, VEC, 6>(p, (const T*)in, (T*)out); break;
+        default: return -101;
+    }
+    return 0;
+}
+
 extern "C" {
+int emu_stencil2d(const pxb_stencil2d* d, const void* in, void* out) {
+    return d->dtype == PXB_F32 ? t_st2<float>(d, in, out) : t_st2<double>(d, in, out);
+}
 int emu_tv_iter_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
                     void* x_out, double* nx, double* nz, int chunk) {
     if (K->dtype == PXB_F32) return t_tma<float>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);

@@ -23,6 +23,7 @@ def lib():
         h.emu_tv_fast.argtypes = [i, i, i, P(K.GradDesc), P(K.PdsParams), vp, vp, vp, vp, vp]
         h.emu_tv_iter.argtypes = [i, P(K.GradDesc), P(K.PdsParams), vp, vp, vp, vp, vp, vp, vp, i]
         h.emu_tv_iter_tma.argtypes = h.emu_tv_iter.argtypes
+        h.emu_stencil2d.argtypes = [P(K.Stencil2D), vp, vp]
         h.emu_dual_update.argtypes = [i, i, i64, i64, i64, d, d, d, vp, vp, vp]
         h.emu_prox_l21.argtypes = [i, i64, i64, i64, d, d, vp, vp]
         h.emu_prox_lincomb.argtypes = [i, P(K.ProxSpec), d, i64, vp, d, vp, d, vp, i64, d, vp, i64]
@@ -76,3 +77,45 @@ def pds_params(tau, sigma, rho, gspec=(K.PROX_NONE, 0.0, 0.0), fkind=K.F_NONE, a
     P.f = f
     P.hkind, P.lam = hkind, lam
     return P
+
+
+def stencil_run_tiled(op, x, adjoint, alpha=1.0, beta=0.0, add=None):
+    """Mirror of Stencil._run_tiled on host arrays (TMA-tiled single-pass kernel, emulated)."""
+    x = np.ascontiguousarray(x)
+    plan = op._tiled_plan(adjoint)
+    if plan is None:
+        return None
+    axis0, inplane, scale = plan
+    D = len(op._arg_shape)
+    shape3 = (1,) * (3 - D) + op._arg_shape
+    batch = max(1, x.size // op.dim)
+    d = K.Stencil2D()
+    d.dtype, d.nimg = dcode(x), batch * shape3[0]
+    d.shape[0], d.shape[1] = shape3[1], shape3[2]
+    keep = None
+    if inplane[0] == "dense":
+        _, k2d, c1, c2 = inplane
+        keep = np.ascontiguousarray(k2d.reshape(-1), dtype=x.dtype)
+        d.dense, d.coef = 1, keep.ctypes.data
+        d.ksize[0], d.ksize[1], d.center[0], d.center[1] = k2d.shape[0], k2d.shape[1], c1, c2
+    else:
+        _, t1, c1, t2, c2 = inplane
+        d.ksize[0], d.ksize[1], d.center[0], d.center[1] = t1.size, t2.size, c1, c2
+        for i, v in enumerate(t1):
+            d.coef1[i] = float(v)
+        for i, v in enumerate(t2):
+            d.coef2[i] = float(v)
+    cur = x
+    if axis0 is not None:
+        k3, c3 = axis0
+        coef = np.ascontiguousarray(k3.reshape(-1), dtype=x.dtype)
+        dd = op._desc(k3, c3, batch, dcode(x), coef.ctypes.data)
+        tmp = np.empty_like(x)
+        lib().emu_stencil(C.byref(dd), 0, p(cur), p(tmp))
+        cur = tmp
+    d.alpha, d.beta = alpha * scale, beta
+    if add is not None:
+        d.add, d.add_period = add.ctypes.data, add.size
+    out = np.empty_like(x)
+    rc = lib().emu_stencil2d(C.byref(d), p(cur), p(out))
+    return out if rc == 0 else None
