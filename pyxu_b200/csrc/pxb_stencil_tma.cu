@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) k_stencil2d_tma(const __grid_constant__ P
     }
     if (DENSE) {
         const T* __restrict__ ck = (const T*)p.coef;
-        for (int i = tid; i < p.k1 * p.k2; i += C::NT) mid[i] = ck[i];
+        for (int i = tid; i < p.k1 * p.k2; i += C::NT) mid[i] = pxb_st2_dense_coef<T>(p, ck, i);
     }
     mbar_wait(&bar, 0);
     const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;

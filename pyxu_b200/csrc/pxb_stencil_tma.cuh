@@ -18,7 +18,9 @@
 struct PxbSt2P {          // by-value kernel parameter
     int n1, n2;           // image rows, columns
     int64_t nimg;
-    int k1, k2, c1, c2;   // taps / centers along rows (axis 1) and columns (axis 2)
+    int k1, k2, c1, c2;   // taps / centers along rows (axis 1) and columns (axis 2) -- k2 / c2 AFTER the alignment padding below
+    int k2src, extra;     // TMA box starts must be 16-byte aligned in global memory (measured: a start at c0 - 3 floats
+                          // faults): the column factor gets `extra` leading zero taps so that its center is a multiple of VEC
     int dense;
     int bw, bh;           // input box: columns (multiple of VEC), rows = TY + k1 - 1
     int ntx, nty;         // tiles per image
@@ -121,6 +123,13 @@ PXB_HD void pxb_st2_store(const PxbSt2P& p, T* __restrict__ out, int64_t img, in
     }
 }
 
+// dense coefficients as the kernel sees them (row-major k1 x k2 with the leading zero taps): element i
+template <class T>
+PXB_HD T pxb_st2_dense_coef(const PxbSt2P& p, const T* __restrict__ ck, int i) {
+    const int q1 = i / p.k2, q = i - q1 * p.k2;
+    return q >= p.extra ? ck[q1 * p.k2src + q - p.extra] : T(0);
+}
+
 // number of VEC-wide vectors that cover a window of k taps starting at a vector boundary
 PXB_HD int pxb_st2_nv(int k, int vec) { return (k - 1 + vec + vec - 1) / vec; }
 
@@ -129,9 +138,16 @@ template <class T, int VEC>
 inline int pxb_st2_setup(PxbSt2P& p) {
     using C = PxbSt2Cfg<T, VEC>;
     if (p.k1 < 1 || p.k2 < 1 || p.k1 > PXB_ST2_MAXTAP || p.k2 > PXB_ST2_MAXTAP) return 1;
+    if (p.c1 < 0 || p.c1 >= p.k1 || p.c2 < 0 || p.c2 >= p.k2) return 3;
+    p.k2src = p.k2;
+    p.extra = (VEC - p.c2 % VEC) % VEC;
+    if (p.k2 + p.extra > PXB_ST2_MAXTAP) return 1;
+    for (int q = p.k2 - 1; q >= 0; --q) p.coef2[q + p.extra] = p.coef2[q];
+    for (int q = 0; q < p.extra; ++q) p.coef2[q] = 0.0;
+    p.k2 += p.extra;
+    p.c2 += p.extra;
     if (pxb_st2_nv(p.k2, VEC) > (VEC == 4 ? 4 : 6)) return 1;  // compiled window widths: 13 taps (fp32), 11 taps (fp64)
     if (p.n2 % VEC) return 2;
-    if (p.c1 < 0 || p.c1 >= p.k1 || p.c2 < 0 || p.c2 >= p.k2) return 3;
     p.bh = C::TY + p.k1 - 1;
     p.bw = C::TX + (pxb_st2_nv(p.k2, VEC) - 1) * VEC;
     if (p.bw > 256 || p.bh > 256) return 4;

@@ -273,7 +273,7 @@ static void t_st2_nv(const PxbSt2P& p, const T* in, T* out) {
                         box[(size_t)i * p.bw + j] = (y >= 0 && y < p.n1 && x >= 0 && x < p.n2) ? in[(img * p.n1 + y) * (int64_t)p.n2 + x] : T(0);
                     }
                 if (p.dense)
-                    for (int i = 0; i < p.k1 * p.k2; ++i) mid[i] = ((const T*)p.coef)[i];
+                    for (int i = 0; i < p.k1 * p.k2; ++i) mid[i] = pxb_st2_dense_coef<T>(p, (const T*)p.coef, i);
                 else
                     for (int it = 0; it < p.bh * C::TXL; ++it) pxb_st2_row_item<T, VEC, NV>(p, box.data(), mid.data(), it / C::TXL, (it % C::TXL) * VEC);
                 for (int tid = 0; tid < C::NT; ++tid) {

@@ -21,7 +21,7 @@ CASES = [
     ((5, 130, 264), [np.r_[1.0, 2.0, -1.0], gauss(7, 1.2), gauss(7, 1.2)], (1, 3, 3)),
     ((4, 130, 264), np.arange(1.0, 10.0).reshape(1, 3, 3), (0, 1, 1)),
     ((4100,), np.r_[1.0, 2, -3, 0.5, 7], (2,)),
-    ((45, 48), [np.r_[2.0], gauss(11, 2.0)], (0, 5)),
+    ((45, 48), [np.r_[2.0], gauss(11, 2.0)], (0, 4)),
 ]
 
 
