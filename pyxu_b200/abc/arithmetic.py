@@ -409,8 +409,38 @@ class _Composed:
     def adjoint(self, arr):
         return self._rhs.adjoint(self._lhs.adjoint(arr))
 
+    def _data_term_grad(self, arr):
+        """grad of alpha*||A x + shift||^2 with A a Stencil the tiled kernel serves:  A^T (2 alpha (A x + shift)) in two
+        passes -- the affine part rides in the stencil kernel's epilogue (out = a*S(in) + b*add) instead of a third pass."""
+        if getattr(self, "_dt_fast", None) is False or not hasattr(self._rhs, "_run_tiled"):
+            return None
+        spec = self._lhs._sql2_spec() if hasattr(self._lhs, "_sql2_spec") else None
+        if spec is None or not arr.is_contiguous():
+            self._dt_fast = False
+            return None
+        alpha, shift = spec
+        key = (arr.dtype, arr.device)
+        cache = getattr(self, "_dt_shift", None)
+        if cache is None or cache[0] != key:
+            dev = None
+            if shift is not None:
+                dev, _ = A.asdevice(np.atleast_1d(shift) if np.isscalar(shift) else shift, dtype=arr.dtype)
+                dev = dev.reshape(-1)
+                if arr.numel() % dev.numel() != 0:
+                    self._dt_fast = False
+                    return None
+            cache = self._dt_shift = (key, dev)
+        r = self._rhs._run_tiled(arr, False, alpha=2.0 * alpha, beta=2.0 * alpha, add=cache[1])
+        if r is None:
+            self._dt_fast = False
+            return None
+        return self._rhs.adjoint(r)
+
     @device_io
     def grad(self, arr):
+        fast = self._data_term_grad(arr)
+        if fast is not None:
+            return fast
         x = self._lhs.grad(self._rhs.apply(arr))
         if self._rhs.is_linear:
             return self._rhs.adjoint(x)
