@@ -109,6 +109,7 @@ typedef struct pxb_stencil2d {
 } pxb_stencil2d;
 int pxb_stencil2d_apply(const pxb_stencil2d* d, const void* in, void* out, void* stream);
 
+
 /* ------------------------------------------------------------------------------------------ */
 /* Gradient stack: ndir first-order 1-D derivative stencils, direction k acting along           */
 /* axis[k] (reference: src/pyxu/operator/linop/diff.py:1113-1265 Gradient,                      */
@@ -160,6 +161,26 @@ int pxb_prox_lincomb(int dtype, const pxb_prox_spec* g, double tau, int64_t n, v
 /* out[i] = a*x[i] + b*y[i % ny] + c*z[i % nz]  (ScaleRule / ArgShiftRule / relaxation algebra). */
 int pxb_lincomb(int dtype, int64_t n, void* out, double a, const void* x, double b, const void* y,
                 int64_t ny, double c, const void* z, int64_t nz, void* stream);
+
+/* One accelerated proximal-gradient (FISTA) iteration on f = alpha_f*||A x + shift||^2, g pointwise, A such a stencil
+ * (reference: src/pyxu/opt/solver/pgd.py:173-191), as TWO tiled passes instead of five:
+ *   which == 0:  out = r = d.alpha * A((1+a) x - a x_prev) + d.beta * d.add      (d describes A; the extrapolated point
+ *                y is formed in shared memory from the two input windows, never written)
+ *   which == 1:  out = x_new = prox_{tau g}((1+a) x - a x_prev + d.alpha * A^T r) (d describes A^T, d.alpha = -tau);
+ *                out may be the x_prev buffer.  norms (nullable): per row += { sum (x_new - x)^2, sum x^2 }
+ *                with row = image / imgs_per_row  (RelError[x], stop.py:353-382).
+ * Envelope as pxb_stencil2d_apply. */
+typedef struct pxb_fista_step {
+    const void* x;
+    const void* x_prev;
+    const void* r;       /* which == 1 */
+    double a;            /* momentum a_k = k / (k + 1 + d);  0: plain proximal gradient */
+    double tau;
+    pxb_prox_spec g;
+    double* norms;
+    int64_t imgs_per_row;
+} pxb_fista_step;
+int pxb_stencil2d_fista(const pxb_stencil2d* d, const pxb_fista_step* f, int which, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Dual term h (reference: src/pyxu/operator/func/norm.py:352-364 L21Norm.prox, :47-52 L1Norm;  */

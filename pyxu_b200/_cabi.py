@@ -91,6 +91,19 @@ class FTerm(C.Structure):
     ]
 
 
+class FistaStep(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("x_prev", C.c_void_p),
+        ("r", C.c_void_p),
+        ("a", C.c_double),
+        ("tau", C.c_double),
+        ("g", ProxSpec),
+        ("norms", C.c_void_p),
+        ("imgs_per_row", C.c_int64),
+    ]
+
+
 class PdsParams(C.Structure):
     _fields_ = [
         ("tau", C.c_double),
@@ -115,6 +128,7 @@ PROTOTYPES = {
     "pxb_stencil_apply": (_i, [_P(StencilDesc), _vp, _vp, _vp]),
     "pxb_stencil_adjoint": (_i, [_P(StencilDesc), _vp, _vp, _vp]),
     "pxb_stencil2d_apply": (_i, [_P(Stencil2D), _vp, _vp, _vp]),
+    "pxb_stencil2d_fista": (_i, [_P(Stencil2D), _P(FistaStep), _i, _vp, _vp]),
     "pxb_gradient_apply": (_i, [_P(GradDesc), _vp, _vp, _vp]),
     "pxb_gradient_adjoint": (_i, [_P(GradDesc), _vp, _vp, _vp]),
     "pxb_prox_lincomb": (_i, [_i, _P(ProxSpec), _d, _i64, _vp, _d, _vp, _d, _vp, _i64, _d, _vp, _i64, _vp]),

@@ -262,6 +262,24 @@ int pxb_stencil2d_apply(const pxb_stencil2d* d, const void* in, void* out, void*
     return 0;
 }
 
+int pxb_stencil2d_fista(const pxb_stencil2d* d, const pxb_fista_step* f, int which, void* out, void* stream) {
+    const char* who = "pxb_stencil2d_fista";
+    if (!d || !f || !out || !f->x) return fail(PXB_EINVAL, "%s: null argument", who);
+    if (d->dtype != PXB_F32 && d->dtype != PXB_F64) return fail(PXB_EINVAL, "%s: bad dtype %d", who, d->dtype);
+    if (which != 0 && which != 1) return fail(PXB_EINVAL, "%s: which must be 0 (residual) or 1 (prox step)", who);
+    if (f->a != 0.0 && !f->x_prev) return fail(PXB_EINVAL, "%s: momentum needs x_prev", who);
+    if (which == 1 && !f->r) return fail(PXB_EINVAL, "%s: the prox step needs r", who);
+    if (which == 1 && (f->g.kind < PXB_PROX_NONE || f->g.kind > PXB_PROX_SQL2)) return fail(PXB_EINVAL, "%s: bad g kind", who);
+    if (which == 1 && (out == f->x || out == f->r)) return fail(PXB_EINVAL, "%s: out may alias x_prev only", who);
+    if (which == 0 && (out == f->x || out == f->x_prev)) return fail(PXB_EINVAL, "%s: out must not alias the inputs", who);
+    if (d->dense && !d->coef) return fail(PXB_EINVAL, "%s: dense kernel without coefficients", who);
+    cudaError_t err = cudaSuccess;
+    if (int why = pxb_stencil2d_fista_try(d, f, which, out, (cudaStream_t)stream, &err)) return fail(PXB_ENOSUP, "%s: outside the tiled kernel's envelope (reason %d)", who, why);
+    pxb_count_launch();
+    if (err != cudaSuccess) return fail(PXB_ECUDA, "%s: %s", who, cudaGetErrorString(err));
+    return 0;
+}
+
 int pxb_gradient_apply(const pxb_grad_desc* d, const void* x, void* z, void* stream) {
     const char* who = "pxb_gradient_apply";
     if (int e = check_grad(d, who)) return e;

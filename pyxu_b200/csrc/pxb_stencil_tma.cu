@@ -10,14 +10,18 @@
 
 namespace {
 
-template <class T, int VEC, int NV, bool DENSE>
-__global__ void __launch_bounds__(256) k_stencil2d_tma(const __grid_constant__ PxbSt2P p, const __grid_constant__ CUtensorMap map, T* __restrict__ out) {
+// MODE 0: out = alpha*S(in) + beta*add      1: the same on the window pa*in + pb*in2 (two box loads, combined in
+// shared memory)      2: proximal-gradient epilogue (pxb_st2_store_prox)
+template <class T, int VEC, int NV, bool DENSE, int MODE>
+__global__ void __launch_bounds__(256) k_stencil2d_tma(const __grid_constant__ PxbSt2P p, const __grid_constant__ CUtensorMap map,
+                                                       const __grid_constant__ CUtensorMap map2, T* __restrict__ out) {
     using C = PxbSt2Cfg<T, VEC>;
     extern __shared__ __align__(128) unsigned char pxb_st2_smem[];
     __shared__ __align__(8) uint64_t bar;
     T* box = reinterpret_cast<T*>(pxb_st2_smem);
     const int box_elems = (p.bh * p.bw + 31) / 32 * 32;
-    T* mid = box + box_elems;  // separable: bh x TX intermediate; dense: k1*k2 coefficients
+    T* box2 = box + box_elems;                       // MODE 1 only
+    T* mid = box + (MODE == 1 ? 2 : 1) * box_elems;  // separable: bh x TX intermediate; dense: k1*k2 coefficients
     const int tid = threadIdx.x;
     unsigned blk = blockIdx.x;
     const int tx = blk % (unsigned)p.ntx; blk /= (unsigned)p.ntx;
@@ -30,14 +34,20 @@ __global__ void __launch_bounds__(256) k_stencil2d_tma(const __grid_constant__ P
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bar, (uint32_t)(p.bh * p.bw * sizeof(T)));
+        const uint32_t bytes = (uint32_t)(p.bh * p.bw * sizeof(T));
+        mbar_expect_tx(&bar, MODE == 1 ? 2 * bytes : bytes);
         tma_load_3d(box, &map, &bar, x0 - p.c2, y0 - p.c1, (int)img);
+        if (MODE == 1) tma_load_3d(box2, &map2, &bar, x0 - p.c2, y0 - p.c1, (int)img);
     }
     if (DENSE) {
         const T* __restrict__ ck = (const T*)p.coef;
         for (int i = tid; i < p.k1 * p.k2; i += C::NT) mid[i] = pxb_st2_dense_coef<T>(p, ck, i);
     }
     mbar_wait(&bar, 0);
+    if (MODE == 1) {
+        for (int it = tid; it < p.bh * p.bw / VEC; it += C::NT) pxb_st2_combine_item<T, VEC>(p, box, box2, it);
+        __syncthreads();
+    }
     const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
     T acc[C::R][VEC];
     if (!DENSE) {
@@ -48,51 +58,94 @@ __global__ void __launch_bounds__(256) k_stencil2d_tma(const __grid_constant__ P
         __syncthreads();
         pxb_st2_dense_item<T, VEC, NV>(p, box, mid, yl, xl, acc);
     }
-    pxb_st2_store<T, VEC>(p, out, img, y0, x0, yl, xl, acc);
+    if (MODE != 2) {
+        pxb_st2_store<T, VEC>(p, out, img, y0, x0, yl, xl, acc);
+    } else {
+        double nrm[2] = {0.0, 0.0};
+        pxb_st2_store_prox<T, VEC>(p, out, img, y0, x0, yl, xl, acc, nrm);
+        if (p.norms) {  // one image per CTA: warp shuffle -> shared -> one atomic pair
+            __shared__ double red[2][C::NT / 32];
+            for (int o = 16; o > 0; o >>= 1) {
+                nrm[0] += __shfl_down_sync(0xffffffffu, nrm[0], o);
+                nrm[1] += __shfl_down_sync(0xffffffffu, nrm[1], o);
+            }
+            if ((tid & 31) == 0) { red[0][tid >> 5] = nrm[0]; red[1][tid >> 5] = nrm[1]; }
+            __syncthreads();
+            if (tid == 0) {
+                double s0 = 0.0, s1 = 0.0;
+                for (int i = 0; i < C::NT / 32; ++i) { s0 += red[0][i]; s1 += red[1][i]; }
+                const int64_t row = img / p.imgs_per_row;
+                atomicAdd(p.norms + 2 * row, s0);
+                atomicAdd(p.norms + 2 * row + 1, s1);
+            }
+        }
+    }
 }
 
-template <class T, int VEC, int NV>
-cudaError_t launch_nv(const PxbSt2P& p, const CUtensorMap& map, T* out, cudaStream_t s) {
+template <class T, int VEC, int NV, bool DENSE, int MODE>
+cudaError_t launch_mode(const PxbSt2P& p, const CUtensorMap& map, const CUtensorMap& map2, T* out, cudaStream_t s) {
     using C = PxbSt2Cfg<T, VEC>;
     const size_t box_bytes = (size_t)((p.bh * p.bw + 31) / 32 * 32) * sizeof(T);
-    const size_t smem = box_bytes + (p.dense ? (size_t)p.k1 * p.k2 * sizeof(T) : (size_t)p.bh * C::TX * sizeof(T));
+    const size_t smem = (MODE == 1 ? 2 : 1) * box_bytes + (DENSE ? (size_t)p.k1 * p.k2 * sizeof(T) : (size_t)p.bh * C::TX * sizeof(T));
     const unsigned grid = (unsigned)((int64_t)p.ntx * p.nty * p.nimg);
-    cudaError_t e;
-    if (p.dense) {
-        auto k = k_stencil2d_tma<T, VEC, NV, true>;
-        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<grid, C::NT, smem, s>>>(p, map, out);
-    } else {
-        auto k = k_stencil2d_tma<T, VEC, NV, false>;
-        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<grid, C::NT, smem, s>>>(p, map, out);
+    auto k = k_stencil2d_tma<T, VEC, NV, DENSE, MODE>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
     }
+    k<<<grid, C::NT, smem, s>>>(p, map, map2, out);
     return cudaGetLastError();
 }
 
+template <class T, int VEC, int NV>
+cudaError_t launch_nv(const PxbSt2P& p, const CUtensorMap& map, const CUtensorMap& map2, int mode, T* out, cudaStream_t s) {
+    if (p.dense) {
+        if (mode == 1) return launch_mode<T, VEC, NV, true, 1>(p, map, map2, out, s);
+        if (mode == 2) return launch_mode<T, VEC, NV, true, 2>(p, map, map2, out, s);
+        return launch_mode<T, VEC, NV, true, 0>(p, map, map2, out, s);
+    }
+    if (mode == 1) return launch_mode<T, VEC, NV, false, 1>(p, map, map2, out, s);
+    if (mode == 2) return launch_mode<T, VEC, NV, false, 2>(p, map, map2, out, s);
+    return launch_mode<T, VEC, NV, false, 0>(p, map, map2, out, s);
+}
+
 template <class T>
-int run(PxbSt2P& p, const void* in, void* out, cudaStream_t s, cudaError_t* err) {
+int run(PxbSt2P& p, const void* in, const void* in2, void* out, cudaStream_t s, cudaError_t* err) {
     constexpr int VEC = 16 / (int)sizeof(T);
     if (int why = pxb_st2_setup<T, VEC>(p)) return why;
     const uint64_t dim[3] = {(uint64_t)p.n2, (uint64_t)p.n1, (uint64_t)p.nimg};
     const uint64_t stride[3] = {1, (uint64_t)p.n2, (uint64_t)p.n1 * (uint64_t)p.n2};
     const uint32_t box[3] = {(uint32_t)p.bw, (uint32_t)p.bh, 1};
-    alignas(64) CUtensorMap map;
+    alignas(64) CUtensorMap map, map2;
     if (!pxb_tma_encode<T>(3, in, dim, stride, box, &map)) return 10;
+    if (!pxb_tma_encode<T>(3, in2 ? in2 : in, dim, stride, box, &map2)) return 10;
+    const int mode = in2 ? 1 : (p.epi == 1 ? 2 : 0);
     const int nv = pxb_st2_nv(p.k2, VEC);
     switch (nv) {
-        case 1: *err = launch_nv<T, VEC, 1>(p, map, (T*)out, s); break;
-        case 2: *err = launch_nv<T, VEC, 2>(p, map, (T*)out, s); break;
-        case 3: *err = launch_nv<T, VEC, 3>(p, map, (T*)out, s); break;
-        case 4: *err = launch_nv<T, VEC, 4>(p, map, (T*)out, s); break;
+        case 1: *err = launch_nv<T, VEC, 1>(p, map, map2, mode, (T*)out, s); break;
+        case 2: *err = launch_nv<T, VEC, 2>(p, map, map2, mode, (T*)out, s); break;
+        case 3: *err = launch_nv<T, VEC, 3>(p, map, map2, mode, (T*)out, s); break;
+        case 4: *err = launch_nv<T, VEC, 4>(p, map, map2, mode, (T*)out, s); break;
         default:
             if constexpr (VEC == 2) {
-                if (nv == 5) { *err = launch_nv<T, VEC, 5>(p, map, (T*)out, s); break; }
-                if (nv == 6) { *err = launch_nv<T, VEC, 6>(p, map, (T*)out, s); break; }
+                if (nv == 5) { *err = launch_nv<T, VEC, 5>(p, map, map2, mode, (T*)out, s); break; }
+                if (nv == 6) { *err = launch_nv<T, VEC, 6>(p, map, map2, mode, (T*)out, s); break; }
             }
             return 1;
     }
     return 0;
+}
+
+// fills the kernel parameter block from the C-ABI descriptors (shared with tests/emu through the header? no: host only)
+void fill(PxbSt2P& p, const pxb_stencil2d* d) {
+    p.n1 = (int)d->shape[0]; p.n2 = (int)d->shape[1]; p.nimg = d->nimg;
+    p.k1 = d->ksize[0]; p.k2 = d->ksize[1]; p.c1 = d->center[0]; p.c2 = d->center[1];
+    p.dense = d->dense;
+    for (int i = 0; i < PXB_ST2_MAXTAP; ++i) { p.coef1[i] = d->coef1[i]; p.coef2[i] = d->coef2[i]; }
+    p.coef = d->coef; p.alpha = d->alpha; p.beta = d->beta; p.add = d->add; p.add_period = d->add_period;
+    if (d->add && d->add_period > 0 && d->add_period >= d->nimg * d->shape[0] * d->shape[1]) p.add_period = 0;
+    p.pa = 1.0; p.pb = 0.0; p.epi = 0; p.e1 = p.e2 = nullptr; p.ea = p.eb = 0.0; p.gkind = 0; p.gp0 = p.gp1 = p.tau = 0.0;
+    p.norms = nullptr; p.imgs_per_row = 1;
 }
 
 }  // namespace
@@ -100,12 +153,28 @@ int run(PxbSt2P& p, const void* in, void* out, cudaStream_t s, cudaError_t* err)
 // > 0: outside the envelope (reason); 0: launched or *err set
 int pxb_stencil2d_try(const pxb_stencil2d* d, const void* in, void* out, cudaStream_t s, cudaError_t* err) {
     PxbSt2P p;
-    p.n1 = (int)d->shape[0]; p.n2 = (int)d->shape[1]; p.nimg = d->nimg;
-    p.k1 = d->ksize[0]; p.k2 = d->ksize[1]; p.c1 = d->center[0]; p.c2 = d->center[1];
-    p.dense = d->dense;
-    for (int i = 0; i < PXB_ST2_MAXTAP; ++i) { p.coef1[i] = d->coef1[i]; p.coef2[i] = d->coef2[i]; }
-    p.coef = d->coef; p.alpha = d->alpha; p.beta = d->beta; p.add = d->add; p.add_period = d->add_period;
+    fill(p, d);
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(d->add)) & 15u) return 6;
-    if (d->add && d->add_period > 0 && d->add_period >= d->nimg * d->shape[0] * d->shape[1]) p.add_period = 0;
-    return d->dtype == PXB_F32 ? run<float>(p, in, out, s, err) : run<double>(p, in, out, s, err);
+    return d->dtype == PXB_F32 ? run<float>(p, in, nullptr, out, s, err) : run<double>(p, in, nullptr, out, s, err);
+}
+
+int pxb_stencil2d_fista_try(const pxb_stencil2d* d, const pxb_fista_step* f, int which, void* out, cudaStream_t s, cudaError_t* err) {
+    PxbSt2P p;
+    fill(p, d);
+    if ((reinterpret_cast<uintptr_t>(f->x) | reinterpret_cast<uintptr_t>(f->x_prev) | reinterpret_cast<uintptr_t>(f->r) | reinterpret_cast<uintptr_t>(out) |
+         reinterpret_cast<uintptr_t>(d->add)) & 15u)
+        return 6;
+    const void *in, *in2 = nullptr;
+    if (which == 0) {  // r = alpha * S((1+a) x - a x_prev) + beta * add
+        in = f->x;
+        if (f->a != 0.0) { in2 = f->x_prev; p.pa = 1.0 + f->a; p.pb = -f->a; }
+    } else {           // x_new = prox_{tau g}((1+a) x - a x_prev + alpha * S(r))
+        in = f->r;
+        p.epi = 1;
+        p.e1 = f->x; p.e2 = f->a != 0.0 ? f->x_prev : nullptr;
+        p.ea = 1.0 + f->a; p.eb = -f->a;
+        p.gkind = f->g.kind; p.gp0 = f->g.p0; p.gp1 = f->g.p1; p.tau = f->tau;
+        p.norms = f->norms; p.imgs_per_row = f->imgs_per_row > 0 ? f->imgs_per_row : 1;
+    }
+    return d->dtype == PXB_F32 ? run<float>(p, in, in2, out, s, err) : run<double>(p, in, in2, out, s, err);
 }

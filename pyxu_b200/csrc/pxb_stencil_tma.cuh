@@ -29,6 +29,18 @@ struct PxbSt2P {          // by-value kernel parameter
     double alpha, beta;
     const void* add;
     int64_t add_period;
+    // prologue (PRO): the stencil acts on  pa*in + pb*in2  (FISTA extrapolation y = (1+a) x - a x_prev), formed in shared memory
+    double pa, pb;
+    // epilogue kind 1 (proximal-gradient step):  v = ea*e1[i] + eb*e2[i] + alpha*S(.)[i];  out = prox_{tau g}(v);
+    //   norms[2*row] += (out - e1)^2, norms[2*row+1] += e1^2   (row = img / imgs_per_row)      -- pgd.py:179-191, stop.py:353-382
+    int epi;
+    const void* e1;
+    const void* e2;
+    double ea, eb;
+    int gkind;
+    double gp0, gp1, tau;
+    double* norms;
+    int64_t imgs_per_row;
 };
 
 template <class T, int VEC>
@@ -128,6 +140,46 @@ template <class T>
 PXB_HD T pxb_st2_dense_coef(const PxbSt2P& p, const T* __restrict__ ck, int i) {
     const int q1 = i / p.k2, q = i - q1 * p.k2;
     return q >= p.extra ? ck[q1 * p.k2src + q - p.extra] : T(0);
+}
+
+// proximal-gradient epilogue for one thread's R x VEC outputs; returns the RelError partial sums in nrm[0..1]
+template <class T, int VEC>
+PXB_HD void pxb_st2_store_prox(const PxbSt2P& p, T* __restrict__ out, int64_t img, int y0, int x0, int yl, int xl, T (*acc)[VEC], double* nrm) {
+    using C = PxbSt2Cfg<T, VEC>;
+    const int x = x0 + xl;
+    if (x >= p.n2) return;
+    const T alpha = T(p.alpha), ea = T(p.ea), eb = T(p.eb), tau = T(p.tau), gp0 = T(p.gp0), gp1 = T(p.gp1);
+    const T* __restrict__ e1 = (const T*)p.e1;
+    const T* __restrict__ e2 = (const T*)p.e2;
+    for (int r = 0; r < C::R; ++r) {
+        const int y = y0 + yl + r;
+        if (y >= p.n1) break;
+        const int64_t lin = (img * p.n1 + y) * (int64_t)p.n2 + x;
+        const PxbVec<T, VEC> a = pxb_vload<T, VEC>(e1 + lin);
+        PxbVec<T, VEC> b;
+        for (int j = 0; j < VEC; ++j) b.v[j] = T(0);
+        if (e2) b = pxb_vload<T, VEC>(e2 + lin);  // read before `out` (which may be the same buffer) is written
+        PxbVec<T, VEC> o;
+        for (int j = 0; j < VEC; ++j) {
+            const T v = ea * a.v[j] + eb * b.v[j] + alpha * acc[r][j];
+            o.v[j] = pxb_prox_eval<T>(p.gkind, gp0, gp1, v, tau);
+            if (p.norms) {
+                const double dd = (double)o.v[j] - (double)a.v[j];
+                nrm[0] += dd * dd;
+                nrm[1] += (double)a.v[j] * (double)a.v[j];
+            }
+        }
+        pxb_vstore<T, VEC>(out + lin, o);
+    }
+}
+
+// prologue: window = pa*box + pb*box2, vector item `it` of the (bh x bw) window
+template <class T, int VEC>
+PXB_HD void pxb_st2_combine_item(const PxbSt2P& p, T* __restrict__ box, const T* __restrict__ box2, int it) {
+    const PxbVec<T, VEC> a = pxb_vload<T, VEC>(box + it * VEC), b = pxb_vload<T, VEC>(box2 + it * VEC);
+    PxbVec<T, VEC> o;
+    for (int j = 0; j < VEC; ++j) o.v[j] = T(p.pa) * a.v[j] + T(p.pb) * b.v[j];
+    pxb_vstore<T, VEC>(box + it * VEC, o);
 }
 
 // number of VEC-wide vectors that cover a window of k taps starting at a vector boundary

@@ -198,9 +198,9 @@ class Stencil(pxo.SquareOp):
             return None
         return axis0, ("sep", f1[0], f1[1], f2[0], f2[1]), scale
 
-    def _run_tiled(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
-        """One pass over HBM for the in-plane part (+ one generic pass when there is a factor along axis 0).
-        Returns None when the tiled kernel does not apply."""
+    def _tiled_desc(self, like, adjoint, alpha=1.0, beta=0.0, add=None):
+        """(pxb_stencil2d descriptor, axis-0 factor or None) for arrays shaped like `like`; None when the tiled kernel
+        does not apply.  The descriptor keeps references to the device buffers it points to."""
         if self._tiled_ok is False:
             return None
         plan = self._tiled_plan(adjoint)
@@ -208,18 +208,19 @@ class Stencil(pxo.SquareOp):
             self._tiled_ok = False
             return None
         axis0, inplane, scale = plan
-        alpha = alpha * scale
         D = len(self._arg_shape)
         shape3 = (1,) * (3 - D) + self._arg_shape
-        batch = max(1, arr.numel() // self.dim)
+        batch = max(1, like.numel() // self.dim)
         d = K.Stencil2D()
-        d.dtype, d.nimg = A.dcode(arr), batch * shape3[0]
+        d.dtype, d.nimg = A.dcode(like), batch * shape3[0]
         d.shape[0], d.shape[1] = shape3[1], shape3[2]
-        keep = None
         if inplane[0] == "dense":
             _, k2d, c1, c2 = inplane
-            keep, _ = A.asdevice(np.ascontiguousarray(k2d.reshape(-1)), dtype=arr.dtype) if ("tiled", adjoint, arr.dtype) not in self._dev_coef else (self._dev_coef[("tiled", adjoint, arr.dtype)], None)
-            self._dev_coef[("tiled", adjoint, arr.dtype)] = keep
+            key = ("tiled", adjoint, like.dtype, like.device)
+            keep = self._dev_coef.get(key)
+            if keep is None:
+                keep, _ = A.asdevice(np.ascontiguousarray(k2d.reshape(-1)), dtype=like.dtype)
+                self._dev_coef[key] = keep
             d.dense, d.coef = 1, keep.data_ptr()
             d.ksize[0], d.ksize[1], d.center[0], d.center[1] = k2d.shape[0], k2d.shape[1], c1, c2
         else:
@@ -230,6 +231,20 @@ class Stencil(pxo.SquareOp):
                 d.coef1[i] = float(v)
             for i, v in enumerate(t2):
                 d.coef2[i] = float(v)
+        d.alpha, d.beta = float(alpha) * scale, float(beta)
+        if add is not None:
+            d.add, d.add_period = add.data_ptr(), add.numel()
+            d._keep = add
+        return d, axis0
+
+    def _run_tiled(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
+        """One pass over HBM for the in-plane part (+ one generic pass when there is a factor along axis 0).
+        Returns None when the tiled kernel does not apply."""
+        got = self._tiled_desc(arr, adjoint, alpha, beta, add)
+        if got is None:
+            return None
+        d, axis0 = got
+        batch = max(1, arr.numel() // self.dim)
         cur = arr
         if axis0 is not None:  # the factor along the slowest axis keeps the generic kernel (one more pass)
             k3, c3 = axis0
@@ -238,9 +253,6 @@ class Stencil(pxo.SquareOp):
             tmp = A.empty_like(arr)
             K.check(K.lib().pxb_stencil_apply(C.byref(dd), A.ptr(cur), A.ptr(tmp), A.stream()), "Stencil")
             cur = tmp
-        d.alpha, d.beta = float(alpha), float(beta)
-        if add is not None:
-            d.add, d.add_period = add.data_ptr(), add.numel()
         out = A.empty_like(arr)
         rc = K.lib().pxb_stencil2d_apply(C.byref(d), A.ptr(cur), A.ptr(out), A.stream())
         if rc == -3:

@@ -260,9 +260,9 @@ static int t_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
 // TMA-tiled 2-D stencil (pxb_stencil_tma.cuh): box load emulated as a zero-filled gather, then the device's
 // per-thread bodies in barrier order.
 template <class T, int VEC, int NV>
-static void t_st2_nv(const PxbSt2P& p, const T* in, T* out) {
+static void t_st2_nv(const PxbSt2P& p, const T* in, const T* in2, T* out) {
     using C = PxbSt2Cfg<T, VEC>;
-    std::vector<T> box((size_t)p.bh * p.bw), mid((size_t)p.bh * C::TX + (size_t)p.k1 * p.k2);
+    std::vector<T> box((size_t)p.bh * p.bw), box2((size_t)p.bh * p.bw), mid((size_t)p.bh * C::TX + (size_t)p.k1 * p.k2);
     for (int64_t img = 0; img < p.nimg; ++img)
         for (int ty = 0; ty < p.nty; ++ty)
             for (int tx = 0; tx < p.ntx; ++tx) {
@@ -270,8 +270,12 @@ static void t_st2_nv(const PxbSt2P& p, const T* in, T* out) {
                 for (int i = 0; i < p.bh; ++i)
                     for (int j = 0; j < p.bw; ++j) {
                         const int y = y0 - p.c1 + i, x = x0 - p.c2 + j;
-                        box[(size_t)i * p.bw + j] = (y >= 0 && y < p.n1 && x >= 0 && x < p.n2) ? in[(img * p.n1 + y) * (int64_t)p.n2 + x] : T(0);
+                        const bool ok = y >= 0 && y < p.n1 && x >= 0 && x < p.n2;
+                        box[(size_t)i * p.bw + j] = ok ? in[(img * p.n1 + y) * (int64_t)p.n2 + x] : T(0);
+                        if (in2) box2[(size_t)i * p.bw + j] = ok ? in2[(img * p.n1 + y) * (int64_t)p.n2 + x] : T(0);
                     }
+                if (in2)
+                    for (int it = 0; it < p.bh * p.bw / VEC; ++it) pxb_st2_combine_item<T, VEC>(p, box.data(), box2.data(), it);
                 if (p.dense)
                     for (int i = 0; i < p.k1 * p.k2; ++i) mid[i] = pxb_st2_dense_coef<T>(p, (const T*)p.coef, i);
                 else
@@ -281,12 +285,18 @@ static void t_st2_nv(const PxbSt2P& p, const T* in, T* out) {
                     T acc[C::R][VEC];
                     if (p.dense) pxb_st2_dense_item<T, VEC, NV>(p, box.data(), mid.data(), yl, xl, acc);
                     else pxb_st2_col_item<T, VEC>(p, mid.data(), yl, xl, acc);
-                    pxb_st2_store<T, VEC>(p, out, img, y0, x0, yl, xl, acc);
+                    if (p.epi == 1) {
+                        double nrm[2] = {0.0, 0.0};
+                        pxb_st2_store_prox<T, VEC>(p, out, img, y0, x0, yl, xl, acc, nrm);
+                        if (p.norms) { p.norms[2 * (img / p.imgs_per_row)] += nrm[0]; p.norms[2 * (img / p.imgs_per_row) + 1] += nrm[1]; }
+                    } else {
+                        pxb_st2_store<T, VEC>(p, out, img, y0, x0, yl, xl, acc);
+                    }
                 }
             }
 }
 template <class T>
-static int t_st2(const pxb_stencil2d* d, const void* in, void* out) {
+static int t_st2(const pxb_stencil2d* d, const pxb_fista_step* f, int which, const void* in0, void* out) {
     constexpr int VEC = 16 / (int)sizeof(T);
     PxbSt2P p;
     p.n1 = (int)d->shape[0]; p.n2 = (int)d->shape[1]; p.nimg = d->nimg;
@@ -295,14 +305,30 @@ static int t_st2(const pxb_stencil2d* d, const void* in, void* out) {
     for (int i = 0; i < PXB_ST2_MAXTAP; ++i) { p.coef1[i] = d->coef1[i]; p.coef2[i] = d->coef2[i]; }
     p.coef = d->coef; p.alpha = d->alpha; p.beta = d->beta; p.add = d->add; p.add_period = d->add_period;
     if (d->add && d->add_period > 0 && d->add_period >= d->nimg * d->shape[0] * d->shape[1]) p.add_period = 0;
+    p.pa = 1.0; p.pb = 0.0; p.epi = 0; p.e1 = p.e2 = nullptr; p.ea = p.eb = 0.0; p.gkind = 0; p.gp0 = p.gp1 = p.tau = 0.0;
+    p.norms = nullptr; p.imgs_per_row = 1;
+    const void *in = in0, *in2 = nullptr;
+    if (f) {  // same mapping as pxb_stencil2d_fista_try
+        if (which == 0) {
+            in = f->x;
+            if (f->a != 0.0) { in2 = f->x_prev; p.pa = 1.0 + f->a; p.pb = -f->a; }
+        } else {
+            in = f->r;
+            p.epi = 1;
+            p.e1 = f->x; p.e2 = f->a != 0.0 ? f->x_prev : nullptr;
+            p.ea = 1.0 + f->a; p.eb = -f->a;
+            p.gkind = f->g.kind; p.gp0 = f->g.p0; p.gp1 = f->g.p1; p.tau = f->tau;
+            p.norms = f->norms; p.imgs_per_row = f->imgs_per_row > 0 ? f->imgs_per_row : 1;
+        }
+    }
     if (int why = pxb_st2_setup<T, VEC>(p)) return -100 - why;
     switch (pxb_st2_nv(p.k2, VEC)) {
-        case 1: t_st2_nv<T, VEC, 1>(p, (const T*)in, (T*)out); break;
-        case 2: t_st2_nv<T, VEC, 2>(p, (const T*)in, (T*)out); break;
-        case 3: t_st2_nv<T, VEC, 3>(p, (const T*)in, (T*)out); break;
-        case 4: t_st2_nv<T, VEC, 4>(p, (const T*)in, (T*)out); break;
-        case 5: t_st2_nv<T, VEC, 5>(p, (const T*)in, (T*)out); break;
-        case 6: t_st2_nv<T, VEC, 6>(p, (const T*)in, (T*)out); break;
+        case 1: t_st2_nv<T, VEC, 1>(p, (const T*)in, (const T*)in2, (T*)out); break;
+        case 2: t_st2_nv<T, VEC, 2>(p, (const T*)in, (const T*)in2, (T*)out); break;
+        case 3: t_st2_nv<T, VEC, 3>(p, (const T*)in, (const T*)in2, (T*)out); break;
+        case 4: t_st2_nv<T, VEC, 4>(p, (const T*)in, (const T*)in2, (T*)out); break;
+        case 5: t_st2_nv<T, VEC, 5>(p, (const T*)in, (const T*)in2, (T*)out); break;
+        case 6: t_st2_nv<T, VEC, 6>(p, (const T*)in, (const T*)in2, (T*)out); break;
         default: return -101;
     }
     return 0;
@@ -310,7 +336,10 @@ static int t_st2(const pxb_stencil2d* d, const void* in, void* out) {
 
 extern "C" {
 int emu_stencil2d(const pxb_stencil2d* d, const void* in, void* out) {
-    return d->dtype == PXB_F32 ? t_st2<float>(d, in, out) : t_st2<double>(d, in, out);
+    return d->dtype == PXB_F32 ? t_st2<float>(d, nullptr, 0, in, out) : t_st2<double>(d, nullptr, 0, in, out);
+}
+int emu_stencil2d_fista(const pxb_stencil2d* d, const pxb_fista_step* f, int which, void* out) {
+    return d->dtype == PXB_F32 ? t_st2<float>(d, f, which, nullptr, out) : t_st2<double>(d, f, which, nullptr, out);
 }
 int emu_tv_iter_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
                     void* x_out, double* nx, double* nz, int chunk) {

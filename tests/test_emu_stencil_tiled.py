@@ -74,3 +74,75 @@ def test_tiled_not_applicable():
     op = pxo.Stencil(arg_shape=(20, 22), kernel=np.ones((3, 3), dtype=np.float32), center=(1, 1), mode="constant")
     x = np.zeros(op.dim, dtype=np.float32)
     assert E.stencil_run_tiled(op, x, False) is None  # fp32: the last axis must be a multiple of 4 samples
+
+
+@pytest.mark.parametrize("dense", [True, False])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fista_two_pass_form(dense, dtype):
+    """pxb_stencil2d_fista (which = 0, 1) == extrapolate, A y + shift, A^T r, soft-threshold, RelError sums -- step by step."""
+    import ctypes as C
+
+    from pyxu_b200 import _cabi as K
+
+    rng = np.random.default_rng(4)
+    shape, batch = (37, 72), 3
+    g1, g2 = gauss(5, 1.0), gauss(5, 1.3)
+    kern = np.outer(g1, g2).astype(dtype) if dense else [g1.astype(dtype), g2.astype(dtype)]
+    op = pxo.Stencil(arg_shape=shape, kernel=kern, center=(2, 1), mode="constant")
+    x = rng.standard_normal((batch, op.dim)).astype(dtype)
+    xp = rng.standard_normal((batch, op.dim)).astype(dtype)
+    shift = rng.standard_normal((batch, op.dim)).astype(dtype)
+    alpha, tau, lam = 0.5, 0.7, 0.05
+    tol = 1e-13 if dtype == np.float64 else 3e-6
+    for a in (0.0, 0.3):
+        y = (1 + a) * x - a * xp
+        r_ref = 2 * alpha * (E.stencil_run(op, y, False) + shift)
+        v = y - tau * E.stencil_run(op, r_ref, True)
+        x_ref = np.sign(v) * np.maximum(np.abs(v) - lam * tau, 0)
+        # descriptors exactly as PGD._setup_fista_fused builds them (host arrays instead of device tensors)
+        fw = _desc(op, x, False, 2 * alpha, 2 * alpha, shift)
+        bw = _desc(op, x, True, -tau, 0.0, None)
+        st = K.FistaStep()
+        r = np.empty_like(x)
+        nrm = np.zeros(2 * batch)
+        st.x, st.x_prev, st.r, st.a, st.tau = x.ctypes.data, xp.ctypes.data, r.ctypes.data, a, tau
+        st.g = K.ProxSpec(K.PROX_L1, 0, lam, 0.0)
+        st.norms, st.imgs_per_row = nrm.ctypes.data, 1
+        assert E.lib().emu_stencil2d_fista(C.byref(fw), C.byref(st), 0, E.p(r)) == 0
+        assert relerr(r, r_ref) < tol
+        out = xp.copy()  # x_new overwrites the x_prev buffer
+        st.x_prev = out.ctypes.data
+        assert E.lib().emu_stencil2d_fista(C.byref(bw), C.byref(st), 1, E.p(out)) == 0
+        assert relerr(out, x_ref) < tol
+        num = ((x_ref.astype(np.float64) - x) ** 2).sum(axis=1)
+        den = (x.astype(np.float64) ** 2).sum(axis=1)
+        assert np.allclose(nrm[0::2], num, rtol=1e-4 if dtype == np.float32 else 1e-10) and np.allclose(nrm[1::2], den, rtol=1e-6)
+
+
+def _desc(op, like, adjoint, alpha, beta, add):
+    """pxb_stencil2d descriptor on host arrays, mirroring Stencil._tiled_desc."""
+    from pyxu_b200 import _cabi as K
+
+    axis0, inplane, scale = op._tiled_plan(adjoint)
+    assert axis0 is None
+    D = len(op._arg_shape)
+    shape3 = (1,) * (3 - D) + op._arg_shape
+    d = K.Stencil2D()
+    d.dtype, d.nimg = E.dcode(like), max(1, like.size // op.dim) * shape3[0]
+    d.shape[0], d.shape[1] = shape3[1], shape3[2]
+    if inplane[0] == "dense":
+        _, k2d, c1, c2 = inplane
+        d._keep = np.ascontiguousarray(k2d.reshape(-1), dtype=like.dtype)
+        d.dense, d.coef = 1, d._keep.ctypes.data
+        d.ksize[0], d.ksize[1], d.center[0], d.center[1] = k2d.shape[0], k2d.shape[1], c1, c2
+    else:
+        _, t1, c1, t2, c2 = inplane
+        d.ksize[0], d.ksize[1], d.center[0], d.center[1] = t1.size, t2.size, c1, c2
+        for i, v in enumerate(t1):
+            d.coef1[i] = float(v)
+        for i, v in enumerate(t2):
+            d.coef2[i] = float(v)
+    d.alpha, d.beta = alpha * scale, beta
+    if add is not None:
+        d.add, d.add_period = add.ctypes.data, add.size
+    return d

@@ -61,3 +61,40 @@ def test_tiled_adjoint_identity_and_epilogue():
     xs = torch.randn(3, op.dim, device="cuda", dtype=torch.float64, generator=gen)
     out = op._run_tiled(xs, False, alpha=0.5, beta=-1.0, add=y)
     assert rel(out, 0.5 * op.apply(xs) - y) < 1e-13
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-5)])
+def test_pgd_two_pass_fista_equals_generic_path(dtype, tol):
+    """PGD on 1/2||A x - y||^2 + lam||x||_1 (batch of images): the two tiled passes per iteration (pxb_stencil2d_fista) against the
+    generic five-pass iteration, same iterates and same iteration count under the default RelError criterion."""
+    import pyxu_b200.operator as pxo
+    import pyxu_b200.opt.solver as pxs
+    import pyxu_b200.opt.stop as pxst
+
+    shape, batch = (96, 128), 4
+    N = shape[0] * shape[1]
+    rng = np.random.default_rng(0)
+    k = np.outer(gauss(5, 1.0), gauss(5, 1.2)).astype(dtype)
+    y = rng.random((batch, N)).astype(dtype)
+
+    def build():
+        A_ = pxo.Stencil(arg_shape=shape, kernel=k, center=(2, 2), mode="constant")
+        f = (0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y)) * A_
+        return pxs.PGD(f=f, g=0.02 * pxo.L1Norm(dim=N), show_progress=False, final_writeback=False), A_
+
+    outs = []
+    for fused in (True, False):
+        slv, A_ = build()
+        tau = 1.0 / float(A_.lipschitz) ** 2
+        if not fused:
+            A_._tiled_ok = False  # the whole operator on the generic gather kernels: no tiled descriptor, no fused step
+        slv.fit(x0=np.zeros((batch, N), dtype=dtype), tau=tau, stop_crit=pxst.MaxIter(40) | pxst.RelError(eps=1e-3, var="x"))
+        assert (slv._fused is not None) == fused
+        assert slv._astate.get("error") is None, slv._astate.get("error")
+        data, hist = slv.stats()
+        outs.append((np.asarray(data["x"], dtype=np.float64), hist))
+    (xa, ha), (xb, hb) = outs
+    assert len(ha) == len(hb) and len(ha) > 5
+    assert np.linalg.norm(xa - xb) / np.linalg.norm(xb) < tol
+    assert np.allclose(ha["RelError[x]_max"] if "RelError[x]_max" in ha.dtype.names else ha["RelError[x]"],
+                       hb["RelError[x]_max"] if "RelError[x]_max" in hb.dtype.names else hb["RelError[x]"], rtol=1e-3 if dtype == np.float32 else 1e-8)
