@@ -162,6 +162,14 @@ int pxb_prox_lincomb(int dtype, const pxb_prox_spec* g, double tau, int64_t n, v
 int pxb_lincomb(int dtype, int64_t n, void* out, double a, const void* x, double b, const void* y,
                 int64_t ny, double c, const void* z, int64_t nz, void* stream);
 
+/* The factor of a separable 3-D stencil along the SLOWEST axis ('constant' boundary) as one streaming pass:
+ *   out[q, :, :] = sum_j coef[j] * in[q + j - c0, :, :]      (coef: HOST array of k0 doubles)
+ * (reference: the axis-0 link of the chain stencil.py:497-538 builds for separable kernels).  Slab cuts: planes beyond an
+ * open side are read from the ghost planes (slab->halo >= the reach on that side).  Envelope: 2..9 taps, plane size a
+ * multiple of 4 (fp32) / 2 (fp64) samples, 16-byte aligned arrays; PXB_ENOSUP otherwise (use pxb_stencil_apply). */
+int pxb_stencil_axis0_apply(int dtype, int64_t batch, const int64_t* shape, const pxb_slab* slab, int k0, int c0,
+                            const double* coef, const void* in, void* out, void* stream);
+
 /* One accelerated proximal-gradient (FISTA) iteration on f = alpha_f*||A x + shift||^2, g pointwise, A such a stencil
  * (reference: src/pyxu/opt/solver/pgd.py:173-191), as TWO tiled passes instead of five:
  *   which == 0:  out = r = d.alpha * A((1+a) x - a x_prev) + d.beta * d.add      (d describes A; the extrapolated point

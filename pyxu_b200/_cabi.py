@@ -129,6 +129,7 @@ PROTOTYPES = {
     "pxb_stencil_adjoint": (_i, [_P(StencilDesc), _vp, _vp, _vp]),
     "pxb_stencil2d_apply": (_i, [_P(Stencil2D), _vp, _vp, _vp]),
     "pxb_stencil2d_fista": (_i, [_P(Stencil2D), _P(FistaStep), _i, _vp, _vp]),
+    "pxb_stencil_axis0_apply": (_i, [_i, _i64, _P(C.c_int64), _P(Slab), _i, _i, _P(C.c_double), _vp, _vp, _vp]),
     "pxb_gradient_apply": (_i, [_P(GradDesc), _vp, _vp, _vp]),
     "pxb_gradient_adjoint": (_i, [_P(GradDesc), _vp, _vp, _vp]),
     "pxb_prox_lincomb": (_i, [_i, _P(ProxSpec), _d, _i64, _vp, _d, _vp, _d, _vp, _i64, _d, _vp, _i64, _vp]),

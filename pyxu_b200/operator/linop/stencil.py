@@ -136,12 +136,14 @@ class Stencil(pxo.SquareOp):
         # A = P_last ... P_first  =>  A^T = P_first^T ... P_last^T
         return out[::-1] if adjoint else out
 
-    def _desc(self, k3, c3, batch, dtype_code, coef_ptr, slab=None):
+    def _desc(self, k3, c3, batch, dtype_code, coef_ptr, slab=None, shape0=None):
         D = len(self._arg_shape)
         d = K.StencilDesc()
         d.dtype = dtype_code
         d.batch = batch
         shape3 = (1,) * (3 - D) + self._arg_shape
+        if shape0 is not None:  # slab-decomposed axis 0: planes owned by this rank
+            shape3 = (int(shape0),) + shape3[1:]
         mode3 = ("constant",) * (3 - D) + self._mode
         for a in range(3):
             d.shape[a] = shape3[a]
@@ -237,6 +239,34 @@ class Stencil(pxo.SquareOp):
             d._keep = add
         return d, axis0
 
+    def _axis0_pass(self, axis0, cur, out, batch, slab=None, shape0=None):
+        """The factor along the slowest axis: streaming kernel (pxb_stencil_axis0_apply), generic gather kernel outside
+        its envelope.  `cur` / `out` address owned plane 0 (tensors or raw pointers)."""
+        k3, c3 = axis0
+        D = len(self._arg_shape)
+        shape3 = (1,) * (3 - D) + self._arg_shape
+        if shape0 is not None:
+            shape3 = (int(shape0),) + shape3[1:]
+        like = cur if hasattr(cur, "dtype") else out
+        dcode = A.dcode(like) if hasattr(like, "dtype") else self._slab_dcode
+        pin = A.ptr(cur) if hasattr(cur, "data_ptr") else cur
+        pout = A.ptr(out) if hasattr(out, "data_ptr") else out
+        k0 = int(k3.shape[0])
+        coef = (C.c_double * k0)(*[float(v) for v in k3.reshape(-1)])
+        rc = K.lib().pxb_stencil_axis0_apply(dcode, batch, (C.c_int64 * 3)(*shape3), C.byref(slab) if slab is not None else None, k0, int(c3[0]),
+                                             coef, pin, pout, A.stream())
+        if rc == -3:
+            key = ("axis0", k3.tobytes(), dcode)
+            dev = self._dev_coef.get(key)
+            if dev is None:
+                import torch
+
+                dev = torch.tensor(k3.reshape(-1), dtype=torch.float32 if dcode == K.F32 else torch.float64, device=A.current_device())
+                self._dev_coef[key] = dev
+            dd = self._desc(k3, c3, batch, dcode, dev.data_ptr(), slab=slab, shape0=shape0)
+            rc = K.lib().pxb_stencil_apply(C.byref(dd), pin, pout, A.stream())
+        K.check(rc, "Stencil (axis 0)")
+
     def _run_tiled(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
         """One pass over HBM for the in-plane part (+ one generic pass when there is a factor along axis 0).
         Returns None when the tiled kernel does not apply."""
@@ -246,12 +276,9 @@ class Stencil(pxo.SquareOp):
         d, axis0 = got
         batch = max(1, arr.numel() // self.dim)
         cur = arr
-        if axis0 is not None:  # the factor along the slowest axis keeps the generic kernel (one more pass)
-            k3, c3 = axis0
-            coef, _ = A.asdevice(np.ascontiguousarray(k3.reshape(-1)), dtype=arr.dtype)
-            dd = self._desc(k3, c3, batch, A.dcode(arr), coef.data_ptr())
+        if axis0 is not None:  # the factor along the slowest axis: one streaming pass of its own
             tmp = A.empty_like(arr)
-            K.check(K.lib().pxb_stencil_apply(C.byref(dd), A.ptr(cur), A.ptr(tmp), A.stream()), "Stencil")
+            self._axis0_pass(axis0, cur, tmp, batch)
             cur = tmp
         out = A.empty_like(arr)
         rc = K.lib().pxb_stencil2d_apply(C.byref(d), A.ptr(cur), A.ptr(out), A.stream())

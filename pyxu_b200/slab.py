@@ -402,3 +402,159 @@ class SlabPD3OTV:
         bufs = [torch.empty_like(mine) for _ in parts]
         dist.all_gather(bufs, mine, group=self.group)
         return torch.cat([b_[: e - a] for b_, (a, e) in zip(bufs, parts)], dim=0)
+
+
+class SlabCondatVuDeblur:
+    """CondatVu on  min 1/2||A x - y||^2 [+ i_+(x)] + lam*||grad x||_{2,1}  for a volume decomposed in z-slabs
+    (configs[4] of BASELINE.json: 3-D TV deblurring with a separable Stencil PSF).
+
+    A is a `constant`-mode separable Stencil (its factor along axis 0 reaches H planes across a cut), the Gradient is
+    the forward-difference stack.  One iteration on every rank (reference iteration: pds.py:429-442):
+        tmp = A_0 x          (axis-0 streaming pass; reads H ghost planes of x)
+        r   = A_12 tmp - y   (tiled in-plane pass, epilogue carries -y)                  -> r ghosts exchanged (H planes)
+        tmp = A_0^T r ;  grad f = A_12^T tmp                                              -> first plane of grad f goes down
+        (x, z) <- pxb_pds_iter(CV, grad f array)   (single kernel, ping-pong)             -> x ghosts (H planes), z planes
+    Exchanges are NCCL send/recv batches on a high-priority stream.
+    """
+
+    def __init__(self, shape, psf, center, y_full=None, y_local=None, lam=0.05, positivity=True, dtype=torch.float32, rho=1.0,
+                 tau=None, sigma=None, group=None):
+        import numpy as np
+
+        from .operator.linop.diff import Gradient
+        from .operator.linop.stencil import Stencil
+
+        A.require_cuda()
+        assert len(shape) == 3 and len(psf) == 3, "3-D volume and a separable PSF (one 1-D factor per axis)"
+        self.shape = tuple(int(s) for s in shape)
+        self.group = group if group is not None else _high_priority_group()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.dev, self.dtype = A.current_device(), dtype
+        npdt = A.np_dtype(dtype)
+        self.Aop = Stencil(arg_shape=self.shape, kernel=[np.asarray(k, dtype=npdt) for k in psf], center=tuple(center), mode="constant")
+        self.K = Gradient(arg_shape=self.shape, dtype=npdt)
+        self.hx = HaloExchanger(self.rank, self.world, self.group)
+        self.start, self.stop = partition(self.shape[0], self.world)[self.rank]
+        self.n0 = n0 = self.stop - self.start
+        n1, n2 = self.shape[1:]
+        self.plane = n1 * n2
+        self.local_voxels = n0 * self.plane
+        k0, c0 = len(psf[0]), int(center[0])
+        self.H = H = max(1, c0, k0 - 1 - c0)
+        assert n0 >= H, "slabs thinner than the PSF's reach along z are not supported"
+        alloc = n0 + 2 * H
+
+        def field(ncomp=1):
+            return torch.zeros((ncomp, alloc, n1, n2), dtype=dtype, device=self.dev)
+
+        self._xb, self._zb, self.cur = [field(), field()], [field(3), field(3)], 0
+        self.r, self.garr, self.tmp = field(), field(), field()
+        if y_local is None:
+            y_local = y_full.reshape(self.shape)[self.start : self.stop]
+        self.neg_y = (-y_local).to(dtype).contiguous()
+        own = slice(H, H + n0)
+        self._xb[0][0, own].copy_(y_local)
+        # step sizes: CondatVu defaults (reference: pds.py:444-517) with beta = ||A||^2, gamma = beta
+        beta = float(self.Aop.lipschitz) ** 2
+        L = float(self.K.lipschitz)
+        t = (1.0 / L**2) * ((-beta / 2) + math.sqrt((beta**2 / 4) + L**2))
+        self.tau = t if tau is None else tau
+        self.sigma = t if sigma is None else sigma
+        self.rho, self.lam, self.positivity = rho, lam, positivity
+        self.comm = torch.cuda.Stream(device=self.dev, priority=-1)
+        self.Aop._slab_dcode = A.dcode(self.r)
+        self._plans = {adj: self.Aop._tiled_plan(adj) for adj in (False, True)}
+        assert all(p is not None and p[0] is not None for p in self._plans.values()), "expected a separable PSF with a factor along axis 0"
+        self._slab = K.Slab(1 if self.hx.lo is not None else 0, 1 if self.hx.hi is not None else 0, H, alloc)
+        self._desc2d = {}
+        for adj, add in ((False, self.neg_y), (True, None)):
+            d, _ = self.Aop._tiled_desc(self.r[0, own], adj, alpha=1.0, beta=1.0 if add is not None else 0.0, add=add)
+            d.nimg = n0
+            self._desc2d[adj] = d
+        self._gdesc = self.K._desc(1, A.dcode(self.r), slab=self._slab, shape0=n0)
+        # z0 = K x0 needs x0's ghost planes
+        self._wait(self._exchange([(self._xb[0][0], H, H)]))
+        K.check(K.lib().pxb_gradient_apply(C.byref(self._gdesc), self._p(self._xb[0], 0), self._p(self._zb[0], 0), A.stream()), "gradient_apply")
+        self._wait(self._exchange([(self._zb[0][0], 1, 1), (self._zb[0][1], 0, 1), (self._zb[0][2], 0, 1)]))
+        torch.cuda.synchronize()
+
+    @property
+    def x(self):
+        return self._xb[self.cur]
+
+    @property
+    def z(self):
+        return self._zb[self.cur]
+
+    @staticmethod
+    def _wait(reqs):
+        for r in reqs:
+            r.wait()
+
+    def _p(self, t, comp, plane=0):
+        return C.c_void_p(t.data_ptr() + t.element_size() * ((comp * t.shape[1] + self.H + plane) * self.plane))
+
+    def _exchange(self, items):
+        """items: [(buf of shape (alloc, n1, n2), planes going up, planes going down)] -- my last `up` owned planes fill
+        the upper neighbour's ghost planes next to its first owned plane, my first `down` owned planes the lower
+        neighbour's ghost planes next to its last owned plane."""
+        H, n0, ops = self.H, self.n0, []
+        for buf, up, down in items:
+            if up:
+                if self.hx.hi is not None:
+                    ops.append(dist.P2POp(dist.isend, buf[H + n0 - up : H + n0], self.hx.hi, self.group))
+                if self.hx.lo is not None:
+                    ops.append(dist.P2POp(dist.irecv, buf[H - up : H], self.hx.lo, self.group))
+            if down:
+                if self.hx.lo is not None:
+                    ops.append(dist.P2POp(dist.isend, buf[H : H + down], self.hx.lo, self.group))
+                if self.hx.hi is not None:
+                    ops.append(dist.P2POp(dist.irecv, buf[H + n0 : H + n0 + down], self.hx.hi, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def _stencil(self, adjoint, src, dst):
+        """dst(owned planes) = A src (or A^T src): axis-0 streaming pass (reads src's ghost planes) + tiled in-plane pass."""
+        axis0 = self._plans[adjoint][0]
+        self.Aop._axis0_pass(axis0, self._p(src, 0), self._p(self.tmp, 0), 1, slab=self._slab, shape0=self.n0)
+        rc = K.lib().pxb_stencil2d_apply(C.byref(self._desc2d[adjoint]), self._p(self.tmp, 0), self._p(dst, 0), A.stream())
+        K.check(rc, "pxb_stencil2d_apply")
+
+    def step(self, want_norms=False):
+        H, n0 = self.H, self.n0
+        src, dst = self.cur, 1 - self.cur
+        xs, zs, xd, zd = self._xb[src], self._zb[src], self._xb[dst], self._zb[dst]
+        nrm = nx = nz = None
+        if want_norms:
+            nrm = torch.zeros((2, 1, 2), dtype=torch.float64, device=self.dev)
+            nx, nz = nrm[0], nrm[1]
+        self._stencil(False, xs, self.r)                                   # r = A x - y
+        self._wait(self._exchange([(self.r[0], H, H)]))
+        self._stencil(True, self.r, self.garr)                             # grad f = A^T r
+        self._wait(self._exchange([(self.garr[0], 0, 1)]))
+        p = K.PdsParams()
+        p.tau, p.sigma, p.rho = self.tau, self.sigma, self.rho
+        p.g = K.ProxSpec(K.PROX_POS if self.positivity else K.PROX_NONE, 0, 0.0, 0.0)
+        f = K.FTerm()
+        f.kind, f.garr = K.F_GRADARR, self._p(self.garr, 0).value
+        p.f = f
+        p.hkind, p.lam = K.DUAL_L21, self.lam
+        rc = K.lib().pxb_pds_iter(K.ALGO_CV, C.byref(self._gdesc), C.byref(p), self._p(xs, 0), self._p(zs, 0), self._p(xd, 0), self._p(zd, 0),
+                                  None, A.ptr(nx), A.ptr(nz), A.stream())
+        K.check(rc, "pxb_pds_iter")
+        self._wait(self._exchange([(xd[0], H, H), (zd[0], 1, 1), (zd[1], 0, 1), (zd[2], 0, 1)]))
+        self.cur = dst
+        if want_norms:
+            v = nrm.reshape(-1)
+            dist.all_reduce(v, group=self.group)
+            return v.cpu().numpy()
+        return None
+
+    def gather_x(self):
+        H = self.H
+        parts = partition(self.shape[0], self.world)
+        nmax = max(b - a for a, b in parts)
+        mine = torch.zeros((nmax, *self.shape[1:]), dtype=self.dtype, device=self.dev)
+        mine[: self.n0].copy_(self.x[0, H : H + self.n0])
+        bufs = [torch.empty_like(mine) for _ in parts]
+        dist.all_gather(bufs, mine, group=self.group)
+        return torch.cat([b_[: e - a] for b_, (a, e) in zip(bufs, parts)], dim=0)

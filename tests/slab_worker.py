@@ -54,6 +54,43 @@ def main():
         if rank == 0:
             print(f"[slab] world={world} shape={shape} mode={mode} overlap={slab.overlap} {dtype}: rel.err={err:.2e} "
                   f"relerr-norms dev=({e_rx:.1e},{e_rz:.1e}) {'OK' if good else 'FAIL'}", flush=True)
+    # ---- CondatVu TV deblurring with a separable 3-D PSF (configs[4] in miniature) -------------------------------
+    from pyxu_b200.slab import SlabCondatVuDeblur
+
+    def gauss(n, s):
+        t_ = np.arange(n) - (n - 1) / 2
+        k = np.exp(-0.5 * (t_ / s) ** 2)
+        return k / k.sum()
+
+    for shape, psf, cen, dtype, tol in [((41, 24, 32), [gauss(7, 1.2), gauss(5, 1.0), gauss(7, 1.5)], (3, 2, 3), torch.float64, 1e-12),
+                                        ((48, 40, 64), [gauss(7, 1.2), gauss(7, 1.2), gauss(7, 1.2)], (3, 3, 3), torch.float32, 2e-5)]:
+        n_iter, lam = 15, 0.05
+        npdt = np.float64 if dtype == torch.float64 else np.float32
+        gen = torch.Generator(device="cuda").manual_seed(11)
+        y = torch.rand(shape, device="cuda", dtype=dtype, generator=gen)
+        slab = SlabCondatVuDeblur(shape, psf, cen, y_full=y, lam=lam, positivity=True, dtype=dtype, rho=0.9)
+        v = None
+        for i in range(n_iter):
+            v = slab.step(want_norms=(i == n_iter - 1))
+        x_slab = slab.gather_x().reshape(-1)
+        N = int(np.prod(shape))
+        Aop = pxo.Stencil(arg_shape=shape, kernel=[np.asarray(k, dtype=npdt) for k in psf], center=cen, mode="constant")
+        f = (0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y.reshape(-1))) * Aop
+        Kop = pxo.Gradient(arg_shape=shape, dtype=npdt)
+        h = lam * pxo.L21Norm(arg_shape=(3, *shape), l2_axis=(0,))
+        slv = pxs.CondatVu(f=f, g=pxo.PositiveOrthant(dim=N), h=h, K=Kop, beta=float(Aop.lipschitz) ** 2, show_progress=False, final_writeback=False)
+        sc = pxst.MaxIter(n_iter) | pxst.RelError(eps=1e-30, var="x") | pxst.RelError(eps=1e-30, var="z")
+        slv.fit(x0=y.reshape(-1), stop_crit=sc, tau=slab.tau, sigma=slab.sigma, rho=0.9)
+        assert slv._astate.get("error") is None, slv._astate.get("error")
+        x_ref = slv._mstate["x"]
+        err = float((x_slab - x_ref).norm() / x_ref.norm())
+        _, hist = slv.stats()
+        rx = float(np.sqrt(v[0]) / np.sqrt(v[1]))
+        e_rx = abs(rx - float(hist[-1]["RelError[x]"])) / max(rx, 1e-300)
+        good = err < tol and e_rx < 1e-5
+        ok &= good
+        if rank == 0:
+            print(f"[slab-deblur] world={world} shape={shape} {dtype}: rel.err={err:.2e} relerr-norm dev={e_rx:.1e} {'OK' if good else 'FAIL'}", flush=True)
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

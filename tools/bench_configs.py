@@ -97,9 +97,9 @@ def main():
         slv = pxs.PGD(f=f, g=g, show_progress=False)
         slv.fit(x0=y, mode=Mode.MANUAL, stop_crit=pxst.ManualStop(), tau=1.0 / float(A.lipschitz) ** 2)
         ms, launches = timed(slv.m_step, K, W, world)
-        assert A._tiled_ok is True
+        assert slv._fused is not None, "the two-pass tiled FISTA form did not apply"
         nvox, name = args.batch * N, f"batch of {args.batch} {n}x{n} images, PGD (FISTA) L1 deconvolution, dense 5x5 Stencil, batch split over {world} GPU(s)"
-        bpv = getattr(slv, "_bytes_per_voxel", 12 + 12 + 8 + 12)
+        bpv = 16 + 16  # r = A y - b: read x, x_prev, b, write r;  x_new = prox(y - tau A^T r): read r, x, x_prev, write x_new
     if rank == 0:
         per = ms / K
         print(json.dumps({"workload": name, "n_gpus": world, "ms_per_iter": per, "gvoxel_iter_per_s": nvox / per / 1e6,
