@@ -5,6 +5,7 @@ Secondary workloads of BASELINE.json (configs[1], configs[2]) through the public
 
     python tools/bench_configs.py --workload deblur2d [--size 8192] [--steps 20]
     python tools/bench_configs.py --workload fista   [--batch 256] [--size 1024]     (torchrun: the batch is dealt out to the ranks)
+    torchrun ... tools/bench_configs.py --workload deblur3d [--shape 2048,2048,1024]  (z-slabs over the ranks)
 """
 import argparse
 import json
@@ -54,12 +55,13 @@ def timed(step, K, W, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["deblur2d", "fista"])
+    ap.add_argument("--workload", required=True, choices=["deblur2d", "fista", "deblur3d"])
     ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--dense", action="store_true", help="dense instead of separable blur kernel")
+    ap.add_argument("--shape", default="2048,2048,1024")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -84,6 +86,19 @@ def main():
         assert slv._plan.iter_ok is True and A._tiled_ok is True
         nvox, name = N, f"2-D TV deblurring {n}x{n} fp32, CondatVu, {'dense' if args.dense else 'separable'} 9x9 Gaussian Stencil blur + L21 o Gradient"
         bpv = 12 + 8 + 28  # A x - y (read x, y; write r) + A^T r + single-kernel CV iteration (read x, grad f, z0, z1; write x, z0, z1)
+    elif args.workload == "deblur3d":
+        from pyxu_b200.slab import SlabCondatVuDeblur, partition
+
+        shape = tuple(int(v) for v in args.shape.split(","))
+        a, b = partition(shape[0], world)[rank]
+        y_local = torch.rand((b - a, *shape[1:]), device="cuda", generator=gen)
+        g7 = gauss(7, 1.2)
+        slab = SlabCondatVuDeblur(shape, [g7, g7, g7], (3, 3, 3), y_local=y_local, lam=0.05, positivity=True, dtype=torch.float32)
+        del y_local
+        ms, launches = timed(slab.step, K, W, world)
+        nvox = int(np.prod(shape))
+        name = f"3-D TV deblurring {'x'.join(map(str, shape))} fp32, CondatVu, separable 7x7x7 Stencil PSF + positivity + L21 o Gradient, {world} z-slab(s)"
+        bpv = 8 + 12 + 8 + 8 + 36  # A_0 x | A_12 . - y | A_0^T r | A_12^T . | single-kernel CV iteration with grad f array
     else:
         n = args.size or 1024
         shape, N = (n, n), n * n
