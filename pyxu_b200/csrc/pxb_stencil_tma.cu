@@ -51,9 +51,13 @@ __global__ void __launch_bounds__(256) k_stencil2d_tma(const __grid_constant__ P
     const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
     T acc[C::R][VEC];
     if (!DENSE) {
-        for (int it = tid; it < p.bh * C::TXL; it += C::NT) pxb_st2_row_item<T, VEC, NV>(p, box, mid, it >> 5, (it & 31) * VEC);
+        __shared__ T c1s[PXB_ST2_MAXTAP];
+        if (tid < PXB_ST2_MAXTAP) c1s[tid] = T(p.coef1[tid]);
+        T c2[NV * VEC - VEC + 1];
+        for (int q = 0; q < NV * VEC - VEC + 1; ++q) c2[q] = T(p.coef2[q]);
+        for (int it = tid; it < p.bh * C::TXL; it += C::NT) pxb_st2_row_item<T, VEC, NV>(p, box, mid, it >> 5, (it & 31) * VEC, c2);
         __syncthreads();
-        pxb_st2_col_item<T, VEC>(p, mid, yl, xl, acc);
+        pxb_st2_col_item<T, VEC>(p, mid, yl, xl, c1s, acc);
     } else {
         __syncthreads();
         pxb_st2_dense_item<T, VEC, NV>(p, box, mid, yl, xl, acc);

@@ -49,8 +49,10 @@ struct PxbSt2Cfg {
 };
 
 // row pass for one vector item: t[y][x..x+VEC) = sum_q c2[q] * in[y][x + q ...]; NV vectors cover the window
+// (coefficients arrive as T: converting the by-value doubles inside the tap loops cost an F2F per tap -- the first
+// version issued 67 instructions per voxel and was issue-bound at 82 %)
 template <class T, int VEC, int NV>
-PXB_HD void pxb_st2_row_item(const PxbSt2P& p, const T* __restrict__ box, T* __restrict__ mid, int y, int xl) {
+PXB_HD void pxb_st2_row_item(const PxbSt2P& p, const T* __restrict__ box, T* __restrict__ mid, int y, int xl, const T* c2) {
     using C = PxbSt2Cfg<T, VEC>;
     T v[NV * VEC];
     const T* __restrict__ src = box + y * p.bw + xl;
@@ -62,7 +64,7 @@ PXB_HD void pxb_st2_row_item(const PxbSt2P& p, const T* __restrict__ box, T* __r
     for (int j = 0; j < VEC; ++j) acc.v[j] = T(0);
     for (int q = 0; q < NV * VEC - VEC + 1; ++q) {
         if (q < p.k2) {
-            const T c = T(p.coef2[q]);
+            const T c = c2[q];
             for (int j = 0; j < VEC; ++j) acc.v[j] += c * v[q + j];
         }
     }
@@ -71,7 +73,7 @@ PXB_HD void pxb_st2_row_item(const PxbSt2P& p, const T* __restrict__ box, T* __r
 
 // column pass + epilogue for one thread: R adjacent rows x VEC columns
 template <class T, int VEC>
-PXB_HD void pxb_st2_col_item(const PxbSt2P& p, const T* __restrict__ mid, int yl, int xl, T (*acc)[VEC]) {
+PXB_HD void pxb_st2_col_item(const PxbSt2P& p, const T* __restrict__ mid, int yl, int xl, const T* __restrict__ c1, T (*acc)[VEC]) {
     using C = PxbSt2Cfg<T, VEC>;
     for (int r = 0; r < C::R; ++r)
         for (int j = 0; j < VEC; ++j) acc[r][j] = T(0);
@@ -80,7 +82,7 @@ PXB_HD void pxb_st2_col_item(const PxbSt2P& p, const T* __restrict__ mid, int yl
         for (int r = 0; r < C::R; ++r) {
             const int q = i - r;
             if (q >= 0 && q < p.k1) {
-                const T c = T(p.coef1[q]);
+                const T c = c1[q];
                 for (int j = 0; j < VEC; ++j) acc[r][j] += c * t.v[j];
             }
         }

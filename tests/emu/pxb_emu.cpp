@@ -278,13 +278,15 @@ static void t_st2_nv(const PxbSt2P& p, const T* in, const T* in2, T* out) {
                     for (int it = 0; it < p.bh * p.bw / VEC; ++it) pxb_st2_combine_item<T, VEC>(p, box.data(), box2.data(), it);
                 if (p.dense)
                     for (int i = 0; i < p.k1 * p.k2; ++i) mid[i] = pxb_st2_dense_coef<T>(p, (const T*)p.coef, i);
-                else
-                    for (int it = 0; it < p.bh * C::TXL; ++it) pxb_st2_row_item<T, VEC, NV>(p, box.data(), mid.data(), it / C::TXL, (it % C::TXL) * VEC);
+                T c1[PXB_ST2_MAXTAP], c2[PXB_ST2_MAXTAP];
+                for (int q = 0; q < PXB_ST2_MAXTAP; ++q) { c1[q] = T(p.coef1[q]); c2[q] = T(p.coef2[q]); }
+                if (!p.dense)
+                    for (int it = 0; it < p.bh * C::TXL; ++it) pxb_st2_row_item<T, VEC, NV>(p, box.data(), mid.data(), it / C::TXL, (it % C::TXL) * VEC, c2);
                 for (int tid = 0; tid < C::NT; ++tid) {
                     const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
                     T acc[C::R][VEC];
                     if (p.dense) pxb_st2_dense_item<T, VEC, NV>(p, box.data(), mid.data(), yl, xl, acc);
-                    else pxb_st2_col_item<T, VEC>(p, mid.data(), yl, xl, acc);
+                    else pxb_st2_col_item<T, VEC>(p, mid.data(), yl, xl, c1, acc);
                     if (p.epi == 1) {
                         double nrm[2] = {0.0, 0.0};
                         pxb_st2_store_prox<T, VEC>(p, out, img, y0, x0, yl, xl, acc, nrm);
