@@ -143,8 +143,17 @@ int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p
             return 0;
         }
         if (pxb_iter_path() == 2) return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: TMA form not applicable (reason %d)", why);
+    } else if (K->ndir == 2 && pxb_iter_path() != 1 && chunk_hint == 0) {
+        // 2-D images: TMA-staged tiles (pxb_tv_tile2d.cu); the marching direct-load form remains the fallback
+        why = pxb_tv_tile2d_try(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, s, &err);
+        if (why == 0) {
+            pxb_count_launch();
+            if (err != cudaSuccess) return pxb_fail(PXB_ECUDA, "pxb_pds_iter (tile2d): %s", cudaGetErrorString(err));
+            return 0;
+        }
+        if (pxb_iter_path() == 2) return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: TMA form not applicable (reason %d)", why);
     } else if (pxb_iter_path() == 2) {
-        return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: TMA form is 3-D only");
+        return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: TMA form not applicable");
     }
     if (K->dtype == PXB_F32) {
         PxbIterPtr<float> a{(const float*)xu_in, (const float*)z_in, (float*)xu_out, (float*)z_out, (float*)x_out, norms_x, norms_z};

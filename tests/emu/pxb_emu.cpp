@@ -12,6 +12,7 @@
 #include "../../pyxu_b200/csrc/pxb_tv_iter.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_tma.cuh"
 #include "../../pyxu_b200/csrc/pxb_stencil_tma.cuh"
+#include "../../pyxu_b200/csrc/pxb_tv_tile2d.cuh"
 #include <vector>
 
 #define FOR_VOX(batch, g)                              \
@@ -336,7 +337,75 @@ static int t_st2(const pxb_stencil2d* d, const pxb_fista_step* f, int which, con
     return 0;
 }
 
+// TMA-tiled 2-D iteration (pxb_tv_tile2d.cuh): boxes gathered with zero fill, then phase A / phase C per thread.
+template <class T>
+static void emu_box3(const T* base, const int64_t dim[3], int64_t s1, int64_t s2, int bw, int rows, int c0, int c1, int64_t c2, T* dst) {
+    for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < bw; ++j) {
+            const int64_t x = (int64_t)c0 + j, y = (int64_t)c1 + i;
+            const bool in = x >= 0 && x < dim[0] && y >= 0 && y < dim[1] && c2 >= 0 && c2 < dim[2];
+            dst[i * bw + j] = in ? base[x + y * s1 + c2 * s2] : T(0);
+        }
+}
+template <class T, int ALGO, bool NORMS, class S>
+static int t_t2_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, bool want_fwd) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    using C = PxbT2Cfg<T, VEC>;
+    PxbTvCoef cf;
+    PxbTvP<T> q;
+    PxbT2Geom g;
+    if (int why = pxb_t2_setup<T, VEC>(*K, *p, cf, q, g)) return -100 - why;
+    bool fwd = true;
+    for (int k = 0; k < 2; ++k) fwd = fwd && cf.cm[k] == 0.0 && cf.cp[k] != 0.0;
+    if ((fwd && q.hkind == PXB_DUAL_L21) != want_fwd) return -130;
+    std::vector<T> sm(C::TOTAL);
+    const int64_t du[3] = {g.n2, g.n1, g.nimg}, dz[3] = {g.n2, g.n1, g.nimg * 2}, ds[3] = {g.n2, g.n1, g.sh_mode ? g.n0 : g.nimg};
+    const T* sptr = q.fkind == PXB_F_GRADARR ? q.garr : q.shift;
+    for (int64_t blk = 0; blk < g.nblocks; ++blk) {
+        const PxbT2Item it = pxb_t2_item(g, blk, C::TY, C::T2);
+        for (auto& v : sm) v = T(4321);
+        const int cc = it.c0 - VEC, cr = it.r0 - 1;
+        emu_box3<T>(a.u_in, du, g.n2, g.s0, C::BW, C::BR, cc, cr, it.img, sm.data() + C::OFF_U);
+        if (g.has_shift) emu_box3<T>(sptr, ds, g.n2, g.s0, C::BW, C::BR, cc, cr, g.sh_mode ? it.i0 : it.img, sm.data() + C::OFF_S);
+        const int64_t pz = it.b * 2 * g.n0 + it.i0;
+        emu_box3<T>(a.z_in, dz, g.n2, g.s0, C::BW, C::BRZ, cc, cr - 1, pz, sm.data() + C::OFF_ZR);
+        emu_box3<T>(a.z_in, dz, g.n2, g.s0, C::BW, C::BR, cc, cr, pz + g.n0, sm.data() + C::OFF_ZC);
+        double acc[4] = {0, 0, 0, 0};
+        for (int tid = 0; tid < C::NT; ++tid) pxb_t2_phaseA<T, VEC, ALGO, NORMS, S>(q, g, it, a, tid, sm.data(), acc);
+        for (int tid = 0; tid < C::NT; ++tid) pxb_t2_phaseC<T, VEC, NORMS, S>(q, g, it, a, tid, sm.data(), acc);
+        if (NORMS) {
+            if (a.norms_x) { a.norms_x[2 * it.b] += acc[0]; a.norms_x[2 * it.b + 1] += acc[1]; }
+            if (a.norms_z) { a.norms_z[2 * it.b] += acc[2]; a.norms_z[2 * it.b + 1] += acc[3]; }
+        }
+    }
+    return 0;
+}
+template <class T>
+static int t_t2(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
+                void* x_out, double* nx, double* nz) {
+    if (K->ndir != 2) return -102;
+    PxbIterPtr<T> a{(const T*)u_in, (const T*)z_in, (T*)u_out, (T*)z_out, (T*)x_out, nx, nz};
+    const bool norms = nx || nz;
+    using SF = PxbSpec<PXB_SCHEME_FWD, -1, PXB_DUAL_L21, -1>;
+#define EMU_T2_TRY(S, fw)                                                                                             \
+    {                                                                                                                 \
+        int rc = algo == PXB_PD3O ? (norms ? t_t2_run<T, PXB_PD3O, true, S>(K, p, a, fw) : t_t2_run<T, PXB_PD3O, false, S>(K, p, a, fw)) \
+                                  : (norms ? t_t2_run<T, PXB_CV, true, S>(K, p, a, fw) : t_t2_run<T, PXB_CV, false, S>(K, p, a, fw));       \
+        if (rc != -130) return rc;                                                                                    \
+    }
+    EMU_T2_TRY(SF, true)
+    EMU_T2_TRY(PxbSpecAny, false)
+#undef EMU_T2_TRY
+    return -131;
+}
+
 extern "C" {
+int emu_tv_tile2d(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
+                  void* x_out, double* nx, double* nz, int unused) {
+    (void)unused;
+    if (K->dtype == PXB_F32) return t_t2<float>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz);
+    return t_t2<double>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz);
+}
 int emu_stencil2d(const pxb_stencil2d* d, const void* in, void* out) {
     return d->dtype == PXB_F32 ? t_st2<float>(d, nullptr, 0, in, out) : t_st2<double>(d, nullptr, 0, in, out);
 }

@@ -29,7 +29,7 @@ def two_pass(algo, d, P, u, z, x, nx=None, nz=None):
 
 def one_pass(algo, d, P, u, z, x, nx=None, nz=None, chunk=0, form="direct"):
     u2, z2 = np.full_like(u, np.nan), np.full_like(z, np.nan)
-    fn = E.lib().emu_tv_iter if form == "direct" else E.lib().emu_tv_iter_tma
+    fn = {"direct": E.lib().emu_tv_iter, "tma": E.lib().emu_tv_iter_tma, "tile2d": E.lib().emu_tv_tile2d}[form]
     rc = fn(algo, C.byref(d), C.byref(P), E.p(u), E.p(z), E.p(u2), E.p(z2), E.p(x) if algo == K.ALGO_PD3O else None,
                              E.p(nx), E.p(nz), chunk)
     assert rc == 0, rc
@@ -71,7 +71,8 @@ def test_iter_equals_two_pass_3d(scheme, algo, dtype, form):
 
 @pytest.mark.parametrize("scheme", SCHEMES)
 @pytest.mark.parametrize("width", [40, 300, 1100])
-def test_iter_equals_two_pass_2d_batched(scheme, width):
+@pytest.mark.parametrize("form", ["direct", "tile2d"])
+def test_iter_equals_two_pass_2d_batched(scheme, width, form):
     """2-D images (marching along the rows), a batch of them, narrow and wide tile variants."""
     rng = np.random.default_rng(7)
     shape, batch = (13, width), 3
@@ -88,7 +89,7 @@ def test_iter_equals_two_pass_2d_batched(scheme, width):
             nxa, nza, nxb, nzb = (np.zeros(2 * batch) for _ in range(4))
             two_pass(algo, d, P, ua, za, xa, nxa, nza)
             xb = x.copy()
-            ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=chunk)
+            ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=chunk, form=form)
             assert relerr(ub, ua) < 2e-6 and relerr(zb, za) < 2e-6
             assert np.allclose(nxa, nxb, rtol=1e-5) and np.allclose(nza, nzb, rtol=1e-5)
 
@@ -105,6 +106,8 @@ def test_iter_cv_gradarr_and_stacked_2d():
     ua, za = u.copy(), z.copy()
     two_pass(K.ALGO_CV, d, P, ua, za, None)
     ub, zb = one_pass(K.ALGO_CV, d, P, u, z, None, chunk=5)
+    assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13
+    ub, zb = one_pass(K.ALGO_CV, d, P, u, z, None, form="tile2d")
     assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13
 
 
@@ -212,3 +215,41 @@ def test_tma_form_golden_3d():
     for _ in range(50):
         u, z = one_pass(K.ALGO_PD3O, d, P, u, z, x, form="tma")
     assert relerr(x, g["pd3o_tv3d/x"]) < 1e-10 and relerr(z, g["pd3o_tv3d/z"]) < 1e-10
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_tile2d_form_fp64_shift_modes_and_golden(scheme):
+    """TMA-tiled 2-D form: per-item / broadcast / scalar shifts, L1 and L21 duals, PD3O and CondatVu; then the reference's fixture."""
+    rng = np.random.default_rng(13)
+    shape, batch = (37, 70), 2
+    Kop = pxo.Gradient(arg_shape=shape, scheme=scheme, sampling=(0.5, 2.0))
+    d = Kop._desc(batch, K.F64)
+    u, x = rng.standard_normal((batch, Kop.dim)), rng.standard_normal((batch, Kop.dim))
+    z = rng.standard_normal((batch, Kop.codim))
+    for shift in (rng.standard_normal(Kop.dim), rng.standard_normal((batch, Kop.dim)), np.r_[0.3]):
+        for hkind, gspec in ((K.DUAL_L21, (K.PROX_POS, 0.0, 0.0)), (K.DUAL_L1, (K.PROX_BOX, -0.2, 0.9))):
+            P = E.pds_params(0.21, 0.19, 0.9, gspec=gspec, fkind=K.F_SQL2, alpha=0.7, shift=shift, hkind=hkind, lam=0.3)
+            for algo in (K.ALGO_PD3O, K.ALGO_CV):
+                ua, za, xa = u.copy(), z.copy(), x.copy()
+                nxa, nza, nxb, nzb = (np.zeros(2 * batch) for _ in range(4))
+                two_pass(algo, d, P, ua, za, xa, nxa, nza)
+                xb = x.copy()
+                ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, form="tile2d")
+                assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13, (scheme, algo, shift.shape)
+                if algo == K.ALGO_PD3O:
+                    assert relerr(xb, xa) < 1e-13
+                assert np.allclose(nxa, nxb, rtol=1e-10) and np.allclose(nza, nzb, rtol=1e-10)
+    if scheme == "forward":
+        g = golden("solvers.npz")
+        y = g["pd3o_tv2d/y"]
+        tau, sigma, rho = (float(g[f"pd3o_tv2d/s1/{k}"]) for k in ("tau", "sigma", "rho"))
+        Kop = pxo.Gradient(arg_shape=(32, 40))
+        shift = np.ascontiguousarray(-y.reshape(-1))  # (kept alive: the parameter block only holds its address)
+        P = E.pds_params(tau, sigma, rho, gspec=POS, fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L21, lam=0.1)
+        d = Kop._desc(1, K.F64)
+        x = y.reshape(-1).copy()
+        z = E.gradient_run(Kop, x, False)
+        u = x.copy()
+        for _ in range(60):
+            u, z = one_pass(K.ALGO_PD3O, d, P, u, z, x, form="tile2d")
+        assert relerr(x, g["pd3o_tv2d/s1/x"]) < 1e-10 and relerr(z, g["pd3o_tv2d/s1/z"]) < 1e-10

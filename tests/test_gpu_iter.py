@@ -116,24 +116,33 @@ def test_iter_vs_two_sweeps_3d(env, scheme, dtype, form, iter_path):
 
 @pytest.mark.parametrize("scheme", ["forward", "backward", "central"])
 @pytest.mark.parametrize("width", [40, 300, 1100])
-def test_iter_vs_two_sweeps_2d_batched(env, scheme, width):
+@pytest.mark.parametrize("form", ["direct", "tma"])
+def test_iter_vs_two_sweeps_2d_batched(env, scheme, width, form, iter_path):
     K = env.K
+    iter_path(1 if form == "direct" else 2)  # 2: TMA-staged 2-D tiles (pxb_tv_tile2d.cu)
     Kop = env.operator.Gradient(arg_shape=(37, width), scheme=scheme, dtype=np.float32)
     shift = torch.randn(Kop.dim, device="cuda", dtype=torch.float32)  # one image: broadcast over the batch
     P = params(K, 0.3, 0.25, 1.0, (K.PROX_L1, 0.05, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L21, 0.2)
     for algo in (K.ALGO_PD3O, K.ALGO_CV):
-        for chunk in (0, 4):
+        for chunk in ((0, 4) if form == "direct" else (0,)):
             a, b = both_forms(env, algo, Kop, 5, torch.float32, P, seed=width + chunk, chunk=chunk)
             assert_same(env, algo, a, b, 2e-6)
 
 
-def test_iter_cv_gradarr_stacked(env):
+@pytest.mark.parametrize("form", ["direct", "tma"])
+def test_iter_cv_gradarr_stacked(env, form, iter_path):
     K = env.K
+    iter_path(1 if form == "direct" else 2)
     Kop = env.operator.Gradient(arg_shape=(3, 33, 24), directions=(1, 2))
     garr = torch.randn(2, Kop.dim, device="cuda", dtype=torch.float64)
     P = params(K, 0.3, 0.25, 0.8, (K.PROX_POS, 0.0, 0.0), K.F_GRADARR, 0.0, None, garr, K.DUAL_L21, 0.2)
-    a, b = both_forms(env, K.ALGO_CV, Kop, 2, torch.float64, P, chunk=7)
+    a, b = both_forms(env, K.ALGO_CV, Kop, 2, torch.float64, P, chunk=7 if form == "direct" else 0)
     assert_same(env, K.ALGO_CV, a, b, 1e-13)
+    # a volume-shaped shift broadcast over the batch (PD3O), fp64
+    shift = torch.randn(Kop.dim, device="cuda", dtype=torch.float64)
+    P = params(K, 0.3, 0.25, 0.8, (K.PROX_POS, 0.0, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L1, 0.2)
+    a, b = both_forms(env, K.ALGO_PD3O, Kop, 2, torch.float64, P)
+    assert_same(env, K.ALGO_PD3O, a, b, 1e-13)
 
 
 def test_iter_envelope_errors(env):
