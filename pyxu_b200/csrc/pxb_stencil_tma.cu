@@ -51,8 +51,11 @@ __global__ void __launch_bounds__(256) k_stencil2d_tma(const __grid_constant__ P
     const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
     T acc[C::R][VEC];
     if (!DENSE) {
-        __shared__ T c1s[PXB_ST2_MAXTAP];
-        if (tid < PXB_ST2_MAXTAP) c1s[tid] = T(p.coef1[tid]);
+        __shared__ T c1s[PXB_ST2_MAXTAP + 2 * (C::R - 1)];  // row factor with R-1 zeros on each side
+        if (tid < PXB_ST2_MAXTAP + 2 * (C::R - 1)) {
+            const int q = tid - (C::R - 1);
+            c1s[tid] = (q >= 0 && q < p.k1) ? T(p.coef1[q]) : T(0);
+        }
         T c2[NV * VEC - VEC + 1];
         for (int q = 0; q < NV * VEC - VEC + 1; ++q) c2[q] = T(p.coef2[q]);
         for (int it = tid; it < p.bh * C::TXL; it += C::NT) pxb_st2_row_item<T, VEC, NV>(p, box, mid, it >> 5, (it & 31) * VEC, c2);

@@ -62,30 +62,29 @@ PXB_HD void pxb_st2_row_item(const PxbSt2P& p, const T* __restrict__ box, T* __r
     }
     PxbVec<T, VEC> acc;
     for (int j = 0; j < VEC; ++j) acc.v[j] = T(0);
-    for (int q = 0; q < NV * VEC - VEC + 1; ++q) {
-        if (q < p.k2) {
-            const T c = c2[q];
-            for (int j = 0; j < VEC; ++j) acc.v[j] += c * v[q + j];
-        }
-    }
+    // every tap the window covers, unconditionally: c2[q] == 0 beyond the kernel (<= VEC-1 wasted taps, no predicates)
+    for (int q = 0; q < NV * VEC - VEC + 1; ++q)
+        for (int j = 0; j < VEC; ++j) acc.v[j] += c2[q] * v[q + j];
     pxb_vstore<T, VEC>(mid + y * C::TX + xl, acc);
 }
 
-// column pass + epilogue for one thread: R adjacent rows x VEC columns
+// column pass for one thread: R adjacent rows x VEC columns.  `c1p` = the row factor padded with R-1 zeros on each
+// side (c1p[R-1+q] = c1[q]), so that the R running outputs take every loaded row without a range test:
+//   out[r] += c1[i - r] * t[i]   for all r   (the coefficient window slides through registers)
 template <class T, int VEC>
-PXB_HD void pxb_st2_col_item(const PxbSt2P& p, const T* __restrict__ mid, int yl, int xl, const T* __restrict__ c1, T (*acc)[VEC]) {
+PXB_HD void pxb_st2_col_item(const PxbSt2P& p, const T* __restrict__ mid, int yl, int xl, const T* __restrict__ c1p, T (*acc)[VEC]) {
     using C = PxbSt2Cfg<T, VEC>;
     for (int r = 0; r < C::R; ++r)
         for (int j = 0; j < VEC; ++j) acc[r][j] = T(0);
+    T cw[C::R];  // cw[r] = c1[i - r]
+    for (int r = 0; r < C::R; ++r) cw[r] = T(0);
+    const T* __restrict__ src = mid + yl * C::TX + xl;
     for (int i = 0; i < C::R + p.k1 - 1; ++i) {
-        const PxbVec<T, VEC> t = pxb_vload<T, VEC>(mid + (yl + i) * C::TX + xl);
-        for (int r = 0; r < C::R; ++r) {
-            const int q = i - r;
-            if (q >= 0 && q < p.k1) {
-                const T c = c1[q];
-                for (int j = 0; j < VEC; ++j) acc[r][j] += c * t.v[j];
-            }
-        }
+        for (int r = C::R - 1; r > 0; --r) cw[r] = cw[r - 1];
+        cw[0] = c1p[C::R - 1 + i];
+        const PxbVec<T, VEC> t = pxb_vload<T, VEC>(src + i * C::TX);
+        for (int r = 0; r < C::R; ++r)
+            for (int j = 0; j < VEC; ++j) acc[r][j] += cw[r] * t.v[j];
     }
 }
 
@@ -200,6 +199,8 @@ inline int pxb_st2_setup(PxbSt2P& p) {
     for (int q = 0; q < p.extra; ++q) p.coef2[q] = 0.0;
     p.k2 += p.extra;
     p.c2 += p.extra;
+    for (int q = p.k2; q < PXB_ST2_MAXTAP; ++q) p.coef2[q] = 0.0;  // the row pass runs every tap its window covers
+    for (int q = p.k1; q < PXB_ST2_MAXTAP; ++q) p.coef1[q] = 0.0;
     if (pxb_st2_nv(p.k2, VEC) > (VEC == 4 ? 4 : 6)) return 1;  // compiled window widths: 13 taps (fp32), 11 taps (fp64)
     if (p.n2 % VEC) return 2;
     p.bh = C::TY + p.k1 - 1;

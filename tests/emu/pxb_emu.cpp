@@ -279,8 +279,12 @@ static void t_st2_nv(const PxbSt2P& p, const T* in, const T* in2, T* out) {
                     for (int it = 0; it < p.bh * p.bw / VEC; ++it) pxb_st2_combine_item<T, VEC>(p, box.data(), box2.data(), it);
                 if (p.dense)
                     for (int i = 0; i < p.k1 * p.k2; ++i) mid[i] = pxb_st2_dense_coef<T>(p, (const T*)p.coef, i);
-                T c1[PXB_ST2_MAXTAP], c2[PXB_ST2_MAXTAP];
-                for (int q = 0; q < PXB_ST2_MAXTAP; ++q) { c1[q] = T(p.coef1[q]); c2[q] = T(p.coef2[q]); }
+                T c1[PXB_ST2_MAXTAP + 2 * (C::R - 1)], c2[PXB_ST2_MAXTAP];
+                for (int q = 0; q < PXB_ST2_MAXTAP; ++q) c2[q] = T(p.coef2[q]);
+                for (int t = 0; t < PXB_ST2_MAXTAP + 2 * (C::R - 1); ++t) {
+                    const int q = t - (C::R - 1);
+                    c1[t] = (q >= 0 && q < p.k1) ? T(p.coef1[q]) : T(0);
+                }
                 if (!p.dense)
                     for (int it = 0; it < p.bh * C::TXL; ++it) pxb_st2_row_item<T, VEC, NV>(p, box.data(), mid.data(), it / C::TXL, (it % C::TXL) * VEC, c2);
                 for (int tid = 0; tid < C::NT; ++tid) {

@@ -35,10 +35,11 @@ def test_struct_layouts_match_the_c_compiler():
     #include <stddef.h>
     #include "pyxu_b200.h"
     int main(void){
-      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(pxb_slab), sizeof(pxb_stencil_desc), sizeof(pxb_grad_desc),
-             sizeof(pxb_prox_spec), sizeof(pxb_fterm), sizeof(pxb_pds_params));
-      printf("%zu %zu %zu %zu\n", offsetof(pxb_stencil_desc, coef), offsetof(pxb_grad_desc, coef),
-             offsetof(pxb_grad_desc, slab), offsetof(pxb_pds_params, lam));
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pxb_slab), sizeof(pxb_stencil_desc), sizeof(pxb_grad_desc),
+             sizeof(pxb_prox_spec), sizeof(pxb_fterm), sizeof(pxb_pds_params), sizeof(pxb_stencil2d), sizeof(pxb_fista_step));
+      printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(pxb_stencil_desc, coef), offsetof(pxb_grad_desc, coef),
+             offsetof(pxb_grad_desc, slab), offsetof(pxb_pds_params, lam), offsetof(pxb_stencil2d, coef), offsetof(pxb_stencil2d, add_period),
+             offsetof(pxb_fista_step, norms));
       return 0; }
     """
     with tempfile.TemporaryDirectory() as td:
@@ -47,8 +48,9 @@ def test_struct_layouts_match_the_c_compiler():
         exe = os.path.join(td, "t")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
-    sizes = [C.sizeof(s) for s in (K.Slab, K.StencilDesc, K.GradDesc, K.ProxSpec, K.FTerm, K.PdsParams)]
-    offs = [K.StencilDesc.coef.offset, K.GradDesc.coef.offset, K.GradDesc.slab.offset, K.PdsParams.lam.offset]
+    sizes = [C.sizeof(s) for s in (K.Slab, K.StencilDesc, K.GradDesc, K.ProxSpec, K.FTerm, K.PdsParams, K.Stencil2D, K.FistaStep)]
+    offs = [K.StencilDesc.coef.offset, K.GradDesc.coef.offset, K.GradDesc.slab.offset, K.PdsParams.lam.offset, K.Stencil2D.coef.offset,
+            K.Stencil2D.add_period.offset, K.FistaStep.norms.offset]
     assert [int(v) for v in out] == sizes + offs
 
 
@@ -57,6 +59,13 @@ def test_argument_errors_are_reported_without_a_gpu():
     d = K.StencilDesc()
     rc = lib.pxb_stencil_apply(C.byref(d), None, None, None)
     assert rc == -1 and b"null" in lib.pxb_last_error()
+    s2 = K.Stencil2D()
+    assert lib.pxb_stencil2d_apply(C.byref(s2), None, None, None) == -1
+    assert lib.pxb_stencil2d_fista(C.byref(s2), None, 0, None, None) == -1
+    one = (C.c_int64 * 3)(4, 4, 4)
+    assert lib.pxb_stencil_axis0_apply(0, 1, one, None, 3, 5, (C.c_double * 3)(1, 2, 1), C.c_void_p(16), C.c_void_p(32), None) == -1  # center outside the kernel
+    assert lib.pxb_pds_iter(0, None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.pxb_set_iter_path(7) == -1 and lib.pxb_set_iter_path(0) == 0
     g = K.GradDesc()
     g.ndir = 7
     rc = lib.pxb_gradient_apply(C.byref(g), C.c_void_p(8), C.c_void_p(16), None)

@@ -258,3 +258,11 @@ def test_large_results_leave_the_device_through_the_pipelined_copy(env):
         assert isinstance(out, np.ndarray) and out.shape == (n,) and np.array_equal(out, t.cpu().numpy())
     t2 = torch.randn(3, (80 << 20) // 12, device="cuda", generator=gen)
     assert np.array_equal(env.A.restore(t2, env.A.HOST), t2.cpu().numpy())
+    # and the way in: a pageable NumPy array above 64 MiB goes through the pinned staging buffers
+    rng = np.random.default_rng(0)
+    for dt in (np.float32, np.float64):
+        h = rng.standard_normal((3, (70 << 20) // 12 + 7)).astype(dt)
+        d, origin = env.A.asdevice(h)
+        assert origin == env.A.HOST and d.is_cuda and tuple(d.shape) == h.shape and np.array_equal(d.cpu().numpy(), h)
+    d32, _ = env.A.asdevice(h, dtype=torch.float32)  # with a dtype conversion on the device
+    assert d32.dtype == torch.float32 and np.array_equal(d32.cpu().numpy(), h.astype(np.float32))
