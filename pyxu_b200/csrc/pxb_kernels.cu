@@ -285,8 +285,12 @@ int pxb_gradient_apply(const pxb_grad_desc* d, const void* x, void* z, void* str
     if (int e = check_grad(d, who)) return e;
     if (!x || !z || x == z) return fail(PXB_EINVAL, "%s: null or aliased arrays", who);
     VoxMap m;
-    if (!make_map(d->batch, d->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        int rc = 0;  // first-order stacks: 128-bit vectorised bodies (pxb_tv_kernels.cu)
+        if (pxb_tv_try_grad(d, false, x, z, s, &rc)) return rc;
+    }
+    if (!make_map(d->batch, d->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     if (d->dtype == PXB_F32) k_grad_apply<float><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const float*)x, (float*)z);
     else k_grad_apply<double><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const double*)x, (double*)z);
     PXB_CHECK_LAUNCH(who);
@@ -298,8 +302,12 @@ int pxb_gradient_adjoint(const pxb_grad_desc* d, const void* z, void* x, void* s
     if (int e = check_grad(d, who)) return e;
     if (!x || !z || x == z) return fail(PXB_EINVAL, "%s: null or aliased arrays", who);
     VoxMap m;
-    if (!make_map(d->batch, d->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        int rc = 0;
+        if (pxb_tv_try_grad(d, true, z, x, s, &rc)) return rc;
+    }
+    if (!make_map(d->batch, d->shape, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
     if (d->dtype == PXB_F32) k_grad_adjoint<float><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const float*)z, (float*)x);
     else k_grad_adjoint<double><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const double*)z, (double*)x);
     PXB_CHECK_LAUNCH(who);

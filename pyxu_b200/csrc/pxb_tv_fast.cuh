@@ -351,3 +351,64 @@ PXB_HD void pxb_tv_dual_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const px
     }
     if (NORMS) { nrm[0] += a0; nrm[1] += a1; }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Gradient stack on its own (LinOp.apply / adjoint of a first-order Gradient): VEC voxels per thread.
+//   apply  : z_k[s] = cm*x[s-e_k] + c0*x[s] + cp*x[s+e_k]          (read 1 array, write NDIR)
+//   adjoint: x[s]   = sum_k cm*z_k[s+e_k] + c0*z_k[s] + cp*z_k[s-e_k]
+// Faces with a folding boundary mode fall back, per voxel, to the generic bodies (as the fused half-steps do).
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int NDIR, int VEC>
+PXB_HD void pxb_tv_grad_apply_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const T* __restrict__ x, T* __restrict__ z, int64_t b, int i0,
+                                  int i1, int i2) {
+    if (pxb_tv_needs_generic<T, NDIR>(q, i0, i1, i2, VEC)) {
+        const PxbGeom g = pxb_geom(d.shape);
+        for (int j = 0; j < VEC; ++j) pxb_body_grad_apply<T>(d, g, x, z, b, i0, i1, i2 + j);
+        return;
+    }
+    const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2;
+    const T* __restrict__ xb = x + b * q.vol + v;
+    T* __restrict__ zb = z + b * NDIR * q.vol + v;
+    const PxbVec<T, VEC> xc = pxb_vload<T, VEC>(xb);
+    for (int k = 0; k < NDIR; ++k) {
+        const int ax = 3 - NDIR + k;
+        PxbVec<T, VEC> o;
+        if (ax == 2) {
+            pxb_tv_taps_row<T, VEC>(xb, xc, q.cp[k], q.c0[k], q.cm[k], i2 > 0, i2 + VEC < q.n2, o.v);
+        } else {
+            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? q.n0 : q.n1;
+            const bool has_lo = i > 0 || (ax == 0 && q.open_lo), has_hi = i < n - 1 || (ax == 0 && q.open_hi);
+            pxb_tv_taps_col<T, VEC>(xb, ax == 0 ? q.s0 : q.s1, xc, q.cp[k], q.c0[k], q.cm[k], has_lo, has_hi, o.v);
+        }
+        pxb_vstore<T, VEC>(zb + k * q.vol, o);
+    }
+}
+
+template <class T, int NDIR, int VEC>
+PXB_HD void pxb_tv_grad_adjoint_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const T* __restrict__ z, T* __restrict__ x, int64_t b, int i0,
+                                    int i1, int i2) {
+    if (pxb_tv_needs_generic<T, NDIR>(q, i0, i1, i2, VEC)) {
+        const PxbGeom g = pxb_geom(d.shape);
+        for (int j = 0; j < VEC; ++j) pxb_body_grad_adjoint<T>(d, g, z, x, b, i0, i1, i2 + j);
+        return;
+    }
+    const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2;
+    const T* __restrict__ zb = z + b * NDIR * q.vol + v;
+    PxbVec<T, VEC> acc;
+    for (int j = 0; j < VEC; ++j) acc.v[j] = T(0);
+    for (int k = 0; k < NDIR; ++k) {
+        const int ax = 3 - NDIR + k;
+        const T* __restrict__ zk = zb + k * q.vol;
+        const PxbVec<T, VEC> c = pxb_vload<T, VEC>(zk);
+        T t[VEC];
+        if (ax == 2) {
+            pxb_tv_taps_row<T, VEC>(zk, c, q.cm[k], q.c0[k], q.cp[k], i2 > 0, i2 + VEC < q.n2, t);
+        } else {
+            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? q.n0 : q.n1;
+            const bool has_lo = i > 0 || (ax == 0 && q.open_lo), has_hi = i < n - 1 || (ax == 0 && q.open_hi);
+            pxb_tv_taps_col<T, VEC>(zk, ax == 0 ? q.s0 : q.s1, c, q.cm[k], q.c0[k], q.cp[k], has_lo, has_hi, t);
+        }
+        for (int j = 0; j < VEC; ++j) acc.v[j] += t[j];
+    }
+    pxb_vstore<T, VEC>(x + b * q.vol + v, acc);
+}

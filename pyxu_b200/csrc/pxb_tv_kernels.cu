@@ -45,6 +45,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksDual) k_tv_dual(const __grid
     if (NORMS) block_accumulate(nrm[0], nrm[1], v.b, v.ok, norms);
 }
 
+template <class T, int NDIR, int VEC, bool ADJ>
+__global__ void __launch_bounds__(kBlock, 4) k_tv_grad(const __grid_constant__ PxbTvP<T> q, const __grid_constant__ pxb_grad_desc d,
+                                                       const __grid_constant__ VoxMap m, const T* __restrict__ in, T* __restrict__ out) {
+    const Vox v = vox_of_thread(m);
+    if (!v.ok) return;
+    if (ADJ) pxb_tv_grad_adjoint_vec<T, NDIR, VEC>(q, d, in, out, v.b, v.i0, v.i1, v.i2 * VEC);
+    else pxb_tv_grad_apply_vec<T, NDIR, VEC>(q, d, in, out, v.b, v.i0, v.i1, v.i2 * VEC);
+}
+
 // widest vector (<= 16 bytes) that divides the row length and matches every pointer's alignment
 template <class T>
 int pick_vec(int64_t n2, std::initializer_list<const void*> ptrs) {
@@ -115,6 +124,49 @@ void dual_dir(int ndir, int vec, A&&... a) {
 }
 
 }  // namespace
+
+namespace {
+
+template <class T, int NDIR, bool ADJ>
+void grad_vec(int vec, const VoxMap& m, cudaStream_t s, const pxb_grad_desc& d, const PxbTvCoef& cf, const void* in, void* out) {
+    pxb_pds_params P{};
+    P.hkind = PXB_DUAL_NONE;
+    PxbTvP<T> q;
+    pxb_tv_prepare<T>(d, cf, P, q);
+    if constexpr (sizeof(T) == 4) {
+        if (vec == 4) { k_tv_grad<T, NDIR, 4, ADJ><<<grid_of(m), kBlock, 0, s>>>(q, d, m, (const T*)in, (T*)out); return; }
+    }
+    if (vec == 2) k_tv_grad<T, NDIR, 2, ADJ><<<grid_of(m), kBlock, 0, s>>>(q, d, m, (const T*)in, (T*)out);
+    else k_tv_grad<T, NDIR, 1, ADJ><<<grid_of(m), kBlock, 0, s>>>(q, d, m, (const T*)in, (T*)out);
+}
+
+template <class T, bool ADJ>
+void grad_dir(int ndir, int vec, const VoxMap& m, cudaStream_t s, const pxb_grad_desc& d, const PxbTvCoef& cf, const void* in, void* out) {
+    if (ndir == 3) grad_vec<T, 3, ADJ>(vec, m, s, d, cf, in, out);
+    else if (ndir == 2) grad_vec<T, 2, ADJ>(vec, m, s, d, cf, in, out);
+    else grad_vec<T, 1, ADJ>(vec, m, s, d, cf, in, out);
+}
+
+}  // namespace
+
+// Gradient.apply / adjoint through the vectorised bodies; false when the descriptor is not a first-order stack
+bool pxb_tv_try_grad(const pxb_grad_desc* K, bool adjoint, const void* in, void* out, cudaStream_t s, int* rc) {
+    PxbTvCoef cf;
+    if (!pxb_tv_fast_coefs(*K, cf)) return false;
+    const bool f32 = K->dtype == PXB_F32;
+    const int vec = f32 ? pick_vec<float>(K->shape[2], {in, out}) : pick_vec<double>(K->shape[2], {in, out});
+    VoxMap m;
+    if (!make_map_vec(K->batch, K->shape, vec, m)) {
+        *rc = pxb_fail(PXB_ENOSUP, "pxb_gradient: grid too large");
+        return true;
+    }
+    if (f32) { if (adjoint) grad_dir<float, true>(K->ndir, vec, m, s, *K, cf, in, out); else grad_dir<float, false>(K->ndir, vec, m, s, *K, cf, in, out); }
+    else { if (adjoint) grad_dir<double, true>(K->ndir, vec, m, s, *K, cf, in, out); else grad_dir<double, false>(K->ndir, vec, m, s, *K, cf, in, out); }
+    pxb_count_launch();
+    cudaError_t e = cudaGetLastError();
+    *rc = e == cudaSuccess ? 0 : pxb_fail(PXB_ECUDA, "pxb_gradient: %s", cudaGetErrorString(e));
+    return true;
+}
 
 bool pxb_tv_try_primal(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu, const void* z, void* x_out, void* w,
                        double* norms, cudaStream_t s, int* rc) {

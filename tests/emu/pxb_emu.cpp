@@ -403,7 +403,44 @@ static int t_t2(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const
     return -131;
 }
 
+// vectorised Gradient apply / adjoint bodies (pxb_tv_fast.cuh), looped like the CUDA thread map
+template <class T, int NDIR, int VEC>
+static void t_tvgrad(bool adj, const pxb_grad_desc* K, const PxbTvCoef& cf, const void* in, void* out) {
+    const PxbGeom g = pxb_geom(K->shape);
+    pxb_pds_params P{};
+    PxbTvP<T> q;
+    pxb_tv_prepare<T>(*K, cf, P, q);
+    for (int64_t b = 0; b < K->batch; ++b)
+        for (int i0 = 0; i0 < g.n0; ++i0)
+            for (int i1 = 0; i1 < g.n1; ++i1)
+                for (int i2 = 0; i2 < g.n2; i2 += VEC) {
+                    if (adj) pxb_tv_grad_adjoint_vec<T, NDIR, VEC>(q, *K, (const T*)in, (T*)out, b, i0, i1, i2);
+                    else pxb_tv_grad_apply_vec<T, NDIR, VEC>(q, *K, (const T*)in, (T*)out, b, i0, i1, i2);
+                }
+}
+template <class T, int NDIR>
+static int t_tvgrad_vec(int vec, bool adj, const pxb_grad_desc* K, const PxbTvCoef& cf, const void* in, void* out) {
+    if (K->shape[2] % vec) return -1;
+    if (vec == 4) t_tvgrad<T, NDIR, 4>(adj, K, cf, in, out);
+    else if (vec == 2) t_tvgrad<T, NDIR, 2>(adj, K, cf, in, out);
+    else if (vec == 1) t_tvgrad<T, NDIR, 1>(adj, K, cf, in, out);
+    else return -1;
+    return 0;
+}
+template <class T>
+static int t_tvgrad_dir(int vec, bool adj, const pxb_grad_desc* K, const void* in, void* out) {
+    PxbTvCoef cf;
+    if (!pxb_tv_fast_coefs(*K, cf)) return -2;
+    if (K->ndir == 3) return t_tvgrad_vec<T, 3>(vec, adj, K, cf, in, out);
+    if (K->ndir == 2) return t_tvgrad_vec<T, 2>(vec, adj, K, cf, in, out);
+    return t_tvgrad_vec<T, 1>(vec, adj, K, cf, in, out);
+}
+
 extern "C" {
+int emu_tv_grad(int vec, int adjoint, const pxb_grad_desc* K, const void* in, void* out) {
+    if (K->dtype == PXB_F32) return t_tvgrad_dir<float>(vec, adjoint != 0, K, in, out);
+    return t_tvgrad_dir<double>(vec, adjoint != 0, K, in, out);
+}
 int emu_tv_tile2d(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
                   void* x_out, double* nx, double* nz, int unused) {
     (void)unused;
