@@ -170,6 +170,30 @@ int pxb_lincomb(int dtype, int64_t n, void* out, double a, const void* x, double
 int pxb_stencil_axis0_apply(int dtype, int64_t batch, const int64_t* shape, const pxb_slab* slab, int k0, int c0,
                             const double* coef, const void* in, void* out, void* stream);
 
+/* A separable 3-D stencil ('constant' boundaries) in ONE pass over HBM where the reference chains three 1-D stencils
+ * (stencil.py:497-538): thread blocks march along axis 0 with the in-plane-filtered planes in a register ring.
+ *   out = alpha * (S_0 S_1 S_2)(in) + beta * add[i % add_period]     (add: dense (batch, n0, n1, n2), nullable)
+ * coef0/1/2: the 1-D factors along axes 0/1/2 (HOST values), center[] their entries on the output sample.
+ * Envelope: 3, 5, 7 or 9 taps along axis 0, <= 16 along axis 1, <= 13 (fp32) / 11 (fp64) along axis 2, last axis a
+ * multiple of 4 / 2 samples, 16-byte aligned arrays; PXB_ENOSUP otherwise (use pxb_stencil_axis0_apply +
+ * pxb_stencil2d_apply).  Slab cuts: as pxb_stencil_axis0_apply. */
+typedef struct pxb_stencil3d {
+    int32_t dtype;
+    int32_t _pad;
+    int64_t batch;
+    int64_t shape[3];
+    int32_t ksize[3];
+    int32_t center[3];
+    double coef0[16];
+    double coef1[16];
+    double coef2[16];
+    double alpha, beta;
+    const void* add;
+    int64_t add_period;
+    pxb_slab slab;
+} pxb_stencil3d;
+int pxb_stencil3d_apply(const pxb_stencil3d* d, const void* in, void* out, void* stream);
+
 /* One accelerated proximal-gradient (FISTA) iteration on f = alpha_f*||A x + shift||^2, g pointwise, A such a stencil
  * (reference: src/pyxu/opt/solver/pgd.py:173-191), as TWO tiled passes instead of five:
  *   which == 0:  out = r = d.alpha * A((1+a) x - a x_prev) + d.beta * d.add      (d describes A; the extrapolated point

@@ -115,6 +115,7 @@ class Stencil(pxo.SquareOp):
 
         self._dev_coef = {}  # (dtype, device, pass, flipped) -> device tensor
         self._tiled_ok = None  # TMA-tiled single-pass kernel (pxb_stencil2d_apply): None = not tried yet
+        self._tiled3d_ok = None  # single-pass separable 3-D kernel (pxb_stencil3d_apply)
         self.lipschitz = self.estimate_lipschitz(__rule=True)
 
     # -- descriptors ---------------------------------------------------------------------
@@ -267,14 +268,52 @@ class Stencil(pxo.SquareOp):
             rc = K.lib().pxb_stencil_apply(C.byref(dd), pin, pout, A.stream())
         K.check(rc, "Stencil (axis 0)")
 
+    def _desc3d(self, dcode, adjoint, batch, alpha=1.0, beta=0.0, add=None, slab=None, shape0=None):
+        """pxb_stencil3d descriptor (single-pass separable 3-D stencil), or None when the operator is not a separable
+        'constant'-mode stencil with a factor along axis 0."""
+        plan = self._tiled_plan(adjoint) if self._tiled_ok is not False else None
+        if plan is None or plan[0] is None or plan[1][0] != "sep":
+            return None
+        (k3, c3), (_, t1, c1, t2, c2), scale = plan
+        D = len(self._arg_shape)
+        shape3 = (1,) * (3 - D) + self._arg_shape
+        d = K.Stencil3D()
+        d.dtype, d.batch = dcode, batch
+        d.shape[0], d.shape[1], d.shape[2] = (shape0 if shape0 is not None else shape3[0]), shape3[1], shape3[2]
+        t0 = k3.reshape(-1)
+        if max(t0.size, t1.size, t2.size) > 16:
+            return None
+        for a, (t, c) in enumerate(((t0, int(c3[0])), (t1, c1), (t2, c2))):
+            d.ksize[a], d.center[a] = t.size, c
+            dst = (d.coef0, d.coef1, d.coef2)[a]
+            for i, v in enumerate(t):
+                dst[i] = float(v)
+        d.alpha, d.beta = float(alpha) * scale, float(beta)
+        if add is not None:
+            d.add, d.add_period = add.data_ptr(), add.numel()
+            d._keep = add
+        d.slab = slab if slab is not None else K.Slab(0, 0, 0, 0)
+        return d
+
     def _run_tiled(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
-        """One pass over HBM for the in-plane part (+ one generic pass when there is a factor along axis 0).
-        Returns None when the tiled kernel does not apply."""
+        """One pass over HBM for the in-plane part (+ one streaming pass when there is a factor along axis 0 that the
+        single-pass 3-D kernel does not take).  Returns None when the tiled kernels do not apply."""
+        batch = max(1, arr.numel() // self.dim)
+        if self._tiled3d_ok is not False:
+            d3 = self._desc3d(A.dcode(arr), adjoint, batch, alpha, beta, add)
+            if d3 is not None:
+                out = A.empty_like(arr)
+                rc = K.lib().pxb_stencil3d_apply(C.byref(d3), A.ptr(arr), A.ptr(out), A.stream())
+                if rc == 0:
+                    self._tiled3d_ok = self._tiled_ok = True
+                    return out
+                if rc != -3:
+                    K.check(rc, "pxb_stencil3d_apply")
+            self._tiled3d_ok = False
         got = self._tiled_desc(arr, adjoint, alpha, beta, add)
         if got is None:
             return None
         d, axis0 = got
-        batch = max(1, arr.numel() // self.dim)
         cur = arr
         if axis0 is not None:  # the factor along the slowest axis: one streaming pass of its own
             tmp = A.empty_like(arr)

@@ -471,6 +471,10 @@ class SlabCondatVuDeblur:
             d, _ = self.Aop._tiled_desc(self.r[0, own], adj, alpha=1.0, beta=1.0 if add is not None else 0.0, add=add)
             d.nimg = n0
             self._desc2d[adj] = d
+        # single-pass separable 3-D kernel (marching, register ring) when the PSF is inside its envelope
+        self._desc3d = {False: self.Aop._desc3d(A.dcode(self.r), False, 1, 1.0, 1.0, self.neg_y, slab=self._slab, shape0=n0),
+                        True: self.Aop._desc3d(A.dcode(self.r), True, 1, slab=self._slab, shape0=n0)}
+        self.single_pass = all(v is not None for v in self._desc3d.values())
         self._gdesc = self.K._desc(1, A.dcode(self.r), slab=self._slab, shape0=n0)
         # z0 = K x0 needs x0's ghost planes
         self._wait(self._exchange([(self._xb[0][0], H, H)]))
@@ -513,7 +517,15 @@ class SlabCondatVuDeblur:
         return dist.batch_isend_irecv(ops) if ops else []
 
     def _stencil(self, adjoint, src, dst):
-        """dst(owned planes) = A src (or A^T src): axis-0 streaming pass (reads src's ghost planes) + tiled in-plane pass."""
+        """dst(owned planes) = A src (or A^T src), reading src's ghost planes: one marching pass (pxb_stencil3d_apply), or
+        axis-0 streaming pass + tiled in-plane pass outside its envelope."""
+        if self.single_pass:
+            rc = K.lib().pxb_stencil3d_apply(C.byref(self._desc3d[adjoint]), self._p(src, 0), self._p(dst, 0), A.stream())
+            if rc == 0:
+                return
+            if rc != -3:
+                K.check(rc, "pxb_stencil3d_apply")
+            self.single_pass = False
         axis0 = self._plans[adjoint][0]
         self.Aop._axis0_pass(axis0, self._p(src, 0), self._p(self.tmp, 0), 1, slab=self._slab, shape0=self.n0)
         rc = K.lib().pxb_stencil2d_apply(C.byref(self._desc2d[adjoint]), self._p(self.tmp, 0), self._p(dst, 0), A.stream())

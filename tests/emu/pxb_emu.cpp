@@ -4,6 +4,7 @@
 // kernels call) for the host and drives them with plain loops, so that index handling (boundary
 // maps, adjoint pre-images, slab halos, fused half-steps) can be checked against the oracle on the
 // GPU-less build container.  Never loaded by the pyxu_b200 package; pointers here are HOST pointers.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 
@@ -13,6 +14,7 @@
 #include "../../pyxu_b200/csrc/pxb_tv_tma.cuh"
 #include "../../pyxu_b200/csrc/pxb_stencil_tma.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_tile2d.cuh"
+#include "../../pyxu_b200/csrc/pxb_stencil3d.cuh"
 #include <vector>
 
 #define FOR_VOX(batch, g)                              \
@@ -436,7 +438,91 @@ static int t_tvgrad_dir(int vec, bool adj, const pxb_grad_desc* K, const void* i
     return t_tvgrad_vec<T, 1>(vec, adj, K, cf, in, out);
 }
 
+// single-pass separable 3-D stencil (pxb_stencil3d.cuh): CTA by CTA, plane by plane; the per-thread register ring is an array
+template <class T, int VEC, int NV, int K0>
+static void t_st3_run(const PxbSt3P& p, const T* in, T* out) {
+    using C = PxbSt3Cfg<T, VEC>;
+    const int64_t s0 = (int64_t)p.s.n1 * p.s.n2;
+    std::vector<T> box((size_t)p.s.bh * p.s.bw), mid((size_t)p.s.bh * C::TX);
+    struct Ring { T v[K0][C::R][VEC]; };
+    std::vector<Ring> rings(C::NT);
+    T c1[PXB_ST2_MAXTAP + 2 * (C::R - 1)], c2[PXB_ST2_MAXTAP], c0v[K0];
+    for (int q = 0; q < PXB_ST2_MAXTAP; ++q) c2[q] = T(p.s.coef2[q]);
+    for (int t = 0; t < PXB_ST2_MAXTAP + 2 * (C::R - 1); ++t) { const int q = t - (C::R - 1); c1[t] = (q >= 0 && q < p.s.k1) ? T(p.s.coef1[q]) : T(0); }
+    for (int k = 0; k < K0; ++k) c0v[k] = T(p.coef0[k]);
+    for (int64_t b = 0; b < p.batch; ++b)
+        for (int ch = 0; ch < p.nchunk; ++ch)
+            for (int ty = 0; ty < p.s.nty; ++ty)
+                for (int tx = 0; tx < p.s.ntx; ++tx) {
+                    const int x0 = tx * C::TX, y0 = ty * C::TY;
+                    const int m0 = ch * p.chunk, m1 = std::min(p.n0, m0 + p.chunk);
+                    const int pl_lo = m0 - p.c0, pl_hi = m1 + K0 - 1 - p.c0;
+                    for (auto& r : rings) std::memset(&r, 0, sizeof(r));
+                    for (int pl = pl_lo; pl < pl_hi; ++pl) {
+                        const bool have = pl >= -p.lo_planes && pl < p.n0 + p.hi_planes;
+                        if (have) {
+                            for (int i = 0; i < p.s.bh; ++i)
+                                for (int j = 0; j < p.s.bw; ++j) {
+                                    const int y = y0 - p.s.c1 + i, x = x0 - p.s.c2 + j;
+                                    box[(size_t)i * p.s.bw + j] = (y >= 0 && y < p.s.n1 && x >= 0 && x < p.s.n2) ? in[b * p.vol + (int64_t)pl * s0 + (int64_t)y * p.s.n2 + x] : T(0);
+                                }
+                            for (int it = 0; it < p.s.bh * C::TXL; ++it) pxb_st3_row_item<T, VEC, NV>(p, box.data(), mid.data(), it / C::TXL, (it % C::TXL) * VEC, c2);
+                        }
+                        const int q = pl - (K0 - 1 - p.c0);
+                        for (int tid = 0; tid < C::NT; ++tid) {
+                            const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
+                            T t[C::R][VEC];
+                            if (have) pxb_st3_col_item<T, VEC>(p, mid.data(), yl, xl, c1, t);
+                            else std::memset(t, 0, sizeof(t));
+                            pxb_st3_push<T, VEC, K0>(rings[tid].v, t);
+                            if (q >= m0) pxb_st3_store<T, VEC, K0>(p, out, c0v, rings[tid].v, b, q, y0, x0, yl, xl);
+                        }
+                    }
+                }
+}
+template <class T, int VEC, int NV>
+static int t_st3_k0(const PxbSt3P& p, const T* in, T* out) {
+    switch (p.k0) {
+        case 3: t_st3_run<T, VEC, NV, 3>(p, in, out); return 0;
+        case 5: t_st3_run<T, VEC, NV, 5>(p, in, out); return 0;
+        case 7: t_st3_run<T, VEC, NV, 7>(p, in, out); return 0;
+        case 9: t_st3_run<T, VEC, NV, 9>(p, in, out); return 0;
+        default: return -111;
+    }
+}
+template <class T>
+static int t_st3(const pxb_stencil3d* d, const void* in, void* out) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    PxbSt3P p;
+    p.s.n1 = (int)d->shape[1]; p.s.n2 = (int)d->shape[2];
+    p.s.k1 = d->ksize[1]; p.s.k2 = d->ksize[2]; p.s.c1 = d->center[1]; p.s.c2 = d->center[2];
+    for (int i = 0; i < PXB_ST2_MAXTAP; ++i) { p.s.coef1[i] = d->coef1[i]; p.s.coef2[i] = d->coef2[i]; p.coef0[i] = d->coef0[i]; }
+    p.s.coef = nullptr; p.s.alpha = d->alpha; p.s.beta = d->beta; p.s.add = d->add; p.s.add_period = d->add_period;
+    if (d->add && d->add_period > 0 && d->add_period >= d->batch * d->shape[0] * d->shape[1] * d->shape[2]) p.s.add_period = 0;
+    p.s.pa = 1.0; p.s.pb = 0.0; p.s.epi = 0; p.s.e1 = p.s.e2 = nullptr; p.s.norms = nullptr; p.s.imgs_per_row = 1;
+    p.n0 = (int)d->shape[0]; p.batch = d->batch;
+    const int halo = d->slab.halo;
+    const int alloc = d->slab.plane_alloc > 0 ? d->slab.plane_alloc : p.n0 + 2 * halo;
+    p.vol = (int64_t)alloc * d->shape[1] * d->shape[2];
+    p.k0 = d->ksize[0]; p.c0 = d->center[0];
+    p.lo_planes = d->slab.open_lo ? p.c0 : 0;
+    p.hi_planes = d->slab.open_hi ? p.k0 - 1 - p.c0 : 0;
+    if (int why = pxb_st3_setup<T, VEC>(p)) return -100 - why;
+    switch (pxb_st2_nv(p.s.k2, VEC)) {
+        case 1: return t_st3_k0<T, VEC, 1>(p, (const T*)in, (T*)out);
+        case 2: return t_st3_k0<T, VEC, 2>(p, (const T*)in, (T*)out);
+        case 3: return t_st3_k0<T, VEC, 3>(p, (const T*)in, (T*)out);
+        case 4: return t_st3_k0<T, VEC, 4>(p, (const T*)in, (T*)out);
+        case 5: return t_st3_k0<T, VEC, 5>(p, (const T*)in, (T*)out);
+        case 6: return t_st3_k0<T, VEC, 6>(p, (const T*)in, (T*)out);
+        default: return -101;
+    }
+}
+
 extern "C" {
+int emu_stencil3d(const pxb_stencil3d* d, const void* in, void* out) {
+    return d->dtype == PXB_F32 ? t_st3<float>(d, in, out) : t_st3<double>(d, in, out);
+}
 int emu_tv_grad(int vec, int adjoint, const pxb_grad_desc* K, const void* in, void* out) {
     if (K->dtype == PXB_F32) return t_tvgrad_dir<float>(vec, adjoint != 0, K, in, out);
     return t_tvgrad_dir<double>(vec, adjoint != 0, K, in, out);

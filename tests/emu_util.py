@@ -27,6 +27,7 @@ def lib():
         h.emu_stencil2d.argtypes = [P(K.Stencil2D), vp, vp]
         h.emu_stencil2d_fista.argtypes = [P(K.Stencil2D), P(K.FistaStep), i, vp]
         h.emu_tv_grad.argtypes = [i, i, P(K.GradDesc), vp, vp]
+        h.emu_stencil3d.argtypes = [P(K.Stencil3D), vp, vp]
         h.emu_dual_update.argtypes = [i, i, i64, i64, i64, d, d, d, vp, vp, vp]
         h.emu_prox_l21.argtypes = [i, i64, i64, i64, d, d, vp, vp]
         h.emu_prox_lincomb.argtypes = [i, P(K.ProxSpec), d, i64, vp, d, vp, d, vp, i64, d, vp, i64]
@@ -121,4 +122,19 @@ def stencil_run_tiled(op, x, adjoint, alpha=1.0, beta=0.0, add=None):
         d.add, d.add_period = add.ctypes.data, add.size
     out = np.empty_like(x)
     rc = lib().emu_stencil2d(C.byref(d), p(cur), p(out))
+    return out if rc == 0 else None
+
+
+def stencil3d_run(op, x, adjoint, alpha=1.0, beta=0.0, add=None, slab=None, shape0=None, raw_ptrs=None):
+    """Single-pass separable 3-D kernel (emulated).  raw_ptrs = (in_ptr, out_ptr) for slab buffers."""
+    batch = 1 if raw_ptrs else max(1, x.size // op.dim)
+    d = op._desc3d(dcode(x), adjoint, batch, alpha, beta, None, slab=slab, shape0=shape0)
+    if d is None:
+        return None
+    if add is not None:
+        d.add, d.add_period = add.ctypes.data, add.size
+    if raw_ptrs:
+        return lib().emu_stencil3d(C.byref(d), raw_ptrs[0], raw_ptrs[1])
+    out = np.empty_like(x)
+    rc = lib().emu_stencil3d(C.byref(d), p(np.ascontiguousarray(x)), p(out))
     return out if rc == 0 else None

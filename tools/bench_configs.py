@@ -98,7 +98,8 @@ def main():
         ms, launches = timed(slab.step, K, W, world)
         nvox = int(np.prod(shape))
         name = f"3-D TV deblurring {'x'.join(map(str, shape))} fp32, CondatVu, separable 7x7x7 Stencil PSF + positivity + L21 o Gradient, {world} z-slab(s)"
-        bpv = 8 + 12 + 8 + 8 + 36  # A_0 x | A_12 . - y | A_0^T r | A_12^T . | single-kernel CV iteration with grad f array
+        # A x - y (read x, y; write r) | A^T r | single-kernel CV iteration with grad f array     (two-pass stencils: 8+12+8+8+36)
+        bpv = (12 + 8 + 36) if slab.single_pass else (8 + 12 + 8 + 8 + 36)
     else:
         n = args.size or 1024
         shape, N = (n, n), n * n
