@@ -13,7 +13,7 @@ namespace {
 // MODE 0: out = alpha*S(in) + beta*add      1: the same on the window pa*in + pb*in2 (two box loads, combined in
 // shared memory)      2: proximal-gradient epilogue (pxb_st2_store_prox)
 template <class T, int VEC, int NV, bool DENSE, int MODE>
-__global__ void __launch_bounds__(256) k_stencil2d_tma(const __grid_constant__ PxbSt2P p, const __grid_constant__ CUtensorMap map,
+__global__ void __launch_bounds__(256, 4) k_stencil2d_tma(const __grid_constant__ PxbSt2P p, const __grid_constant__ CUtensorMap map,
                                                        const __grid_constant__ CUtensorMap map2, T* __restrict__ out) {
     using C = PxbSt2Cfg<T, VEC>;
     constexpr int NBOX = MODE == 1 ? 2 : 1;  // boxes per stage
