@@ -12,6 +12,86 @@ namespace {
 
 // MODE 0: out = alpha*S(in) + beta*add      1: the same on the window pa*in + pb*in2 (two box loads, combined in
 // shared memory)      2: proximal-gradient epilogue (pxb_st2_store_prox)
+// One tile per CTA, no in-CTA pipelining: the dense (FMA-bound) instances.  Walking several tiles per CTA (below) costs them
+// occupancy and wave balance: measured 8192^2 dense 9x9 0.264 ms here vs 0.28-0.31 ms through the pipelined kernel.
+template <class T, int VEC, int NV, bool DENSE, int MODE>
+__global__ void __launch_bounds__(256) k_stencil2d_one(const __grid_constant__ PxbSt2P p, const __grid_constant__ CUtensorMap map,
+                                                       const __grid_constant__ CUtensorMap map2, T* __restrict__ out) {
+    using C = PxbSt2Cfg<T, VEC>;
+    extern __shared__ __align__(128) unsigned char pxb_st2_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    T* box = reinterpret_cast<T*>(pxb_st2_smem);
+    const int box_elems = (p.bh * p.bw + 31) / 32 * 32;
+    T* box2 = box + box_elems;                       // MODE 1 only
+    T* mid = box + (MODE == 1 ? 2 : 1) * box_elems;  // separable: bh x TX intermediate; dense: k1*k2 coefficients
+    const int tid = threadIdx.x;
+    unsigned blk = blockIdx.x;
+    const int tx = blk % (unsigned)p.ntx; blk /= (unsigned)p.ntx;
+    const int ty = blk % (unsigned)p.nty;
+    const int64_t img = blk / (unsigned)p.nty;
+    const int x0 = tx * C::TX, y0 = ty * C::TY;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(p.bh * p.bw * sizeof(T));
+        mbar_expect_tx(&bar, MODE == 1 ? 2 * bytes : bytes);
+        tma_load_3d(box, &map, &bar, x0 - p.c2, y0 - p.c1, (int)img);
+        if (MODE == 1) tma_load_3d(box2, &map2, &bar, x0 - p.c2, y0 - p.c1, (int)img);
+    }
+    if (DENSE) {
+        const T* __restrict__ ck = (const T*)p.coef;
+        for (int i = tid; i < p.k1 * p.k2; i += C::NT) mid[i] = pxb_st2_dense_coef<T>(p, ck, i);
+    }
+    mbar_wait(&bar, 0);
+    if (MODE == 1) {
+        for (int it = tid; it < p.bh * p.bw / VEC; it += C::NT) pxb_st2_combine_item<T, VEC>(p, box, box2, it);
+        __syncthreads();
+    }
+    const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
+    T acc[C::R][VEC];
+    if (!DENSE) {
+        __shared__ T c1s[PXB_ST2_MAXTAP + 2 * (C::R - 1)];  // row factor with R-1 zeros on each side
+        if (tid < PXB_ST2_MAXTAP + 2 * (C::R - 1)) {
+            const int q = tid - (C::R - 1);
+            c1s[tid] = (q >= 0 && q < p.k1) ? T(p.coef1[q]) : T(0);
+        }
+        T c2[NV * VEC - VEC + 1];
+        for (int q = 0; q < NV * VEC - VEC + 1; ++q) c2[q] = T(p.coef2[q]);
+        for (int it = tid; it < p.bh * C::TXL; it += C::NT) pxb_st2_row_item<T, VEC, NV>(p, box, mid, it >> 5, (it & 31) * VEC, c2);
+        __syncthreads();
+        pxb_st2_col_item<T, VEC>(p, mid, yl, xl, c1s, acc);
+    } else {
+        __syncthreads();
+        pxb_st2_dense_item<T, VEC, NV>(p, box, mid, yl, xl, acc);
+    }
+    if (MODE != 2) {
+        pxb_st2_store<T, VEC>(p, out, img, y0, x0, yl, xl, acc);
+    } else {
+        double nrm[2] = {0.0, 0.0};
+        pxb_st2_store_prox<T, VEC>(p, out, img, y0, x0, yl, xl, acc, nrm);
+        if (p.norms) {  // one image per CTA: warp shuffle -> shared -> one atomic pair
+            __shared__ double red[2][C::NT / 32];
+            for (int o = 16; o > 0; o >>= 1) {
+                nrm[0] += __shfl_down_sync(0xffffffffu, nrm[0], o);
+                nrm[1] += __shfl_down_sync(0xffffffffu, nrm[1], o);
+            }
+            if ((tid & 31) == 0) { red[0][tid >> 5] = nrm[0]; red[1][tid >> 5] = nrm[1]; }
+            __syncthreads();
+            if (tid == 0) {
+                double s0 = 0.0, s1 = 0.0;
+                for (int i = 0; i < C::NT / 32; ++i) { s0 += red[0][i]; s1 += red[1][i]; }
+                const int64_t row = img / p.imgs_per_row;
+                atomicAdd(p.norms + 2 * row, s0);
+                atomicAdd(p.norms + 2 * row + 1, s1);
+            }
+        }
+    }
+}
+
+// Several consecutive tiles per CTA with the next tile's box in flight: the separable (load-latency-bound) instances.
 template <class T, int VEC, int NV, bool DENSE, int MODE>
 __global__ void __launch_bounds__(256, 4) k_stencil2d_tma(const __grid_constant__ PxbSt2P p, const __grid_constant__ CUtensorMap map,
                                                        const __grid_constant__ CUtensorMap map2, T* __restrict__ out) {
@@ -113,7 +193,7 @@ cudaError_t launch_mode(const PxbSt2P& p, const CUtensorMap& map, const CUtensor
     const size_t box_bytes = (size_t)((p.bh * p.bw + 31) / 32 * 32) * sizeof(T);
     const size_t smem = (p.tpc > 1 ? 2 : 1) * (MODE == 1 ? 2 : 1) * box_bytes + (DENSE ? (size_t)p.k1 * p.k2 * sizeof(T) : (size_t)p.bh * C::TX * sizeof(T));
     const unsigned grid = (unsigned)((int64_t)p.ngx * p.nty * p.nimg);
-    auto k = k_stencil2d_tma<T, VEC, NV, DENSE, MODE>;
+    auto k = p.tpc > 1 ? k_stencil2d_tma<T, VEC, NV, DENSE, MODE> : k_stencil2d_one<T, VEC, NV, DENSE, MODE>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
