@@ -53,25 +53,31 @@ __global__ void __launch_bounds__(256) k_stencil3d(const __grid_constant__ PxbSt
             for (int j = 0; j < VEC; ++j) ring[k][r][j] = T(0);
     const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
 
-    for (int pl = pl_lo; pl < pl_hi; ++pl) {
-        T t[C::R][VEC];
-        const bool have = pl >= ra && pl < rb;
-        if (have) {
-            const int k = pl - ra;
-            const T* box = stage0 + (k & 1) * box_elems;
-            mbar_wait(&bar[k & 1], (uint32_t)(k >> 1) & 1u);
-            for (int it = tid; it < p.s.bh * C::TXL; it += C::NT) pxb_st3_row_item<T, VEC, NV>(p, box, mid, it >> 5, (it & 31) * VEC, c2);
-            __syncthreads();  // intermediate complete; this stage's box is free
-            if (tid == 0 && pl + 2 < rb) issue(pl + 2);
-            pxb_st3_col_item<T, VEC>(p, mid, yl, xl, c1s, t);
-        } else {
-            for (int r = 0; r < C::R; ++r)
-                for (int j = 0; j < VEC; ++j) t[r][j] = T(0);
+    for (int base = pl_lo; base < pl_hi; base += K0) {
+#pragma unroll
+        for (int u = 0; u < K0; ++u) {  // plane base+u -> ring slot u (compile-time after unrolling)
+            const int pl = base + u;
+            if (pl < pl_hi) {
+                const bool have = pl >= ra && pl < rb;
+                const int q = pl - (K0 - 1 - p.c0);
+                T addv[C::R][VEC];
+                if (q >= m0) pxb_st3_load_add<T, VEC>(p, addv, b, q, y0, x0, yl, xl);  // in flight during the passes
+                if (have) {
+                    const int k = pl - ra;
+                    const T* box = stage0 + (k & 1) * box_elems;
+                    mbar_wait(&bar[k & 1], (uint32_t)(k >> 1) & 1u);
+                    for (int it = tid; it < p.s.bh * C::TXL; it += C::NT) pxb_st3_row_item<T, VEC, NV>(p, box, mid, it >> 5, (it & 31) * VEC, c2);
+                    __syncthreads();  // intermediate complete; this stage's box is free
+                    if (tid == 0 && pl + 2 < rb) issue(pl + 2);
+                    pxb_st3_col_item<T, VEC>(p, mid, yl, xl, c1s, ring[u]);
+                } else {
+                    for (int r = 0; r < C::R; ++r)
+                        for (int j = 0; j < VEC; ++j) ring[u][r][j] = T(0);
+                }
+                if (q >= m0) pxb_st3_store<T, VEC, K0>(p, out, c0v, ring, u, addv, b, q, y0, x0, yl, xl);
+                if (have && pl + 1 < rb) __syncthreads();  // `mid` is rewritten by the next plane's row pass
+            }
         }
-        pxb_st3_push<T, VEC, K0>(ring, t);
-        const int q = pl - (K0 - 1 - p.c0);
-        if (q >= m0) pxb_st3_store<T, VEC, K0>(p, out, c0v, ring, b, q, y0, x0, yl, xl);
-        if (have && pl + 1 < rb) __syncthreads();  // `mid` is rewritten by the next plane's row pass
     }
 }
 

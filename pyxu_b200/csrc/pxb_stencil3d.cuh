@@ -60,25 +60,17 @@ PXB_HD void pxb_st3_col_item(const PxbSt3P& p, const T* __restrict__ mid, int yl
     }
 }
 
-// push the newest filtered plane into the register ring and combine: out = sum_j c0[j] * ring[j]  (ring[K0-1] = newest)
+// The ring of the last K0 in-plane-filtered planes is indexed CIRCULARLY with compile-time slots: the marching loop is
+// unrolled K0 times, plane u of a group writes slot u, and the K0-tap combination reads slot (u + 1 + k) % K0 for tap k
+// (oldest plane first).  (A shifting ring cost K0*R*VEC register moves per plane: 7 of the 64 instructions per voxel.)
+// `addv`: the epilogue's `add` samples, loaded by the caller ahead of the passes (their latency was the top stall).
 template <class T, int VEC, int K0>
-PXB_HD void pxb_st3_push(T (*ring)[PxbSt3Cfg<T, VEC>::R][VEC], const T (*t)[VEC]) {
-    using C = PxbSt3Cfg<T, VEC>;
-    for (int k = 0; k + 1 < K0; ++k)
-        for (int r = 0; r < C::R; ++r)
-            for (int j = 0; j < VEC; ++j) ring[k][r][j] = ring[k + 1][r][j];
-    for (int r = 0; r < C::R; ++r)
-        for (int j = 0; j < VEC; ++j) ring[K0 - 1][r][j] = t[r][j];
-}
-
-template <class T, int VEC, int K0>
-PXB_HD void pxb_st3_store(const PxbSt3P& p, T* __restrict__ out, const T* c0v, const T (*ring)[PxbSt3Cfg<T, VEC>::R][VEC], int64_t b, int q, int y0, int x0,
-                          int yl, int xl) {
+PXB_HD void pxb_st3_store(const PxbSt3P& p, T* __restrict__ out, const T* c0v, const T (*ring)[PxbSt3Cfg<T, VEC>::R][VEC], int u, const T (*addv)[VEC],
+                          int64_t b, int q, int y0, int x0, int yl, int xl) {
     using C = PxbSt3Cfg<T, VEC>;
     const int x = x0 + xl;
     if (x >= p.s.n2) return;
     const T alpha = T(p.s.alpha), beta = T(p.s.beta);
-    const T* __restrict__ add = (const T*)p.s.add;
     const int64_t s0 = (int64_t)p.s.n1 * p.s.n2;
     for (int r = 0; r < C::R; ++r) {
         const int y = y0 + yl + r;
@@ -86,20 +78,31 @@ PXB_HD void pxb_st3_store(const PxbSt3P& p, T* __restrict__ out, const T* c0v, c
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) {
             T a = T(0);
-            for (int k = 0; k < K0; ++k) a += c0v[k] * ring[k][r][j];
+            for (int k = 0; k < K0; ++k) a += c0v[k] * ring[(u + 1 + k) % K0][r][j];
             o.v[j] = alpha * a;
+            if (p.s.add) o.v[j] += beta * addv[r][j];
         }
-        const int64_t inplane = (int64_t)y * p.s.n2 + x;
-        if (add) {  // `add` is dense (batch, n0, n1, n2): no ghost planes
-            const int64_t al = (b * p.n0 + q) * s0 + inplane;
-            if (p.s.add_period <= 0) {
-                const PxbVec<T, VEC> a = pxb_vload<T, VEC>(add + al);
-                for (int j = 0; j < VEC; ++j) o.v[j] += beta * a.v[j];
-            } else {
-                for (int j = 0; j < VEC; ++j) o.v[j] += beta * add[(al + j) % p.s.add_period];
-            }
+        pxb_vstore<T, VEC>(out + b * p.vol + (int64_t)q * s0 + (int64_t)y * p.s.n2 + x, o);
+    }
+}
+
+// the epilogue's `add` samples of output plane q for this thread (`add` is dense (batch, n0, n1, n2): no ghost planes)
+template <class T, int VEC>
+PXB_HD void pxb_st3_load_add(const PxbSt3P& p, T (*addv)[VEC], int64_t b, int q, int y0, int x0, int yl, int xl) {
+    using C = PxbSt3Cfg<T, VEC>;
+    const T* __restrict__ add = (const T*)p.s.add;
+    const int x = x0 + xl;
+    for (int r = 0; r < C::R; ++r) {
+        const int y = y0 + yl + r;
+        for (int j = 0; j < VEC; ++j) addv[r][j] = T(0);
+        if (!add || x >= p.s.n2 || y >= p.s.n1) continue;
+        const int64_t al = ((b * p.n0 + q) * (int64_t)p.s.n1 + y) * p.s.n2 + x;
+        if (p.s.add_period <= 0) {
+            const PxbVec<T, VEC> a = pxb_vload<T, VEC>(add + al);
+            for (int j = 0; j < VEC; ++j) addv[r][j] = a.v[j];
+        } else {
+            for (int j = 0; j < VEC; ++j) addv[r][j] = add[(al + j) % p.s.add_period];
         }
-        pxb_vstore<T, VEC>(out + b * p.vol + (int64_t)q * s0 + inplane, o);
     }
 }
 

@@ -75,7 +75,8 @@ struct PxbSpec {
     static constexpr int SCHEME = SCHEME_;  // PXB_SCHEME_*
     static constexpr int GK = GK_;          // -1 run time, else pxb_prox_kind
     static constexpr int HK = HK_;          // -1 run time, else pxb_dual_kind
-    static constexpr int FK = FK_;          // -1 run time, 1: f = alpha ||x + shift||^2 with a per-voxel shift array
+    static constexpr int FK = FK_;          // -1 run time, 1: f = alpha ||x + shift||^2 with a per-voxel shift array,
+                                            //  2: grad f handed over as a per-voxel array (CondatVu with a non-local f)
 };
 using PxbSpecAny = PxbSpec<PXB_SCHEME_ANY, -1, -1, -1>;
 

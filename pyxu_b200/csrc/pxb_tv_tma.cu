@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(32 * TY, 2)
         const int s = (m - R.mlo) % C::NSTAGE;
         T* st = stages + s * C::STAGE;
         uint64_t* bar = full + s;
-        const bool staged_shift = S::FK == 1 || tg.has_shift;
+        const bool staged_shift = S::FK >= 1 || tg.has_shift;
         const uint32_t bytes = C::BYTES_BOX * (3 + (staged_shift ? 1 : 0)) + C::BYTES_BOX1;
         mbar_expect_tx(bar, bytes);
         const int cc = it.c0 - VEC, cr = it.r0 - 1, cp = m + tg.gl;
@@ -137,6 +137,8 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
     };
     if (spec == 1) go(k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecFwdPos>);
     else if (spec == 2) go(k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecFwdNone>);
+    else if (spec == 3 && ALGO == PXB_CV) go(k_tv_iter_tma<T, VEC, TY, PXB_CV, NORMS, PxbSpecFwdPosG>);
+    else if (spec == 4 && ALGO == PXB_CV) go(k_tv_iter_tma<T, VEC, TY, PXB_CV, NORMS, PxbSpecFwdNoneG>);
     else go(k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecAny>);
     return 0;
 }

@@ -81,15 +81,21 @@ inline int pxb_tma_setup(const pxb_grad_desc& d, const pxb_pds_params& P, const 
 }
 
 // which compiled instance serves a problem: 1 / 2 = forward differences + L21 + per-voxel shifted squared-l2 data
-// term with g = positivity / none; 0 = the generic instance
+// term with g = positivity / none; 3 / 4 = the same with grad f handed over as an array (CondatVu); 0 = the generic instance
 using PxbSpecFwdPos = PxbSpec<PXB_SCHEME_FWD, PXB_PROX_POS, PXB_DUAL_L21, 1>;
 using PxbSpecFwdNone = PxbSpec<PXB_SCHEME_FWD, PXB_PROX_NONE, PXB_DUAL_L21, 1>;
+using PxbSpecFwdPosG = PxbSpec<PXB_SCHEME_FWD, PXB_PROX_POS, PXB_DUAL_L21, 2>;   // CondatVu, grad f array
+using PxbSpecFwdNoneG = PxbSpec<PXB_SCHEME_FWD, PXB_PROX_NONE, PXB_DUAL_L21, 2>;
 template <class T>
 inline int pxb_tma_pick_spec(const PxbTvCoef& cf, const PxbTvP<T>& q, const PxbTmaGeom& tg) {
     bool fwd = true;
     for (int k = 0; k < 3; ++k) fwd = fwd && cf.cm[k] == 0.0 && cf.cp[k] != 0.0;
-    if (!(fwd && q.hkind == PXB_DUAL_L21 && q.fkind == PXB_F_SQL2 && tg.has_shift)) return 0;
-    return q.gkind == PXB_PROX_POS ? 1 : (q.gkind == PXB_PROX_NONE ? 2 : 0);
+    if (!(fwd && q.hkind == PXB_DUAL_L21 && tg.has_shift)) return 0;
+    const int g = q.gkind == PXB_PROX_POS ? 1 : (q.gkind == PXB_PROX_NONE ? 2 : 0);
+    if (g == 0) return 0;
+    if (q.fkind == PXB_F_SQL2) return g;           // 1, 2
+    if (q.fkind == PXB_F_GRADARR) return 2 + g;    // 3, 4 (CondatVu only)
+    return 0;
 }
 
 template <class T, int VEC>
@@ -147,7 +153,7 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
     const PxbVec<T, W> old = pxb_vload<T, W>(st + C::OFF_U + i);
     PxbVec<T, W> sh;
     for (int j = 0; j < W; ++j) sh.v[j] = T(0);
-    if (S::FK == 1 || tg.has_shift) sh = pxb_vload<T, W>(st + C::OFF_S + i);
+    if (S::FK >= 1 || tg.has_shift) sh = pxb_vload<T, W>(st + C::OFF_S + i);
     else if (q.fkind == PXB_F_SQL2 && q.shift_mode == PXB_SHIFT_SCALAR) { for (int j = 0; j < W; ++j) sh.v[j] = q.shift[0]; }
     const int gk = pxb_gkind<S>(q);
     for (int j = 0; j < W; ++j) {
@@ -161,7 +167,8 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
             xo[j] = x;
         } else {
             T gf = T(0);
-            if (S::FK == 1 || q.fkind == PXB_F_SQL2) gf = (old.v[j] + sh.v[j]) * q.two_alpha;
+            if (S::FK == 2) gf = sh.v[j];
+            else if (S::FK == 1 || q.fkind == PXB_F_SQL2) gf = (old.v[j] + sh.v[j]) * q.two_alpha;
             else if (q.fkind == PXB_F_GRADARR) gf = sh.v[j];
             const T vv = old.v[j] - q.tau * gf - q.tau * kz[j];
             const T xt = pxb_prox_eval<T>(gk, q.gp0, q.gp1, vv, q.tau);

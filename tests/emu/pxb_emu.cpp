@@ -207,7 +207,7 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
             const int b = (int)it.b;
             int cu[5] = {it.c0 - VEC, it.r0 - 1, m + tg.gl, 0, b};
             emu_tma_box<T>(mu, C::BR, cu, st + C::OFF_U);
-            if (S::FK == 1 || tg.has_shift) { int cs[5] = {cu[0], cu[1], cu[2], 0, tg.sh_batched ? b : 0}; emu_tma_box<T>(ms, C::BR, cs, st + C::OFF_S); }
+            if (S::FK >= 1 || tg.has_shift) { int cs[5] = {cu[0], cu[1], cu[2], 0, tg.sh_batched ? b : 0}; emu_tma_box<T>(ms, C::BR, cs, st + C::OFF_S); }
             emu_tma_box<T>(mz, C::BR, cu, st + C::OFF_Z0);
             int c2[5] = {cu[0], cu[1], cu[2], 2, b};
             emu_tma_box<T>(mz, C::BR, c2, st + C::OFF_Z2);
@@ -255,6 +255,10 @@ static int t_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
     }
     EMU_TMA_TRY(PxbSpecFwdPos, 1)
     EMU_TMA_TRY(PxbSpecFwdNone, 2)
+    if (algo == PXB_CV) {
+        EMU_TMA_TRY(PxbSpecFwdPosG, 3)
+        EMU_TMA_TRY(PxbSpecFwdNoneG, 4)
+    }
     EMU_TMA_TRY(PxbSpecAny, 0)
 #undef EMU_TMA_TRY
     return -131;
@@ -469,13 +473,14 @@ static void t_st3_run(const PxbSt3P& p, const T* in, T* out) {
                             for (int it = 0; it < p.s.bh * C::TXL; ++it) pxb_st3_row_item<T, VEC, NV>(p, box.data(), mid.data(), it / C::TXL, (it % C::TXL) * VEC, c2);
                         }
                         const int q = pl - (K0 - 1 - p.c0);
+                        const int u = (pl - pl_lo) % K0;  // ring slot of this plane, as in the unrolled device loop
                         for (int tid = 0; tid < C::NT; ++tid) {
                             const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
-                            T t[C::R][VEC];
-                            if (have) pxb_st3_col_item<T, VEC>(p, mid.data(), yl, xl, c1, t);
-                            else std::memset(t, 0, sizeof(t));
-                            pxb_st3_push<T, VEC, K0>(rings[tid].v, t);
-                            if (q >= m0) pxb_st3_store<T, VEC, K0>(p, out, c0v, rings[tid].v, b, q, y0, x0, yl, xl);
+                            T addv[C::R][VEC];
+                            if (q >= m0) pxb_st3_load_add<T, VEC>(p, addv, b, q, y0, x0, yl, xl);
+                            if (have) pxb_st3_col_item<T, VEC>(p, mid.data(), yl, xl, c1, rings[tid].v[u]);
+                            else std::memset(rings[tid].v[u], 0, sizeof(rings[tid].v[u]));
+                            if (q >= m0) pxb_st3_store<T, VEC, K0>(p, out, c0v, rings[tid].v, u, addv, b, q, y0, x0, yl, xl);
                         }
                     }
                 }

@@ -199,6 +199,14 @@ def test_tma_form_batched_shift_modes_gradarr(scheme):
     two_pass(K.ALGO_CV, d, P, ua, za, None)
     ub, zb = one_pass(K.ALGO_CV, d, P, u, z, None, chunk=0, form="tma")
     assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13
+    for gk in (K.PROX_POS, K.PROX_NONE):  # the instances specialised for CondatVu + grad f array (forward scheme) / the generic one
+        P = E.pds_params(0.3, 0.25, 0.8, gspec=(gk, 0.0, 0.0), fkind=K.F_GRADARR, garr=garr, hkind=K.DUAL_L21, lam=0.2)
+        ua, za = u.copy(), z.copy()
+        nxa, nza, nxb, nzb = (np.zeros(2 * batch) for _ in range(4))
+        two_pass(K.ALGO_CV, d, P, ua, za, None, nxa, nza)
+        ub, zb = one_pass(K.ALGO_CV, d, P, u, z, None, nxb, nzb, chunk=3, form="tma")
+        assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13
+        assert np.allclose(nxa, nxb, rtol=1e-10) and np.allclose(nza, nzb, rtol=1e-10)
 
 
 def test_tma_form_golden_3d():
