@@ -45,12 +45,14 @@ __global__ void __launch_bounds__(256) k_stencil2d_one(const __grid_constant__ P
         const T* __restrict__ ck = (const T*)p.coef;
         for (int i = tid; i < p.k1 * p.k2; i += C::NT) mid[i] = pxb_st2_dense_coef<T>(p, ck, i);
     }
+    const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
+    PxbSt2Epi<T, VEC> epi;
+    pxb_st2_load_epi<T, VEC>(p, epi, img, y0, x0, yl, xl);  // in flight while the box arrives
     mbar_wait(&bar, 0);
     if (MODE == 1) {
         for (int it = tid; it < p.bh * p.bw / VEC; it += C::NT) pxb_st2_combine_item<T, VEC>(p, box, box2, it);
         __syncthreads();
     }
-    const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
     T acc[C::R][VEC];
     if (!DENSE) {
         __shared__ T c1s[PXB_ST2_MAXTAP + 2 * (C::R - 1)];  // row factor with R-1 zeros on each side
@@ -68,10 +70,10 @@ __global__ void __launch_bounds__(256) k_stencil2d_one(const __grid_constant__ P
         pxb_st2_dense_item<T, VEC, NV>(p, box, mid, yl, xl, acc);
     }
     if (MODE != 2) {
-        pxb_st2_store<T, VEC>(p, out, img, y0, x0, yl, xl, acc);
+        pxb_st2_store<T, VEC>(p, out, epi, img, y0, x0, yl, xl, acc);
     } else {
         double nrm[2] = {0.0, 0.0};
-        pxb_st2_store_prox<T, VEC>(p, out, img, y0, x0, yl, xl, acc, nrm);
+        pxb_st2_store_prox<T, VEC>(p, out, epi, img, y0, x0, yl, xl, acc, nrm);
         if (p.norms) {  // one image per CTA: warp shuffle -> shared -> one atomic pair
             __shared__ double red[2][C::NT / 32];
             for (int o = 16; o > 0; o >>= 1) {
@@ -146,6 +148,9 @@ __global__ void __launch_bounds__(256, 4) k_stencil2d_tma(const __grid_constant_
 
     for (int t = 0; t < ntile; ++t) {
         T* box = stage0 + (t & 1) * NBOX * box_elems;
+        const int x0 = (tx0 + t) * C::TX;
+        PxbSt2Epi<T, VEC> epi;
+        pxb_st2_load_epi<T, VEC>(p, epi, img, y0, x0, yl, xl);  // in flight while the box arrives / the passes run
         mbar_wait(&bar[t & 1], (uint32_t)(t >> 1) & 1u);
         if (MODE == 1) {
             for (int it = tid; it < p.bh * p.bw / VEC; it += C::NT) pxb_st2_combine_item<T, VEC>(p, box, box + box_elems, it);
@@ -161,9 +166,8 @@ __global__ void __launch_bounds__(256, 4) k_stencil2d_tma(const __grid_constant_
             if (t == 0) __syncthreads();                      // coefficients staged
             pxb_st2_dense_item<T, VEC, NV>(p, box, mid, yl, xl, acc);
         }
-        const int x0 = (tx0 + t) * C::TX;
-        if (MODE != 2) pxb_st2_store<T, VEC>(p, out, img, y0, x0, yl, xl, acc);
-        else pxb_st2_store_prox<T, VEC>(p, out, img, y0, x0, yl, xl, acc, nrm);
+        if (MODE != 2) pxb_st2_store<T, VEC>(p, out, epi, img, y0, x0, yl, xl, acc);
+        else pxb_st2_store_prox<T, VEC>(p, out, epi, img, y0, x0, yl, xl, acc, nrm);
         if (t + 1 < ntile) {
             __syncthreads();                                  // separable: `mid` is free again; dense: this stage's box is
             if (DENSE && tid == 0 && t + 2 < ntile) issue(t + 2);

@@ -111,29 +111,83 @@ PXB_HD void pxb_st2_dense_item(const PxbSt2P& p, const T* __restrict__ box, cons
     }
 }
 
+// The epilogue's global operands (`add`; x / x_prev of the prox step) are loaded by pxb_st2_load_epi BEFORE the thread
+// waits for its TMA box, so their DRAM latency overlaps the box load and the passes (ncu on the first version: the
+// epilogue loads were the top stall, long-scoreboard, of every instance with an epilogue operand).
+template <class T, int VEC>
+struct PxbSt2Epi {
+    T a[PxbSt2Cfg<T, VEC>::R][VEC];  // add            | x      (prox step)
+    T b[PxbSt2Cfg<T, VEC>::R][VEC];  //                | x_prev (prox step)
+};
+
+template <class T, int VEC>
+PXB_HD void pxb_st2_load_epi(const PxbSt2P& p, PxbSt2Epi<T, VEC>& e, int64_t img, int y0, int x0, int yl, int xl) {
+    using C = PxbSt2Cfg<T, VEC>;
+    const int x = x0 + xl;
+    const T* __restrict__ pa = (const T*)(p.epi == 1 ? p.e1 : p.add);
+    const T* __restrict__ pb = (const T*)(p.epi == 1 ? p.e2 : nullptr);
+    for (int r = 0; r < C::R; ++r) {
+        for (int j = 0; j < VEC; ++j) e.a[r][j] = e.b[r][j] = T(0);
+        const int y = y0 + yl + r;
+        if (x >= p.n2 || y >= p.n1) continue;
+        const int64_t lin = (img * p.n1 + y) * (int64_t)p.n2 + x;
+        if (pa) {
+            if (p.epi == 1 || p.add_period <= 0) {
+                const PxbVec<T, VEC> v = pxb_vload<T, VEC>(pa + lin);
+                for (int j = 0; j < VEC; ++j) e.a[r][j] = v.v[j];
+            } else {
+                for (int j = 0; j < VEC; ++j) e.a[r][j] = pa[(lin + j) % p.add_period];
+            }
+        }
+        if (pb) {
+            const PxbVec<T, VEC> v = pxb_vload<T, VEC>(pb + lin);
+            for (int j = 0; j < VEC; ++j) e.b[r][j] = v.v[j];
+        }
+    }
+}
+
 // epilogue + store of one thread's R x VEC outputs (tile origin (y0, x0) of image `img`)
 template <class T, int VEC>
-PXB_HD void pxb_st2_store(const PxbSt2P& p, T* __restrict__ out, int64_t img, int y0, int x0, int yl, int xl, T (*acc)[VEC]) {
+PXB_HD void pxb_st2_store(const PxbSt2P& p, T* __restrict__ out, const PxbSt2Epi<T, VEC>& e, int64_t img, int y0, int x0, int yl, int xl, T (*acc)[VEC]) {
     using C = PxbSt2Cfg<T, VEC>;
     const int x = x0 + xl;
     if (x >= p.n2) return;
     const T alpha = T(p.alpha), beta = T(p.beta);
-    const T* __restrict__ add = (const T*)p.add;
     for (int r = 0; r < C::R; ++r) {
         const int y = y0 + yl + r;
         if (y >= p.n1) break;
         const int64_t lin = (img * p.n1 + y) * (int64_t)p.n2 + x;
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = alpha * acc[r][j];
-        if (add) {
-            if (p.add_period <= 0) {
-                const PxbVec<T, VEC> a = pxb_vload<T, VEC>(add + lin);
-                for (int j = 0; j < VEC; ++j) o.v[j] += beta * a.v[j];
-            } else {
-                for (int j = 0; j < VEC; ++j) o.v[j] += beta * add[(lin + j) % p.add_period];
+        if (p.add)
+            for (int j = 0; j < VEC; ++j) o.v[j] += beta * e.a[r][j];
+        pxb_vstore<T, VEC>(out + lin, o);
+    }
+}
+
+// proximal-gradient epilogue for one thread's R x VEC outputs; returns the RelError partial sums in nrm[0..1]
+template <class T, int VEC>
+PXB_HD void pxb_st2_store_prox(const PxbSt2P& p, T* __restrict__ out, const PxbSt2Epi<T, VEC>& e, int64_t img, int y0, int x0, int yl, int xl,
+                               T (*acc)[VEC], double* nrm) {
+    using C = PxbSt2Cfg<T, VEC>;
+    const int x = x0 + xl;
+    if (x >= p.n2) return;
+    const T alpha = T(p.alpha), ea = T(p.ea), eb = T(p.eb), tau = T(p.tau), gp0 = T(p.gp0), gp1 = T(p.gp1);
+    for (int r = 0; r < C::R; ++r) {
+        const int y = y0 + yl + r;
+        if (y >= p.n1) break;
+        const int64_t lin = (img * p.n1 + y) * (int64_t)p.n2 + x;
+        PxbVec<T, VEC> o;
+        for (int j = 0; j < VEC; ++j) {
+            const T v = ea * e.a[r][j] + eb * e.b[r][j] + alpha * acc[r][j];
+            o.v[j] = pxb_prox_eval<T>(p.gkind, gp0, gp1, v, tau);
+            if (p.norms) {
+                const double dd = (double)o.v[j] - (double)e.a[r][j];
+                nrm[0] += dd * dd;
+                nrm[1] += (double)e.a[r][j] * (double)e.a[r][j];
             }
         }
-        pxb_vstore<T, VEC>(out + lin, o);
+        pxb_vstore<T, VEC>(out + lin, o);  // (`out` may be the x_prev buffer: its samples were read into e.b above)
     }
 }
 
@@ -142,37 +196,6 @@ template <class T>
 PXB_HD T pxb_st2_dense_coef(const PxbSt2P& p, const T* __restrict__ ck, int i) {
     const int q1 = i / p.k2, q = i - q1 * p.k2;
     return q >= p.extra ? ck[q1 * p.k2src + q - p.extra] : T(0);
-}
-
-// proximal-gradient epilogue for one thread's R x VEC outputs; returns the RelError partial sums in nrm[0..1]
-template <class T, int VEC>
-PXB_HD void pxb_st2_store_prox(const PxbSt2P& p, T* __restrict__ out, int64_t img, int y0, int x0, int yl, int xl, T (*acc)[VEC], double* nrm) {
-    using C = PxbSt2Cfg<T, VEC>;
-    const int x = x0 + xl;
-    if (x >= p.n2) return;
-    const T alpha = T(p.alpha), ea = T(p.ea), eb = T(p.eb), tau = T(p.tau), gp0 = T(p.gp0), gp1 = T(p.gp1);
-    const T* __restrict__ e1 = (const T*)p.e1;
-    const T* __restrict__ e2 = (const T*)p.e2;
-    for (int r = 0; r < C::R; ++r) {
-        const int y = y0 + yl + r;
-        if (y >= p.n1) break;
-        const int64_t lin = (img * p.n1 + y) * (int64_t)p.n2 + x;
-        const PxbVec<T, VEC> a = pxb_vload<T, VEC>(e1 + lin);
-        PxbVec<T, VEC> b;
-        for (int j = 0; j < VEC; ++j) b.v[j] = T(0);
-        if (e2) b = pxb_vload<T, VEC>(e2 + lin);  // read before `out` (which may be the same buffer) is written
-        PxbVec<T, VEC> o;
-        for (int j = 0; j < VEC; ++j) {
-            const T v = ea * a.v[j] + eb * b.v[j] + alpha * acc[r][j];
-            o.v[j] = pxb_prox_eval<T>(p.gkind, gp0, gp1, v, tau);
-            if (p.norms) {
-                const double dd = (double)o.v[j] - (double)a.v[j];
-                nrm[0] += dd * dd;
-                nrm[1] += (double)a.v[j] * (double)a.v[j];
-            }
-        }
-        pxb_vstore<T, VEC>(out + lin, o);
-    }
 }
 
 // prologue: window = pa*box + pb*box2, vector item `it` of the (bh x bw) window

@@ -298,12 +298,14 @@ static void t_st2_nv(const PxbSt2P& p, const T* in, const T* in2, T* out) {
                     T acc[C::R][VEC];
                     if (p.dense) pxb_st2_dense_item<T, VEC, NV>(p, box.data(), mid.data(), yl, xl, acc);
                     else pxb_st2_col_item<T, VEC>(p, mid.data(), yl, xl, c1, acc);
+                    PxbSt2Epi<T, VEC> epi;
+                    pxb_st2_load_epi<T, VEC>(p, epi, img, y0, x0, yl, xl);
                     if (p.epi == 1) {
                         double nrm[2] = {0.0, 0.0};
-                        pxb_st2_store_prox<T, VEC>(p, out, img, y0, x0, yl, xl, acc, nrm);
+                        pxb_st2_store_prox<T, VEC>(p, out, epi, img, y0, x0, yl, xl, acc, nrm);
                         if (p.norms) { p.norms[2 * (img / p.imgs_per_row)] += nrm[0]; p.norms[2 * (img / p.imgs_per_row) + 1] += nrm[1]; }
                     } else {
-                        pxb_st2_store<T, VEC>(p, out, img, y0, x0, yl, xl, acc);
+                        pxb_st2_store<T, VEC>(p, out, epi, img, y0, x0, yl, xl, acc);
                     }
                 }
             }
