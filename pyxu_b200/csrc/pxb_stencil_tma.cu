@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) k_stencil2d_one(const __grid_constant__ P
     }
     const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
     PxbSt2Epi<T, VEC> epi;
-    pxb_st2_load_epi<T, VEC>(p, epi, img, y0, x0, yl, xl);  // in flight while the box arrives
+    if (DENSE) pxb_st2_prefetch_epi<T, VEC>(p, img, y0, x0, yl, xl);   // towards L2 while the box arrives
+    else pxb_st2_load_epi<T, VEC>(p, epi, img, y0, x0, yl, xl);        // into registers, in flight while the box arrives
     mbar_wait(&bar, 0);
     if (MODE == 1) {
         for (int it = tid; it < p.bh * p.bw / VEC; it += C::NT) pxb_st2_combine_item<T, VEC>(p, box, box2, it);
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(256) k_stencil2d_one(const __grid_constant__ P
     } else {
         __syncthreads();
         pxb_st2_dense_item<T, VEC, NV>(p, box, mid, yl, xl, acc);
+        pxb_st2_load_epi<T, VEC>(p, epi, img, y0, x0, yl, xl);
     }
     if (MODE != 2) {
         pxb_st2_store<T, VEC>(p, out, epi, img, y0, x0, yl, xl, acc);

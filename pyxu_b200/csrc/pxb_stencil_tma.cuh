@@ -120,6 +120,31 @@ struct PxbSt2Epi {
     T b[PxbSt2Cfg<T, VEC>::R][VEC];  //                | x_prev (prox step)
 };
 
+// L2 prefetch of the same operands, for the dense (register-hungry, FMA-bound) instances: holding the operands in
+// registers across the accumulation cost them occupancy (FISTA 5x5: 1.76 -> 1.91 ms), a prefetch costs nothing.
+PXB_HD void pxb_prefetch_l2(const void* ptr) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;
+#endif
+}
+template <class T, int VEC>
+PXB_HD void pxb_st2_prefetch_epi(const PxbSt2P& p, int64_t img, int y0, int x0, int yl, int xl) {
+    using C = PxbSt2Cfg<T, VEC>;
+    const int x = x0 + xl;
+    const T* __restrict__ pa = (const T*)(p.epi == 1 ? p.e1 : p.add);
+    const T* __restrict__ pb = (const T*)(p.epi == 1 ? p.e2 : nullptr);
+    if (x >= p.n2 || (!pa && !pb) || (p.epi != 1 && p.add_period > 0)) return;
+    for (int r = 0; r < C::R; ++r) {
+        const int y = y0 + yl + r;
+        if (y >= p.n1) break;
+        const int64_t lin = (img * p.n1 + y) * (int64_t)p.n2 + x;
+        if (pa) pxb_prefetch_l2(pa + lin);
+        if (pb) pxb_prefetch_l2(pb + lin);
+    }
+}
+
 template <class T, int VEC>
 PXB_HD void pxb_st2_load_epi(const PxbSt2P& p, PxbSt2Epi<T, VEC>& e, int64_t img, int y0, int x0, int yl, int xl) {
     using C = PxbSt2Cfg<T, VEC>;
