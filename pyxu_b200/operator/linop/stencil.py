@@ -192,6 +192,16 @@ class Stencil(pxo.SquareOp):
             else:
                 return None
         if dense is not None:
+            # a 2-D kernel that is an outer product (every Gaussian / box PSF) runs through the separable passes:
+            # 2*k taps per sample instead of k*k, and the kernel becomes memory- instead of FMA-bound.  The test is
+            # on the singular values, at the resolution of the kernel's own dtype.
+            k2d, c1, c2 = dense
+            if min(k2d.shape) > 1 and max(k2d.shape) <= 16:
+                u, sv, vt = np.linalg.svd(np.asarray(k2d, dtype=np.float64))
+                if sv[0] > 0 and sv[1] <= 8 * np.finfo(self._dtype).eps * sv[0]:
+                    t1 = (u[:, 0] * sv[0]).astype(self._dtype)
+                    t2 = vt[0].astype(self._dtype)
+                    return axis0, ("sep", t1, c1, t2, c2), scale
             return axis0, ("dense",) + dense, scale
         if f1 is None and f2 is None:
             return None

@@ -66,6 +66,19 @@ def test_tiled_epilogue_and_adjoint_identity():
     assert relerr(out, 0.5 * E.stencil_run(op, xs, False) - y) < 1e-13
 
 
+def test_rank_one_dense_kernels_take_the_separable_passes():
+    g9 = gauss(9, 1.7)
+    op = pxo.Stencil(arg_shape=(40, 64), kernel=np.outer(g9, g9), center=(4, 4), mode="constant")
+    assert op._tiled_plan(False)[1][0] == "sep" and op._tiled_plan(True)[1][0] == "sep"
+    x = np.random.default_rng(0).standard_normal(op.dim)
+    for adj in (False, True):
+        assert relerr(E.stencil_run_tiled(op, x, adj), E.stencil_run(op, x, adj)) < 1e-13
+    full = pxo.Stencil(arg_shape=(40, 64), kernel=np.outer(g9, g9) + 0.01 * np.eye(9), center=(4, 4), mode="constant")
+    assert full._tiled_plan(False)[1][0] == "dense"
+    f32 = pxo.Stencil(arg_shape=(40, 64), kernel=np.outer(g9, g9).astype(np.float32), center=(4, 4), mode="constant")
+    assert f32._tiled_plan(False)[1][0] == "sep"  # rank 1 at fp32 resolution
+
+
 def test_tiled_not_applicable():
     op = pxo.Stencil(arg_shape=(20, 24), kernel=np.ones((3, 3)), center=(1, 1), mode="reflect")
     assert op._tiled_plan(False) is None
@@ -87,7 +100,7 @@ def test_fista_two_pass_form(dense, dtype):
     rng = np.random.default_rng(4)
     shape, batch = (37, 72), 3
     g1, g2 = gauss(5, 1.0), gauss(5, 1.3)
-    kern = np.outer(g1, g2).astype(dtype) if dense else [g1.astype(dtype), g2.astype(dtype)]
+    kern = (np.outer(g1, g2) + 0.03 * np.eye(5)).astype(dtype) if dense else [g1.astype(dtype), g2.astype(dtype)]  # full rank: dense instance
     op = pxo.Stencil(arg_shape=shape, kernel=kern, center=(2, 1), mode="constant")
     x = rng.standard_normal((batch, op.dim)).astype(dtype)
     xp = rng.standard_normal((batch, op.dim)).astype(dtype)

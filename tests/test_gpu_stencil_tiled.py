@@ -74,7 +74,7 @@ def test_pgd_two_pass_fista_equals_generic_path(dtype, tol):
     shape, batch = (96, 128), 4
     N = shape[0] * shape[1]
     rng = np.random.default_rng(0)
-    k = np.outer(gauss(5, 1.0), gauss(5, 1.2)).astype(dtype)
+    k = (np.outer(gauss(5, 1.0), gauss(5, 1.2)) + 0.02 * np.eye(5)).astype(dtype)  # full rank: the dense instances
     y = rng.random((batch, N)).astype(dtype)
 
     def build():

@@ -114,7 +114,10 @@ def main():
         lo, hi = split_batch(args.batch, world)[rank]
         B = hi - lo
         g1 = gauss(5, 1.0)
-        A = pxo.Stencil(arg_shape=shape, kernel=np.outer(g1, g1), center=(2, 2), mode="constant")
+        psf = np.outer(g1, g1)
+        if args.dense:  # a PSF that is not an outer product: the register-blocked dense instance
+            psf = psf + 0.02 * np.eye(5, dtype=np.float32)
+        A = pxo.Stencil(arg_shape=shape, kernel=psf, center=(2, 2), mode="constant")
         y = torch.rand(B, N, device="cuda", generator=gen)
         f = (0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y)) * A
         g = 0.02 * pxo.L1Norm(dim=N)
@@ -122,7 +125,7 @@ def main():
         slv.fit(x0=y, mode=Mode.MANUAL, stop_crit=pxst.ManualStop(), tau=1.0 / float(A.lipschitz) ** 2)
         ms, launches = timed(slv.m_step, K, W, world)
         assert slv._fused is not None, "the two-pass tiled FISTA form did not apply"
-        nvox, name = args.batch * N, f"batch of {args.batch} {n}x{n} images, PGD (FISTA) L1 deconvolution, dense 5x5 Stencil, batch split over {world} GPU(s)"
+        nvox, name = args.batch * N, f"batch of {args.batch} {n}x{n} images, PGD (FISTA) L1 deconvolution, 5x5 Stencil ({'full-rank PSF: dense instance' if args.dense else 'Gaussian PSF given as a 2-D array: rank 1, separable passes'}), batch split over {world} GPU(s)"
         bpv = 16 + 16  # r = A y - b: read x, x_prev, b, write r;  x_new = prox(y - tau A^T r): read r, x, x_prev, write x_new
     if rank == 0:
         per = ms / K
