@@ -418,7 +418,7 @@ class SlabCondatVuDeblur:
     """
 
     def __init__(self, shape, psf, center, y_full=None, y_local=None, lam=0.05, positivity=True, dtype=torch.float32, rho=1.0,
-                 tau=None, sigma=None, group=None):
+                 tau=None, sigma=None, group=None, overlap=True):
         import numpy as np
 
         from .operator.linop.diff import Gradient
@@ -465,16 +465,12 @@ class SlabCondatVuDeblur:
         self.Aop._slab_dcode = A.dcode(self.r)
         self._plans = {adj: self.Aop._tiled_plan(adj) for adj in (False, True)}
         assert all(p is not None and p[0] is not None for p in self._plans.values()), "expected a separable PSF with a factor along axis 0"
+        self._alloc = alloc
         self._slab = K.Slab(1 if self.hx.lo is not None else 0, 1 if self.hx.hi is not None else 0, H, alloc)
-        self._desc2d = {}
-        for adj, add in ((False, self.neg_y), (True, None)):
-            d, _ = self.Aop._tiled_desc(self.r[0, own], adj, alpha=1.0, beta=1.0 if add is not None else 0.0, add=add)
-            d.nimg = n0
-            self._desc2d[adj] = d
-        # single-pass separable 3-D kernel (marching, register ring) when the PSF is inside its envelope
-        self._desc3d = {False: self.Aop._desc3d(A.dcode(self.r), False, 1, 1.0, 1.0, self.neg_y, slab=self._slab, shape0=n0),
-                        True: self.Aop._desc3d(A.dcode(self.r), True, 1, slab=self._slab, shape0=n0)}
-        self.single_pass = all(v is not None for v in self._desc3d.values())
+        self._cache = {}   # descriptors per (kind, adjoint / parity, p0, p1): built once
+        self.single_pass = self.Aop._desc3d(A.dcode(self.r), False, 1, slab=self._slab, shape0=n0) is not None
+        self.edge = max(H, min(8, n0 // 4))  # planes of the boundary launches that precede each exchange
+        self.overlap = bool(overlap) and self.world > 1 and n0 >= 4 * self.edge
         self._gdesc = self.K._desc(1, A.dcode(self.r), slab=self._slab, shape0=n0)
         # z0 = K x0 needs x0's ghost planes
         self._wait(self._exchange([(self._xb[0][0], H, H)]))
@@ -516,44 +512,91 @@ class SlabCondatVuDeblur:
                     ops.append(dist.P2POp(dist.irecv, buf[H + n0 : H + n0 + down], self.hx.hi, self.group))
         return dist.batch_isend_irecv(ops) if ops else []
 
-    def _stencil(self, adjoint, src, dst):
-        """dst(owned planes) = A src (or A^T src), reading src's ghost planes: one marching pass (pxb_stencil3d_apply), or
-        axis-0 streaming pass + tiled in-plane pass outside its envelope."""
-        if self.single_pass:
-            rc = K.lib().pxb_stencil3d_apply(C.byref(self._desc3d[adjoint]), self._p(src, 0), self._p(dst, 0), A.stream())
-            if rc == 0:
-                return
-            if rc != -3:
-                K.check(rc, "pxb_stencil3d_apply")
-            self.single_pass = False
-        axis0 = self._plans[adjoint][0]
-        self.Aop._axis0_pass(axis0, self._p(src, 0), self._p(self.tmp, 0), 1, slab=self._slab, shape0=self.n0)
-        rc = K.lib().pxb_stencil2d_apply(C.byref(self._desc2d[adjoint]), self._p(self.tmp, 0), self._p(dst, 0), A.stream())
-        K.check(rc, "pxb_stencil2d_apply")
+    def _sub_slab(self, p0, p1):
+        """Slab flags of a launch restricted to owned planes [p0, p1): an interior cut is an open side."""
+        lo = 1 if (p0 > 0 or self.hx.lo is not None) else 0
+        hi = 1 if (p1 < self.n0 or self.hx.hi is not None) else 0
+        return K.Slab(lo, hi, self.H, self._alloc)
+
+    def _stencil(self, adjoint, src, dst, p0=0, p1=None):
+        """dst[p0:p1] = (A src - y | A^T src)[p0:p1], reading src's neighbouring / ghost planes: one marching pass
+        (pxb_stencil3d_apply), or axis-0 streaming pass + tiled in-plane pass outside its envelope."""
+        p1 = self.n0 if p1 is None else p1
+        key = ("st", adjoint, p0, p1)
+        c = self._cache.get(key)
+        if c is None:
+            slab = self._sub_slab(p0, p1)
+            add = None if adjoint else self.neg_y[p0:p1]
+            d3 = self.Aop._desc3d(A.dcode(self.r), adjoint, 1, 1.0, 0.0 if adjoint else 1.0, add, slab=slab, shape0=p1 - p0) if self.single_pass else None
+            d2 = None
+            if d3 is None:
+                own = slice(self.H + p0, self.H + p1)
+                d2, _ = self.Aop._tiled_desc(self.r[0, own], adjoint, alpha=1.0, beta=0.0 if adjoint else 1.0, add=add)
+                d2.nimg = p1 - p0
+            c = self._cache[key] = (d3, d2, slab, self._plans[adjoint][0])
+        d3, d2, slab, axis0 = c
+        if d3 is not None:
+            rc = K.lib().pxb_stencil3d_apply(C.byref(d3), self._p(src, 0, p0), self._p(dst, 0, p0), A.stream())
+            if rc == -3:  # outside the marching kernel's envelope (e.g. an even number of taps along z): two passes from now on
+                self.single_pass = False
+                self._cache = {k: v for k, v in self._cache.items() if k[0] != "st"}
+                return self._stencil(adjoint, src, dst, p0, p1)
+            K.check(rc, "pxb_stencil3d_apply")
+            return
+        self.Aop._axis0_pass(axis0, self._p(src, 0, p0), self._p(self.tmp, 0, p0), 1, slab=slab, shape0=p1 - p0)
+        K.check(K.lib().pxb_stencil2d_apply(C.byref(d2), self._p(self.tmp, 0, p0), self._p(dst, 0, p0), A.stream()), "pxb_stencil2d_apply")
+
+    def _iter(self, src, dst, nx, nz, p0=0, p1=None):
+        p1 = self.n0 if p1 is None else p1
+        key = ("it", src, p0, p1)
+        c = self._cache.get(key)
+        if c is None:
+            gd = self.K._desc(1, A.dcode(self.r), slab=self._sub_slab(p0, p1), shape0=p1 - p0)
+            p = K.PdsParams()
+            p.tau, p.sigma, p.rho = self.tau, self.sigma, self.rho
+            p.g = K.ProxSpec(K.PROX_POS if self.positivity else K.PROX_NONE, 0, 0.0, 0.0)
+            f = K.FTerm()
+            f.kind, f.garr = K.F_GRADARR, self._p(self.garr, 0, p0).value
+            p.f = f
+            p.hkind, p.lam = K.DUAL_L21, self.lam
+            xs, zs, xd, zd = self._xb[src], self._zb[src], self._xb[dst], self._zb[dst]
+            c = self._cache[key] = (gd, p, self._p(xs, 0, p0), self._p(zs, 0, p0), self._p(xd, 0, p0), self._p(zd, 0, p0))
+        gd, p, a0, a1, a2, a3 = c
+        rc = K.lib().pxb_pds_iter(K.ALGO_CV, C.byref(gd), C.byref(p), a0, a1, a2, a3, None, A.ptr(nx), A.ptr(nz), A.stream())
+        K.check(rc, "pxb_pds_iter")
+
+    def _staged(self, fn, exchange_items):
+        """One stage of the iteration: `fn(p0, p1)` on the boundary chunks, their planes sent on the side stream while
+        `fn` runs on the interior; the next stage starts once the ghost planes have arrived."""
+        n0, e = self.n0, self.edge
+        main = torch.cuda.current_stream()
+        if self.overlap:
+            lo, hi = (e if self.hx.lo is not None else 0), (n0 - e if self.hx.hi is not None else n0)
+            if lo:
+                fn(0, lo)
+            if hi < n0:
+                fn(hi, n0)
+            self.comm.wait_stream(main)
+            with torch.cuda.stream(self.comm):
+                self._wait(self._exchange(exchange_items))
+            fn(lo, hi)
+            main.wait_stream(self.comm)
+        else:
+            fn(0, n0)
+            self._wait(self._exchange(exchange_items))
 
     def step(self, want_norms=False):
-        H, n0 = self.H, self.n0
+        H = self.H
         src, dst = self.cur, 1 - self.cur
-        xs, zs, xd, zd = self._xb[src], self._zb[src], self._xb[dst], self._zb[dst]
+        xs, xd, zd = self._xb[src], self._xb[dst], self._zb[dst]
         nrm = nx = nz = None
         if want_norms:
             nrm = torch.zeros((2, 1, 2), dtype=torch.float64, device=self.dev)
             nx, nz = nrm[0], nrm[1]
-        self._stencil(False, xs, self.r)                                   # r = A x - y
-        self._wait(self._exchange([(self.r[0], H, H)]))
-        self._stencil(True, self.r, self.garr)                             # grad f = A^T r
-        self._wait(self._exchange([(self.garr[0], 0, 1)]))
-        p = K.PdsParams()
-        p.tau, p.sigma, p.rho = self.tau, self.sigma, self.rho
-        p.g = K.ProxSpec(K.PROX_POS if self.positivity else K.PROX_NONE, 0, 0.0, 0.0)
-        f = K.FTerm()
-        f.kind, f.garr = K.F_GRADARR, self._p(self.garr, 0).value
-        p.f = f
-        p.hkind, p.lam = K.DUAL_L21, self.lam
-        rc = K.lib().pxb_pds_iter(K.ALGO_CV, C.byref(self._gdesc), C.byref(p), self._p(xs, 0), self._p(zs, 0), self._p(xd, 0), self._p(zd, 0),
-                                  None, A.ptr(nx), A.ptr(nz), A.stream())
-        K.check(rc, "pxb_pds_iter")
-        self._wait(self._exchange([(xd[0], H, H), (zd[0], 1, 1), (zd[1], 0, 1), (zd[2], 0, 1)]))
+        self._staged(lambda a, b: self._stencil(False, xs, self.r, a, b), [(self.r[0], H, H)])          # r = A x - y
+        self._staged(lambda a, b: self._stencil(True, self.r, self.garr, a, b), [(self.garr[0], 0, 1)])  # grad f = A^T r
+        self._staged(lambda a, b: self._iter(src, dst, nx, nz, a, b),
+                     [(xd[0], H, H), (zd[0], 1, 1), (zd[1], 0, 1), (zd[2], 0, 1)])                        # (x, z) <- CV iteration
         self.cur = dst
         if want_norms:
             v = nrm.reshape(-1)

@@ -62,13 +62,15 @@ def main():
         k = np.exp(-0.5 * (t_ / s) ** 2)
         return k / k.sum()
 
-    for shape, psf, cen, dtype, tol in [((41, 24, 32), [gauss(7, 1.2), gauss(5, 1.0), gauss(7, 1.5)], (3, 2, 3), torch.float64, 1e-12),
-                                        ((48, 40, 64), [gauss(7, 1.2), gauss(7, 1.2), gauss(7, 1.2)], (3, 3, 3), torch.float32, 2e-5)]:
+    for shape, psf, cen, dtype, tol, ovl in [((41, 24, 32), [gauss(7, 1.2), gauss(5, 1.0), gauss(7, 1.5)], (3, 2, 3), torch.float64, 1e-12, True),
+                                             ((41, 24, 32), [gauss(6, 1.2), gauss(5, 1.0), gauss(7, 1.5)], (2, 2, 3), torch.float64, 1e-12, True),
+                                             ((72, 40, 64), [gauss(7, 1.2), gauss(7, 1.2), gauss(7, 1.2)], (3, 3, 3), torch.float32, 2e-5, True),
+                                             ((48, 40, 64), [gauss(7, 1.2), gauss(7, 1.2), gauss(7, 1.2)], (3, 3, 3), torch.float32, 2e-5, False)]:
         n_iter, lam = 15, 0.05
         npdt = np.float64 if dtype == torch.float64 else np.float32
         gen = torch.Generator(device="cuda").manual_seed(11)
         y = torch.rand(shape, device="cuda", dtype=dtype, generator=gen)
-        slab = SlabCondatVuDeblur(shape, psf, cen, y_full=y, lam=lam, positivity=True, dtype=dtype, rho=0.9)
+        slab = SlabCondatVuDeblur(shape, psf, cen, y_full=y, lam=lam, positivity=True, dtype=dtype, rho=0.9, overlap=ovl)
         v = None
         for i in range(n_iter):
             v = slab.step(want_norms=(i == n_iter - 1))
@@ -90,7 +92,8 @@ def main():
         good = err < tol and e_rx < 1e-5
         ok &= good
         if rank == 0:
-            print(f"[slab-deblur] world={world} shape={shape} {dtype}: rel.err={err:.2e} relerr-norm dev={e_rx:.1e} {'OK' if good else 'FAIL'}", flush=True)
+            print(f"[slab-deblur] world={world} shape={shape} {dtype} overlap={slab.overlap} single_pass={slab.single_pass}: rel.err={err:.2e} "
+                  f"relerr-norm dev={e_rx:.1e} {'OK' if good else 'FAIL'}", flush=True)
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

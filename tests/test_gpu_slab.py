@@ -26,7 +26,7 @@ def _run(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("OK") == 7 and "FAIL" not in r.stdout
+    assert r.stdout.count("OK") == 9 and "FAIL" not in r.stdout
 
 
 def test_slab_world1():

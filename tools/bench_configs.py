@@ -104,6 +104,7 @@ def main():
         slab = SlabCondatVuDeblur(shape, [g7, g7, g7], (3, 3, 3), y_local=y_local, lam=0.05, positivity=True, dtype=torch.float32)
         del y_local
         ms, launches = timed(slab.step, K, W, world)
+        launches = launches  # (3 stages x up to 3 sub-range launches when the exchanges are overlapped)
         nvox = int(np.prod(shape))
         name = f"3-D TV deblurring {'x'.join(map(str, shape))} fp32, CondatVu, separable 7x7x7 Stencil PSF + positivity + L21 o Gradient, {world} z-slab(s)"
         # A x - y (read x, y; write r) | A^T r | single-kernel CV iteration with grad f array     (two-pass stencils: 8+12+8+8+36)
