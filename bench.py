@@ -39,7 +39,7 @@ BYTES_PER_VOXEL = {"pxb_pds_iter": 9 * 4, "pxb_pds_primal": 8 * 4, "pxb_pds_dual
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--size", type=int, default=1024, help="cube edge of the volume (default: the named 1024^3 workload)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -167,7 +167,11 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.rows.append([c.strip() for c in ln.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in ln.split(",")]))
+
+    def mark(self):
+        """host time stamp; summary(t0, t1) keeps the samples taken between two marks"""
+        return time.time()
 
     def __exit__(self, *a):
         if self.proc:
@@ -178,9 +182,14 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        rows = [r for ts, r in self.rows if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.11)]
+        in_window = len(rows)
+        if not rows and self.rows:  # region shorter than the sampling period: the sample nearest to it
+            mid = 0.5 * ((t0 or 0) + (t1 or 0))
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - mid))[1]]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])), mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -190,7 +199,8 @@ class ClockSampler:
                 pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "samples_in_timed_region": in_window}
 
 
 def measured_peak():
@@ -297,16 +307,18 @@ def main():
         for _ in range(k):
             step()
 
-    run_steps(W)
-    pending.clear()
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with ClockSampler(local) as clk:  # nvidia-smi is started before the warm-up so that it is sampling when the timed region begins
+        run_steps(W)
+        pending.clear()
+        barrier()
         l0 = _cabi.launch_count()
+        t_begin = clk.mark()
         e0.record()
         run_steps(K)
         e1.record()
         barrier()
+        t_end = clk.mark()
         l1 = _cabi.launch_count()
     ms = e0.elapsed_time(e1)
     launches = int(l1 - l0)
@@ -370,7 +382,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         ncpu = args.cpu_size
         v1, thr, dt1 = run_cpu(ncpu, 2, 1)
-        iters = int(max(3, min(60, 12.0 / max(dt1 / 2, 1e-3))))
+        iters = int(max(3, min(400, 12.0 / max(dt1 / 2, 1e-3))))  # ~12 s of CPU work
         v, thr, dtc = run_cpu(ncpu, iters, 0)
         cpu = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
                "sample": f"oracle/tv_oracle.c (C/OpenMP pass-by-pass port of the reference's PD3O iteration) on a {ncpu}^3 fp32 phantom, {iters} iterations, {dtc:.1f} s"}
@@ -383,7 +395,7 @@ def main():
                        "decomposition": "single GPU" if world == 1 else f"{world} z-slabs, boundary planes of the new iterate (5 planes per interface) exchanged by NCCL send/recv while the interior is computed",
                        "l2_policy": f"inputs larger than L2: {4 * nvox / world / 2**20:.0f} MiB per field per GPU vs 126 MB L2",
                        "iterations_per_step": 1},
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "clocks": clk.summary(t_begin, t_end), "e2e": e2e, "gpu_launches": launches,
             "roofline": dominant, "roofline_all": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
