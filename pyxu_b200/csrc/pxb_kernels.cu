@@ -13,6 +13,7 @@
 #include <string>
 
 #include "pxb_launch.cuh"
+#include "pxb_tv_fast.cuh"
 
 namespace {
 thread_local std::string g_err;
@@ -110,6 +111,80 @@ __global__ void __launch_bounds__(kBlock) k_lincomb(pxb_prox_spec g, T tau, int6
         T v = pxb_lincomb_at<T>(a, x, b, y, ny, c, z, nz, i);
         if (PROX) v = pxb_prox_eval<T>(g.kind, T(g.p0), T(g.p1), v, tau);
         out[i] = v;
+    }
+}
+
+// 128-bit forms of the elementwise kernels (n, the broadcast periods and every base address multiples of the vector):
+// the scalar forms reached 4.1-4.6 TB/s, i.e. 0.63-0.70 of the measured copy bandwidth.
+template <class T, int VEC, bool PROX>
+__global__ void __launch_bounds__(kBlock) k_lincomb_vec(pxb_prox_spec g, T tau, int64_t nv, T* out, T a, const T* x, T b, const T* y,
+                                                        int64_t ny, T c, const T* z, int64_t nz) {
+    for (int64_t iv = (int64_t)blockIdx.x * kBlock + threadIdx.x; iv < nv; iv += (int64_t)gridDim.x * kBlock) {
+        const int64_t i = iv * VEC;
+        PxbVec<T, VEC> v = pxb_vload<T, VEC>(x + i);
+        for (int j = 0; j < VEC; ++j) v.v[j] *= a;
+        if (y) {
+            const PxbVec<T, VEC> t = pxb_vload<T, VEC>(y + (ny ? i % ny : i));
+            for (int j = 0; j < VEC; ++j) v.v[j] += b * t.v[j];
+        }
+        if (z) {
+            const PxbVec<T, VEC> t = pxb_vload<T, VEC>(z + (nz ? i % nz : i));
+            for (int j = 0; j < VEC; ++j) v.v[j] += c * t.v[j];
+        }
+        if (PROX)
+            for (int j = 0; j < VEC; ++j) v.v[j] = pxb_prox_eval<T>(g.kind, T(g.p0), T(g.p1), v.v[j], tau);
+        pxb_vstore<T, VEC>(out + i, v);
+    }
+}
+
+template <class T, int VEC>
+__global__ void __launch_bounds__(kBlock) k_sqnorms_vec(int64_t rows, int64_t n, const T* __restrict__ x, const T* __restrict__ y,
+                                                        double* __restrict__ out, int64_t per) {
+    const int64_t r = blockIdx.x / per;
+    const int64_t chunk = blockIdx.x % per;
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t i = (chunk * kBlock + threadIdx.x) * VEC; i < n; i += per * kBlock * VEC) {
+        const PxbVec<T, VEC> xv = pxb_vload<T, VEC>(x + r * n + i);
+        if (y) {
+            const PxbVec<T, VEC> yv = pxb_vload<T, VEC>(y + r * n + i);
+            for (int j = 0; j < VEC; ++j) {
+                const double d = (double)xv.v[j] - (double)yv.v[j];
+                a0 += d * d;
+                a1 += (double)yv.v[j] * (double)yv.v[j];
+            }
+        } else {
+            for (int j = 0; j < VEC; ++j) a0 += (double)xv.v[j] * (double)xv.v[j];
+        }
+    }
+    block_accumulate(a0, a1, r, true, out);
+}
+
+// group soft-threshold out = x * (1 - t / max(||x_group||, t)) with VEC consecutive `inner` samples per thread, GROUP <= 3
+template <class T, int VEC>
+__global__ void __launch_bounds__(kBlock) k_prox_l21_vec(int64_t outer, int group, int64_t inner, T lam, T tau, const T* __restrict__ x,
+                                                         T* __restrict__ out) {
+    const int64_t innerv = inner / VEC;
+    const int64_t per = (innerv + kBlock - 1) / kBlock;
+    const int64_t o = blockIdx.x / per;
+    const int64_t iv = (blockIdx.x % per) * kBlock + threadIdx.x;
+    if (iv >= innerv) return;
+    const int64_t base = o * group * inner + iv * VEC;
+    const T t = tau * lam;
+    PxbVec<T, VEC> v[3];
+    T nn[VEC];
+    for (int j = 0; j < VEC; ++j) nn[j] = T(0);
+    for (int k = 0; k < group; ++k) {
+        v[k] = pxb_vload<T, VEC>(x + base + k * inner);
+        for (int j = 0; j < VEC; ++j) nn[j] += v[k].v[j] * v[k].v[j];
+    }
+    T sc[VEC];
+    for (int j = 0; j < VEC; ++j) {
+        const T nrm = sqrt(nn[j]);
+        sc[j] = T(1) - t / (nrm > t ? nrm : t);
+    }
+    for (int k = 0; k < group; ++k) {
+        for (int j = 0; j < VEC; ++j) v[k].v[j] *= sc[j];
+        pxb_vstore<T, VEC>(out + base + k * inner, v[k]);
     }
 }
 
@@ -325,6 +400,23 @@ static int lincomb_launch(bool prox, int dtype, const pxb_prox_spec* g, double t
     if (ny >= n) ny = 0;
     if (nz >= n) nz = 0;
     cudaStream_t s = (cudaStream_t)stream;
+    {   // 128-bit form when sizes, periods and addresses allow
+        const int vec = dtype == PXB_F32 ? 4 : 2;
+        const uintptr_t bits = reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z);
+        if (n % vec == 0 && ny % vec == 0 && nz % vec == 0 && (bits & 15u) == 0) {
+            const int64_t nv = n / vec;
+            const unsigned gridv = flat_grid(nv);
+            if (dtype == PXB_F32) {
+                if (prox) k_lincomb_vec<float, 4, true><<<gridv, kBlock, 0, s>>>(gs, (float)tau, nv, (float*)out, (float)a, (const float*)x, (float)b, (const float*)y, ny, (float)c, (const float*)z, nz);
+                else k_lincomb_vec<float, 4, false><<<gridv, kBlock, 0, s>>>(gs, (float)tau, nv, (float*)out, (float)a, (const float*)x, (float)b, (const float*)y, ny, (float)c, (const float*)z, nz);
+            } else {
+                if (prox) k_lincomb_vec<double, 2, true><<<gridv, kBlock, 0, s>>>(gs, tau, nv, (double*)out, a, (const double*)x, b, (const double*)y, ny, c, (const double*)z, nz);
+                else k_lincomb_vec<double, 2, false><<<gridv, kBlock, 0, s>>>(gs, tau, nv, (double*)out, a, (const double*)x, b, (const double*)y, ny, c, (const double*)z, nz);
+            }
+            PXB_CHECK_LAUNCH(who);
+            return 0;
+        }
+    }
     const unsigned grid = flat_grid(n);
     if (dtype == PXB_F32) {
         if (prox) k_lincomb<float, true><<<grid, kBlock, 0, s>>>(gs, (float)tau, n, (float*)out, (float)a, (const float*)x, (float)b, (const float*)y, ny, (float)c, (const float*)z, nz);
@@ -362,6 +454,15 @@ int pxb_prox_l21(int dtype, int64_t outer, int64_t group, int64_t inner, double 
     unsigned grid;
     if (int e = ogi_grid(outer, inner, grid, who)) return e;
     cudaStream_t s = (cudaStream_t)stream;
+    const int vec = dtype == PXB_F32 ? 4 : 2;
+    if (group <= 3 && inner % vec == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+        unsigned gridv;
+        if (int e = ogi_grid(outer, inner / vec, gridv, who)) return e;
+        if (dtype == PXB_F32) k_prox_l21_vec<float, 4><<<gridv, kBlock, 0, s>>>(outer, (int)group, inner, (float)lam, (float)tau, (const float*)x, (float*)out);
+        else k_prox_l21_vec<double, 2><<<gridv, kBlock, 0, s>>>(outer, (int)group, inner, lam, tau, (const double*)x, (double*)out);
+        PXB_CHECK_LAUNCH(who);
+        return 0;
+    }
     if (dtype == PXB_F32) k_prox_l21<float><<<grid, kBlock, 0, s>>>(outer, group, inner, (float)lam, (float)tau, (const float*)x, (float*)out);
     else k_prox_l21<double><<<grid, kBlock, 0, s>>>(outer, group, inner, lam, tau, (const double*)x, (double*)out);
     PXB_CHECK_LAUNCH(who);
@@ -468,7 +569,11 @@ int pxb_sqnorms(int dtype, int64_t rows, int64_t n, const void* x, const void* y
     if (per < 1) per = 1;
     if (rows * per > 0x7fffffffLL) return fail(PXB_ENOSUP, "%s: grid too large", who);
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == PXB_F32) k_sqnorms<float><<<(unsigned)(rows * per), kBlock, 0, s>>>(rows, n, (const float*)x, (const float*)y, out, per);
+    const int vec = dtype == PXB_F32 ? 4 : 2;
+    if (n % vec == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0) {
+        if (dtype == PXB_F32) k_sqnorms_vec<float, 4><<<(unsigned)(rows * per), kBlock, 0, s>>>(rows, n, (const float*)x, (const float*)y, out, per);
+        else k_sqnorms_vec<double, 2><<<(unsigned)(rows * per), kBlock, 0, s>>>(rows, n, (const double*)x, (const double*)y, out, per);
+    } else if (dtype == PXB_F32) k_sqnorms<float><<<(unsigned)(rows * per), kBlock, 0, s>>>(rows, n, (const float*)x, (const float*)y, out, per);
     else k_sqnorms<double><<<(unsigned)(rows * per), kBlock, 0, s>>>(rows, n, (const double*)x, (const double*)y, out, per);
     PXB_CHECK_LAUNCH(who);
     return 0;
