@@ -112,3 +112,25 @@ def test_solver_argument_validation():
 class _Unbounded(pxa.DiffFunc):
     def __init__(self, n):
         super().__init__((1, n))
+
+
+def test_bench_clock_sampler_windows_on_the_timed_region():
+    """bench.py keeps the nvidia-smi samples taken inside the timed region (or the nearest one when the region is
+    shorter than the sampling period) and reports throttle reasons only from those."""
+    import importlib.util
+    import os
+
+    from conftest import ROOT
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    clk = bench.ClockSampler(0)
+    row = lambda mhz, cap: ["0", str(mhz), "1965", "700", "Not Active", "Not Active", "Not Active", cap]
+    clk.rows = [(10.0, row(1965, "Not Active")), (10.1, row(1800, "Active")), (10.2, row(1700, "Active")), (10.6, row(900, "Not Active"))]
+    s = clk.summary(10.05, 10.25)
+    assert s["samples_in_timed_region"] == 2 and s["sm_mhz"] == 1750.0 and s["reasons"] == ["sw_power_cap"] and s["sm_max_mhz"] == 1965.0
+    s = clk.summary(10.30, 10.32)  # nothing inside: the nearest sample stands in
+    assert s["samples_in_timed_region"] == 0 and s["samples"] == 1 and s["sm_mhz"] == 1700.0
+    clk.rows = []
+    assert clk.summary(0.0, 1.0)["samples"] == 0

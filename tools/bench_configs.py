@@ -55,7 +55,7 @@ def timed(step, K, W, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["deblur2d", "fista", "deblur3d"])
+    ap.add_argument("--workload", required=True, choices=["deblur2d", "fista", "deblur3d", "tv2d"])
     ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--steps", type=int, default=20)
@@ -77,6 +77,31 @@ def main():
         dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=torch.device("cuda", local))
     gen = torch.Generator(device="cuda").manual_seed(1 + rank)
     K, W = args.steps, max(3, args.warmup)
+    if args.workload == "tv2d":
+        # configs[0]: the reference's own CPU-runnable case -- 2-D TV denoising 512x512 float64, PD3O, 200 iterations,
+        # HOST arrays in and out through Solver.fit() (wall clock, transfers and Python included)
+        import time
+
+        n = args.size or 512
+        shape, N = (n, n), n * n
+        rng = np.random.default_rng(0)
+        y = rng.random(N)
+        def solve():
+            f = 0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y)
+            Kop = pxo.Gradient(arg_shape=shape)
+            h = 0.1 * pxo.L21Norm(arg_shape=(2, *shape), l2_axis=(0,))
+            slv = pxs.PD3O(f=f, g=pxo.PositiveOrthant(dim=N), h=h, K=Kop, show_progress=False, final_writeback=False)
+            slv.fit(x0=y.copy(), stop_crit=pxst.MaxIter(200))
+            return slv.solution()
+        solve()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x = solve()
+        dt = time.perf_counter() - t0
+        assert isinstance(x, np.ndarray) and x.dtype == np.float64
+        print(json.dumps({"workload": f"2-D TV denoising {n}x{n} float64, PD3O, 200 iterations, host arrays through Solver.fit()", "n_gpus": 1,
+                          "seconds": dt, "iterations_per_s": 200 / dt, "gvoxel_iter_per_s": N * 200 / dt / 1e9}))
+        return
     if args.workload == "deblur2d":
         n = args.size or 8192
         shape, N = (n, n), n * n
