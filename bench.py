@@ -377,6 +377,36 @@ def main():
                "what": "PD3O(...).fit(x0=<host array>, stop_crit=MaxIter(K)|RelError) + solution(): H2D of x0 and of the data y, "
                        "K fused iterations with the RelError scalars read back every step, D2H of x"}
         del slv2
+    elif world > 1 and not args.no_e2e:
+        # multi-GPU end to end: every rank uploads its z-slab of the data from pinned host memory, K iterations with the
+        # RelError sums all-reduced and read back every step, the slab of x copied back to a host array
+        from pyxu_b200 import _array as A_
+        from pyxu_b200.slab import SlabPD3OTV as _Slab, partition as _part
+
+        a_, b_ = _part(n, world)[rank]
+        y_host = torch.empty((b_ - a_, n, n), dtype=torch.float32, pin_memory=True)
+        y_host.copy_(slv.shift_h[0, slv.HALO : slv.HALO + slv.n0].neg())  # (the phantom's slab, staged outside the timed region)
+        del slv, step
+        torch.cuda.empty_cache()
+        barrier()
+        t0 = time.perf_counter()
+        y_dev = y_host.to(dev, non_blocking=True)
+        slv2 = _Slab(shape, y_local=y_dev, lam=LAM, positivity=True, dtype=torch.float32)
+        for _ in range(K):
+            v = slv2.step(want_norms=True)
+        slv2.materialize_x()
+        x_host = A_.restore(slv2.x[0, slv2.HALO : slv2.HALO + slv2.n0].contiguous().reshape(-1), A_.HOST)
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        assert isinstance(x_host, np.ndarray) and np.isfinite(x_host[:: max(1, x_host.size // 1000)]).all() and np.isfinite(v).all()
+        e2e = {"value": nvox * K / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(4 * nvox / K), "d2h_bytes_per_step": int(4 * nvox / K + 32 * world),
+               "seconds": dt,
+               "what": "per rank: H2D of its z-slab of the data from pinned host memory, SlabPD3OTV set-up (halo exchange, z0 = K x0), K single-kernel "
+                       "iterations with the RelError sums all-reduced and read back every step, D2H of its slab of x; wall clock, max over ranks"}
+        del slv2
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
