@@ -188,6 +188,42 @@ __global__ void __launch_bounds__(kBlock) k_prox_l21_vec(int64_t outer, int grou
     }
 }
 
+// dual update z <- (1-rho) z + rho prox_{sigma h*}(z + sigma t) with VEC consecutive `inner` samples per thread, GROUP <= 3
+template <class T, int VEC>
+__global__ void __launch_bounds__(kBlock) k_dual_update_vec(int kind, int64_t outer, int group, int64_t inner, T lam, T sigma, T rho,
+                                                            T* __restrict__ z, const T* __restrict__ t, double* __restrict__ norms) {
+    const int64_t innerv = inner / VEC;
+    const int64_t per = (innerv + kBlock - 1) / kBlock;
+    const int64_t o = blockIdx.x / per;
+    const int64_t iv = (blockIdx.x % per) * kBlock + threadIdx.x;
+    const bool ok = iv < innerv;
+    double a0 = 0.0, a1 = 0.0;
+    if (ok) {
+        const int64_t base = o * group * inner + iv * VEC;
+        PxbVec<T, VEC> zo[3];
+        T p[VEC][PXB_MAX_DIRS];
+        for (int k = 0; k < group; ++k) {
+            zo[k] = pxb_vload<T, VEC>(z + base + k * inner);
+            const PxbVec<T, VEC> tv = pxb_vload<T, VEC>(t + base + k * inner);
+            for (int j = 0; j < VEC; ++j) p[j][k] = zo[k].v[j] + sigma * tv.v[j];
+        }
+        for (int j = 0; j < VEC; ++j) pxb_dual_prox_group<T>(kind, group, lam, sigma, p[j]);
+        for (int k = 0; k < group; ++k) {
+            PxbVec<T, VEC> zn;
+            for (int j = 0; j < VEC; ++j) {
+                zn.v[j] = (T(1) - rho) * zo[k].v[j] + rho * p[j][k];
+                if (norms) {
+                    const double dd = (double)zn.v[j] - (double)zo[k].v[j];
+                    a0 += dd * dd;
+                    a1 += (double)zo[k].v[j] * (double)zo[k].v[j];
+                }
+            }
+            pxb_vstore<T, VEC>(z + base + k * inner, zn);
+        }
+    }
+    if (norms) block_accumulate(a0, a1, o, ok, norms);
+}
+
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_sqnorms(int64_t rows, int64_t n, const T* __restrict__ x, const T* __restrict__ y,
                                                     double* __restrict__ out, int64_t per) {
@@ -479,6 +515,15 @@ int pxb_dual_update(int dtype, int kind, int64_t outer, int64_t group, int64_t i
     unsigned grid;
     if (int e = ogi_grid(outer, inner, grid, who)) return e;
     cudaStream_t s = (cudaStream_t)stream;
+    const int vec = dtype == PXB_F32 ? 4 : 2;
+    if (group <= 3 && kind != PXB_DUAL_NONE && inner % vec == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(t)) & 15u) == 0) {
+        unsigned gridv;
+        if (int e = ogi_grid(outer, inner / vec, gridv, who)) return e;
+        if (dtype == PXB_F32) k_dual_update_vec<float, 4><<<gridv, kBlock, 0, s>>>(kind, outer, (int)group, inner, (float)lam, (float)sigma, (float)rho, (float*)z, (const float*)t, norms);
+        else k_dual_update_vec<double, 2><<<gridv, kBlock, 0, s>>>(kind, outer, (int)group, inner, lam, sigma, rho, (double*)z, (const double*)t, norms);
+        PXB_CHECK_LAUNCH(who);
+        return 0;
+    }
     if (dtype == PXB_F32) k_dual_update<float><<<grid, kBlock, 0, s>>>(kind, outer, group, inner, (float)lam, (float)sigma, (float)rho, (float*)z, (const float*)t, norms);
     else k_dual_update<double><<<grid, kBlock, 0, s>>>(kind, outer, group, inner, lam, sigma, rho, (double*)z, (const double*)t, norms);
     PXB_CHECK_LAUNCH(who);
