@@ -266,3 +266,28 @@ def test_large_results_leave_the_device_through_the_pipelined_copy(env):
         assert origin == env.A.HOST and d.is_cuda and tuple(d.shape) == h.shape and np.array_equal(d.cpu().numpy(), h)
     d32, _ = env.A.asdevice(h, dtype=torch.float32)  # with a dtype conversion on the device
     assert d32.dtype == torch.float32 and np.array_equal(d32.cpu().numpy(), h.astype(np.float32))
+
+
+@pytest.mark.parametrize("form", ["direct", "tma"])
+def test_iter_random_small_shapes(env, form, iter_path):
+    """Ragged / degenerate geometries: single planes, fewer rows than a tile, one vector per row, 1-3 chunks, batches --
+    every scheme, PD3O and CondatVu, fp32 and fp64, against the two-sweep kernels."""
+    K = env.K
+    iter_path(1 if form == "direct" else 2)
+    rng = np.random.default_rng(123)
+    schemes = ["forward", "backward", "central"]
+    for trial in range(36):
+        dtype = torch.float64 if trial % 2 else torch.float32
+        vec = 2 if dtype == torch.float64 else 4
+        ndim = 3 if trial % 3 else 2
+        n2 = vec * int(rng.integers(1, 40))
+        shape = (int(rng.integers(1, 12)), int(rng.integers(1, 20)), n2) if ndim == 3 else (int(rng.integers(1, 40)), n2)
+        batch = int(rng.integers(1, 4))
+        Kop = env.operator.Gradient(arg_shape=shape, scheme=schemes[trial % 3], dtype=np.float64 if dtype == torch.float64 else np.float32,
+                                    sampling=float(rng.uniform(0.5, 2.0)))
+        shift = torch.randn(Kop.dim if trial % 4 else batch * Kop.dim, device="cuda", dtype=dtype)
+        gspec = [(K.PROX_POS, 0.0, 0.0), (K.PROX_NONE, 0.0, 0.0), (K.PROX_L1, 0.05, 0.0)][trial % 3]
+        P = params(K, 0.21, 0.19, float(rng.uniform(0.7, 1.3)), gspec, K.F_SQL2, 0.5, shift, None, K.DUAL_L21 if trial % 5 else K.DUAL_L1, 0.3)
+        algo = K.ALGO_PD3O if trial % 2 == 0 else K.ALGO_CV
+        a, b = both_forms(env, algo, Kop, batch, dtype, P, seed=trial)
+        assert_same(env, algo, a, b, 1e-12 if dtype == torch.float64 else 3e-6)
