@@ -18,6 +18,9 @@
 //   ring          w(m) lives in slot m & 3;  phase A of plane m+1 / m+2 never touches a slot phase C of plane m
 //                 still reads, hence ONE __syncthreads per plane
 //
+// This file holds the algorithm, the geometry and the direct-load (L1/L2-served) form; the forms that run by default
+// stage their operands by TMA: pxb_tv_tma.cuh (3-D, marching, 3-stage mbarrier ring) and pxb_tv_tile2d.cuh (2-D tiles).
+//
 // Like the other bodies these are __host__ __device__ so that tests/emu can run the exact per-thread code on the
 // CPU (phase A for every thread, then phase C for every thread: the same order the barrier enforces).
 #pragma once
