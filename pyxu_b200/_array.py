@@ -71,6 +71,18 @@ _CHUNK = 64 << 20     # bytes per staging buffer (measured on the B200 host: 64 
 _STAGE = None         # pinned staging buffers (allocated once, on first use)
 
 
+def _copy_threads():
+    """Host threads of the staged copies: 3/4 of the cores, shared between the ranks of this node (torchrun sets
+    LOCAL_WORLD_SIZE), at most 12; PXB_D2H_THREADS overrides."""
+    import os
+
+    forced = int(os.environ.get("PXB_D2H_THREADS", 0))
+    if forced > 0:
+        return forced
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, min(12, (os.cpu_count() or 2) * 3 // 4 // ranks))
+
+
 def _advise_hugepages(arr):
     """First touch of a fresh multi-GiB NumPy array is page-fault bound (~2 GB/s with 4 KiB pages): ask for
     transparent huge pages.  Best effort."""
@@ -100,7 +112,7 @@ def _d2h_pipelined(t):
     out = np.empty(t.numel(), dtype=np_dtype(t.dtype))
     _advise_hugepages(out)
     out_b = out.view(np.uint8)
-    nthreads = int(os.environ.get("PXB_D2H_THREADS", 0)) or max(1, min(12, (os.cpu_count() or 2) * 3 // 4))
+    nthreads = _copy_threads()
     copy_stream = torch.cuda.Stream(device=t.device)
     copy_stream.wait_stream(torch.cuda.current_stream())
     nchunks = (nbytes + _CHUNK - 1) // _CHUNK
@@ -147,7 +159,7 @@ def _h2d_pipelined(arr, want):
     nbytes = src.size
     out = torch.empty(arr.shape, dtype=torch_dtype(arr.dtype), device=current_device())
     flat = out.reshape(-1).view(torch.uint8)
-    nthreads = int(os.environ.get("PXB_D2H_THREADS", 0)) or max(1, min(12, (os.cpu_count() or 2) * 3 // 4))
+    nthreads = _copy_threads()
     copy_stream = torch.cuda.Stream(device=out.device)
     nchunks = (nbytes + _CHUNK - 1) // _CHUNK
     events = [None] * nb
