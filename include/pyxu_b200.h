@@ -293,6 +293,12 @@ int pxb_pds_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
  * 1 = direct-load form only, 2 = TMA form only (PXB_ENOSUP when it does not apply).  Environment variable
  * PXB_TV_ITER=direct|tma sets the initial value.  For A/B measurements and tests. */
 int pxb_set_iter_path(int path);
+/* Folding boundary modes (wrap / reflect / symmetric / edge; pad.py:252-302) inside pxb_pds_iter: 1 = the single-kernel
+ * forms serve them too (the samples within two of a folding face, and the out-of-domain rim of the w tiles, go through
+ * the per-sample boundary map / pre-image gather; single-domain arrays only), 0 = PXB_ENOSUP as before, so that callers
+ * take pxb_pds_primal + pxb_pds_dual, -1 = back to the initial value (environment variable PXB_TV_ITER_MODES=0|1, else the
+ * library's default). */
+int pxb_set_iter_modes(int on);
 /* same, with the number of planes one thread block marches through fixed by the caller (tuning / tests) */
 int pxb_pds_iter_chunked(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in,
                          void* xu_out, void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk, void* stream);

@@ -330,7 +330,28 @@ int pxb_iter_path() {
     return v;
 }
 
+// Default of the folding-mode instances of the single-kernel iteration (see pxb_set_iter_modes).
+#ifndef PXB_ITER_MODES_DEFAULT
+#define PXB_ITER_MODES_DEFAULT 0
+#endif
+static std::atomic<int> g_iter_modes{-1};
+int pxb_iter_modes() {
+    int v = g_iter_modes.load();
+    if (v < 0) {
+        const char* e = getenv("PXB_TV_ITER_MODES");
+        v = e ? (atoi(e) != 0 ? 1 : 0) : PXB_ITER_MODES_DEFAULT;
+        g_iter_modes.store(v);
+    }
+    return v;
+}
+
 extern "C" {
+int pxb_set_iter_modes(int on) {
+    if (on < -1 || on > 1) return fail(PXB_EINVAL, "pxb_set_iter_modes: 0, 1 or -1 (back to the initial value)");
+    g_iter_modes.store(on);
+    return 0;
+}
+
 int pxb_set_iter_path(int path) {
     if (path < 0 || path > 2) return fail(PXB_EINVAL, "pxb_set_iter_path: 0 (auto), 1 (direct loads) or 2 (TMA)");
     g_iter_path.store(path);

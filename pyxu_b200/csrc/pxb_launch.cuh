@@ -146,6 +146,7 @@ int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p
 int pxb_tv_tma_try(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out, void* z_out,
                    void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, cudaError_t* err);
 int pxb_iter_path();  // 0 auto, 1 direct-load form only, 2 TMA form only
+int pxb_iter_modes(); // 1: folding boundary modes run the single-kernel forms too, 0: they take the two-sweep form
 int pxb_stencil2d_try(const pxb_stencil2d* d, const void* in, void* out, cudaStream_t s, cudaError_t* err);
 int pxb_stencil2d_fista_try(const pxb_stencil2d* d, const pxb_fista_step* f, int which, void* out, cudaStream_t s, cudaError_t* err);
 int pxb_tv_tile2d_try(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out, void* z_out,

@@ -5,11 +5,11 @@
 
 namespace {
 
-template <class T, int VEC, int ALGO, bool NORMS, class S>
+template <class T, int VEC, int ALGO, bool NORMS, class S, bool MODES = false>
 __global__ void __launch_bounds__(256, 3)
     k_tv_tile2d(const __grid_constant__ PxbTvP<T> q, const __grid_constant__ PxbT2Geom g, const __grid_constant__ PxbIterPtr<T> a,
                 const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_zr,
-                const __grid_constant__ CUtensorMap map_zc) {
+                const __grid_constant__ CUtensorMap map_zc, const __grid_constant__ PxbModeArgs<MODES> ma) {
     using C = PxbT2Cfg<T, VEC>;
     extern __shared__ __align__(128) unsigned char pxb_t2_smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256, 3)
     }
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     mbar_wait(&bar, 0);
-    pxb_t2_phaseA<T, VEC, ALGO, NORMS, S>(q, g, it, a, tid, sm, acc);
+    pxb_t2_phaseA<T, VEC, ALGO, NORMS, S, MODES>(q, g, it, a, tid, sm, acc, ma.ctx());
     __syncthreads();
     pxb_t2_phaseC<T, VEC, NORMS, S>(q, g, it, a, tid, sm, acc);
     if (NORMS) {
@@ -59,7 +59,7 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
     PxbTvCoef cf;
     PxbTvP<T> q;
     PxbT2Geom g;
-    if (int why = pxb_t2_setup<T, VEC>(d, P, cf, q, g)) return why;
+    if (int why = pxb_t2_setup<T, VEC>(d, P, cf, q, g, pxb_iter_modes() != 0)) return why;
     alignas(64) CUtensorMap tu, ts, tzr, tzc;
     const uint64_t stride[3] = {1, (uint64_t)g.n2, (uint64_t)g.s0};
     const uint64_t dim_u[3] = {(uint64_t)g.n2, (uint64_t)g.n1, (uint64_t)g.nimg};
@@ -75,9 +75,17 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
     auto go = [&](auto kern) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) { *err = e; return; }
-        kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, a, tu, ts, tzr, tzc);
+        kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, a, tu, ts, tzr, tzc, PxbModeArgs<false>{});
         *err = cudaGetLastError();
     };
+    if (pxb_any_mode(d)) {  // folding boundary modes: the generic instance with the per-sample path on the faces
+        auto kern = k_tv_tile2d<T, VEC, ALGO, NORMS, PxbSpecAny, true>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) { *err = e; return 0; }
+        kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, a, tu, ts, tzr, tzc, PxbModeArgs<true>{d, P});
+        *err = cudaGetLastError();
+        return 0;
+    }
     if (fwd && q.hkind == PXB_DUAL_L21) go(k_tv_tile2d<T, VEC, ALGO, NORMS, PxbSpec<PXB_SCHEME_FWD, -1, PXB_DUAL_L21, -1>>);
     else go(k_tv_tile2d<T, VEC, ALGO, NORMS, PxbSpecAny>);
     return 0;

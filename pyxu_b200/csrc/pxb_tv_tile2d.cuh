@@ -102,8 +102,11 @@ PXB_HD PxbT2Item pxb_t2_item(const PxbT2Geom& g, int64_t blk, int ty, int t2) {
 
 // phase A for thread `tid`: w of rows {wy, wy+8} of the tile (+ the rims this thread owns) -> shared memory; new primal
 // iterate (and x) of the tile's own samples -> global memory.
-template <class T, int VEC, int ALGO, bool NORMS, class S>
-PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Item& it, const PxbIterPtr<T>& a, int tid, T* __restrict__ sm, double* acc) {
+// MODES (folding boundary modes): as in pxb_tv_tma.cuh, the samples of the two-sample band along a folding face and the
+// out-of-image cells of the w tile are recomputed through the per-sample path of pxb_tv_iter.cuh.
+template <class T, int VEC, int ALGO, bool NORMS, class S, bool MODES = false>
+PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Item& it, const PxbIterPtr<T>& a, int tid, T* __restrict__ sm, double* acc,
+                          const PxbModeCtx mc = PxbModeCtx{nullptr, nullptr}) {
     using C = PxbT2Cfg<T, VEC>;
     T* __restrict__ wsm = sm + C::OFF_W;
     const int lane = tid & 31, wy = tid >> 5, cl = lane * VEC;
@@ -113,8 +116,13 @@ PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
         const bool in = r < g.n1 && c < g.n2;
         T wv[VEC], xo[VEC], un[VEC], uo[VEC];
         pxb_t2_w<T, VEC, VEC, ALGO, S>(q, g, sm, rl + 1, cl + VEC, wv, xo, un, uo);
+        bool keep = in;
+        if (MODES && pxb_item_needs_any<T, 2>(q, it.i0, r, c, VEC)) {
+            pxb_item_any<T, VEC, ALGO>(mc, a.u_in, a.z_in, it.b, it.i0, r, c, wv, xo, un, uo);
+            keep = true;
+        }
         PxbVec<T, VEC> o;
-        for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
+        for (int j = 0; j < VEC; ++j) o.v[j] = keep ? wv[j] : T(0);
         pxb_vstore<T, VEC>(wsm + (rl + 1) * C::BW + cl + VEC, o);
         if (in) {
             const int64_t lin = base + (int64_t)r * g.n2 + c;
@@ -145,7 +153,11 @@ PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
             const int br = top ? 0 : C::TY + 1, r = top ? it.r0 - 1 : it.r0 + C::TY, c = it.c0 + cl;
             T wv[VEC], xo[VEC], un[VEC], uo[VEC];
             pxb_t2_w<T, VEC, VEC, ALGO, S>(q, g, sm, br, cl + VEC, wv, xo, un, uo);
-            const bool in = r >= 0 && r < g.n1 && c < g.n2;
+            bool in = r >= 0 && r < g.n1 && c < g.n2;
+            if (MODES && pxb_item_needs_any<T, 2>(q, it.i0, r, c, VEC)) {
+                pxb_item_any<T, VEC, ALGO>(mc, a.u_in, a.z_in, it.b, it.i0, r, c, wv, xo, un, uo);
+                in = true;
+            }
             PxbVec<T, VEC> o;
             for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
             pxb_vstore<T, VEC>(wsm + br * C::BW + cl + VEC, o);
@@ -158,7 +170,12 @@ PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
             const int bc = left ? VEC - 1 : VEC + C::T2, r = it.r0 + rl, c = left ? it.c0 - 1 : it.c0 + C::T2;
             T wv[1], xo[1], un[1], uo[1];
             pxb_t2_w<T, VEC, 1, ALGO, S>(q, g, sm, rl + 1, bc, wv, xo, un, uo);
-            wsm[(rl + 1) * C::BW + bc] = (r < g.n1 && c >= 0 && c < g.n2) ? wv[0] : T(0);
+            bool in = r < g.n1 && c >= 0 && c < g.n2;
+            if (MODES && pxb_item_needs_any<T, 2>(q, it.i0, r, c, 1)) {
+                pxb_item_any<T, 1, ALGO>(mc, a.u_in, a.z_in, it.b, it.i0, r, c, wv, xo, un, uo);
+                in = true;
+            }
+            wsm[(rl + 1) * C::BW + bc] = in ? wv[0] : T(0);
         }
     }
 }
@@ -216,12 +233,12 @@ PXB_HD void pxb_t2_phaseC(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
 
 // host: eligibility + geometry.  0 or a reason code.
 template <class T, int VEC>
-inline int pxb_t2_setup(const pxb_grad_desc& d, const pxb_pds_params& P, PxbTvCoef& cf, PxbTvP<T>& q, PxbT2Geom& g) {
+inline int pxb_t2_setup(const pxb_grad_desc& d, const pxb_pds_params& P, PxbTvCoef& cf, PxbTvP<T>& q, PxbT2Geom& g, bool allow_modes = false) {
     using C = PxbT2Cfg<T, VEC>;
     if (!pxb_tv_fast_coefs(d, cf)) return 1;
     if (d.ndir != 2) return 2;
     if (P.hkind != PXB_DUAL_L21 && P.hkind != PXB_DUAL_L1) return 3;
-    if (d.mode[1] != PXB_CONSTANT || d.mode[2] != PXB_CONSTANT) return 4;
+    if (pxb_any_mode(d) && !allow_modes) return 4;
     if (d.shape[2] % VEC) return 5;
     if (d.slab.halo != 0 || d.slab.open_lo || d.slab.open_hi) return 7;
     if (d.shape[0] < 1 || d.shape[1] < 1 || d.shape[2] < 1 || d.batch < 1) return 9;

@@ -208,9 +208,13 @@ PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const Pxb
 }
 
 // phase A of plane m out of stage `st` (plane m) and, for two-sided / backward schemes, `st_next` (plane m+1).
-template <class T, int VEC, int TY, int ALGO, bool NORMS, class S = PxbSpecAny>
+// MODES (folding boundary modes): the staged boxes are zero-filled outside the domain, i.e. they carry the 'constant'
+// extension; the samples for which that is not the reference's arithmetic -- the two-sample band along a folding face
+// and the out-of-domain cells / planes of the w ring -- are recomputed through the per-sample path of pxb_tv_iter.cuh.
+template <class T, int VEC, int TY, int ALGO, bool NORMS, class S = PxbSpecAny, bool MODES = false>
 PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTmaGeom& tg, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid,
-                           int m, const T* __restrict__ st, const T* __restrict__ st_next, T* ring, PxbTmaThread<T, VEC>& th) {
+                           int m, const T* __restrict__ st, const T* __restrict__ st_next, T* ring, PxbTmaThread<T, VEC>& th,
+                           const PxbModeCtx mc = PxbModeCtx{nullptr, nullptr}) {
     using C = PxbTmaCfg<T, VEC, TY>;
     using R = typename C::Ring;
     T* __restrict__ slot = ring + (m & 3) * R::SLOT;
@@ -223,8 +227,13 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         T wv[VEC], z0c[VEC], xo[VEC], un[VEC], uo[VEC];
         pxb_tma_w<T, VEC, TY, VEC, ALGO, S>(q, tg, st, st_next, rl + 1, cl + VEC, th.z0p, wv, z0c, th.zc[1], th.zc[2], xo, un, uo);
         for (int j = 0; j < VEC; ++j) { th.zc[0][j] = z0c[j]; th.z0p[j] = z0c[j]; }
+        bool keep = in;
+        if (MODES && pxb_item_needs_any<T, 3>(q, m, r, c, VEC)) {
+            pxb_item_any<T, VEC, ALGO>(mc, a.u_in, a.z_in, it.b, m, r, c, wv, xo, un, uo);
+            keep = true;
+        }
         PxbVec<T, VEC> o;
-        for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
+        for (int j = 0; j < VEC; ++j) o.v[j] = keep ? wv[j] : T(0);
         pxb_vstore<T, VEC>(slot + (rl + 1) * R::RS + cl + VEC, o);
         if (own && in) {
             const int64_t lin = it.lin_base + (int64_t)m * g.sM + (int64_t)r * g.sR + c;
@@ -259,7 +268,11 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             const int r = top ? it.r0 - 1 : it.r0 + TY, c = it.c0 + cl;
             T wv[VEC], z0c[VEC], z1c[VEC], z2c[VEC], xo[VEC], un[VEC], uo[VEC];
             pxb_tma_w<T, VEC, TY, VEC, ALGO, S>(q, tg, st, st_next, br, cl + VEC, th.z0p_rim, wv, z0c, z1c, z2c, xo, un, uo);
-            const bool in = r >= 0 && r < g.nR && c < g.nC;
+            bool in = r >= 0 && r < g.nR && c < g.nC;
+            if (MODES && pxb_item_needs_any<T, 3>(q, m, r, c, VEC)) {
+                pxb_item_any<T, VEC, ALGO>(mc, a.u_in, a.z_in, it.b, m, r, c, wv, xo, un, uo);
+                in = true;
+            }
             PxbVec<T, VEC> o;
             for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
             pxb_vstore<T, VEC>(slot + br * R::RS + cl + VEC, o);
@@ -277,7 +290,11 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             const int r = it.r0 + hl, c = left ? it.c0 - 1 : it.c0 + C::T2;
             T wv[1], z0c[1], z1c[1], z2c[1], xo[1], un[1], uo[1];
             pxb_tma_w<T, VEC, TY, 1, ALGO, S>(q, tg, st, st_next, hl + 1, bc, &th.z0p_col, wv, z0c, z1c, z2c, xo, un, uo);
-            const bool in = r < g.nR && c >= 0 && c < g.nC;
+            bool in = r < g.nR && c >= 0 && c < g.nC;
+            if (MODES && pxb_item_needs_any<T, 3>(q, m, r, c, 1)) {
+                pxb_item_any<T, 1, ALGO>(mc, a.u_in, a.z_in, it.b, m, r, c, wv, xo, un, uo);
+                in = true;
+            }
             slot[(hl + 1) * R::RS + bc] = in ? wv[0] : T(0);
         }
         th.z0p_col = st[C::OFF_Z0 + (hl + 1) * C::BW + bc];

@@ -17,6 +17,9 @@
 #include "../../pyxu_b200/csrc/pxb_stencil3d.cuh"
 #include <vector>
 
+// folding boundary modes inside the single-kernel iteration forms (pxb_set_iter_modes on the device side)
+static bool g_allow_modes = true;
+
 #define FOR_VOX(batch, g)                              \
     for (int64_t b = 0; b < (batch); ++b)              \
         for (int i0 = 0; i0 < (g).n0; ++i0)            \
@@ -108,12 +111,14 @@ static int t_tv_dir(int vec, int which, int algo, const pxb_grad_desc* K, const 
 // single-kernel iteration (pxb_tv_iter.cuh): every CTA is replayed as "phase A for all threads, then phase C for
 // all threads" per plane -- the order the device's one barrier per plane enforces -- with the CTA's shared-memory
 // ring as a host array.  Same template instances as the launcher in pxb_tv_iter.cu.
-template <class T, int VEC, int TXL, int TY, int NDIR, int ALGO, bool NORMS>
+template <class T, int VEC, int TXL, int TY, int NDIR, int ALGO, bool NORMS, bool MODES>
 static int t_iter_cfg(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, int chunk) {
     using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
     PxbTvCoef cf;
     PxbIterGeom g;
-    if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, 5, cf, g)) return -100 - why;
+    if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, 5, cf, g, g_allow_modes)) return -100 - why;
+    if (pxb_any_mode(*K) != MODES) return -130;  // the launcher's rule: folding modes <=> the MODES instance
+    const PxbModeCtx mc{K, p};
     PxbTvP<T> q;
     pxb_tv_prepare<T>(*K, cf, *p, q);
     std::vector<T> smem(C::NSLOT * C::SLOT);
@@ -124,7 +129,7 @@ static int t_iter_cfg(const pxb_grad_desc* K, const pxb_pds_params* p, const Pxb
         for (auto& s : st) std::memset(&s, 0, sizeof(s));
         for (auto& v : smem) v = T(12345);  // poison: cells that are read must have been written
         for (int m = R.mlo; m < R.mhi; ++m) {
-            for (int tid = 0; tid < C::NT; ++tid) pxb_iter_phaseA<T, VEC, TXL, TY, NDIR, ALGO, NORMS>(q, g, it, a, tid, m, smem.data(), st[tid]);
+            for (int tid = 0; tid < C::NT; ++tid) pxb_iter_phaseA<T, VEC, TXL, TY, NDIR, ALGO, NORMS, MODES>(q, g, it, a, tid, m, smem.data(), st[tid], mc);
             const int mm = m - R.lag;
             for (int tid = 0; tid < C::NT; ++tid) {
                 if (mm >= it.m0 && mm < it.m1)
@@ -140,12 +145,17 @@ static int t_iter_cfg(const pxb_grad_desc* K, const pxb_pds_params* p, const Pxb
     }
     return 0;
 }
+template <class T, int NDIR, int ALGO, bool NORMS, bool MODES>
+static int t_iter_tile_m(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, int chunk) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (NDIR == 3) return t_iter_cfg<T, VEC, 32, 8, 3, ALGO, NORMS, MODES>(K, p, a, chunk);
+    if (K->shape[2] <= 128 * VEC) return t_iter_cfg<T, VEC, 128, 1, 2, ALGO, NORMS, MODES>(K, p, a, chunk);
+    return t_iter_cfg<T, VEC, 256, 1, 2, ALGO, NORMS, MODES>(K, p, a, chunk);
+}
 template <class T, int NDIR, int ALGO, bool NORMS>
 static int t_iter_tile(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, int chunk) {
-    constexpr int VEC = 16 / (int)sizeof(T);
-    if (NDIR == 3) return t_iter_cfg<T, VEC, 32, 8, 3, ALGO, NORMS>(K, p, a, chunk);
-    if (K->shape[2] <= 128 * VEC) return t_iter_cfg<T, VEC, 128, 1, 2, ALGO, NORMS>(K, p, a, chunk);
-    return t_iter_cfg<T, VEC, 256, 1, 2, ALGO, NORMS>(K, p, a, chunk);
+    const int rc = t_iter_tile_m<T, NDIR, ALGO, NORMS, false>(K, p, a, chunk);
+    return rc != -130 ? rc : t_iter_tile_m<T, NDIR, ALGO, NORMS, true>(K, p, a, chunk);
 }
 template <class T>
 static int t_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
@@ -178,20 +188,22 @@ static void emu_tma_box(const PxbTmaBoxDesc& m, uint32_t rows, const int c[5], T
             dst[i1 * m.box[0] + i0] = v;
         }
 }
-template <class T, int ALGO, bool NORMS, class S>
+template <class T, int ALGO, bool NORMS, class S, bool MODES = false>
 static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, int chunk, int want_spec) {
     constexpr int VEC = 16 / (int)sizeof(T), TY = 8;
     using C = PxbTmaCfg<T, VEC, TY>;
     using R = typename C::Ring;
     PxbTvCoef cf;
     PxbIterGeom g;
-    if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, 5, cf, g)) return -100 - why;
+    if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, 5, cf, g, g_allow_modes)) return -100 - why;
+    if (pxb_any_mode(*K) != MODES) return -130;  // folding modes <=> the MODES instance (generic specialisation), as in the launcher
+    const PxbModeCtx mc{K, p};
     PxbTvP<T> q;
     pxb_tv_prepare<T>(*K, cf, *p, q);
     PxbTmaGeom tg;
     PxbTmaBoxDesc mu, ms, mz;
     if (int why = pxb_tma_setup<T, VEC, TY>(*K, *p, cf, g, q, a.u_in, a.z_in, tg, mu, ms, mz)) return -100 - why;
-    if (pxb_tma_pick_spec<T>(cf, q, tg) != want_spec) return -130;  // the caller dispatches on the same rule as the launcher
+    if (!MODES && pxb_tma_pick_spec<T>(cf, q, tg) != want_spec) return -130;  // the caller dispatches on the same rule as the launcher
     std::vector<T> stages(C::NSTAGE * C::STAGE), ring(R::NSLOT * R::SLOT);
     std::vector<PxbTmaThread<T, VEC>> th(C::NT);
     for (int64_t blk = 0; blk < g.nblocks; ++blk) {
@@ -223,7 +235,7 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
             const int k = m - Rg.mlo;
             const T* st = stages.data() + (k % C::NSTAGE) * C::STAGE;
             const T* st_next = need_next ? stages.data() + ((k + 1) % C::NSTAGE) * C::STAGE : st;
-            for (int tid = 0; tid < C::NT; ++tid) pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S>(q, g, tg, it, a, tid, m, st, st_next, ring.data(), th[tid]);
+            for (int tid = 0; tid < C::NT; ++tid) pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring.data(), th[tid], mc);
             if (m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
             const int mm = m - lag;
             for (int tid = 0; tid < C::NT; ++tid) {
@@ -247,12 +259,14 @@ static int t_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
     PxbIterPtr<T> a{(const T*)u_in, (const T*)z_in, (T*)u_out, (T*)z_out, (T*)x_out, nx, nz};
     const bool norms = nx || nz;
     // try the instances in the launcher's order; exactly one accepts (-130 = "not my problem")
-#define EMU_TMA_TRY(S, id)                                                                                              \
+#define EMU_TMA_TRY_M(S, id, M)                                                                                         \
     {                                                                                                                   \
-        int rc = algo == PXB_PD3O ? (norms ? t_tma_run<T, PXB_PD3O, true, S>(K, p, a, chunk, id) : t_tma_run<T, PXB_PD3O, false, S>(K, p, a, chunk, id)) \
-                                  : (norms ? t_tma_run<T, PXB_CV, true, S>(K, p, a, chunk, id) : t_tma_run<T, PXB_CV, false, S>(K, p, a, chunk, id));       \
+        int rc = algo == PXB_PD3O ? (norms ? t_tma_run<T, PXB_PD3O, true, S, M>(K, p, a, chunk, id) : t_tma_run<T, PXB_PD3O, false, S, M>(K, p, a, chunk, id)) \
+                                  : (norms ? t_tma_run<T, PXB_CV, true, S, M>(K, p, a, chunk, id) : t_tma_run<T, PXB_CV, false, S, M>(K, p, a, chunk, id));       \
         if (rc != -130) return rc;                                                                                      \
     }
+#define EMU_TMA_TRY(S, id) EMU_TMA_TRY_M(S, id, false)
+    EMU_TMA_TRY_M(PxbSpecAny, 0, true)
     EMU_TMA_TRY(PxbSpecFwdPos, 1)
     EMU_TMA_TRY(PxbSpecFwdNone, 2)
     if (algo == PXB_CV) {
@@ -261,6 +275,7 @@ static int t_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
     }
     EMU_TMA_TRY(PxbSpecAny, 0)
 #undef EMU_TMA_TRY
+#undef EMU_TMA_TRY_M
     return -131;
 }
 
@@ -359,17 +374,19 @@ static void emu_box3(const T* base, const int64_t dim[3], int64_t s1, int64_t s2
             dst[i * bw + j] = in ? base[x + y * s1 + c2 * s2] : T(0);
         }
 }
-template <class T, int ALGO, bool NORMS, class S>
+template <class T, int ALGO, bool NORMS, class S, bool MODES = false>
 static int t_t2_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, bool want_fwd) {
     constexpr int VEC = 16 / (int)sizeof(T);
     using C = PxbT2Cfg<T, VEC>;
     PxbTvCoef cf;
     PxbTvP<T> q;
     PxbT2Geom g;
-    if (int why = pxb_t2_setup<T, VEC>(*K, *p, cf, q, g)) return -100 - why;
+    if (int why = pxb_t2_setup<T, VEC>(*K, *p, cf, q, g, g_allow_modes)) return -100 - why;
+    if (pxb_any_mode(*K) != MODES) return -130;
+    const PxbModeCtx mc{K, p};
     bool fwd = true;
     for (int k = 0; k < 2; ++k) fwd = fwd && cf.cm[k] == 0.0 && cf.cp[k] != 0.0;
-    if ((fwd && q.hkind == PXB_DUAL_L21) != want_fwd) return -130;
+    if (!MODES && (fwd && q.hkind == PXB_DUAL_L21) != want_fwd) return -130;
     std::vector<T> sm(C::TOTAL);
     const int64_t du[3] = {g.n2, g.n1, g.nimg}, dz[3] = {g.n2, g.n1, g.nimg * 2}, ds[3] = {g.n2, g.n1, g.sh_mode ? g.n0 : g.nimg};
     const T* sptr = q.fkind == PXB_F_GRADARR ? q.garr : q.shift;
@@ -383,7 +400,7 @@ static int t_t2_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIt
         emu_box3<T>(a.z_in, dz, g.n2, g.s0, C::BW, C::BRZ, cc, cr - 1, pz, sm.data() + C::OFF_ZR);
         emu_box3<T>(a.z_in, dz, g.n2, g.s0, C::BW, C::BR, cc, cr, pz + g.n0, sm.data() + C::OFF_ZC);
         double acc[4] = {0, 0, 0, 0};
-        for (int tid = 0; tid < C::NT; ++tid) pxb_t2_phaseA<T, VEC, ALGO, NORMS, S>(q, g, it, a, tid, sm.data(), acc);
+        for (int tid = 0; tid < C::NT; ++tid) pxb_t2_phaseA<T, VEC, ALGO, NORMS, S, MODES>(q, g, it, a, tid, sm.data(), acc, mc);
         for (int tid = 0; tid < C::NT; ++tid) pxb_t2_phaseC<T, VEC, NORMS, S>(q, g, it, a, tid, sm.data(), acc);
         if (NORMS) {
             if (a.norms_x) { a.norms_x[2 * it.b] += acc[0]; a.norms_x[2 * it.b + 1] += acc[1]; }
@@ -399,15 +416,18 @@ static int t_t2(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const
     PxbIterPtr<T> a{(const T*)u_in, (const T*)z_in, (T*)u_out, (T*)z_out, (T*)x_out, nx, nz};
     const bool norms = nx || nz;
     using SF = PxbSpec<PXB_SCHEME_FWD, -1, PXB_DUAL_L21, -1>;
-#define EMU_T2_TRY(S, fw)                                                                                             \
+#define EMU_T2_TRY_M(S, fw, M)                                                                                        \
     {                                                                                                                 \
-        int rc = algo == PXB_PD3O ? (norms ? t_t2_run<T, PXB_PD3O, true, S>(K, p, a, fw) : t_t2_run<T, PXB_PD3O, false, S>(K, p, a, fw)) \
-                                  : (norms ? t_t2_run<T, PXB_CV, true, S>(K, p, a, fw) : t_t2_run<T, PXB_CV, false, S>(K, p, a, fw));       \
+        int rc = algo == PXB_PD3O ? (norms ? t_t2_run<T, PXB_PD3O, true, S, M>(K, p, a, fw) : t_t2_run<T, PXB_PD3O, false, S, M>(K, p, a, fw)) \
+                                  : (norms ? t_t2_run<T, PXB_CV, true, S, M>(K, p, a, fw) : t_t2_run<T, PXB_CV, false, S, M>(K, p, a, fw));       \
         if (rc != -130) return rc;                                                                                    \
     }
+#define EMU_T2_TRY(S, fw) EMU_T2_TRY_M(S, fw, false)
+    EMU_T2_TRY_M(PxbSpecAny, false, true)
     EMU_T2_TRY(SF, true)
     EMU_T2_TRY(PxbSpecAny, false)
 #undef EMU_T2_TRY
+#undef EMU_T2_TRY_M
     return -131;
 }
 
@@ -546,6 +566,7 @@ int emu_stencil2d(const pxb_stencil2d* d, const void* in, void* out) {
 int emu_stencil2d_fista(const pxb_stencil2d* d, const pxb_fista_step* f, int which, void* out) {
     return d->dtype == PXB_F32 ? t_st2<float>(d, f, which, nullptr, out) : t_st2<double>(d, f, which, nullptr, out);
 }
+void emu_set_iter_modes(int on) { g_allow_modes = on != 0; }
 int emu_tv_iter_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
                     void* x_out, double* nx, double* nz, int chunk) {
     if (K->dtype == PXB_F32) return t_tma<float>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);

@@ -66,6 +66,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.pxb_stencil_axis0_apply(0, 1, one, None, 3, 5, (C.c_double * 3)(1, 2, 1), C.c_void_p(16), C.c_void_p(32), None) == -1  # center outside the kernel
     assert lib.pxb_pds_iter(0, None, None, None, None, None, None, None, None, None, None) == -1
     assert lib.pxb_set_iter_path(7) == -1 and lib.pxb_set_iter_path(0) == 0
+    assert lib.pxb_set_iter_modes(2) == -1
     g = K.GradDesc()
     g.ndir = 7
     rc = lib.pxb_gradient_apply(C.byref(g), C.c_void_p(8), C.c_void_p(16), None)

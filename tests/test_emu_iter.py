@@ -117,7 +117,12 @@ def test_iter_not_eligible():
     P = E.pds_params(0.3, 0.25, 1.0, hkind=K.DUAL_L21, lam=0.2)
     a = np.zeros(Kop.dim)
     z = np.zeros(Kop.codim)
-    assert E.lib().emu_tv_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), E.p(a), E.p(z), E.p(a.copy()), E.p(z.copy()), None, None, None, 0) == -104
+    E.lib().emu_set_iter_modes(0)  # pxb_set_iter_modes(0): folding modes are declined (callers take the two-sweep form)
+    try:
+        for fn in (E.lib().emu_tv_iter, E.lib().emu_tv_tile2d):
+            assert fn(K.ALGO_PD3O, C.byref(d), C.byref(P), E.p(a), E.p(z), E.p(a.copy()), E.p(z.copy()), None, None, None, 0) == -104
+    finally:
+        E.lib().emu_set_iter_modes(1)
     Kop = pxo.Gradient(arg_shape=(8, 15))  # last axis not a multiple of the vector width
     d = Kop._desc(1, K.F64)
     assert E.lib().emu_tv_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), E.p(a), E.p(z), E.p(a.copy()), E.p(z.copy()), None, None, None, 0) == -105
@@ -261,3 +266,118 @@ def test_tile2d_form_fp64_shift_modes_and_golden(scheme):
         for _ in range(60):
             u, z = one_pass(K.ALGO_PD3O, d, P, u, z, x, form="tile2d")
         assert relerr(x, g["pd3o_tv2d/s1/x"]) < 1e-10 and relerr(z, g["pd3o_tv2d/s1/z"]) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Folding boundary modes (numpy.pad wrap / reflect / symmetric / edge, pad.py:252-302) inside the single-kernel forms:
+# the MODES instances recompute the two-sample band along each folding face and the out-of-domain rim of the w tiles
+# through the per-sample boundary map / pre-image gather.  Reference: the generic two-pass bodies (themselves checked
+# against fixtures of the real reference for every mode, test_emu_kernels.py).
+# ---------------------------------------------------------------------------------------------------------
+MODES = ["wrap", "reflect", "symmetric", "edge"]
+
+
+@pytest.mark.parametrize("mode", MODES + [("constant", "reflect", "wrap"), ("edge", "constant", "symmetric")])
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("form", ["direct", "tma"])
+def test_iter_modes_3d(mode, scheme, form):
+    rng = np.random.default_rng(21)
+    for dtype, shape in ((np.float64, (7, 19, 2 * 64 + 6)), (np.float32, (3, 9, 4 * 32 + 8)), (np.float64, (3, 3, 4))):
+        Kop = pxo.Gradient(arg_shape=shape, scheme=scheme, mode=mode, sampling=(1.0, 0.5, 2.0))
+        d = Kop._desc(1, E.dcode(np.zeros(1, dtype=dtype)))
+        shift = rng.standard_normal(Kop.dim).astype(dtype)
+        for algo in (K.ALGO_PD3O, K.ALGO_CV):
+            P = E.pds_params(0.21, 0.19, 0.9, gspec=(K.PROX_POS, 0.0, 0.0), fkind=K.F_SQL2, alpha=0.7, shift=shift, hkind=K.DUAL_L21, lam=0.3)
+            for chunk in (0, 3):
+                u = rng.standard_normal(Kop.dim).astype(dtype)
+                x = rng.standard_normal(Kop.dim).astype(dtype)
+                z = rng.standard_normal(Kop.codim).astype(dtype)
+                ua, za, xa = u.copy(), z.copy(), x.copy()
+                nxa, nza, nxb, nzb = np.zeros(2), np.zeros(2), np.zeros(2), np.zeros(2)
+                two_pass(algo, d, P, ua, za, xa, nxa, nza)
+                xb = x.copy()
+                ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=chunk, form=form)
+                tol = 1e-13 if dtype == np.float64 else 2e-6
+                assert relerr(ub, ua) < tol and relerr(zb, za) < tol, (mode, scheme, algo, chunk, shape)
+                if algo == K.ALGO_PD3O:
+                    assert relerr(xb, xa) < tol
+                rt = 1e-5 if dtype == np.float32 else 1e-10
+                assert np.allclose(nxa, nxb, rtol=rt) and np.allclose(nza, nzb, rtol=rt)
+
+
+@pytest.mark.parametrize("mode", MODES + [("reflect", "wrap"), ("constant", "edge")])
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("form", ["direct", "tile2d"])
+def test_iter_modes_2d_batched(mode, scheme, form):
+    rng = np.random.default_rng(23)
+    for dtype, shape, batch in ((np.float32, (37, 300), 2), (np.float64, (16, 64), 1), (np.float64, (3, 4), 3)):
+        Kop = pxo.Gradient(arg_shape=shape, scheme=scheme, mode=mode)
+        d = Kop._desc(batch, E.dcode(np.zeros(1, dtype=dtype)))
+        shift = rng.standard_normal((batch, Kop.dim)).astype(dtype)
+        garr = rng.standard_normal((batch, Kop.dim)).astype(dtype)
+        u = rng.standard_normal((batch, Kop.dim)).astype(dtype)
+        x = rng.standard_normal((batch, Kop.dim)).astype(dtype)
+        z = rng.standard_normal((batch, Kop.codim)).astype(dtype)
+        cases = [(K.ALGO_PD3O, dict(fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L21)),
+                 (K.ALGO_CV, dict(fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L1)),
+                 (K.ALGO_CV, dict(fkind=K.F_GRADARR, garr=garr, hkind=K.DUAL_L21))]
+        for algo, kw in cases:
+            P = E.pds_params(0.3, 0.25, 0.95, gspec=(K.PROX_L1, 0.05, 0.0), lam=0.2, **kw)
+            ua, za, xa = u.copy(), z.copy(), x.copy()
+            nxa, nza, nxb, nzb = (np.zeros(2 * batch) for _ in range(4))
+            two_pass(algo, d, P, ua, za, xa, nxa, nza)
+            xb = x.copy()
+            ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, form=form)
+            tol = 1e-13 if dtype == np.float64 else 2e-6
+            assert relerr(ub, ua) < tol and relerr(zb, za) < tol, (mode, scheme, algo, shape)
+            if algo == K.ALGO_PD3O:
+                assert relerr(xb, xa) < tol
+            rt = 1e-5 if dtype == np.float32 else 1e-10
+            assert np.allclose(nxa, nxb, rtol=rt) and np.allclose(nza, nzb, rtol=rt)
+
+
+def test_iter_modes_stacked_2d_in_3d_shape():
+    """2-D gradient over the last two axes of a 3-D arg_shape: axis 0 enumerates images, its mode is never consulted."""
+    rng = np.random.default_rng(25)
+    Kop = pxo.Gradient(arg_shape=(3, 11, 24), directions=(1, 2), mode=("constant", "reflect", "wrap"))
+    d = Kop._desc(2, K.F64)
+    shift = np.r_[0.2]  # (kept alive: the parameter block only holds its address)
+    P = E.pds_params(0.3, 0.25, 0.8, gspec=(K.PROX_POS, 0.0, 0.0), fkind=K.F_SQL2, alpha=0.4, shift=shift, hkind=K.DUAL_L21, lam=0.2)
+    u, x, z = rng.standard_normal((2, Kop.dim)), rng.standard_normal((2, Kop.dim)), rng.standard_normal((2, Kop.codim))
+    for form in ("direct", "tile2d"):
+        ua, za, xa = u.copy(), z.copy(), x.copy()
+        two_pass(K.ALGO_PD3O, d, P, ua, za, xa)
+        xb = x.copy()
+        ub, zb = one_pass(K.ALGO_PD3O, d, P, u, z, xb, form=form)
+        assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13 and relerr(xb, xa) < 1e-13
+
+
+def _solve_modes(prefix, shape, mode, n_iter, lam, gspec, y, x0, form):
+    g = golden("solvers.npz")
+    tau, sigma, rho = (float(g[f"{prefix}/{k}"]) for k in ("tau", "sigma", "rho"))
+    Kop = pxo.Gradient(arg_shape=shape, mode=mode)
+    shift = np.ascontiguousarray(-y.reshape(-1))
+    P = E.pds_params(tau, sigma, rho, gspec=gspec, fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L21, lam=lam)
+    d = Kop._desc(1, K.F64)
+    x = np.ascontiguousarray(x0, dtype=np.float64).copy()
+    z = E.gradient_run(Kop, x, False)
+    u = x.copy()
+    for _ in range(n_iter):
+        u, z = one_pass(K.ALGO_PD3O, d, P, u, z, x, form=form)
+    return x, z, g
+
+
+@pytest.mark.parametrize("mode", ["reflect", "wrap", "symmetric", "edge"])
+@pytest.mark.parametrize("form", ["direct", "tile2d"])
+def test_iter_modes_golden_2d(mode, form):
+    """40 PD3O iterations with a folding boundary mode against the real reference's NumPy float64 solver (<= 1e-10)."""
+    y = golden("solvers.npz")["pd3o_tv2d/y"]
+    x, z, g = _solve_modes(f"pd3o_tv2d/{mode}", (32, 40), mode, 40, 0.15, (K.PROX_NONE, 0.0, 0.0), y, np.zeros(y.size), form)
+    assert relerr(x, g[f"pd3o_tv2d/{mode}/x"]) < 1e-10 and relerr(z, g[f"pd3o_tv2d/{mode}/z"]) < 1e-10
+
+
+@pytest.mark.parametrize("form", ["direct", "tma"])
+def test_iter_modes_golden_3d_mixed(form):
+    y3 = golden("solvers.npz")["pd3o_tv3d/y"]
+    x, z, g = _solve_modes("pd3o_tv3d/mixed", (10, 12, 14), ("reflect", "wrap", "constant"), 30, 0.08, POS, y3, y3.reshape(-1), form)
+    assert relerr(x, g["pd3o_tv3d/mixed/x"]) < 1e-10 and relerr(z, g["pd3o_tv3d/mixed/z"]) < 1e-10
