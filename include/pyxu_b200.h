@@ -283,7 +283,8 @@ int pxb_pds_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void* w,
  * Same algebra as pxb_pds_primal followed by pxb_pds_dual (pds.py:429-442, :747-761); w never leaves the SM.
  * norms_x / norms_z (nullable): per batch row += { sum (new-old)^2, sum old^2 } for x (PD3O: against the previous
  * content of x_out) and z.
- * Envelope: K a 2- or 3-direction first-order Gradient with 'constant' boundaries, 16-byte aligned arrays, last
+ * Envelope: K a 2- or 3-direction first-order Gradient (any boundary mode on single-domain arrays, 'constant' on slabs;
+ * see pxb_set_iter_modes), 16-byte aligned arrays, last
  * axis a multiple of 4 (fp32) / 2 (fp64) samples, h = lam*L21 | lam*L1, f pointwise (PD3O) or any (CV, garr).
  * Returns PXB_ENOSUP outside the envelope: callers fall back to the two-pass form.
  * With an open slab side the ghost planes of xu_in, z_in (and of the shift array) must hold the neighbour's data. */
@@ -293,11 +294,11 @@ int pxb_pds_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
  * 1 = direct-load form only, 2 = TMA form only (PXB_ENOSUP when it does not apply).  Environment variable
  * PXB_TV_ITER=direct|tma sets the initial value.  For A/B measurements and tests. */
 int pxb_set_iter_path(int path);
-/* Folding boundary modes (wrap / reflect / symmetric / edge; pad.py:252-302) inside pxb_pds_iter: 1 = the single-kernel
- * forms serve them too (the samples within two of a folding face, and the out-of-domain rim of the w tiles, go through
- * the per-sample boundary map / pre-image gather; single-domain arrays only), 0 = PXB_ENOSUP as before, so that callers
- * take pxb_pds_primal + pxb_pds_dual, -1 = back to the initial value (environment variable PXB_TV_ITER_MODES=0|1, else the
- * library's default). */
+/* Folding boundary modes (wrap / reflect / symmetric / edge; pad.py:252-302) inside pxb_pds_iter: 1 (default) = the
+ * single-kernel forms serve them too (the samples within two of a folding face, and the out-of-domain rim of the w
+ * tiles, go through the per-sample boundary map / pre-image gather; single-domain arrays only: slabs answer PXB_ENOSUP),
+ * 0 = PXB_ENOSUP for every folding mode, so that callers take pxb_pds_primal + pxb_pds_dual (A/B measurements, tests),
+ * -1 = back to the initial value (environment variable PXB_TV_ITER_MODES=0|1, else 1). */
 int pxb_set_iter_modes(int on);
 /* same, with the number of planes one thread block marches through fixed by the caller (tuning / tests) */
 int pxb_pds_iter_chunked(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in,

@@ -330,9 +330,9 @@ int pxb_iter_path() {
     return v;
 }
 
-// Default of the folding-mode instances of the single-kernel iteration (see pxb_set_iter_modes).
+// Default of the folding-mode instances of the single-kernel iteration (see pxb_set_iter_modes): on.
 #ifndef PXB_ITER_MODES_DEFAULT
-#define PXB_ITER_MODES_DEFAULT 0
+#define PXB_ITER_MODES_DEFAULT 1
 #endif
 static std::atomic<int> g_iter_modes{-1};
 int pxb_iter_modes() {

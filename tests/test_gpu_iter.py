@@ -153,8 +153,12 @@ def test_iter_envelope_errors(env):
     u, z = torch.zeros(Kop.dim, device="cuda", dtype=torch.float64), torch.zeros(Kop.codim, device="cuda", dtype=torch.float64)
     u2, z2 = u.clone(), z.clone()
     n0 = lib.pxb_launch_count()
-    assert lib.pxb_pds_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), u.data_ptr(), z.data_ptr(), u2.data_ptr(), z2.data_ptr(), None, None, None, None) == -3
-    assert b"reason 4" in lib.pxb_last_error()
+    K.check(lib.pxb_set_iter_modes(0), "pxb_set_iter_modes")  # folding modes declined: callers take the two-sweep form
+    try:
+        assert lib.pxb_pds_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), u.data_ptr(), z.data_ptr(), u2.data_ptr(), z2.data_ptr(), None, None, None, None) == -3
+        assert b"reason 4" in lib.pxb_last_error()
+    finally:
+        lib.pxb_set_iter_modes(-1)
     assert lib.pxb_pds_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), u.data_ptr(), z.data_ptr(), u.data_ptr(), z2.data_ptr(), None, None, None, None) == -1
     assert lib.pxb_launch_count() == n0  # nothing was launched
 
