@@ -59,6 +59,9 @@ struct PxbTvP {
     int64_t s0, s1, vol;  // vol: elements between components / batch items
     int mode[3];
     int open_lo, open_hi;
+    // Folding boundary modes, per AXIS (see pxb_tv_fold_kz): the sample whose K^T z gains cp*z[n-1] (fold_hi) / cm*z[0]
+    // (fold_lo) on top of the 'constant' arithmetic; PXB_NOSRC when the axis does not fold or the tap is absent.
+    int fold_hi[3], fold_lo[3];
 };
 
 
@@ -96,8 +99,16 @@ PXB_HD void pxb_tv_prepare(const pxb_grad_desc& d, const PxbTvCoef& cf, const px
     const PxbGeom g = pxb_geom(d.shape);
     q.n0 = g.n0; q.n1 = g.n1; q.n2 = g.n2; q.s0 = g.s0; q.s1 = g.s1;
     q.vol = pxb_vol(g, d.slab);
-    for (int a = 0; a < 3; ++a) q.mode[a] = d.mode[a];
+    for (int a = 0; a < 3; ++a) { q.mode[a] = d.mode[a]; q.fold_hi[a] = q.fold_lo[a] = PXB_NOSRC; }
     q.open_lo = d.slab.open_lo; q.open_hi = d.slab.open_hi;
+    if (d.slab.halo == 0 && !d.slab.open_lo && !d.slab.open_hi && d.ndir <= 3) {
+        for (int k = 0; k < d.ndir; ++k) {
+            const int ax = 3 - d.ndir + k, n = ax == 0 ? g.n0 : (ax == 1 ? g.n1 : g.n2);
+            if (d.mode[ax] == PXB_CONSTANT) continue;
+            if (cf.cp[k] != 0.0) q.fold_hi[ax] = pxb_bmap(n, n, d.mode[ax]);
+            if (cf.cm[k] != 0.0) q.fold_lo[ax] = pxb_bmap(-1, n, d.mode[ax]);
+        }
+    }
     q.shift = (const T*)P.f.shift; q.garr = (const T*)P.f.garr; q.shift_period = P.f.shift_period;
     q.shift_mode = PXB_SHIFT_NONE;
     if (P.f.kind == PXB_F_SQL2 && P.f.shift) {
@@ -213,6 +224,127 @@ PXB_HD void pxb_tv_taps_col(const T* __restrict__ f, int64_t st, const PxbVec<T,
     if (c_lo != T(0) && has_lo) {
         const PxbVec<T, VEC> dn = pxb_vload<T, VEC>(f - st);
         for (int j = 0; j < VEC; ++j) out[j] += c_lo * dn.v[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Folding boundary modes (numpy.pad wrap / reflect / symmetric / edge, pad.py:252-302) for radius-1 taps.
+// K_k = Trim o S_k o Pad_k pads axis ax by one sample on the side(s) where S_k has a tap, so
+//     (K_k w)[s]   = cm w[m(s-1)] + c0 w[s] + cp w[m(s+1)]             m = the boundary map (pxb_bmap)
+//     (K_k^T z)[t] = 'constant' arithmetic + [t == m(n)] cp z[n-1] + [t == m(-1)] cm z[0]
+// (the transpose of Pad adds the padded cell n, resp. -1, onto the sample it was copied from, pad.py:307-375; of the
+// taps that reach that cell only z[n-1] through cp, resp. z[0] through cm, lie inside the domain).  One sample per
+// line and side gains one term: m(n) = 0 | n-2 | n-1 | n-1 and m(-1) = n-1 | 1 | 0 | 0 for wrap | reflect | symmetric |
+// edge -- folded on the host into PxbTvP::fold_hi / fold_lo.  The term is added from global memory (one coalesced
+// vector load for a row / plane face, one scalar load by one lane for a column face).
+//   zimg: component 0 of the batch item, sample (0, 0, 0);  the W samples (i0, i1, i2..) lie inside the domain.
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int W, int NDIR>
+PXB_HD void pxb_tv_fold_kz(const PxbTvP<T>& q, const T* __restrict__ zimg, int i0, int i1, int i2, T* kz) {
+    const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1;
+    for (int k = 0; k < NDIR; ++k) {
+        const int ax = 3 - NDIR + k;
+        const T* __restrict__ zk = zimg + k * q.vol;
+        if (ax == 2) {
+            const int th = q.fold_hi[2], tl = q.fold_lo[2];
+            if (th >= i2 && th < i2 + W) {
+                const T zf = zk[v + q.n2 - 1];
+                for (int j = 0; j < W; ++j)
+                    if (i2 + j == th) kz[j] += q.cp[k] * zf;
+            }
+            if (tl >= i2 && tl < i2 + W) {
+                const T zf = zk[v];
+                for (int j = 0; j < W; ++j)
+                    if (i2 + j == tl) kz[j] += q.cm[k] * zf;
+            }
+        } else {
+            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? q.n0 : q.n1;
+            const int64_t st = ax == 0 ? q.s0 : q.s1;
+            const T* __restrict__ line = zk + v + i2 - (int64_t)i * st;
+            if (i == q.fold_hi[ax]) {
+                const PxbVec<T, W> f = pxb_vload<T, W>(line + (int64_t)(n - 1) * st);
+                for (int j = 0; j < W; ++j) kz[j] += q.cp[k] * f.v[j];
+            }
+            if (i == q.fold_lo[ax]) {
+                const PxbVec<T, W> f = pxb_vload<T, W>(line);
+                for (int j = 0; j < W; ++j) kz[j] += q.cm[k] * f.v[j];
+            }
+        }
+    }
+}
+
+// w = the point K is applied to in the dual half-step, for W in-domain samples starting at (b, i0, i1, i2), straight
+// from global memory with every boundary mode honoured.  The tiled single-kernel forms call it for the cells of
+// their w tiles that lie one step outside the domain (K w reads there w at the sample the boundary map folds the cell
+// onto); out of line: a vanishing fraction of the cells takes it, its registers must not weigh on the tiled path.
+template <class T, int W, int NDIR, int ALGO>
+PXB_NOINLINE void pxb_tv_w_global(const PxbTvP<T>& q, const T* __restrict__ xu, const T* __restrict__ z, int64_t b, int i0, int i1, int i2, T* wv) {
+    const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2;
+    const int64_t lin = b * q.vol + v;
+    const T* __restrict__ zimg = z + b * NDIR * q.vol;
+    T kz[W];
+    for (int j = 0; j < W; ++j) kz[j] = T(0);
+    for (int k = 0; k < NDIR; ++k) {
+        const int ax = 3 - NDIR + k;
+        const T* __restrict__ zk = zimg + k * q.vol + v;
+        const PxbVec<T, W> c = pxb_vload<T, W>(zk);
+        T t[W];
+        if (ax == 2) {
+            pxb_tv_taps_row<T, W>(zk, c, q.cm[k], q.c0[k], q.cp[k], i2 > 0, i2 + W < q.n2, t);
+        } else {
+            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? q.n0 : q.n1;
+            pxb_tv_taps_col<T, W>(zk, ax == 0 ? q.s0 : q.s1, c, q.cm[k], q.c0[k], q.cp[k], i > 0, i < n - 1, t);
+        }
+        for (int j = 0; j < W; ++j) kz[j] += t[j];
+    }
+    pxb_tv_fold_kz<T, W, NDIR>(q, zimg, i0, i1, i2, kz);
+    const PxbVec<T, W> old = pxb_vload<T, W>(xu + lin);
+    PxbVec<T, W> sh;
+    for (int j = 0; j < W; ++j) sh.v[j] = T(0);
+    if (q.fkind == PXB_F_SQL2) {
+        if (q.shift_mode == PXB_SHIFT_LIN) sh = pxb_vload<T, W>(q.shift + lin);
+        else if (q.shift_mode == PXB_SHIFT_VOL) sh = pxb_vload<T, W>(q.shift + v);
+        else if (q.shift_mode == PXB_SHIFT_SCALAR) { for (int j = 0; j < W; ++j) sh.v[j] = q.shift[0]; }
+        else if (q.shift_mode == PXB_SHIFT_MOD) { for (int j = 0; j < W; ++j) sh.v[j] = q.shift[(lin + j) % q.shift_period]; }
+    } else if (q.fkind == PXB_F_GRADARR) {
+        sh = pxb_vload<T, W>(q.garr + lin);
+    }
+    for (int j = 0; j < W; ++j) {
+        if (ALGO == PXB_PD3O) {
+            const T x = pxb_prox_eval<T>(q.gkind, q.gp0, q.gp1, old.v[j] - q.tau * kz[j], q.tau);
+            const T gf = (q.fkind == PXB_F_SQL2) ? (x + sh.v[j]) * q.two_alpha : T(0);
+            wv[j] = x + (x - q.tau * gf) - old.v[j];
+        } else {
+            T gf = T(0);
+            if (q.fkind == PXB_F_SQL2) gf = (old.v[j] + sh.v[j]) * q.two_alpha;
+            else if (q.fkind == PXB_F_GRADARR) gf = sh.v[j];
+            const T xt = pxb_prox_eval<T>(q.gkind, q.gp0, q.gp1, old.v[j] - q.tau * gf - q.tau * kz[j], q.tau);
+            wv[j] = T(2) * xt - old.v[j];
+        }
+    }
+}
+
+// The W cells starting at (i0, i1, i2) of a w tile, not all inside the domain: what K w reads there.  A cell one step
+// outside along exactly one folding axis holds w at the sample the boundary map sends it to; nothing reads the others
+// ('constant' axes read zeros; corners and cells further out are never touched by an axis-aligned radius-1 stencil).
+// Row vectors are W-aligned and n2 is a multiple of W, so along the columns only cell 0 of the vector can be "n2".
+template <class T, int W, int NDIR, int ALGO>
+PXB_HD void pxb_tv_w_outside(const PxbTvP<T>& q, const T* __restrict__ xu, const T* __restrict__ z, int64_t b, int i0, int i1, int i2, T* wv) {
+    for (int j = 0; j < W; ++j) wv[j] = T(0);
+    const bool o0 = NDIR == 3 && (i0 < 0 || i0 >= q.n0), o1 = i1 < 0 || i1 >= q.n1, o2 = i2 < 0 || i2 >= q.n2;
+    if ((o0 ? 1 : 0) + (o1 ? 1 : 0) + (o2 ? 1 : 0) != 1) return;
+    if (NDIR == 2 && (i0 < 0 || i0 >= q.n0)) return;
+    if (o2) {
+        if ((i2 != -1 && i2 != q.n2) || q.mode[2] == PXB_CONSTANT) return;
+        T w1[1];
+        pxb_tv_w_global<T, 1, NDIR, ALGO>(q, xu, z, b, i0, i1, pxb_bmap(i2, q.n2, q.mode[2]), w1);
+        wv[0] = w1[0];
+    } else if (o1) {
+        if ((i1 != -1 && i1 != q.n1) || q.mode[1] == PXB_CONSTANT) return;
+        pxb_tv_w_global<T, W, NDIR, ALGO>(q, xu, z, b, i0, pxb_bmap(i1, q.n1, q.mode[1]), i2, wv);
+    } else {
+        if ((i0 != -1 && i0 != q.n0) || q.mode[0] == PXB_CONSTANT) return;
+        pxb_tv_w_global<T, W, NDIR, ALGO>(q, xu, z, b, pxb_bmap(i0, q.n0, q.mode[0]), i1, i2, wv);
     }
 }
 

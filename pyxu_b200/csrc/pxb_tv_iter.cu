@@ -13,8 +13,7 @@ namespace {
 // occupancy target: 3 CTAs of 256 threads per SM (<= 80 registers), each with ~20 KB of ring
 template <class T, int VEC, int TXL, int TY, int NDIR, int ALGO, bool NORMS, bool MODES>
 __global__ void __launch_bounds__(TXL* TY, (TXL * TY >= 256 ? 3 : 6))
-    k_tv_iter(const __grid_constant__ PxbTvP<T> q, const __grid_constant__ PxbIterGeom g, const __grid_constant__ PxbIterPtr<T> a,
-              const __grid_constant__ PxbModeArgs<MODES> ma) {
+    k_tv_iter(const __grid_constant__ PxbTvP<T> q, const __grid_constant__ PxbIterGeom g, const __grid_constant__ PxbIterPtr<T> a) {
     using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
     extern __shared__ __align__(16) unsigned char pxb_iter_smem[];
     T* smem = reinterpret_cast<T*>(pxb_iter_smem);
@@ -27,7 +26,7 @@ __global__ void __launch_bounds__(TXL* TY, (TXL * TY >= 256 ? 3 : 6))
     for (int k = 0; k < 4; ++k) st.acc[k] = 0.0;
 
     for (int m = R.mlo; m < R.mhi; ++m) {
-        pxb_iter_phaseA<T, VEC, TXL, TY, NDIR, ALGO, NORMS, MODES>(q, g, it, a, tid, m, smem, st, ma.ctx());
+        pxb_iter_phaseA<T, VEC, TXL, TY, NDIR, ALGO, NORMS, MODES>(q, g, it, a, tid, m, smem, st);
         __syncthreads();
         const int mm = m - R.lag;
         if (mm >= it.m0 && mm < it.m1) {
@@ -65,22 +64,21 @@ __global__ void __launch_bounds__(TXL* TY, (TXL * TY >= 256 ? 3 : 6))
 }
 
 template <class T, int VEC, int TXL, int TY, int NDIR, int ALGO, bool NORMS, bool MODES>
-cudaError_t launch_inst(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterPtr<T>& a, const PxbModeArgs<MODES>& ma, cudaStream_t s) {
+cudaError_t launch_inst(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterPtr<T>& a, cudaStream_t s) {
     using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
     auto kern = k_tv_iter<T, VEC, TXL, TY, NDIR, ALGO, NORMS, MODES>;
     if (C::SMEM > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
     }
-    kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, a, ma);
+    kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, a);
     return cudaGetLastError();
 }
-// folding boundary modes run the MODES instance (per-sample path on the faces, see pxb_tv_iter.cuh)
+// folding boundary modes run the MODES instance (fold terms of K^T z, folded rim of the w tiles: pxb_tv_iter.cuh)
 template <class T, int VEC, int TXL, int TY, int NDIR, int ALGO, bool NORMS>
-cudaError_t launch_cfg(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterPtr<T>& a,
-                       cudaStream_t s) {
-    if (pxb_any_mode(d)) return launch_inst<T, VEC, TXL, TY, NDIR, ALGO, NORMS, true>(q, g, a, PxbModeArgs<true>{d, P}, s);
-    return launch_inst<T, VEC, TXL, TY, NDIR, ALGO, NORMS, false>(q, g, a, PxbModeArgs<false>{}, s);
+cudaError_t launch_cfg(const pxb_grad_desc& d, const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterPtr<T>& a, cudaStream_t s) {
+    if (pxb_any_mode(d)) return launch_inst<T, VEC, TXL, TY, NDIR, ALGO, NORMS, true>(q, g, a, s);
+    return launch_inst<T, VEC, TXL, TY, NDIR, ALGO, NORMS, false>(q, g, a, s);
 }
 
 template <class T>
@@ -98,12 +96,12 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
         constexpr int TXL = 32, TY = 8;
         if (int why = pxb_iter_setup(d, P, VEC, TY, TXL * VEC, chunk_hint, 148 * 3, cf, g, pxb_iter_modes() != 0)) return why;
         pxb_tv_prepare<T>(d, cf, P, q);
-        *err = launch_cfg<T, VEC, TXL, TY, 3, ALGO, NORMS>(d, P, q, g, a, s);
+        *err = launch_cfg<T, VEC, TXL, TY, 3, ALGO, NORMS>(d, q, g, a, s);
     } else {
         const bool narrow = d.shape[2] <= 128 * VEC;
         if (int why = pxb_iter_setup(d, P, VEC, 1, (narrow ? 128 : 256) * VEC, chunk_hint, 148 * 3, cf, g, pxb_iter_modes() != 0)) return why;
         pxb_tv_prepare<T>(d, cf, P, q);
-        *err = narrow ? launch_cfg<T, VEC, 128, 1, 2, ALGO, NORMS>(d, P, q, g, a, s) : launch_cfg<T, VEC, 256, 1, 2, ALGO, NORMS>(d, P, q, g, a, s);
+        *err = narrow ? launch_cfg<T, VEC, 128, 1, 2, ALGO, NORMS>(d, q, g, a, s) : launch_cfg<T, VEC, 256, 1, 2, ALGO, NORMS>(d, q, g, a, s);
     }
     return 0;
 }

@@ -111,105 +111,23 @@ PXB_HD PxbIterItem pxb_iter_item(const PxbIterGeom& g, int64_t blk, int ty, int 
 
 
 // ---------------------------------------------------------------------------------------------------------
-// Boundary modes other than 'constant' (numpy.pad wrap / reflect / symmetric / edge).  The tiled forms keep their
-// 'constant' arithmetic everywhere except (a) in-domain samples within two samples of a folding face, where K^T z
-// gathers through the pre-images of the boundary map, and (b) the out-of-domain rim cells / planes of the w ring,
-// which must hold w at the sample the boundary map folds them onto (K w reads them as the padded array).  Both go
-// through this per-sample function: generic bodies of pxb_core.cuh, operands from global memory, out of line so that
-// its registers do not weigh on the tiled path (a vanishing fraction of the samples takes it).
-//   res = { w, x, new primal iterate, old primal iterate };  coordinates may lie outside the domain along one axis.
+// Boundary modes other than 'constant' (numpy.pad wrap / reflect / symmetric / edge): the MODES instances of the tiled
+// forms keep the 'constant' arithmetic and add (a) to K^T z of the one sample per line and side onto which the padded
+// cell folds, one term from global memory (pxb_tv_fold_kz), and (b) into the cells of the w tile that lie one step
+// outside the domain, w at the sample the boundary map folds them onto (pxb_tv_w_outside), because K w reads them as
+// the padded array.  Nothing else changes: phase C is the 'constant' code.
 // ---------------------------------------------------------------------------------------------------------
-template <class T, int ALGO>
-PXB_NOINLINE void pxb_w_at_any(const pxb_grad_desc& d, const pxb_pds_params& P, const T* u_in, const T* z_in, int64_t b, int i0, int i1, int i2,
-                               T* res) {
-    const PxbGeom gg = pxb_geom(d.shape);
-    const int j0 = pxb_bmap(i0, gg.n0, d.mode[0], d.slab.open_lo, d.slab.open_hi), j1 = pxb_bmap(i1, gg.n1, d.mode[1]), j2 = pxb_bmap(i2, gg.n2, d.mode[2]);
-    if (j0 == PXB_NOSRC || j1 == PXB_NOSRC || j2 == PXB_NOSRC) {
-        res[0] = res[1] = res[2] = res[3] = T(0);
-        return;
-    }
-    const int64_t vol = pxb_vol(gg, d.slab);
-    const int64_t lin = b * vol + (int64_t)j0 * gg.s0 + (int64_t)j1 * gg.s1 + j2;
-    T kz = T(0);
-    if (P.hkind != PXB_DUAL_NONE) kz = pxb_grad_adj_at<T>(d, gg, z_in + b * d.ndir * vol, vol, j0, j1, j2);
-    const T old = u_in[lin];
-    T un, xo, wo;
-    pxb_primal_at<T>(ALGO, P, kz, old, lin, un, xo, wo);
-    res[0] = wo; res[1] = xo; res[2] = un; res[3] = old;
-}
-
-// does the W-sample item at (i0, i1, i2 ..) leave the 'constant' arithmetic?  (outside the domain along an axis, or
-// within the two-sample band of a folding face)
-template <class T, int NDIR>
-PXB_HD bool pxb_item_needs_any(const PxbTvP<T>& q, int i0, int i1, int i2, int w) {
-    if (i0 < 0 || i0 >= q.n0 || i1 < 0 || i1 >= q.n1 || i2 < 0 || i2 >= q.n2) return true;
-    return pxb_tv_needs_generic<T, NDIR>(q, i0, i1, i2, w);
-}
 PXB_HD bool pxb_any_mode(const pxb_grad_desc& d) {
     for (int k = 0; k < d.ndir; ++k)
         if (d.mode[3 - d.ndir + k] != PXB_CONSTANT) return true;
     return false;
 }
 
-struct PxbModeCtx {  // full descriptors for the per-sample path (null d: every mode is 'constant')
-    const pxb_grad_desc* d;
-    const pxb_pds_params* P;
-};
-// kernel parameter carrying them by value: empty for the instances that only know 'constant'
-template <bool MODES>
-struct PxbModeArgs {
-    PXB_HD PxbModeCtx ctx() const { return PxbModeCtx{nullptr, nullptr}; }
-};
-template <>
-struct PxbModeArgs<true> {
-    pxb_grad_desc d;
-    pxb_pds_params P;
-    PXB_HD PxbModeCtx ctx() const { return PxbModeCtx{&d, &P}; }
-};
-
-// W samples starting at (i0, i1, i2) through the per-sample path.  Samples more than one step outside the domain are
-// never read by anybody (partial tiles): they are zero.
-template <class T, int W, int ALGO>
-PXB_HD void pxb_item_any(const PxbModeCtx& mc, const T* u_in, const T* z_in, int64_t b, int i0, int i1, int i2, T* wv, T* xo, T* un, T* uo) {
-    const pxb_grad_desc& d = *mc.d;
-    for (int j = 0; j < W; ++j) {
-        T res[4] = {T(0), T(0), T(0), T(0)};
-        const int c = i2 + j;
-        if (i0 >= -1 && i0 <= d.shape[0] && i1 >= -1 && i1 <= d.shape[1] && c >= -1 && c <= d.shape[2]) pxb_w_at_any<T, ALGO>(d, *mc.P, u_in, z_in, b, i0, i1, c, res);
-        wv[j] = res[0]; xo[j] = res[1]; un[j] = res[2]; uo[j] = res[3];
-    }
-}
-
-// stores + RelError[x] sums of an item whose new primal iterate was computed outside pxb_iter_w
-template <class T, int W, int ALGO, bool NORMS>
-PXB_HD void pxb_item_commit(const PxbIterPtr<T>& a, int64_t lin, const T* xo, const T* un, const T* uo, double* acc) {
-    PxbVec<T, W> o;
-    if (ALGO == PXB_PD3O) {
-        if (NORMS && a.norms_x) {
-            const PxbVec<T, W> xp = pxb_vload<T, W>(a.x_out + lin);
-            for (int j = 0; j < W; ++j) {
-                const double dd = (double)xo[j] - (double)xp.v[j];
-                acc[0] += dd * dd;
-                acc[1] += (double)xp.v[j] * (double)xp.v[j];
-            }
-        }
-        if (a.x_out) { for (int j = 0; j < W; ++j) o.v[j] = xo[j]; pxb_vstore<T, W>(a.x_out + lin, o); }
-    } else if (NORMS && a.norms_x) {
-        for (int j = 0; j < W; ++j) {
-            const double dd = (double)un[j] - (double)uo[j];
-            acc[0] += dd * dd;
-            acc[1] += (double)uo[j] * (double)uo[j];
-        }
-    }
-    for (int j = 0; j < W; ++j) o.v[j] = un[j];
-    pxb_vstore<T, W>(a.u_out + lin, o);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // w (and, when `store`, the new primal iterate) for W consecutive samples starting at (m, r, c).
 // The samples lie inside the domain or on a ghost plane of an open slab side.
 // ---------------------------------------------------------------------------------------------------------
-template <class T, int W, int NDIR, int ALGO, bool NORMS>
+template <class T, int W, int NDIR, int ALGO, bool NORMS, bool MODES = false>
 PXB_HD void pxb_iter_w(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int m, int r, int c,
                        bool store, T* wv, T (*zc)[W], double* acc) {
     constexpr bool HASR = NDIR == 3;
@@ -238,6 +156,7 @@ PXB_HD void pxb_iter_w(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterIt
         pxb_tv_taps_row<T, W>(zk, cv, q.cm[KC], q.c0[KC], q.cp[KC], c > 0, c + W < g.nC, t);
         for (int j = 0; j < W; ++j) kz[j] += t[j];
     }
+    if (MODES) pxb_tv_fold_kz<T, W, NDIR>(q, a.z_in + it.b * NDIR * g.vol, NDIR == 3 ? m : it.si, NDIR == 3 ? r : m, c, kz);
     const int64_t lin = it.lin_base + off;
     const PxbVec<T, W> old = pxb_vload<T, W>(a.u_in + lin);
     PxbVec<T, W> sh;
@@ -295,37 +214,21 @@ PXB_HD void pxb_iter_w(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterIt
 // ---------------------------------------------------------------------------------------------------------
 template <class T, int VEC, int TXL, int TY, int NDIR, int ALGO, bool NORMS, bool MODES = false>
 PXB_HD void pxb_iter_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid, int m,
-                            T* smem, PxbIterThread<T, VEC>& st, const PxbModeCtx mc = PxbModeCtx{nullptr, nullptr}) {
+                            T* smem, PxbIterThread<T, VEC>& st) {
     using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
     T* __restrict__ slot = smem + (m & 3) * C::SLOT;
     const bool plane_in = (m >= 0 || g.open_lo) && (m < g.nM || g.open_hi);
     const bool own = m >= it.m0 && m < it.m1;
     const int rl = tid / TXL, cx = tid - rl * TXL, cl = cx * VEC;
-    // (i0, i1, i2) of sample (m, r, c): NDIR == 3: (m, r, c);  NDIR == 2: (image index, m, c)
+    // (i0, i1) of sample (m, r): NDIR == 3: (m, r);  NDIR == 2: (image index, m)
 #define PXB_I0(m_, r_) (NDIR == 3 ? (m_) : it.si)
 #define PXB_I1(m_, r_) (NDIR == 3 ? (r_) : (m_))
     {
         const int r = it.r0 + rl, c = it.c0 + cl;
-        const bool in = plane_in && r < g.nR && c < g.nC;
-        bool fast = in;
-        if (MODES && fast) fast = !pxb_tv_needs_generic<T, NDIR>(q, PXB_I0(m, r), PXB_I1(m, r), c, VEC);
         PxbVec<T, VEC> wv;
-        if (fast) {
-            pxb_iter_w<T, VEC, NDIR, ALGO, NORMS>(q, g, it, a, m, r, c, own, wv.v, st.zc, st.acc);
-        } else if (MODES) {
-            T xo[VEC], un[VEC], uo[VEC];
-            pxb_item_any<T, VEC, ALGO>(mc, a.u_in, a.z_in, it.b, PXB_I0(m, r), PXB_I1(m, r), c, wv.v, xo, un, uo);
-            if (in) {
-                const int64_t off = (int64_t)m * g.sM + (int64_t)r * g.sR + c;
-                for (int k = 0; k < NDIR; ++k) {
-                    const PxbVec<T, VEC> zv = pxb_vload<T, VEC>(a.z_in + it.z_base + off + k * g.vol);
-                    for (int jj = 0; jj < VEC; ++jj) st.zc[k][jj] = zv.v[jj];
-                }
-                if (own) pxb_item_commit<T, VEC, ALGO, NORMS>(a, it.lin_base + off, xo, un, uo, st.acc);
-            }
-        } else {
-            for (int j = 0; j < VEC; ++j) wv.v[j] = T(0);
-        }
+        if (plane_in && r < g.nR && c < g.nC) pxb_iter_w<T, VEC, NDIR, ALGO, NORMS, MODES>(q, g, it, a, m, r, c, own, wv.v, st.zc, st.acc);
+        else if (MODES) pxb_tv_w_outside<T, VEC, NDIR, ALGO>(q, a.u_in, a.z_in, it.b, PXB_I0(m, r), PXB_I1(m, r), c, wv.v);
+        else for (int j = 0; j < VEC; ++j) wv.v[j] = T(0);
         pxb_vstore<T, VEC>(slot + (rl + C::R0) * C::RS + cl + VEC, wv);
     }
     if (!own) return;  // planes of the neighbouring chunks are only needed at the tile's own positions
@@ -334,18 +237,10 @@ PXB_HD void pxb_iter_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
         const T coef = top ? q.cm[C::KR] : q.cp[C::KR];
         if (coef != T(0)) {
             const int r = top ? it.r0 - 1 : it.r0 + TY, c = it.c0 + cl;
-            const bool in = r >= 0 && r < g.nR && c < g.nC;
-            bool fast = in;
-            if (MODES && fast) fast = !pxb_tv_needs_generic<T, NDIR>(q, PXB_I0(m, r), PXB_I1(m, r), c, VEC);
             PxbVec<T, VEC> wv;
-            if (fast) {
-                pxb_iter_w<T, VEC, NDIR, ALGO, false>(q, g, it, a, m, r, c, false, wv.v, (T(*)[VEC]) nullptr, st.acc);
-            } else if (MODES) {
-                T xo[VEC], un[VEC], uo[VEC];
-                pxb_item_any<T, VEC, ALGO>(mc, a.u_in, a.z_in, it.b, PXB_I0(m, r), PXB_I1(m, r), c, wv.v, xo, un, uo);
-            } else {
-                for (int j = 0; j < VEC; ++j) wv.v[j] = T(0);
-            }
+            if (r >= 0 && r < g.nR && c < g.nC) pxb_iter_w<T, VEC, NDIR, ALGO, false, MODES>(q, g, it, a, m, r, c, false, wv.v, (T(*)[VEC]) nullptr, st.acc);
+            else if (MODES) pxb_tv_w_outside<T, VEC, NDIR, ALGO>(q, a.u_in, a.z_in, it.b, PXB_I0(m, r), PXB_I1(m, r), c, wv.v);
+            else for (int j = 0; j < VEC; ++j) wv.v[j] = T(0);
             pxb_vstore<T, VEC>(slot + (top ? 0 : TY + 1) * C::RS + cl + VEC, wv);
         }
     }
@@ -356,18 +251,10 @@ PXB_HD void pxb_iter_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
         const T coef = left ? q.cm[C::KC] : q.cp[C::KC];
         if (coef != T(0)) {
             const int r = it.r0 + hl, c = left ? it.c0 - 1 : it.c0 + C::T2;
-            const bool in = r < g.nR && c >= 0 && c < g.nC;
-            bool fast = in;
-            if (MODES && fast) fast = !pxb_tv_needs_generic<T, NDIR>(q, PXB_I0(m, r), PXB_I1(m, r), c, 1);
             T w1[1];
-            if (fast) {
-                pxb_iter_w<T, 1, NDIR, ALGO, false>(q, g, it, a, m, r, c, false, w1, (T(*)[1]) nullptr, st.acc);
-            } else if (MODES) {
-                T xo[1], un[1], uo[1];
-                pxb_item_any<T, 1, ALGO>(mc, a.u_in, a.z_in, it.b, PXB_I0(m, r), PXB_I1(m, r), c, w1, xo, un, uo);
-            } else {
-                w1[0] = T(0);
-            }
+            if (r < g.nR && c >= 0 && c < g.nC) pxb_iter_w<T, 1, NDIR, ALGO, false, MODES>(q, g, it, a, m, r, c, false, w1, (T(*)[1]) nullptr, st.acc);
+            else if (MODES) pxb_tv_w_outside<T, 1, NDIR, ALGO>(q, a.u_in, a.z_in, it.b, PXB_I0(m, r), PXB_I1(m, r), c, w1);
+            else w1[0] = T(0);
             slot[(hl + C::R0) * C::RS + (left ? VEC - 1 : VEC + C::T2)] = w1[0];
         }
     }

@@ -9,7 +9,7 @@ template <class T, int VEC, int ALGO, bool NORMS, class S, bool MODES = false>
 __global__ void __launch_bounds__(256, 3)
     k_tv_tile2d(const __grid_constant__ PxbTvP<T> q, const __grid_constant__ PxbT2Geom g, const __grid_constant__ PxbIterPtr<T> a,
                 const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_zr,
-                const __grid_constant__ CUtensorMap map_zc, const __grid_constant__ PxbModeArgs<MODES> ma) {
+                const __grid_constant__ CUtensorMap map_zc) {
     using C = PxbT2Cfg<T, VEC>;
     extern __shared__ __align__(128) unsigned char pxb_t2_smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256, 3)
     }
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     mbar_wait(&bar, 0);
-    pxb_t2_phaseA<T, VEC, ALGO, NORMS, S, MODES>(q, g, it, a, tid, sm, acc, ma.ctx());
+    pxb_t2_phaseA<T, VEC, ALGO, NORMS, S, MODES>(q, g, it, a, tid, sm, acc);
     __syncthreads();
     pxb_t2_phaseC<T, VEC, NORMS, S>(q, g, it, a, tid, sm, acc);
     if (NORMS) {
@@ -75,15 +75,12 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
     auto go = [&](auto kern) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) { *err = e; return; }
-        kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, a, tu, ts, tzr, tzc, PxbModeArgs<false>{});
+        kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, a, tu, ts, tzr, tzc);
         *err = cudaGetLastError();
     };
-    if (pxb_any_mode(d)) {  // folding boundary modes: the generic instance with the per-sample path on the faces
-        auto kern = k_tv_tile2d<T, VEC, ALGO, NORMS, PxbSpecAny, true>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) { *err = e; return 0; }
-        kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, a, tu, ts, tzr, tzc, PxbModeArgs<true>{d, P});
-        *err = cudaGetLastError();
+    if (pxb_any_mode(d)) {  // folding boundary modes: MODES instances (fold terms of K^T z, folded rim of the w tile)
+        if (fwd && q.hkind == PXB_DUAL_L21) go(k_tv_tile2d<T, VEC, ALGO, NORMS, PxbSpec<PXB_SCHEME_FWD, -1, PXB_DUAL_L21, -1>, true>);
+        else go(k_tv_tile2d<T, VEC, ALGO, NORMS, PxbSpecAny, true>);
         return 0;
     }
     if (fwd && q.hkind == PXB_DUAL_L21) go(k_tv_tile2d<T, VEC, ALGO, NORMS, PxbSpec<PXB_SCHEME_FWD, -1, PXB_DUAL_L21, -1>>);

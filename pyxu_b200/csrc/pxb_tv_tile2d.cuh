@@ -33,8 +33,11 @@ struct PxbT2Geom {
 };
 
 // w / new primal iterate for W samples at box position (row br of the (TY+2)-row boxes, column bc)
-template <class T, int VEC, int W, int ALGO, class S>
-PXB_HD void pxb_t2_w(const PxbTvP<T>& q, const PxbT2Geom& g, const T* __restrict__ sm, int br, int bc, T* wv, T* xo, T* un, T* uold) {
+// `fold` (MODES instances, in-image samples only): z of the batch item (component 0, image 0) for the fold terms of
+// K^T z (pxb_tv_fold_kz) at sample (f0, f1, f2); null otherwise.
+template <class T, int VEC, int W, int ALGO, class S, bool MODES = false>
+PXB_HD void pxb_t2_w(const PxbTvP<T>& q, const PxbT2Geom& g, const T* __restrict__ sm, int br, int bc, T* wv, T* xo, T* un, T* uold,
+                     const T* __restrict__ fold = nullptr, int f0 = 0, int f1 = 0, int f2 = 0) {
     using C = PxbT2Cfg<T, VEC>;
     const int i = br * C::BW + bc, iz = (br + 1) * C::BW + bc;
     T kz[W];
@@ -57,6 +60,7 @@ PXB_HD void pxb_t2_w(const PxbTvP<T>& q, const PxbT2Geom& g, const T* __restrict
             if (pxb_has_cp<S>(q, 1)) kz[j] += q.cp[1] * (j > 0 ? c.v[j > 0 ? j - 1 : 0] : lo);
         }
     }
+    if (MODES && fold) pxb_tv_fold_kz<T, W, 2>(q, fold, f0, f1, f2, kz);
     const PxbVec<T, W> old = pxb_vload<T, W>(sm + C::OFF_U + i);
     PxbVec<T, W> sh;
     for (int j = 0; j < W; ++j) sh.v[j] = T(0);
@@ -102,11 +106,10 @@ PXB_HD PxbT2Item pxb_t2_item(const PxbT2Geom& g, int64_t blk, int ty, int t2) {
 
 // phase A for thread `tid`: w of rows {wy, wy+8} of the tile (+ the rims this thread owns) -> shared memory; new primal
 // iterate (and x) of the tile's own samples -> global memory.
-// MODES (folding boundary modes): as in pxb_tv_tma.cuh, the samples of the two-sample band along a folding face and the
-// out-of-image cells of the w tile are recomputed through the per-sample path of pxb_tv_iter.cuh.
+// MODES (folding boundary modes): as in pxb_tv_tma.cuh -- in-image samples add the fold terms of K^T z, the cells of the
+// w tile one step outside the image receive w at the sample the boundary map folds them onto.
 template <class T, int VEC, int ALGO, bool NORMS, class S, bool MODES = false>
-PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Item& it, const PxbIterPtr<T>& a, int tid, T* __restrict__ sm, double* acc,
-                          const PxbModeCtx mc = PxbModeCtx{nullptr, nullptr}) {
+PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Item& it, const PxbIterPtr<T>& a, int tid, T* __restrict__ sm, double* acc) {
     using C = PxbT2Cfg<T, VEC>;
     T* __restrict__ wsm = sm + C::OFF_W;
     const int lane = tid & 31, wy = tid >> 5, cl = lane * VEC;
@@ -115,12 +118,10 @@ PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
         const int rl = wy + 8 * half, r = it.r0 + rl, c = it.c0 + cl;
         const bool in = r < g.n1 && c < g.n2;
         T wv[VEC], xo[VEC], un[VEC], uo[VEC];
-        pxb_t2_w<T, VEC, VEC, ALGO, S>(q, g, sm, rl + 1, cl + VEC, wv, xo, un, uo);
-        bool keep = in;
-        if (MODES && pxb_item_needs_any<T, 2>(q, it.i0, r, c, VEC)) {
-            pxb_item_any<T, VEC, ALGO>(mc, a.u_in, a.z_in, it.b, it.i0, r, c, wv, xo, un, uo);
-            keep = true;
-        }
+        const T* __restrict__ zimg = a.z_in + it.b * 2 * g.vol;
+        pxb_t2_w<T, VEC, VEC, ALGO, S, MODES>(q, g, sm, rl + 1, cl + VEC, wv, xo, un, uo, in ? zimg : nullptr, it.i0, r, c);
+        if (MODES && !in) pxb_tv_w_outside<T, VEC, 2, ALGO>(q, a.u_in, a.z_in, it.b, it.i0, r, c, wv);
+        const bool keep = MODES || in;
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = keep ? wv[j] : T(0);
         pxb_vstore<T, VEC>(wsm + (rl + 1) * C::BW + cl + VEC, o);
@@ -152,10 +153,10 @@ PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
         if (top ? pxb_has_cm<S>(q, 0) : pxb_has_cp<S>(q, 0)) {
             const int br = top ? 0 : C::TY + 1, r = top ? it.r0 - 1 : it.r0 + C::TY, c = it.c0 + cl;
             T wv[VEC], xo[VEC], un[VEC], uo[VEC];
-            pxb_t2_w<T, VEC, VEC, ALGO, S>(q, g, sm, br, cl + VEC, wv, xo, un, uo);
             bool in = r >= 0 && r < g.n1 && c < g.n2;
-            if (MODES && pxb_item_needs_any<T, 2>(q, it.i0, r, c, VEC)) {
-                pxb_item_any<T, VEC, ALGO>(mc, a.u_in, a.z_in, it.b, it.i0, r, c, wv, xo, un, uo);
+            pxb_t2_w<T, VEC, VEC, ALGO, S, MODES>(q, g, sm, br, cl + VEC, wv, xo, un, uo, in ? a.z_in + it.b * 2 * g.vol : nullptr, it.i0, r, c);
+            if (MODES && !in) {
+                pxb_tv_w_outside<T, VEC, 2, ALGO>(q, a.u_in, a.z_in, it.b, it.i0, r, c, wv);
                 in = true;
             }
             PxbVec<T, VEC> o;
@@ -169,10 +170,10 @@ PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
         if (left ? pxb_has_cm<S>(q, 1) : pxb_has_cp<S>(q, 1)) {
             const int bc = left ? VEC - 1 : VEC + C::T2, r = it.r0 + rl, c = left ? it.c0 - 1 : it.c0 + C::T2;
             T wv[1], xo[1], un[1], uo[1];
-            pxb_t2_w<T, VEC, 1, ALGO, S>(q, g, sm, rl + 1, bc, wv, xo, un, uo);
             bool in = r < g.n1 && c >= 0 && c < g.n2;
-            if (MODES && pxb_item_needs_any<T, 2>(q, it.i0, r, c, 1)) {
-                pxb_item_any<T, 1, ALGO>(mc, a.u_in, a.z_in, it.b, it.i0, r, c, wv, xo, un, uo);
+            pxb_t2_w<T, VEC, 1, ALGO, S, MODES>(q, g, sm, rl + 1, bc, wv, xo, un, uo, in ? a.z_in + it.b * 2 * g.vol : nullptr, it.i0, r, c);
+            if (MODES && !in) {
+                pxb_tv_w_outside<T, 1, 2, ALGO>(q, a.u_in, a.z_in, it.b, it.i0, r, c, wv);
                 in = true;
             }
             wsm[(rl + 1) * C::BW + bc] = in ? wv[0] : T(0);

@@ -15,8 +15,7 @@ template <class T, int VEC, int TY, int ALGO, bool NORMS, class S, bool MODES = 
 __global__ void __launch_bounds__(32 * TY, 2)
     k_tv_iter_tma(const __grid_constant__ PxbTvP<T> q, const __grid_constant__ PxbIterGeom g, const __grid_constant__ PxbTmaGeom tg,
                   const __grid_constant__ PxbIterPtr<T> a, const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s,
-                  const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_z1,
-                  const __grid_constant__ PxbModeArgs<MODES> ma) {
+                  const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_z1) {
     using C = PxbTmaCfg<T, VEC, TY>;
     extern __shared__ __align__(128) unsigned char pxb_tma_smem[];
     T* stages = reinterpret_cast<T*>(pxb_tma_smem);
@@ -73,7 +72,7 @@ __global__ void __launch_bounds__(32 * TY, 2)
             mbar_wait(full + s1, s1 == 0 ? par ^ 1u : par);
             st_next = stages + s1 * C::STAGE;
         }
-        pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring, th, ma.ctx());
+        pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring, th);
         __syncthreads();  // w(m) complete; every thread is done with stage s
         if (tid == 0 && m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
         const int mm = m - lag;
@@ -133,15 +132,13 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
         // (the attribute is per function: set it on every launch path once; cheap enough to repeat)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) { *err = e; return; }
-        kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, tg, a, tu, ts, tz, tz1, PxbModeArgs<false>{});
+        kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, tg, a, tu, ts, tz, tz1);
         *err = cudaGetLastError();
     };
-    if (pxb_any_mode(d)) {  // folding boundary modes: the generic instance with the per-sample path on the faces
-        auto kern = k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecAny, true>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) { *err = e; return 0; }
-        kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, tg, a, tu, ts, tz, tz1, PxbModeArgs<true>{d, P});
-        *err = cudaGetLastError();
+    if (pxb_any_mode(d)) {  // folding boundary modes: MODES instances (fold terms of K^T z, folded rim of the w ring)
+        if (spec == 1) go(k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecFwdPos, true>);
+        else if (spec == 2) go(k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecFwdNone, true>);
+        else go(k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecAny, true>);
         return 0;
     }
     if (spec == 1) go(k_tv_iter_tma<T, VEC, TY, ALGO, NORMS, PxbSpecFwdPos>);

@@ -109,9 +109,12 @@ struct PxbTmaThread {
 };
 
 // w / new primal iterate for W samples whose box position is (row br, column bc) -- everything from shared memory.
-template <class T, int VEC, int TY, int W, int ALGO, class S>
+// `fold` (MODES instances, in-domain samples only): the image's z (component 0, sample (0, 0, 0)) for the fold terms of
+// K^T z (pxb_tv_fold_kz) at sample (f0, f1, f2); null otherwise.
+template <class T, int VEC, int TY, int W, int ALGO, class S, bool MODES = false>
 PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restrict__ st, const T* __restrict__ st_next, int br, int bc,
-                      const T* z0p, T* wv, T* z0c, T* z1c, T* z2c, T* xo, T* un, T* uold) {
+                      const T* z0p, T* wv, T* z0c, T* z1c, T* z2c, T* xo, T* un, T* uold, const T* __restrict__ fold = nullptr, int f0 = 0,
+                      int f1 = 0, int f2 = 0) {
     using C = PxbTmaCfg<T, VEC, TY>;
     const int i = br * C::BW + bc, i1 = (br + 1) * C::BW + bc;
     T kz[W];
@@ -150,6 +153,7 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
             if (pxb_has_cp<S>(q, 2)) kz[j] += q.cp[2] * (j > 0 ? c.v[j > 0 ? j - 1 : 0] : lo);
         }
     }
+    if (MODES && fold) pxb_tv_fold_kz<T, W, 3>(q, fold, f0, f1, f2, kz);
     const PxbVec<T, W> old = pxb_vload<T, W>(st + C::OFF_U + i);
     PxbVec<T, W> sh;
     for (int j = 0; j < W; ++j) sh.v[j] = T(0);
@@ -209,12 +213,12 @@ PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const Pxb
 
 // phase A of plane m out of stage `st` (plane m) and, for two-sided / backward schemes, `st_next` (plane m+1).
 // MODES (folding boundary modes): the staged boxes are zero-filled outside the domain, i.e. they carry the 'constant'
-// extension; the samples for which that is not the reference's arithmetic -- the two-sample band along a folding face
-// and the out-of-domain cells / planes of the w ring -- are recomputed through the per-sample path of pxb_tv_iter.cuh.
+// extension.  In-domain samples add the fold terms of K^T z (pxb_tv_fold_kz); the cells of the w ring one step outside
+// the domain -- rim rows / columns of the edge tiles, the plane past the last one -- receive w at the sample the
+// boundary map folds them onto (pxb_tv_w_outside), which K w then reads as the padded array.
 template <class T, int VEC, int TY, int ALGO, bool NORMS, class S = PxbSpecAny, bool MODES = false>
 PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTmaGeom& tg, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid,
-                           int m, const T* __restrict__ st, const T* __restrict__ st_next, T* ring, PxbTmaThread<T, VEC>& th,
-                           const PxbModeCtx mc = PxbModeCtx{nullptr, nullptr}) {
+                           int m, const T* __restrict__ st, const T* __restrict__ st_next, T* ring, PxbTmaThread<T, VEC>& th) {
     using C = PxbTmaCfg<T, VEC, TY>;
     using R = typename C::Ring;
     T* __restrict__ slot = ring + (m & 3) * R::SLOT;
@@ -225,13 +229,12 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         const int r = it.r0 + rl, c = it.c0 + cl;
         const bool in = plane_in && r < g.nR && c < g.nC;
         T wv[VEC], z0c[VEC], xo[VEC], un[VEC], uo[VEC];
-        pxb_tma_w<T, VEC, TY, VEC, ALGO, S>(q, tg, st, st_next, rl + 1, cl + VEC, th.z0p, wv, z0c, th.zc[1], th.zc[2], xo, un, uo);
+        const T* __restrict__ zimg = a.z_in + it.b * 3 * g.vol;
+        pxb_tma_w<T, VEC, TY, VEC, ALGO, S, MODES>(q, tg, st, st_next, rl + 1, cl + VEC, th.z0p, wv, z0c, th.zc[1], th.zc[2], xo, un, uo,
+                                                   in ? zimg : nullptr, m, r, c);
         for (int j = 0; j < VEC; ++j) { th.zc[0][j] = z0c[j]; th.z0p[j] = z0c[j]; }
-        bool keep = in;
-        if (MODES && pxb_item_needs_any<T, 3>(q, m, r, c, VEC)) {
-            pxb_item_any<T, VEC, ALGO>(mc, a.u_in, a.z_in, it.b, m, r, c, wv, xo, un, uo);
-            keep = true;
-        }
+        if (MODES && !in) pxb_tv_w_outside<T, VEC, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);
+        const bool keep = MODES || in;
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = keep ? wv[j] : T(0);
         pxb_vstore<T, VEC>(slot + (rl + 1) * R::RS + cl + VEC, o);
@@ -267,10 +270,11 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         if (own && need) {
             const int r = top ? it.r0 - 1 : it.r0 + TY, c = it.c0 + cl;
             T wv[VEC], z0c[VEC], z1c[VEC], z2c[VEC], xo[VEC], un[VEC], uo[VEC];
-            pxb_tma_w<T, VEC, TY, VEC, ALGO, S>(q, tg, st, st_next, br, cl + VEC, th.z0p_rim, wv, z0c, z1c, z2c, xo, un, uo);
             bool in = r >= 0 && r < g.nR && c < g.nC;
-            if (MODES && pxb_item_needs_any<T, 3>(q, m, r, c, VEC)) {
-                pxb_item_any<T, VEC, ALGO>(mc, a.u_in, a.z_in, it.b, m, r, c, wv, xo, un, uo);
+            pxb_tma_w<T, VEC, TY, VEC, ALGO, S, MODES>(q, tg, st, st_next, br, cl + VEC, th.z0p_rim, wv, z0c, z1c, z2c, xo, un, uo,
+                                                       in ? a.z_in + it.b * 3 * g.vol : nullptr, m, r, c);
+            if (MODES && !in) {
+                pxb_tv_w_outside<T, VEC, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);
                 in = true;
             }
             PxbVec<T, VEC> o;
@@ -289,10 +293,11 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         if (own && need) {
             const int r = it.r0 + hl, c = left ? it.c0 - 1 : it.c0 + C::T2;
             T wv[1], z0c[1], z1c[1], z2c[1], xo[1], un[1], uo[1];
-            pxb_tma_w<T, VEC, TY, 1, ALGO, S>(q, tg, st, st_next, hl + 1, bc, &th.z0p_col, wv, z0c, z1c, z2c, xo, un, uo);
             bool in = r < g.nR && c >= 0 && c < g.nC;
-            if (MODES && pxb_item_needs_any<T, 3>(q, m, r, c, 1)) {
-                pxb_item_any<T, 1, ALGO>(mc, a.u_in, a.z_in, it.b, m, r, c, wv, xo, un, uo);
+            pxb_tma_w<T, VEC, TY, 1, ALGO, S, MODES>(q, tg, st, st_next, hl + 1, bc, &th.z0p_col, wv, z0c, z1c, z2c, xo, un, uo,
+                                                     in ? a.z_in + it.b * 3 * g.vol : nullptr, m, r, c);
+            if (MODES && !in) {
+                pxb_tv_w_outside<T, 1, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);
                 in = true;
             }
             slot[(hl + 1) * R::RS + bc] = in ? wv[0] : T(0);

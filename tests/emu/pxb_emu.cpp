@@ -118,7 +118,6 @@ static int t_iter_cfg(const pxb_grad_desc* K, const pxb_pds_params* p, const Pxb
     PxbIterGeom g;
     if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, 5, cf, g, g_allow_modes)) return -100 - why;
     if (pxb_any_mode(*K) != MODES) return -130;  // the launcher's rule: folding modes <=> the MODES instance
-    const PxbModeCtx mc{K, p};
     PxbTvP<T> q;
     pxb_tv_prepare<T>(*K, cf, *p, q);
     std::vector<T> smem(C::NSLOT * C::SLOT);
@@ -129,7 +128,7 @@ static int t_iter_cfg(const pxb_grad_desc* K, const pxb_pds_params* p, const Pxb
         for (auto& s : st) std::memset(&s, 0, sizeof(s));
         for (auto& v : smem) v = T(12345);  // poison: cells that are read must have been written
         for (int m = R.mlo; m < R.mhi; ++m) {
-            for (int tid = 0; tid < C::NT; ++tid) pxb_iter_phaseA<T, VEC, TXL, TY, NDIR, ALGO, NORMS, MODES>(q, g, it, a, tid, m, smem.data(), st[tid], mc);
+            for (int tid = 0; tid < C::NT; ++tid) pxb_iter_phaseA<T, VEC, TXL, TY, NDIR, ALGO, NORMS, MODES>(q, g, it, a, tid, m, smem.data(), st[tid]);
             const int mm = m - R.lag;
             for (int tid = 0; tid < C::NT; ++tid) {
                 if (mm >= it.m0 && mm < it.m1)
@@ -196,14 +195,17 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
     PxbTvCoef cf;
     PxbIterGeom g;
     if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, 5, cf, g, g_allow_modes)) return -100 - why;
-    if (pxb_any_mode(*K) != MODES) return -130;  // folding modes <=> the MODES instance (generic specialisation), as in the launcher
-    const PxbModeCtx mc{K, p};
+    if (pxb_any_mode(*K) != MODES) return -130;  // folding modes <=> the MODES instances, as in the launcher
     PxbTvP<T> q;
     pxb_tv_prepare<T>(*K, cf, *p, q);
     PxbTmaGeom tg;
     PxbTmaBoxDesc mu, ms, mz;
     if (int why = pxb_tma_setup<T, VEC, TY>(*K, *p, cf, g, q, a.u_in, a.z_in, tg, mu, ms, mz)) return -100 - why;
-    if (!MODES && pxb_tma_pick_spec<T>(cf, q, tg) != want_spec) return -130;  // the caller dispatches on the same rule as the launcher
+    {   // the caller dispatches on the same rule as the launcher (MODES: specialised for the PD3O-style instances 1 / 2 only)
+        int spec = pxb_tma_pick_spec<T>(cf, q, tg);
+        if (MODES && spec > 2) spec = 0;
+        if (spec != want_spec) return -130;
+    }
     std::vector<T> stages(C::NSTAGE * C::STAGE), ring(R::NSLOT * R::SLOT);
     std::vector<PxbTmaThread<T, VEC>> th(C::NT);
     for (int64_t blk = 0; blk < g.nblocks; ++blk) {
@@ -235,7 +237,7 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
             const int k = m - Rg.mlo;
             const T* st = stages.data() + (k % C::NSTAGE) * C::STAGE;
             const T* st_next = need_next ? stages.data() + ((k + 1) % C::NSTAGE) * C::STAGE : st;
-            for (int tid = 0; tid < C::NT; ++tid) pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring.data(), th[tid], mc);
+            for (int tid = 0; tid < C::NT; ++tid) pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring.data(), th[tid]);
             if (m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
             const int mm = m - lag;
             for (int tid = 0; tid < C::NT; ++tid) {
@@ -266,6 +268,8 @@ static int t_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
         if (rc != -130) return rc;                                                                                      \
     }
 #define EMU_TMA_TRY(S, id) EMU_TMA_TRY_M(S, id, false)
+    EMU_TMA_TRY_M(PxbSpecFwdPos, 1, true)
+    EMU_TMA_TRY_M(PxbSpecFwdNone, 2, true)
     EMU_TMA_TRY_M(PxbSpecAny, 0, true)
     EMU_TMA_TRY(PxbSpecFwdPos, 1)
     EMU_TMA_TRY(PxbSpecFwdNone, 2)
@@ -383,10 +387,9 @@ static int t_t2_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIt
     PxbT2Geom g;
     if (int why = pxb_t2_setup<T, VEC>(*K, *p, cf, q, g, g_allow_modes)) return -100 - why;
     if (pxb_any_mode(*K) != MODES) return -130;
-    const PxbModeCtx mc{K, p};
     bool fwd = true;
     for (int k = 0; k < 2; ++k) fwd = fwd && cf.cm[k] == 0.0 && cf.cp[k] != 0.0;
-    if (!MODES && (fwd && q.hkind == PXB_DUAL_L21) != want_fwd) return -130;
+    if ((fwd && q.hkind == PXB_DUAL_L21) != want_fwd) return -130;
     std::vector<T> sm(C::TOTAL);
     const int64_t du[3] = {g.n2, g.n1, g.nimg}, dz[3] = {g.n2, g.n1, g.nimg * 2}, ds[3] = {g.n2, g.n1, g.sh_mode ? g.n0 : g.nimg};
     const T* sptr = q.fkind == PXB_F_GRADARR ? q.garr : q.shift;
@@ -400,7 +403,7 @@ static int t_t2_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIt
         emu_box3<T>(a.z_in, dz, g.n2, g.s0, C::BW, C::BRZ, cc, cr - 1, pz, sm.data() + C::OFF_ZR);
         emu_box3<T>(a.z_in, dz, g.n2, g.s0, C::BW, C::BR, cc, cr, pz + g.n0, sm.data() + C::OFF_ZC);
         double acc[4] = {0, 0, 0, 0};
-        for (int tid = 0; tid < C::NT; ++tid) pxb_t2_phaseA<T, VEC, ALGO, NORMS, S, MODES>(q, g, it, a, tid, sm.data(), acc, mc);
+        for (int tid = 0; tid < C::NT; ++tid) pxb_t2_phaseA<T, VEC, ALGO, NORMS, S, MODES>(q, g, it, a, tid, sm.data(), acc);
         for (int tid = 0; tid < C::NT; ++tid) pxb_t2_phaseC<T, VEC, NORMS, S>(q, g, it, a, tid, sm.data(), acc);
         if (NORMS) {
             if (a.norms_x) { a.norms_x[2 * it.b] += acc[0]; a.norms_x[2 * it.b + 1] += acc[1]; }
@@ -423,6 +426,7 @@ static int t_t2(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const
         if (rc != -130) return rc;                                                                                    \
     }
 #define EMU_T2_TRY(S, fw) EMU_T2_TRY_M(S, fw, false)
+    EMU_T2_TRY_M(SF, true, true)
     EMU_T2_TRY_M(PxbSpecAny, false, true)
     EMU_T2_TRY(SF, true)
     EMU_T2_TRY(PxbSpecAny, false)
