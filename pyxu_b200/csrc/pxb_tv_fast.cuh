@@ -101,13 +101,11 @@ PXB_HD void pxb_tv_prepare(const pxb_grad_desc& d, const PxbTvCoef& cf, const px
     q.vol = pxb_vol(g, d.slab);
     for (int a = 0; a < 3; ++a) { q.mode[a] = d.mode[a]; q.fold_hi[a] = q.fold_lo[a] = PXB_NOSRC; }
     q.open_lo = d.slab.open_lo; q.open_hi = d.slab.open_hi;
-    if (d.slab.halo == 0 && !d.slab.open_lo && !d.slab.open_hi && d.ndir <= 3) {
-        for (int k = 0; k < d.ndir; ++k) {
-            const int ax = 3 - d.ndir + k, n = ax == 0 ? g.n0 : (ax == 1 ? g.n1 : g.n2);
-            if (d.mode[ax] == PXB_CONSTANT) continue;
-            if (cf.cp[k] != 0.0) q.fold_hi[ax] = pxb_bmap(n, n, d.mode[ax]);
-            if (cf.cm[k] != 0.0) q.fold_lo[ax] = pxb_bmap(-1, n, d.mode[ax]);
-        }
+    for (int k = 0; k < d.ndir && k < PXB_MAX_DIRS; ++k) {  // an open slab side is not a boundary: nothing folds there
+        const int ax = 3 - d.ndir + k, n = ax == 0 ? g.n0 : (ax == 1 ? g.n1 : g.n2);
+        if (ax < 0 || d.mode[ax] == PXB_CONSTANT) continue;
+        if (cf.cp[k] != 0.0 && !(ax == 0 && d.slab.open_hi)) q.fold_hi[ax] = pxb_bmap(n, n, d.mode[ax]);
+        if (cf.cm[k] != 0.0 && !(ax == 0 && d.slab.open_lo)) q.fold_lo[ax] = pxb_bmap(-1, n, d.mode[ax]);
     }
     q.shift = (const T*)P.f.shift; q.garr = (const T*)P.f.garr; q.shift_period = P.f.shift_period;
     q.shift_mode = PXB_SHIFT_NONE;
@@ -157,51 +155,16 @@ PXB_HD void pxb_vstore(T* __restrict__ p, const PxbVec<T, VEC>& r) {
     }
 }
 
-// Which of this vector's voxels need the generic (folding-aware) body?  A face along axis a matters only when
-// its mode is not 'constant' (and, for axis 0, the side is not an open slab cut).  With radius-1 taps the
-// boundary extension folds samples onto the face voxel itself (wrap / symmetric / edge) or onto its neighbour
-// ('reflect': m(-1) = 1, m(n) = n-2), hence a band of two voxels per face.
-template <class T, int NDIR>
-PXB_HD bool pxb_tv_needs_generic(const PxbTvP<T>& q, int i0, int i1, int i2, int vec) {
-    if (NDIR >= 3 && q.mode[0] != PXB_CONSTANT)
-        if ((i0 <= 1 && !q.open_lo) || (i0 >= q.n0 - 2 && !q.open_hi)) return true;
-    if (NDIR >= 2 && q.mode[1] != PXB_CONSTANT)
-        if (i1 <= 1 || i1 >= q.n1 - 2) return true;
-    if (q.mode[2] != PXB_CONSTANT)
-        if (i2 <= 1 || i2 + vec >= q.n2 - 1) return true;
-    return false;
-}
-
-// The folding-aware generic bodies are kept out of line on the device so that their register needs do not
-// dictate the occupancy of the fast path (they run for a vanishing fraction of the voxels).
-template <class T>
-PXB_NOINLINE void pxb_tv_primal_generic(int algo, const pxb_grad_desc& d, const pxb_pds_params& P, T* xu, const T* z, T* x_out, T* w,
-                                        bool want_norms, double* nrm, int64_t b, int i0, int i1, int i2, int vec) {
-    const PxbGeom g = pxb_geom(d.shape);
-    double n0 = 0.0, n1 = 0.0;
-    for (int j = 0; j < vec; ++j)
-        pxb_body_primal<T>(algo, d, g, P, xu, z, (const T*)nullptr, x_out, w, want_norms, n0, n1, b, i0, i1, i2 + j);
-    nrm[0] += n0;
-    nrm[1] += n1;
-}
-
-template <class T>
-PXB_NOINLINE void pxb_tv_dual_generic(const pxb_grad_desc& d, const pxb_pds_params& P, const T* w, T* z, bool want_norms, double* nrm,
-                                      int64_t b, int i0, int i1, int i2, int vec) {
-    const PxbGeom g = pxb_geom(d.shape);
-    double n0 = 0.0, n1 = 0.0;
-    for (int j = 0; j < vec; ++j) pxb_body_dual<T>(d, g, P, w, z, want_norms, n0, n1, b, i0, i1, i2 + j);
-    nrm[0] += n0;
-    nrm[1] += n1;
-}
-
 // taps of one direction along the row itself:  out[j] = c_hi * f[j+1] + c_0 * f[j] + c_lo * f[j-1]
 // (the vector's own elements serve as neighbours, the two ends come from one scalar load each)
+// off_lo / off_hi: where the neighbours of the vector's first / last element live relative to f (-1 / VEC inside the
+// row; the sample the boundary map folds them onto at a folding face, see pxb_tv_nbr)
 template <class T, int VEC>
-PXB_HD void pxb_tv_taps_row(const T* __restrict__ f, const PxbVec<T, VEC>& c, T c_hi, T c_0, T c_lo, bool has_lo, bool has_hi, T* out) {
+PXB_HD void pxb_tv_taps_row(const T* __restrict__ f, const PxbVec<T, VEC>& c, T c_hi, T c_0, T c_lo, bool has_lo, bool has_hi, T* out,
+                            int off_lo = -1, int off_hi = VEC) {
     T lo = T(0), hi = T(0);
-    if (c_lo != T(0) && has_lo) lo = f[-1];
-    if (c_hi != T(0) && has_hi) hi = f[VEC];
+    if (c_lo != T(0) && has_lo) lo = f[off_lo];
+    if (c_hi != T(0) && has_hi) hi = f[off_hi];
     for (int j = 0; j < VEC; ++j) {
         const T up = (j + 1 < VEC) ? c.v[j + 1 < VEC ? j + 1 : 0] : hi;
         const T dn = (j > 0) ? c.v[j > 0 ? j - 1 : 0] : lo;
@@ -212,18 +175,35 @@ PXB_HD void pxb_tv_taps_row(const T* __restrict__ f, const PxbVec<T, VEC>& c, T 
     }
 }
 
-// taps of one direction across rows / planes:  out[j] = c_hi * f[s + st] + c_0 * f[s] + c_lo * f[s - st]
+// taps of one direction across rows / planes:  out[j] = c_hi * f[s + d_hi st] + c_0 * f[s] + c_lo * f[s + d_lo st]
+// (d_lo, d_hi) = (-1, +1) inside the domain; at a folding face the step to the sample the neighbour folds onto
 template <class T, int VEC>
 PXB_HD void pxb_tv_taps_col(const T* __restrict__ f, int64_t st, const PxbVec<T, VEC>& c, T c_hi, T c_0, T c_lo, bool has_lo, bool has_hi,
-                            T* out) {
+                            T* out, int d_lo = -1, int d_hi = 1) {
     for (int j = 0; j < VEC; ++j) out[j] = c_0 * c.v[j];
     if (c_hi != T(0) && has_hi) {
-        const PxbVec<T, VEC> up = pxb_vload<T, VEC>(f + st);
+        const PxbVec<T, VEC> up = pxb_vload<T, VEC>(f + d_hi * st);
         for (int j = 0; j < VEC; ++j) out[j] += c_hi * up.v[j];
     }
     if (c_lo != T(0) && has_lo) {
-        const PxbVec<T, VEC> dn = pxb_vload<T, VEC>(f - st);
+        const PxbVec<T, VEC> dn = pxb_vload<T, VEC>(f + d_lo * st);
         for (int j = 0; j < VEC; ++j) out[j] += c_lo * dn.v[j];
+    }
+}
+
+// Neighbours of samples [i, i + w) of a line of length n under K (apply direction): (K w)[s] = cm w[m(s-1)] + c0 w[s] +
+// cp w[m(s+1)] with m the boundary map (pad.py:252-302).  d_lo / d_hi: step from sample i to the lower neighbour / from
+// sample i + w - 1 to the upper one (-1 / +1 inside the line, the fold at a folding face); has_*: false where the
+// neighbour is a zero of the 'constant' extension.  Open slab sides (axis 0) read their ghost planes.
+template <class T>
+PXB_HD void pxb_tv_nbr(const PxbTvP<T>& q, int ax, int i, int w, int n, int& d_lo, int& d_hi, bool& has_lo, bool& has_hi) {
+    d_lo = -1;
+    d_hi = 1;
+    has_lo = i > 0 || (ax == 0 && q.open_lo);
+    has_hi = i + w < n || (ax == 0 && q.open_hi);
+    if (q.mode[ax] != PXB_CONSTANT) {
+        if (!has_lo) { d_lo = pxb_bmap(-1, n, q.mode[ax]) - i; has_lo = true; }
+        if (!has_hi) { d_hi = pxb_bmap(n, n, q.mode[ax]) - (i + w - 1); has_hi = true; }
     }
 }
 
@@ -355,16 +335,13 @@ template <class T, int NDIR, int VEC, int ALGO, bool NORMS>
 PXB_HD void pxb_tv_primal_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const pxb_pds_params& P, T* __restrict__ xu,
                               const T* __restrict__ z, T* __restrict__ x_out, T* __restrict__ w, double* nrm, int64_t b, int i0,
                               int i1, int i2) {
-    if (pxb_tv_needs_generic<T, NDIR>(q, i0, i1, i2, VEC)) {
-        pxb_tv_primal_generic<T>(ALGO, d, P, xu, z, x_out, w, NORMS, nrm, b, i0, i1, i2, VEC);
-        return;
-    }
     const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2;
     const int64_t lin = b * q.vol + v;
     const T* __restrict__ zb = z + b * NDIR * q.vol + v;
     T kz[VEC];
     for (int j = 0; j < VEC; ++j) kz[j] = T(0);
-    // (K_k^T z)[s] = cm*z_k[s+st] + c0*z_k[s] + cp*z_k[s-st]   (rows outside the domain contribute nothing)
+    // (K_k^T z)[s] = cm*z_k[s+st] + c0*z_k[s] + cp*z_k[s-st]   (rows outside the domain contribute nothing; folding
+    // faces add their term below)
     for (int k = 0; k < NDIR; ++k) {
         const int ax = 3 - NDIR + k;
         const T* __restrict__ zk = zb + k * q.vol;
@@ -379,6 +356,7 @@ PXB_HD void pxb_tv_primal_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const 
         }
         for (int j = 0; j < VEC; ++j) kz[j] += t[j];
     }
+    pxb_tv_fold_kz<T, VEC, NDIR>(q, z + b * NDIR * q.vol, i0, i1, i2, kz);
     const PxbVec<T, VEC> old = pxb_vload<T, VEC>(xu + lin);
     PxbVec<T, VEC> sh;
     for (int j = 0; j < VEC; ++j) sh.v[j] = T(0);
@@ -436,10 +414,6 @@ PXB_HD void pxb_tv_primal_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const 
 template <class T, int NDIR, int VEC, bool NORMS>
 PXB_HD void pxb_tv_dual_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const pxb_pds_params& P, const T* __restrict__ w,
                             T* __restrict__ z, double* nrm, int64_t b, int i0, int i1, int i2) {
-    if (pxb_tv_needs_generic<T, NDIR>(q, i0, i1, i2, VEC)) {
-        pxb_tv_dual_generic<T>(d, P, w, z, NORMS, nrm, b, i0, i1, i2, VEC);
-        return;
-    }
     const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2;
     const T* __restrict__ wb = w + b * q.vol + v;
     T* __restrict__ zb = z + b * NDIR * q.vol + v;
@@ -450,12 +424,14 @@ PXB_HD void pxb_tv_dual_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const px
         const int ax = 3 - NDIR + k;
         const PxbVec<T, VEC> zc = pxb_vload<T, VEC>(zb + k * q.vol);
         T kw[VEC];
+        int d_lo, d_hi;
+        bool has_lo, has_hi;
         if (ax == 2) {
-            pxb_tv_taps_row<T, VEC>(wb, wc, q.cp[k], q.c0[k], q.cm[k], i2 > 0, i2 + VEC < q.n2, kw);
+            pxb_tv_nbr<T>(q, 2, i2, VEC, q.n2, d_lo, d_hi, has_lo, has_hi);
+            pxb_tv_taps_row<T, VEC>(wb, wc, q.cp[k], q.c0[k], q.cm[k], has_lo, has_hi, kw, d_lo, VEC - 1 + d_hi);
         } else {
-            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? q.n0 : q.n1;
-            const bool has_lo = i > 0 || (ax == 0 && q.open_lo), has_hi = i < n - 1 || (ax == 0 && q.open_hi);
-            pxb_tv_taps_col<T, VEC>(wb, ax == 0 ? q.s0 : q.s1, wc, q.cp[k], q.c0[k], q.cm[k], has_lo, has_hi, kw);
+            pxb_tv_nbr<T>(q, ax, ax == 0 ? i0 : i1, 1, ax == 0 ? q.n0 : q.n1, d_lo, d_hi, has_lo, has_hi);
+            pxb_tv_taps_col<T, VEC>(wb, ax == 0 ? q.s0 : q.s1, wc, q.cp[k], q.c0[k], q.cm[k], has_lo, has_hi, kw, d_lo, d_hi);
         }
         for (int j = 0; j < VEC; ++j) {
             zo[k][j] = zc.v[j];
@@ -494,11 +470,6 @@ PXB_HD void pxb_tv_dual_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const px
 template <class T, int NDIR, int VEC>
 PXB_HD void pxb_tv_grad_apply_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const T* __restrict__ x, T* __restrict__ z, int64_t b, int i0,
                                   int i1, int i2) {
-    if (pxb_tv_needs_generic<T, NDIR>(q, i0, i1, i2, VEC)) {
-        const PxbGeom g = pxb_geom(d.shape);
-        for (int j = 0; j < VEC; ++j) pxb_body_grad_apply<T>(d, g, x, z, b, i0, i1, i2 + j);
-        return;
-    }
     const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2;
     const T* __restrict__ xb = x + b * q.vol + v;
     T* __restrict__ zb = z + b * NDIR * q.vol + v;
@@ -506,12 +477,14 @@ PXB_HD void pxb_tv_grad_apply_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, co
     for (int k = 0; k < NDIR; ++k) {
         const int ax = 3 - NDIR + k;
         PxbVec<T, VEC> o;
+        int d_lo, d_hi;
+        bool has_lo, has_hi;
         if (ax == 2) {
-            pxb_tv_taps_row<T, VEC>(xb, xc, q.cp[k], q.c0[k], q.cm[k], i2 > 0, i2 + VEC < q.n2, o.v);
+            pxb_tv_nbr<T>(q, 2, i2, VEC, q.n2, d_lo, d_hi, has_lo, has_hi);
+            pxb_tv_taps_row<T, VEC>(xb, xc, q.cp[k], q.c0[k], q.cm[k], has_lo, has_hi, o.v, d_lo, VEC - 1 + d_hi);
         } else {
-            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? q.n0 : q.n1;
-            const bool has_lo = i > 0 || (ax == 0 && q.open_lo), has_hi = i < n - 1 || (ax == 0 && q.open_hi);
-            pxb_tv_taps_col<T, VEC>(xb, ax == 0 ? q.s0 : q.s1, xc, q.cp[k], q.c0[k], q.cm[k], has_lo, has_hi, o.v);
+            pxb_tv_nbr<T>(q, ax, ax == 0 ? i0 : i1, 1, ax == 0 ? q.n0 : q.n1, d_lo, d_hi, has_lo, has_hi);
+            pxb_tv_taps_col<T, VEC>(xb, ax == 0 ? q.s0 : q.s1, xc, q.cp[k], q.c0[k], q.cm[k], has_lo, has_hi, o.v, d_lo, d_hi);
         }
         pxb_vstore<T, VEC>(zb + k * q.vol, o);
     }
@@ -520,11 +493,6 @@ PXB_HD void pxb_tv_grad_apply_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, co
 template <class T, int NDIR, int VEC>
 PXB_HD void pxb_tv_grad_adjoint_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const T* __restrict__ z, T* __restrict__ x, int64_t b, int i0,
                                     int i1, int i2) {
-    if (pxb_tv_needs_generic<T, NDIR>(q, i0, i1, i2, VEC)) {
-        const PxbGeom g = pxb_geom(d.shape);
-        for (int j = 0; j < VEC; ++j) pxb_body_grad_adjoint<T>(d, g, z, x, b, i0, i1, i2 + j);
-        return;
-    }
     const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2;
     const T* __restrict__ zb = z + b * NDIR * q.vol + v;
     PxbVec<T, VEC> acc;
@@ -543,5 +511,6 @@ PXB_HD void pxb_tv_grad_adjoint_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, 
         }
         for (int j = 0; j < VEC; ++j) acc.v[j] += t[j];
     }
+    pxb_tv_fold_kz<T, VEC, NDIR>(q, z + b * NDIR * q.vol, i0, i1, i2, acc.v);
     pxb_vstore<T, VEC>(x + b * q.vol + v, acc);
 }

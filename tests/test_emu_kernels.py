@@ -258,3 +258,43 @@ def test_fast_gradient_bodies_equal_generic(scheme, vec):
             E.lib().emu_gradient(C.byref(d), adj, E.p(src), E.p(a))
             assert E.lib().emu_tv_grad(vec, adj, C.byref(d), E.p(src), E.p(b)) == 0
             assert relerr(b, a) < 1e-13, (scheme, vec, shape, mode, adj)
+
+
+def test_fast_bodies_fold_terms_random_small_geometries():
+    """The vectorised bodies have no per-voxel fallback: folding boundary modes are the 'constant' arithmetic plus the fold
+    terms (pxb_tv_fold_kz / pxb_tv_nbr).  Random small geometries -- including lines as short as the vector, where the two
+    faces of an axis fold onto the same or neighbouring samples -- against the generic bodies."""
+    rng = np.random.default_rng(77)
+    modes_all = ["constant", "wrap", "reflect", "symmetric", "edge"]
+    for trial in range(60):
+        D = int(rng.integers(1, 4))
+        vec = int(rng.choice([1, 2, 4]))
+        shape = tuple(int(rng.integers(3, 7)) for _ in range(D - 1)) + (vec * int(rng.integers(1, 4)) if vec > 2 else max(3, vec * int(rng.integers(1, 4))),)
+        if shape[-1] % vec:
+            vec = 1
+        mode = tuple(str(rng.choice(modes_all)) for _ in range(D))
+        scheme = str(rng.choice(["forward", "backward", "central"]))
+        Kop = pxo.Gradient(arg_shape=shape, mode=mode, scheme=scheme)
+        batch = int(rng.integers(1, 3))
+        d = Kop._desc(batch, K.F64)
+        x, z = rng.standard_normal((batch, Kop.dim)), rng.standard_normal((batch, Kop.codim))
+        for adj, src, n_out in ((0, x, Kop.codim), (1, z, Kop.dim)):
+            a, b = np.full((batch, n_out), np.nan), np.full((batch, n_out), np.nan)
+            E.lib().emu_gradient(C.byref(d), adj, E.p(src), E.p(a))
+            assert E.lib().emu_tv_grad(vec, adj, C.byref(d), E.p(src), E.p(b)) == 0
+            assert relerr(b, a) < 1e-13, (trial, shape, mode, scheme, vec, adj)
+        shift = rng.standard_normal((batch, Kop.dim))
+        P = E.pds_params(0.21, 0.19, 1.1, gspec=(K.PROX_POS, 0.0, 0.0), fkind=K.F_SQL2, alpha=0.7, shift=shift, hkind=K.DUAL_L21, lam=0.3)
+        for algo in (K.ALGO_PD3O, K.ALGO_CV):
+            res = []
+            for v in (0, vec):
+                u, xx, w, zz = x.copy(), x[::-1].copy(), np.zeros_like(x), z.copy()
+                if v:
+                    assert E.lib().emu_tv_fast(v, 0, algo, C.byref(d), C.byref(P), E.p(u), E.p(zz), E.p(xx) if algo == K.ALGO_PD3O else None, E.p(w), None) == 0
+                    assert E.lib().emu_tv_fast(v, 1, algo, C.byref(d), C.byref(P), None, E.p(zz), None, E.p(w), None) == 0
+                else:
+                    E.lib().emu_pds_primal(algo, C.byref(d), C.byref(P), E.p(u), E.p(zz), None, E.p(xx) if algo == K.ALGO_PD3O else None, E.p(w), None)
+                    E.lib().emu_pds_dual(C.byref(d), C.byref(P), E.p(w), E.p(zz), None)
+                res.append((u, w, zz))
+            for a_, b_ in zip(res[1], res[0]):
+                assert relerr(a_, b_) < 1e-13, (trial, shape, mode, scheme, vec, algo)
