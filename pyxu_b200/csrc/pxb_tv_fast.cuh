@@ -259,6 +259,9 @@ PXB_HD void pxb_tv_fold_kz(const PxbTvP<T>& q, const T* __restrict__ zimg, int i
 // onto); out of line: a vanishing fraction of the cells takes it, its registers must not weigh on the tiled path.
 template <class T, int W, int NDIR, int ALGO>
 PXB_NOINLINE void pxb_tv_w_global(const PxbTvP<T>& q, const T* __restrict__ xu, const T* __restrict__ z, int64_t b, int i0, int i1, int i2, T* wv) {
+#if defined(PXB_EMU_COUNT_W_GLOBAL)  // tests/emu only: how many cells took this path
+    PXB_EMU_COUNT_W_GLOBAL += W;
+#endif
     const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2;
     const int64_t lin = b * q.vol + v;
     const T* __restrict__ zimg = z + b * NDIR * q.vol;

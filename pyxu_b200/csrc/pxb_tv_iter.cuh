@@ -123,6 +123,19 @@ PXB_HD bool pxb_any_mode(const pxb_grad_desc& d) {
     return false;
 }
 
+// The forms that stage their operands in shared memory (TMA) can often serve a rim cell without leaving the tile: the
+// rim cell at coordinate e (= t0 - 1 or t0 + tn) of a tile [t0, t0 + tn) along an axis of length n stands for
+//   e itself when it lies inside the domain,
+//   the sample the boundary map folds it onto when that sample belongs to the tile (reflect / symmetric / edge on the
+//   tile that touches the face; wrap only when the tile spans the axis),
+// else PXB_NOSRC: a zero of the 'constant' extension, or (MODES) a far sample that pxb_tv_w_outside fetches.
+PXB_HD int pxb_rim_src(int e, int n, int mode, int t0, int tn, bool modes) {
+    if (e >= 0 && e < n) return e;
+    if (!modes || mode == PXB_CONSTANT) return PXB_NOSRC;
+    const int f = pxb_bmap(e, n, mode);
+    return (f >= t0 && f < t0 + tn && f >= 0 && f < n) ? f : PXB_NOSRC;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // w (and, when `store`, the new primal iterate) for W consecutive samples starting at (m, r, c).
 // The samples lie inside the domain or on a ghost plane of an open slab side.

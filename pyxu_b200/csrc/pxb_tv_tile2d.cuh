@@ -153,14 +153,18 @@ PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
         if (top ? pxb_has_cm<S>(q, 0) : pxb_has_cp<S>(q, 0)) {
             const int br = top ? 0 : C::TY + 1, r = top ? it.r0 - 1 : it.r0 + C::TY, c = it.c0 + cl;
             T wv[VEC], xo[VEC], un[VEC], uo[VEC];
-            bool in = r >= 0 && r < g.n1 && c < g.n2;
-            pxb_t2_w<T, VEC, VEC, ALGO, S, MODES>(q, g, sm, br, cl + VEC, wv, xo, un, uo, in ? a.z_in + it.b * 2 * g.vol : nullptr, it.i0, r, c);
-            if (MODES && !in) {
-                pxb_tv_w_outside<T, VEC, 2, ALGO>(q, a.u_in, a.z_in, it.b, it.i0, r, c, wv);
-                in = true;
-            }
             PxbVec<T, VEC> o;
-            for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
+            if (MODES) {  // the row this rim row stands for (pxb_rim_src), evaluated from the tile's own boxes when it lies in the tile
+                const int rs = pxb_rim_src(r, g.n1, q.mode[1], it.r0, C::TY, true);
+                if (rs != PXB_NOSRC && c < g.n2)
+                    pxb_t2_w<T, VEC, VEC, ALGO, S, true>(q, g, sm, rs - (it.r0 - 1), cl + VEC, wv, xo, un, uo, a.z_in + it.b * 2 * g.vol, it.i0, rs, c);
+                else pxb_tv_w_outside<T, VEC, 2, ALGO>(q, a.u_in, a.z_in, it.b, it.i0, r, c, wv);  // a fold onto another tile ('wrap'), or zeros
+                for (int j = 0; j < VEC; ++j) o.v[j] = wv[j];
+            } else {
+                pxb_t2_w<T, VEC, VEC, ALGO, S>(q, g, sm, br, cl + VEC, wv, xo, un, uo);
+                const bool in = r >= 0 && r < g.n1 && c < g.n2;
+                for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
+            }
             pxb_vstore<T, VEC>(wsm + br * C::BW + cl + VEC, o);
         }
     }
@@ -170,13 +174,16 @@ PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
         if (left ? pxb_has_cm<S>(q, 1) : pxb_has_cp<S>(q, 1)) {
             const int bc = left ? VEC - 1 : VEC + C::T2, r = it.r0 + rl, c = left ? it.c0 - 1 : it.c0 + C::T2;
             T wv[1], xo[1], un[1], uo[1];
-            bool in = r < g.n1 && c >= 0 && c < g.n2;
-            pxb_t2_w<T, VEC, 1, ALGO, S, MODES>(q, g, sm, rl + 1, bc, wv, xo, un, uo, in ? a.z_in + it.b * 2 * g.vol : nullptr, it.i0, r, c);
-            if (MODES && !in) {
-                pxb_tv_w_outside<T, 1, 2, ALGO>(q, a.u_in, a.z_in, it.b, it.i0, r, c, wv);
-                in = true;
+            if (MODES) {
+                const int cs = pxb_rim_src(c, g.n2, q.mode[2], it.c0, C::T2, true);
+                if (r < g.n1 && cs != PXB_NOSRC)
+                    pxb_t2_w<T, VEC, 1, ALGO, S, true>(q, g, sm, rl + 1, cs - (it.c0 - VEC), wv, xo, un, uo, a.z_in + it.b * 2 * g.vol, it.i0, r, cs);
+                else pxb_tv_w_outside<T, 1, 2, ALGO>(q, a.u_in, a.z_in, it.b, it.i0, r, c, wv);
+                wsm[(rl + 1) * C::BW + bc] = wv[0];
+            } else {
+                pxb_t2_w<T, VEC, 1, ALGO, S>(q, g, sm, rl + 1, bc, wv, xo, un, uo);
+                wsm[(rl + 1) * C::BW + bc] = (r < g.n1 && c >= 0 && c < g.n2) ? wv[0] : T(0);
             }
-            wsm[(rl + 1) * C::BW + bc] = in ? wv[0] : T(0);
         }
     }
 }

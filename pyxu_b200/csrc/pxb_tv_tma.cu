@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(32 * TY, 2)
     for (int k = 0; k < 3; ++k)
         for (int j = 0; j < VEC; ++j) th.zc[k][j] = th.zprev[k][j] = T(0);
     for (int k = 0; k < 4; ++k) th.acc[k] = 0.0;
-    pxb_tma_prologue<T, VEC, TY>(q, g, it, a, tid, R.mlo, th);
+    pxb_tma_prologue<T, VEC, TY, MODES>(q, g, it, a, tid, R.mlo, th);
 
     const int lag = S::SCHEME == PXB_SCHEME_FWD ? 1 : R.lag;
     int s = 0;            // stage of plane m, and the parity of its mbarrier phase

@@ -184,7 +184,8 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
 }
 
 // z0 of plane mlo-1 at the samples whose previous-plane value this thread carries (start of a work item)
-template <class T, int VEC, int TY>
+// (MODES: a rim thread carries the value at the sample its rim cell stands for, see pxb_rim_src)
+template <class T, int VEC, int TY, bool MODES = false>
 PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid, int mlo,
                              PxbTmaThread<T, VEC>& st) {
     using C = PxbTmaCfg<T, VEC, TY>;
@@ -200,14 +201,14 @@ PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const Pxb
         if (r < g.nR && c < g.nC) { const PxbVec<T, VEC> v = pxb_vload<T, VEC>(z0 + (int64_t)r * g.sR + c); for (int j = 0; j < VEC; ++j) st.z0p[j] = v.v[j]; }
     }
     if (tid < 2 * C::TXL) {
-        const int r = tid < C::TXL ? it.r0 - 1 : it.r0 + TY, c = it.c0 + cl;
-        if (r >= 0 && r < g.nR && c < g.nC) { const PxbVec<T, VEC> v = pxb_vload<T, VEC>(z0 + (int64_t)r * g.sR + c); for (int j = 0; j < VEC; ++j) st.z0p_rim[j] = v.v[j]; }
+        const int r = pxb_rim_src(tid < C::TXL ? it.r0 - 1 : it.r0 + TY, g.nR, q.mode[1], it.r0, TY, MODES), c = it.c0 + cl;
+        if (r != PXB_NOSRC && c < g.nC) { const PxbVec<T, VEC> v = pxb_vload<T, VEC>(z0 + (int64_t)r * g.sR + c); for (int j = 0; j < VEC; ++j) st.z0p_rim[j] = v.v[j]; }
     }
     if (tid >= C::NT - 2 * TY) {
         const int h = tid - (C::NT - 2 * TY);
         const bool left = h < TY;
-        const int r = it.r0 + (left ? h : h - TY), c = left ? it.c0 - 1 : it.c0 + C::T2;
-        if (r < g.nR && c >= 0 && c < g.nC) st.z0p_col = z0[(int64_t)r * g.sR + c];
+        const int r = it.r0 + (left ? h : h - TY), c = pxb_rim_src(left ? it.c0 - 1 : it.c0 + C::T2, g.nC, q.mode[2], it.c0, C::T2, MODES);
+        if (r < g.nR && c != PXB_NOSRC) st.z0p_col = z0[(int64_t)r * g.sR + c];
     }
 }
 
@@ -267,21 +268,31 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         const bool top = tid < C::TXL;
         const int br = top ? 0 : TY + 1;
         const bool need = top ? pxb_has_cm<S>(q, 1) : pxb_has_cp<S>(q, 1);
+        int rs = 0, brs = br;  // MODES: the row this rim row stands for (pxb_rim_src) and its row in the staged boxes
+        if (MODES) {
+            rs = pxb_rim_src(top ? it.r0 - 1 : it.r0 + TY, g.nR, q.mode[1], it.r0, TY, true);
+            if (rs != PXB_NOSRC) brs = rs - (it.r0 - 1);
+        }
         if (own && need) {
             const int r = top ? it.r0 - 1 : it.r0 + TY, c = it.c0 + cl;
             T wv[VEC], z0c[VEC], z1c[VEC], z2c[VEC], xo[VEC], un[VEC], uo[VEC];
-            bool in = r >= 0 && r < g.nR && c < g.nC;
-            pxb_tma_w<T, VEC, TY, VEC, ALGO, S, MODES>(q, tg, st, st_next, br, cl + VEC, th.z0p_rim, wv, z0c, z1c, z2c, xo, un, uo,
-                                                       in ? a.z_in + it.b * 3 * g.vol : nullptr, m, r, c);
-            if (MODES && !in) {
-                pxb_tv_w_outside<T, VEC, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);
-                in = true;
+            if (MODES) {
+                const bool ev = rs != PXB_NOSRC && c < g.nC;
+                if (ev) pxb_tma_w<T, VEC, TY, VEC, ALGO, S, true>(q, tg, st, st_next, brs, cl + VEC, th.z0p_rim, wv, z0c, z1c, z2c, xo, un, uo,
+                                                                  a.z_in + it.b * 3 * g.vol, m, rs, c);
+                else pxb_tv_w_outside<T, VEC, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);  // a fold onto another tile ('wrap'), or zeros
+                PxbVec<T, VEC> o;
+                for (int j = 0; j < VEC; ++j) o.v[j] = wv[j];
+                pxb_vstore<T, VEC>(slot + br * R::RS + cl + VEC, o);
+            } else {
+                pxb_tma_w<T, VEC, TY, VEC, ALGO, S>(q, tg, st, st_next, br, cl + VEC, th.z0p_rim, wv, z0c, z1c, z2c, xo, un, uo);
+                const bool in = r >= 0 && r < g.nR && c < g.nC;
+                PxbVec<T, VEC> o;
+                for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
+                pxb_vstore<T, VEC>(slot + br * R::RS + cl + VEC, o);
             }
-            PxbVec<T, VEC> o;
-            for (int j = 0; j < VEC; ++j) o.v[j] = in ? wv[j] : T(0);
-            pxb_vstore<T, VEC>(slot + br * R::RS + cl + VEC, o);
         }
-        const PxbVec<T, VEC> z = pxb_vload<T, VEC>(st + C::OFF_Z0 + br * C::BW + cl + VEC);
+        const PxbVec<T, VEC> z = pxb_vload<T, VEC>(st + C::OFF_Z0 + (MODES ? brs : br) * C::BW + cl + VEC);
         for (int j = 0; j < VEC; ++j) th.z0p_rim[j] = z.v[j];
     }
     if (tid >= C::NT - 2 * TY) {
@@ -290,18 +301,26 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         const int hl = left ? h : h - TY;
         const int bc = left ? VEC - 1 : VEC + C::T2;
         const bool need = left ? pxb_has_cm<S>(q, 2) : pxb_has_cp<S>(q, 2);
+        int cs = 0, bcs = bc;  // MODES: the column this rim cell stands for and its column in the staged boxes
+        if (MODES) {
+            cs = pxb_rim_src(left ? it.c0 - 1 : it.c0 + C::T2, g.nC, q.mode[2], it.c0, C::T2, true);
+            if (cs != PXB_NOSRC) bcs = cs - (it.c0 - VEC);
+        }
         if (own && need) {
             const int r = it.r0 + hl, c = left ? it.c0 - 1 : it.c0 + C::T2;
             T wv[1], z0c[1], z1c[1], z2c[1], xo[1], un[1], uo[1];
-            bool in = r < g.nR && c >= 0 && c < g.nC;
-            pxb_tma_w<T, VEC, TY, 1, ALGO, S, MODES>(q, tg, st, st_next, hl + 1, bc, &th.z0p_col, wv, z0c, z1c, z2c, xo, un, uo,
-                                                     in ? a.z_in + it.b * 3 * g.vol : nullptr, m, r, c);
-            if (MODES && !in) {
-                pxb_tv_w_outside<T, 1, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);
-                in = true;
+            if (MODES) {
+                const bool ev = r < g.nR && cs != PXB_NOSRC;
+                if (ev) pxb_tma_w<T, VEC, TY, 1, ALGO, S, true>(q, tg, st, st_next, hl + 1, bcs, &th.z0p_col, wv, z0c, z1c, z2c, xo, un, uo,
+                                                                a.z_in + it.b * 3 * g.vol, m, r, cs);
+                else pxb_tv_w_outside<T, 1, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);
+                slot[(hl + 1) * R::RS + bc] = wv[0];
+            } else {
+                pxb_tma_w<T, VEC, TY, 1, ALGO, S>(q, tg, st, st_next, hl + 1, bc, &th.z0p_col, wv, z0c, z1c, z2c, xo, un, uo);
+                const bool in = r < g.nR && c >= 0 && c < g.nC;
+                slot[(hl + 1) * R::RS + bc] = in ? wv[0] : T(0);
             }
-            slot[(hl + 1) * R::RS + bc] = in ? wv[0] : T(0);
         }
-        th.z0p_col = st[C::OFF_Z0 + (hl + 1) * C::BW + bc];
+        th.z0p_col = st[C::OFF_Z0 + (hl + 1) * C::BW + (MODES ? bcs : bc)];
     }
 }

@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cstring>
 
+static long g_w_global_cells = 0;  // cells of the w tiles evaluated by pxb_tv_w_global (folded rims that left the tile)
+#define PXB_EMU_COUNT_W_GLOBAL g_w_global_cells
 #include "../../pyxu_b200/csrc/pxb_core.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_fast.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_iter.cuh"
@@ -231,7 +233,7 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
         for (int m = Rg.mlo; m < Rg.mlo + C::NSTAGE && m < mload_hi; ++m) issue(m);
         for (int tid = 0; tid < C::NT; ++tid) {
             std::memset(&th[tid], 0, sizeof(th[tid]));
-            pxb_tma_prologue<T, VEC, TY>(q, g, it, a, tid, Rg.mlo, th[tid]);
+            pxb_tma_prologue<T, VEC, TY, MODES>(q, g, it, a, tid, Rg.mlo, th[tid]);
         }
         for (int m = Rg.mlo; m < Rg.mhi; ++m) {
             const int k = m - Rg.mlo;
@@ -571,6 +573,11 @@ int emu_stencil2d_fista(const pxb_stencil2d* d, const pxb_fista_step* f, int whi
     return d->dtype == PXB_F32 ? t_st2<float>(d, f, which, nullptr, out) : t_st2<double>(d, f, which, nullptr, out);
 }
 void emu_set_iter_modes(int on) { g_allow_modes = on != 0; }
+long emu_w_global_cells(int reset) {
+    const long v = g_w_global_cells;
+    if (reset) g_w_global_cells = 0;
+    return v;
+}
 int emu_tv_iter_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
                     void* x_out, double* nx, double* nz, int chunk) {
     if (K->dtype == PXB_F32) return t_tma<float>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);

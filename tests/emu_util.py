@@ -23,6 +23,7 @@ def lib():
         h.emu_tv_fast.argtypes = [i, i, i, P(K.GradDesc), P(K.PdsParams), vp, vp, vp, vp, vp]
         h.emu_tv_iter.argtypes = [i, P(K.GradDesc), P(K.PdsParams), vp, vp, vp, vp, vp, vp, vp, i]
         h.emu_tv_iter_tma.argtypes = h.emu_tv_iter.argtypes
+        h.emu_w_global_cells.argtypes, h.emu_w_global_cells.restype = [i], C.c_long
         h.emu_tv_tile2d.argtypes = h.emu_tv_iter.argtypes
         h.emu_stencil2d.argtypes = [P(K.Stencil2D), vp, vp]
         h.emu_stencil2d_fista.argtypes = [P(K.Stencil2D), P(K.FistaStep), i, vp]

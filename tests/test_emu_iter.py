@@ -282,7 +282,8 @@ MODES = ["wrap", "reflect", "symmetric", "edge"]
 @pytest.mark.parametrize("form", ["direct", "tma"])
 def test_iter_modes_3d(mode, scheme, form):
     rng = np.random.default_rng(21)
-    for dtype, shape in ((np.float64, (7, 19, 2 * 64 + 6)), (np.float32, (3, 9, 4 * 32 + 8)), (np.float64, (3, 3, 4))):
+    # ragged tiles; full tiles (the folded rim of an edge tile is then served from its own staged boxes); a tiny volume
+    for dtype, shape in ((np.float64, (7, 19, 2 * 64 + 6)), (np.float32, (3, 9, 4 * 32 + 8)), (np.float64, (9, 16, 128)), (np.float32, (4, 8, 256)), (np.float64, (3, 3, 4))):
         Kop = pxo.Gradient(arg_shape=shape, scheme=scheme, mode=mode, sampling=(1.0, 0.5, 2.0))
         d = Kop._desc(1, E.dcode(np.zeros(1, dtype=dtype)))
         shift = rng.standard_normal(Kop.dim).astype(dtype)
@@ -310,7 +311,7 @@ def test_iter_modes_3d(mode, scheme, form):
 @pytest.mark.parametrize("form", ["direct", "tile2d"])
 def test_iter_modes_2d_batched(mode, scheme, form):
     rng = np.random.default_rng(23)
-    for dtype, shape, batch in ((np.float32, (37, 300), 2), (np.float64, (16, 64), 1), (np.float64, (3, 4), 3)):
+    for dtype, shape, batch in ((np.float32, (37, 300), 2), (np.float64, (16, 64), 1), (np.float32, (32, 256), 2), (np.float64, (3, 4), 3)):
         Kop = pxo.Gradient(arg_shape=shape, scheme=scheme, mode=mode)
         d = Kop._desc(batch, E.dcode(np.zeros(1, dtype=dtype)))
         shift = rng.standard_normal((batch, Kop.dim)).astype(dtype)
@@ -381,3 +382,30 @@ def test_iter_modes_golden_3d_mixed(form):
     y3 = golden("solvers.npz")["pd3o_tv3d/y"]
     x, z, g = _solve_modes("pd3o_tv3d/mixed", (10, 12, 14), ("reflect", "wrap", "constant"), 30, 0.08, POS, y3, y3.reshape(-1), form)
     assert relerr(x, g["pd3o_tv3d/mixed/x"]) < 1e-10 and relerr(z, g["pd3o_tv3d/mixed/z"]) < 1e-10
+
+
+def test_iter_modes_folded_rim_is_served_from_the_tile():
+    """On full tiles the staged forms evaluate a folded rim row / column from the tile's own boxes (pxb_rim_src): the
+    global-memory evaluator only runs for the plane past the last one (3-D) and for 'wrap', whose fold lands in another tile."""
+    rng = np.random.default_rng(31)
+    shape3, shape2 = (8, 16, 256), (32, 256)  # fp32: 2 x 2 tiles per plane; 2 x 2 tiles
+    counts = {}
+    for mode in ("reflect", "symmetric", "edge", "wrap"):
+        for form, shape in (("tma", shape3), ("tile2d", shape2)):
+            Kop = pxo.Gradient(arg_shape=shape, mode=mode, dtype=np.float32)
+            d = Kop._desc(1, K.F32)
+            shift = rng.standard_normal(Kop.dim).astype(np.float32)
+            P = E.pds_params(0.21, 0.19, 0.9, gspec=POS, fkind=K.F_SQL2, alpha=0.7, shift=shift, hkind=K.DUAL_L21, lam=0.3)
+            u, x, z = (rng.standard_normal(n).astype(np.float32) for n in (Kop.dim, Kop.dim, Kop.codim))
+            ua, za, xa = u.copy(), z.copy(), x.copy()
+            two_pass(K.ALGO_PD3O, d, P, ua, za, xa)
+            E.lib().emu_w_global_cells(1)
+            ub, zb = one_pass(K.ALGO_PD3O, d, P, u, z, x.copy(), form=form)
+            counts[mode, form] = E.lib().emu_w_global_cells(1)
+            assert relerr(ub, ua) < 2e-6 and relerr(zb, za) < 2e-6
+    plane = shape3[1] * shape3[2]
+    for mode in ("reflect", "symmetric", "edge"):
+        assert counts[mode, "tile2d"] == 0
+        assert counts[mode, "tma"] == plane  # forward differences: the plane past the last one, once per tile
+    assert counts["wrap", "tile2d"] == shape2[0] + shape2[1]          # one rim column cell per row + one rim row
+    assert counts["wrap", "tma"] == plane + shape3[0] * (shape3[1] + shape3[2])
