@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PXB_ABI_VERSION 1
+#define PXB_ABI_VERSION 2
 
 enum pxb_dtype { PXB_F32 = 0, PXB_F64 = 1 };
 
@@ -106,8 +106,41 @@ typedef struct pxb_stencil2d {
     double alpha, beta;
     const void* add;
     int64_t add_period;
+    /* Input images of another extent than the output (`shape`), and where the output grid sits in them: output sample    */
+    /* (y, x) correlates the input samples (y + origin[0] - center[0] + q1, x + origin[1] - center[1] + q2); samples        */
+    /* outside the input are zeros.  in_shape = {0, 0}: same extent, origin ignored.  in_shape[1] must be a multiple of     */
+    /* 4 (fp32) / 2 (fp64).  This is how the folding boundary modes run: S o Pad reads the padded array (pxb_pad2d) and      */
+    /* writes the trimmed one; S^T o Trim^T reads the array and writes the padded extent, which pxb_pad2d_adjoint folds.    */
+    int64_t in_shape[2];
+    int32_t origin[2];
 } pxb_stencil2d;
 int pxb_stencil2d_apply(const pxb_stencil2d* d, const void* in, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Pad over the two trailing axes and its transpose (reference: src/pyxu/operator/linop/pad.py:236-375), the pieces of  */
+/* Stencil = Trim o S0 o Pad (stencil.py:76-84) that the tiled stencil does not absorb when a mode folds.               */
+/*   ext is (nimg, ext_shape[0], ext_shape[1]); the array sits at rows [org[0], org[0] + shape[0]), columns             */
+/*   [org[1], org[1] + shape[1]) of it and is extended by lo[] / hi[] samples before / after (org >= lo; anything        */
+/*   beyond the padded extent is filler: alignment of the rows to 16 bytes).                                             */
+/*   pxb_pad2d:          ext[e1 + org[0], e2 + org[1]] = in[m1(e1), m2(e2)]   for -lo <= e < shape + hi, else 0          */
+/*                       (m = numpy.pad's index map of mode[]; 'constant' cells are 0)                                   */
+/*   pxb_pad2d_adjoint:  out[t1, t2] = alpha * sum over the cells (e1, e2) of the padded extent with m1(e1) = t1,        */
+/*                       m2(e2) = t2 of ext[e1 + org[0], e2 + org[1]]   +   beta * add[i % add_period]                   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct pxb_pad2d_desc {
+    int32_t dtype;
+    int32_t _pad;
+    int64_t nimg;
+    int64_t shape[2];
+    int64_t ext_shape[2];
+    int32_t org[2];
+    int32_t lo[2];
+    int32_t hi[2];
+    int32_t mode[2];
+} pxb_pad2d_desc;
+int pxb_pad2d(const pxb_pad2d_desc* d, const void* in, void* ext, void* stream);
+int pxb_pad2d_adjoint(const pxb_pad2d_desc* d, const void* ext, void* out, double alpha, double beta, const void* add,
+                      int64_t add_period, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------ */

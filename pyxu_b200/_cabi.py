@@ -18,7 +18,7 @@ DUAL_NONE, DUAL_L21, DUAL_L1 = range(3)
 F_NONE, F_SQL2, F_GRADARR = range(3)
 ALGO_PD3O, ALGO_CV = 0, 1
 MAX_DIRS, MAX_GTAP = 3, 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class NativeLibraryError(RuntimeError):
@@ -58,6 +58,22 @@ class Stencil2D(C.Structure):
         ("beta", C.c_double),
         ("add", C.c_void_p),
         ("add_period", C.c_int64),
+        ("in_shape", C.c_int64 * 2),
+        ("origin", C.c_int32 * 2),
+    ]
+
+
+class Pad2D(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("_pad", C.c_int32),
+        ("nimg", C.c_int64),
+        ("shape", C.c_int64 * 2),
+        ("ext_shape", C.c_int64 * 2),
+        ("org", C.c_int32 * 2),
+        ("lo", C.c_int32 * 2),
+        ("hi", C.c_int32 * 2),
+        ("mode", C.c_int32 * 2),
     ]
 
 
@@ -148,6 +164,8 @@ PROTOTYPES = {
     "pxb_stencil_adjoint": (_i, [_P(StencilDesc), _vp, _vp, _vp]),
     "pxb_stencil2d_apply": (_i, [_P(Stencil2D), _vp, _vp, _vp]),
     "pxb_stencil2d_fista": (_i, [_P(Stencil2D), _P(FistaStep), _i, _vp, _vp]),
+    "pxb_pad2d": (_i, [_P(Pad2D), _vp, _vp, _vp]),
+    "pxb_pad2d_adjoint": (_i, [_P(Pad2D), _vp, _vp, _d, _d, _vp, _i64, _vp]),
     "pxb_stencil_axis0_apply": (_i, [_i, _i64, _P(C.c_int64), _P(Slab), _i, _i, _P(C.c_double), _vp, _vp, _vp]),
     "pxb_stencil3d_apply": (_i, [_P(Stencil3D), _vp, _vp, _vp]),
     "pxb_gradient_apply": (_i, [_P(GradDesc), _vp, _vp, _vp]),

@@ -446,6 +446,41 @@ PXB_HD void pxb_body_dual(const pxb_grad_desc& d, const PxbGeom& g, const pxb_pd
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pad over the two trailing axes and its transpose (reference: pad.py:236-375), per sample.  See include/pyxu_b200.h.
+// ---------------------------------------------------------------------------------------------
+// cell (r, c) of the padded image `img`
+template <class T>
+PXB_HD T pxb_pad2d_at(const pxb_pad2d_desc& d, const T* __restrict__ in, int64_t img, int r, int c) {
+    const int n1 = (int)d.shape[0], n2 = (int)d.shape[1];
+    const int e1 = r - d.org[0], e2 = c - d.org[1];
+    if (e1 < -d.lo[0] || e1 >= n1 + d.hi[0] || e2 < -d.lo[1] || e2 >= n2 + d.hi[1]) return T(0);  // filler beyond the padded extent
+    const int j1 = pxb_bmap(e1, n1, d.mode[0]), j2 = pxb_bmap(e2, n2, d.mode[1]);
+    if (j1 == PXB_NOSRC || j2 == PXB_NOSRC) return T(0);
+    return in[(img * n1 + j1) * (int64_t)n2 + j2];
+}
+
+// sample (t1, t2) of Pad^T ext: every cell of the padded extent that was copied from it
+template <class T>
+PXB_HD T pxb_pad2d_adj_at(const pxb_pad2d_desc& d, const T* __restrict__ ext, int64_t img, int t1, int t2) {
+    const int n1 = (int)d.shape[0], n2 = (int)d.shape[1];
+    const int64_t m2 = d.ext_shape[1];
+    const T* __restrict__ e = ext + img * d.ext_shape[0] * m2;
+    PxbPre P1, P2;
+    pxb_preimage(t1, n1, d.mode[0], pxb_imax(d.lo[0], d.hi[0]), 0, 0, P1);
+    pxb_preimage(t2, n2, d.mode[1], pxb_imax(d.lo[1], d.hi[1]), 0, 0, P2);
+    T acc = T(0);
+    for (int a = 0; a < P1.cnt; ++a) {
+        const int r_lo = pxb_imax(P1.lo[a], -d.lo[0]), r_hi = pxb_imin(P1.hi[a], n1 + d.hi[0] - 1);
+        for (int r = r_lo; r <= r_hi; ++r)
+            for (int b = 0; b < P2.cnt; ++b) {
+                const int c_lo = pxb_imax(P2.lo[b], -d.lo[1]), c_hi = pxb_imin(P2.hi[b], n2 + d.hi[1] - 1);
+                for (int c = c_lo; c <= c_hi; ++c) acc += e[(int64_t)(r + d.org[0]) * m2 + c + d.org[1]];
+            }
+    }
+    return acc;
+}
+
 // dual update from a precomputed t = K w, arbitrary group size (outer, group, inner); same closed forms as above.
 template <class T>
 PXB_HD void pxb_body_dual_update(int kind, int64_t group, int64_t inner, T lam, T sigma, T rho, T* __restrict__ z,

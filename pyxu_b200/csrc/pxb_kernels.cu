@@ -314,6 +314,26 @@ unsigned flat_grid(int64_t n) {
     return (unsigned)b;
 }
 
+// Pad / Pad^T over the two trailing axes (pxb_pad2d / pxb_pad2d_adjoint): one thread per written sample
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_pad2d(const __grid_constant__ pxb_pad2d_desc d, const __grid_constant__ VoxMap m, const T* __restrict__ in,
+                                                  T* __restrict__ ext) {
+    const Vox v = vox_of_thread(m);
+    if (!v.ok) return;
+    ext[(v.b * d.ext_shape[0] + v.i1) * d.ext_shape[1] + v.i2] = pxb_pad2d_at<T>(d, in, v.b, v.i1, v.i2);
+}
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_pad2d_adjoint(const __grid_constant__ pxb_pad2d_desc d, const __grid_constant__ VoxMap m,
+                                                          const T* __restrict__ ext, T* __restrict__ out, T alpha, T beta, const T* __restrict__ add,
+                                                          int64_t add_period) {
+    const Vox v = vox_of_thread(m);
+    if (!v.ok) return;
+    const int64_t lin = (v.b * d.shape[0] + v.i1) * d.shape[1] + v.i2;
+    T o = alpha * pxb_pad2d_adj_at<T>(d, ext, v.b, v.i1, v.i2);
+    if (add) o += beta * add[add_period > 0 ? lin % add_period : lin];
+    out[lin] = o;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -391,6 +411,52 @@ int pxb_stencil2d_apply(const pxb_stencil2d* d, const void* in, void* out, void*
     if (int why = pxb_stencil2d_try(d, in, out, (cudaStream_t)stream, &err)) return fail(PXB_ENOSUP, "%s: outside the tiled kernel's envelope (reason %d)", who, why);
     pxb_count_launch();
     if (err != cudaSuccess) return fail(PXB_ECUDA, "%s: %s", who, cudaGetErrorString(err));
+    return 0;
+}
+
+static int pad2d_check(const pxb_pad2d_desc* d, const char* who) {
+    if (!d) return fail(PXB_EINVAL, "%s: null descriptor", who);
+    if (d->dtype != PXB_F32 && d->dtype != PXB_F64) return fail(PXB_EINVAL, "%s: bad dtype %d", who, d->dtype);
+    if (d->nimg < 1 || d->shape[0] < 1 || d->shape[1] < 1) return fail(PXB_EINVAL, "%s: empty array", who);
+    for (int a = 0; a < 2; ++a) {
+        if (d->lo[a] < 0 || d->hi[a] < 0 || d->org[a] < d->lo[a] || d->ext_shape[a] < d->org[a] + d->shape[a] + d->hi[a])
+            return fail(PXB_EINVAL, "%s: padded extent too small along axis %d", who, a);
+        if (d->mode[a] < PXB_CONSTANT || d->mode[a] > PXB_EDGE) return fail(PXB_EINVAL, "%s: bad mode %d", who, d->mode[a]);
+        // a coordinate folds at most once (pad.py:217-229)
+        const int64_t n = d->shape[a], w = d->lo[a] > d->hi[a] ? d->lo[a] : d->hi[a];
+        const int64_t lim = d->mode[a] == PXB_REFLECT ? n - 1 : ((d->mode[a] == PXB_WRAP || d->mode[a] == PXB_SYMMETRIC) ? n : w);
+        if (w > lim) return fail(PXB_EINVAL, "%s: pad width %lld along axis %d exceeds the limit %lld of the mode", who, (long long)w, a, (long long)lim);
+    }
+    return 0;
+}
+
+int pxb_pad2d(const pxb_pad2d_desc* d, const void* in, void* ext, void* stream) {
+    const char* who = "pxb_pad2d";
+    if (int rc = pad2d_check(d, who)) return rc;
+    if (!in || !ext || in == ext) return fail(PXB_EINVAL, "%s: null or aliased arrays", who);
+    VoxMap m;
+    const int64_t sh[3] = {1, d->ext_shape[0], d->ext_shape[1]};
+    if (!make_map(d->nimg, sh, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->dtype == PXB_F32) k_pad2d<float><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const float*)in, (float*)ext);
+    else k_pad2d<double><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const double*)in, (double*)ext);
+    PXB_CHECK_LAUNCH(who);
+    return 0;
+}
+
+int pxb_pad2d_adjoint(const pxb_pad2d_desc* d, const void* ext, void* out, double alpha, double beta, const void* add, int64_t add_period,
+                      void* stream) {
+    const char* who = "pxb_pad2d_adjoint";
+    if (int rc = pad2d_check(d, who)) return rc;
+    if (!ext || !out || ext == out) return fail(PXB_EINVAL, "%s: null or aliased arrays", who);
+    VoxMap m;
+    const int64_t sh[3] = {1, d->shape[0], d->shape[1]};
+    if (!make_map(d->nimg, sh, m)) return fail(PXB_ENOSUP, "%s: grid too large", who);
+    if (add && add_period >= d->nimg * d->shape[0] * d->shape[1]) add_period = 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->dtype == PXB_F32) k_pad2d_adjoint<float><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const float*)ext, (float*)out, (float)alpha, (float)beta, (const float*)add, add_period);
+    else k_pad2d_adjoint<double><<<grid_of(m), kBlock, 0, s>>>(*d, m, (const double*)ext, (double*)out, alpha, beta, (const double*)add, add_period);
+    PXB_CHECK_LAUNCH(who);
     return 0;
 }
 

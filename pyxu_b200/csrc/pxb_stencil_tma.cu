@@ -221,11 +221,12 @@ cudaError_t launch_nv(const PxbSt2P& p, const CUtensorMap& map, const CUtensorMa
 }
 
 template <class T>
-int run(PxbSt2P& p, const void* in, const void* in2, void* out, cudaStream_t s, cudaError_t* err) {
+int run(PxbSt2P& p, const PxbSt2In* ext, const void* in, const void* in2, void* out, cudaStream_t s, cudaError_t* err) {
     constexpr int VEC = 16 / (int)sizeof(T);
-    if (int why = pxb_st2_setup<T, VEC>(p)) return why;
-    const uint64_t dim[3] = {(uint64_t)p.n2, (uint64_t)p.n1, (uint64_t)p.nimg};
-    const uint64_t stride[3] = {1, (uint64_t)p.n2, (uint64_t)p.n1 * (uint64_t)p.n2};
+    if (int why = pxb_st2_setup<T, VEC>(p, ext)) return why;
+    const uint64_t in_n1 = ext ? ext->n1 : p.n1, in_n2 = ext ? ext->n2 : p.n2;
+    const uint64_t dim[3] = {in_n2, in_n1, (uint64_t)p.nimg};
+    const uint64_t stride[3] = {1, in_n2, in_n1 * in_n2};
     const uint32_t box[3] = {(uint32_t)p.bw, (uint32_t)p.bh, 1};
     alignas(64) CUtensorMap map, map2;
     if (!pxb_tma_encode<T>(3, in, dim, stride, box, &map)) return 10;
@@ -247,31 +248,42 @@ int run(PxbSt2P& p, const void* in, const void* in2, void* out, cudaStream_t s, 
     return 0;
 }
 
-// fills the kernel parameter block from the C-ABI descriptors (shared with tests/emu through the header? no: host only)
-void fill(PxbSt2P& p, const pxb_stencil2d* d) {
+// fills the kernel parameter block from the C-ABI descriptors (shared with tests/emu through the header? no: host only);
+// true when the input has an extent of its own (`ext`)
+bool fill(PxbSt2P& p, PxbSt2In& ext, const pxb_stencil2d* d) {
     p.n1 = (int)d->shape[0]; p.n2 = (int)d->shape[1]; p.nimg = d->nimg;
     p.k1 = d->ksize[0]; p.k2 = d->ksize[1]; p.c1 = d->center[0]; p.c2 = d->center[1];
+    const bool own_extent = d->in_shape[0] > 0 && d->in_shape[1] > 0;
+    if (own_extent) {  // fold the origin of the output grid into the centers: the kernels only use them to place their windows
+        ext.n1 = (int)d->in_shape[0]; ext.n2 = (int)d->in_shape[1];
+        p.c1 -= d->origin[0]; p.c2 -= d->origin[1];
+    }
     p.dense = d->dense;
     for (int i = 0; i < PXB_ST2_MAXTAP; ++i) { p.coef1[i] = d->coef1[i]; p.coef2[i] = d->coef2[i]; }
     p.coef = d->coef; p.alpha = d->alpha; p.beta = d->beta; p.add = d->add; p.add_period = d->add_period;
     if (d->add && d->add_period > 0 && d->add_period >= d->nimg * d->shape[0] * d->shape[1]) p.add_period = 0;
     p.pa = 1.0; p.pb = 0.0; p.epi = 0; p.e1 = p.e2 = nullptr; p.ea = p.eb = 0.0; p.gkind = 0; p.gp0 = p.gp1 = p.tau = 0.0;
     p.norms = nullptr; p.imgs_per_row = 1;
+    return own_extent;
 }
 
 }  // namespace
 
 // > 0: outside the envelope (reason); 0: launched or *err set
 int pxb_stencil2d_try(const pxb_stencil2d* d, const void* in, void* out, cudaStream_t s, cudaError_t* err) {
+    if (d->center[0] < 0 || d->center[0] >= d->ksize[0] || d->center[1] < 0 || d->center[1] >= d->ksize[1]) return 3;
     PxbSt2P p;
-    fill(p, d);
+    PxbSt2In ext;
+    const PxbSt2In* pe = fill(p, ext, d) ? &ext : nullptr;
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(d->add)) & 15u) return 6;
-    return d->dtype == PXB_F32 ? run<float>(p, in, nullptr, out, s, err) : run<double>(p, in, nullptr, out, s, err);
+    return d->dtype == PXB_F32 ? run<float>(p, pe, in, nullptr, out, s, err) : run<double>(p, pe, in, nullptr, out, s, err);
 }
 
 int pxb_stencil2d_fista_try(const pxb_stencil2d* d, const pxb_fista_step* f, int which, void* out, cudaStream_t s, cudaError_t* err) {
+    if (d->in_shape[0] > 0 || d->in_shape[1] > 0) return 7;  // the fused proximal-gradient passes keep input and output on one grid
     PxbSt2P p;
-    fill(p, d);
+    PxbSt2In ext;
+    fill(p, ext, d);
     if ((reinterpret_cast<uintptr_t>(f->x) | reinterpret_cast<uintptr_t>(f->x_prev) | reinterpret_cast<uintptr_t>(f->r) | reinterpret_cast<uintptr_t>(out) |
          reinterpret_cast<uintptr_t>(d->add)) & 15u)
         return 6;
@@ -287,5 +299,5 @@ int pxb_stencil2d_fista_try(const pxb_stencil2d* d, const pxb_fista_step* f, int
         p.gkind = f->g.kind; p.gp0 = f->g.p0; p.gp1 = f->g.p1; p.tau = f->tau;
         p.norms = f->norms; p.imgs_per_row = f->imgs_per_row > 0 ? f->imgs_per_row : 1;
     }
-    return d->dtype == PXB_F32 ? run<float>(p, in, in2, out, s, err) : run<double>(p, in, in2, out, s, err);
+    return d->dtype == PXB_F32 ? run<float>(p, nullptr, in, in2, out, s, err) : run<double>(p, nullptr, in, in2, out, s, err);
 }

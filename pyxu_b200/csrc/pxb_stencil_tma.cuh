@@ -16,9 +16,11 @@
 #define PXB_ST2_MAXTAP 16
 
 struct PxbSt2P {          // by-value kernel parameter
-    int n1, n2;           // image rows, columns
+    int n1, n2;           // image rows, columns (the OUTPUT grid)
     int64_t nimg;
-    int k1, k2, c1, c2;   // taps / centers along rows (axis 1) and columns (axis 2) -- k2 / c2 AFTER the alignment padding below
+    int k1, k2, c1, c2;   // taps / centers along rows (axis 1) and columns (axis 2) -- k2 / c2 AFTER the alignment padding below;
+                          // the window of output tile (y0, x0) starts at input sample (y0 - c1, x0 - c2): with an input of another
+                          // extent the origin of the output grid is folded into c1 / c2, which then may leave [0, k)
     int k2src, extra;     // TMA box starts must be 16-byte aligned in global memory (measured: a start at c0 - 3 floats
                           // faults): the column factor gets `extra` leading zero taps so that its center is a multiple of VEC
     int dense;
@@ -42,6 +44,12 @@ struct PxbSt2P {          // by-value kernel parameter
     double gp0, gp1, tau;
     double* norms;
     int64_t imgs_per_row;
+};
+
+// Host side only: extent of the input images when it differs from the output grid (pxb_stencil2d::in_shape).  It shapes
+// the tensor map, whose zero fill is the 'constant' extension of the input; the kernels never see it.
+struct PxbSt2In {
+    int n1, n2;
 };
 
 template <class T, int VEC>
@@ -237,10 +245,12 @@ PXB_HD int pxb_st2_nv(int k, int vec) { return (k - 1 + vec + vec - 1) / vec; }
 
 // host: geometry.  Returns 0 or a reason code when outside the envelope.
 template <class T, int VEC>
-inline int pxb_st2_setup(PxbSt2P& p) {
+inline int pxb_st2_setup(PxbSt2P& p, const PxbSt2In* in = nullptr) {
     using C = PxbSt2Cfg<T, VEC>;
     if (p.k1 < 1 || p.k2 < 1 || p.k1 > PXB_ST2_MAXTAP || p.k2 > PXB_ST2_MAXTAP) return 1;
-    if (p.c1 < 0 || p.c1 >= p.k1 || p.c2 < 0 || p.c2 >= p.k2) return 3;
+    // (with an input of another extent the centers were validated before the origin was folded into them)
+    if (!in && (p.c1 < 0 || p.c1 >= p.k1 || p.c2 < 0 || p.c2 >= p.k2)) return 3;
+    if (in && in->n2 % VEC) return 2;
     p.k2src = p.k2;
     p.extra = (VEC - p.c2 % VEC) % VEC;
     if (p.k2 + p.extra > PXB_ST2_MAXTAP) return 1;

@@ -24,6 +24,13 @@ from ...abc.operator import device_io
 
 _PAD_LIMIT = dict(constant=np.inf, wrap=lambda n: n, reflect=lambda n: n - 1, symmetric=lambda n: n, edge=np.inf)
 
+# Folding boundary modes through Pad -> tiled stencil / tiled stencil -> Pad^T (Stencil._run_padded) instead of the gather
+# kernels.  Verified against the gather kernels and the reference's fixtures on the CPU emulation of the kernel bodies;
+# off until it has run on a GPU (PYXU_B200_STENCIL_PADDED=1 switches it on).
+import os as _os
+
+PADDED_TILED = _os.environ.get("PYXU_B200_STENCIL_PADDED", "0") == "1"
+
 
 def canonical_mode(mode, ndim):
     """tuple[str] of length ndim (reference: pad.py:190-205)."""
@@ -116,6 +123,8 @@ class Stencil(pxo.SquareOp):
         self._dev_coef = {}  # (dtype, device, pass, flipped) -> device tensor
         self._tiled_ok = None  # TMA-tiled single-pass kernel (pxb_stencil2d_apply): None = not tried yet
         self._tiled3d_ok = None  # single-pass separable 3-D kernel (pxb_stencil3d_apply)
+        self._padded_ok = None  # Pad -> tiled stencil / tiled stencil -> Pad^T for folding boundary modes (_run_padded)
+        self._folds = any(m != "constant" for m, p in zip(self._mode, self._pad_width) if p[0] > 0)
         self.lipschitz = self.estimate_lipschitz(__rule=True)
 
     # -- descriptors ---------------------------------------------------------------------
@@ -164,10 +173,11 @@ class Stencil(pxo.SquareOp):
         return t
 
     # -- TMA-tiled path ('constant' boundaries) --------------------------------------------------------
-    def _tiled_plan(self, adjoint):
+    def _tiled_plan(self, adjoint, allow_modes=False):
         """Splits the stencil into (factor along axis 0 | None, in-plane part) when the tiled kernel applies.
-        In-plane part: ("sep", taps1, c1, taps2, c2) or ("dense", k2d, c1, c2).  None when not applicable."""
-        if any(m != "constant" for m, p in zip(self._mode, self._pad_width) if p[0] > 0):
+        In-plane part: ("sep", taps1, c1, taps2, c2) or ("dense", k2d, c1, c2).  None when not applicable.
+        allow_modes: also for folding boundary modes (the caller then wraps the in-plane part in Pad / Pad^T, _run_padded)."""
+        if not allow_modes and any(m != "constant" for m, p in zip(self._mode, self._pad_width) if p[0] > 0):
             return None
         passes = self._passes(False)
         if adjoint:  # zero-padded correlation: transpose = correlation with the reversed kernel, mirrored center
@@ -305,9 +315,112 @@ class Stencil(pxo.SquareOp):
         d.slab = slab if slab is not None else K.Slab(0, 0, 0, 0)
         return d
 
+    # -- folding boundary modes through the tiled kernel -------------------------------------------------
+    def _run_padded(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
+        """Stencil = Trim o S0 o Pad (reference: stencil.py:76-84) with a folding mode on an in-plane axis, as two passes over
+        HBM instead of the gather kernels' per-sample index maps:
+            apply    Pad (pxb_pad2d, folded halo written once)  ->  tiled S0 reading the padded array, writing the trimmed one
+            adjoint  tiled S0^T reading the array (zero-extended by the TMA unit = Trim^T), writing the padded extent
+                     ->  Pad^T (pxb_pad2d_adjoint: every padded cell added onto the sample it was copied from)
+        The per-axis operators commute, so a factor along axis 0 keeps its own pass.  None when the tiled kernel does not apply."""
+        if self._padded_ok is False:
+            return None
+        plan = self._tiled_plan(adjoint, allow_modes=True)
+        if plan is None:
+            self._padded_ok = False
+            return None
+        axis0, inplane, scale = plan
+        D = len(self._arg_shape)
+        shape3 = (1,) * (3 - D) + self._arg_shape
+        mode3 = ("constant",) * (3 - D) + self._mode
+        n1, n2 = shape3[1], shape3[2]
+        vec = 16 // arr.element_size()
+        if n2 % vec:
+            self._padded_ok = False
+            return None
+        batch = max(1, arr.numel() // self.dim)
+        nimg = batch * shape3[0]
+        if inplane[0] == "dense":
+            _, k2d, c1, c2 = inplane
+            k1n, k2n = k2d.shape
+        else:
+            _, t1, c1, t2, c2 = inplane
+            k1n, k2n = t1.size, t2.size
+        # pad widths of the operator itself: (center, k - 1 - center); the plan of the adjoint carries the mirrored center
+        lo = [k1n - 1 - c1, k2n - 1 - c2] if adjoint else [c1, c2]
+        hi = [c1, c2] if adjoint else [k1n - 1 - c1, k2n - 1 - c2]
+        for a in (0, 1):  # a 'constant' axis needs no halo: the TMA zero fill is its extension
+            if mode3[1 + a] == "constant":
+                lo[a] = hi[a] = 0
+        org = (lo[0], -(-lo[1] // vec) * vec)  # rows of the padded array stay 16-byte aligned, and so does the image inside them
+        n1e, n2e = n1 + lo[0] + hi[0], -(-(org[1] + n2 + hi[1]) // vec) * vec
+        pd = K.Pad2D()
+        pd.dtype, pd.nimg = A.dcode(arr), nimg
+        pd.shape[0], pd.shape[1], pd.ext_shape[0], pd.ext_shape[1] = n1, n2, n1e, n2e
+        for a in (0, 1):
+            pd.org[a], pd.lo[a], pd.hi[a], pd.mode[a] = org[a], lo[a], hi[a], K.MODES[mode3[1 + a]]
+        d = K.Stencil2D()
+        d.dtype, d.nimg = A.dcode(arr), nimg
+        if inplane[0] == "dense":
+            key = ("tiled", adjoint, arr.dtype, arr.device)
+            keep = self._dev_coef.get(key)
+            if keep is None:
+                keep, _ = A.asdevice(np.ascontiguousarray(k2d.reshape(-1)), dtype=arr.dtype)
+                self._dev_coef[key] = keep
+            d.dense, d.coef = 1, keep.data_ptr()
+        else:
+            d.dense = 0
+            for i, v in enumerate(t1):
+                d.coef1[i] = float(v)
+            for i, v in enumerate(t2):
+                d.coef2[i] = float(v)
+        d.ksize[0], d.ksize[1], d.center[0], d.center[1] = k1n, k2n, c1, c2
+        cur = arr
+        if axis0 is not None:  # the factor along the slowest axis: its own pass (commutes with the in-plane part)
+            tmp = A.empty_like(arr)
+            if mode3[0] == "constant":
+                self._axis0_pass(axis0, cur, tmp, batch)
+            else:  # gather kernel with the boundary map; the plan of the adjoint holds the reversed kernel: undo
+                k3, c3 = axis0
+                if adjoint:
+                    k3, c3 = np.ascontiguousarray(np.flip(k3)), np.array(k3.shape) - c3 - 1
+                coef, _ = A.asdevice(k3.reshape(-1), dtype=arr.dtype)
+                dd = self._desc(k3, c3, batch, A.dcode(arr), coef.data_ptr())
+                fn = K.lib().pxb_stencil_adjoint if adjoint else K.lib().pxb_stencil_apply
+                K.check(fn(C.byref(dd), A.ptr(cur), A.ptr(tmp), A.stream()), "Stencil (axis 0)")
+            cur = tmp
+        import torch
+
+        ext = torch.empty(nimg * n1e * n2e, dtype=arr.dtype, device=arr.device)
+        out = A.empty_like(arr)
+        if not adjoint:
+            K.check(K.lib().pxb_pad2d(C.byref(pd), A.ptr(cur), A.ptr(ext), A.stream()), "pxb_pad2d")
+            d.shape[0], d.shape[1], d.in_shape[0], d.in_shape[1] = n1, n2, n1e, n2e
+            d.origin[0], d.origin[1] = org
+            d.alpha, d.beta = float(alpha) * scale, float(beta)
+            if add is not None:
+                d.add, d.add_period = add.data_ptr(), add.numel()
+            rc = K.lib().pxb_stencil2d_apply(C.byref(d), A.ptr(ext), A.ptr(out), A.stream())
+        else:
+            d.shape[0], d.shape[1], d.in_shape[0], d.in_shape[1] = n1e, n2e, n1, n2
+            d.origin[0], d.origin[1] = -org[0], -org[1]
+            d.alpha, d.beta = scale, 0.0
+            rc = K.lib().pxb_stencil2d_apply(C.byref(d), A.ptr(cur), A.ptr(ext), A.stream())
+        if rc == -3:
+            self._padded_ok = False
+            return None
+        K.check(rc, "pxb_stencil2d_apply")
+        if adjoint:
+            K.check(K.lib().pxb_pad2d_adjoint(C.byref(pd), A.ptr(ext), A.ptr(out), float(alpha), float(beta), A.ptr(add) if add is not None else None,
+                                              add.numel() if add is not None else 0, A.stream()), "pxb_pad2d_adjoint")
+        self._padded_ok = True
+        return out
+
     def _run_tiled(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
         """One pass over HBM for the in-plane part (+ one streaming pass when there is a factor along axis 0 that the
         single-pass 3-D kernel does not take).  Returns None when the tiled kernels do not apply."""
+        if PADDED_TILED and self._folds:
+            return self._run_padded(arr, adjoint, alpha, beta, add)
         batch = max(1, arr.numel() // self.dim)
         if self._tiled3d_ok is not False:
             d3 = self._desc3d(A.dcode(arr), adjoint, batch, alpha, beta, add)

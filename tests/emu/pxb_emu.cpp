@@ -288,7 +288,8 @@ static int t_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
 // TMA-tiled 2-D stencil (pxb_stencil_tma.cuh): box load emulated as a zero-filled gather, then the device's
 // per-thread bodies in barrier order.
 template <class T, int VEC, int NV>
-static void t_st2_nv(const PxbSt2P& p, const T* in, const T* in2, T* out) {
+static void t_st2_nv(const PxbSt2P& p, const PxbSt2In& ext, const T* in, const T* in2, T* out) {
+    const int in_n1 = ext.n1, in_n2 = ext.n2;
     using C = PxbSt2Cfg<T, VEC>;
     std::vector<T> box((size_t)p.bh * p.bw), box2((size_t)p.bh * p.bw), mid((size_t)p.bh * C::TX + (size_t)p.k1 * p.k2);
     for (int64_t img = 0; img < p.nimg; ++img)
@@ -298,9 +299,9 @@ static void t_st2_nv(const PxbSt2P& p, const T* in, const T* in2, T* out) {
                 for (int i = 0; i < p.bh; ++i)
                     for (int j = 0; j < p.bw; ++j) {
                         const int y = y0 - p.c1 + i, x = x0 - p.c2 + j;
-                        const bool ok = y >= 0 && y < p.n1 && x >= 0 && x < p.n2;
-                        box[(size_t)i * p.bw + j] = ok ? in[(img * p.n1 + y) * (int64_t)p.n2 + x] : T(0);
-                        if (in2) box2[(size_t)i * p.bw + j] = ok ? in2[(img * p.n1 + y) * (int64_t)p.n2 + x] : T(0);
+                        const bool ok = y >= 0 && y < in_n1 && x >= 0 && x < in_n2;  // the tensor map's extent: zero fill beyond
+                        box[(size_t)i * p.bw + j] = ok ? in[(img * in_n1 + y) * (int64_t)in_n2 + x] : T(0);
+                        if (in2) box2[(size_t)i * p.bw + j] = ok ? in2[(img * in_n1 + y) * (int64_t)in_n2 + x] : T(0);
                     }
                 if (in2)
                     for (int it = 0; it < p.bh * p.bw / VEC; ++it) pxb_st2_combine_item<T, VEC>(p, box.data(), box2.data(), it);
@@ -337,6 +338,14 @@ static int t_st2(const pxb_stencil2d* d, const pxb_fista_step* f, int which, con
     PxbSt2P p;
     p.n1 = (int)d->shape[0]; p.n2 = (int)d->shape[1]; p.nimg = d->nimg;
     p.k1 = d->ksize[0]; p.k2 = d->ksize[1]; p.c1 = d->center[0]; p.c2 = d->center[1];
+    if (p.c1 < 0 || p.c1 >= p.k1 || p.c2 < 0 || p.c2 >= p.k2) return -103;
+    PxbSt2In ext{p.n1, p.n2};
+    const bool own_extent = d->in_shape[0] > 0 && d->in_shape[1] > 0;
+    if (own_extent) {  // as the launcher: the origin of the output grid folded into the centers
+        if (f) return -107;
+        ext.n1 = (int)d->in_shape[0]; ext.n2 = (int)d->in_shape[1];
+        p.c1 -= d->origin[0]; p.c2 -= d->origin[1];
+    }
     p.dense = d->dense;
     for (int i = 0; i < PXB_ST2_MAXTAP; ++i) { p.coef1[i] = d->coef1[i]; p.coef2[i] = d->coef2[i]; }
     p.coef = d->coef; p.alpha = d->alpha; p.beta = d->beta; p.add = d->add; p.add_period = d->add_period;
@@ -357,14 +366,14 @@ static int t_st2(const pxb_stencil2d* d, const pxb_fista_step* f, int which, con
             p.norms = f->norms; p.imgs_per_row = f->imgs_per_row > 0 ? f->imgs_per_row : 1;
         }
     }
-    if (int why = pxb_st2_setup<T, VEC>(p)) return -100 - why;
+    if (int why = pxb_st2_setup<T, VEC>(p, own_extent ? &ext : nullptr)) return -100 - why;
     switch (pxb_st2_nv(p.k2, VEC)) {
-        case 1: t_st2_nv<T, VEC, 1>(p, (const T*)in, (const T*)in2, (T*)out); break;
-        case 2: t_st2_nv<T, VEC, 2>(p, (const T*)in, (const T*)in2, (T*)out); break;
-        case 3: t_st2_nv<T, VEC, 3>(p, (const T*)in, (const T*)in2, (T*)out); break;
-        case 4: t_st2_nv<T, VEC, 4>(p, (const T*)in, (const T*)in2, (T*)out); break;
-        case 5: t_st2_nv<T, VEC, 5>(p, (const T*)in, (const T*)in2, (T*)out); break;
-        case 6: t_st2_nv<T, VEC, 6>(p, (const T*)in, (const T*)in2, (T*)out); break;
+        case 1: t_st2_nv<T, VEC, 1>(p, ext, (const T*)in, (const T*)in2, (T*)out); break;
+        case 2: t_st2_nv<T, VEC, 2>(p, ext, (const T*)in, (const T*)in2, (T*)out); break;
+        case 3: t_st2_nv<T, VEC, 3>(p, ext, (const T*)in, (const T*)in2, (T*)out); break;
+        case 4: t_st2_nv<T, VEC, 4>(p, ext, (const T*)in, (const T*)in2, (T*)out); break;
+        case 5: t_st2_nv<T, VEC, 5>(p, ext, (const T*)in, (const T*)in2, (T*)out); break;
+        case 6: t_st2_nv<T, VEC, 6>(p, ext, (const T*)in, (const T*)in2, (T*)out); break;
         default: return -101;
     }
     return 0;
@@ -552,6 +561,22 @@ static int t_st3(const pxb_stencil3d* d, const void* in, void* out) {
     }
 }
 
+template <class T>
+static void t_pad2d(const pxb_pad2d_desc* d, bool adj, const void* a, void* b, double alpha, double beta, const void* add, int64_t add_period) {
+    const int64_t rows = adj ? d->shape[0] : d->ext_shape[0], cols = adj ? d->shape[1] : d->ext_shape[1];
+    if (add && add_period >= d->nimg * d->shape[0] * d->shape[1]) add_period = 0;
+    for (int64_t img = 0; img < d->nimg; ++img)
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) {
+                const int64_t lin = (img * rows + r) * cols + c;
+                if (!adj) ((T*)b)[lin] = pxb_pad2d_at<T>(*d, (const T*)a, img, r, c);
+                else {
+                    T o = T(alpha) * pxb_pad2d_adj_at<T>(*d, (const T*)a, img, r, c);
+                    if (add) o += T(beta) * ((const T*)add)[add_period > 0 ? lin % add_period : lin];
+                    ((T*)b)[lin] = o;
+                }
+            }
+}
 extern "C" {
 int emu_stencil3d(const pxb_stencil3d* d, const void* in, void* out) {
     return d->dtype == PXB_F32 ? t_st3<float>(d, in, out) : t_st3<double>(d, in, out);
@@ -565,6 +590,14 @@ int emu_tv_tile2d(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, con
     (void)unused;
     if (K->dtype == PXB_F32) return t_t2<float>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz);
     return t_t2<double>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz);
+}
+int emu_pad2d(const pxb_pad2d_desc* d, const void* in, void* ext) {
+    if (d->dtype == PXB_F32) t_pad2d<float>(d, false, in, ext, 1.0, 0.0, nullptr, 0); else t_pad2d<double>(d, false, in, ext, 1.0, 0.0, nullptr, 0);
+    return 0;
+}
+int emu_pad2d_adjoint(const pxb_pad2d_desc* d, const void* ext, void* out, double alpha, double beta, const void* add, int64_t add_period) {
+    if (d->dtype == PXB_F32) t_pad2d<float>(d, true, ext, out, alpha, beta, add, add_period); else t_pad2d<double>(d, true, ext, out, alpha, beta, add, add_period);
+    return 0;
 }
 int emu_stencil2d(const pxb_stencil2d* d, const void* in, void* out) {
     return d->dtype == PXB_F32 ? t_st2<float>(d, nullptr, 0, in, out) : t_st2<double>(d, nullptr, 0, in, out);

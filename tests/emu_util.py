@@ -26,6 +26,8 @@ def lib():
         h.emu_w_global_cells.argtypes, h.emu_w_global_cells.restype = [i], C.c_long
         h.emu_tv_tile2d.argtypes = h.emu_tv_iter.argtypes
         h.emu_stencil2d.argtypes = [P(K.Stencil2D), vp, vp]
+        h.emu_pad2d.argtypes = [P(K.Pad2D), vp, vp]
+        h.emu_pad2d_adjoint.argtypes = [P(K.Pad2D), vp, vp, d, d, vp, i64]
         h.emu_stencil2d_fista.argtypes = [P(K.Stencil2D), P(K.FistaStep), i, vp]
         h.emu_tv_grad.argtypes = [i, i, P(K.GradDesc), vp, vp]
         h.emu_stencil3d.argtypes = [P(K.Stencil3D), vp, vp]
@@ -139,3 +141,80 @@ def stencil3d_run(op, x, adjoint, alpha=1.0, beta=0.0, add=None, slab=None, shap
     out = np.empty_like(x)
     rc = lib().emu_stencil3d(C.byref(d), p(np.ascontiguousarray(x)), p(out))
     return out if rc == 0 else None
+
+
+def stencil_run_padded(op, x, adjoint, alpha=1.0, beta=0.0, add=None):
+    """Mirror of Stencil._run_padded on host arrays: Pad -> tiled stencil (apply) / tiled stencil -> Pad^T (adjoint), emulated."""
+    x = np.ascontiguousarray(x)
+    plan = op._tiled_plan(adjoint, allow_modes=True)
+    if plan is None:
+        return None
+    axis0, inplane, scale = plan
+    D = len(op._arg_shape)
+    shape3 = (1,) * (3 - D) + op._arg_shape
+    mode3 = ("constant",) * (3 - D) + op._mode
+    n1, n2 = shape3[1], shape3[2]
+    vec = 16 // x.itemsize
+    if n2 % vec:
+        return None
+    batch = max(1, x.size // op.dim)
+    nimg = batch * shape3[0]
+    keep = None
+    d = K.Stencil2D()
+    d.dtype, d.nimg = dcode(x), nimg
+    if inplane[0] == "dense":
+        _, k2d, c1, c2 = inplane
+        k1n, k2n = k2d.shape
+        keep = np.ascontiguousarray(k2d.reshape(-1), dtype=x.dtype)
+        d.dense, d.coef = 1, keep.ctypes.data
+    else:
+        _, t1, c1, t2, c2 = inplane
+        k1n, k2n = t1.size, t2.size
+        for i, v in enumerate(t1):
+            d.coef1[i] = float(v)
+        for i, v in enumerate(t2):
+            d.coef2[i] = float(v)
+    d.ksize[0], d.ksize[1], d.center[0], d.center[1] = k1n, k2n, c1, c2
+    lo = [k1n - 1 - c1, k2n - 1 - c2] if adjoint else [c1, c2]
+    hi = [c1, c2] if adjoint else [k1n - 1 - c1, k2n - 1 - c2]
+    for a in (0, 1):
+        if mode3[1 + a] == "constant":
+            lo[a] = hi[a] = 0
+    org = (lo[0], -(-lo[1] // vec) * vec)
+    n1e, n2e = n1 + lo[0] + hi[0], -(-(org[1] + n2 + hi[1]) // vec) * vec
+    pd = K.Pad2D()
+    pd.dtype, pd.nimg = dcode(x), nimg
+    pd.shape[0], pd.shape[1], pd.ext_shape[0], pd.ext_shape[1] = n1, n2, n1e, n2e
+    for a in (0, 1):
+        pd.org[a], pd.lo[a], pd.hi[a], pd.mode[a] = org[a], lo[a], hi[a], K.MODES[mode3[1 + a]]
+    cur = x
+    if axis0 is not None:
+        k3, c3 = axis0
+        if mode3[0] != "constant" and adjoint:
+            k3, c3 = np.ascontiguousarray(np.flip(k3)), np.array(k3.shape) - c3 - 1
+        coef = np.ascontiguousarray(k3.reshape(-1), dtype=x.dtype)
+        dd = op._desc(k3, c3, batch, dcode(x), coef.ctypes.data)
+        if mode3[0] == "constant":
+            dd.mode[0] = K.MODES["constant"]
+        tmp = np.empty_like(x)
+        lib().emu_stencil(C.byref(dd), int(adjoint and mode3[0] != "constant"), p(cur), p(tmp))
+        cur = tmp
+    ext = np.full(nimg * n1e * n2e, np.nan, dtype=x.dtype)
+    out = np.full_like(x, np.nan)
+    if not adjoint:
+        lib().emu_pad2d(C.byref(pd), p(cur), p(ext))
+        d.shape[0], d.shape[1], d.in_shape[0], d.in_shape[1] = n1, n2, n1e, n2e
+        d.origin[0], d.origin[1] = org
+        d.alpha, d.beta = alpha * scale, beta
+        if add is not None:
+            d.add, d.add_period = add.ctypes.data, add.size
+        rc = lib().emu_stencil2d(C.byref(d), p(ext), p(out))
+        return out if rc == 0 else None
+    d.shape[0], d.shape[1], d.in_shape[0], d.in_shape[1] = n1e, n2e, n1, n2
+    d.origin[0], d.origin[1] = -org[0], -org[1]
+    d.alpha, d.beta = scale, 0.0
+    rc = lib().emu_stencil2d(C.byref(d), p(cur), p(ext))
+    if rc != 0:
+        return None
+    lib().emu_pad2d_adjoint(C.byref(pd), p(ext), p(out), alpha, beta, p(add), add.size if add is not None else 0)
+    return out

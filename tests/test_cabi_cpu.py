@@ -35,11 +35,11 @@ def test_struct_layouts_match_the_c_compiler():
     #include <stddef.h>
     #include "pyxu_b200.h"
     int main(void){
-      printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pxb_slab), sizeof(pxb_stencil_desc), sizeof(pxb_grad_desc),
-             sizeof(pxb_prox_spec), sizeof(pxb_fterm), sizeof(pxb_pds_params), sizeof(pxb_stencil2d), sizeof(pxb_fista_step));
-      printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(pxb_stencil_desc, coef), offsetof(pxb_grad_desc, coef),
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pxb_slab), sizeof(pxb_stencil_desc), sizeof(pxb_grad_desc),
+             sizeof(pxb_prox_spec), sizeof(pxb_fterm), sizeof(pxb_pds_params), sizeof(pxb_stencil2d), sizeof(pxb_fista_step), sizeof(pxb_pad2d_desc));
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", offsetof(pxb_stencil_desc, coef), offsetof(pxb_grad_desc, coef),
              offsetof(pxb_grad_desc, slab), offsetof(pxb_pds_params, lam), offsetof(pxb_stencil2d, coef), offsetof(pxb_stencil2d, add_period),
-             offsetof(pxb_fista_step, norms));
+             offsetof(pxb_fista_step, norms), offsetof(pxb_stencil2d, origin), offsetof(pxb_pad2d_desc, mode));
       return 0; }
     """
     with tempfile.TemporaryDirectory() as td:
@@ -48,9 +48,9 @@ def test_struct_layouts_match_the_c_compiler():
         exe = os.path.join(td, "t")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
-    sizes = [C.sizeof(s) for s in (K.Slab, K.StencilDesc, K.GradDesc, K.ProxSpec, K.FTerm, K.PdsParams, K.Stencil2D, K.FistaStep)]
+    sizes = [C.sizeof(s) for s in (K.Slab, K.StencilDesc, K.GradDesc, K.ProxSpec, K.FTerm, K.PdsParams, K.Stencil2D, K.FistaStep, K.Pad2D)]
     offs = [K.StencilDesc.coef.offset, K.GradDesc.coef.offset, K.GradDesc.slab.offset, K.PdsParams.lam.offset, K.Stencil2D.coef.offset,
-            K.Stencil2D.add_period.offset, K.FistaStep.norms.offset]
+            K.Stencil2D.add_period.offset, K.FistaStep.norms.offset, K.Stencil2D.origin.offset, K.Pad2D.mode.offset]
     assert [int(v) for v in out] == sizes + offs
 
 

@@ -206,3 +206,65 @@ def test_single_pass_3d_slab_cuts():
             assert E.stencil3d_run(op, buf, adj, slab=slab, shape0=n0, raw_ptrs=(ptr(buf), ptr(out))) == 0
             got.append(out[H : H + n0])
         assert relerr(np.concatenate(got, axis=0), ref) < 1e-13, adj
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Folding boundary modes through the tiled kernel (Stencil._run_padded): Pad (pxb_pad2d) -> tiled S0 on the padded array /
+# tiled S0^T onto the padded extent -> Pad^T (pxb_pad2d_adjoint).  Against the gather kernels, the fixtures of the real
+# reference and the adjoint identity.
+# ---------------------------------------------------------------------------------------------------------
+PADDED_CASES = [
+    # (arg_shape, kernel, center, mode)
+    ((70, 300), [gauss(9, 1.7), gauss(9, 1.7)], (4, 4), "reflect"),                       # config[1]'s blur with a folding mode
+    ((70, 300), np.outer(gauss(9, 1.7), gauss(9, 1.7)) + 0.01 * np.arange(81.0).reshape(9, 9), (4, 4), "symmetric"),  # dense 9x9
+    ((40, 72), [gauss(5, 1.0), gauss(7, 1.3)], (0, 6), ("wrap", "symmetric")),           # one-sided pads
+    ((33, 64), np.arange(1.0, 16.0).reshape(3, 5) / 7, (2, 0), ("constant", "wrap")),     # a 'constant' axis next to a folding one
+    ((33, 64), np.arange(1.0, 16.0).reshape(3, 5) / 7, (1, 4), ("edge", "reflect")),
+    ((5, 9, 64), [gauss(3, 1.0), gauss(5, 1.0), gauss(9, 1.5)], (1, 2, 4), ("reflect", "symmetric", "wrap")),   # folding factor along axis 0
+    ((5, 9, 64), [gauss(3, 1.0), gauss(5, 1.0), gauss(9, 1.5)], (2, 0, 8), ("constant", "edge", "reflect")),
+    ((4, 37, 72), np.arange(1.0, 10.0).reshape(1, 3, 3), (0, 1, 1), ("constant", "wrap", "edge")),             # dense 2-D kernel on a stack of planes
+    ((128,), [gauss(9, 2.0)], (4,), "symmetric"),
+    ((4, 8), np.arange(1.0, 13.0).reshape(3, 4), (2, 3), "wrap"),                          # pads as wide as the mode allows on a tiny image
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("ci", range(len(PADDED_CASES)))
+def test_padded_tiled_equals_generic(ci, dtype):
+    shape, kern, cen, mode = PADDED_CASES[ci]
+    k = [np.asarray(_, dtype=dtype) for _ in kern] if isinstance(kern, list) else np.asarray(kern, dtype=dtype)
+    op = pxo.Stencil(arg_shape=shape, kernel=k, center=cen, mode=mode)
+    rng = np.random.default_rng(100 + ci)
+    x = rng.standard_normal((2, op.dim)).astype(dtype)
+    tol = 1e-13 if dtype == np.float64 else 3e-6
+    for adj in (False, True):
+        ref = E.stencil_run(op, x, adj)
+        out = E.stencil_run_padded(op, x, adj)
+        assert out is not None and np.isfinite(out).all() and relerr(out, ref) < tol, (ci, adj, relerr(out, ref))
+    y = rng.standard_normal((2, op.dim)).astype(dtype)
+    lhs, rhs = np.vdot(E.stencil_run_padded(op, x, False).astype(np.float64), y), np.vdot(x, E.stencil_run_padded(op, y, True).astype(np.float64))
+    assert abs(lhs - rhs) < (1e-11 if dtype == np.float64 else 2e-4) * (1 + abs(lhs))
+
+
+def test_padded_tiled_epilogue():
+    """alpha * S(x) + beta * add in both directions (the '- y' of a data term rides in the stencil pass / in the fold)."""
+    rng = np.random.default_rng(5)
+    op = pxo.Stencil(arg_shape=(50, 140), kernel=[gauss(9, 1.7), gauss(5, 1.0)], center=(4, 1), mode=("reflect", "wrap"))
+    x, y = rng.standard_normal((3, op.dim)), rng.standard_normal(op.dim)  # `add` broadcast over the stack
+    for adj in (False, True):
+        out = E.stencil_run_padded(op, x, adj, alpha=0.5, beta=-1.5, add=y)
+        assert relerr(out, 0.5 * E.stencil_run(op, x, adj) - 1.5 * y) < 1e-13
+
+
+@pytest.mark.parametrize("case", [c for c in cases.STENCIL_CASES if c["mode"] != "constant"], ids=lambda c: c["name"])
+def test_padded_tiled_golden(case):
+    """Fixtures produced by the real reference (tests/golden/make_golden.py); cases whose last axis is not a multiple of
+    the vector width stay on the gather kernels."""
+    g = golden("stencil.npz")
+    n = case["name"]
+    op = cases.make_stencil(type("ns", (), {"operator": pxo}), case)
+    got = [E.stencil_run_padded(op, g[f"{n}/x"], False), E.stencil_run_padded(op, g[f"{n}/y"], True)]
+    if case["arg_shape"][-1] % 2 or len(case["arg_shape"]) == 3 and not isinstance(case["kernel"], list):
+        assert got[0] is None and got[1] is None
+        return
+    assert relerr(got[0], g[f"{n}/apply"]) < 1e-13 and relerr(got[1], g[f"{n}/adjoint"]) < 1e-13
