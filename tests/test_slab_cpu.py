@@ -110,7 +110,7 @@ def _exchange(ranks, name, comp, up, down, periodic):
 
 
 @pytest.mark.parametrize("fast", [0, 1])
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("mode,subrange", [("constant", True), ("constant", False), ("wrap", True),
                                            (("reflect", "wrap", "symmetric"), False), (("edge", "constant", "reflect"), False)])
 def test_slab_decomposed_iteration_equals_single_domain(world, mode, subrange, fast):
@@ -259,7 +259,7 @@ def _exchange_iter(ranks, idx):
 
 
 @pytest.mark.parametrize("form", ["direct", "tma"])
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("scheme", ["forward"])
 def test_slab_single_kernel_iteration_equals_single_domain(world, form, scheme):
     shape, n_iter, lam = (13, 6, 8), 10, 0.08
