@@ -276,7 +276,8 @@ PXB_NOINLINE void pxb_tv_w_global(const PxbTvP<T>& q, const T* __restrict__ xu, 
             pxb_tv_taps_row<T, W>(zk, c, q.cm[k], q.c0[k], q.cp[k], i2 > 0, i2 + W < q.n2, t);
         } else {
             const int i = ax == 0 ? i0 : i1, n = ax == 0 ? q.n0 : q.n1;
-            pxb_tv_taps_col<T, W>(zk, ax == 0 ? q.s0 : q.s1, c, q.cm[k], q.c0[k], q.cp[k], i > 0, i < n - 1, t);
+            const bool has_lo = i > 0 || (ax == 0 && q.open_lo), has_hi = i < n - 1 || (ax == 0 && q.open_hi);  // slab cuts read their ghost planes
+            pxb_tv_taps_col<T, W>(zk, ax == 0 ? q.s0 : q.s1, c, q.cm[k], q.c0[k], q.cp[k], has_lo, has_hi, t);
         }
         for (int j = 0; j < W; ++j) kz[j] += t[j];
     }
@@ -314,7 +315,9 @@ PXB_NOINLINE void pxb_tv_w_global(const PxbTvP<T>& q, const T* __restrict__ xu, 
 template <class T, int W, int NDIR, int ALGO>
 PXB_HD void pxb_tv_w_outside(const PxbTvP<T>& q, const T* __restrict__ xu, const T* __restrict__ z, int64_t b, int i0, int i1, int i2, T* wv) {
     for (int j = 0; j < W; ++j) wv[j] = T(0);
-    const bool o0 = NDIR == 3 && (i0 < 0 || i0 >= q.n0), o1 = i1 < 0 || i1 >= q.n1, o2 = i2 < 0 || i2 >= q.n2;
+    // (the ghost planes of an open slab side are not outside: callers only come here for them at in-plane cells nobody reads)
+    const bool o0 = NDIR == 3 && ((i0 < 0 && !q.open_lo) || (i0 >= q.n0 && !q.open_hi)), o1 = i1 < 0 || i1 >= q.n1, o2 = i2 < 0 || i2 >= q.n2;
+    if (NDIR == 3 && !o0 && (i0 < 0 || i0 >= q.n0)) return;
     if ((o0 ? 1 : 0) + (o1 ? 1 : 0) + (o2 ? 1 : 0) != 1) return;
     if (NDIR == 2 && (i0 < 0 || i0 >= q.n0)) return;
     if (o2) {

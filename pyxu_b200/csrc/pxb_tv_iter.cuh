@@ -240,8 +240,8 @@ PXB_HD void pxb_iter_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
         const int r = it.r0 + rl, c = it.c0 + cl;
         PxbVec<T, VEC> wv;
         if (plane_in && r < g.nR && c < g.nC) pxb_iter_w<T, VEC, NDIR, ALGO, NORMS, MODES>(q, g, it, a, m, r, c, own, wv.v, st.zc, st.acc);
-        else if (MODES) pxb_tv_w_outside<T, VEC, NDIR, ALGO>(q, a.u_in, a.z_in, it.b, PXB_I0(m, r), PXB_I1(m, r), c, wv.v);
-        else for (int j = 0; j < VEC; ++j) wv.v[j] = T(0);
+        else if (MODES && (own || !plane_in)) pxb_tv_w_outside<T, VEC, NDIR, ALGO>(q, a.u_in, a.z_in, it.b, PXB_I0(m, r), PXB_I1(m, r), c, wv.v);
+        else for (int j = 0; j < VEC; ++j) wv.v[j] = T(0);  // (on the planes of neighbouring chunks / slabs only the tile's own cells are read)
         pxb_vstore<T, VEC>(slot + (rl + C::R0) * C::RS + cl + VEC, wv);
     }
     if (!own) return;  // planes of the neighbouring chunks are only needed at the tile's own positions
@@ -370,14 +370,16 @@ PXB_HD PxbIterRange pxb_iter_range(const PxbTvP<T>& q, const PxbIterItem& it) {
 // host side: eligibility + geometry (shared by the launcher and by tests/emu)
 // ---------------------------------------------------------------------------------------------------------
 // returns 0 when the single-kernel iteration applies, else a reason code (> 0)
-// `allow_modes`: folding boundary modes are served by the MODES instances (single-domain arrays only: on a slab the
-// closed faces of the end ranks would need the far rank's planes for 'wrap', and the two-sweep form handles that)
+// `allow_modes`: folding boundary modes are served by the MODES instances.  On a slab an open side is not a boundary; a
+// closed one folds onto the slab's own planes, which 'wrap' along axis 0 cannot do unless the slab is the whole volume
+// (the caller opens every side for a ring exchange instead).
 inline int pxb_iter_setup(const pxb_grad_desc& d, const pxb_pds_params& P, int vec, int ty, int t2, int chunk_hint, int resident, PxbTvCoef& cf,
                           PxbIterGeom& g, bool allow_modes = false) {
     if (!pxb_tv_fast_coefs(d, cf)) return 1;
     if (d.ndir != 2 && d.ndir != 3) return 2;
     if (P.hkind != PXB_DUAL_L21 && P.hkind != PXB_DUAL_L1) return 3;
-    if (pxb_any_mode(d) && (!allow_modes || d.slab.halo != 0 || d.slab.open_lo || d.slab.open_hi || d.slab.plane_alloc > 0)) return 4;
+    if (pxb_any_mode(d) && !allow_modes) return 4;
+    if (d.ndir == 3 && d.mode[0] == PXB_WRAP && d.slab.open_lo != d.slab.open_hi) return 4;
     if (d.shape[2] % vec) return 5;
     if (d.shape[0] < 1 || d.shape[1] < 1 || d.shape[2] < 1 || d.batch < 1) return 9;
     const PxbGeom gg = pxb_geom(d.shape);

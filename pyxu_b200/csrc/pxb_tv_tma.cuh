@@ -234,8 +234,10 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         pxb_tma_w<T, VEC, TY, VEC, ALGO, S, MODES>(q, tg, st, st_next, rl + 1, cl + VEC, th.z0p, wv, z0c, th.zc[1], th.zc[2], xo, un, uo,
                                                    in ? zimg : nullptr, m, r, c);
         for (int j = 0; j < VEC; ++j) { th.zc[0][j] = z0c[j]; th.z0p[j] = z0c[j]; }
-        if (MODES && !in) pxb_tv_w_outside<T, VEC, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);
-        const bool keep = MODES || in;
+        // (on the planes of neighbouring chunks / slabs only the tile's own, in-plane-inside cells are read)
+        const bool fold = MODES && !in && (own || !plane_in);
+        if (fold) pxb_tv_w_outside<T, VEC, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);
+        const bool keep = fold || in;
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = keep ? wv[j] : T(0);
         pxb_vstore<T, VEC>(slot + (rl + 1) * R::RS + cl + VEC, o);

@@ -26,6 +26,7 @@ half-step is issued as [interior planes] on the main stream and [boundary plane]
 """
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -150,8 +151,11 @@ class SlabPD3OTV:
         def field(ncomp=1):
             return torch.zeros((ncomp, alloc, n1, n2), dtype=dtype, device=self.dev)
 
-        # single-kernel iteration: 'constant' boundaries (the kernel's envelope); ping-pong (u, z) pairs, no w array
-        self.fused = bool(fused) and all(m == "constant" for m in modes)
+        # single-kernel iteration; ping-pong (u, z) pairs, no w array.  'constant' boundaries by default; with folding modes
+        # (in-plane folds on every rank, folds along z on the closed sides of the end ranks, 'wrap' along z as a ring of open
+        # sides) the kernels are checked rank by rank on the CPU emulation (tests/test_slab_cpu.py) but have not run on
+        # several GPUs yet: PYXU_B200_SLAB_FUSED_MODES=1 switches them on, otherwise those problems take the two-sweep form.
+        self.fused = bool(fused) and (all(m == "constant" for m in modes) or os.environ.get("PYXU_B200_SLAB_FUSED_MODES", "0") == "1")
         self.edge = max(1, min(int(edge), self.n0 // 2))  # planes of the boundary launches that precede the exchange
         if y_local is None:
             y_local = y_full.reshape(self.shape)[self.start : self.stop]

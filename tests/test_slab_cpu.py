@@ -213,11 +213,11 @@ class _RankIter:
 
     H = 1
 
-    def __init__(self, shape, y, a, b, rank, world, scheme):
+    def __init__(self, shape, y, a, b, rank, world, scheme, mode="constant", periodic=False):
         self.n0, self.plane = b - a, shape[1] * shape[2]
-        self.has_lo, self.has_hi = rank > 0, rank < world - 1
+        self.has_lo, self.has_hi = rank > 0 or periodic, rank < world - 1 or periodic
         alloc = self.n0 + 2 * self.H
-        self.K = pxo.Gradient(arg_shape=shape, scheme=scheme)
+        self.K = pxo.Gradient(arg_shape=shape, scheme=scheme, mode=mode)
         f = lambda c=1: np.zeros((c, alloc) + shape[1:])
         self.ub, self.zb, self.x, self.sh = [f(), f()], [f(3), f(3)], f(), f()
         self.cur = 0
@@ -246,28 +246,40 @@ class _RankIter:
         assert rc == 0, rc
 
 
-def _exchange_iter(ranks, idx):
-    """u, z_0..2 first owned plane -> lower neighbour's upper ghost; z_0 last owned plane -> upper neighbour's lower ghost"""
+def _exchange_iter(ranks, idx, periodic=False):
+    """u, z_0..2 first owned plane -> lower neighbour's upper ghost; z_0 last owned plane -> upper neighbour's lower ghost
+    (periodic: a ring, as HaloExchanger(periodic=True) for 'wrap' along z)"""
+    W = len(ranks)
     for r, rk in enumerate(ranks):
-        if r > 0:
-            lo = ranks[r - 1]
+        if r > 0 or (periodic and W > 1):
+            lo = ranks[(r - 1) % W]
             lo.ub[idx][0][-1] = rk.ub[idx][0][1]
             for c in range(3):
                 lo.zb[idx][c][-1] = rk.zb[idx][c][1]
-        if r + 1 < len(ranks):
-            ranks[r + 1].zb[idx][0][0] = rk.zb[idx][0][rk.n0]
+        if r + 1 < W or (periodic and W > 1):
+            ranks[(r + 1) % W].zb[idx][0][0] = rk.zb[idx][0][rk.n0]
 
 
+# 'constant' (the form SlabPD3OTV runs by default) and folding modes: in-plane folds on every rank, folds along z on the
+# closed sides of the end ranks, 'wrap' along z as a ring of open sides
+SLAB_ITER_MODES = ["constant", ("constant", "reflect", "wrap"), ("reflect", "symmetric", "edge"), ("edge", "wrap", "reflect"),
+                   ("wrap", "reflect", "symmetric")]
+
+
+@pytest.mark.parametrize("mode", SLAB_ITER_MODES, ids=lambda m: m if isinstance(m, str) else "-".join(m))
 @pytest.mark.parametrize("form", ["direct", "tma"])
 @pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("scheme", ["forward"])
-def test_slab_single_kernel_iteration_equals_single_domain(world, form, scheme):
-    shape, n_iter, lam = (13, 6, 8), 10, 0.08
+@pytest.mark.parametrize("shape", [(13, 6, 8), (9, 16, 64)], ids=["ragged", "fulltiles"])  # full tiles: folded rims served from the tile's boxes
+def test_slab_single_kernel_iteration_equals_single_domain(world, form, scheme, mode, shape):
+    n_iter, lam = (10 if shape[2] == 8 else 4), 0.08
     tau = sigma = 0.28
     rho = 1.3
     y = np.random.default_rng(1).random(shape)
+    periodic = (mode if isinstance(mode, str) else mode[0]) == "wrap" and world > 1
+    zfold = (mode if isinstance(mode, str) else mode[0]) not in ("constant", "wrap")
     # single-domain reference: two-sweep generic bodies
-    Kop = pxo.Gradient(arg_shape=shape, scheme=scheme)
+    Kop = pxo.Gradient(arg_shape=shape, scheme=scheme, mode=mode)
     shift = np.ascontiguousarray(-y.reshape(-1))
     P = E.pds_params(tau, sigma, rho, gspec=(K.PROX_POS, 0, 0), fkind=K.F_SQL2, alpha=0.5, shift=shift, hkind=K.DUAL_L21, lam=lam)
     d = Kop._desc(1, K.F64)
@@ -279,23 +291,30 @@ def test_slab_single_kernel_iteration_equals_single_domain(world, form, scheme):
         E.lib().emu_pds_dual(C.byref(d), C.byref(P), E.p(w), E.p(z_ref), None)
 
     parts = partition(shape[0], world)
-    ranks = [_RankIter(shape, y, a, b, r, world, scheme) for r, (a, b) in enumerate(parts)]
+    ranks = [_RankIter(shape, y, a, b, r, world, scheme, mode, periodic) for r, (a, b) in enumerate(parts)]
     prm = (tau, sigma, rho, lam)
     for r, rk in enumerate(ranks):  # ghost planes of x0 and of the shift; z0 = K x0
-        if r > 0:
-            ranks[r - 1].x[0][-1] = rk.x[0][1]
-            ranks[r - 1].sh[0][-1] = rk.sh[0][1]
-        if r + 1 < world:
-            ranks[r + 1].x[0][0] = rk.x[0][rk.n0]
-            ranks[r + 1].sh[0][0] = rk.sh[0][rk.n0]
+        if r > 0 or periodic:
+            ranks[(r - 1) % world].x[0][-1] = rk.x[0][1]
+            ranks[(r - 1) % world].sh[0][-1] = rk.sh[0][1]
+        if r + 1 < world or periodic:
+            ranks[(r + 1) % world].x[0][0] = rk.x[0][rk.n0]
+            ranks[(r + 1) % world].sh[0][0] = rk.sh[0][rk.n0]
     for rk in ranks:
         dd = rk.desc(0, rk.n0)
         E.lib().emu_gradient(C.byref(dd), 0, rk.ptr(rk.x, 0, 0), rk.ptr(rk.zb[0], 0, 0))
-    _exchange_iter(ranks, 0)
+        # the vectorised Gradient body (what pxb_gradient_apply launches for this descriptor) agrees on the slab: open sides
+        # read their ghost planes, closed ones fold onto the slab's own planes
+        zv = np.zeros_like(rk.zb[0])
+        assert E.lib().emu_tv_grad(2, 0, C.byref(dd), rk.ptr(rk.x, 0, 0), rk.ptr(zv, 0, 0)) == 0
+        assert np.allclose(zv[:, 1:-1], rk.zb[0][:, 1:-1], rtol=1e-14, atol=1e-15)
+    _exchange_iter(ranks, 0, periodic)
     for it in range(n_iter):
         for rk in ranks:  # boundary chunks first, then the interior (same order as SlabPD3OTV._step_fused)
             e = 2
             lo, hi = (e if rk.has_lo else 0), (rk.n0 - e if rk.has_hi else rk.n0)
+            if zfold:  # a fold along z must not meet a sub-range cut: whole-slab launches (SlabPD3OTV.overlap is off)
+                lo, hi = 0, rk.n0
             if lo:
                 rk.iterate(0, lo, prm, form, 3)
             if hi < rk.n0:
@@ -304,7 +323,7 @@ def test_slab_single_kernel_iteration_equals_single_domain(world, form, scheme):
                 rk.iterate(lo, hi, prm, form, 2)
         for rk in ranks:
             rk.cur = 1 - rk.cur
-        _exchange_iter(ranks, ranks[0].cur)
+        _exchange_iter(ranks, ranks[0].cur, periodic)
     x = np.concatenate([rk.x[0, 1:-1] for rk in ranks], axis=0).reshape(-1)
     z = np.concatenate([rk.zb[rk.cur][:, 1:-1] for rk in ranks], axis=1).reshape(-1)
     assert np.allclose(x, x_ref, rtol=1e-13, atol=1e-15) and np.allclose(z, z_ref, rtol=1e-13, atol=1e-15)
