@@ -43,3 +43,22 @@ for name, shape, batch, kern, cen in [
         op._tiled_ok = force
         ms = timeit(lambda: op.apply(x))
         print(f"{name:28s} {label:8s} {ms:8.3f} ms   {nbytes / ms / 1e6:7.0f} GB/s (8 B/voxel)", flush=True)
+
+# Folding boundary modes: Pad -> tiled stencil / tiled stencil -> Pad^T (Stencil._run_padded, PYXU_B200_STENCIL_PADDED=1)
+# against the gather kernels.
+from pyxu_b200.operator.linop import stencil as _st
+
+if _st.PADDED_TILED:
+    for name, shape, kern, cen in [
+        ("8192^2 separable 9x9", (8192, 8192), [gauss(9, 1.7), gauss(9, 1.7)], (4, 4)),
+        ("8192^2 dense 5x5", (8192, 8192), np.outer(gauss(5, 1.0), gauss(5, 1.0)) + np.float32(0.01) * np.arange(25, dtype=np.float32).reshape(5, 5), (2, 2)),
+    ]:
+        x = torch.randn(1, int(np.prod(shape)), device="cuda", dtype=torch.float32)
+        nbytes = 8 * x.numel()
+        for mode in ("reflect", "wrap"):
+            for label, force in (("padded", None), ("gather", False)):
+                op = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode=mode)
+                op._padded_ok = force
+                for adj in (False, True):
+                    ms = timeit(lambda: op.adjoint(x) if adj else op.apply(x))
+                    print(f"{name:22s} {mode:8s} {'adjoint' if adj else 'apply':8s} {label:8s} {ms:8.3f} ms   {nbytes / ms / 1e6:7.0f} GB/s (8 B/voxel)", flush=True)
