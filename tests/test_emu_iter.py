@@ -409,3 +409,29 @@ def test_iter_modes_folded_rim_is_served_from_the_tile():
         assert counts[mode, "tma"] == plane  # forward differences: the plane past the last one, once per tile
     assert counts["wrap", "tile2d"] == shape2[0] + shape2[1]          # one rim column cell per row + one rim row
     assert counts["wrap", "tma"] == plane + shape3[0] * (shape3[1] + shape3[2])
+
+
+@pytest.mark.parametrize("form", ["direct", "tma"])
+def test_iter_modes_3d_batched_and_degenerate_axes(form):
+    """Folding modes with a batch of volumes (per-item and broadcast shifts), and axes of length 1 / 2 where both faces of
+    an axis fold onto the same or neighbouring samples."""
+    rng = np.random.default_rng(41)
+    for shape, mode, batch in (((5, 11, 24), ("reflect", "wrap", "symmetric"), 2), ((1, 9, 8), ("symmetric", "edge", "wrap"), 3),
+                               ((2, 2, 8), ("wrap", "symmetric", "edge"), 2), ((4, 1, 4), ("edge", "wrap", "reflect"), 1)):
+        for scheme in SCHEMES:
+            if scheme == "central" and min(shape) == 1:
+                continue  # a 3-tap kernel pads by 2 > the axis length: refused at construction, as in the reference (pad.py:217-229)
+            Kop = pxo.Gradient(arg_shape=shape, scheme=scheme, mode=mode)
+            d = Kop._desc(batch, K.F64)
+            u, x = rng.standard_normal((batch, Kop.dim)), rng.standard_normal((batch, Kop.dim))
+            z = rng.standard_normal((batch, Kop.codim))
+            for shift in (rng.standard_normal(Kop.dim), rng.standard_normal((batch, Kop.dim))):
+                P = E.pds_params(0.21, 0.19, 0.9, gspec=(K.PROX_POS, 0.0, 0.0), fkind=K.F_SQL2, alpha=0.7, shift=shift, hkind=K.DUAL_L21, lam=0.3)
+                for algo in (K.ALGO_PD3O, K.ALGO_CV):
+                    ua, za, xa = u.copy(), z.copy(), x.copy()
+                    nxa, nza, nxb, nzb = (np.zeros(2 * batch) for _ in range(4))
+                    two_pass(algo, d, P, ua, za, xa, nxa, nza)
+                    xb = x.copy()
+                    ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=2, form=form)
+                    assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13, (shape, mode, scheme, algo, shift.shape)
+                    assert np.allclose(nxa, nxb, rtol=1e-10) and np.allclose(nza, nzb, rtol=1e-10)
