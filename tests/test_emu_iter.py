@@ -435,3 +435,22 @@ def test_iter_modes_3d_batched_and_degenerate_axes(form):
                     ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=2, form=form)
                     assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13, (shape, mode, scheme, algo, shift.shape)
                     assert np.allclose(nxa, nxb, rtol=1e-10) and np.allclose(nza, nzb, rtol=1e-10)
+
+
+def test_iter_modes_periodic_shift_direct_form():
+    """A shift that repeats with a period of its own (one image of a stack: PXB_SHIFT_MOD) is declined by the staged forms and
+    served by the direct-load one, folding modes included (the out-of-line evaluator addresses the shift the same way)."""
+    rng = np.random.default_rng(43)
+    Kop = pxo.Gradient(arg_shape=(3, 11, 24), directions=(1, 2), mode=("constant", "symmetric", "wrap"))
+    d = Kop._desc(2, K.F64)
+    shift = rng.standard_normal(11 * 24)  # one image, broadcast over the 3 images of each of the 2 batch items
+    P = E.pds_params(0.3, 0.25, 0.8, gspec=(K.PROX_POS, 0.0, 0.0), fkind=K.F_SQL2, alpha=0.4, shift=shift, hkind=K.DUAL_L21, lam=0.2)
+    u, x, z = rng.standard_normal((2, Kop.dim)), rng.standard_normal((2, Kop.dim)), rng.standard_normal((2, Kop.codim))
+    a, zz = np.zeros_like(u), np.zeros_like(z)
+    assert E.lib().emu_tv_tile2d(K.ALGO_PD3O, C.byref(d), C.byref(P), E.p(u), E.p(z), E.p(a), E.p(zz), E.p(x.copy()), None, None, 0) == -121
+    for algo in (K.ALGO_PD3O, K.ALGO_CV):
+        ua, za, xa = u.copy(), z.copy(), x.copy()
+        two_pass(algo, d, P, ua, za, xa)
+        xb = x.copy()
+        ub, zb = one_pass(algo, d, P, u, z, xb, form="direct")
+        assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13
