@@ -62,5 +62,30 @@ slv = pxs.CondatVu(f=(0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y1)) * A, g=None,
 slv.fit(x0=y1, stop_crit=pxst.MaxIter(3))
 G = pxo.Gradient(arg_shape=(9, 21, 136), dtype=np.float32, mode=("reflect", "constant", "wrap"))
 G.adjoint(G.apply(x3[0, : G.dim].contiguous()))
+# folding boundary modes: MODES instances of the three single-kernel forms (full and ragged tiles, wrap = the global rim
+# evaluator), the two-sweep kernels, and the Pad -> tiled stencil -> Pad^T path when it is switched on
+for path in (2, 1):
+    lib.pxb_set_iter_path(path)
+    for shape, mode in (((19, 21, 136), ("reflect", "symmetric", "wrap")), ((16, 16, 256), "wrap"), ((37, 136), ("edge", "reflect")), ((32, 256), "wrap")):
+        N, D = int(np.prod(shape)), len(shape)
+        y = torch.rand(N, device="cuda")
+        slv = pxs.PD3O(f=0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y), g=pxo.PositiveOrthant(dim=N), h=0.08 * pxo.L21Norm(arg_shape=(D, *shape), l2_axis=(0,)),
+                       K=pxo.Gradient(arg_shape=shape, dtype=np.float32, mode=mode), show_progress=False, final_writeback=False)
+        slv.fit(x0=y, stop_crit=pxst.MaxIter(3) | pxst.RelError(eps=1e-30, var="x") | pxst.RelError(eps=1e-30, var="z"))
+        assert slv._plan.iter_ok is True
+        slv.solution()
+lib.pxb_set_iter_path(0)
+lib.pxb_set_iter_modes(0)
+slv = pxs.PD3O(f=0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y), g=None, h=0.08 * pxo.L21Norm(arg_shape=(D, *shape), l2_axis=(0,)),
+               K=pxo.Gradient(arg_shape=shape, dtype=np.float32, mode="reflect"), show_progress=False, final_writeback=False)
+slv.fit(x0=y, stop_crit=pxst.MaxIter(3))
+assert slv._plan.iter_ok is False  # two sweeps
+lib.pxb_set_iter_modes(-1)
+from pyxu_b200.operator.linop import stencil as _st
+
+for kern, cen in (([gauss(9, 1.7), gauss(9, 1.7)], (4, 4)), (np.outer(gauss(5, 1.0), gauss(5, 1.0)) + 0.02 * np.eye(5, dtype=np.float32), (1, 3))):
+    op = pxo.Stencil(arg_shape=(70, 520), kernel=kern, center=cen, mode=("reflect", "wrap"))
+    op.apply(x2), op.adjoint(x2)
+    assert op._padded_ok is (True if _st.PADDED_TILED else None)
 torch.cuda.synchronize()
 print("sanitize_kernels: all launches completed")
