@@ -3,6 +3,8 @@ CPU checks of the TMA-tiled 2-D stencil (pyxu_b200/csrc/pxb_stencil_tma.cuh): th
 box load emulated as a zero-filled gather, against (a) the generic per-sample bodies, (b) fixtures from the real
 reference for the 'constant'-mode cases, (c) the adjoint identity <Sx, y> == <x, S^T y>.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -268,3 +270,43 @@ def test_padded_tiled_golden(case):
         assert got[0] is None and got[1] is None
         return
     assert relerr(got[0], g[f"{n}/apply"]) < 1e-13 and relerr(got[1], g[f"{n}/adjoint"]) < 1e-13
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_pad2d_is_numpy_pad_and_its_transpose(dtype):
+    """pxb_pad2d reproduces numpy.pad (what the reference's Pad calls, pad.py:252-302) bit for bit for every mode and pad width the
+    reference admits (pad.py:217-229), filler columns included; pxb_pad2d_adjoint is its exact transpose."""
+    rng = np.random.default_rng(17)
+    names = ["constant", "wrap", "reflect", "symmetric", "edge"]
+    for trial in range(40):
+        n1, n2, nimg = int(rng.integers(1, 9)), int(rng.integers(1, 12)), int(rng.integers(1, 4))
+        modes = [str(rng.choice(names)) for _ in range(2)]
+        lo, hi = [0, 0], [0, 0]
+        for a, n in enumerate((n1, n2)):
+            lim = {"constant": 5, "edge": 5, "wrap": n, "symmetric": n, "reflect": n - 1}[modes[a]]
+            lo[a], hi[a] = int(rng.integers(0, lim + 1)), int(rng.integers(0, lim + 1))
+        org = [lo[0] + int(rng.integers(0, 2)), lo[1] + int(rng.integers(0, 4))]
+        ext = [org[0] + n1 + hi[0] + int(rng.integers(0, 2)), org[1] + n2 + hi[1] + int(rng.integers(0, 4))]
+        d = E.K.Pad2D()
+        d.dtype, d.nimg = E.dcode(np.zeros(1, dtype=dtype)), nimg
+        d.shape[0], d.shape[1], d.ext_shape[0], d.ext_shape[1] = n1, n2, ext[0], ext[1]
+        for a in (0, 1):
+            d.org[a], d.lo[a], d.hi[a], d.mode[a] = org[a], lo[a], hi[a], E.K.MODES[modes[a]]
+        x = rng.standard_normal((nimg, n1, n2)).astype(dtype)
+        got = np.full((nimg, ext[0], ext[1]), np.nan, dtype=dtype)
+        E.lib().emu_pad2d(C.byref(d), E.p(x), E.p(got))
+        want = np.zeros_like(got)
+        ref = x
+        for a in (0, 1):  # numpy.pad axis by axis, as Pad.apply does for mixed modes (pad.py:270-302)
+            pw = [(0, 0)] * 3
+            pw[1 + a] = (lo[a], hi[a])
+            ref = np.pad(ref, pw, mode=modes[a])
+        want[:, org[0] - lo[0] : org[0] + n1 + hi[0], org[1] - lo[1] : org[1] + n2 + hi[1]] = ref
+        assert np.array_equal(got, want), (trial, modes, lo, hi)
+        y = rng.standard_normal(got.shape).astype(dtype)
+        back = np.full_like(x, np.nan)
+        E.lib().emu_pad2d_adjoint(C.byref(d), E.p(y), E.p(back), 1.0, 0.0, None, 0)
+        yin = np.zeros_like(y)  # only the padded extent takes part
+        yin[:, org[0] - lo[0] : org[0] + n1 + hi[0], org[1] - lo[1] : org[1] + n2 + hi[1]] = y[:, org[0] - lo[0] : org[0] + n1 + hi[0], org[1] - lo[1] : org[1] + n2 + hi[1]]
+        lhs, rhs = np.vdot(got.astype(np.float64), yin), np.vdot(x.astype(np.float64), back)
+        assert abs(lhs - rhs) < (1e-12 if dtype == np.float64 else 1e-4) * (1 + abs(lhs)), (trial, modes, lo, hi)

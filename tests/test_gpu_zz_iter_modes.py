@@ -69,6 +69,29 @@ def test_modes_vs_two_sweeps_2d_batched(env, mode, form, modes_on):
             assert_same(env, K.ALGO_CV, a, b, tol)
 
 
+@pytest.mark.parametrize("mode", MODES + [("wrap", "reflect", "symmetric")])
+def test_modes_full_tiles_3d_and_2d(env, mode, modes_on):
+    """Full tiles: the folded rim rows / columns of the edge tiles are served from the tile's own staged boxes (pxb_rim_src), and
+    a larger volume (256 x 64 x 256) so that many CTAs, chunks and bands take part."""
+    K = env.K
+    modes_on(2)
+    for dtype, shape in ((torch.float32, (16, 32, 256)), (torch.float64, (9, 16, 128)), (torch.float32, (256, 64, 256))):
+        Kop = env.operator.Gradient(arg_shape=shape, mode=mode, dtype=np.float32 if dtype == torch.float32 else np.float64)
+        shift = torch.randn(Kop.dim, device="cuda", dtype=dtype)
+        P = params(K, 0.21, 0.19, 0.9, (K.PROX_POS, 0.0, 0.0), K.F_SQL2, 0.7, shift, None, K.DUAL_L21, 0.3)
+        for algo in (K.ALGO_PD3O, K.ALGO_CV):
+            a, b = both_forms(env, algo, Kop, 1, dtype, P, seed=5)
+            assert_same(env, algo, a, b, 1e-13 if dtype == torch.float64 else 2e-6)
+    mode2 = mode if isinstance(mode, str) else mode[1:]
+    for dtype, shape, batch in ((torch.float32, (64, 512), 2), (torch.float64, (32, 128), 1)):
+        Kop = env.operator.Gradient(arg_shape=shape, mode=mode2, dtype=np.float32 if dtype == torch.float32 else np.float64)
+        shift = torch.randn(batch, Kop.dim, device="cuda", dtype=dtype)
+        P = params(K, 0.3, 0.25, 0.95, (K.PROX_L1, 0.05, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L21, 0.2)
+        for algo in (K.ALGO_PD3O, K.ALGO_CV):
+            a, b = both_forms(env, algo, Kop, batch, dtype, P, seed=6)
+            assert_same(env, algo, a, b, 1e-13 if dtype == torch.float64 else 2e-6)
+
+
 def test_modes_solver_fit_against_reference_fixtures(env, modes_on):
     """Solver.fit() with folding modes runs the single-kernel form and reproduces the real reference (<= 1e-10)."""
     import types
