@@ -251,7 +251,8 @@ class Solver:
 
             stop_crit |= Memorize(var="objective_func")
         self._astate.update(history=[], idx=0, logger=_init_logger(), stop_crit=stop_crit, track_objective=track_objective,
-                            mode=mode, active=None, worker=None)
+                            mode=mode, active=None, worker=None, pending_log=[], history_dtype=None,
+                            live_log=(mode is Mode.BLOCK) and self._astate["stdout"])  # a stream handler shows every record as it comes
 
     def _fit_run(self):
         mode = self._astate["mode"]
@@ -291,17 +292,28 @@ class Solver:
 
         def _log(msg=None):
             if msg is None:
-                h = ast["history"][-1][0]
-                msg = [f"[{dt.datetime.now()}] Iteration {ast['idx']:>_d}"]
-                for field, value in zip(h.dtype.names, h):
-                    msg.append(f"\t{field}: {value}")
-                msg = "\n".join(msg)
+                if not ast.get("live_log"):
+                    # The per-iteration record goes to the log FILE only: keep (time, record) and render the same text in
+                    # batches (Python's logging costs ~100 us per record -- more than an iteration of a small problem takes
+                    # on the GPU).  Nothing is lost: the batch is written before any other message, at the latest every
+                    # second / 256 records, on stop, on error and on cleanup.
+                    pend = ast.setdefault("pending_log", [])
+                    pend.append((dt.datetime.now(), ast["idx"], ast["history"][-1][0]))
+                    if len(pend) >= 256 or (pend[-1][0] - pend[0][0]).total_seconds() > 1.0:
+                        self._flush_log()
+                    return
+                msg = self._render_iteration(dt.datetime.now(), ast["idx"], ast["history"][-1][0])
+            else:
+                self._flush_log()
             ast["logger"].info(msg)
 
         def _update_history():
             data = ast["stop_crit"].info()
-            dtype = np.dtype([("iteration", np.int64)] + [(k, np.float64) for k in data])
-            rec = np.zeros(1, dtype=dtype)
+            keys = tuple(data)
+            cache = ast.get("history_dtype")
+            if cache is None or cache[0] != keys:  # the fields never change during a fit(): build the record type once
+                cache = ast["history_dtype"] = (keys, np.dtype([("iteration", np.int64)] + [(k, np.float64) for k in keys]))
+            rec = np.zeros(1, dtype=cache[1])
             rec["iteration"] = ast["idx"]
             for k, v in data.items():
                 rec[k] = v
@@ -332,11 +344,39 @@ class Solver:
             if ast["wb_rate"] is not None:
                 _, r = divmod(ast["idx"], ast["wb_rate"])
                 msg = "\n".join([msg, f"Last valid checkpoint done at iteration={ast['idx'] - r}."])
+            self._flush_log()
             ast["logger"].exception(msg, exc_info=e)
             ast["error"] = e
             return False
 
+    @staticmethod
+    def _render_iteration(when, idx, h):
+        msg = [f"[{when}] Iteration {idx:>_d}"]
+        for field, value in zip(h.dtype.names, h):
+            msg.append(f"\t{field}: {value}")
+        return "\n".join(msg)
+
+    def _flush_log(self):
+        """Writes the iteration records kept back by _step() to the log file, in the format the logger gives them."""
+        pend = self._astate.get("pending_log")
+        if not pend:
+            return
+        logger = self._astate.get("logger")
+        text = "".join(f"INFO -- {self._render_iteration(*rec)}\n" for rec in pend)
+        pend.clear()
+        for h in (logger.handlers if logger is not None else ()):
+            if isinstance(h, logging.FileHandler):
+                h.acquire()
+                try:
+                    if h.stream is None:
+                        h.stream = h._open()
+                    h.stream.write(text)
+                    h.flush()
+                finally:
+                    h.release()
+
     def _cleanup_logger(self):
+        self._flush_log()
         logger = logging.getLogger(str(self.workdir))
         for handler in logger.handlers:
             handler.close()

@@ -104,6 +104,19 @@ class _Plan:
         return self._w
 
     def params(self, mst, garr=None):
+        # the block only changes when a step size does (or, for CondatVu with a non-local f, the grad f array moves): built once
+        key = (mst["tau"], mst["sigma"], mst["rho"])
+        hit = getattr(self, "_params_cache", None)
+        if hit is not None and hit[0] == key:
+            p = hit[1]
+            if garr is not None:
+                p.f.garr = garr.data_ptr()
+            return p
+        p = self._build_params(mst, garr)
+        self._params_cache = (key, p)
+        return p
+
+    def _build_params(self, mst, garr=None):
         p = K.PdsParams()
         p.tau, p.sigma, p.rho = float(mst["tau"]), float(mst["sigma"]), float(mst["rho"])
         p.g = K.ProxSpec(int(self.gspec[0]), 0, float(self.gspec[1]), float(self.gspec[2]))
