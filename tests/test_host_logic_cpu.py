@@ -134,3 +134,48 @@ def test_bench_clock_sampler_windows_on_the_timed_region():
     assert s["samples_in_timed_region"] == 0 and s["samples"] == 1 and s["sm_mhz"] == 1700.0
     clk.rows = []
     assert clk.summary(0.0, 1.0)["samples"] == 0
+
+
+def test_solver_loop_log_file_and_history_without_a_device():
+    """The Solver loop itself (reference: abc/solver.py:571-718) on a toy iteration that needs no device: one history record and
+    one log entry per iteration -- the entries are rendered in batches but the file reads as if each had been logged on its
+    own --, the end-of-run message last, pending entries written before an exception is logged."""
+    from pyxu_b200.abc.solver import Solver
+
+    class Halver(Solver):
+        def __init__(self, fail_at=None, **kw):
+            super().__init__(log_var=("x",), final_writeback=False, **kw)
+            self.fail_at = fail_at
+
+        def m_init(self, x0):
+            self._mstate["x"] = np.asarray(x0, dtype=float)
+
+        def m_step(self):
+            if self.fail_at is not None and self._astate["idx"] == self.fail_at:
+                raise RuntimeError("boom")
+            self._mstate["x"] = self._mstate["x"] / 2
+
+        def solution(self):
+            return self._mstate["x"]
+
+    slv = Halver(show_progress=False)
+    slv.fit(x0=np.ones(3), stop_crit=pxst.MaxIter(600))
+    _, hist = slv.stats()
+    assert len(hist) == 601 and hist["iteration"].tolist() == list(range(601)) and hist["N_iter"][-1] == 601
+    lines = open(slv.logfile).read().splitlines()
+    heads = [ln for ln in lines if ln.startswith("INFO -- [")]
+    its = [int(ln.rsplit("Iteration ", 1)[1].replace("_", "")) for ln in heads if "Iteration" in ln]
+    assert its == list(range(601))                       # every iteration once, in order, across several batches
+    assert heads[-1].endswith("Stopping Criterion satisfied -> END") and lines[-1] == heads[-1]
+    assert lines[1] == "\titeration: 0" and lines[2] == "\tN_iter: 1.0"
+    assert np.allclose(slv.solution(), 0.5**600)
+    # an exception inside m_step: the entries kept back are on disk before the traceback
+    slv = Halver(fail_at=5, show_progress=False)
+    slv.fit(x0=np.ones(3), stop_crit=pxst.MaxIter(50))
+    assert isinstance(slv._astate.get("error"), RuntimeError)
+    text = open(slv.logfile).read()
+    assert text.index("Iteration 4") < text.index("EXCEPTION RAISED") and "boom" in text
+    # show_progress=True (BLOCK mode streams to stdout): entries are logged one by one, same file
+    slv = Halver(show_progress=True)
+    slv.fit(x0=np.ones(3), stop_crit=pxst.MaxIter(3))
+    assert sum("Iteration" in ln for ln in open(slv.logfile)) == 4
