@@ -484,18 +484,15 @@ class PD3O(_PrimalDualSplitting):
         return float(tau), float(sigma), float(delta)
 
     def _optimize_step_sizes(self, gamma):
-        """Same linear program as the reference (pds.py:831-864), solved with scipy's HiGHS."""
-        from scipy.optimize import linprog
-
-        c = np.array([-1, -1])
-        A_ub = np.array([[1, 1], [1, 0]])
-        b_ub = np.array([np.log(0.99) - 2 * np.log(self._K.lipschitz), np.log(1 / gamma)])
-        A_eq = np.array([[1, -1]])
-        b_eq = np.array([0])
-        result = linprog(c=c, A_ub=A_ub, b_ub=b_ub, A_eq=A_eq, b_eq=b_eq, bounds=(None, None))
-        if not result.success:
-            warnings.warn("Automatic parameter selection has not converged.", UserWarning)
-        return np.exp(result.x)
+        """The reference solves a linear program with scipy's HiGHS (pds.py:831-864):
+            maximise log tau + log sigma   s.t.  log tau + log sigma <= log 0.99 - 2 log ||K||,  log tau <= log(1/gamma),  tau = sigma.
+        With the equality it has one unknown and the unique solution log tau = min(b0 / 2, b1), which HiGHS' presolve
+        returns exactly (tests/test_host_logic_cpu.py checks bit equality against scipy on random instances): no solver call,
+        and scipy.optimize is not imported on the first fit()."""
+        b0 = np.log(0.99) - 2 * np.log(self._K.lipschitz)
+        b1 = np.log(1 / gamma)
+        t = np.exp(min(b0 / 2, b1))
+        return np.array([t, t])
 
 
 def ChambollePock(g=None, h=None, K=None, base=CondatVu, **kwargs):

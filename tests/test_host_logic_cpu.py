@@ -179,3 +179,24 @@ def test_solver_loop_log_file_and_history_without_a_device():
     slv = Halver(show_progress=True)
     slv.fit(x0=np.ones(3), stop_crit=pxst.MaxIter(3))
     assert sum("Iteration" in ln for ln in open(slv.logfile)) == 4
+
+
+def test_pd3o_step_size_rule_equals_the_reference_linear_program():
+    """PD3O default step sizes: the reference calls scipy.optimize.linprog (pds.py:831-864); here the program's
+    closed-form solution is used.  Same numbers, bit for bit, on random operator norms and gammas."""
+    from scipy.optimize import linprog
+
+    rng = np.random.default_rng(0)
+    N = 12
+    for _ in range(60):
+        L, beta = float(np.exp(rng.uniform(-3, 5))), float(np.exp(rng.uniform(-4, 4)))
+        Kop = pxo.Gradient(arg_shape=(3, 4))
+        Kop.lipschitz = L
+        for klass, strat in ((pxs.PD3O, 1), (pxs.PD3O, 2), (pxs.PD3O, 3)):
+            slv = klass(f=0.5 * beta * pxo.SquaredL2Norm(dim=N), g=None, h=pxo.L21Norm(arg_shape=(2, 3, 4), l2_axis=(0,)), K=Kop, show_progress=False)
+            gamma = slv._set_gamma(strat)
+            got = slv._optimize_step_sizes(gamma)
+            b_ub = np.array([np.log(0.99) - 2 * np.log(L), np.log(1 / gamma)])
+            ref = linprog(c=np.array([-1, -1]), A_ub=np.array([[1, 1], [1, 0]]), b_ub=b_ub, A_eq=np.array([[1, -1]]), b_eq=np.array([0]),
+                          bounds=(None, None))
+            assert ref.success and np.array_equal(got, np.exp(ref.x)), (L, gamma, got, np.exp(ref.x))
