@@ -391,8 +391,20 @@ class Stencil(pxo.SquareOp):
             cur = tmp
         import torch
 
-        ext = torch.empty(nimg * n1e * n2e, dtype=arr.dtype, device=arr.device)
         out = A.empty_like(arr)
+        if (n1e, n2e) == (n1, n2):  # only the factor along axis 0 folds: the in-plane part is the plain tiled call
+            d.shape[0], d.shape[1] = n1, n2
+            d.alpha, d.beta = float(alpha) * scale, float(beta)
+            if add is not None:
+                d.add, d.add_period = add.data_ptr(), add.numel()
+            rc = K.lib().pxb_stencil2d_apply(C.byref(d), A.ptr(cur), A.ptr(out), A.stream())
+            if rc == -3:
+                self._padded_ok = False
+                return None
+            K.check(rc, "pxb_stencil2d_apply")
+            self._padded_ok = True
+            return out
+        ext = torch.empty(nimg * n1e * n2e, dtype=arr.dtype, device=arr.device)
         if not adjoint:
             K.check(K.lib().pxb_pad2d(C.byref(pd), A.ptr(cur), A.ptr(ext), A.stream()), "pxb_pad2d")
             d.shape[0], d.shape[1], d.in_shape[0], d.in_shape[1] = n1, n2, n1e, n2e

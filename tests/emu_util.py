@@ -199,8 +199,15 @@ def stencil_run_padded(op, x, adjoint, alpha=1.0, beta=0.0, add=None):
         tmp = np.empty_like(x)
         lib().emu_stencil(C.byref(dd), int(adjoint and mode3[0] != "constant"), p(cur), p(tmp))
         cur = tmp
-    ext = np.full(nimg * n1e * n2e, np.nan, dtype=x.dtype)
     out = np.full_like(x, np.nan)
+    if (n1e, n2e) == (n1, n2):  # only the factor along axis 0 folds
+        d.shape[0], d.shape[1] = n1, n2
+        d.alpha, d.beta = alpha * scale, beta
+        if add is not None:
+            d.add, d.add_period = add.ctypes.data, add.size
+        rc = lib().emu_stencil2d(C.byref(d), p(cur), p(out))
+        return out if rc == 0 else None
+    ext = np.full(nimg * n1e * n2e, np.nan, dtype=x.dtype)
     if not adjoint:
         lib().emu_pad2d(C.byref(pd), p(cur), p(ext))
         d.shape[0], d.shape[1], d.in_shape[0], d.in_shape[1] = n1, n2, n1e, n2e

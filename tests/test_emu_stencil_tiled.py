@@ -227,6 +227,7 @@ PADDED_CASES = [
     ((4, 37, 72), np.arange(1.0, 10.0).reshape(1, 3, 3), (0, 1, 1), ("constant", "wrap", "edge")),             # dense 2-D kernel on a stack of planes
     ((128,), [gauss(9, 2.0)], (4,), "symmetric"),
     ((4, 8), np.arange(1.0, 13.0).reshape(3, 4), (2, 3), "wrap"),                          # pads as wide as the mode allows on a tiny image
+    ((6, 9, 64), [gauss(3, 1.0), gauss(5, 1.0), gauss(9, 1.5)], (0, 2, 4), ("symmetric", "constant", "constant")),  # only axis 0 folds
 ]
 
 
