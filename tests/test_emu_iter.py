@@ -454,3 +454,49 @@ def test_iter_modes_periodic_shift_direct_form():
         xb = x.copy()
         ub, zb = one_pass(algo, d, P, u, z, xb, form="direct")
         assert relerr(ub, ua) < 1e-13 and relerr(zb, za) < 1e-13
+
+
+def test_iter_modes_random_geometries():
+    """Random shapes around the tile sizes (8 rows x 32 vectors in 3-D, 16 x 32 vectors in 2-D), modes, schemes, batches and
+    chunk lengths: every single-kernel form against the two-pass generic bodies."""
+    rng = np.random.default_rng(2024)
+    names = ["constant", "wrap", "reflect", "symmetric", "edge"]
+    for trial in range(36):
+        ndim = 3 if trial % 2 == 0 else 2
+        dtype = np.float64 if trial % 3 else np.float32
+        vec = 2 if dtype == np.float64 else 4
+        t2 = 32 * vec
+        cols = int(rng.choice([vec * int(rng.integers(1, 6)), t2, t2 + vec * int(rng.integers(1, 4)), 2 * t2]))
+        if ndim == 3:
+            shape = (int(rng.integers(1, 12)), int(rng.choice([3, 7, 8, 9, 16, 17])), cols)
+        else:
+            shape = (int(rng.choice([3, 15, 16, 17, 32, 33])), cols)
+        scheme = str(rng.choice(SCHEMES))
+        p = 2 if scheme == "central" else 1
+        mode = []
+        for n in shape:
+            ok = [m for m in names if m in ("constant", "edge") or p <= (n - 1 if m == "reflect" else n)]
+            ok = [m for m in ok if not (m == "reflect" and n <= 2)]
+            mode.append(str(rng.choice(ok)))
+        batch = int(rng.integers(1, 3))
+        Kop = pxo.Gradient(arg_shape=shape, scheme=scheme, mode=tuple(mode))
+        d = Kop._desc(batch, E.dcode(np.zeros(1, dtype=dtype)))
+        shift = rng.standard_normal((batch, Kop.dim)).astype(dtype)
+        hk, gs = ((K.DUAL_L21, (K.PROX_POS, 0.0, 0.0)), (K.DUAL_L1, (K.PROX_BOX, -0.3, 0.8)))[trial % 2]
+        P = E.pds_params(0.21, 0.19, 0.9, gspec=gs, fkind=K.F_SQL2, alpha=0.7, shift=shift, hkind=hk, lam=0.3)
+        u, x = (rng.standard_normal((batch, Kop.dim)).astype(dtype) for _ in range(2))
+        z = rng.standard_normal((batch, Kop.codim)).astype(dtype)
+        algo = K.ALGO_PD3O if trial % 4 < 2 else K.ALGO_CV
+        ua, za, xa = u.copy(), z.copy(), x.copy()
+        nxa, nza = np.zeros(2 * batch), np.zeros(2 * batch)
+        two_pass(algo, d, P, ua, za, xa, nxa, nza)
+        tol = 1e-13 if dtype == np.float64 else 3e-6
+        for form in (("direct", "tma") if ndim == 3 else ("direct", "tile2d")):
+            nxb, nzb = np.zeros(2 * batch), np.zeros(2 * batch)
+            xb = x.copy()
+            ub, zb = one_pass(algo, d, P, u, z, xb, nxb, nzb, chunk=int(rng.choice([0, 1, 3])) if form != "tile2d" else 0, form=form)
+            assert relerr(ub, ua) < tol and relerr(zb, za) < tol, (trial, shape, mode, scheme, form, algo)
+            if algo == K.ALGO_PD3O:
+                assert relerr(xb, xa) < tol
+            rt = 1e-10 if dtype == np.float64 else 1e-4
+            assert np.allclose(nxa, nxb, rtol=rt) and np.allclose(nza, nzb, rtol=rt), (trial, shape, mode, scheme, form)
