@@ -1,0 +1,98 @@
+"""The GPU parity tests of the solvers (tests/test_gpu_solvers.py: every fixture the real reference produced, re-run through
+Solver.fit()) replayed on the build container: same test functions, same tolerances, with the device emulated
+(tests/emu_device.py: CPU tensors + the kernel bodies of tests/emu behind the C-ABI entry points).  This is how the host logic
+around the kernels that have not run on a GPU yet -- the folding-mode instances of the single-kernel iteration after their last
+change, Stencil._run_padded -- is checked end to end against the reference's fixtures."""
+import types
+
+import numpy as np
+import pytest
+
+import cases
+import test_gpu_solvers as G
+from conftest import golden
+from emu_device import emulated_device
+
+
+@pytest.fixture
+def dev():
+    import pyxu_b200.operator as pxo
+    import pyxu_b200.opt.solver as pxs
+    import pyxu_b200.opt.stop as pxst
+
+    with emulated_device() as lib:
+        yield types.SimpleNamespace(operator=pxo, solver=pxs, stop=pxst, lib=lib)
+
+
+@pytest.mark.parametrize("strat", [1, 2, 3])
+def test_pd3o_tv2d(dev, strat):
+    G.test_pd3o_tv2d(dev, strat)
+    assert "pds_iter:tile2d" in dev.lib.log and "pds_primal" not in dev.lib.log
+
+
+def test_default_stop_iteration_count_and_cv(dev):
+    G.test_pd3o_tv2d_default_stop_iteration_count(dev)
+    G.test_cv_tv2d(dev)
+
+
+@pytest.mark.parametrize("mode", ["reflect", "wrap", "symmetric", "edge"])
+def test_pd3o_tv2d_folding_modes_run_the_single_kernel_form(dev, mode):
+    G.test_pd3o_tv2d_modes(dev, mode)
+    assert "pds_iter:tile2d" in dev.lib.log and "pds_dual" not in dev.lib.log
+    dev.lib.log.clear()
+    dev.lib.pxb_set_iter_modes(0)  # ... and the two-sweep form when they are switched off
+    G.test_pd3o_tv2d_modes(dev, mode)
+    assert "pds_dual" in dev.lib.log and not any(s.startswith("pds_iter") for s in dev.lib.log)
+
+
+def test_pd3o_tv3d_constant_and_mixed_modes(dev):
+    G.test_pd3o_tv3d(dev)
+    # 50 iterations 'constant' + 30 with (reflect, wrap, constant): TMA form; the fp32 run has 14 columns (not a multiple of
+    # 4 samples): outside the single-kernel envelope -> 50 two-sweep iterations
+    assert dev.lib.log.count("pds_iter:tma") == 80 and dev.lib.log.count("pds_dual") == 50
+
+
+@pytest.mark.parametrize("tag", ["dense", "sep"])
+def test_cv_deblur2d(dev, tag):
+    G.test_cv_deblur2d(dev, tag)
+    assert "stencil2d" in dev.lib.log
+
+
+def test_cv_deblur3d_and_generic_path(dev):
+    G.test_cv_deblur3d(dev)
+    G.test_generic_path_equals_fused_path(dev)
+
+
+@pytest.mark.parametrize("padded", [False, True])
+def test_reflect_mode_blur_through_gather_and_padded_tiled_paths(dev, padded, monkeypatch):
+    """PD3O / PGD with a reflect-mode blur in the data term: the gather kernels (default) and Stencil._run_padded
+    (PYXU_B200_STENCIL_PADDED=1: pxb_pad2d -> tiled stencil -> pxb_pad2d_adjoint) must both reproduce the reference."""
+    from pyxu_b200.operator.linop import stencil as st
+
+    monkeypatch.setattr(st, "PADDED_TILED", padded)
+    G.test_pd3o_deblur2d_semi_fused(dev)
+    G.test_pgd_stacked_images_equal_per_image_solves(dev)
+    assert ("pad2d" in dev.lib.log and "pad2d_adjoint" in dev.lib.log) == padded
+    # CondatVu with the same blur: fused TV iteration + grad f through the two padded passes
+    g = golden("solvers.npz")
+    yb = g["cv_deblur2d/sep/y"]
+    g9 = cases.gaussian_1d(9, 1.5)
+    res = []
+    for kern in (np.outer(g9, g9), [g9, g9]):
+        slv, Aop = cases.build_tv_deblur(dev, yb, (28, 24), kern, (4, 4), lam=0.02, blur_mode="reflect", positivity=True)
+        slv.fit(x0=np.zeros(yb.size), stop_crit=dev.stop.MaxIter(25))
+        assert slv._astate.get("error") is None, slv._astate.get("error")
+        assert (Aop._padded_ok is True) == padded
+        res.append(slv.stats()[0]["x"])
+    assert G.relerr(res[0], res[1]) < 1e-12  # dense and separable statements of the same blur
+
+
+@pytest.mark.parametrize("acc", [True, False])
+def test_pgd_l1_deconv(dev, acc):
+    G.test_pgd_l1_deconv(dev, acc)
+    assert "stencil2d_fista" in dev.lib.log
+
+
+def test_pgd_default_stop_and_manual_async_modes(dev):
+    G.test_pgd_default_stop_iteration_count(dev)
+    G.test_manual_and_async_modes(dev)
