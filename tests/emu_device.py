@@ -181,10 +181,32 @@ class EmuLib:
         return self._ok("pds_iter:direct", self.h.emu_tv_iter(*args))
 
 
+class _Stream:  # stands in for torch.cuda.Stream / Event: the emulated device executes every call synchronously
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+
 @contextlib.contextmanager
-def emulated_device():
-    """Patches pyxu_b200 to run on CPU tensors with the emulated library; yields the EmuLib (launch log, toggles)."""
+def emulated_device(cuda_runtime=False):
+    """Patches pyxu_b200 to run on CPU tensors with the emulated library; yields the EmuLib (launch log, toggles).
+    cuda_runtime: also stub the few torch.cuda calls the slab classes make (streams, events, synchronize)."""
     lib = EmuLib()
+    cuda_saved = {}
+    if cuda_runtime:
+        stubs = dict(Stream=_Stream, Event=_Stream, synchronize=lambda *a: None, current_stream=lambda *a: _Stream(),
+                     stream=lambda s: contextlib.nullcontext(), empty_cache=lambda: None)
+        for k, v in stubs.items():
+            cuda_saved[k] = getattr(torch.cuda, k)
+            setattr(torch.cuda, k, v)
     saved = (A.require_cuda, A.current_device, A.stream, K.lib, A._BIG, A.asdevice)
     orig_asdevice = A.asdevice
 
@@ -208,3 +230,5 @@ def emulated_device():
     finally:
         A.require_cuda, A.current_device, A.stream, K.lib, A._BIG, A.asdevice = saved
         lib.h.emu_set_iter_modes(1)
+        for k, v in cuda_saved.items():
+            setattr(torch.cuda, k, v)

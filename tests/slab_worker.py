@@ -1,5 +1,9 @@
 """torchrun worker: z-slab PD3O-TV on WORLD_SIZE GPUs must reproduce the single-GPU PD3O solver.
-Usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/slab_worker.py"""
+Usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/slab_worker.py
+
+PXB_SLAB_WORKER_DEVICE=cpu runs the same script without GPUs (tests/test_slab_cpu.py): gloo instead of NCCL, and the device
+emulated by tests/emu_device.py (CPU tensors, the kernel bodies of tests/emu behind the C ABI) -- the slab classes' own Python
+(buffer layout, launch order, exchanges, norms) is then what is under test."""
 import os
 import sys
 
@@ -11,10 +15,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def main(dev="cuda"):
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if dev == "cuda":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
     import pyxu_b200.operator as pxo
     import pyxu_b200.opt.solver as pxs
     import pyxu_b200.opt.stop as pxst
@@ -27,8 +34,8 @@ def main():
                                              ((32, 16, 24), "wrap", True, torch.float64, 1e-13),
                                              ((64, 48, 64), "constant", True, torch.float32, 1e-5)]:
         n_iter, lam = 25, 0.08
-        gen = torch.Generator(device="cuda").manual_seed(7)
-        y = torch.rand(shape, device="cuda", dtype=dtype, generator=gen)
+        gen = torch.Generator(device=dev).manual_seed(7)
+        y = torch.rand(shape, device=dev, dtype=dtype, generator=gen)
         slab = SlabPD3OTV(shape, y_full=y, lam=lam, positivity=True, dtype=dtype, mode=mode, overlap=overlap, rho=1.2)
         v = None
         for i in range(n_iter):  # norms only now and then: x is then rebuilt from the previous iterate when needed
@@ -68,8 +75,8 @@ def main():
                                              ((48, 40, 64), [gauss(7, 1.2), gauss(7, 1.2), gauss(7, 1.2)], (3, 3, 3), torch.float32, 2e-5, False)]:
         n_iter, lam = 15, 0.05
         npdt = np.float64 if dtype == torch.float64 else np.float32
-        gen = torch.Generator(device="cuda").manual_seed(11)
-        y = torch.rand(shape, device="cuda", dtype=dtype, generator=gen)
+        gen = torch.Generator(device=dev).manual_seed(11)
+        y = torch.rand(shape, device=dev, dtype=dtype, generator=gen)
         slab = SlabCondatVuDeblur(shape, psf, cen, y_full=y, lam=lam, positivity=True, dtype=dtype, rho=0.9, overlap=ovl)
         v = None
         for i in range(n_iter):
@@ -94,11 +101,18 @@ def main():
         if rank == 0:
             print(f"[slab-deblur] world={world} shape={shape} {dtype} overlap={slab.overlap} single_pass={slab.single_pass}: rel.err={err:.2e} "
                   f"relerr-norm dev={e_rx:.1e} {'OK' if good else 'FAIL'}", flush=True)
-    t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     sys.exit(0 if t.item() == 1.0 else 1)
 
 
 if __name__ == "__main__":
-    main()
+    if os.environ.get("PXB_SLAB_WORKER_DEVICE", "cuda") == "cpu":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from emu_device import emulated_device
+
+        with emulated_device(cuda_runtime=True):
+            main("cpu")
+    else:
+        main()
