@@ -96,3 +96,30 @@ def test_pgd_l1_deconv(dev, acc):
 def test_pgd_default_stop_and_manual_async_modes(dev):
     G.test_pgd_default_stop_iteration_count(dev)
     G.test_manual_and_async_modes(dev)
+
+
+@pytest.mark.parametrize("padded", [False, True])
+def test_operator_fixtures_through_the_real_operators(dev, padded, monkeypatch):
+    """Stencil / Convolve / Gradient / proximal-map fixtures of the real reference through the operator classes themselves
+    (tests/test_gpu_operators.py's cases), with and without the padded tiled path for folding Stencil modes."""
+    import test_gpu_operators as GO
+    from pyxu_b200.operator.linop import stencil as st
+
+    monkeypatch.setattr(st, "PADDED_TILED", padded)
+    g = golden("stencil.npz")
+    used = 0
+    for case in cases.STENCIL_CASES:
+        n = case["name"]
+        for dtype, tol in ((np.float64, 1e-12), (np.float32, 5e-6)):
+            op = cases.make_stencil(dev, case, dtype=dtype)
+            out = op.apply(g[f"{n}/x"].astype(dtype))
+            assert isinstance(out, np.ndarray) and out.dtype == dtype  # NumPy in -> NumPy out
+            assert GO.relerr(out, g[f"{n}/apply"]) < tol and GO.relerr(op.adjoint(g[f"{n}/y"].astype(dtype)), g[f"{n}/adjoint"]) < tol, (n, dtype)
+            used += op._padded_ok is True
+    assert (used > 0) == padded
+    for case in cases.GRADIENT_CASES:
+        GO.test_gradient_golden(dev, case)
+    GO.test_funcs_golden(dev)
+    for shape, ks, modes in (((37, 53), (5, 5), ("reflect", "wrap")), ((19, 23, 17), (3, 4, 5), ("symmetric", "edge", "constant")), ((301,), (9,), ("wrap",)),
+                             ((36, 64), (9, 9), ("reflect", "symmetric")), ((12, 20, 36), (7, 7, 7), ("constant", "reflect", "symmetric"))):
+        GO.test_stencil_vs_oracle_random(dev, shape, ks, modes)
