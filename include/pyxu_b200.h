@@ -202,6 +202,15 @@ int pxb_lincomb(int dtype, int64_t n, void* out, double a, const void* x, double
  * multiple of 4 (fp32) / 2 (fp64) samples, 16-byte aligned arrays; PXB_ENOSUP otherwise (use pxb_stencil_apply). */
 int pxb_stencil_axis0_apply(int dtype, int64_t batch, const int64_t* shape, const pxb_slab* slab, int k0, int c0,
                             const double* coef, const void* in, void* out, void* stream);
+/* The same streaming pass with a FOLDING boundary mode along axis 0 (single-domain arrays), both directions of
+ * Trim o S0 o Pad (stencil.py:76-84, 130-146):
+ *   adjoint == 0:  out[q] = sum_j coef[j] * in[m(q + j - c0)]            (m: numpy.pad's index map of `mode`, pad.py:252-302)
+ *   adjoint != 0:  coef / c0 hold the REVERSED taps and the mirrored centre (k0 - 1 - centre); out[t] = sum over the padded
+ *                  coordinates e with m(e) = t of  sum_j coef[j] * in[e + j - c0]  (in zero outside the array): the
+ *                  transpose, Pad^T o S0^T o Trim^T (pad.py:307-375).
+ * Envelope as pxb_stencil_axis0_apply; PXB_ENOSUP otherwise (use pxb_stencil_apply / pxb_stencil_adjoint). */
+int pxb_stencil_axis0_fold(int dtype, int64_t batch, const int64_t* shape, int k0, int c0, const double* coef, int mode,
+                           int adjoint, const void* in, void* out, void* stream);
 
 /* A separable 3-D stencil ('constant' boundaries) in ONE pass over HBM where the reference chains three 1-D stencils
  * (stencil.py:497-538): thread blocks march along axis 0 with the in-plane-filtered planes in a register ring.

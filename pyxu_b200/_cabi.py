@@ -167,6 +167,7 @@ PROTOTYPES = {
     "pxb_pad2d": (_i, [_P(Pad2D), _vp, _vp, _vp]),
     "pxb_pad2d_adjoint": (_i, [_P(Pad2D), _vp, _vp, _d, _d, _vp, _i64, _vp]),
     "pxb_stencil_axis0_apply": (_i, [_i, _i64, _P(C.c_int64), _P(Slab), _i, _i, _P(C.c_double), _vp, _vp, _vp]),
+    "pxb_stencil_axis0_fold": (_i, [_i, _i64, _P(C.c_int64), _i, _i, _P(C.c_double), _i, _i, _vp, _vp, _vp]),
     "pxb_stencil3d_apply": (_i, [_P(Stencil3D), _vp, _vp, _vp]),
     "pxb_gradient_apply": (_i, [_P(GradDesc), _vp, _vp, _vp]),
     "pxb_gradient_adjoint": (_i, [_P(GradDesc), _vp, _vp, _vp]),

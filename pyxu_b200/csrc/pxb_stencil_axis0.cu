@@ -8,58 +8,28 @@
 // Slabs: planes outside the owned range are read when the side is open (ghost planes hold the neighbour's data),
 // and count as zero otherwise -- numpy.pad 'constant' (pad.py:252-258).
 #include "pxb_launch.cuh"
-#include "pxb_tv_fast.cuh"
+#include "pxb_stencil_axis0.cuh"
 
 namespace {
 
-struct Axis0P {
-    int n0;              // owned planes
-    int64_t plane;       // elements per plane
-    int64_t vol;         // elements between batch items
-    int c0, chunk, nchunk;
-    int lo_planes, hi_planes;  // readable planes below plane 0 / above plane n0-1 (open slab sides)
-    double coef[16];
-};
-
-template <class T, int VEC, int K0>
+// FOLD = false: 'constant' boundary (and slab cuts), the instances measured in DESIGN.md.  FOLD = true: a folding boundary mode
+// along axis 0, both directions (pxb_stencil_axis0_fold).
+template <class T, int VEC, int K0, bool FOLD>
 __global__ void __launch_bounds__(256) k_stencil_axis0(const __grid_constant__ Axis0P p, const T* __restrict__ in, T* __restrict__ out) {
     const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (col >= p.plane) return;
     const int ch = blockIdx.y;
     const int64_t b = blockIdx.z;
     const int m0 = ch * p.chunk, m1 = min(p.n0, m0 + p.chunk);
-    const T* __restrict__ src = in + b * p.vol + col;
-    T* __restrict__ dst = out + b * p.vol + col;
-    T c[K0];
-    for (int j = 0; j < K0; ++j) c[j] = T(p.coef[j]);
-    PxbVec<T, VEC> ring[K0];
-    for (int j = 0; j < K0; ++j)
-        for (int v = 0; v < VEC; ++v) ring[j].v[v] = T(0);
-    const int last = m1 + K0 - 1 - p.c0;  // one past the last input plane
-    for (int pl = m0 - p.c0; pl < last; ++pl) {
-        PxbVec<T, VEC> t;
-        if (pl >= -p.lo_planes && pl < p.n0 + p.hi_planes) t = pxb_vload<T, VEC>(src + (int64_t)pl * p.plane);
-        else for (int v = 0; v < VEC; ++v) t.v[v] = T(0);
-        for (int j = 0; j + 1 < K0; ++j) ring[j] = ring[j + 1];
-        ring[K0 - 1] = t;
-        const int q = pl - (K0 - 1 - p.c0);
-        if (q >= m0) {
-            PxbVec<T, VEC> o;
-            for (int v = 0; v < VEC; ++v) {
-                T a = T(0);
-                for (int j = 0; j < K0; ++j) a += c[j] * ring[j].v[v];
-                o.v[v] = a;
-            }
-            pxb_vstore<T, VEC>(dst + (int64_t)q * p.plane, o);
-        }
-    }
+    pxb_axis0_column<T, VEC, K0, FOLD>(p, in + b * p.vol + col, out + b * p.vol + col, m0, m1);
 }
 
 template <class T, int VEC, int K0>
 void launch(const Axis0P& p, int64_t batch, const void* in, void* out, cudaStream_t s) {
     const int64_t cols = p.plane / VEC;
     dim3 grid((unsigned)((cols + 255) / 256), (unsigned)p.nchunk, (unsigned)batch);
-    k_stencil_axis0<T, VEC, K0><<<grid, 256, 0, s>>>(p, (const T*)in, (T*)out);
+    if (p.mode != PXB_CONSTANT) k_stencil_axis0<T, VEC, K0, true><<<grid, 256, 0, s>>>(p, (const T*)in, (T*)out);
+    else k_stencil_axis0<T, VEC, K0, false><<<grid, 256, 0, s>>>(p, (const T*)in, (T*)out);
 }
 
 template <class T>
@@ -80,9 +50,8 @@ bool dispatch(int k0, const Axis0P& p, int64_t batch, const void* in, void* out,
 
 }  // namespace
 
-extern "C" int pxb_stencil_axis0_apply(int dtype, int64_t batch, const int64_t* shape, const pxb_slab* slab, int k0, int c0, const double* coef,
-                                       const void* in, void* out, void* stream) {
-    const char* who = "pxb_stencil_axis0_apply";
+static int axis0_run(const char* who, int dtype, int64_t batch, const int64_t* shape, const pxb_slab* slab, int k0, int c0, const double* coef,
+                     int mode, int adjoint, const void* in, void* out, void* stream) {
     if (dtype != PXB_F32 && dtype != PXB_F64) return pxb_fail(PXB_EINVAL, "%s: bad dtype %d", who, dtype);
     if (!shape || !coef || !in || !out || in == out) return pxb_fail(PXB_EINVAL, "%s: null or aliased argument", who);
     if (batch < 1 || shape[0] < 1 || shape[1] < 1 || shape[2] < 1) return pxb_fail(PXB_EINVAL, "%s: empty array", who);
@@ -96,6 +65,11 @@ extern "C" int pxb_stencil_axis0_apply(int dtype, int64_t batch, const int64_t* 
     p.vol = (int64_t)alloc * p.plane;
     if (halo > 0 && batch != 1) return pxb_fail(PXB_EINVAL, "%s: slabs require batch == 1", who);
     p.c0 = c0;
+    p.mode = mode;
+    p.adjoint = adjoint;
+    // pad widths of the operator itself: with the reversed taps of the adjoint the centre is mirrored back
+    p.pad_lo = adjoint ? k0 - 1 - c0 : c0;
+    p.pad_hi = adjoint ? c0 : k0 - 1 - c0;
     p.lo_planes = slab && slab->open_lo ? c0 : 0;
     p.hi_planes = slab && slab->open_hi ? k0 - 1 - c0 : 0;
     if (p.lo_planes > halo || p.hi_planes > halo) return pxb_fail(PXB_EINVAL, "%s: the stencil reaches %d / %d planes across an open side but halo = %d", who, p.lo_planes, p.hi_planes, halo);
@@ -113,4 +87,21 @@ extern "C" int pxb_stencil_axis0_apply(int dtype, int64_t batch, const int64_t* 
     if (!ok) return pxb_fail(PXB_ENOSUP, "%s: kernel extent %d not compiled", who, k0);
     PXB_CHECK_LAUNCH(who);
     return 0;
+}
+
+extern "C" int pxb_stencil_axis0_apply(int dtype, int64_t batch, const int64_t* shape, const pxb_slab* slab, int k0, int c0, const double* coef,
+                                       const void* in, void* out, void* stream) {
+    return axis0_run("pxb_stencil_axis0_apply", dtype, batch, shape, slab, k0, c0, coef, PXB_CONSTANT, 0, in, out, stream);
+}
+
+extern "C" int pxb_stencil_axis0_fold(int dtype, int64_t batch, const int64_t* shape, int k0, int c0, const double* coef, int mode, int adjoint,
+                                      const void* in, void* out, void* stream) {
+    const char* who = "pxb_stencil_axis0_fold";
+    if (mode < PXB_CONSTANT || mode > PXB_EDGE) return pxb_fail(PXB_EINVAL, "%s: bad mode %d", who, mode);
+    if (shape && k0 >= 1) {  // a coordinate folds at most once (pad.py:217-229)
+        const int64_t n = shape[0], w = k0 - 1;
+        const int64_t lim = mode == PXB_REFLECT ? n - 1 : ((mode == PXB_WRAP || mode == PXB_SYMMETRIC) ? n : w);
+        if (mode != PXB_CONSTANT && w > lim) return pxb_fail(PXB_EINVAL, "%s: %d taps exceed what mode %d admits on %lld planes", who, k0, mode, (long long)n);
+    }
+    return axis0_run(who, dtype, batch, shape, nullptr, k0, c0, coef, mode, adjoint ? 1 : 0, in, out, stream);
 }

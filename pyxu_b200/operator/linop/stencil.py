@@ -380,14 +380,22 @@ class Stencil(pxo.SquareOp):
             tmp = A.empty_like(arr)
             if mode3[0] == "constant":
                 self._axis0_pass(axis0, cur, tmp, batch)
-            else:  # gather kernel with the boundary map; the plan of the adjoint holds the reversed kernel: undo
+            else:
+                # streaming pass with the boundary map (the plan of the adjoint already holds the reversed taps and the mirrored
+                # centre, which is what the kernel's transposed form takes); gather kernel outside its envelope
                 k3, c3 = axis0
-                if adjoint:
-                    k3, c3 = np.ascontiguousarray(np.flip(k3)), np.array(k3.shape) - c3 - 1
-                coef, _ = A.asdevice(k3.reshape(-1), dtype=arr.dtype)
-                dd = self._desc(k3, c3, batch, A.dcode(arr), coef.data_ptr())
-                fn = K.lib().pxb_stencil_adjoint if adjoint else K.lib().pxb_stencil_apply
-                K.check(fn(C.byref(dd), A.ptr(cur), A.ptr(tmp), A.stream()), "Stencil (axis 0)")
+                k0 = int(k3.shape[0])
+                taps = (C.c_double * k0)(*[float(v) for v in k3.reshape(-1)])
+                rc = K.lib().pxb_stencil_axis0_fold(A.dcode(arr), batch, (C.c_int64 * 3)(*shape3), k0, int(c3[0]), taps, K.MODES[mode3[0]], int(adjoint),
+                                                    A.ptr(cur), A.ptr(tmp), A.stream())
+                if rc == -3:
+                    if adjoint:
+                        k3, c3 = np.ascontiguousarray(np.flip(k3)), np.array(k3.shape) - c3 - 1
+                    coef, _ = A.asdevice(k3.reshape(-1), dtype=arr.dtype)
+                    dd = self._desc(k3, c3, batch, A.dcode(arr), coef.data_ptr())
+                    fn = K.lib().pxb_stencil_adjoint if adjoint else K.lib().pxb_stencil_apply
+                    rc = fn(C.byref(dd), A.ptr(cur), A.ptr(tmp), A.stream())
+                K.check(rc, "Stencil (axis 0)")
             cur = tmp
         import torch
 

@@ -17,6 +17,7 @@ static long g_w_global_cells = 0;  // cells of the w tiles evaluated by pxb_tv_w
 #include "../../pyxu_b200/csrc/pxb_stencil_tma.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_tile2d.cuh"
 #include "../../pyxu_b200/csrc/pxb_stencil3d.cuh"
+#include "../../pyxu_b200/csrc/pxb_stencil_axis0.cuh"
 #include <vector>
 
 // folding boundary modes inside the single-kernel iteration forms (pxb_set_iter_modes on the device side)
@@ -577,7 +578,48 @@ static void t_pad2d(const pxb_pad2d_desc* d, bool adj, const void* a, void* b, d
                 }
             }
 }
+// streaming axis-0 stencil with a folding mode (pxb_stencil_axis0.cuh): column by column, chunk by chunk, as the grid does
+template <class T, int K0>
+static void t_axis0_k(const Axis0P& p, int64_t batch, const T* in, T* out) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    for (int64_t b = 0; b < batch; ++b)
+        for (int ch = 0; ch < p.nchunk; ++ch)
+            for (int64_t col = 0; col < p.plane; col += VEC) {
+                const int m0 = ch * p.chunk, m1 = std::min(p.n0, m0 + p.chunk);
+                pxb_axis0_column<T, VEC, K0, true>(p, in + b * p.vol + col, out + b * p.vol + col, m0, m1);
+            }
+}
+template <class T>
+static int t_axis0(int64_t batch, const int64_t* shape, int k0, int c0, const double* coef, int mode, int adjoint, const void* in, void* out, int chunk) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    Axis0P p;
+    p.n0 = (int)shape[0]; p.plane = shape[1] * shape[2]; p.vol = (int64_t)p.n0 * p.plane;
+    p.c0 = c0; p.mode = mode; p.adjoint = adjoint ? 1 : 0;
+    p.pad_lo = adjoint ? k0 - 1 - c0 : c0; p.pad_hi = adjoint ? c0 : k0 - 1 - c0;
+    p.lo_planes = p.hi_planes = 0;
+    if (k0 < 2 || k0 > 9 || p.plane % VEC || c0 < 0 || c0 >= k0) return -103;
+    for (int j = 0; j < 16; ++j) p.coef[j] = j < k0 ? coef[j] : 0.0;
+    p.chunk = chunk > 0 ? std::min(chunk, p.n0) : p.n0;
+    p.nchunk = (p.n0 + p.chunk - 1) / p.chunk;
+    switch (k0) {
+        case 2: t_axis0_k<T, 2>(p, batch, (const T*)in, (T*)out); break;
+        case 3: t_axis0_k<T, 3>(p, batch, (const T*)in, (T*)out); break;
+        case 4: t_axis0_k<T, 4>(p, batch, (const T*)in, (T*)out); break;
+        case 5: t_axis0_k<T, 5>(p, batch, (const T*)in, (T*)out); break;
+        case 6: t_axis0_k<T, 6>(p, batch, (const T*)in, (T*)out); break;
+        case 7: t_axis0_k<T, 7>(p, batch, (const T*)in, (T*)out); break;
+        case 8: t_axis0_k<T, 8>(p, batch, (const T*)in, (T*)out); break;
+        case 9: t_axis0_k<T, 9>(p, batch, (const T*)in, (T*)out); break;
+        default: return -103;
+    }
+    return 0;
+}
 extern "C" {
+int emu_stencil_axis0_fold(int dtype, int64_t batch, const int64_t* shape, int k0, int c0, const double* coef, int mode, int adjoint, const void* in,
+                           void* out, int chunk) {
+    return dtype == PXB_F32 ? t_axis0<float>(batch, shape, k0, c0, coef, mode, adjoint, in, out, chunk)
+                            : t_axis0<double>(batch, shape, k0, c0, coef, mode, adjoint, in, out, chunk);
+}
 int emu_stencil3d(const pxb_stencil3d* d, const void* in, void* out) {
     return d->dtype == PXB_F32 ? t_st3<float>(d, in, out) : t_st3<double>(d, in, out);
 }

@@ -89,6 +89,10 @@ class EmuLib:
     def pxb_stencil_axis0_apply(self, *a):
         return ENOSUP  # the streaming kernel's body is not replayed on the host: callers take the gather kernel, as on a GPU outside its envelope
 
+    def pxb_stencil_axis0_fold(self, dtype, batch, shape, k0, c0, coef, mode, adjoint, x, out, stream):
+        # several chunks, so that chunk borders take part (the launcher picks its own chunk length from the grid size)
+        return self._ok("stencil_axis0_fold", self.h.emu_stencil_axis0_fold(dtype, batch, shape, k0, c0, coef, mode, adjoint, x, out, 3))
+
     def pxb_pad2d(self, d, x, ext, stream):
         return self._ok("pad2d", self.h.emu_pad2d(d, x, ext))
 

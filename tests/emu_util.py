@@ -31,6 +31,7 @@ def lib():
         h.emu_stencil2d_fista.argtypes = [P(K.Stencil2D), P(K.FistaStep), i, vp]
         h.emu_tv_grad.argtypes = [i, i, P(K.GradDesc), vp, vp]
         h.emu_stencil3d.argtypes = [P(K.Stencil3D), vp, vp]
+        h.emu_stencil_axis0_fold.argtypes = [i, i64, P(C.c_int64), i, i, P(C.c_double), i, i, vp, vp, i]
         h.emu_dual_update.argtypes = [i, i, i64, i64, i64, d, d, d, vp, vp, vp]
         h.emu_prox_l21.argtypes = [i, i64, i64, i64, d, d, vp, vp]
         h.emu_prox_lincomb.argtypes = [i, P(K.ProxSpec), d, i64, vp, d, vp, d, vp, i64, d, vp, i64]

@@ -123,3 +123,35 @@ def test_operator_fixtures_through_the_real_operators(dev, padded, monkeypatch):
     for shape, ks, modes in (((37, 53), (5, 5), ("reflect", "wrap")), ((19, 23, 17), (3, 4, 5), ("symmetric", "edge", "constant")), ((301,), (9,), ("wrap",)),
                              ((36, 64), (9, 9), ("reflect", "symmetric")), ((12, 20, 36), (7, 7, 7), ("constant", "reflect", "symmetric"))):
         GO.test_stencil_vs_oracle_random(dev, shape, ks, modes)
+
+
+def test_3d_separable_stencil_with_folding_modes_padded_path(dev, monkeypatch):
+    """3-D separable stencils with a folding mode on every axis through the real Stencil class with the padded tiled path on:
+    streaming axis-0 pass with the boundary map (pxb_stencil_axis0_fold) + Pad -> tiled stencil / tiled stencil -> Pad^T,
+    against the gather kernels and the fixture of the real reference (3d_sep_mixed)."""
+    import test_gpu_operators as GO
+    from pyxu_b200.operator.linop import stencil as st
+
+    rng = np.random.default_rng(8)
+    g7 = cases.gaussian_1d(7, 1.2)
+    for shape, kern, cen, mode in (((9, 12, 32), [g7, cases.gaussian_1d(5, 1.0), g7], (3, 2, 3), "reflect"),
+                                   ((9, 12, 32), [rng.standard_normal(4), g7, rng.standard_normal(3)], (0, 6, 2), ("wrap", "symmetric", "edge")),
+                                   ((7, 10, 16), [rng.standard_normal(3), np.ones(1), g7], (2, 0, 3), ("symmetric", "constant", "reflect"))):
+        x = rng.standard_normal((2, int(np.prod(shape))))
+        outs = {}
+        for padded in (True, False):
+            monkeypatch.setattr(st, "PADDED_TILED", padded)
+            op = dev.operator.Stencil(arg_shape=shape, kernel=kern, center=cen, mode=mode)
+            dev.lib.log.clear()
+            outs[padded] = (op.apply(x), op.adjoint(x))
+            assert ("stencil_axis0_fold" in dev.lib.log and "pad2d" in dev.lib.log) == padded
+        for a, b in zip(outs[True], outs[False]):
+            assert GO.relerr(a, b) < 1e-13
+        y = rng.standard_normal(x.shape)
+        assert abs(np.vdot(outs[True][0], y) - np.vdot(x, op.adjoint(y) if False else dev.operator.Stencil(arg_shape=shape, kernel=kern, center=cen, mode=mode).adjoint(y))) < 1e-9
+    monkeypatch.setattr(st, "PADDED_TILED", True)
+    case = [c for c in cases.STENCIL_CASES if c["name"] == "3d_sep_mixed"][0]
+    gold = golden("stencil.npz")
+    # the fixture's last axis has 7 samples (not a multiple of the vector width): that operator stays on the gather kernels
+    op = cases.make_stencil(dev, case)
+    assert GO.relerr(op.apply(gold["3d_sep_mixed/x"]), gold["3d_sep_mixed/apply"]) < 1e-12 and op._padded_ok is False

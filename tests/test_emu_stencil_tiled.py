@@ -311,3 +311,31 @@ def test_pad2d_is_numpy_pad_and_its_transpose(dtype):
         yin[:, org[0] - lo[0] : org[0] + n1 + hi[0], org[1] - lo[1] : org[1] + n2 + hi[1]] = y[:, org[0] - lo[0] : org[0] + n1 + hi[0], org[1] - lo[1] : org[1] + n2 + hi[1]]
         lhs, rhs = np.vdot(got.astype(np.float64), yin), np.vdot(x.astype(np.float64), back)
         assert abs(lhs - rhs) < (1e-12 if dtype == np.float64 else 1e-4) * (1 + abs(lhs)), (trial, modes, lo, hi)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_axis0_streaming_kernel_with_folding_modes(dtype):
+    """pxb_stencil_axis0_fold (streaming register-ring kernel, folding boundary mode along axis 0): apply = S o Pad, adjoint =
+    Pad^T o S0^T, against the gather kernels for every mode, tap count, centre and chunk length."""
+    rng = np.random.default_rng(23)
+    vec = 2 if dtype == np.float64 else 4
+    for trial in range(60):
+        k0 = int(rng.integers(2, 10))
+        mode = str(rng.choice(["wrap", "reflect", "symmetric", "edge", "constant"]))
+        nmin = {"wrap": k0 - 1, "symmetric": k0 - 1, "reflect": k0, "edge": 1, "constant": 1}[mode]
+        n0 = int(rng.integers(max(nmin, 2), max(nmin, 2) + 9))
+        shape = (n0, int(rng.integers(1, 4)), vec * int(rng.integers(1, 4)))
+        c0 = int(rng.integers(0, k0))
+        taps = rng.standard_normal(k0)
+        op = pxo.Stencil(arg_shape=shape, kernel=[taps.astype(dtype), np.ones(1, dtype=dtype), np.ones(1, dtype=dtype)], center=(c0, 0, 0),
+                         mode=(mode, "constant", "constant"))
+        batch = int(rng.integers(1, 3))
+        x = rng.standard_normal((batch, op.dim)).astype(dtype)
+        for adj in (False, True):
+            ref = E.stencil_run(op, x, adj)
+            k, c = (taps[::-1].copy(), k0 - 1 - c0) if adj else (taps, c0)  # the transposed form takes the reversed taps
+            out = np.full_like(x, np.nan)
+            rc = E.lib().emu_stencil_axis0_fold(E.dcode(x), batch, (C.c_int64 * 3)(*shape), k0, c, (C.c_double * k0)(*k), E.K.MODES[mode], int(adj),
+                                                E.p(x), E.p(out), int(rng.choice([0, 1, 2, 5])))
+            assert rc == 0
+            assert relerr(out, ref) < (1e-13 if dtype == np.float64 else 3e-6), (trial, shape, k0, c0, mode, adj)
