@@ -87,5 +87,7 @@ for kern, cen in (([gauss(9, 1.7), gauss(9, 1.7)], (4, 4)), (np.outer(gauss(5, 1
     op = pxo.Stencil(arg_shape=(70, 520), kernel=kern, center=cen, mode=("reflect", "wrap"))
     op.apply(x2), op.adjoint(x2)
     assert op._padded_ok is (True if _st.PADDED_TILED else None)
+op = pxo.Stencil(arg_shape=(21, 19, 136), kernel=[gauss(5, 1.0), gauss(5, 1.0), gauss(7, 1.2)], center=(1, 2, 3), mode=("reflect", "wrap", "symmetric"))
+op.apply(x3), op.adjoint(x3)  # (padded path: streaming axis-0 pass with the boundary map + Pad -> tiled stencil / -> Pad^T)
 torch.cuda.synchronize()
 print("sanitize_kernels: all launches completed")
