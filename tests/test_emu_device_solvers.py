@@ -155,3 +155,41 @@ def test_3d_separable_stencil_with_folding_modes_padded_path(dev, monkeypatch):
     # the fixture's last axis has 7 samples (not a multiple of the vector width): that operator stays on the gather kernels
     op = cases.make_stencil(dev, case)
     assert GO.relerr(op.apply(gold["3d_sep_mixed/x"]), gold["3d_sep_mixed/apply"]) < 1e-12 and op._padded_ok is False
+
+
+def test_bench_usage_pattern(dev):
+    """What bench.py does with the solver: Mode.MANUAL + ManualStop with m_step() driven by hand and a probe around the fused
+    kernel (the kernel-only number), then fit(MaxIter | RelError) + solution() on host arrays (the end-to-end number)."""
+    from pyxu_b200.abc.solver import Mode
+
+    pxo, pxs, pxst = dev.operator, dev.solver, dev.stop
+    shape = (8, 16, 64)
+    N = int(np.prod(shape))
+    y = np.random.default_rng(0).random(N).astype(np.float32)
+    import torch
+
+    yt = torch.from_numpy(y.copy())
+    f = 0.5 * pxo.SquaredL2Norm(dim=N).argshift(-yt)
+    Kop = pxo.Gradient(arg_shape=shape, dtype=np.float32)
+    h = 0.08 * pxo.L21Norm(arg_shape=(3, *shape), l2_axis=(0,))
+    slv = pxs.PD3O(f=f, g=pxo.PositiveOrthant(dim=N), h=h, K=Kop, show_progress=False)
+    slv.fit(x0=yt, mode=Mode.MANUAL, stop_crit=pxst.ManualStop())
+    assert slv._plan.kind == "fused"
+    tags = []
+    slv._probe = tags.append
+    n0 = dev.lib.pxb_launch_count()
+    for _ in range(7):
+        slv.m_step()
+    assert dev.lib.pxb_launch_count() - n0 == 7 and tags == ["iter_begin", "iter_end"] * 7 and slv._plan.iter_ok is True
+    slv._probe = None
+    x_manual = slv._materialize("x").clone()
+    # end to end with host arrays
+    f2 = 0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y)
+    slv2 = pxs.PD3O(f=f2, g=pxo.PositiveOrthant(dim=N), h=h, K=Kop, show_progress=False, final_writeback=False)
+    slv2.fit(x0=y.copy(), stop_crit=pxst.MaxIter(7) | pxst.RelError(eps=1e-30, var="x"))
+    assert slv2._astate.get("error") is None and "_fused_norms" in slv2._mstate
+    x_host = slv2.solution()
+    _, hist = slv2.stats()
+    assert isinstance(x_host, np.ndarray) and x_host.dtype == np.float32 and len(hist) == 8 and np.isfinite(hist["RelError[x]"][1:]).all()
+    assert np.allclose(x_host, x_manual.numpy(), rtol=1e-6, atol=1e-7)
+    assert sum("Iteration" in ln for ln in open(slv2.logfile)) == 8
