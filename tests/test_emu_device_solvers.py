@@ -193,3 +193,16 @@ def test_bench_usage_pattern(dev):
     assert isinstance(x_host, np.ndarray) and x_host.dtype == np.float32 and len(hist) == 8 and np.isfinite(hist["RelError[x]"][1:]).all()
     assert np.allclose(x_host, x_manual.numpy(), rtol=1e-6, atol=1e-7)
     assert sum("Iteration" in ln for ln in open(slv2.logfile)) == 8
+
+
+def test_opt_in_gpu_tests_are_themselves_sound(dev, monkeypatch):
+    """The host-array tests of tests/test_gpu_zz_stencil_padded.py (skipped on a GPU box unless PYXU_B200_STENCIL_PADDED=1) run
+    here on the emulated device, so that the first GPU run of the padded path does not stumble over the tests."""
+    import test_gpu_zz_stencil_padded as GP
+    from pyxu_b200.operator.linop import stencil as st
+
+    monkeypatch.setattr(st, "PADDED_TILED", True)
+    for case in cases.STENCIL_CASES:
+        if case["mode"] != "constant" and case["arg_shape"][-1] % 2 == 0:
+            GP.test_padded_golden(case)
+    GP.test_cv_deblur_reflect_blur_uses_the_padded_path()
