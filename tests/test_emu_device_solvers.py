@@ -206,3 +206,32 @@ def test_opt_in_gpu_tests_are_themselves_sound(dev, monkeypatch):
         if case["mode"] != "constant" and case["arg_shape"][-1] % 2 == 0:
             GP.test_padded_golden(case)
     GP.test_cv_deblur_reflect_blur_uses_the_padded_path()
+
+
+def test_gpu_tests_of_the_folding_modes_replayed(dev, monkeypatch):
+    """tests/test_gpu_zz_iter_modes.py (single-kernel iteration with folding modes against the two-sweep kernels through the
+    C ABI, full tiles included) with its arrays on the emulated device: the kernels' bodies AND the test code are checked before
+    their next GPU run.  (The largest volume of the full-tile test is cut down here: the host replays every CTA.)"""
+    import types
+
+    import test_gpu_iter as GI
+    import test_gpu_zz_iter_modes as GM
+    from pyxu_b200 import _array as A
+    from pyxu_b200 import _cabi as K
+
+    monkeypatch.setattr(GI, "DEV", "cpu")
+    env = types.SimpleNamespace(operator=dev.operator, solver=dev.solver, stop=dev.stop, A=A, K=K, lib=dev.lib)
+    select = lambda p: K.check(dev.lib.pxb_set_iter_path(p), "pxb_set_iter_path")
+    real_gradient = dev.operator.Gradient
+
+    def small_gradient(arg_shape, **kw):  # 256 x 64 x 256 -> 24 x 64 x 256: same tiles per plane, fewer planes
+        return real_gradient(arg_shape=(24,) + tuple(arg_shape[1:]) if tuple(arg_shape) == (256, 64, 256) else arg_shape, **kw)
+
+    monkeypatch.setattr(dev.operator, "Gradient", small_gradient)
+    for mode in ("reflect", ("wrap", "reflect", "symmetric")):
+        GM.test_modes_full_tiles_3d_and_2d(env, mode, select)
+    monkeypatch.setattr(dev.operator, "Gradient", real_gradient)
+    GM.test_modes_vs_two_sweeps_3d(env, ("edge", "constant", "symmetric"), "tma", select)
+    GM.test_modes_vs_two_sweeps_2d_batched(env, ("reflect", "wrap"), "tile2d", select)
+    GM.test_modes_solver_fit_against_reference_fixtures(env, select)
+    dev.lib.pxb_set_iter_path(0)

@@ -18,6 +18,15 @@ from conftest import golden
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
+# Where the test arrays live.  "cuda" on a GPU box; tests/test_emu_device_solvers.py replays some of these functions on the
+# emulated device (tests/emu_device.py) with DEV = "cpu".
+DEV = "cuda"
+
+
+def _sync():
+    if DEV == "cuda":
+        torch.cuda.synchronize()
+
 
 @pytest.fixture(scope="module")
 def env():
@@ -63,26 +72,26 @@ def params(K, tau, sigma, rho, gspec, fkind, alpha, shift, garr, hkind, lam):
 def both_forms(env, algo, Kop, batch, dtype, P, seed=0, chunk=0, norms=True):
     """Runs one iteration in both forms from the same random state; returns ((u, z, x, nx, nz) two-sweep, same single-kernel)."""
     K, lib, A = env.K, env.lib, env.A
-    gen = torch.Generator(device="cuda").manual_seed(seed)
-    rnd = lambda *s: torch.randn(*s, device="cuda", dtype=dtype, generator=gen)
+    gen = torch.Generator(device=DEV).manual_seed(seed)
+    rnd = lambda *s: torch.randn(*s, device=DEV, dtype=dtype, generator=gen)
     d = Kop._desc(batch, K.F32 if dtype == torch.float32 else K.F64)
     u, x, z = rnd(batch, Kop.dim), rnd(batch, Kop.dim), rnd(batch, Kop.codim)
     st = A.stream()
     # two sweeps (in place)
     ua, xa, za, w = u.clone(), x.clone(), z.clone(), torch.empty_like(u)
-    na = torch.zeros((2, batch, 2), dtype=torch.float64, device="cuda")
+    na = torch.zeros((2, batch, 2), dtype=torch.float64, device=DEV)
     pd3o = algo == K.ALGO_PD3O
     K.check(lib.pxb_pds_primal(algo, C.byref(d), C.byref(P), ua.data_ptr(), za.data_ptr(), None, xa.data_ptr() if pd3o else None, w.data_ptr(),
                                na[0].data_ptr() if norms else None, st), "primal")
     K.check(lib.pxb_pds_dual(C.byref(d), C.byref(P), w.data_ptr(), za.data_ptr(), na[1].data_ptr() if norms else None, st), "dual")
     # one sweep (out of place)
     ub, zb, xb = torch.full_like(u, float("nan")), torch.full_like(z, float("nan")), x.clone()
-    nb = torch.zeros((2, batch, 2), dtype=torch.float64, device="cuda")
+    nb = torch.zeros((2, batch, 2), dtype=torch.float64, device=DEV)
     args = (algo, C.byref(d), C.byref(P), u.data_ptr(), z.data_ptr(), ub.data_ptr(), zb.data_ptr(), xb.data_ptr() if pd3o else None,
             nb[0].data_ptr() if norms else None, nb[1].data_ptr() if norms else None)
     rc = lib.pxb_pds_iter_chunked(*args, chunk, st) if chunk else lib.pxb_pds_iter(*args, st)
     K.check(rc, "pxb_pds_iter")
-    torch.cuda.synchronize()
+    _sync()
     return (ua, za, xa, na), (ub, zb, xb, nb)
 
 
@@ -104,7 +113,7 @@ def test_iter_vs_two_sweeps_3d(env, scheme, dtype, form, iter_path):
     vec = 4 if dtype == torch.float32 else 2
     shape = (21, 19, 32 * vec * 2 + 3 * vec)  # 3 row tiles (ragged), 3 column tiles (ragged)
     Kop = env.operator.Gradient(arg_shape=shape, scheme=scheme, sampling=(1.0, 0.5, 2.0), dtype=np.float32 if dtype == torch.float32 else np.float64)
-    shift = torch.randn(Kop.dim, device="cuda", dtype=dtype)
+    shift = torch.randn(Kop.dim, device=DEV, dtype=dtype)
     tol = 1e-13 if dtype == torch.float64 else 2e-6
     for algo in (K.ALGO_PD3O, K.ALGO_CV):
         for hkind, gspec in ((K.DUAL_L21, (K.PROX_POS, 0.0, 0.0)), (K.DUAL_L1, (K.PROX_BOX, 0.2, 0.9))):
@@ -121,7 +130,7 @@ def test_iter_vs_two_sweeps_2d_batched(env, scheme, width, form, iter_path):
     K = env.K
     iter_path(1 if form == "direct" else 2)  # 2: TMA-staged 2-D tiles (pxb_tv_tile2d.cu)
     Kop = env.operator.Gradient(arg_shape=(37, width), scheme=scheme, dtype=np.float32)
-    shift = torch.randn(Kop.dim, device="cuda", dtype=torch.float32)  # one image: broadcast over the batch
+    shift = torch.randn(Kop.dim, device=DEV, dtype=torch.float32)  # one image: broadcast over the batch
     P = params(K, 0.3, 0.25, 1.0, (K.PROX_L1, 0.05, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L21, 0.2)
     for algo in (K.ALGO_PD3O, K.ALGO_CV):
         for chunk in ((0, 4) if form == "direct" else (0,)):
@@ -134,12 +143,12 @@ def test_iter_cv_gradarr_stacked(env, form, iter_path):
     K = env.K
     iter_path(1 if form == "direct" else 2)
     Kop = env.operator.Gradient(arg_shape=(3, 33, 24), directions=(1, 2))
-    garr = torch.randn(2, Kop.dim, device="cuda", dtype=torch.float64)
+    garr = torch.randn(2, Kop.dim, device=DEV, dtype=torch.float64)
     P = params(K, 0.3, 0.25, 0.8, (K.PROX_POS, 0.0, 0.0), K.F_GRADARR, 0.0, None, garr, K.DUAL_L21, 0.2)
     a, b = both_forms(env, K.ALGO_CV, Kop, 2, torch.float64, P, chunk=7 if form == "direct" else 0)
     assert_same(env, K.ALGO_CV, a, b, 1e-13)
     # a volume-shaped shift broadcast over the batch (PD3O), fp64
-    shift = torch.randn(Kop.dim, device="cuda", dtype=torch.float64)
+    shift = torch.randn(Kop.dim, device=DEV, dtype=torch.float64)
     P = params(K, 0.3, 0.25, 0.8, (K.PROX_POS, 0.0, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L1, 0.2)
     a, b = both_forms(env, K.ALGO_PD3O, Kop, 2, torch.float64, P)
     assert_same(env, K.ALGO_PD3O, a, b, 1e-13)
@@ -150,7 +159,7 @@ def test_iter_envelope_errors(env):
     Kop = env.operator.Gradient(arg_shape=(8, 16), mode="reflect")
     d = Kop._desc(1, K.F64)
     P = params(K, 0.3, 0.25, 1.0, (K.PROX_NONE, 0.0, 0.0), K.F_NONE, 0.0, None, None, K.DUAL_L21, 0.2)
-    u, z = torch.zeros(Kop.dim, device="cuda", dtype=torch.float64), torch.zeros(Kop.codim, device="cuda", dtype=torch.float64)
+    u, z = torch.zeros(Kop.dim, device=DEV, dtype=torch.float64), torch.zeros(Kop.codim, device=DEV, dtype=torch.float64)
     u2, z2 = u.clone(), z.clone()
     n0 = lib.pxb_launch_count()
     K.check(lib.pxb_set_iter_modes(0), "pxb_set_iter_modes")  # folding modes declined: callers take the two-sweep form
@@ -169,14 +178,14 @@ def test_tma_form_batched_shift_modes(env, scheme, iter_path):
     K = env.K
     iter_path(2)
     Kop = env.operator.Gradient(arg_shape=(9, 21, 136), scheme=scheme, dtype=np.float32)
-    gen = torch.Generator(device="cuda").manual_seed(3)
+    gen = torch.Generator(device=DEV).manual_seed(3)
     for shape in ((Kop.dim,), (3, Kop.dim), (1,)):
-        shift = torch.randn(*shape, device="cuda", dtype=torch.float32, generator=gen)
+        shift = torch.randn(*shape, device=DEV, dtype=torch.float32, generator=gen)
         P = params(K, 0.21, 0.19, 0.9, (K.PROX_POS, 0.0, 0.0), K.F_SQL2, 0.7, shift, None, K.DUAL_L21, 0.3)
         for algo in (K.ALGO_PD3O, K.ALGO_CV):
             a, b = both_forms(env, algo, Kop, 3, torch.float32, P, seed=len(shape), chunk=4)
             assert_same(env, algo, a, b, 2e-6)
-    garr = torch.randn(3, Kop.dim, device="cuda", dtype=torch.float32, generator=gen)
+    garr = torch.randn(3, Kop.dim, device=DEV, dtype=torch.float32, generator=gen)
     P = params(K, 0.3, 0.25, 0.8, (K.PROX_L1, 0.1, 0.0), K.F_GRADARR, 0.0, None, garr, K.DUAL_L1, 0.2)
     a, b = both_forms(env, K.ALGO_CV, Kop, 3, torch.float32, P)
     assert_same(env, K.ALGO_CV, a, b, 2e-6)
@@ -188,7 +197,7 @@ def test_iter_large_volume_properties(env, form, iter_path):
     K = env.K
     iter_path(1 if form == "direct" else 2)
     Kop = env.operator.Gradient(arg_shape=(256, 256, 256), dtype=np.float32)
-    shift = torch.randn(Kop.dim, device="cuda", dtype=torch.float32)
+    shift = torch.randn(Kop.dim, device=DEV, dtype=torch.float32)
     P = params(K, 0.28, 0.28, 1.0, (K.PROX_POS, 0.0, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L21, 0.08)
     a, b = both_forms(env, K.ALGO_PD3O, Kop, 1, torch.float32, P, seed=1)
     assert_same(env, K.ALGO_PD3O, a, b, 2e-6)
@@ -255,12 +264,12 @@ def test_solver_fp32_tolerance_256cube_vs_oracle_property(env):
 
 def test_large_results_leave_the_device_through_the_pipelined_copy(env):
     """HOST-origin results above 64 MiB: chunked D2H through pinned staging buffers == plain .cpu()."""
-    gen = torch.Generator(device="cuda").manual_seed(5)
+    gen = torch.Generator(device=DEV).manual_seed(5)
     for dt, n in ((torch.float32, (70 << 20) // 4 + 12345), (torch.float64, (97 << 20) // 8 + 1)):
-        t = torch.randn(n, device="cuda", dtype=dt, generator=gen)
+        t = torch.randn(n, device=DEV, dtype=dt, generator=gen)
         out = env.A.restore(t, env.A.HOST)
         assert isinstance(out, np.ndarray) and out.shape == (n,) and np.array_equal(out, t.cpu().numpy())
-    t2 = torch.randn(3, (80 << 20) // 12, device="cuda", generator=gen)
+    t2 = torch.randn(3, (80 << 20) // 12, device=DEV, generator=gen)
     assert np.array_equal(env.A.restore(t2, env.A.HOST), t2.cpu().numpy())
     # and the way in: a pageable NumPy array above 64 MiB goes through the pinned staging buffers
     rng = np.random.default_rng(0)
@@ -289,7 +298,7 @@ def test_iter_random_small_shapes(env, form, iter_path):
         batch = int(rng.integers(1, 4))
         Kop = env.operator.Gradient(arg_shape=shape, scheme=schemes[trial % 3], dtype=np.float64 if dtype == torch.float64 else np.float32,
                                     sampling=float(rng.uniform(0.5, 2.0)))
-        shift = torch.randn(Kop.dim if trial % 4 else batch * Kop.dim, device="cuda", dtype=dtype)
+        shift = torch.randn(Kop.dim if trial % 4 else batch * Kop.dim, device=DEV, dtype=dtype)
         gspec = [(K.PROX_POS, 0.0, 0.0), (K.PROX_NONE, 0.0, 0.0), (K.PROX_L1, 0.05, 0.0)][trial % 3]
         P = params(K, 0.21, 0.19, float(rng.uniform(0.7, 1.3)), gspec, K.F_SQL2, 0.5, shift, None, K.DUAL_L21 if trial % 5 else K.DUAL_L1, 0.3)
         algo = K.ALGO_PD3O if trial % 2 == 0 else K.ALGO_CV

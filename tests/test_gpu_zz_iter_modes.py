@@ -13,6 +13,7 @@ import pytest
 
 import cases
 from conftest import golden
+import test_gpu_iter as GI
 from test_gpu_iter import assert_same, both_forms, env, params  # noqa: F401  (env is a fixture)
 
 pytestmark = pytest.mark.gpu
@@ -41,7 +42,7 @@ def test_modes_vs_two_sweeps_3d(env, mode, form, modes_on):
         for scheme in ("forward", "backward", "central"):
             Kop = env.operator.Gradient(arg_shape=shape, scheme=scheme, mode=mode, sampling=(1.0, 0.5, 2.0),
                                         dtype=np.float32 if dtype == torch.float32 else np.float64)
-            shift = torch.randn(Kop.dim, device="cuda", dtype=dtype)
+            shift = torch.randn(Kop.dim, device=GI.DEV, dtype=dtype)
             for algo, hkind, gspec in ((K.ALGO_PD3O, K.DUAL_L21, (K.PROX_POS, 0.0, 0.0)), (K.ALGO_CV, K.DUAL_L1, (K.PROX_BOX, 0.2, 0.9))):
                 P = params(K, 0.21, 0.19, 0.9, gspec, K.F_SQL2, 0.7, shift, None, hkind, 0.3)
                 for chunk in (0, 5):
@@ -58,8 +59,8 @@ def test_modes_vs_two_sweeps_2d_batched(env, mode, form, modes_on):
         tol = 1e-13 if dtype == torch.float64 else 2e-6
         for scheme in ("forward", "backward", "central"):
             Kop = env.operator.Gradient(arg_shape=shape, scheme=scheme, mode=mode, dtype=np.float32 if dtype == torch.float32 else np.float64)
-            shift = torch.randn(batch, Kop.dim, device="cuda", dtype=dtype)
-            garr = torch.randn(batch, Kop.dim, device="cuda", dtype=dtype)
+            shift = torch.randn(batch, Kop.dim, device=GI.DEV, dtype=dtype)
+            garr = torch.randn(batch, Kop.dim, device=GI.DEV, dtype=dtype)
             P = params(K, 0.3, 0.25, 0.95, (K.PROX_L1, 0.05, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L21, 0.2)
             for algo in (K.ALGO_PD3O, K.ALGO_CV):
                 a, b = both_forms(env, algo, Kop, batch, dtype, P, seed=3)
@@ -77,7 +78,7 @@ def test_modes_full_tiles_3d_and_2d(env, mode, modes_on):
     modes_on(2)
     for dtype, shape in ((torch.float32, (16, 32, 256)), (torch.float64, (9, 16, 128)), (torch.float32, (256, 64, 256))):
         Kop = env.operator.Gradient(arg_shape=shape, mode=mode, dtype=np.float32 if dtype == torch.float32 else np.float64)
-        shift = torch.randn(Kop.dim, device="cuda", dtype=dtype)
+        shift = torch.randn(Kop.dim, device=GI.DEV, dtype=dtype)
         P = params(K, 0.21, 0.19, 0.9, (K.PROX_POS, 0.0, 0.0), K.F_SQL2, 0.7, shift, None, K.DUAL_L21, 0.3)
         for algo in (K.ALGO_PD3O, K.ALGO_CV):
             a, b = both_forms(env, algo, Kop, 1, dtype, P, seed=5)
@@ -85,7 +86,7 @@ def test_modes_full_tiles_3d_and_2d(env, mode, modes_on):
     mode2 = mode if isinstance(mode, str) else mode[1:]
     for dtype, shape, batch in ((torch.float32, (64, 512), 2), (torch.float64, (32, 128), 1)):
         Kop = env.operator.Gradient(arg_shape=shape, mode=mode2, dtype=np.float32 if dtype == torch.float32 else np.float64)
-        shift = torch.randn(batch, Kop.dim, device="cuda", dtype=dtype)
+        shift = torch.randn(batch, Kop.dim, device=GI.DEV, dtype=dtype)
         P = params(K, 0.3, 0.25, 0.95, (K.PROX_L1, 0.05, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L21, 0.2)
         for algo in (K.ALGO_PD3O, K.ALGO_CV):
             a, b = both_forms(env, algo, Kop, batch, dtype, P, seed=6)
