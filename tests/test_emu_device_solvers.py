@@ -202,10 +202,16 @@ def test_opt_in_gpu_tests_are_themselves_sound(dev, monkeypatch):
     from pyxu_b200.operator.linop import stencil as st
 
     monkeypatch.setattr(st, "PADDED_TILED", True)
+    monkeypatch.setattr(GP, "DEV", "cpu")
     for case in cases.STENCIL_CASES:
         if case["mode"] != "constant" and case["arg_shape"][-1] % 2 == 0:
             GP.test_padded_golden(case)
     GP.test_cv_deblur_reflect_blur_uses_the_padded_path()
+    small = [((37, 68), k, c, m) if len(sh) == 2 else ((sh[0], 18, 40) if len(sh) == 3 else sh, k, c, m) for sh, k, c, m in GP.CASES]
+    monkeypatch.setattr(GP, "CASES", small)  # same operators on smaller arrays: the host replays every CTA
+    for ci in range(len(small)):
+        for dtype in (np.float64, np.float32):
+            GP.test_padded_vs_generic(ci, dtype)
 
 
 def test_gpu_tests_of_the_folding_modes_replayed(dev, monkeypatch):

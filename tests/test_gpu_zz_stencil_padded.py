@@ -19,6 +19,7 @@ from conftest import golden
 
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="opt-in path, CPU-verified only: first GPU run")]
 torch = pytest.importorskip("torch")
+DEV = "cuda"  # tests/test_emu_device_solvers.py replays these functions on the emulated device with DEV = "cpu"
 
 
 @pytest.fixture(autouse=True)
@@ -61,9 +62,9 @@ def test_padded_vs_generic(ci, dtype):
     op = pxo.Stencil(arg_shape=shape, kernel=k, center=cen, mode=mode)
     generic = pxo.Stencil(arg_shape=shape, kernel=k, center=cen, mode=mode)
     generic._padded_ok = False
-    gen = torch.Generator(device="cuda").manual_seed(ci)
-    x = torch.randn(3, op.dim, device="cuda", dtype=torch.float64 if dtype == np.float64 else torch.float32, generator=gen)
-    y = torch.randn(3, op.dim, device="cuda", dtype=x.dtype, generator=gen)
+    gen = torch.Generator(device=DEV).manual_seed(ci)
+    x = torch.randn(3, op.dim, device=DEV, dtype=torch.float64 if dtype == np.float64 else torch.float32, generator=gen)
+    y = torch.randn(3, op.dim, device=DEV, dtype=x.dtype, generator=gen)
     tol = 1e-13 if dtype == np.float64 else 3e-6
     for adj in (False, True):
         a = op.adjoint(x) if adj else op.apply(x)
