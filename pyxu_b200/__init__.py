@@ -14,3 +14,4 @@ __version__ = "0.1.0"
 
 from . import abc, operator, opt  # noqa: F401,E402
 from ._cabi import NativeLibraryError  # noqa: F401,E402
+from ._array import release_host_results, reserve_host_results  # noqa: F401,E402

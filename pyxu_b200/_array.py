@@ -14,6 +14,7 @@ PyTorch is only the allocator / stream / DLPack provider here; all arithmetic go
 C ABI (pyxu_b200._cabi).
 """
 import ctypes as C
+import threading
 
 import numpy as np
 import torch
@@ -68,19 +69,38 @@ def asdevice(arr, dtype=None):
 
 _BIG = 64 << 20      # results above this size leave the device through the pipelined path
 _CHUNK = 64 << 20     # bytes per staging buffer (measured on the B200 host: 64 MiB x 12 threads -> ~30 GB/s, .cpu(): 2.2 GB/s)
+_NSTAGE = 3
 _STAGE = None         # pinned staging buffers (allocated once, on first use)
+_STAGE_EVENTS = [None] * _NSTAGE   # last device-side use of each staging buffer (a copy that reads or writes it)
+_STAGE_LOCK = threading.Lock()     # the staging buffers are process-wide: one staged copy at a time (ASYNC-mode workers included)
+
+
+def _staging():
+    """The pinned staging buffers; before a host thread touches buffer k again, the last copy that used it must be over
+    (`_stage_free(k)`) -- also across calls: a staged upload returns with its last copies still in flight on the copy stream."""
+    global _STAGE
+    if _STAGE is None or _STAGE[0].numel() != _CHUNK:
+        _STAGE = [torch.empty(_CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(_NSTAGE)]
+    return _STAGE
+
+
+def _stage_free(k):
+    ev = _STAGE_EVENTS[k]
+    if ev is not None:
+        ev.synchronize()
+        _STAGE_EVENTS[k] = None
 
 
 def _copy_threads():
     """Host threads of the staged copies: 3/4 of the cores, shared between the ranks of this node (torchrun sets
-    LOCAL_WORLD_SIZE), at most 12; PXB_D2H_THREADS overrides."""
+    LOCAL_WORLD_SIZE), at least 4 (the copies of different ranks rarely coincide), at most 12; PXB_D2H_THREADS overrides."""
     import os
 
     forced = int(os.environ.get("PXB_D2H_THREADS", 0))
     if forced > 0:
         return forced
     ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-    return max(1, min(12, (os.cpu_count() or 2) * 3 // 4 // ranks))
+    return max(4, min(12, (os.cpu_count() or 2) * 3 // 4 // ranks))
 
 
 def _advise_hugepages(arr):
@@ -97,16 +117,57 @@ def _advise_hugepages(arr):
         pass
 
 
+# -- reserved pinned result buffers ---------------------------------------------------------------------------------
+# A result that lands in pinned memory leaves the device at PCIe speed (measured: 57 GB/s against ~30 GB/s through the
+# staging buffers into fresh pageable memory), but pinning is slow (cudaHostAlloc: ~2.4 GB/s), so it only pays when the
+# buffer is reused: `reserve_host_results(nbytes)` pins result buffers ahead of time (a serving loop does it once);
+# restore() hands them out as NumPy arrays and takes them back when the array is garbage-collected.
+_RESULT_POOL = {}   # nbytes -> [free pinned uint8 tensors]
+_POOL_LOCK = threading.Lock()
+
+
+def reserve_host_results(nbytes, count=1):
+    """Pin `count` host buffers of `nbytes` for results of that size (solution() / stats() of host-array solves)."""
+    nbytes = int(nbytes)
+    bufs = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(int(count))]
+    with _POOL_LOCK:
+        _RESULT_POOL.setdefault(nbytes, []).extend(bufs)
+
+
+def release_host_results():
+    with _POOL_LOCK:
+        _RESULT_POOL.clear()
+
+
+def _give_back(nbytes, buf):
+    with _POOL_LOCK:
+        if nbytes in _RESULT_POOL:
+            _RESULT_POOL[nbytes].append(buf)
+
+
+def _d2h_reserved(t):
+    """Device tensor -> NumPy array backed by a reserved pinned buffer (None when no free buffer of that size exists)."""
+    import weakref
+
+    nbytes = t.numel() * t.element_size()
+    with _POOL_LOCK:
+        free = _RESULT_POOL.get(nbytes)
+        buf = free.pop() if free else None
+    if buf is None:
+        return None
+    buf.view(t.dtype).copy_(t.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out = buf.numpy().view(np_dtype(t.dtype)).reshape(tuple(t.shape))
+    weakref.finalize(out, _give_back, nbytes, buf)  # views keep `out` alive through .base
+    return out
+
+
 def _d2h_pipelined(t):
     """Device -> pageable host array at PCIe speed: chunks travel into pinned staging buffers on a copy stream while
     a few host threads move the previous chunk into the result (first-touch faults spread over the threads)."""
-    import os
     from concurrent.futures import ThreadPoolExecutor
 
-    global _STAGE
-    nb = 3
-    if _STAGE is None or _STAGE[0].numel() != _CHUNK:
-        _STAGE = [torch.empty(_CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(nb)]
+    nb = _NSTAGE
     flat = t.reshape(-1).view(torch.uint8)
     nbytes = flat.numel()
     out = np.empty(t.numel(), dtype=np_dtype(t.dtype))
@@ -121,21 +182,23 @@ def _d2h_pipelined(t):
     def move(buf, lo, hi, a, b):  # staging[a:b] -> out[lo+a : lo+b]
         np.copyto(out_b[lo + a : lo + b], buf[a:b])
 
-    with ThreadPoolExecutor(nthreads) as pool:
+    with _STAGE_LOCK, ThreadPoolExecutor(nthreads) as pool:
+        stage = _staging()
         for k in range(nchunks + 1):
             if k < nchunks:
                 for f in futures[k % nb]:
                     f.result()  # the buffer's previous content has been copied out
+                _stage_free(k % nb)  # (an earlier staged upload may still be reading it)
                 lo, hi = k * _CHUNK, min(nbytes, (k + 1) * _CHUNK)
                 with torch.cuda.stream(copy_stream):
-                    _STAGE[k % nb][: hi - lo].copy_(flat[lo:hi], non_blocking=True)
+                    stage[k % nb][: hi - lo].copy_(flat[lo:hi], non_blocking=True)
                     events[k] = torch.cuda.Event()
                     events[k].record()
             if k >= 1:
                 j = k - 1
                 events[j].synchronize()
                 lo, hi = j * _CHUNK, min(nbytes, (j + 1) * _CHUNK)
-                buf = _STAGE[j % nb].numpy()
+                buf = stage[j % nb].numpy()
                 step = -(-(hi - lo) // nthreads)
                 futures[j % nb] = [pool.submit(move, buf, lo, hi, a, min(hi - lo, a + step)) for a in range(0, hi - lo, step)]
         for fs in futures:
@@ -148,13 +211,9 @@ def _d2h_pipelined(t):
 def _h2d_pipelined(arr, want):
     """Pageable NumPy array -> device tensor: host threads copy chunks into pinned staging buffers while the previous
     chunk's async H2D copy is in flight (a plain .to(device) of pageable memory goes through one bounce buffer)."""
-    import os
     from concurrent.futures import ThreadPoolExecutor
 
-    global _STAGE
-    nb = 3
-    if _STAGE is None or _STAGE[0].numel() != _CHUNK:
-        _STAGE = [torch.empty(_CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(nb)]
+    nb = _NSTAGE
     src = np.ascontiguousarray(arr).reshape(-1).view(np.uint8)
     nbytes = src.size
     out = torch.empty(arr.shape, dtype=torch_dtype(arr.dtype), device=current_device())
@@ -162,24 +221,25 @@ def _h2d_pipelined(arr, want):
     nthreads = _copy_threads()
     copy_stream = torch.cuda.Stream(device=out.device)
     nchunks = (nbytes + _CHUNK - 1) // _CHUNK
-    events = [None] * nb
 
     def move(buf, lo, a, b):
         np.copyto(buf[a:b], src[lo + a : lo + b])
 
-    with ThreadPoolExecutor(nthreads) as pool:
+    with _STAGE_LOCK, ThreadPoolExecutor(nthreads) as pool:
+        stage = _staging()
         for k in range(nchunks):
             lo, hi = k * _CHUNK, min(nbytes, (k + 1) * _CHUNK)
-            if events[k % nb] is not None:
-                events[k % nb].synchronize()  # the staging buffer's previous H2D copy has completed
-            buf = _STAGE[k % nb].numpy()
+            _stage_free(k % nb)  # the staging buffer's previous copy (of this call or an earlier one) has completed
+            buf = stage[k % nb].numpy()
             step = -(-(hi - lo) // nthreads)
             for f in [pool.submit(move, buf, lo, a, min(hi - lo, a + step)) for a in range(0, hi - lo, step)]:
                 f.result()
             with torch.cuda.stream(copy_stream):
-                flat[lo:hi].copy_(_STAGE[k % nb][: hi - lo], non_blocking=True)
-                events[k % nb] = torch.cuda.Event()
-                events[k % nb].record()
+                flat[lo:hi].copy_(stage[k % nb][: hi - lo], non_blocking=True)
+                _STAGE_EVENTS[k % nb] = torch.cuda.Event()
+                _STAGE_EVENTS[k % nb].record()
+    # the last copies are still in flight: their events stay in _STAGE_EVENTS, which every later user of a staging
+    # buffer waits on before a host thread writes into it again
     torch.cuda.current_stream().wait_stream(copy_stream)
     return out if out.dtype == want else out.to(want)
 
@@ -187,8 +247,13 @@ def _h2d_pipelined(arr, want):
 def restore(t, origin):
     """Give a result back in the caller's memory space."""
     if origin == HOST:
-        if t.is_cuda and t.is_contiguous() and t.numel() * t.element_size() >= _BIG and t.dtype in (torch.float32, torch.float64):
-            return _d2h_pipelined(t)
+        if t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.float64):
+            if _RESULT_POOL:
+                out = _d2h_reserved(t)
+                if out is not None:
+                    return out
+            if t.numel() * t.element_size() >= _BIG:
+                return _d2h_pipelined(t)
         return t.cpu().numpy()
     return t
 

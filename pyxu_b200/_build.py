@@ -1,8 +1,10 @@
 """
-In-tree build of libpyxu_b200.so with nvcc for sm_100a (and of the test-only helpers).
+In-tree build of libpyxu_b200.so with nvcc for sm_100a.
 
     python -m pyxu_b200._build            # build the CUDA library
-    python -m pyxu_b200._build --all      # + oracle C helper + host emulation used by CPU tests
+
+(The checker's helpers -- the oracle's C port, the staged reference, the host emulation of the kernel bodies -- are built by
+oracle/build.py and tests/emu/build.py: the package names nothing under oracle/ or tests/.)
 """
 import os
 import shutil
@@ -61,28 +63,5 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 
-def build_emu(force=False):
-    """Host build of the per-voxel kernel bodies (tests/emu): CPU test infrastructure only."""
-    src = os.path.join(ROOT, "tests", "emu", "pxb_emu.cpp")
-    out = os.path.join(ROOT, "tests", "emu", "libpxb_emu.so")
-    deps = [src, os.path.join(ROOT, "include", "pyxu_b200.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
-    if force or _newer(out, deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", out, src], check=True)
-    return out
-
-
-def build_oracle(force=False):
-    """C restatement used as the multi-threaded CPU baseline (oracle/): test/bench infrastructure only."""
-    src = os.path.join(ROOT, "oracle", "tv_oracle.c")
-    out = os.path.join(ROOT, "oracle", "libtv_oracle.so")
-    if not os.path.exists(src):
-        return None
-    if force or _newer(out, [src]):
-        subprocess.run(["gcc", "-O3", "-march=x86-64-v2", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"], check=True)
-    return out
-
-
 if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
-    if "--all" in sys.argv:
-        print(build_emu(), build_oracle())

@@ -58,6 +58,10 @@ class StoppingCriterion:
     def _state_vars(self):
         return None
 
+    # True when the decision can differ between the ranks of a z-slab decomposed solve (e.g. a wall-clock limit)
+    def _rank_local(self):
+        return False
+
 
 class _Composition(StoppingCriterion):
     def __init__(self, lhs, rhs, op):
@@ -83,6 +87,38 @@ class _Composition(StoppingCriterion):
         a, b = self._lhs._state_vars(), self._rhs._state_vars()
         return None if (a is None or b is None) else (a | b)
 
+    def _rank_local(self):
+        return self._lhs._rank_local() or self._rhs._rank_local()
+
+
+def _workdir(folder, exist_ok):
+    """The solver's scratch directory: a fresh temporary one, or `folder` (emptied; refused when it exists unless exist_ok)."""
+    if folder is None:
+        return plib.Path(tempfile.mkdtemp(prefix="pyxu_"))
+    try:
+        path = plib.Path(folder).expanduser().resolve()
+    except TypeError:
+        raise TypeError(f"folder: a path is expected, not {type(folder).__name__}") from None
+    if path.exists() and not exist_ok:
+        raise FileExistsError(f"{path} already exists.")
+    shutil.rmtree(path, ignore_errors=True)
+    path.mkdir(parents=True)
+    return path
+
+
+def _rate(name, value, base, default=None):
+    """A logging / checkpoint period: a positive integer that is a multiple of `base` (stop_rate), or `default` when None."""
+    if value is None:
+        return default
+    try:
+        ok = value >= 1 and int(value) == value and int(value) % base == 0
+    except TypeError:
+        ok = False
+    if not ok:
+        what = "a positive integer" if base == 1 else f"a positive multiple of stop_rate ({base})"
+        raise ValueError(f"{name}: {what} is expected, got {value!r}")
+    return int(value)
+
 
 class Solver:
     def __init__(self, *, folder=None, exist_ok=False, stop_rate=1, writeback_rate=None, verbosity=None,
@@ -95,56 +131,38 @@ class Solver:
         self._astate = dict(history=None, idx=0, log_rate=None, log_var=None, logger=None, stdout=None, stop_crit=None,
                             stop_rate=None, track_objective=None, wb_rate=None, workdir=None, mode=None, active=None,
                             worker=None, origin=A.DEVICE)
+        ast = self._astate
+        ast["workdir"] = _workdir(folder, exist_ok)
+        ast["stop_rate"] = _rate("stop_rate", stop_rate, 1)
+        if ast["stop_rate"] is None:
+            raise ValueError("stop_rate: a positive integer is expected, got None")
+        ast["wb_rate"] = _rate("writeback_rate", writeback_rate, ast["stop_rate"])
+        ast["log_rate"] = _rate("verbosity", verbosity, ast["stop_rate"], default=ast["stop_rate"])
+        ast["stdout"] = bool(show_progress)
+        if isinstance(log_var, str):
+            log_var = (log_var,)
         try:
-            if folder is None:
-                folder = plib.Path(tempfile.mkdtemp(prefix="pyxu_"))
-            elif (folder := plib.Path(folder).expanduser().resolve()).exists() and (not exist_ok):
-                raise FileExistsError(f"{folder} already exists.")
-            else:
-                shutil.rmtree(folder, ignore_errors=True)
-                folder.mkdir(parents=True)
-            self._astate["workdir"] = folder
-        except FileExistsError:
-            raise
-        except Exception:
-            raise Exception(f"folder: expected path-like, got {type(folder)}.")
-
-        try:
-            assert stop_rate >= 1
-            self._astate["stop_rate"] = int(stop_rate)
-        except Exception:
-            raise ValueError(f"stop_rate must be positive, got {stop_rate}.")
-        try:
-            self._astate["wb_rate"] = writeback_rate
-            if writeback_rate is not None:
-                assert writeback_rate % self._astate["stop_rate"] == 0
-                self._astate["wb_rate"] = int(writeback_rate)
-        except Exception:
-            raise ValueError(f"writeback_rate must be a multiple of stop_rate({stop_rate}), got {writeback_rate}.")
-        try:
-            if verbosity is None:
-                verbosity = self._astate["stop_rate"]
-            assert verbosity % self._astate["stop_rate"] == 0
-            self._astate["log_rate"] = int(verbosity)
-            self._astate["stdout"] = bool(show_progress)
-        except Exception:
-            raise ValueError(f"verbosity must be a multiple of stop_rate({stop_rate}), got {verbosity}.")
-        try:
-            if isinstance(log_var, str):
-                log_var = (log_var,)
-            self._astate["log_var"] = frozenset(log_var)
-        except Exception:
-            raise ValueError(f"log_var: expected collection, got {type(log_var)}.")
+            ast["log_var"] = frozenset(log_var)
+        except TypeError:
+            raise ValueError(f"log_var: a collection of variable names is expected, got {type(log_var).__name__}") from None
 
     # -- user API ---------------------------------------------------------------------------
     def fit(self, **kwargs):
+        import time
+
+        t0 = time.perf_counter()
         self._fit_init(
             mode=kwargs.pop("mode", Mode.BLOCK),
             stop_crit=kwargs.pop("stop_crit", None),
             track_objective=kwargs.pop("track_objective", False),
         )
+        t1 = time.perf_counter()
         self.m_init(**kwargs)
+        t2 = time.perf_counter()
         self._fit_run()
+        # host-side wall clock of the three phases (the device may still be working when BLOCK mode returns with a
+        # criterion that never synchronises); bench.py reports it as the end-to-end breakdown
+        self._astate["timing"] = dict(setup_s=t1 - t0, m_init_s=t2 - t1, run_s=time.perf_counter() - t2)
 
     def m_init(self, **kwargs):
         raise NotImplementedError
@@ -182,7 +200,9 @@ class Solver:
         history = self._astate["history"]
         if history is not None:
             history = np.concatenate(history, dtype=history[0].dtype, axis=0) if len(history) > 0 else None
-        data = {k: self._logged(k) for k in self._astate["log_var"]}
+        # (sorted: under a z-slab decomposition every variable is a collective gather, and the iteration order of a
+        # frozenset of strings differs between the ranks' interpreters)
+        data = {k: self._logged(k) for k in sorted(self._astate["log_var"])}
         return data, history
 
     @property
@@ -217,6 +237,7 @@ class Solver:
         for k, v in dict(history=history, **data).items():
             if v is None:
                 continue
+            v = getattr(v, "local", v)  # a ShardedArray: every rank dumps its own planes
             kwargs[k] = v.cpu().numpy() if hasattr(v, "is_cuda") else np.asarray(v)
         np.savez(self.datafile, **kwargs)
 
@@ -285,69 +306,75 @@ class Solver:
         raise ValueError(msg)
 
     def _step(self):
+        """One turn of the loop (reference: solver.py:588-667): test the criterion on the current state, log, checkpoint,
+        then iterate.  Returns False once the criterion is met or an exception was raised (kept in _astate["error"])."""
         ast = self._astate
-        must_stop = ast["idx"] % ast["stop_rate"] == 0
-        must_log = ast["idx"] % ast["log_rate"] == 0
-        must_wb = (ast["wb_rate"] is not None) and (ast["idx"] % ast["wb_rate"] == 0)
-
-        def _log(msg=None):
-            if msg is None:
-                if not ast.get("live_log"):
-                    # The per-iteration record goes to the log FILE only: keep (time, record) and render the same text in
-                    # batches (Python's logging costs ~100 us per record -- more than an iteration of a small problem takes
-                    # on the GPU).  Nothing is lost: the batch is written before any other message, at the latest every
-                    # second / 256 records, on stop, on error and on cleanup.
-                    pend = ast.setdefault("pending_log", [])
-                    pend.append((dt.datetime.now(), ast["idx"], ast["history"][-1][0]))
-                    if len(pend) >= 256 or (pend[-1][0] - pend[0][0]).total_seconds() > 1.0:
-                        self._flush_log()
-                    return
-                msg = self._render_iteration(dt.datetime.now(), ast["idx"], ast["history"][-1][0])
-            else:
-                self._flush_log()
-            ast["logger"].info(msg)
-
-        def _update_history():
-            data = ast["stop_crit"].info()
-            keys = tuple(data)
-            cache = ast.get("history_dtype")
-            if cache is None or cache[0] != keys:  # the fields never change during a fit(): build the record type once
-                cache = ast["history_dtype"] = (keys, np.dtype([("iteration", np.int64)] + [(k, np.float64) for k in keys]))
-            rec = np.zeros(1, dtype=cache[1])
-            rec["iteration"] = ast["idx"]
-            for k, v in data.items():
-                rec[k] = v
-            ast["history"].append(rec)
-
+        idx = ast["idx"]
+        on_stop_beat = idx % ast["stop_rate"] == 0
         try:
-            if must_stop and ast["track_objective"]:
-                self._mstate["objective_func"] = self.objective_func().reshape(-1)
-            if must_stop and ast["stop_crit"].stop(self._mstate):
-                _update_history()
-                _log()
-                _log(msg=f"[{dt.datetime.now()}] Stopping Criterion satisfied -> END")
-                if self._final_writeback:
-                    self.writeback()
-                return False
-            if must_stop:
-                _update_history()
-            if must_log:
-                _log()
-            if must_wb:
+            if on_stop_beat:
+                if ast["track_objective"]:
+                    self._mstate["objective_func"] = self.objective_func().reshape(-1)
+                met = ast["stop_crit"].stop(self._mstate)
+                self._record_history()
+                if met:
+                    self._log_iteration()
+                    self._log_message(f"[{dt.datetime.now()}] Stopping Criterion satisfied -> END")
+                    if self._final_writeback:
+                        self.writeback()
+                    return False
+            if idx % ast["log_rate"] == 0:
+                self._log_iteration()
+            if ast["wb_rate"] is not None and idx % ast["wb_rate"] == 0:
                 self.writeback()
-            ast["idx"] += 1
+            ast["idx"] = idx + 1
             self.m_step()
             return True
         except Exception as e:
-            msg = f"[{dt.datetime.now()}] Something went wrong -> EXCEPTION RAISED"
-            print("\n".join([msg, f"More information: {self.logfile}."]), file=sys.stderr)
-            if ast["wb_rate"] is not None:
-                _, r = divmod(ast["idx"], ast["wb_rate"])
-                msg = "\n".join([msg, f"Last valid checkpoint done at iteration={ast['idx'] - r}."])
-            self._flush_log()
-            ast["logger"].exception(msg, exc_info=e)
-            ast["error"] = e
+            self._on_error(e)
             return False
+
+    def _record_history(self):
+        ast = self._astate
+        data = ast["stop_crit"].info()
+        keys = tuple(data)
+        cache = ast.get("history_dtype")
+        if cache is None or cache[0] != keys:  # the fields never change during a fit(): build the record type once
+            cache = ast["history_dtype"] = (keys, np.dtype([("iteration", np.int64)] + [(k, np.float64) for k in keys]))
+        rec = np.zeros(1, dtype=cache[1])
+        rec["iteration"] = ast["idx"]
+        for k, v in data.items():
+            rec[k] = v
+        ast["history"].append(rec)
+
+    def _log_iteration(self):
+        ast = self._astate
+        when, rec = dt.datetime.now(), ast["history"][-1][0]
+        if ast.get("live_log"):
+            ast["logger"].info(self._render_iteration(when, ast["idx"], rec))
+            return
+        # The per-iteration record goes to the log FILE only: keep (time, record) and render the same text in batches
+        # (Python's logging costs ~100 us per record -- more than an iteration of a small problem takes on the GPU).
+        # Nothing is lost: the batch is written before any other message, at the latest every second / 256 records, on
+        # stop, on error and on cleanup.
+        pend = ast.setdefault("pending_log", [])
+        pend.append((when, ast["idx"], rec))
+        if len(pend) >= 256 or (when - pend[0][0]).total_seconds() > 1.0:
+            self._flush_log()
+
+    def _log_message(self, msg):
+        self._flush_log()
+        self._astate["logger"].info(msg)
+
+    def _on_error(self, e):
+        ast = self._astate
+        lines = [f"[{dt.datetime.now()}] Something went wrong -> EXCEPTION RAISED"]
+        print(lines[0], f"More information: {self.logfile}.", sep="\n", file=sys.stderr)
+        if ast["wb_rate"] is not None:
+            lines.append(f"Last valid checkpoint done at iteration={ast['idx'] - ast['idx'] % ast['wb_rate']}.")
+        self._flush_log()
+        ast["logger"].exception("\n".join(lines), exc_info=e)
+        ast["error"] = e
 
     @staticmethod
     def _render_iteration(when, idx, h):

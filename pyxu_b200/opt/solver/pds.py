@@ -44,7 +44,9 @@ def _is_null(op):
 class _Plan:
     """Decides how one iteration is executed and owns the descriptors / work buffers."""
 
-    def __init__(self, solver, algo, x0):
+    def __init__(self, solver, algo, x0, part=None):
+        """x0: the primal iterate on the device (a slab's planes under a z-slab decomposition; `part` = (volume shape,
+        rank, world) then makes the planner keep only this rank's planes of per-voxel arrays)."""
         f, g, h, Kop = solver._f, solver._g, solver._h, solver._K
         self.algo = algo
         self._x0_like = x0
@@ -54,22 +56,23 @@ class _Plan:
         self.hspec = None if _is_null(h) else h._dual_spec()
         self.h_null = _is_null(h)
         self.fkind, self.falpha, self.fshift = None, 0.0, None
+        self.fstencil = None  # f = alpha*||A x + c||^2 with A a Stencil: (A, alpha, c on the device or None)
         if _is_null(f):
             self.fkind = K.F_NONE
         else:
             s = f._sql2_spec()
             if s is not None:
                 self.fkind, self.falpha = K.F_SQL2, float(s[0])
-                if s[1] is not None:
-                    if isinstance(s[1], float):
-                        import torch
+                self.fshift = self._shift_on_device(s[1], x0, part)
+                if self.fshift is not None and x0.numel() % self.fshift.numel() != 0:
+                    self.fkind = None
+            elif part is not None:
+                from ...operator.linop.stencil import Stencil
 
-                        self.fshift = torch.full((1,), s[1], dtype=x0.dtype, device=x0.device)
-                    else:
-                        self.fshift, _ = A.asdevice(s[1], dtype=x0.dtype)
-                        self.fshift = self.fshift.reshape(-1)
-                        if x0.numel() % self.fshift.numel() != 0:
-                            self.fkind = None
+                lhs, rhs = getattr(f, "_lhs", None), getattr(f, "_rhs", None)
+                s = lhs._sql2_spec() if hasattr(lhs, "_sql2_spec") else None
+                if s is not None and isinstance(rhs, Stencil):
+                    self.fstencil = (rhs, float(s[0]), self._shift_on_device(s[1], x0, part))
 
         from ...operator.linop.diff import _DiffStack
 
@@ -96,6 +99,24 @@ class _Plan:
         self._w = None
         self.iter_ok = None if self.kind == "fused" else False  # single-kernel iteration: None = not tried yet
         self.alt = None  # (primal, dual) spare buffers of the ping-pong
+
+    @staticmethod
+    def _shift_on_device(c, x0, part):
+        """The data-term shift as a flat device tensor of x0's dtype (None: no shift; one sample: a scalar shift)."""
+        if c is None:
+            return None
+        if isinstance(c, float):
+            import torch
+
+            return torch.full((1,), c, dtype=x0.dtype, device=x0.device)
+        if part is not None:
+            from ... import slab
+
+            n = int(c.numel()) if hasattr(c, "numel") else int(np.size(c))
+            if isinstance(c, slab.ShardedArray) or n == int(np.prod(part[0])):
+                c, _ = slab.local_part(c, *part)  # only this rank's planes cross the bus
+        dev, _ = A.asdevice(c, dtype=x0.dtype)
+        return dev.reshape(-1)
 
     @property
     def w(self):  # work array of the two-sweep form, allocated on first use
@@ -161,34 +182,127 @@ class _PrimalDualSplitting(Solver):
             else:
                 raise ValueError("Optional argument ``h`` mut be specified if ``K`` is not None.")
         self._plan = None
+        self._slab = None
 
     # ---------------------------------------------------------------------------------------
-    def m_init(self, x0, z0=None, tau=None, sigma=None, rho=None, tuning_strategy=1):
+    def m_init(self, x0, z0=None, tau=None, sigma=None, rho=None, tuning_strategy=1, distributed=None):
+        """Same arguments as the reference (pds.py:158-207, 723-745) plus `distributed`: under torch.distributed with more
+        than one rank a 3-D problem with the fused TV structure is decomposed into z-slabs, one per rank (pyxu_b200.slab;
+        None = automatic, True = required, False = every rank solves its own problem)."""
         mst = self._mstate
+        self._slab = None
+        self._tuning_strategy = int(tuning_strategy)
+        gamma = self._set_gamma(tuning_strategy)
+        mst["tau"], mst["sigma"], delta = self._set_step_sizes(tau, sigma, gamma)
+        mst["rho"] = self._set_momentum_term(rho, delta)
+        if self._m_init_slab(x0, z0, distributed):
+            return
         x0d, origin = A.asdevice(x0)
         self._astate["origin"] = origin
-        mst["x"] = x0d.clone()  # never write into the caller's buffer
+        mst["x"] = x0d.clone() if origin == A.DEVICE else x0d  # never write into the caller's buffer (a host array was copied already)
         if z0 is None:
             mst["z"] = self._K(mst["x"])
             if mst["z"].data_ptr() == mst["x"].data_ptr():
                 mst["z"] = mst["z"].clone()
         else:
-            z0d, _ = A.asdevice(z0, dtype=x0d.dtype)
-            mst["z"] = z0d.clone()
-        self._tuning_strategy = int(tuning_strategy)
-        gamma = self._set_gamma(tuning_strategy)
-        mst["tau"], mst["sigma"], delta = self._set_step_sizes(tau, sigma, gamma)
-        mst["rho"] = self._set_momentum_term(rho, delta)
+            z0d, zo = A.asdevice(z0, dtype=x0d.dtype)
+            mst["z"] = z0d.clone() if zo == A.DEVICE else z0d
         self._plan = _Plan(self, self._ALGO, mst["x"])
         self._setup_fused_norms()
 
-    def _setup_fused_norms(self):
+    # -- z-slab decomposition over the ranks of torch.distributed (pyxu_b200.slab) -------------------------------
+    def _m_init_slab(self, x0, z0, distributed):
+        """Hands the iteration to a slab engine when the problem decomposes; returns False for a single-domain solve."""
+        from ... import slab
+        from ...operator.linop.diff import _DiffStack
+
+        sharded_in = isinstance(x0, slab.ShardedArray)
+        ctx = slab.context(True if (sharded_in and distributed is None) else distributed)
+        if ctx is None:
+            return False
+        required = distributed is True or sharded_in
+        Kop = self._K
+        n_in = int(x0.numel()) if hasattr(x0, "numel") else int(np.size(x0))
+        ok = isinstance(Kop, _DiffStack) and len(Kop.arg_shape) == 3 and Kop._dirs == (0, 1, 2) and n_in == Kop.dim
+        if ok:
+            vol = Kop.arg_shape
+            ok = vol[0] >= 3 * ctx[1]
+        if not ok:
+            if required:
+                raise NotImplementedError("z-slab decomposition needs K = Gradient of a 3-D volume (all three directions), one volume per solve, "
+                                          "and at least 3 planes per rank")
+            return False
+        mst, ast = self._mstate, self._astate
+        rank, world = ctx
+        part = (vol, rank, world)
+        x_loc, _ = slab.local_part(x0, *part)
+        x0d, origin = A.asdevice(x_loc)
+        x0d = x0d.reshape(-1)
+        plan = _Plan(self, self._ALGO, x0d, part=part)
+        stencil_term = plan.kind == "fused" and plan.fkind == K.F_GRADARR and plan.fstencil is not None
+        if plan.kind != "fused" or (plan.fkind == K.F_GRADARR and not stencil_term):
+            if required:
+                raise NotImplementedError("this problem has no z-slab form: it needs h o K = (L21 | L1) o Gradient, a pointwise prox for g and a data term "
+                                          "that is null, alpha*||x + c||^2, or (CondatVu) alpha*||A x + c||^2 with A a separable Stencil")
+            return False
+        ast["origin"] = origin
+        ast["sharded"] = sharded_in
+        z0d = None
+        if z0 is not None:
+            z_loc, _ = slab.local_part(z0, *part, comps=3)
+            z0d, _ = A.asdevice(z_loc, dtype=x0d.dtype)
+        self._plan = plan
+        mst["x"] = mst["z"] = None  # live in the engine's slab buffers; materialised by _logged()
+        crit = ast["stop_crit"]
+        reads = crit._state_vars() if crit is not None else None
+        self._setup_fused_norms(device=x0d.device)
+        served = frozenset(k for k in ("x", "z") if k in mst.get("_fused_norms", {}))
+        if ast["track_objective"] or reads is None or not (reads <= served) or crit._rank_local():
+            raise NotImplementedError("z-slab decomposition: the stopping criterion must be built from MaxIter / ManualStop / RelError (2-norm, no f) "
+                                      "on x or z, evaluated every iteration (stop_rate = 1); objective tracking is not available")
+        params = plan._build_params(mst, garr=x0d)  # (garr is re-pointed by the engine)
+        if stencil_term:
+            Aop, alpha, c = plan.fstencil
+            self._slab = slab.SlabDeblurCV(Kop, Aop, alpha, params, x0d, z0d, c, rank, world)
+        else:
+            self._slab = slab.SlabTV(self._ALGO, Kop, params, x0d, z0d, plan.fshift, rank, world)
+        plan.iter_ok = True
+        return True
+
+    def _step_slab(self):
+        self._zero_norms()
+        eng = self._slab
+        want_x = self._nx is not None or self._x_every
+        eng.probe = self._probe
+        eng.step(self._nx, self._nz, want_x)
+        if self._nrm is not None and eng.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(self._nrm, group=eng.group)  # the single fused scalar all-reduce of the stopping criterion
+
+    def _logged(self, k):
+        if getattr(self, "_slab", None) is None:
+            return super()._logged(k)
+        if k not in self._astate["log_var"] or k not in ("x", "z"):
+            return None
+        from ... import slab
+
+        eng = self._slab
+        loc = eng.x_local().unsqueeze(0) if k == "x" else eng.z_local()
+        if self._astate.get("sharded"):
+            out = A.restore(loc.contiguous().reshape(-1), self._astate["origin"])
+            return slab.ShardedArray(out, eng.shape, comps=loc.shape[0], rank=eng.rank, world=eng.world)
+        full = slab.gather_planes(loc, eng.shape, eng.world, group=eng.group) if eng.world > 1 else loc.contiguous()
+        return A.restore(full.reshape(-1), self._astate["origin"])
+
+    def _setup_fused_norms(self, device=None):
         """If the stopping criterion is RelError on x / z evaluated every iteration, let the update kernels
         accumulate its norms (no extra pass, no x_prev copy).  Also decides whether PD3O's x must be written by
         every iteration or only when somebody asks for it (`_materialize`)."""
         import torch
 
         mst, ast = self._mstate, self._astate
+        device = mst["x"].device if device is None else device
         crit = ast["stop_crit"]
         want = crit._fused_vars() if crit is not None else frozenset()
         self._nx = self._nz = self._nrm = None
@@ -203,7 +317,7 @@ class _PrimalDualSplitting(Solver):
             rows = self._plan.batch
             if want:
                 # one (2, rows, 2) buffer: a single memset per iteration and a single 32-byte readback
-                self._nrm = torch.zeros((2, rows, 2), dtype=torch.float64, device=mst["x"].device)
+                self._nrm = torch.zeros((2, rows, 2), dtype=torch.float64, device=device)
                 fused = {"_all": self._nrm, "_host": None, "_stamp": -1}
                 if "x" in want:
                     self._nx = fused["x"] = self._nrm[0]
@@ -352,6 +466,8 @@ class CondatVu(_PrimalDualSplitting):
     _ALGO = K.ALGO_CV
 
     def m_step(self):
+        if self._slab is not None:
+            return self._step_slab()
         mst, pl = self._mstate, self._plan
         if pl.kind == "fused":
             garr = self._f.grad(mst["x"]) if pl.fkind == K.F_GRADARR else None
@@ -413,9 +529,11 @@ class PD3O(_PrimalDualSplitting):
 
     _ALGO = K.ALGO_PD3O
 
-    def m_init(self, x0, z0=None, tau=None, sigma=None, rho=None, tuning_strategy=1):
-        super().m_init(x0=x0, z0=z0, tau=tau, sigma=sigma, rho=rho, tuning_strategy=tuning_strategy)
+    def m_init(self, x0, z0=None, tau=None, sigma=None, rho=None, tuning_strategy=1, distributed=None):
+        super().m_init(x0=x0, z0=z0, tau=tau, sigma=sigma, rho=rho, tuning_strategy=tuning_strategy, distributed=distributed)
         mst = self._mstate
+        if self._slab is not None:  # (g = h = 0 never takes the slab path: u0 = x0 there)
+            return
         # if x0 == u0 the first step would not move x when g = h = 0 (reference: pds.py:741-745)
         if _is_null(self._g) and _is_null(self._h):
             mst["u"] = kr.lincomb(1.01, mst["x"])
@@ -423,6 +541,8 @@ class PD3O(_PrimalDualSplitting):
             mst["u"] = mst["x"].clone()
 
     def m_step(self):
+        if self._slab is not None:
+            return self._step_slab()
         mst, pl = self._mstate, self._plan
         tau, rho = mst["tau"], mst["rho"]
         if pl.kind == "fused":

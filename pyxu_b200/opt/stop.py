@@ -77,6 +77,9 @@ class MaxDuration(StoppingCriterion):
     def info(self):
         return dict(duration=(self._t_now - self._t_start).total_seconds())
 
+    def _rank_local(self):
+        return True
+
     def clear(self):
         self._t_start = dt.datetime.now()
         self._t_now = self._t_start

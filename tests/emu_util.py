@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-from pyxu_b200 import _build, _cabi as K
+from pyxu_b200 import _cabi as K
 
 _lib = None
 
@@ -12,7 +12,12 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        path = _build.build_emu()
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("_pxb_emu_build", os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        path = mod.build_emu()
         h = C.CDLL(path)
         vp, i, i64, d = C.c_void_p, C.c_int, C.c_int64, C.c_double
         P = C.POINTER

@@ -13,7 +13,8 @@ import types
 REFERENCE_SRC = "/root/reference/src"
 
 
-def load():
+def load(src=REFERENCE_SRC):
+    """src: directory that holds the `pyxu` package (the mounted reference, or its staged copy under oracle/_ref)."""
     _orig = _ilm.version
     _ilm.version = lambda name: "0+reference" if name == "pyxu" else _orig(name)
 
@@ -42,8 +43,8 @@ def load():
 
         sp.SparseArray = _SparseArray
 
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    if src not in sys.path:
+        sys.path.insert(0, src)
     import pyxu  # noqa: F401
     import pyxu.abc as pxa
     import pyxu.operator as pxo

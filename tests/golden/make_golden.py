@@ -191,6 +191,44 @@ def solvers(ns):
     print("solvers.npz", len(out))
 
 
+def slabs(ns):
+    """Volumes tall enough to be cut into 2, 3, 4 or 8 z-slabs (tests of the multi-GPU path compare with these, i.e. with
+    the reference itself, not with the repo's single-domain solver)."""
+    stop = ns.stop
+    out = {}
+    shape = (32, 12, 16)
+    _, y = cases.phantom(shape, seed=21)
+    out["y"] = y
+    slv = cases.build_tv_denoise(ns, y, shape, lam=0.08)
+    slv.fit(x0=y.reshape(-1).copy(), stop_crit=stop.MaxIter(25), rho=1.2)
+    _record(slv, "pd3o_tv3d", out)
+    slv = cases.build_tv_denoise(ns, y, shape, lam=0.3)
+    slv.fit(x0=y.reshape(-1).copy())  # default criterion: the iteration count must match too
+    _record(slv, "pd3o_tv3d/default_stop", out)
+    for tag, mode in (("ring", ("wrap", "reflect", "edge")), ("fold", ("reflect", "symmetric", "wrap")), ("edge", ("edge", "constant", "symmetric"))):
+        slv = cases.build_tv_denoise(ns, y, shape, lam=0.08, mode=mode)
+        slv.fit(x0=y.reshape(-1).copy(), stop_crit=stop.MaxIter(20), tuning_strategy=3)
+        _record(slv, f"pd3o_tv3d/{tag}", out)
+    slv = cases.build_tv_denoise(ns, y, shape, lam=0.08, solver="CondatVu", positivity=False)
+    slv.fit(x0=np.zeros(y.size), stop_crit=stop.MaxIter(25))
+    _record(slv, "cv_tv3d", out)
+    # CondatVu deblurring, separable 7x5x7 PSF (reaches 3 planes across a cut) + positivity; then the same PSF given dense
+    x3, _ = cases.phantom(shape, seed=22)
+    psf = [cases.gaussian_1d(7, 1.2), cases.gaussian_1d(5, 1.0), cases.gaussian_1d(7, 1.5)]
+    slv, A = cases.build_tv_deblur(ns, np.zeros(shape), shape, psf, (3, 2, 3), positivity=True)
+    yb = A.apply(x3.reshape(-1)) + 0.01 * np.random.default_rng(23).standard_normal(x3.size)
+    out["cv_deblur3d/y"] = yb
+    slv, A = cases.build_tv_deblur(ns, yb, shape, psf, (3, 2, 3), lam=0.02, positivity=True)
+    slv.fit(x0=np.zeros(yb.size), stop_crit=stop.MaxIter(15), rho=0.9)
+    _record(slv, "cv_deblur3d", out)
+    psf6 = [cases.gaussian_1d(6, 1.2), cases.gaussian_1d(5, 1.0), cases.gaussian_1d(7, 1.5)]  # even tap count along z, off-centre
+    slv, A = cases.build_tv_deblur(ns, yb, shape, psf6, (2, 2, 3), lam=0.02, positivity=True)
+    slv.fit(x0=np.zeros(yb.size), stop_crit=stop.MaxIter(15))
+    _record(slv, "cv_deblur3d/even", out)
+    np.savez_compressed(os.path.join(HERE, "slabs.npz"), **out)
+    print("slabs.npz", len(out))
+
+
 def config0(ns):
     """BASELINE.json configs[0] at full size: 512x512 float64 PD3O TV denoising, 200 iterations.
 
@@ -211,6 +249,6 @@ def config0(ns):
 
 if __name__ == "__main__":
     ns = _ref_import.load()
-    which = sys.argv[1:] or ["stencils", "gradients", "funcs", "solvers", "config0"]
+    which = sys.argv[1:] or ["stencils", "gradients", "funcs", "solvers", "slabs", "config0"]
     for w in which:
         globals()[w](ns)

@@ -3,10 +3,8 @@ pxb_pad2d -> pxb_stencil2d_apply on the padded array / pxb_stencil2d_apply onto 
 against the gather kernels (pinned on the real reference by the golden-vector tests), the reference's fixtures, the adjoint
 identity and the solver path that uses it (CondatVu deblurring with a reflect-mode blur).
 
-The path is switched off by default until it has run on a GPU (PYXU_B200_STENCIL_PADDED=1 switches it on).  These tests switch it
-on for themselves and are marked xfail(strict=False): the round's GPU budget was spent before they could run, so their first
-run is the next GPU run of the suite -- an XPASS there is the missing verification, a failure is reported as xfail instead of
-breaking a suite whose default paths it does not touch.  (The file sorts last; the slab test runs in a process of its own.)"""
+The path is the default (PYXU_B200_STENCIL_PADDED=0 switches it off); the tests pin it on so that they compare what they
+say they compare whatever the environment holds."""
 import os
 import subprocess
 import sys
@@ -17,7 +15,7 @@ import pytest
 import cases
 from conftest import golden
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="opt-in path, CPU-verified only: first GPU run")]
+pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 DEV = "cuda"  # tests/test_emu_device_solvers.py replays these functions on the emulated device with DEV = "cpu"
 
@@ -113,21 +111,3 @@ def test_cv_deblur_reflect_blur_uses_the_padded_path():
         assert (Aop._padded_ok is True) == padded
         res.append(slv.stats()[0]["x"])
     assert np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1]) < 1e-11
-
-
-def test_slab_single_kernel_form_with_folding_modes():
-    """SlabPD3OTV with PYXU_B200_SLAB_FUSED_MODES=1 (single-kernel iteration with folding modes on slabs; world 1 here, 2 when the
-    box has the GPUs): the torchrun worker of tests/test_gpu_slab.py in a process of its own."""
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    import socket
-
-    for world in ([1, 2] if torch.cuda.device_count() >= 2 else [1]):
-        s = socket.socket()
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
-        s.close()
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-               "--master-port", str(port), os.path.join(root, "tests", "slab_worker.py")]
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, PYXU_B200_SLAB_FUSED_MODES="1"))
-        print(r.stdout[-3000:], r.stderr[-2000:])
-        assert r.returncode == 0 and r.stdout.count("OK") == 9 and "FAIL" not in r.stdout

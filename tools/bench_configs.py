@@ -120,20 +120,26 @@ def main():
         nvox, name = N, f"2-D TV deblurring {n}x{n} fp32, CondatVu, {'dense' if args.dense else 'separable'} 9x9 Gaussian Stencil blur + L21 o Gradient"
         bpv = 12 + 8 + 28  # A x - y (read x, y; write r) + A^T r + single-kernel CV iteration (read x, grad f, z0, z1; write x, z0, z1)
     elif args.workload == "deblur3d":
-        from pyxu_b200.slab import SlabCondatVuDeblur, partition
+        from pyxu_b200.slab import ShardedArray, partition
 
         shape = tuple(int(v) for v in args.shape.split(","))
+        N = int(np.prod(shape))
         a, b = partition(shape[0], world)[rank]
+        sh = lambda t: ShardedArray(t, shape, rank=rank, world=world)
         y_local = torch.rand((b - a, *shape[1:]), device="cuda", generator=gen)
         g7 = gauss(7, 1.2)
-        slab = SlabCondatVuDeblur(shape, [g7, g7, g7], (3, 3, 3), y_local=y_local, lam=0.05, positivity=True, dtype=torch.float32)
+        A = pxo.Stencil(arg_shape=shape, kernel=[g7, g7, g7], center=(3, 3, 3), mode="constant")
+        f = (0.5 * pxo.SquaredL2Norm(dim=N).argshift(sh(-y_local))) * A
+        Kop = pxo.Gradient(arg_shape=shape, dtype=np.float32)
+        h = 0.05 * pxo.L21Norm(arg_shape=(3, *shape), l2_axis=(0,))
+        slv = pxs.CondatVu(f=f, g=pxo.PositiveOrthant(dim=N), h=h, K=Kop, beta=float(A.lipschitz) ** 2, show_progress=False)
+        slv.fit(x0=sh(y_local), mode=Mode.MANUAL, stop_crit=pxst.ManualStop(), distributed=True)
         del y_local
-        ms, launches = timed(slab.step, K, W, world)
-        launches = launches  # (3 stages x up to 3 sub-range launches when the exchanges are overlapped)
-        nvox = int(np.prod(shape))
+        ms, launches = timed(slv.m_step, K, W, world)
+        nvox = N
         name = f"3-D TV deblurring {'x'.join(map(str, shape))} fp32, CondatVu, separable 7x7x7 Stencil PSF + positivity + L21 o Gradient, {world} z-slab(s)"
-        # A x - y (read x, y; write r) | A^T r | single-kernel CV iteration with grad f array     (two-pass stencils: 8+12+8+8+36)
-        bpv = (12 + 8 + 36) if slab.single_pass else (8 + 12 + 8 + 8 + 36)
+        # 2 alpha (A x + c) (read x, c; write r) | A^T r | single-kernel CV iteration with grad f array     (two-pass stencils: 8+12+8+8+36)
+        bpv = (12 + 8 + 36) if slv._slab.single_pass else (8 + 12 + 8 + 8 + 36)
     else:
         n = args.size or 1024
         shape, N = (n, n), n * n
