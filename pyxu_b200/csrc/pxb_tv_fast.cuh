@@ -373,7 +373,7 @@ PXB_HD void pxb_tv_primal_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const 
         else if (q.shift_mode == PXB_SHIFT_MOD) { for (int j = 0; j < VEC; ++j) sh.v[j] = q.shift[(lin + j) % q.shift_period]; }
     }
     PxbVec<T, VEC> xn, xo, wo;
-    double a0 = 0.0, a1 = 0.0;
+    T a0 = T(0), a1 = T(0);  // one vector's RelError partial sums in the working precision, widened once
     if (ALGO == PXB_PD3O) {
         PxbVec<T, VEC> xprev;
         if (NORMS) xprev = pxb_vload<T, VEC>(x_out + lin);
@@ -385,9 +385,9 @@ PXB_HD void pxb_tv_primal_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const 
             xn.v[j] = q.one_m_rho * old.v[j] + q.rho * ut;
             xo.v[j] = x;
             if (NORMS) {
-                const double dd = (double)x - (double)xprev.v[j];
+                const T dd = x - xprev.v[j];
                 a0 += dd * dd;
-                a1 += (double)xprev.v[j] * (double)xprev.v[j];
+                a1 += xprev.v[j] * xprev.v[j];
             }
         }
         pxb_vstore<T, VEC>(x_out + lin, xo);
@@ -403,15 +403,15 @@ PXB_HD void pxb_tv_primal_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const 
             wo.v[j] = T(2) * xt - old.v[j];
             xn.v[j] = q.rho * xt + q.one_m_rho * old.v[j];
             if (NORMS) {
-                const double dd = (double)xn.v[j] - (double)old.v[j];
+                const T dd = xn.v[j] - old.v[j];
                 a0 += dd * dd;
-                a1 += (double)old.v[j] * (double)old.v[j];
+                a1 += old.v[j] * old.v[j];
             }
         }
     }
     pxb_vstore<T, VEC>(xu + lin, xn);
     pxb_vstore<T, VEC>(w + lin, wo);
-    if (NORMS) { nrm[0] += a0; nrm[1] += a1; }
+    if (NORMS) { nrm[0] += (double)a0; nrm[1] += (double)a1; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -444,7 +444,7 @@ PXB_HD void pxb_tv_dual_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const px
             p[k][j] = zc.v[j] + q.sigma * kw[j];
         }
     }
-    double a0 = 0.0, a1 = 0.0;
+    T a0 = T(0), a1 = T(0);
     for (int j = 0; j < VEC; ++j) {
         T grp[PXB_MAX_DIRS];
         for (int k = 0; k < NDIR; ++k) grp[k] = p[k][j];
@@ -452,9 +452,9 @@ PXB_HD void pxb_tv_dual_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const px
         for (int k = 0; k < NDIR; ++k) {
             const T zn = q.one_m_rho * zo[k][j] + q.rho * grp[k];
             if (NORMS) {
-                const double dd = (double)zn - (double)zo[k][j];
+                const T dd = zn - zo[k][j];
                 a0 += dd * dd;
-                a1 += (double)zo[k][j] * (double)zo[k][j];
+                a1 += zo[k][j] * zo[k][j];
             }
             p[k][j] = zn;
         }
@@ -464,7 +464,7 @@ PXB_HD void pxb_tv_dual_vec(const PxbTvP<T>& q, const pxb_grad_desc& d, const px
         for (int j = 0; j < VEC; ++j) o.v[j] = p[k][j];
         pxb_vstore<T, VEC>(zb + k * q.vol, o);
     }
-    if (NORMS) { nrm[0] += a0; nrm[1] += a1; }
+    if (NORMS) { nrm[0] += (double)a0; nrm[1] += (double)a1; }
 }
 
 // ---------------------------------------------------------------------------------------------------------

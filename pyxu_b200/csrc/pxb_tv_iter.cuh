@@ -193,17 +193,21 @@ PXB_HD void pxb_iter_w(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterIt
         if (store) {
             if (NORMS && a.norms_x) {
                 const PxbVec<T, W> xprev = pxb_vload<T, W>(a.x_out + lin);
+                T s0 = T(0), s1 = T(0);  // one vector's partial sums in the working precision, widened once
                 for (int j = 0; j < W; ++j) {
-                    const double dd = (double)xo.v[j] - (double)xprev.v[j];
-                    acc[0] += dd * dd;
-                    acc[1] += (double)xprev.v[j] * (double)xprev.v[j];
+                    const T dd = xo.v[j] - xprev.v[j];
+                    s0 += dd * dd;
+                    s1 += xprev.v[j] * xprev.v[j];
                 }
+                acc[0] += (double)s0;
+                acc[1] += (double)s1;
             }
             if (a.x_out) pxb_vstore<T, W>(a.x_out + lin, xo);
         }
     } else {
         PxbVec<T, W> ga;
         if (q.fkind == PXB_F_GRADARR) ga = pxb_vload<T, W>(q.garr + lin);
+        T s0 = T(0), s1 = T(0);
         for (int j = 0; j < W; ++j) {
             T gf = T(0);
             if (q.fkind == PXB_F_SQL2) gf = (old.v[j] + sh.v[j]) * q.two_alpha;
@@ -213,11 +217,12 @@ PXB_HD void pxb_iter_w(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterIt
             wv[j] = T(2) * xt - old.v[j];
             un.v[j] = q.rho * xt + q.one_m_rho * old.v[j];
             if (NORMS && store && a.norms_x) {
-                const double dd = (double)un.v[j] - (double)old.v[j];
-                acc[0] += dd * dd;
-                acc[1] += (double)old.v[j] * (double)old.v[j];
+                const T dd = un.v[j] - old.v[j];
+                s0 += dd * dd;
+                s1 += old.v[j] * old.v[j];
             }
         }
+        if (NORMS && store && a.norms_x) { acc[0] += (double)s0; acc[1] += (double)s1; }
     }
     if (store) pxb_vstore<T, W>(a.u_out + lin, un);
 }
@@ -327,7 +332,7 @@ PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
             p[C::KC][j] = zo[C::KC][j] + q.sigma * kw;
         }
     }
-    double a0 = 0.0, a1 = 0.0;
+    T a0 = T(0), a1 = T(0);  // RelError[z] partial sums of this vector in the working precision, widened once below
     for (int j = 0; j < VEC; ++j) {
         T grp[PXB_MAX_DIRS];
         for (int k = 0; k < NDIR; ++k) grp[k] = p[k][j];
@@ -335,9 +340,9 @@ PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
         for (int k = 0; k < NDIR; ++k) {
             const T zn = q.one_m_rho * zo[k][j] + q.rho * grp[k];
             if (NORMS) {
-                const double dd = (double)zn - (double)zo[k][j];
+                const T dd = zn - zo[k][j];
                 a0 += dd * dd;
-                a1 += (double)zo[k][j] * (double)zo[k][j];
+                a1 += zo[k][j] * zo[k][j];
             }
             p[k][j] = zn;
         }
@@ -348,7 +353,7 @@ PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
         for (int j = 0; j < VEC; ++j) o.v[j] = p[k][j];
         pxb_vstore<T, VEC>(zb + k * g.vol, o);
     }
-    if (NORMS) { acc[2] += a0; acc[3] += a1; }
+    if (NORMS) { acc[2] += (double)a0; acc[3] += (double)a1; }
 }
 
 // The marching loop of one thread between barriers (`sync` is __syncthreads on the device; the host emulation

@@ -130,19 +130,25 @@ PXB_HD void pxb_t2_phaseA(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
             if (ALGO == PXB_PD3O) {
                 if (NORMS && a.norms_x) {
                     const PxbVec<T, VEC> xp = pxb_vload<T, VEC>(a.x_out + lin);
+                    T s0 = T(0), s1 = T(0);  // one vector's partial sums in the working precision, widened once
                     for (int j = 0; j < VEC; ++j) {
-                        const double dd = (double)xo[j] - (double)xp.v[j];
-                        acc[0] += dd * dd;
-                        acc[1] += (double)xp.v[j] * (double)xp.v[j];
+                        const T dd = xo[j] - xp.v[j];
+                        s0 += dd * dd;
+                        s1 += xp.v[j] * xp.v[j];
                     }
+                    acc[0] += (double)s0;
+                    acc[1] += (double)s1;
                 }
                 if (a.x_out) { for (int j = 0; j < VEC; ++j) o.v[j] = xo[j]; pxb_vstore<T, VEC>(a.x_out + lin, o); }
             } else if (NORMS && a.norms_x) {
+                T s0 = T(0), s1 = T(0);
                 for (int j = 0; j < VEC; ++j) {
-                    const double dd = (double)un[j] - (double)uo[j];
-                    acc[0] += dd * dd;
-                    acc[1] += (double)uo[j] * (double)uo[j];
+                    const T dd = un[j] - uo[j];
+                    s0 += dd * dd;
+                    s1 += uo[j] * uo[j];
                 }
+                acc[0] += (double)s0;
+                acc[1] += (double)s1;
             }
             for (int j = 0; j < VEC; ++j) o.v[j] = un[j];
             pxb_vstore<T, VEC>(a.u_out + lin, o);
@@ -222,17 +228,19 @@ PXB_HD void pxb_t2_phaseC(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
             }
         }
         PxbVec<T, VEC> o0, o1;
+        T a0 = T(0), a1 = T(0);
         for (int j = 0; j < VEC; ++j) {
             T grp[PXB_MAX_DIRS] = {p[0][j], p[1][j], T(0)};
             pxb_dual_prox_group<T>(pxb_hkind<S>(q), 2, q.lam, q.sigma, grp);
             o0.v[j] = q.one_m_rho * z0.v[j] + q.rho * grp[0];
             o1.v[j] = q.one_m_rho * z1.v[j] + q.rho * grp[1];
             if (NORMS) {
-                const double d0 = (double)o0.v[j] - (double)z0.v[j], d1 = (double)o1.v[j] - (double)z1.v[j];
-                acc[2] += d0 * d0 + d1 * d1;
-                acc[3] += (double)z0.v[j] * (double)z0.v[j] + (double)z1.v[j] * (double)z1.v[j];
+                const T d0 = o0.v[j] - z0.v[j], d1 = o1.v[j] - z1.v[j];
+                a0 += d0 * d0 + d1 * d1;
+                a1 += z0.v[j] * z0.v[j] + z1.v[j] * z1.v[j];
             }
         }
+        if (NORMS) { acc[2] += (double)a0; acc[3] += (double)a1; }
         T* __restrict__ zb = a.z_out + it.b * 2 * g.vol + (int64_t)it.i0 * g.s0 + (int64_t)r * g.n2 + c;
         pxb_vstore<T, VEC>(zb, o0);
         pxb_vstore<T, VEC>(zb + g.vol, o1);

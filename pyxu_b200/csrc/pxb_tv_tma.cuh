@@ -245,20 +245,28 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             const int64_t lin = it.lin_base + (int64_t)m * g.sM + (int64_t)r * g.sR + c;
             if (ALGO == PXB_PD3O) {
                 if (NORMS && a.norms_x) {
+                    // partial sums of one vector in the working precision, widened once (fp32: the per-sample fp64
+                    // conversions and FMAs made the criterion-carrying instance issue-bound: 9.3 ms instead of 7.5 at 1024^3)
                     const PxbVec<T, VEC> xp = pxb_vload<T, VEC>(a.x_out + lin);
+                    T s0 = T(0), s1 = T(0);
                     for (int j = 0; j < VEC; ++j) {
-                        const double dd = (double)xo[j] - (double)xp.v[j];
-                        th.acc[0] += dd * dd;
-                        th.acc[1] += (double)xp.v[j] * (double)xp.v[j];
+                        const T dd = xo[j] - xp.v[j];
+                        s0 += dd * dd;
+                        s1 += xp.v[j] * xp.v[j];
                     }
+                    th.acc[0] += (double)s0;
+                    th.acc[1] += (double)s1;
                 }
                 if (a.x_out) { for (int j = 0; j < VEC; ++j) o.v[j] = xo[j]; pxb_vstore<T, VEC>(a.x_out + lin, o); }
             } else if (NORMS && a.norms_x) {
+                T s0 = T(0), s1 = T(0);
                 for (int j = 0; j < VEC; ++j) {
-                    const double dd = (double)un[j] - (double)uo[j];
-                    th.acc[0] += dd * dd;
-                    th.acc[1] += (double)uo[j] * (double)uo[j];
+                    const T dd = un[j] - uo[j];
+                    s0 += dd * dd;
+                    s1 += uo[j] * uo[j];
                 }
+                th.acc[0] += (double)s0;
+                th.acc[1] += (double)s1;
             }
             for (int j = 0; j < VEC; ++j) o.v[j] = un[j];
             pxb_vstore<T, VEC>(a.u_out + lin, o);
