@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PXB_ABI_VERSION 2
+#define PXB_ABI_VERSION 3
 
 enum pxb_dtype { PXB_F32 = 0, PXB_F64 = 1 };
 
@@ -342,6 +342,35 @@ int pxb_set_iter_path(int path);
  * 0 = PXB_ENOSUP for every folding mode, so that callers take pxb_pds_primal + pxb_pds_dual (A/B measurements, tests),
  * -1 = back to the initial value (environment variable PXB_TV_ITER_MODES=0|1, else 1). */
 int pxb_set_iter_modes(int on);
+/* Up to `n` iterations queued back to back on the stream, the stopping rule tested ON THE DEVICE after each one, so that the
+ * host is out of the loop (reference loop: abc/solver.py:588-652 tests the criterion on the host before every step; for a
+ * 512x512 problem an iteration is ~3 us of GPU work against ~30 us of host turnaround).
+ *   (xu_a, z_a) holds the current iterate; iteration i reads pair (i even ? a : b) and writes the other one.
+ *   x           PD3O: x, rewritten by every iteration (needed for RelError[x]; nullable when eps_x <= 0).
+ *   norms       DEVICE double[n][2][batch][2], zeroed by the caller: iteration i accumulates its RelError sums
+ *               {sum (new-old)^2, sum old^2} for x ([i][0]) and z ([i][1]) there -- the host replays its criterion / history
+ *               from them afterwards, so the log is the same as with one launch per iteration.
+ *   rule        RelError thresholds as in stop.py:353-382: a variable's test holds when sqrt(num) <= eps*sqrt(den) for every
+ *               (all = 1) / any (all = 0) batch row; `table` bit (2*px + pz) tells whether the composed criterion stops for
+ *               outcomes (px, pz) -- the host builds it from its criterion tree with the non-norm leaves (MaxIter ...) false.
+ *   ctl         DEVICE pxb_iter_ctl, zeroed by the caller before the first batch: `done` counts the iterations carried out
+ *               (the iterate is in pair a when done is even), `stop` is raised by the iteration that met the rule; launches
+ *               behind it return without touching anything.
+ * Envelope and return codes as pxb_pds_iter (PXB_ENOSUP: nothing was launched). */
+typedef struct pxb_stop_rule {
+    double eps_x, eps_z;
+    int32_t all_x, all_z;
+    int32_t table;
+    int32_t _pad;
+} pxb_stop_rule;
+typedef struct pxb_iter_ctl {
+    int32_t stop;
+    int32_t done;
+    uint32_t ticket; /* internal: thread blocks of the running iteration that have finished */
+    int32_t _pad;
+} pxb_iter_ctl;
+int pxb_pds_iter_n(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu_a, void* z_a, void* xu_b, void* z_b,
+                   void* x, double* norms, int n, const pxb_stop_rule* rule, pxb_iter_ctl* ctl, void* stream);
 /* same, with the number of planes one thread block marches through fixed by the caller (tuning / tests) */
 int pxb_pds_iter_chunked(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in,
                          void* xu_out, void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk, void* stream);

@@ -18,7 +18,7 @@ DUAL_NONE, DUAL_L21, DUAL_L1 = range(3)
 F_NONE, F_SQL2, F_GRADARR = range(3)
 ALGO_PD3O, ALGO_CV = 0, 1
 MAX_DIRS, MAX_GTAP = 3, 16
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class NativeLibraryError(RuntimeError):
@@ -152,6 +152,14 @@ class PdsParams(C.Structure):
     ]
 
 
+class StopRule(C.Structure):
+    _fields_ = [("eps_x", C.c_double), ("eps_z", C.c_double), ("all_x", C.c_int32), ("all_z", C.c_int32), ("table", C.c_int32), ("_pad", C.c_int32)]
+
+
+class IterCtl(C.Structure):
+    _fields_ = [("stop", C.c_int32), ("done", C.c_int32), ("ticket", C.c_uint32), ("_pad", C.c_int32)]
+
+
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _P = C.POINTER
 
@@ -178,6 +186,7 @@ PROTOTYPES = {
     "pxb_pds_primal": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pxb_pds_dual": (_i, [_P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp]),
     "pxb_pds_iter": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pxb_pds_iter_n": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _i, _P(StopRule), _vp, _vp]),
     "pxb_pds_iter_chunked": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pxb_set_iter_path": (_i, [_i]),
     "pxb_set_iter_modes": (_i, [_i]),

@@ -62,6 +62,25 @@ class StoppingCriterion:
     def _rank_local(self):
         return False
 
+    # -- iterations queued back to back with the rule tested on the device (pxb_pds_iter_n) ----------------------------
+    # _device_eval(px, pz): the decision given the outcomes of the RelError tests on x and z, every other leaf taken as
+    #     "not met"; raises NotImplementedError when the criterion cannot be expressed that way.
+    # _device_leaves(): [(var, eps, satisfy_all)] of the RelError leaves.
+    # _budget(): how many iterations may run before a leaf the device does not evaluate (MaxIter) could fire.
+    # _replay(sums): the decisions and info() fields of len(sums) consecutive stop() calls, sums[i] = the fused sums
+    #     (2, rows, 2) of call i; leaves the criterion in the state those calls would have left it in.
+    def _device_eval(self, px, pz):
+        raise NotImplementedError
+
+    def _device_leaves(self):
+        return []
+
+    def _budget(self):
+        return float("inf")
+
+    def _replay(self, sums):
+        raise NotImplementedError
+
 
 class _Composition(StoppingCriterion):
     def __init__(self, lhs, rhs, op):
@@ -89,6 +108,19 @@ class _Composition(StoppingCriterion):
 
     def _rank_local(self):
         return self._lhs._rank_local() or self._rhs._rank_local()
+
+    def _device_eval(self, px, pz):
+        return bool(self._op(self._lhs._device_eval(px, pz), self._rhs._device_eval(px, pz)))
+
+    def _device_leaves(self):
+        return self._lhs._device_leaves() + self._rhs._device_leaves()
+
+    def _budget(self):
+        return min(self._lhs._budget(), self._rhs._budget())
+
+    def _replay(self, sums):
+        (da, ia), (db, ib) = self._lhs._replay(sums), self._rhs._replay(sums)
+        return self._op(da, db), {**ia, **ib}
 
 
 def _workdir(folder, exist_ok):
@@ -308,31 +340,37 @@ class Solver:
     def _step(self):
         """One turn of the loop (reference: solver.py:588-667): test the criterion on the current state, log, checkpoint,
         then iterate.  Returns False once the criterion is met or an exception was raised (kept in _astate["error"])."""
-        ast = self._astate
-        idx = ast["idx"]
-        on_stop_beat = idx % ast["stop_rate"] == 0
         try:
-            if on_stop_beat:
-                if ast["track_objective"]:
-                    self._mstate["objective_func"] = self.objective_func().reshape(-1)
-                met = ast["stop_crit"].stop(self._mstate)
-                self._record_history()
-                if met:
-                    self._log_iteration()
-                    self._log_message(f"[{dt.datetime.now()}] Stopping Criterion satisfied -> END")
-                    if self._final_writeback:
-                        self.writeback()
-                    return False
-            if idx % ast["log_rate"] == 0:
-                self._log_iteration()
-            if ast["wb_rate"] is not None and idx % ast["wb_rate"] == 0:
-                self.writeback()
-            ast["idx"] = idx + 1
+            if not self._pre_step():
+                return False
+            self._astate["idx"] += 1
             self.m_step()
             return True
         except Exception as e:
             self._on_error(e)
             return False
+
+    def _pre_step(self):
+        """What precedes an iteration: criterion test (on the stop_rate beat), history record, log line, checkpoint.
+        False when the criterion is met (the closing log line and the final writeback are then done)."""
+        ast = self._astate
+        idx = ast["idx"]
+        if idx % ast["stop_rate"] == 0:
+            if ast["track_objective"]:
+                self._mstate["objective_func"] = self.objective_func().reshape(-1)
+            met = ast["stop_crit"].stop(self._mstate)
+            self._record_history()
+            if met:
+                self._log_iteration()
+                self._log_message(f"[{dt.datetime.now()}] Stopping Criterion satisfied -> END")
+                if self._final_writeback:
+                    self.writeback()
+                return False
+        if idx % ast["log_rate"] == 0:
+            self._log_iteration()
+        if ast["wb_rate"] is not None and idx % ast["wb_rate"] == 0:
+            self.writeback()
+        return True
 
     def _record_history(self):
         ast = self._astate
@@ -362,6 +400,32 @@ class Solver:
         if len(pend) >= 256 or (when - pend[0][0]).total_seconds() > 1.0:
             self._flush_log()
 
+    def _record_block(self, first_idx, info):
+        """History records (and log lines) of consecutive criterion tests replayed in one go: `info` maps the criterion's
+        fields to arrays, one entry per test; the test of iteration first_idx + i is entry i."""
+        ast = self._astate
+        keys = tuple(info)
+        m = len(next(iter(info.values()))) if info else 0
+        if m == 0:
+            return
+        cache = ast.get("history_dtype")
+        if cache is None or cache[0] != keys:
+            cache = ast["history_dtype"] = (keys, np.dtype([("iteration", np.int64)] + [(k, np.float64) for k in keys]))
+        recs = np.zeros(m, dtype=cache[1])
+        recs["iteration"] = first_idx + np.arange(m)
+        for k, v in info.items():
+            recs[k] = v
+        ast["history"].append(recs)
+        sel = recs if ast["log_rate"] == 1 else recs[recs["iteration"] % ast["log_rate"] == 0]
+        if len(sel):
+            if ast.get("live_log"):
+                for r in sel:
+                    ast["logger"].info(self._render_iteration(dt.datetime.now(), int(r["iteration"]), r))
+            else:
+                ast.setdefault("pending_log", []).append((dt.datetime.now(), None, sel))
+                if len(ast["pending_log"]) >= 256:
+                    self._flush_log()
+
     def _log_message(self, msg):
         self._flush_log()
         self._astate["logger"].info(msg)
@@ -389,7 +453,16 @@ class Solver:
         if not pend:
             return
         logger = self._astate.get("logger")
-        text = "".join(f"INFO -- {self._render_iteration(*rec)}\n" for rec in pend)
+        parts = []
+        for when, idx, rec in pend:
+            if idx is None:  # a block of records (see _record_block): one line group per row
+                names = rec.dtype.names[1:]
+                head = f"INFO -- [{when}] Iteration "
+                for row in rec.tolist():
+                    parts.append(head + f"{row[0]:>_d}\n\titeration: {row[0]}" + "".join(f"\n\t{n}: {v}" for n, v in zip(names, row[1:])) + "\n")
+            else:
+                parts.append(f"INFO -- {self._render_iteration(when, idx, rec)}\n")
+        text = "".join(parts)
         pend.clear()
         for h in (logger.handlers if logger is not None else ()):
             if isinstance(h, logging.FileHandler):

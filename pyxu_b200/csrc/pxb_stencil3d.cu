@@ -88,7 +88,7 @@ cudaError_t launch(const PxbSt3P& p, const CUtensorMap& map, T* out, cudaStream_
     const size_t smem = 2 * box_bytes + (size_t)p.s.bh * C::TX * sizeof(T);
     auto k = k_stencil3d<T, VEC, NV, K0>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = pxb_smem_attr_once((const void*)k, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const unsigned grid = (unsigned)((int64_t)p.s.ntx * p.s.nty * p.nchunk * p.batch);
@@ -116,7 +116,7 @@ int run(PxbSt3P& p, const void* in, void* out, cudaStream_t s, cudaError_t* err)
     const uint64_t stride[4] = {1, (uint64_t)p.s.n2, (uint64_t)s0, (uint64_t)p.vol};
     const uint32_t box[4] = {(uint32_t)p.s.bw, (uint32_t)p.s.bh, 1, 1};
     alignas(64) CUtensorMap map;
-    if (!pxb_tma_encode<T>(4, (const T*)in - (int64_t)p.lo_planes * s0, dim, stride, box, &map)) return 10;
+    if (!pxb_tma_encode_cached<T>(4, (const T*)in - (int64_t)p.lo_planes * s0, dim, stride, box, &map)) return 10;
     bool ok = false;
     switch (pxb_st2_nv(p.s.k2, VEC)) {
         case 1: ok = launch_k0<T, VEC, 1>(p, map, (T*)out, s, err); break;

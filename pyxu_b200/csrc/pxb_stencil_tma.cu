@@ -201,7 +201,7 @@ cudaError_t launch_mode(const PxbSt2P& p, const CUtensorMap& map, const CUtensor
     const unsigned grid = (unsigned)((int64_t)p.ngx * p.nty * p.nimg);
     auto k = p.tpc > 1 ? k_stencil2d_tma<T, VEC, NV, DENSE, MODE> : k_stencil2d_one<T, VEC, NV, DENSE, MODE>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = pxb_smem_attr_once((const void*)k, (int)smem);
         if (e != cudaSuccess) return e;
     }
     k<<<grid, C::NT, smem, s>>>(p, map, map2, out);
@@ -229,8 +229,8 @@ int run(PxbSt2P& p, const PxbSt2In* ext, const void* in, const void* in2, void* 
     const uint64_t stride[3] = {1, in_n2, in_n1 * in_n2};
     const uint32_t box[3] = {(uint32_t)p.bw, (uint32_t)p.bh, 1};
     alignas(64) CUtensorMap map, map2;
-    if (!pxb_tma_encode<T>(3, in, dim, stride, box, &map)) return 10;
-    if (!pxb_tma_encode<T>(3, in2 ? in2 : in, dim, stride, box, &map2)) return 10;
+    if (!pxb_tma_encode_cached<T>(3, in, dim, stride, box, &map)) return 10;
+    if (!pxb_tma_encode_cached<T>(3, in2 ? in2 : in, dim, stride, box, &map2)) return 10;
     const int mode = in2 ? 1 : (p.epi == 1 ? 2 : 0);
     const int nv = pxb_st2_nv(p.k2, VEC);
     switch (nv) {

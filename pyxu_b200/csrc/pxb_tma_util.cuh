@@ -4,6 +4,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
+
+#include <mutex>
 
 static __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -81,4 +84,52 @@ static inline bool pxb_tma_encode(int rank, const void* base, const uint64_t* di
     const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
     return fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ---- launch-side caches ---------------------------------------------------------------------------------
+// A solver iterates on the same few (pointer, geometry) pairs -- the two halves of a ping-pong, the boundary / interior
+// launches of a slab: their tensor maps are encoded once.  The key holds everything that goes into the encoding, so a
+// recycled pointer with another geometry can never hit a stale entry.  Per host thread, no lock.
+struct PxbMapKey {
+    const void* base;
+    uint64_t dim[5], stride[5];
+    uint32_t box[5];
+    int32_t rank, esize;
+};
+template <class T>
+static inline bool pxb_tma_encode_cached(int rank, const void* base, const uint64_t* dim, const uint64_t* stride, const uint32_t* box, CUtensorMap* out) {
+    constexpr int N = 32;
+    struct Entry { PxbMapKey key; CUtensorMap map; bool used; };
+    static thread_local Entry cache[N];
+    static thread_local int next = 0;
+    PxbMapKey k;
+    memset(&k, 0, sizeof(k));
+    k.base = base; k.rank = rank; k.esize = (int32_t)sizeof(T);
+    for (int i = 0; i < rank; ++i) { k.dim[i] = dim[i]; k.stride[i] = stride[i]; k.box[i] = box[i]; }
+    for (int i = 0; i < N; ++i)
+        if (cache[i].used && memcmp(&cache[i].key, &k, sizeof(k)) == 0) { *out = cache[i].map; return true; }
+    if (!pxb_tma_encode<T>(rank, base, dim, stride, box, out)) return false;
+    Entry& e = cache[next];
+    next = (next + 1) % N;
+    e.key = k; e.map = *out; e.used = true;
+    return true;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the function: set it the first time a kernel is launched
+// from this process, not on every launch
+static inline cudaError_t pxb_smem_attr_once(const void* kern, int bytes) {
+    constexpr int N = 128;
+    static const void* seen[N];
+    static int nseen = 0;
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (int i = 0; i < nseen; ++i)
+            if (seen[i] == kern) return cudaSuccess;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    if (nseen < N) seen[nseen++] = kern;
+    return cudaSuccess;
 }

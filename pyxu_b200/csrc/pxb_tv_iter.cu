@@ -6,6 +6,7 @@
 #include <initializer_list>
 
 #include "pxb_launch.cuh"
+#include "pxb_tma_util.cuh"
 #include "pxb_tv_iter.cuh"
 
 namespace {
@@ -15,6 +16,7 @@ template <class T, int VEC, int TXL, int TY, int NDIR, int ALGO, bool NORMS, boo
 __global__ void __launch_bounds__(TXL* TY, (TXL * TY >= 256 ? 3 : 6))
     k_tv_iter(const __grid_constant__ PxbTvP<T> q, const __grid_constant__ PxbIterGeom g, const __grid_constant__ PxbIterPtr<T> a) {
     using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
+    if (NORMS && pxb_iter_stopped(a.stop)) return;  // an earlier iteration of this batch met the stopping rule
     extern __shared__ __align__(16) unsigned char pxb_iter_smem[];
     T* smem = reinterpret_cast<T*>(pxb_iter_smem);
     const PxbIterItem it = pxb_iter_item(g, (int64_t)blockIdx.x, TY, C::T2);
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(TXL* TY, (TXL * TY >= 256 ? 3 : 6))
             if (l == 0) {
                 if (a.norms_x) { atomicAdd(a.norms_x + 2 * it.b, v[0]); atomicAdd(a.norms_x + 2 * it.b + 1, v[1]); }
                 if (a.norms_z) { atomicAdd(a.norms_z + 2 * it.b, v[2]); atomicAdd(a.norms_z + 2 * it.b + 1, v[3]); }
+                pxb_iter_finish(a.stop, a.norms_x, a.norms_z, gridDim.x);
             }
         }
     }
@@ -68,7 +71,7 @@ cudaError_t launch_inst(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterP
     using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
     auto kern = k_tv_iter<T, VEC, TXL, TY, NDIR, ALGO, NORMS, MODES>;
     if (C::SMEM > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaError_t e = pxb_smem_attr_once((const void*)kern, (int)C::SMEM);
         if (e != cudaSuccess) return e;
     }
     kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, a);
@@ -132,7 +135,7 @@ bool aligned16(std::initializer_list<const void*> ptrs) {
 // 0: launched; PXB_ENOSUP: the descriptor is outside the envelope of the single-kernel form (the caller falls
 // back to pxb_pds_primal + pxb_pds_dual); other negative codes: errors.
 int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out,
-                       void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s) {
+                       void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, const PxbIterStop* stop) {
     const void* sh = (p->f.kind == PXB_F_SQL2 && p->f.shift_period > 1) ? p->f.shift : nullptr;
     const void* ga = p->f.kind == PXB_F_GRADARR ? p->f.garr : nullptr;
     if (!aligned16({xu_in, z_in, xu_out, z_out, x_out, sh, ga})) return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: arrays must be 16-byte aligned");
@@ -142,7 +145,7 @@ int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p
     int why;
     // 3-D volumes: TMA-staged pipeline (pxb_tv_tma.cu) unless the direct-load form is forced or the TMA form declines
     if (K->ndir == 3 && pxb_iter_path() != 1) {
-        why = pxb_tv_tma_try(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, chunk_hint, s, &err);
+        why = pxb_tv_tma_try(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, chunk_hint, s, &err, stop);
         if (why == 0) {
             pxb_count_launch();
             if (err != cudaSuccess) return pxb_fail(PXB_ECUDA, "pxb_pds_iter (tma): %s", cudaGetErrorString(err));
@@ -151,7 +154,7 @@ int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p
         if (pxb_iter_path() == 2) return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: TMA form not applicable (reason %d)", why);
     } else if (K->ndir == 2 && pxb_iter_path() != 1 && chunk_hint == 0) {
         // 2-D images: TMA-staged tiles (pxb_tv_tile2d.cu); the marching direct-load form remains the fallback
-        why = pxb_tv_tile2d_try(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, s, &err);
+        why = pxb_tv_tile2d_try(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, s, &err, stop);
         if (why == 0) {
             pxb_count_launch();
             if (err != cudaSuccess) return pxb_fail(PXB_ECUDA, "pxb_pds_iter (tile2d): %s", cudaGetErrorString(err));
@@ -161,15 +164,36 @@ int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p
     } else if (pxb_iter_path() == 2) {
         return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: TMA form not applicable");
     }
+    const PxbIterStop st = stop ? *stop : PxbIterStop{};
     if (K->dtype == PXB_F32) {
-        PxbIterPtr<float> a{(const float*)xu_in, (const float*)z_in, (float*)xu_out, (float*)z_out, (float*)x_out, norms_x, norms_z};
+        PxbIterPtr<float> a{(const float*)xu_in, (const float*)z_in, (float*)xu_out, (float*)z_out, (float*)x_out, norms_x, norms_z, st};
         why = dispatch<float>(algo, *K, *p, a, chunk_hint, s, &err);
     } else {
-        PxbIterPtr<double> a{(const double*)xu_in, (const double*)z_in, (double*)xu_out, (double*)z_out, (double*)x_out, norms_x, norms_z};
+        PxbIterPtr<double> a{(const double*)xu_in, (const double*)z_in, (double*)xu_out, (double*)z_out, (double*)x_out, norms_x, norms_z, st};
         why = dispatch<double>(algo, *K, *p, a, chunk_hint, s, &err);
     }
     if (why) return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: not eligible for the single-kernel iteration (reason %d)", why);
     pxb_count_launch();
     if (err != cudaSuccess) return pxb_fail(PXB_ECUDA, "pxb_pds_iter: %s", cudaGetErrorString(err));
+    return 0;
+}
+
+// n iterations queued back to back on the stream, alternating the two (xu, z) pairs; see pxb_pds_iter_n in the header.
+int pxb_tv_iter_launch_n(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu_a, void* z_a, void* xu_b, void* z_b, void* x_out,
+                         double* norms, int n, const pxb_stop_rule* rule, void* ctl, cudaStream_t s) {
+    PxbIterStop st{};
+    st.ctl = (int32_t*)ctl;
+    st.eps_x = rule->eps_x; st.eps_z = rule->eps_z;
+    st.all_x = rule->all_x; st.all_z = rule->all_z;
+    st.table = rule->table;
+    st.rows = (int32_t)K->batch;
+    const int64_t per = 4 * K->batch;
+    for (int i = 0; i < n; ++i) {
+        double* nx = rule->eps_x > 0 ? norms + (int64_t)i * per : nullptr;
+        double* nz = rule->eps_z > 0 ? norms + (int64_t)i * per + 2 * K->batch : nullptr;
+        const bool even = (i & 1) == 0;
+        int rc = pxb_tv_iter_launch(algo, K, p, even ? xu_a : xu_b, even ? z_a : z_b, even ? xu_b : xu_a, even ? z_b : z_a, x_out, nx, nz, 0, s, &st);
+        if (rc != 0) return i == 0 ? rc : pxb_fail(PXB_ECUDA, "pxb_pds_iter_n: launch %d of %d failed after earlier ones succeeded", i, n);
+    }
     return 0;
 }

@@ -41,6 +41,17 @@ struct PxbIterGeom {
     int64_t nblocks;
 };
 
+// Device-side stopping rule of iterations launched back to back without the host in the loop (pxb_pds_iter_n): the last
+// thread block of an iteration evaluates RelError on the sums the iteration accumulated and, when the rule is met, raises
+// ctl[0]; the launches queued behind it return at once.  ctl = {stop, done, ticket, -}: pxb_iter_ctl on the device.
+struct PxbIterStop {
+    int32_t* ctl;         // null: single launch, the host evaluates the criterion
+    double eps_x, eps_z;  // RelError thresholds (<= 0: the variable takes no part)
+    int32_t all_x, all_z; // over the batch rows: every row (1) / any row (0)   (satisfy_all, stop.py:353-382)
+    int32_t table;        // bit (2*px + pz): stop for that combination of outcomes
+    int32_t rows;
+};
+
 template <class T>
 struct PxbIterPtr {
     const T* u_in;   // PD3O: u     CV: x
@@ -50,7 +61,40 @@ struct PxbIterPtr {
     T* x_out;        // PD3O only, nullable: x is then not materialised (36 B/voxel form)
     double* norms_x; // nullable pair per batch row (RelError[x])
     double* norms_z;
+    PxbIterStop stop;
 };
+
+#ifdef __CUDACC__
+static __device__ __forceinline__ bool pxb_iter_stopped(const PxbIterStop& s) {
+    return s.ctl != nullptr && *reinterpret_cast<const volatile int32_t*>(s.ctl) != 0;
+}
+// Called by the one thread of a block that has just added the block's sums: the block that draws the last ticket sees every
+// block's contribution (fence before the ticket), evaluates the rule exactly as the host does -- sqrt(num) <= eps * sqrt(den) in
+// IEEE double, the same operations NumPy performs (stop.py:371-378) -- and counts the iteration.
+static __device__ __forceinline__ void pxb_iter_finish(const PxbIterStop& s, const double* nx, const double* nz, unsigned nblocks) {
+    if (s.ctl == nullptr) return;
+    __threadfence();
+    unsigned* ticket = reinterpret_cast<unsigned*>(s.ctl + 2);
+    if (atomicAdd(ticket, 1u) != nblocks - 1u) return;
+    *ticket = 0u;  // (the next launch starts once this kernel has ended)
+    __threadfence();
+    auto met = [&](const double* n, double eps, int all) -> int {
+        if (n == nullptr || !(eps > 0.0)) return 0;
+        bool every = true, some = false;
+        for (int r = 0; r < s.rows; ++r) {
+            const double num = sqrt(__ldcg(n + 2 * r)), den = sqrt(__ldcg(n + 2 * r + 1));
+            const bool ok = num <= eps * den;
+            every = every && ok;
+            some = some || ok;
+        }
+        return (all ? every : some) ? 1 : 0;
+    };
+    const int px = met(nx, s.eps_x, s.all_x), pz = met(nz, s.eps_z, s.all_z);
+    s.ctl[1] += 1;
+    if ((s.table >> (2 * px + pz)) & 1) *reinterpret_cast<volatile int32_t*>(s.ctl) = 1;
+    __threadfence();
+}
+#endif
 
 struct PxbIterItem {
     int64_t lin_base;  // offset of the image in u-like arrays

@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(256, 3)
                 const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_zr,
                 const __grid_constant__ CUtensorMap map_zc) {
     using C = PxbT2Cfg<T, VEC>;
+    if (NORMS && pxb_iter_stopped(a.stop)) return;  // an earlier iteration of this batch met the stopping rule
     extern __shared__ __align__(128) unsigned char pxb_t2_smem[];
     __shared__ __align__(8) uint64_t bar;
     T* sm = reinterpret_cast<T*>(pxb_t2_smem);
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256, 3)
                 for (int k = 0; k < 4; ++k) s4[k] += red[k][i];
             if (a.norms_x) { atomicAdd(a.norms_x + 2 * it.b, s4[0]); atomicAdd(a.norms_x + 2 * it.b + 1, s4[1]); }
             if (a.norms_z) { atomicAdd(a.norms_z + 2 * it.b, s4[2]); atomicAdd(a.norms_z + 2 * it.b + 1, s4[3]); }
+            pxb_iter_finish(a.stop, a.norms_x, a.norms_z, gridDim.x);
         }
     }
 }
@@ -67,13 +69,13 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
     const uint64_t dim_s[3] = {(uint64_t)g.n2, (uint64_t)g.n1, (uint64_t)(g.sh_mode ? g.n0 : g.nimg)};
     const uint32_t box[3] = {(uint32_t)C::BW, (uint32_t)C::BR, 1}, boxz[3] = {(uint32_t)C::BW, (uint32_t)C::BRZ, 1};
     const void* sptr = q.fkind == PXB_F_GRADARR ? (const void*)q.garr : (const void*)q.shift;
-    if (!pxb_tma_encode<T>(3, a.u_in, dim_u, stride, box, &tu) || !pxb_tma_encode<T>(3, g.has_shift ? sptr : (const void*)a.u_in, g.has_shift ? dim_s : dim_u, stride, box, &ts) ||
-        !pxb_tma_encode<T>(3, a.z_in, dim_z, stride, boxz, &tzr) || !pxb_tma_encode<T>(3, a.z_in, dim_z, stride, box, &tzc))
+    if (!pxb_tma_encode_cached<T>(3, a.u_in, dim_u, stride, box, &tu) || !pxb_tma_encode_cached<T>(3, g.has_shift ? sptr : (const void*)a.u_in, g.has_shift ? dim_s : dim_u, stride, box, &ts) ||
+        !pxb_tma_encode_cached<T>(3, a.z_in, dim_z, stride, boxz, &tzr) || !pxb_tma_encode_cached<T>(3, a.z_in, dim_z, stride, box, &tzc))
         return 23;
     bool fwd = true;
     for (int k = 0; k < 2; ++k) fwd = fwd && cf.cm[k] == 0.0 && cf.cp[k] != 0.0;
     auto go = [&](auto kern) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaError_t e = pxb_smem_attr_once((const void*)kern, (int)C::SMEM);
         if (e != cudaSuccess) { *err = e; return; }
         kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, a, tu, ts, tzr, tzc);
         *err = cudaGetLastError();
@@ -92,12 +94,13 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
 
 // > 0: not eligible (reason), 0: launched (or *err set)
 int pxb_tv_tile2d_try(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out, void* z_out,
-                      void* x_out, double* norms_x, double* norms_z, cudaStream_t s, cudaError_t* err) {
+                      void* x_out, double* norms_x, double* norms_z, cudaStream_t s, cudaError_t* err, const PxbIterStop* stop) {
     if (K->ndir != 2) return 2;
     const bool norms = norms_x || norms_z;
+    const PxbIterStop st = stop ? *stop : PxbIterStop{};
 #define PXB_T2_GO(T)                                                                                                  \
     {                                                                                                                 \
-        PxbIterPtr<T> a{(const T*)xu_in, (const T*)z_in, (T*)xu_out, (T*)z_out, (T*)x_out, norms_x, norms_z};         \
+        PxbIterPtr<T> a{(const T*)xu_in, (const T*)z_in, (T*)xu_out, (T*)z_out, (T*)x_out, norms_x, norms_z, st};     \
         if (algo == PXB_PD3O) return norms ? run<T, PXB_PD3O, true>(*K, *p, a, s, err) : run<T, PXB_PD3O, false>(*K, *p, a, s, err); \
         return norms ? run<T, PXB_CV, true>(*K, *p, a, s, err) : run<T, PXB_CV, false>(*K, *p, a, s, err);            \
     }

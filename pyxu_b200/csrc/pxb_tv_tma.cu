@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(32 * TY, 2)
                   const __grid_constant__ PxbIterPtr<T> a, const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s,
                   const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_z1) {
     using C = PxbTmaCfg<T, VEC, TY>;
+    if (NORMS && pxb_iter_stopped(a.stop)) return;  // an earlier iteration of this batch met the stopping rule
     extern __shared__ __align__(128) unsigned char pxb_tma_smem[];
     T* stages = reinterpret_cast<T*>(pxb_tma_smem);
     T* ring = reinterpret_cast<T*>(pxb_tma_smem + C::SMEM_STAGES);
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(32 * TY, 2)
                 for (int kk = 0; kk < 4; ++kk) s4[kk] += red[kk][i];
             if (a.norms_x) { atomicAdd(a.norms_x + 2 * it.b, s4[0]); atomicAdd(a.norms_x + 2 * it.b + 1, s4[1]); }
             if (a.norms_z) { atomicAdd(a.norms_z + 2 * it.b, s4[2]); atomicAdd(a.norms_z + 2 * it.b + 1, s4[3]); }
+            pxb_iter_finish(a.stop, a.norms_x, a.norms_z, gridDim.x);
         }
     }
 }
@@ -123,14 +125,14 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
     PxbTmaBoxDesc mz1 = mz;
     mz1.box[1] = C::BR1;
     alignas(64) CUtensorMap tu, ts, tz, tz1;
-    auto enc = [](const PxbTmaBoxDesc& m, CUtensorMap* out) { return pxb_tma_encode<T>(5, m.base, m.dim, m.stride, m.box, out); };
+    auto enc = [](const PxbTmaBoxDesc& m, CUtensorMap* out) { return pxb_tma_encode_cached<T>(5, m.base, m.dim, m.stride, m.box, out); };
     if (!enc(mu, &tu) || !enc(ms, &ts) || !enc(mz, &tz) || !enc(mz1, &tz1)) return 23;
     // specialised instances: forward differences + L21 + shifted squared-l2 data term staged per voxel + g in
     // {positivity, none}; everything else runs the generic instance
     const int spec = pxb_tma_pick_spec<T>(cf, q, tg);
     auto go = [&](auto kern) {
         // (the attribute is per function: set it on every launch path once; cheap enough to repeat)
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaError_t e = pxb_smem_attr_once((const void*)kern, (int)C::SMEM);
         if (e != cudaSuccess) { *err = e; return; }
         kern<<<(unsigned)g.nblocks, C::NT, C::SMEM, s>>>(q, g, tg, a, tu, ts, tz, tz1);
         *err = cudaGetLastError();
@@ -160,12 +162,13 @@ int dispatch(int algo, const pxb_grad_desc& d, const pxb_pds_params& P, const Px
 
 // > 0: not eligible (reason), 0: launched (or *err set)
 int pxb_tv_tma_try(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out, void* z_out,
-                   void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, cudaError_t* err) {
+                   void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, cudaError_t* err, const PxbIterStop* stop) {
     if (K->ndir != 3) return 20;
+    const PxbIterStop st = stop ? *stop : PxbIterStop{};
     if (K->dtype == PXB_F32) {
-        PxbIterPtr<float> a{(const float*)xu_in, (const float*)z_in, (float*)xu_out, (float*)z_out, (float*)x_out, norms_x, norms_z};
+        PxbIterPtr<float> a{(const float*)xu_in, (const float*)z_in, (float*)xu_out, (float*)z_out, (float*)x_out, norms_x, norms_z, st};
         return dispatch<float>(algo, *K, *p, a, chunk_hint, s, err);
     }
-    PxbIterPtr<double> a{(const double*)xu_in, (const double*)z_in, (double*)xu_out, (double*)z_out, (double*)x_out, norms_x, norms_z};
+    PxbIterPtr<double> a{(const double*)xu_in, (const double*)z_in, (double*)xu_out, (double*)z_out, (double*)x_out, norms_x, norms_z, st};
     return dispatch<double>(algo, *K, *p, a, chunk_hint, s, err);
 }

@@ -363,6 +363,112 @@ class _PrimalDualSplitting(Solver):
             self._x_stale = True
         return True
 
+    # -- iterations queued back to back, the stopping rule tested on the device (pxb_pds_iter_n) ---------------------------
+    _BATCH_MAX = 256       # iterations per native call, at most
+    _BATCH_SECONDS = 0.25  # ... and no more than about this much device time: the log / history lag the device by one batch
+
+    def _batch_rule(self):
+        """The device-side form of the stopping criterion (K.StopRule) when this solve can run with the host out of the loop:
+        BLOCK mode, single-kernel iteration with a pointwise data term, RelError sums fused, a criterion made of MaxIter /
+        ManualStop / RelError leaves, nothing that needs the host between iterations (objective tracking, checkpoints)."""
+        ast, pl = self._astate, self._plan
+        from ...abc.solver import Mode
+
+        if ast["mode"] is not Mode.BLOCK or self._slab is not None or pl is None or pl.kind != "fused" or pl.fkind == K.F_GRADARR:
+            return None
+        if self._nrm is None or ast["track_objective"] or ast["wb_rate"] is not None or ast["stop_rate"] != 1 or self._x_every:
+            return None
+        crit = ast["stop_crit"]
+        try:
+            table = sum(int(bool(crit._device_eval(bool(px), bool(pz)))) << (2 * px + pz) for px in (0, 1) for pz in (0, 1))
+        except NotImplementedError:
+            return None
+        leaves = {}
+        for var, eps, every in crit._device_leaves():
+            if leaves.setdefault(var, (eps, every)) != (eps, every):
+                return None  # two different tests on the same variable
+        if not leaves or not set(leaves) <= {"x", "z"} or ("x" in leaves) != (self._nx is not None) or ("z" in leaves) != (self._nz is not None):
+            return None
+        r = K.StopRule()
+        r.eps_x, r.all_x = leaves.get("x", (0.0, True))
+        r.eps_z, r.all_z = leaves.get("z", (0.0, True))
+        r.table = table
+        return r
+
+    def _fit_run(self):
+        rule = self._batch_rule() if self._plan is not None else None
+        if rule is None:
+            return super()._fit_run()
+        try:
+            self._run_batched(rule)
+        except Exception as e:
+            self._on_error(e)
+        self._astate.update(mode=None, active=None, worker=None)
+        self._cleanup_logger()
+
+    def _run_batched(self, rule):
+        import time
+
+        import torch
+
+        ast, mst, pl = self._astate, self._mstate, self._plan
+        crit = ast["stop_crit"]
+        # the first iteration goes through m_step(): it decides whether pxb_pds_iter serves this problem at all
+        if not self._pre_step():
+            return
+        ast["idx"] += 1
+        self.m_step()
+        if pl.iter_ok is not True:
+            while self._step():
+                pass
+            return
+        algo = self._ALGO
+        key = "u" if algo == K.ALGO_PD3O else "x"
+        rows = pl.batch
+        cap, per_iter = 8, None
+        buf = torch.empty(self._BATCH_MAX * 4 * rows + 2, dtype=torch.float64, device=mst["z"].device)  # sums of every iteration | ctl
+        ctl_view = buf[-2:].view(torch.int32)
+        p = pl.params(mst)
+        fused = mst["_fused_norms"]
+        while True:
+            if not self._pre_step():  # the test that follows the last iteration carried out (host side, as in the reference's loop)
+                return
+            n = int(min(cap, self._BATCH_MAX, crit._budget()))
+            if n < 2:
+                ast["idx"] += 1
+                self.m_step()
+                continue
+            if pl.alt is None:
+                pl.alt = (A.empty_like(mst[key]), A.empty_like(mst["z"]))
+            want_x = algo == K.ALGO_PD3O and self._nx is not None
+            buf.zero_()
+            t0 = time.perf_counter()
+            rc = K.lib().pxb_pds_iter_n(algo, C.byref(pl.gdesc), C.byref(p), A.ptr(mst[key]), A.ptr(mst["z"]), A.ptr(pl.alt[0]), A.ptr(pl.alt[1]),
+                                        A.ptr(mst["x"]) if want_x else None, A.ptr(buf), n, C.byref(rule), A.ptr(ctl_view), A.stream())
+            K.check(rc, "pxb_pds_iter_n")
+            host = buf.cpu()  # ONE readback per batch: the sums of its iterations and the control block
+            done = int(host[-2:].view(torch.int32)[1])
+            dt = time.perf_counter() - t0
+            assert 1 <= done <= n, (done, n)
+            sums = host[: done * 4 * rows].numpy().reshape(done, 2, rows, 2)
+            if done % 2:  # the iterate is in the other pair
+                cur = pl.alt
+                pl.alt = (mst[key], mst["z"])
+                mst[key], mst["z"] = cur
+            if algo == K.ALGO_PD3O and not want_x:
+                self._x_stale = True
+            idx0 = ast["idx"]
+            ast["idx"] = idx0 + done
+            if done > 1:  # the tests between the iterations of the batch: none of them stopped it
+                decisions, info = crit._replay(sums[: done - 1])
+                if bool(np.any(decisions)):
+                    raise RuntimeError("pxb_pds_iter_n went past an iteration at which the host-side criterion stops")
+                self._record_block(idx0 + 1, info)
+            # the sums of the last iteration wait for the test at the top of the loop
+            fused["_host"], fused["_stamp"] = sums[done - 1], 0
+            per_iter = dt / done if per_iter is None else min(per_iter, dt / done)
+            cap = max(2, min(cap * 2, self._BATCH_MAX, int(self._BATCH_SECONDS / max(per_iter, 1e-7))))
+
     def _materialize(self, name):
         """x of PD3O is not written by the single-kernel iteration unless something needs it every step; rebuild it
         on demand from the previous iterate: x_k = prox_{tau g}(u_{k-1} - tau K^T z_{k-1})  (pds.py:747-750)."""

@@ -39,6 +39,17 @@ class MaxIter(StoppingCriterion):
     def clear(self):
         self._i = 0
 
+    def _device_eval(self, px, pz):
+        return False
+
+    def _budget(self):
+        return self._n - self._i + 1  # iterations that may run before the test after the last of them can be the one that fires
+
+    def _replay(self, sums):
+        calls = self._i + 1 + np.arange(len(sums))
+        self._i += len(sums)
+        return calls > self._n, dict(N_iter=calls)
+
     def _state_vars(self):
         return frozenset()
 
@@ -52,6 +63,12 @@ class ManualStop(StoppingCriterion):
 
     def info(self):
         return dict()
+
+    def _device_eval(self, px, pz):
+        return False
+
+    def _replay(self, sums):
+        return np.zeros(len(sums), dtype=bool), dict()
 
     def _state_vars(self):
         return frozenset()
@@ -196,6 +213,29 @@ class RelError(_NormCriterion):
 
     def _fused_vars(self):
         return frozenset([self._var]) if (self._f is None and self._norm == 2) else frozenset()
+
+    def _device_eval(self, px, pz):
+        if not self._fused_vars() or self._var not in ("x", "z"):
+            raise NotImplementedError
+        return px if self._var == "x" else pz
+
+    def _device_leaves(self):
+        return [(self._var, float(self._eps), bool(self._satisfy_all))]
+
+    def _replay(self, sums):
+        if not (self._started and self._fused_vars()):
+            raise NotImplementedError
+        sq = np.asarray(sums)[:, 0 if self._var == "x" else 1]  # (m, rows, 2)
+        num, den = np.sqrt(sq[..., 0]), np.sqrt(sq[..., 1])
+        ok = num <= self._eps * den
+        decisions = ok.all(axis=1) if self._satisfy_all else ok.any(axis=1)
+        with np.errstate(all="ignore"):
+            val = num / den
+        val[np.isnan(val)] = 0
+        self._val = val[-1].reshape(-1, 1)
+        if val.shape[1] == 1:
+            return decisions, {self._label(): val[:, 0]}
+        return decisions, {f"{self._label()}_min": val.min(axis=1), f"{self._label()}_max": val.max(axis=1)}
 
     def stop(self, state):
         fused = state.get("_fused_norms", {}).get(self._var) if isinstance(state, dict) else None

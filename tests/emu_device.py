@@ -185,6 +185,37 @@ class EmuLib:
         return self._ok("pds_iter:direct", self.h.emu_tv_iter(*args))
 
 
+    def pxb_pds_iter_n(self, algo, Kd, p, xu_a, z_a, xu_b, z_b, x, norms, n, rule, ctl, stream):
+        """pxb_tv_iter_launch_n + the device-side rule of pxb_iter_finish (pxb_tv_iter.cuh), restated: iteration i accumulates into
+        norms[i], the rule is tested after it, later iterations do nothing once it is met."""
+        if Kd is None or p is None or rule is None or n < 1:
+            return EINVAL
+        g, r = self._gdesc(Kd), self._gdesc(rule)
+        rows = int(g.batch)
+        addr = lambda q: q.value if hasattr(q, "value") else q
+        ctl_arr = np.ctypeslib.as_array(C.cast(addr(ctl), C.POINTER(C.c_int32)), shape=(4,))
+        nrm = np.ctypeslib.as_array(C.cast(addr(norms), C.POINTER(C.c_double)), shape=(n, 2, rows, 2))
+        for i in range(n):
+            if ctl_arr[0]:
+                break
+            nx = C.c_void_p(addr(norms) + 8 * (i * 4 * rows)) if r.eps_x > 0 else None
+            nz = C.c_void_p(addr(norms) + 8 * (i * 4 * rows + 2 * rows)) if r.eps_z > 0 else None
+            pair = (xu_a, z_a, xu_b, z_b) if i % 2 == 0 else (xu_b, z_b, xu_a, z_a)
+            rc = self.pxb_pds_iter(algo, Kd, p, *pair, x, nx, nz, stream)
+            if rc != 0:
+                return rc if i == 0 else -2
+            def met(k, eps, every):
+                if not eps > 0:
+                    return 0
+                ok = np.sqrt(nrm[i, k, :, 0]) <= eps * np.sqrt(nrm[i, k, :, 1])
+                return int(ok.all() if every else ok.any())
+            px, pz = met(0, r.eps_x, r.all_x), met(1, r.eps_z, r.all_z)
+            ctl_arr[1] += 1
+            if (r.table >> (2 * px + pz)) & 1:
+                ctl_arr[0] = 1
+        return 0
+
+
 class _Stream:  # stands in for torch.cuda.Stream / Event: the emulated device executes every call synchronously
     def __init__(self, *a, **k):
         pass

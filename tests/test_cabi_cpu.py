@@ -35,8 +35,10 @@ def test_struct_layouts_match_the_c_compiler():
     #include <stddef.h>
     #include "pyxu_b200.h"
     int main(void){
-      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pxb_slab), sizeof(pxb_stencil_desc), sizeof(pxb_grad_desc),
-             sizeof(pxb_prox_spec), sizeof(pxb_fterm), sizeof(pxb_pds_params), sizeof(pxb_stencil2d), sizeof(pxb_fista_step), sizeof(pxb_pad2d_desc));
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pxb_slab), sizeof(pxb_stencil_desc), sizeof(pxb_grad_desc),
+             sizeof(pxb_prox_spec), sizeof(pxb_fterm), sizeof(pxb_pds_params), sizeof(pxb_stencil2d), sizeof(pxb_fista_step), sizeof(pxb_pad2d_desc),
+             sizeof(pxb_stop_rule), sizeof(pxb_iter_ctl));
+      printf("%zu %zu ", offsetof(pxb_stop_rule, table), offsetof(pxb_iter_ctl, ticket));
       printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", offsetof(pxb_stencil_desc, coef), offsetof(pxb_grad_desc, coef),
              offsetof(pxb_grad_desc, slab), offsetof(pxb_pds_params, lam), offsetof(pxb_stencil2d, coef), offsetof(pxb_stencil2d, add_period),
              offsetof(pxb_fista_step, norms), offsetof(pxb_stencil2d, origin), offsetof(pxb_pad2d_desc, mode));
@@ -48,8 +50,8 @@ def test_struct_layouts_match_the_c_compiler():
         exe = os.path.join(td, "t")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
-    sizes = [C.sizeof(s) for s in (K.Slab, K.StencilDesc, K.GradDesc, K.ProxSpec, K.FTerm, K.PdsParams, K.Stencil2D, K.FistaStep, K.Pad2D)]
-    offs = [K.StencilDesc.coef.offset, K.GradDesc.coef.offset, K.GradDesc.slab.offset, K.PdsParams.lam.offset, K.Stencil2D.coef.offset,
+    sizes = [C.sizeof(s) for s in (K.Slab, K.StencilDesc, K.GradDesc, K.ProxSpec, K.FTerm, K.PdsParams, K.Stencil2D, K.FistaStep, K.Pad2D, K.StopRule, K.IterCtl)]
+    offs = [K.StopRule.table.offset, K.IterCtl.ticket.offset, K.StencilDesc.coef.offset, K.GradDesc.coef.offset, K.GradDesc.slab.offset, K.PdsParams.lam.offset, K.Stencil2D.coef.offset,
             K.Stencil2D.add_period.offset, K.FistaStep.norms.offset, K.Stencil2D.origin.offset, K.Pad2D.mode.offset]
     assert [int(v) for v in out] == sizes + offs
 
@@ -65,6 +67,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     one = (C.c_int64 * 3)(4, 4, 4)
     assert lib.pxb_stencil_axis0_apply(0, 1, one, None, 3, 5, (C.c_double * 3)(1, 2, 1), C.c_void_p(16), C.c_void_p(32), None) == -1  # center outside the kernel
     assert lib.pxb_pds_iter(0, None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.pxb_pds_iter_n(0, None, None, None, None, None, None, None, None, 4, None, None, None) == -1
     assert lib.pxb_set_iter_path(7) == -1 and lib.pxb_set_iter_path(0) == 0
     assert lib.pxb_set_iter_modes(2) == -1
     g = K.GradDesc()

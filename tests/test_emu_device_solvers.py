@@ -35,6 +35,15 @@ def test_default_stop_iteration_count_and_cv(dev):
     G.test_cv_tv2d(dev)
 
 
+@pytest.mark.parametrize("case", ["pd3o2d", "cv2d", "pd3o3d_maxiter_or_relerr", "pd3o_stacked_any"])
+def test_iterations_queued_back_to_back_equal_one_launch_per_iteration(dev, case, monkeypatch):
+    calls = []
+    real = dev.lib.pxb_pds_iter_n
+    dev.lib.pxb_pds_iter_n = lambda *a: (calls.append(a[9]), real(*a))[1]
+    G.test_iterations_queued_back_to_back_equal_one_launch_per_iteration(dev, case, monkeypatch)
+    assert len(calls) >= 1 and calls[0] == 8  # the batched loop did run (first batch: 8 iterations)
+
+
 @pytest.mark.parametrize("mode", ["reflect", "wrap", "symmetric", "edge"])
 def test_pd3o_tv2d_folding_modes_run_the_single_kernel_form(dev, mode):
     G.test_pd3o_tv2d_modes(dev, mode)

@@ -74,6 +74,53 @@ def test_pd3o_tv2d_default_stop_iteration_count(px):
     assert len(hist2) == len(hist)
 
 
+@pytest.mark.parametrize("case", ["pd3o2d", "cv2d", "pd3o3d_maxiter_or_relerr", "pd3o_stacked_any"])
+def test_iterations_queued_back_to_back_equal_one_launch_per_iteration(px, case, monkeypatch):
+    """pxb_pds_iter_n (the stopping rule tested on the device, the host replays history and log from the recorded sums) against
+    the loop that launches one iteration at a time: same iteration count, bit-identical history, iterates and log text."""
+    import re
+
+    from pyxu_b200.opt.solver import pds
+
+    g = golden("solvers.npz")
+    res = []
+    for batched in (True, False):
+        if not batched:
+            monkeypatch.setattr(pds._PrimalDualSplitting, "_batch_rule", lambda self: None)
+        kw = {}
+        if case == "pd3o2d":
+            y = g["pd3o_tv2d/y"]
+            slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.1)
+            x0 = y.reshape(-1).copy()
+        elif case == "cv2d":
+            y = g["pd3o_tv2d/y"]
+            slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.1, solver="CondatVu")
+            x0 = y.reshape(-1).copy()
+        elif case == "pd3o3d_maxiter_or_relerr":
+            y = g["pd3o_tv3d/y"]
+            slv = cases.build_tv_denoise(px, y, (10, 12, 14), lam=0.08)
+            x0 = y.reshape(-1).copy()
+            kw = dict(stop_crit=px.stop.MaxIter(37) | px.stop.RelError(eps=1e-5, var="z"))  # z only: PD3O's x is rebuilt on demand
+        else:  # a stack of three problems: the rule must hold for ANY row
+            y = np.stack([g["pd3o_tv2d/y"] * s_ for s_ in (1.0, 0.5, 2.0)]).reshape(3, -1)
+            N = y.shape[1]
+            slv = px.solver.PD3O(f=0.5 * px.operator.SquaredL2Norm(dim=N).argshift(-y), g=px.operator.PositiveOrthant(dim=N),
+                                 h=0.1 * px.operator.L21Norm(arg_shape=(2, 32, 40), l2_axis=(0,)), K=px.operator.Gradient(arg_shape=(32, 40)),
+                                 show_progress=False)
+            x0 = y.copy()
+            kw = dict(stop_crit=px.stop.RelError(eps=2e-4, var="x", satisfy_all=False) | px.stop.MaxIter(400))
+        slv.fit(x0=x0, **kw)
+        assert slv._astate.get("error") is None, slv._astate.get("error")
+        data, hist = slv.stats()
+        res.append((data, hist, re.sub(r"\[\d{4}-[^\]]*\]", "[t]", open(slv.logfile).read())))
+    (d1, h1, l1), (d0, h0, l0) = res
+    assert len(h1) == len(h0) and np.array_equal(h1, h0)
+    assert np.array_equal(np.asarray(d1["x"]), np.asarray(d0["x"])) and np.array_equal(np.asarray(d1["z"]), np.asarray(d0["z"]))
+    assert l1 == l0
+    if case == "pd3o2d":
+        assert len(h1) == int(g["pd3o_tv2d/default_stop/n_hist"])  # ... which is the reference's own iteration count
+
+
 @pytest.mark.parametrize("mode", ["reflect", "wrap", "symmetric", "edge"])
 def test_pd3o_tv2d_modes(px, mode):
     g = golden("solvers.npz")
