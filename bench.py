@@ -638,7 +638,7 @@ def main():
             env.barrier()
             dt = env.max_over_ranks(time.perf_counter() - t0)
             assert slv2._astate.get("error") is None, slv2._astate.get("error")
-            assert slv2._plan.kind == "fused" and "_fused_norms" in slv2._mstate and len(slv2._astate["history"]) == K + 1
+            assert slv2._plan.kind == "fused" and "_fused_norms" in slv2._mstate and sum(len(h_) for h_ in slv2._astate["history"]) == K + 1
             x_loc = getattr(x_host, "local", x_host)
             assert isinstance(x_loc, np.ndarray) and x_loc.size == local_vox and np.isfinite(x_loc[:: max(1, local_vox // 1000)]).all()
             tm = slv2._astate["timing"]
@@ -649,7 +649,8 @@ def main():
         e2e = {"value": nvox * K / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(2 * 4 * nvox / K),
                "d2h_bytes_per_step": int(4 * nvox / K + 16 * world), "seconds": dt, "parts": runs[1], "first_call": runs[0],
                "what": "per rank: PD3O(...).fit(x0=<pinned host array>, stop_crit=MaxIter(K)|RelError[x]) + solution(): H2D of x0 and of the data y "
-                       "(this rank's planes), K fused iterations with the RelError sums (all-reduced on N ranks) read back every step, D2H of x into a "
+                       "(this rank's planes), K fused iterations with RelError[x] tested after every one of them (1 GPU: on the device, iterations "
+                       "queued back to back, sums read back per batch; N ranks: sums all-reduced and read back every step), D2H of x into a "
                        "pinned result buffer reserved beforehand (reserve_host_results); wall clock between barriers, max over ranks; second of two "
                        "calls (the first one, which also pays one-off initialisation, is `first_call`)"}
         A_.release_host_results()

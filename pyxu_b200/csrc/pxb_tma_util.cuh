@@ -115,21 +115,22 @@ static inline bool pxb_tma_encode_cached(int rank, const void* base, const uint6
     return true;
 }
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the function: set it the first time a kernel is launched
-// from this process, not on every launch
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the function: raise it when a launch needs more than any
+// earlier launch of that kernel from this process did (some kernels size their shared memory at run time), not on every launch
 static inline cudaError_t pxb_smem_attr_once(const void* kern, int bytes) {
-    constexpr int N = 128;
+    constexpr int N = 256;
     static const void* seen[N];
+    static int granted[N];
     static int nseen = 0;
     static std::mutex mu;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        for (int i = 0; i < nseen; ++i)
-            if (seen[i] == kern) return cudaSuccess;
-    }
+    std::lock_guard<std::mutex> lk(mu);
+    int slot = -1;
+    for (int i = 0; i < nseen; ++i)
+        if (seen[i] == kern) { slot = i; break; }
+    if (slot >= 0 && granted[slot] >= bytes) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    std::lock_guard<std::mutex> lk(mu);
-    if (nseen < N) seen[nseen++] = kern;
+    if (slot < 0 && nseen < N) { slot = nseen++; seen[slot] = kern; }
+    if (slot >= 0) granted[slot] = bytes;
     return cudaSuccess;
 }

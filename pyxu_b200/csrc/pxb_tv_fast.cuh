@@ -219,35 +219,44 @@ PXB_HD void pxb_tv_nbr(const PxbTvP<T>& q, int ax, int i, int w, int n, int& d_l
 // vector load for a row / plane face, one scalar load by one lane for a column face).
 //   zimg: component 0 of the batch item, sample (0, 0, 0);  the W samples (i0, i1, i2..) lie inside the domain.
 // ---------------------------------------------------------------------------------------------------------
-template <class T, int W, int NDIR>
+// (The tests come first and everything else -- addresses included -- sits inside the taken branches: ncu on the 512^3 reflect
+//  instance showed the unconditional 64-bit address arithmetic of the first version as 125 M of the 182 M instructions the MODES
+//  instance executed on top of the 'constant' one.)  LO = false drops the fold_lo terms at compile time (forward differences).
+template <class T, int W, int NDIR, bool LO = true>
 PXB_HD void pxb_tv_fold_kz(const PxbTvP<T>& q, const T* __restrict__ zimg, int i0, int i1, int i2, T* kz) {
-    const int64_t v = (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1;
     for (int k = 0; k < NDIR; ++k) {
         const int ax = 3 - NDIR + k;
-        const T* __restrict__ zk = zimg + k * q.vol;
         if (ax == 2) {
-            const int th = q.fold_hi[2], tl = q.fold_lo[2];
-            if (th >= i2 && th < i2 + W) {
-                const T zf = zk[v + q.n2 - 1];
-                for (int j = 0; j < W; ++j)
-                    if (i2 + j == th) kz[j] += q.cp[k] * zf;
-            }
-            if (tl >= i2 && tl < i2 + W) {
-                const T zf = zk[v];
-                for (int j = 0; j < W; ++j)
-                    if (i2 + j == tl) kz[j] += q.cm[k] * zf;
+            const int th = q.fold_hi[2], tl = LO ? q.fold_lo[2] : PXB_NOSRC;
+            const bool hi = th >= i2 && th < i2 + W, lo = LO && tl >= i2 && tl < i2 + W;
+            if (hi || lo) {
+                const T* __restrict__ row = zimg + k * q.vol + (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1;
+                if (hi) {
+                    const T zf = row[q.n2 - 1];
+                    for (int j = 0; j < W; ++j)
+                        if (i2 + j == th) kz[j] += q.cp[k] * zf;
+                }
+                if (lo) {
+                    const T zf = row[0];
+                    for (int j = 0; j < W; ++j)
+                        if (i2 + j == tl) kz[j] += q.cm[k] * zf;
+                }
             }
         } else {
-            const int i = ax == 0 ? i0 : i1, n = ax == 0 ? q.n0 : q.n1;
-            const int64_t st = ax == 0 ? q.s0 : q.s1;
-            const T* __restrict__ line = zk + v + i2 - (int64_t)i * st;
-            if (i == q.fold_hi[ax]) {
-                const PxbVec<T, W> f = pxb_vload<T, W>(line + (int64_t)(n - 1) * st);
-                for (int j = 0; j < W; ++j) kz[j] += q.cp[k] * f.v[j];
-            }
-            if (i == q.fold_lo[ax]) {
-                const PxbVec<T, W> f = pxb_vload<T, W>(line);
-                for (int j = 0; j < W; ++j) kz[j] += q.cm[k] * f.v[j];
+            const int i = ax == 0 ? i0 : i1;
+            const bool hi = i == q.fold_hi[ax], lo = LO && i == q.fold_lo[ax];
+            if (hi || lo) {
+                const int n = ax == 0 ? q.n0 : q.n1;
+                const int64_t st = ax == 0 ? q.s0 : q.s1;
+                const T* __restrict__ line = zimg + k * q.vol + (int64_t)i0 * q.s0 + (int64_t)i1 * q.s1 + i2 - (int64_t)i * st;
+                if (hi) {
+                    const PxbVec<T, W> f = pxb_vload<T, W>(line + (int64_t)(n - 1) * st);
+                    for (int j = 0; j < W; ++j) kz[j] += q.cp[k] * f.v[j];
+                }
+                if (lo) {
+                    const PxbVec<T, W> f = pxb_vload<T, W>(line);
+                    for (int j = 0; j < W; ++j) kz[j] += q.cm[k] * f.v[j];
+                }
             }
         }
     }

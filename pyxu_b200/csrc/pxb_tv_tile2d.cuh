@@ -60,7 +60,7 @@ PXB_HD void pxb_t2_w(const PxbTvP<T>& q, const PxbT2Geom& g, const T* __restrict
             if (pxb_has_cp<S>(q, 1)) kz[j] += q.cp[1] * (j > 0 ? c.v[j > 0 ? j - 1 : 0] : lo);
         }
     }
-    if (MODES && fold) pxb_tv_fold_kz<T, W, 2>(q, fold, f0, f1, f2, kz);
+    if (MODES && fold) pxb_tv_fold_kz<T, W, 2, S::SCHEME != PXB_SCHEME_FWD>(q, fold, f0, f1, f2, kz);
     const PxbVec<T, W> old = pxb_vload<T, W>(sm + C::OFF_U + i);
     PxbVec<T, W> sh;
     for (int j = 0; j < W; ++j) sh.v[j] = T(0);

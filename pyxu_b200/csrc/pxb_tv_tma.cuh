@@ -153,7 +153,7 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
             if (pxb_has_cp<S>(q, 2)) kz[j] += q.cp[2] * (j > 0 ? c.v[j > 0 ? j - 1 : 0] : lo);
         }
     }
-    if (MODES && fold) pxb_tv_fold_kz<T, W, 3>(q, fold, f0, f1, f2, kz);
+    if (MODES && fold) pxb_tv_fold_kz<T, W, 3, S::SCHEME != PXB_SCHEME_FWD>(q, fold, f0, f1, f2, kz);
     const PxbVec<T, W> old = pxb_vload<T, W>(st + C::OFF_U + i);
     PxbVec<T, W> sh;
     for (int j = 0; j < W; ++j) sh.v[j] = T(0);

@@ -374,11 +374,15 @@ class SlabTV(_Engine):
                 return False
             if hi < n0 and not self._iter(hi, n0, src, dst, want_x, nx, nz):
                 return False
+            self._tick("edges_end")
             self.comm.wait_stream(main)
             with torch.cuda.stream(self.comm):
+                self._tick("exchange_begin")
                 self._wait(self._exchange_state(dst))  # the new boundary planes travel while the interior is computed
+                self._tick("exchange_end")
             if not self._iter(lo, hi, src, dst, want_x, nx, nz):
                 return False
+            self._tick("interior_end")
         else:
             if not self._iter(0, n0, src, dst, want_x, nx, nz):
                 return False
