@@ -356,6 +356,7 @@ int pxb_set_iter_modes(int on);
  *   ctl         DEVICE pxb_iter_ctl, zeroed by the caller before the first batch: `done` counts the iterations carried out
  *               (the iterate is in pair a when done is even), `stop` is raised by the iteration that met the rule; launches
  *               behind it return without touching anything.
+ * rule == NULL (norms, ctl then unused): n plain iterations, for criteria only the host evaluates (MaxIter); x is then left alone.
  * Envelope and return codes as pxb_pds_iter (PXB_ENOSUP: nothing was launched). */
 typedef struct pxb_stop_rule {
     double eps_x, eps_z;
@@ -371,6 +372,32 @@ typedef struct pxb_iter_ctl {
 } pxb_iter_ctl;
 int pxb_pds_iter_n(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu_a, void* z_a, void* xu_b, void* z_b,
                    void* x, double* norms, int n, const pxb_stop_rule* rule, pxb_iter_ctl* ctl, void* stream);
+/* pxb_pds_iter on a z-slab with the halo exchange FUSED into the kernel (no reference counterpart: the reference distributes
+ * through Dask arrays).  The thread blocks that produce the slab's first / last owned plane also store it -- u, z_0, z_1, z_2 of
+ * the first plane, z_0 of the last one -- into the neighbours' ghost planes through peer memory (NVLink), then bump a counter in
+ * the neighbour's memory; the blocks that read a ghost plane wait until the neighbour's counter says its previous iteration has
+ * delivered (epoch * tiles per plane).  Those blocks are scheduled first.  All pointers are DEVICE addresses valid on this GPU
+ * (peer mappings of the neighbours' allocations); a null neighbour side is a closed side of the volume.
+ *   dn_u, dn_z    lower neighbour: the ghost plane ABOVE its last owned plane, in the buffers it will READ next iteration
+ *                 (primal; z component 0, the other components dn_zvol elements apart)
+ *   up_z0         upper neighbour: the ghost plane BELOW its first owned plane of z component 0
+ *   dn_flag, up_flag   counters in the neighbours' memory (uint32, monotonically increasing over the solve)
+ *   lo_wait, hi_wait   counters in this rank's memory which the lower / upper neighbour bumps
+ *   epoch         iterations completed before this one (0 for the first: the initial ghost planes are exchanged by the host)
+ * Envelope: as pxb_pds_iter for 3-D volumes (TMA form), batch 1.  PXB_ENOSUP: nothing was launched. */
+typedef struct pxb_peer {
+    void* dn_u;
+    void* dn_z;
+    int64_t dn_zvol;
+    void* up_z0;
+    uint32_t* dn_flag;
+    uint32_t* up_flag;
+    const uint32_t* lo_wait;
+    const uint32_t* hi_wait;
+    int64_t epoch;
+} pxb_peer;
+int pxb_pds_iter_p2p(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out,
+                     void* z_out, void* x_out, double* norms_x, double* norms_z, const pxb_peer* peer, void* stream);
 /* same, with the number of planes one thread block marches through fixed by the caller (tuning / tests) */
 int pxb_pds_iter_chunked(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in,
                          void* xu_out, void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk, void* stream);

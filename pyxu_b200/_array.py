@@ -282,6 +282,11 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def synchronize():
+    """Wait for the work queued on the current stream."""
+    torch.cuda.current_stream().synchronize()
+
+
 def np_dtype(torch_dtype):
     return np.float32 if torch_dtype == torch.float32 else np.float64
 

@@ -156,6 +156,11 @@ class StopRule(C.Structure):
     _fields_ = [("eps_x", C.c_double), ("eps_z", C.c_double), ("all_x", C.c_int32), ("all_z", C.c_int32), ("table", C.c_int32), ("_pad", C.c_int32)]
 
 
+class Peer(C.Structure):
+    _fields_ = [("dn_u", C.c_void_p), ("dn_z", C.c_void_p), ("dn_zvol", C.c_int64), ("up_z0", C.c_void_p), ("dn_flag", C.c_void_p),
+                ("up_flag", C.c_void_p), ("lo_wait", C.c_void_p), ("hi_wait", C.c_void_p), ("epoch", C.c_int64)]
+
+
 class IterCtl(C.Structure):
     _fields_ = [("stop", C.c_int32), ("done", C.c_int32), ("ticket", C.c_uint32), ("_pad", C.c_int32)]
 
@@ -186,6 +191,7 @@ PROTOTYPES = {
     "pxb_pds_primal": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pxb_pds_dual": (_i, [_P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp]),
     "pxb_pds_iter": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pxb_pds_iter_p2p": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _P(Peer), _vp]),
     "pxb_pds_iter_n": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _i, _P(StopRule), _vp, _vp]),
     "pxb_pds_iter_chunked": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pxb_set_iter_path": (_i, [_i]),

@@ -682,15 +682,36 @@ int pxb_pds_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, cons
     return pxb_tv_iter_launch(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, 0, (cudaStream_t)stream);
 }
 
+int pxb_pds_iter_p2p(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out,
+                     void* z_out, void* x_out, double* norms_x, double* norms_z, const pxb_peer* peer, void* stream) {
+    const char* who = "pxb_pds_iter_p2p";
+    if (int e = check_pds(K, p, who)) return e;
+    if (algo != PXB_PD3O && algo != PXB_CV) return fail(PXB_EINVAL, "%s: bad algo %d", who, algo);
+    if (!xu_in || !z_in || !xu_out || !z_out || xu_in == xu_out || z_in == z_out) return fail(PXB_EINVAL, "%s: the update is out of place (ping-pong buffers)", who);
+    if (!peer) return fail(PXB_EINVAL, "%s: null peer block", who);
+    if ((peer->dn_u != nullptr) != (peer->dn_z != nullptr) || (peer->dn_u != nullptr) != (peer->dn_flag != nullptr) || (peer->dn_u != nullptr) != (peer->lo_wait != nullptr))
+        return fail(PXB_EINVAL, "%s: the lower neighbour needs dn_u, dn_z, dn_flag and lo_wait together", who);
+    if ((peer->up_z0 != nullptr) != (peer->up_flag != nullptr) || (peer->up_z0 != nullptr) != (peer->hi_wait != nullptr))
+        return fail(PXB_EINVAL, "%s: the upper neighbour needs up_z0, up_flag and hi_wait together", who);
+    if ((peer->dn_u != nullptr) != (K->slab.open_lo != 0) || (peer->up_z0 != nullptr) != (K->slab.open_hi != 0))
+        return fail(PXB_EINVAL, "%s: a neighbour on exactly the open sides of the slab", who);
+    if (peer->epoch < 0) return fail(PXB_EINVAL, "%s: negative epoch", who);
+    if (!(p->sigma > 0)) return fail(PXB_EINVAL, "%s: sigma must be > 0", who);
+    return pxb_tv_iter_launch(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, 0, (cudaStream_t)stream, nullptr, peer);
+}
+
 int pxb_pds_iter_n(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu_a, void* z_a, void* xu_b, void* z_b, void* x,
                    double* norms, int n, const pxb_stop_rule* rule, pxb_iter_ctl* ctl, void* stream) {
     const char* who = "pxb_pds_iter_n";
     if (int e = check_pds(K, p, who)) return e;
     if (algo != PXB_PD3O && algo != PXB_CV) return fail(PXB_EINVAL, "%s: bad algo %d", who, algo);
     if (!xu_a || !z_a || !xu_b || !z_b || xu_a == xu_b || z_a == z_b) return fail(PXB_EINVAL, "%s: two distinct (xu, z) pairs are needed", who);
-    if (!norms || !rule || !ctl || n < 1) return fail(PXB_EINVAL, "%s: null norms / rule / ctl or n < 1", who);
-    if (!(rule->eps_x > 0) && !(rule->eps_z > 0)) return fail(PXB_EINVAL, "%s: the rule tests neither x nor z", who);
-    if (algo == PXB_PD3O && rule->eps_x > 0 && !x) return fail(PXB_EINVAL, "%s: RelError[x] needs x (it holds the previous x)", who);
+    if (n < 1) return fail(PXB_EINVAL, "%s: n < 1", who);
+    if (rule) {
+        if (!norms || !ctl) return fail(PXB_EINVAL, "%s: a rule needs norms and ctl", who);
+        if (!(rule->eps_x > 0) && !(rule->eps_z > 0)) return fail(PXB_EINVAL, "%s: the rule tests neither x nor z", who);
+        if (algo == PXB_PD3O && rule->eps_x > 0 && !x) return fail(PXB_EINVAL, "%s: RelError[x] needs x (it holds the previous x)", who);
+    }
     if (!(p->sigma > 0)) return fail(PXB_EINVAL, "%s: sigma must be > 0", who);
     return pxb_tv_iter_launch_n(algo, K, p, xu_a, z_a, xu_b, z_b, x, norms, n, rule, ctl, (cudaStream_t)stream);
 }

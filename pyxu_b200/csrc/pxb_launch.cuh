@@ -143,11 +143,13 @@ bool pxb_tv_try_dual(const pxb_grad_desc* K, const pxb_pds_params* p, const void
 // single-kernel iteration (pxb_tv_iter.cu); PXB_ENOSUP when the descriptor is outside its envelope
 struct PxbIterStop;  // device-side stopping rule of back-to-back iterations (pxb_tv_iter.cuh)
 int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out,
-                       void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, const PxbIterStop* stop = nullptr);
+                       void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, const PxbIterStop* stop = nullptr,
+                       const pxb_peer* peer = nullptr);
 int pxb_tv_iter_launch_n(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu_a, void* z_a, void* xu_b, void* z_b, void* x_out,
                          double* norms, int n, const pxb_stop_rule* rule, void* ctl, cudaStream_t s);
 int pxb_tv_tma_try(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out, void* z_out,
-                   void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, cudaError_t* err, const PxbIterStop* stop = nullptr);
+                   void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, cudaError_t* err, const PxbIterStop* stop = nullptr,
+                   const pxb_peer* peer = nullptr);
 int pxb_iter_path();  // 0 auto, 1 direct-load form only, 2 TMA form only
 int pxb_iter_modes(); // 1: folding boundary modes run the single-kernel forms too, 0: they take the two-sweep form
 int pxb_stencil2d_try(const pxb_stencil2d* d, const void* in, void* out, cudaStream_t s, cudaError_t* err);

@@ -135,7 +135,8 @@ bool aligned16(std::initializer_list<const void*> ptrs) {
 // 0: launched; PXB_ENOSUP: the descriptor is outside the envelope of the single-kernel form (the caller falls
 // back to pxb_pds_primal + pxb_pds_dual); other negative codes: errors.
 int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out,
-                       void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, const PxbIterStop* stop) {
+                       void* z_out, void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, const PxbIterStop* stop,
+                       const pxb_peer* peer) {
     const void* sh = (p->f.kind == PXB_F_SQL2 && p->f.shift_period > 1) ? p->f.shift : nullptr;
     const void* ga = p->f.kind == PXB_F_GRADARR ? p->f.garr : nullptr;
     if (!aligned16({xu_in, z_in, xu_out, z_out, x_out, sh, ga})) return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: arrays must be 16-byte aligned");
@@ -144,14 +145,15 @@ int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p
     cudaError_t err = cudaSuccess;
     int why;
     // 3-D volumes: TMA-staged pipeline (pxb_tv_tma.cu) unless the direct-load form is forced or the TMA form declines
+    if (peer && (K->ndir != 3 || pxb_iter_path() == 1)) return pxb_fail(PXB_ENOSUP, "pxb_pds_iter_p2p: only the TMA form of 3-D volumes carries the peer-memory exchange");
     if (K->ndir == 3 && pxb_iter_path() != 1) {
-        why = pxb_tv_tma_try(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, chunk_hint, s, &err, stop);
+        why = pxb_tv_tma_try(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, chunk_hint, s, &err, stop, peer);
         if (why == 0) {
             pxb_count_launch();
             if (err != cudaSuccess) return pxb_fail(PXB_ECUDA, "pxb_pds_iter (tma): %s", cudaGetErrorString(err));
             return 0;
         }
-        if (pxb_iter_path() == 2) return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: TMA form not applicable (reason %d)", why);
+        if (pxb_iter_path() == 2 || peer) return pxb_fail(PXB_ENOSUP, "pxb_pds_iter: TMA form not applicable (reason %d)", why);
     } else if (K->ndir == 2 && pxb_iter_path() != 1 && chunk_hint == 0) {
         // 2-D images: TMA-staged tiles (pxb_tv_tile2d.cu); the marching direct-load form remains the fallback
         why = pxb_tv_tile2d_try(algo, K, p, xu_in, z_in, xu_out, z_out, x_out, norms_x, norms_z, s, &err, stop);
@@ -182,17 +184,19 @@ int pxb_tv_iter_launch(int algo, const pxb_grad_desc* K, const pxb_pds_params* p
 int pxb_tv_iter_launch_n(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu_a, void* z_a, void* xu_b, void* z_b, void* x_out,
                          double* norms, int n, const pxb_stop_rule* rule, void* ctl, cudaStream_t s) {
     PxbIterStop st{};
-    st.ctl = (int32_t*)ctl;
-    st.eps_x = rule->eps_x; st.eps_z = rule->eps_z;
-    st.all_x = rule->all_x; st.all_z = rule->all_z;
-    st.table = rule->table;
-    st.rows = (int32_t)K->batch;
+    if (rule) {  // (no rule: n plain iterations -- a criterion the host alone evaluates, e.g. MaxIter)
+        st.ctl = (int32_t*)ctl;
+        st.eps_x = rule->eps_x; st.eps_z = rule->eps_z;
+        st.all_x = rule->all_x; st.all_z = rule->all_z;
+        st.table = rule->table;
+        st.rows = (int32_t)K->batch;
+    }
     const int64_t per = 4 * K->batch;
     for (int i = 0; i < n; ++i) {
-        double* nx = rule->eps_x > 0 ? norms + (int64_t)i * per : nullptr;
-        double* nz = rule->eps_z > 0 ? norms + (int64_t)i * per + 2 * K->batch : nullptr;
+        double* nx = rule && rule->eps_x > 0 ? norms + (int64_t)i * per : nullptr;
+        double* nz = rule && rule->eps_z > 0 ? norms + (int64_t)i * per + 2 * K->batch : nullptr;
         const bool even = (i & 1) == 0;
-        int rc = pxb_tv_iter_launch(algo, K, p, even ? xu_a : xu_b, even ? z_a : z_b, even ? xu_b : xu_a, even ? z_b : z_a, x_out, nx, nz, 0, s, &st);
+        int rc = pxb_tv_iter_launch(algo, K, p, even ? xu_a : xu_b, even ? z_a : z_b, even ? xu_b : xu_a, even ? z_b : z_a, x_out, nx, nz, 0, s, rule ? &st : nullptr);
         if (rc != 0) return i == 0 ? rc : pxb_fail(PXB_ECUDA, "pxb_pds_iter_n: launch %d of %d failed after earlier ones succeeded", i, n);
     }
     return 0;

@@ -39,6 +39,7 @@ struct PxbIterGeom {
     int ndir;
     int open_lo, open_hi; // slab cuts along M (NDIR == 3): ghost planes hold the neighbour's u, z, shift
     int64_t nblocks;
+    int edge_first;       // peer-memory exchange: the first and the last chunk of every tile come first in the block order
 };
 
 // Device-side stopping rule of iterations launched back to back without the host in the loop (pxb_pds_iter_n): the last
@@ -52,6 +53,24 @@ struct PxbIterStop {
     int32_t rows;
 };
 
+// Halo exchange fused into the iteration (pxb_pds_iter_p2p): the thread blocks that produce a slab's first / last plane store
+// it into the neighbour's ghost planes as well -- peer memory over NVLink, the same 16-byte stores -- then bump a counter in the
+// neighbour's memory; the neighbour's blocks that READ those ghost planes in its next iteration wait for the counter first.
+// Edge chunks come first in the block order, so the data is on its way a whole iteration before it is needed and the wait is
+// normally over before it starts.  No NCCL call, no side stream, one launch per iteration and rank.
+template <class T>
+struct PxbPeer {
+    T* dn_u;                 // lower neighbour's upper ghost plane of the primal output (null: no lower neighbour)
+    T* dn_z;                 // ... of z, component 0; components dn_zvol elements apart
+    int64_t dn_zvol;
+    T* up_z0;                // upper neighbour's lower ghost plane of z component 0
+    unsigned* dn_flag;       // counters in the neighbours' memory: += 1 per thread block that has delivered its share
+    unsigned* up_flag;
+    const unsigned* lo_wait; // counters in this rank's memory, bumped by the lower / upper neighbour
+    const unsigned* hi_wait;
+    unsigned target;         // value they must have reached before this iteration reads its ghost planes
+};
+
 template <class T>
 struct PxbIterPtr {
     const T* u_in;   // PD3O: u     CV: x
@@ -62,9 +81,21 @@ struct PxbIterPtr {
     double* norms_x; // nullable pair per batch row (RelError[x])
     double* norms_z;
     PxbIterStop stop;
+    PxbPeer<T> peer;
 };
 
 #ifdef __CUDACC__
+// spin (one thread) until the neighbour's counter has reached `target`; bounded, then trap: a lost signal must fail the
+// launch loudly instead of hanging the device
+static __device__ __forceinline__ void pxb_peer_wait(const unsigned* flag, unsigned target) {
+    for (unsigned spin = 0; spin < (1u << 28); ++spin) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - target) >= 0) return;
+        __nanosleep(64);
+    }
+    __trap();
+}
 static __device__ __forceinline__ bool pxb_iter_stopped(const PxbIterStop& s) {
     return s.ctl != nullptr && *reinterpret_cast<const volatile int32_t*>(s.ctl) != 0;
 }
@@ -131,14 +162,29 @@ PXB_HD PxbIterItem pxb_iter_item(const PxbIterGeom& g, int64_t blk, int ty, int 
     const int64_t per_img = (int64_t)g.ntR * g.ntC * g.nchunk;
     const int64_t img = blk / per_img;
     int64_t rem = blk - img * per_img;
-    const int64_t full_band = (int64_t)g.band * g.ntC * g.nchunk;
-    const int bi = (int)(rem / full_band);
-    rem -= bi * full_band;
-    const int rows_here = g.ntR - bi * g.band < g.band ? g.ntR - bi * g.band : g.band;
-    const int per_chunk = rows_here * g.ntC;
-    const int ch = (int)(rem / per_chunk);
-    const int r2 = (int)(rem - (int64_t)ch * per_chunk);
-    const int tR = bi * g.band + r2 / g.ntC, tC = r2 % g.ntC;
+    int ch, tR, tC;
+    // edge_first: the chunks that hold a slab's first / last plane -- what the neighbours wait for -- before the interior ones
+    const int n_edge = g.edge_first ? (g.nchunk >= 2 ? 2 : 1) : 0;
+    const int64_t tiles = (int64_t)g.ntR * g.ntC;
+    if (rem < n_edge * tiles) {
+        const int e = (int)(rem / tiles), t = (int)(rem - (int64_t)e * tiles);
+        ch = e == 0 ? 0 : g.nchunk - 1;
+        tR = t / g.ntC;
+        tC = t % g.ntC;
+    } else {
+        rem -= n_edge * tiles;
+        const int nch = g.nchunk - n_edge;
+        const int64_t full_band = (int64_t)g.band * g.ntC * nch;
+        const int bi = (int)(rem / full_band);
+        rem -= bi * full_band;
+        const int rows_here = g.ntR - bi * g.band < g.band ? g.ntR - bi * g.band : g.band;
+        const int per_chunk = rows_here * g.ntC;
+        ch = (int)(rem / per_chunk);
+        const int r2 = (int)(rem - (int64_t)ch * per_chunk);
+        ch += n_edge ? 1 : 0;
+        tR = bi * g.band + r2 / g.ntC;
+        tC = r2 % g.ntC;
+    }
     const int64_t b = img / g.sub;
     const int si = (int)(img - b * g.sub);
     it.b = b;
@@ -396,6 +442,9 @@ PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = p[k][j];
         pxb_vstore<T, VEC>(zb + k * g.vol, o);
+        // peer-memory exchange: the first owned plane of every component goes down, the last one of component 0 goes up
+        if (NDIR == 3 && a.peer.dn_z != nullptr && mm == 0) pxb_vstore<T, VEC>(a.peer.dn_z + k * a.peer.dn_zvol + (int64_t)r * g.sR + c, o);
+        if (NDIR == 3 && k == 0 && a.peer.up_z0 != nullptr && mm == g.nM - 1) pxb_vstore<T, VEC>(a.peer.up_z0 + (int64_t)r * g.sR + c, o);
     }
     if (NORMS) { acc[2] += (double)a0; acc[3] += (double)a1; }
 }
@@ -463,6 +512,7 @@ inline int pxb_iter_setup(const pxb_grad_desc& d, const pxb_pds_params& P, int v
     g.chunk = chunk;
     g.nchunk = (g.nM + chunk - 1) / chunk;
     g.nblocks = tiles * g.nchunk;
+    g.edge_first = 0;
     if (g.nblocks <= 0 || g.nblocks > 0x7fffffffLL) return 8;
     return 0;
 }

@@ -50,6 +50,10 @@ __global__ void __launch_bounds__(32 * TY, 2)
         for (int s = 0; s < C::NSTAGE; ++s) mbar_init(full + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // peer-memory exchange: the ghost planes this work item reads were stored by the neighbour's previous iteration
+        if (a.peer.lo_wait != nullptr && it.m0 == 0) pxb_peer_wait(a.peer.lo_wait, a.peer.target);
+        if (a.peer.hi_wait != nullptr && it.m1 == g.nM) pxb_peer_wait(a.peer.hi_wait, a.peer.target);
+        if (a.peer.lo_wait != nullptr || a.peer.hi_wait != nullptr) asm volatile("fence.proxy.async;" ::: "memory");  // ... and are read by TMA
     }
     __syncthreads();
     if (tid == 0)
@@ -90,6 +94,18 @@ __global__ void __launch_bounds__(32 * TY, 2)
     }
     // a stage filled for `need_next` beyond the last plane has been waited on above (k1), nothing is in flight here
 
+    {   // peer-memory exchange: this work item's share of the boundary planes is in the neighbours' memory -> tell them
+        const bool dn = a.peer.dn_flag != nullptr && it.m0 == 0, up = a.peer.up_flag != nullptr && it.m1 == g.nM;
+        if (dn || up) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                if (dn) atomicAdd_system(a.peer.dn_flag, 1u);
+                if (up) atomicAdd_system(a.peer.up_flag, 1u);
+            }
+        }
+    }
+
     if (NORMS) {
         __shared__ double red[4][C::NT / 32];
         double v[4] = {th.acc[0], th.acc[1], th.acc[2], th.acc[3]};
@@ -111,13 +127,21 @@ __global__ void __launch_bounds__(32 * TY, 2)
 }
 
 template <class T, int ALGO, bool NORMS>
-int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a, int chunk_hint, cudaStream_t s, cudaError_t* err) {
+int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a_in, int chunk_hint, cudaStream_t s, cudaError_t* err, const pxb_peer* peer) {
     constexpr int VEC = 16 / (int)sizeof(T), TY = 8;
     using C = PxbTmaCfg<T, VEC, TY>;
     PxbTvCoef cf;
     PxbIterGeom g;
     PxbTvP<T> q;
     if (int why = pxb_iter_setup(d, P, VEC, TY, C::T2, chunk_hint, 148 * 2, cf, g, pxb_iter_modes() != 0)) return why;
+    PxbIterPtr<T> a = a_in;
+    if (peer) {  // halo exchange through peer memory: edge chunks first, counters in units of one per edge thread block
+        if (d.batch != 1) return 24;
+        g.edge_first = 1;
+        a.peer.dn_u = (T*)peer->dn_u; a.peer.dn_z = (T*)peer->dn_z; a.peer.dn_zvol = peer->dn_zvol; a.peer.up_z0 = (T*)peer->up_z0;
+        a.peer.dn_flag = peer->dn_flag; a.peer.up_flag = peer->up_flag; a.peer.lo_wait = peer->lo_wait; a.peer.hi_wait = peer->hi_wait;
+        a.peer.target = (unsigned)((uint64_t)peer->epoch * (uint64_t)g.ntR * (uint64_t)g.ntC);
+    }
     pxb_tv_prepare<T>(d, cf, P, q);
     PxbTmaGeom tg;
     PxbTmaBoxDesc mu, ms, mz;
@@ -152,23 +176,25 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a,
 }
 
 template <class T>
-int dispatch(int algo, const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a, int chunk_hint, cudaStream_t s, cudaError_t* err) {
+int dispatch(int algo, const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a, int chunk_hint, cudaStream_t s, cudaError_t* err,
+             const pxb_peer* peer) {
     const bool norms = a.norms_x || a.norms_z;
-    if (algo == PXB_PD3O) return norms ? run<T, PXB_PD3O, true>(d, P, a, chunk_hint, s, err) : run<T, PXB_PD3O, false>(d, P, a, chunk_hint, s, err);
-    return norms ? run<T, PXB_CV, true>(d, P, a, chunk_hint, s, err) : run<T, PXB_CV, false>(d, P, a, chunk_hint, s, err);
+    if (algo == PXB_PD3O) return norms ? run<T, PXB_PD3O, true>(d, P, a, chunk_hint, s, err, peer) : run<T, PXB_PD3O, false>(d, P, a, chunk_hint, s, err, peer);
+    return norms ? run<T, PXB_CV, true>(d, P, a, chunk_hint, s, err, peer) : run<T, PXB_CV, false>(d, P, a, chunk_hint, s, err, peer);
 }
 
 }  // namespace
 
 // > 0: not eligible (reason), 0: launched (or *err set)
 int pxb_tv_tma_try(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out, void* z_out,
-                   void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, cudaError_t* err, const PxbIterStop* stop) {
+                   void* x_out, double* norms_x, double* norms_z, int chunk_hint, cudaStream_t s, cudaError_t* err, const PxbIterStop* stop,
+                   const pxb_peer* peer) {
     if (K->ndir != 3) return 20;
     const PxbIterStop st = stop ? *stop : PxbIterStop{};
     if (K->dtype == PXB_F32) {
-        PxbIterPtr<float> a{(const float*)xu_in, (const float*)z_in, (float*)xu_out, (float*)z_out, (float*)x_out, norms_x, norms_z, st};
-        return dispatch<float>(algo, *K, *p, a, chunk_hint, s, err);
+        PxbIterPtr<float> a{(const float*)xu_in, (const float*)z_in, (float*)xu_out, (float*)z_out, (float*)x_out, norms_x, norms_z, st, {}};
+        return dispatch<float>(algo, *K, *p, a, chunk_hint, s, err, peer);
     }
-    PxbIterPtr<double> a{(const double*)xu_in, (const double*)z_in, (double*)xu_out, (double*)z_out, (double*)x_out, norms_x, norms_z, st};
-    return dispatch<double>(algo, *K, *p, a, chunk_hint, s, err);
+    PxbIterPtr<double> a{(const double*)xu_in, (const double*)z_in, (double*)xu_out, (double*)z_out, (double*)x_out, norms_x, norms_z, st, {}};
+    return dispatch<double>(algo, *K, *p, a, chunk_hint, s, err, peer);
 }

@@ -270,6 +270,8 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             }
             for (int j = 0; j < VEC; ++j) o.v[j] = un[j];
             pxb_vstore<T, VEC>(a.u_out + lin, o);
+            // peer-memory exchange: the first owned plane of the new primal iterate is the lower neighbour's upper ghost plane
+            if (a.peer.dn_u != nullptr && m == 0) pxb_vstore<T, VEC>(a.peer.dn_u + (int64_t)r * g.sR + c, o);
         }
     }
     // rims: w of the neighbouring tiles' border samples (only on planes this work item updates); the carried z0 of

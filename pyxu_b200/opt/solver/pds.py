@@ -376,7 +376,7 @@ class _PrimalDualSplitting(Solver):
 
         if ast["mode"] is not Mode.BLOCK or self._slab is not None or pl is None or pl.kind != "fused" or pl.fkind == K.F_GRADARR:
             return None
-        if self._nrm is None or ast["track_objective"] or ast["wb_rate"] is not None or ast["stop_rate"] != 1 or self._x_every:
+        if ast["track_objective"] or ast["wb_rate"] is not None or ast["stop_rate"] != 1 or self._x_every:
             return None
         crit = ast["stop_crit"]
         try:
@@ -387,6 +387,8 @@ class _PrimalDualSplitting(Solver):
         for var, eps, every in crit._device_leaves():
             if leaves.setdefault(var, (eps, every)) != (eps, every):
                 return None  # two different tests on the same variable
+        if not leaves and self._nrm is None:
+            return False if table == 0 else None  # nothing for the device to test (MaxIter / ManualStop only): plain batches
         if not leaves or not set(leaves) <= {"x", "z"} or ("x" in leaves) != (self._nx is not None) or ("z" in leaves) != (self._nz is not None):
             return None
         r = K.StopRule()
@@ -397,7 +399,7 @@ class _PrimalDualSplitting(Solver):
 
     def _fit_run(self):
         rule = self._batch_rule() if self._plan is not None else None
-        if rule is None:
+        if rule is None:  # (False: batches without a device-side rule)
             return super()._fit_run()
         try:
             self._run_batched(rule)
@@ -426,9 +428,41 @@ class _PrimalDualSplitting(Solver):
         key = "u" if algo == K.ALGO_PD3O else "x"
         rows = pl.batch
         cap, per_iter = 8, None
+        p = pl.params(mst)
+        if rule is False:  # the device has nothing to test: plain batches, the host counts
+            while True:
+                if not self._pre_step():
+                    return
+                n = int(min(cap, self._BATCH_MAX, crit._budget()))
+                if n < 2:
+                    ast["idx"] += 1
+                    self.m_step()
+                    continue
+                if pl.alt is None:
+                    pl.alt = (A.empty_like(mst[key]), A.empty_like(mst["z"]))
+                t0 = time.perf_counter()
+                rc = K.lib().pxb_pds_iter_n(algo, C.byref(pl.gdesc), C.byref(p), A.ptr(mst[key]), A.ptr(mst["z"]), A.ptr(pl.alt[0]), A.ptr(pl.alt[1]),
+                                            None, None, n, None, None, A.stream())
+                K.check(rc, "pxb_pds_iter_n")
+                if n % 2:
+                    cur = pl.alt
+                    pl.alt = (mst[key], mst["z"])
+                    mst[key], mst["z"] = cur
+                if algo == K.ALGO_PD3O:
+                    self._x_stale = True
+                idx0 = ast["idx"]
+                ast["idx"] = idx0 + n
+                decisions, info = crit._replay(np.empty((n - 1, 0)))
+                if bool(np.any(decisions)):
+                    raise RuntimeError("a batch of iterations went past the one at which the criterion stops")
+                self._record_block(idx0 + 1, info)
+                if cap < self._BATCH_MAX:  # (launches are asynchronous: time a batch only while the batch size is still growing)
+                    A.synchronize()
+                    dt = (time.perf_counter() - t0) / n
+                    per_iter = dt if per_iter is None else min(per_iter, dt)
+                    cap = max(2, min(cap * 2, self._BATCH_MAX, int(self._BATCH_SECONDS / max(per_iter, 1e-7))))
         buf = torch.empty(self._BATCH_MAX * 4 * rows + 2, dtype=torch.float64, device=mst["z"].device)  # sums of every iteration | ctl
         ctl_view = buf[-2:].view(torch.int32)
-        p = pl.params(mst)
         fused = mst["_fused_norms"]
         while True:
             if not self._pre_step():  # the test that follows the last iteration carried out (host side, as in the reference's loop)

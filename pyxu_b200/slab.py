@@ -179,6 +179,69 @@ class HaloExchanger:
         return dist.batch_isend_irecv(ops) if ops else []
 
 
+# -- peer memory: the neighbours' slab buffers mapped into this process ---------------------------------------------------
+_PEER_POOL = {}  # (kind, shape, dtype, rank, world) -> dict(bufs=..., lo=..., hi=...): kept for the life of the process (see PeerBuffers)
+
+
+def release_pool():
+    """Drop the pooled slab buffers (collective in spirit: call it on every rank, with no solve in flight)."""
+    _PEER_POOL.clear()
+
+
+def _p2p_enabled():
+    import os
+
+    return (os.environ.get("PYXU_B200_SLAB_P2P", "1") != "0" and dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+            and dist.get_world_size() > 1 and torch.cuda.is_available())
+
+
+class PeerBuffers:
+    """The state buffers of a SlabTV engine together with the lower / upper neighbour's, the latter mapped into this process
+    through CUDA IPC (torch's own tensor sharing: cudaIpcGetMemHandle on the exporting rank, cudaIpcOpenMemHandle with lazy
+    peer access here), so that the iteration kernel can store boundary planes straight into the neighbours' ghost planes over
+    NVLink (pxb_pds_iter_p2p).  Buffers and mappings are POOLED per (shape, dtype, rank, world): mapping costs milliseconds, and a
+    neighbour may still be writing its last boundary planes into this rank's ghost planes when this rank's solve has already
+    returned -- memory that is never handed back to the allocator cannot be corrupted by that."""
+
+    def __init__(self, make, rank, world, lo, hi):
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        self.bufs = make()  # name -> tensor
+        mine = {k: reduce_tensor(t) for k, t in self.bufs.items()}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        opened = {}
+
+        def open_rank(r):
+            if r is None:
+                return None
+            if r not in opened:
+                opened[r] = {k: fn(*args) for k, (fn, args) in everyone[r].items()}
+            return opened[r]
+
+        self.lo, self.hi = open_rank(lo), open_rank(hi)
+
+
+def peer_buffers(key, make, rank, world, lo, hi):
+    """Pooled PeerBuffers, or None when peer memory cannot be set up on EVERY rank (the decision is agreed on collectively)."""
+    if key in _PEER_POOL:
+        return _PEER_POOL[key]
+    ok, pb = 1, None
+    try:
+        pb = PeerBuffers(make, rank, world, lo, hi)
+    except Exception as e:  # an allocator that cannot export IPC handles, no peer access between the two GPUs, ...
+        import warnings
+
+        warnings.warn(f"pyxu_b200.slab: peer-memory halo exchange unavailable ({type(e).__name__}: {e}); using NCCL send/recv")
+        ok = 0
+    flag = torch.tensor([ok], device=A.current_device(), dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return None
+    _PEER_POOL[key] = pb
+    return pb
+
+
 def _copy_params(p):
     q = K.PdsParams.from_buffer_copy(p)
     return q
@@ -245,7 +308,7 @@ class SlabTV(_Engine):
     shift   None | this rank's planes of the data-term shift c (n0 * plane samples, device) | a 1-sample tensor
     """
 
-    def __init__(self, algo, Kop, params, x0, z0=None, shift=None, rank=0, world=1, group=None, overlap=True, fused=True, edge=8):
+    def __init__(self, algo, Kop, params, x0, z0=None, shift=None, rank=0, world=1, group=None, overlap=True, fused=True, edge=8, p2p=None):
         A.require_cuda()
         self.algo, self.dtype = algo, x0.dtype
         modes = tuple(Kop._mode)
@@ -262,8 +325,28 @@ class SlabTV(_Engine):
         self.x = self._field() if algo == K.ALGO_PD3O else None  # PD3O's x (CondatVu's primal variable IS x)
         self._x_stale = False
         self._iter_cache, self._fn_iter = {}, K.lib().pxb_pds_iter
-        self._pb = [self._field(), self._field()]
-        self._zb = [self._field(3), self._field(3)]
+        # Halo exchange fused into the kernel through peer memory (pxb_pds_iter_p2p) when every rank can map its neighbours'
+        # buffers; NCCL send/recv on a side stream otherwise (PYXU_B200_SLAB_P2P=0 forces the latter for A/B runs).
+        self.p2p, self._epoch, self._peers = None, 0, {}
+        if self.fused and world > 1 and p2p is not False and _p2p_enabled():
+            make = lambda: dict(p0=self._field(), p1=self._field(), z0=self._field(3), z1=self._field(3),
+                                flags=torch.zeros(4, dtype=torch.int32, device=self.dev))
+            key = ("tv", self.shape, self.dtype, rank, world, bool(self.hx.periodic))
+            reused = key in _PEER_POOL
+            self.p2p = peer_buffers(key, make, rank, world, self.hx.lo, self.hx.hi)
+            if self.p2p is not None:
+                # nobody may still be writing into pooled buffers (a neighbour's last iteration of an earlier solve), and
+                # nobody may start before every rank has reset its counters
+                torch.cuda.synchronize()
+                dist.barrier()
+                b = self.p2p.bufs
+                if reused:
+                    for t in b.values():
+                        t.zero_()
+                self._pb, self._zb, self._flags = [b["p0"], b["p1"]], [b["z0"], b["z1"]], b["flags"]
+        if self.p2p is None:
+            self._pb = [self._field(), self._field()]
+            self._zb = [self._field(3), self._field(3)]
         self.cur = 0
         self.w = None
         self.shift_h = None
@@ -293,6 +376,9 @@ class SlabTV(_Engine):
             if self.shift_h is not None:
                 self._wait(self.hx.exchange(self.shift_h[0], h, n0, up=True, down=True))
             self._wait(self._exchange_state(self.cur))
+        if self.p2p is not None:  # every rank's counters are zero and its ghost planes filled before anybody iterates
+            torch.cuda.synchronize()
+            dist.barrier()
 
     # current iterate (the ping-pong index flips every single-kernel iteration)
     @property
@@ -360,12 +446,68 @@ class SlabTV(_Engine):
         self._iter_cache["ran"] = True
         return True
 
+    def _peer_block(self, dst):
+        """pxb_peer for an iteration that writes iterate `dst`: where this slab's new boundary planes go in the neighbours' copies
+        of that iterate, and the counters on both sides."""
+        pr = self._peers.get(dst)
+        if pr is None:
+            es, H, plane = self._pb[0].element_size(), self.H, self.plane
+            parts = partition(self.shape[0], self.world)
+            pr = K.Peer()
+            mine = self._flags.data_ptr()
+            if self.hx.lo is not None:
+                nb = self.p2p.lo
+                n_lo = parts[self.hx.lo][1] - parts[self.hx.lo][0]
+                up, zz = nb["p%d" % dst], nb["z%d" % dst]
+                pr.dn_u = up.data_ptr() + es * (H + n_lo) * plane
+                pr.dn_z = zz.data_ptr() + es * (H + n_lo) * plane
+                pr.dn_zvol = zz.shape[1] * plane
+                pr.dn_flag = nb["flags"].data_ptr() + 4  # I am its upper neighbour
+                pr.lo_wait = mine
+            if self.hx.hi is not None:
+                nb = self.p2p.hi
+                pr.up_z0 = nb["z%d" % dst].data_ptr() + es * (H - 1) * plane
+                pr.up_flag = nb["flags"].data_ptr()      # I am its lower neighbour
+                pr.hi_wait = mine + 4
+            self._peers[dst] = pr
+        pr.epoch = self._epoch
+        return pr
+
+    def _step_p2p(self, nx, nz, want_x):
+        """One launch: the kernel stores the new boundary planes into the neighbours' ghost planes itself (pxb_pds_iter_p2p)."""
+        src, dst = self.cur, 1 - self.cur
+        key = ("p2p", src)
+        c = self._iter_cache.get(key)
+        if c is None:
+            d, p = self._desc(0, self.n0), self._params(0, True)
+            ptr = lambda t, comp: self._p(t, comp, 0)
+            c = (d, p, C.byref(d), C.byref(p), ptr(self._pb[src], 0), ptr(self._zb[src], 0), ptr(self._pb[dst], 0), ptr(self._zb[dst], 0),
+                 ptr(self.x, 0) if self.x is not None else None)
+            self._iter_cache[key] = c
+        pr = self._peer_block(dst)
+        self._tick("iter_begin")
+        rc = K.lib().pxb_pds_iter_p2p(self.algo, c[2], c[3], c[4], c[5], c[6], c[7], c[8] if want_x else None, A.ptr(nx), A.ptr(nz), C.byref(pr), A.stream())
+        if rc == -3 and self._epoch == 0:
+            return False
+        if rc:
+            K.check(rc, "pxb_pds_iter_p2p")
+        self._tick("iter_end")
+        self._epoch += 1
+        return True
+
     def _step_fused(self, nx, nz, want_x):
         n0, e = self.n0, self.edge
         src, dst = self.cur, 1 - self.cur
         want_x = bool(want_x) and self.x is not None
         if want_x and nx is not None and self._x_stale:
             self.materialize_x()  # RelError[x] compares with the previous x
+        if self.p2p is not None:
+            if self._step_p2p(nx, nz, want_x):
+                self.cur = dst
+                if self.x is not None:
+                    self._x_stale = not want_x
+                return True
+            self.p2p = None  # the kernel declined (outside the TMA form's envelope): NCCL exchange from here on, same buffers
         main = torch.cuda.current_stream()
         self._tick("iter_begin")
         if self.world > 1 and self.overlap and n0 >= 4 * e:

@@ -190,13 +190,15 @@ static void emu_tma_box(const PxbTmaBoxDesc& m, uint32_t rows, const int c[5], T
             dst[i1 * m.box[0] + i0] = v;
         }
 }
+static const pxb_peer* g_emu_peer = nullptr;  // set by emu_tv_iter_tma_p2p for the duration of one call
 template <class T, int ALGO, bool NORMS, class S, bool MODES = false>
-static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a, int chunk, int want_spec) {
+static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a_in, int chunk, int want_spec) {
     constexpr int VEC = 16 / (int)sizeof(T), TY = 8;
     using C = PxbTmaCfg<T, VEC, TY>;
     using R = typename C::Ring;
     PxbTvCoef cf;
     PxbIterGeom g;
+    PxbIterPtr<T> a = a_in;
     if (int why = pxb_iter_setup(*K, *p, VEC, TY, C::T2, chunk, 5, cf, g, g_allow_modes)) return -100 - why;
     if (pxb_any_mode(*K) != MODES) return -130;  // folding modes <=> the MODES instances, as in the launcher
     PxbTvP<T> q;
@@ -209,10 +211,22 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
         if (MODES && spec > 2) spec = 0;
         if (spec != want_spec) return -130;
     }
+    if (const pxb_peer* peer = g_emu_peer) {  // as run() in pxb_tv_tma.cu
+        if (K->batch != 1) return -124;
+        g.edge_first = 1;
+        a.peer.dn_u = (T*)peer->dn_u; a.peer.dn_z = (T*)peer->dn_z; a.peer.dn_zvol = peer->dn_zvol; a.peer.up_z0 = (T*)peer->up_z0;
+        a.peer.dn_flag = peer->dn_flag; a.peer.up_flag = peer->up_flag; a.peer.lo_wait = peer->lo_wait; a.peer.hi_wait = peer->hi_wait;
+        a.peer.target = (unsigned)((uint64_t)peer->epoch * (uint64_t)g.ntR * (uint64_t)g.ntC);
+    }
     std::vector<T> stages(C::NSTAGE * C::STAGE), ring(R::NSLOT * R::SLOT);
     std::vector<PxbTmaThread<T, VEC>> th(C::NT);
     for (int64_t blk = 0; blk < g.nblocks; ++blk) {
         const PxbIterItem it = pxb_iter_item(g, blk, TY, C::T2);
+        // the waits of the kernel's prologue: in this sequential replay the neighbour's previous iteration is long over, so a
+        // counter short of its target is a counting error
+        if (a.peer.lo_wait && it.m0 == 0 && (int)(*a.peer.lo_wait - a.peer.target) < 0) return -140;
+        if (a.peer.hi_wait && it.m1 == g.nM && (int)(*a.peer.hi_wait - a.peer.target) < 0) return -141;
+        if (g.edge_first && blk < (int64_t)(g.nchunk >= 2 ? 2 : 1) * g.ntR * g.ntC && !(it.m0 == 0 || it.m1 == g.nM)) return -142;  // edges first
         const PxbIterRange Rg = pxb_iter_range<T>(q, it);
         const bool need_next = pxb_has_cm<S>(q, 0);
         const int lag = S::SCHEME == PXB_SCHEME_FWD ? 1 : Rg.lag;
@@ -249,6 +263,8 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
                 std::memcpy(th[tid].zprev, th[tid].zc, sizeof(th[tid].zc));
             }
         }
+        if (a.peer.dn_flag && it.m0 == 0) *a.peer.dn_flag += 1u;
+        if (a.peer.up_flag && it.m1 == g.nM) *a.peer.up_flag += 1u;
         if (NORMS)
             for (int tid = 0; tid < C::NT; ++tid) {
                 if (a.norms_x) { a.norms_x[2 * it.b] += th[tid].acc[0]; a.norms_x[2 * it.b + 1] += th[tid].acc[1]; }
@@ -657,6 +673,14 @@ int emu_tv_iter_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, c
                     void* x_out, double* nx, double* nz, int chunk) {
     if (K->dtype == PXB_F32) return t_tma<float>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);
     return t_tma<double>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);
+}
+// the same with the halo exchange fused in (pxb_pds_iter_p2p): `peer` points into the neighbouring ranks' arrays of this process
+int emu_tv_iter_tma_p2p(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
+                        void* x_out, double* nx, double* nz, int chunk, const pxb_peer* peer) {
+    g_emu_peer = peer;
+    const int rc = emu_tv_iter_tma(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);
+    g_emu_peer = nullptr;
+    return rc;
 }
 int emu_tv_iter(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,
                 void* x_out, double* nx, double* nz, int chunk) {

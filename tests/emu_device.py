@@ -188,8 +188,15 @@ class EmuLib:
     def pxb_pds_iter_n(self, algo, Kd, p, xu_a, z_a, xu_b, z_b, x, norms, n, rule, ctl, stream):
         """pxb_tv_iter_launch_n + the device-side rule of pxb_iter_finish (pxb_tv_iter.cuh), restated: iteration i accumulates into
         norms[i], the rule is tested after it, later iterations do nothing once it is met."""
-        if Kd is None or p is None or rule is None or n < 1:
+        if Kd is None or p is None or n < 1:
             return EINVAL
+        if rule is None:  # plain batch
+            for i in range(n):
+                pair = (xu_a, z_a, xu_b, z_b) if i % 2 == 0 else (xu_b, z_b, xu_a, z_a)
+                rc = self.pxb_pds_iter(algo, Kd, p, *pair, x, None, None, stream)
+                if rc != 0:
+                    return rc if i == 0 else -2
+            return 0
         g, r = self._gdesc(Kd), self._gdesc(rule)
         rows = int(g.batch)
         addr = lambda q: q.value if hasattr(q, "value") else q
@@ -243,6 +250,8 @@ def emulated_device(cuda_runtime=False):
             cuda_saved[k] = getattr(torch.cuda, k)
             setattr(torch.cuda, k, v)
     saved = (A.require_cuda, A.current_device, A.stream, K.lib, A._BIG, A.asdevice)
+    saved_sync = A.synchronize
+    A.synchronize = lambda: None
     orig_asdevice = A.asdevice
 
     def asdevice(arr, dtype=None):
@@ -264,6 +273,7 @@ def emulated_device(cuda_runtime=False):
         yield lib
     finally:
         A.require_cuda, A.current_device, A.stream, K.lib, A._BIG, A.asdevice = saved
+        A.synchronize = saved_sync
         lib.h.emu_set_iter_modes(1)
         for k, v in cuda_saved.items():
             setattr(torch.cuda, k, v)

@@ -38,6 +38,7 @@ def test_struct_layouts_match_the_c_compiler():
       printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pxb_slab), sizeof(pxb_stencil_desc), sizeof(pxb_grad_desc),
              sizeof(pxb_prox_spec), sizeof(pxb_fterm), sizeof(pxb_pds_params), sizeof(pxb_stencil2d), sizeof(pxb_fista_step), sizeof(pxb_pad2d_desc),
              sizeof(pxb_stop_rule), sizeof(pxb_iter_ctl));
+      printf("%zu %zu ", sizeof(pxb_peer), offsetof(pxb_peer, epoch));
       printf("%zu %zu ", offsetof(pxb_stop_rule, table), offsetof(pxb_iter_ctl, ticket));
       printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", offsetof(pxb_stencil_desc, coef), offsetof(pxb_grad_desc, coef),
              offsetof(pxb_grad_desc, slab), offsetof(pxb_pds_params, lam), offsetof(pxb_stencil2d, coef), offsetof(pxb_stencil2d, add_period),
@@ -50,10 +51,11 @@ def test_struct_layouts_match_the_c_compiler():
         exe = os.path.join(td, "t")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    extra = [C.sizeof(K.Peer), K.Peer.epoch.offset]
     sizes = [C.sizeof(s) for s in (K.Slab, K.StencilDesc, K.GradDesc, K.ProxSpec, K.FTerm, K.PdsParams, K.Stencil2D, K.FistaStep, K.Pad2D, K.StopRule, K.IterCtl)]
     offs = [K.StopRule.table.offset, K.IterCtl.ticket.offset, K.StencilDesc.coef.offset, K.GradDesc.coef.offset, K.GradDesc.slab.offset, K.PdsParams.lam.offset, K.Stencil2D.coef.offset,
             K.Stencil2D.add_period.offset, K.FistaStep.norms.offset, K.Stencil2D.origin.offset, K.Pad2D.mode.offset]
-    assert [int(v) for v in out] == sizes + offs
+    assert [int(v) for v in out] == sizes + extra + offs
 
 
 def test_argument_errors_are_reported_without_a_gpu():
@@ -68,6 +70,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.pxb_stencil_axis0_apply(0, 1, one, None, 3, 5, (C.c_double * 3)(1, 2, 1), C.c_void_p(16), C.c_void_p(32), None) == -1  # center outside the kernel
     assert lib.pxb_pds_iter(0, None, None, None, None, None, None, None, None, None, None) == -1
     assert lib.pxb_pds_iter_n(0, None, None, None, None, None, None, None, None, 4, None, None, None) == -1
+    assert lib.pxb_pds_iter_p2p(0, None, None, None, None, None, None, None, None, None, None, None) == -1
     assert lib.pxb_set_iter_path(7) == -1 and lib.pxb_set_iter_path(0) == 0
     assert lib.pxb_set_iter_modes(2) == -1
     g = K.GradDesc()

@@ -35,7 +35,7 @@ def test_default_stop_iteration_count_and_cv(dev):
     G.test_cv_tv2d(dev)
 
 
-@pytest.mark.parametrize("case", ["pd3o2d", "cv2d", "pd3o3d_maxiter_or_relerr", "pd3o_stacked_any"])
+@pytest.mark.parametrize("case", ["pd3o2d", "cv2d", "pd3o3d_maxiter_or_relerr", "pd3o_stacked_any", "maxiter_only"])
 def test_iterations_queued_back_to_back_equal_one_launch_per_iteration(dev, case, monkeypatch):
     calls = []
     real = dev.lib.pxb_pds_iter_n

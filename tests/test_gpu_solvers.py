@@ -74,7 +74,7 @@ def test_pd3o_tv2d_default_stop_iteration_count(px):
     assert len(hist2) == len(hist)
 
 
-@pytest.mark.parametrize("case", ["pd3o2d", "cv2d", "pd3o3d_maxiter_or_relerr", "pd3o_stacked_any"])
+@pytest.mark.parametrize("case", ["pd3o2d", "cv2d", "pd3o3d_maxiter_or_relerr", "pd3o_stacked_any", "maxiter_only"])
 def test_iterations_queued_back_to_back_equal_one_launch_per_iteration(px, case, monkeypatch):
     """pxb_pds_iter_n (the stopping rule tested on the device, the host replays history and log from the recorded sums) against
     the loop that launches one iteration at a time: same iteration count, bit-identical history, iterates and log text."""
@@ -92,6 +92,11 @@ def test_iterations_queued_back_to_back_equal_one_launch_per_iteration(px, case,
             y = g["pd3o_tv2d/y"]
             slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.1)
             x0 = y.reshape(-1).copy()
+        elif case == "maxiter_only":  # nothing for the device to test: plain batches, the host counts
+            y = g["pd3o_tv2d/y"]
+            slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.1)
+            x0 = y.reshape(-1).copy()
+            kw = dict(stop_crit=px.stop.MaxIter(60))
         elif case == "cv2d":
             y = g["pd3o_tv2d/y"]
             slv = cases.build_tv_denoise(px, y, (32, 40), lam=0.1, solver="CondatVu")
@@ -119,6 +124,8 @@ def test_iterations_queued_back_to_back_equal_one_launch_per_iteration(px, case,
     assert l1 == l0
     if case == "pd3o2d":
         assert len(h1) == int(g["pd3o_tv2d/default_stop/n_hist"])  # ... which is the reference's own iteration count
+    if case == "maxiter_only":
+        assert len(h1) == 61 and relerr(d1["x"], g["pd3o_tv2d/s1/x"]) < TOL64
 
 
 @pytest.mark.parametrize("mode", ["reflect", "wrap", "symmetric", "edge"])

@@ -329,6 +329,73 @@ def test_slab_single_kernel_iteration_equals_single_domain(world, form, scheme, 
     assert np.allclose(x, x_ref, rtol=1e-13, atol=1e-15) and np.allclose(z, z_ref, rtol=1e-13, atol=1e-15)
 
 
+@pytest.mark.parametrize("mode", ["constant", ("reflect", "symmetric", "edge"), ("wrap", "reflect", "symmetric")], ids=lambda m: m if isinstance(m, str) else "-".join(m))
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("shape,chunk", [((26, 6, 8), 3), ((41, 16, 64), 0), ((12, 16, 64), 0)], ids=["ragged-chunk3", "fulltiles", "one-chunk-slabs"])
+def test_slab_iteration_with_the_exchange_fused_into_the_kernel(world, mode, shape, chunk):
+    """pxb_pds_iter_p2p: ONE launch per rank and iteration; the kernel body stores the new boundary planes into the neighbours'
+    ghost planes (here: the other simulated ranks' arrays), bumps their counters, and checks the neighbours' counters before
+    reading its own ghost planes.  No exchange between iterations; result = the single-domain iteration, bit for bit in
+    what is exchanged, to rounding in the rest (the single-domain reference runs the generic two-sweep bodies)."""
+    n_iter, lam = 6, 0.08
+    tau = sigma = 0.28
+    rho = 1.3
+    y = np.random.default_rng(3).random(shape)
+    m0 = mode if isinstance(mode, str) else mode[0]
+    periodic = m0 == "wrap" and world > 1
+    x_ref, z_ref = _single_domain(shape, y, mode, n_iter, tau, sigma, rho, lam)
+    parts = partition(shape[0], world)
+    ranks = [_RankIter(shape, y, a, b, r, world, "forward", mode, periodic) for r, (a, b) in enumerate(parts)]
+    flags = [np.zeros(4, dtype=np.uint32) for _ in ranks]
+    for r, rk in enumerate(ranks):  # what the engine's set-up exchanges once over NCCL: ghost planes of x0 and of the shift; z0 = K x0
+        if r > 0 or periodic:
+            ranks[(r - 1) % world].x[0][-1] = rk.x[0][1]
+            ranks[(r - 1) % world].sh[0][-1] = rk.sh[0][1]
+        if r + 1 < world or periodic:
+            ranks[(r + 1) % world].x[0][0] = rk.x[0][rk.n0]
+            ranks[(r + 1) % world].sh[0][0] = rk.sh[0][rk.n0]
+    for rk in ranks:
+        dd = rk.desc(0, rk.n0)
+        E.lib().emu_gradient(C.byref(dd), 0, rk.ptr(rk.x, 0, 0), rk.ptr(rk.zb[0], 0, 0))
+    _exchange_iter(ranks, 0, periodic)
+    fn = E.lib().emu_tv_iter_tma_p2p
+    fn.argtypes = E.lib().emu_tv_iter_tma.argtypes + [C.POINTER(K.Peer)]
+    addr = lambda t, comp, plane_index, rk: t.ctypes.data + 8 * ((comp * t.shape[1] + plane_index) * rk.plane)
+    for it in range(n_iter):
+        for r, rk in enumerate(ranks):
+            s, t = rk.cur, 1 - rk.cur
+            pr = K.Peer()
+            if rk.has_lo:
+                lo = ranks[(r - 1) % world]
+                pr.dn_u = addr(lo.ub[t], 0, rk.H + lo.n0, lo)
+                pr.dn_z = addr(lo.zb[t], 0, rk.H + lo.n0, lo)
+                pr.dn_zvol = lo.zb[t].shape[1] * lo.plane
+                pr.dn_flag = flags[(r - 1) % world].ctypes.data + 4
+                pr.lo_wait = flags[r].ctypes.data
+            if rk.has_hi:
+                hi = ranks[(r + 1) % world]
+                pr.up_z0 = addr(hi.zb[t], 0, rk.H - 1, hi)
+                pr.up_flag = flags[(r + 1) % world].ctypes.data
+                pr.hi_wait = flags[r].ctypes.data + 4
+            pr.epoch = it
+            d = rk.desc(0, rk.n0)
+            P = E.pds_params(tau, sigma, rho, gspec=(K.PROX_POS, 0, 0), fkind=K.F_SQL2, alpha=0.5, hkind=K.DUAL_L21, lam=lam)
+            P.f.shift = rk.sh.ctypes.data + 8 * rk.H * rk.plane
+            P.f.shift_period = rk.sh.shape[1] * rk.plane
+            rc = fn(K.ALGO_PD3O, C.byref(d), C.byref(P), rk.ptr(rk.ub[s], 0, 0), rk.ptr(rk.zb[s], 0, 0), rk.ptr(rk.ub[t], 0, 0), rk.ptr(rk.zb[t], 0, 0),
+                    rk.ptr(rk.x, 0, 0), None, None, chunk, C.byref(pr))
+            assert rc == 0, (rc, r, it)
+        for rk in ranks:
+            rk.cur = 1 - rk.cur
+    x = np.concatenate([rk.x[0, 1:-1] for rk in ranks], axis=0)
+    z = np.concatenate([rk.zb[rk.cur][:, 1:-1] for rk in ranks], axis=1)
+    assert np.allclose(x, x_ref, rtol=1e-13, atol=1e-15) and np.allclose(z, z_ref, rtol=1e-13, atol=1e-15)
+    # every edge thread block signalled once per iteration: counters = iterations x tiles per plane
+    tiles = -(-shape[1] // 8) * -(-shape[2] // 64)
+    for r, rk in enumerate(ranks):
+        assert flags[r][0] == (n_iter * tiles if rk.has_lo else 0) and flags[r][1] == (n_iter * tiles if rk.has_hi else 0)
+
+
 def _worker_many(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
