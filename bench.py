@@ -581,6 +581,10 @@ def main():
         slv._plan.iter_ok = False
         if slv._slab is not None:
             slv._slab.fused = False
+    exchange = None
+    if slv._slab is not None:
+        exchange = ("stored into the neighbours' ghost planes by the iteration kernel itself (peer memory over NVLink, pxb_pds_iter_p2p), edge chunks first"
+                    if slv._slab.p2p is not None else "NCCL send/recv on a high-priority stream while the interior is computed")
     slv._probe = probe
     with ClockSampler(env.local) as clk:  # nvidia-smi is started before the warm-up so that it is sampling when the timed region begins
         for _ in range(W):
@@ -659,6 +663,11 @@ def main():
 
     configs = None
     if not args.no_configs:
+        if world > 1:
+            from pyxu_b200 import slab
+
+            slab.release_pool()  # the headline volume's pooled slab buffers
+            env.barrier()
         configs = secondary_configs(env, peak)
 
     cpu = None
@@ -683,7 +692,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(n),
                        "solver": "pyxu_b200.opt.solver.PD3O(f, g, h, K).fit() -- the same object at every N",
-                       "decomposition": "single GPU" if world == 1 else f"{world} z-slabs behind Solver.fit(), boundary planes of the new iterate (5 planes per interface) exchanged by NCCL send/recv while the interior is computed",
+                       "decomposition": "single GPU" if world == 1 else f"{world} z-slabs behind Solver.fit(); boundary planes of the new iterate (5 planes per interface): {exchange}",
                        "l2_policy": f"inputs larger than L2: {4 * nvox / world / 2**20:.0f} MiB per field per GPU vs 126 MB L2",
                        "iterations_per_step": 1},
             "clocks": clk.summary(t_begin, t_end), "e2e": e2e, "gpu_launches": launches, "parity": parity,
@@ -691,6 +700,10 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        from pyxu_b200 import slab
+
+        slab.release_pool()  # drop the mappings of the neighbours' buffers before anybody's process ends
+        env.barrier()
         dist.destroy_process_group()
 
 

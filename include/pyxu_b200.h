@@ -411,6 +411,9 @@ int pxb_sqnorms(int dtype, int64_t rows, int64_t n, const void* x, const void* y
 
 /* misc */
 int pxb_abi_version(void);
+/* Lets kernels launched on the calling thread's current device reach memory of `peer_device` (needed once per pair before
+ * pxb_pds_iter_p2p is handed pointers into a neighbour's allocation).  PXB_ENOSUP when the two GPUs have no peer path. */
+int pxb_enable_peer_access(int peer_device);
 const char* pxb_last_error(void);
 /* number of kernels this library has launched in the calling process (bench's gpu_launches) */
 int64_t pxb_launch_count(void);

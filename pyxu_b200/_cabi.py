@@ -173,6 +173,7 @@ PROTOTYPES = {
     "pxb_abi_version": (_i, []),
     "pxb_last_error": (C.c_char_p, []),
     "pxb_launch_count": (_i64, []),
+    "pxb_enable_peer_access": (_i, [_i]),
     "pxb_stencil_apply": (_i, [_P(StencilDesc), _vp, _vp, _vp]),
     "pxb_stencil_adjoint": (_i, [_P(StencilDesc), _vp, _vp, _vp]),
     "pxb_stencil2d_apply": (_i, [_P(Stencil2D), _vp, _vp, _vp]),

@@ -379,6 +379,23 @@ int pxb_set_iter_path(int path) {
 }
 
 int pxb_abi_version(void) { return PXB_ABI_VERSION; }
+
+int pxb_enable_peer_access(int peer_device) {
+    int me = -1;
+    cudaError_t e = cudaGetDevice(&me);
+    if (e != cudaSuccess) return pxb_fail(PXB_ECUDA, "pxb_enable_peer_access: %s", cudaGetErrorString(e));
+    if (me == peer_device) return 0;
+    int can = 0;
+    e = cudaDeviceCanAccessPeer(&can, me, peer_device);
+    if (e != cudaSuccess || !can) {
+        (void)cudaGetLastError();
+        return pxb_fail(PXB_ENOSUP, "pxb_enable_peer_access: device %d cannot access device %d", me, peer_device);
+    }
+    e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) return pxb_fail(PXB_ECUDA, "pxb_enable_peer_access: %s", cudaGetErrorString(e));
+    return 0;
+}
 const char* pxb_last_error(void) { return g_err.c_str(); }
 int64_t pxb_launch_count(void) { return g_launches.load(); }
 

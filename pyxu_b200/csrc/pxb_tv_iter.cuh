@@ -88,7 +88,7 @@ struct PxbIterPtr {
 // spin (one thread) until the neighbour's counter has reached `target`; bounded, then trap: a lost signal must fail the
 // launch loudly instead of hanging the device
 static __device__ __forceinline__ void pxb_peer_wait(const unsigned* flag, unsigned target) {
-    for (unsigned spin = 0; spin < (1u << 28); ++spin) {
+    for (unsigned spin = 0; spin < (1u << 24); ++spin) {  // ~10 s
         unsigned v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int)(v - target) >= 0) return;

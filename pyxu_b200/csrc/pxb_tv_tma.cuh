@@ -105,6 +105,8 @@ struct PxbTmaThread {
     T z0p[VEC];       // z0 of the previous plane at: own samples ...
     T z0p_rim[VEC];   //   ... the rim-row samples this thread computes (warps 0, 1)
     T z0p_col;        //   ... the rim-column sample (last 2*TY threads)
+    T xp[VEC];        // PD3O + RelError[x]: the previous x of the plane phase A visits next, loaded one plane ahead so that
+                      // the global-load latency is not in the per-plane critical path (everything else is staged by TMA)
     double acc[4];
 };
 
@@ -241,13 +243,19 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = keep ? wv[j] : T(0);
         pxb_vstore<T, VEC>(slot + (rl + 1) * R::RS + cl + VEC, o);
+        // previous x of this thread's samples on the NEXT plane (consumed one plane later)
+        PxbVec<T, VEC> xp_next;
+        const bool pre = ALGO == PXB_PD3O && NORMS && a.norms_x != nullptr && m + 1 >= it.m0 && m + 1 < it.m1 && r < g.nR && c < g.nC;
+        if (pre) xp_next = pxb_vload<T, VEC>(a.x_out + it.lin_base + (int64_t)(m + 1) * g.sM + (int64_t)r * g.sR + c);
         if (own && in) {
             const int64_t lin = it.lin_base + (int64_t)m * g.sM + (int64_t)r * g.sR + c;
             if (ALGO == PXB_PD3O) {
                 if (NORMS && a.norms_x) {
                     // partial sums of one vector in the working precision, widened once (fp32: the per-sample fp64
                     // conversions and FMAs made the criterion-carrying instance issue-bound: 9.3 ms instead of 7.5 at 1024^3)
-                    const PxbVec<T, VEC> xp = pxb_vload<T, VEC>(a.x_out + lin);
+                    PxbVec<T, VEC> xp;
+                    if (m == it.m0) xp = pxb_vload<T, VEC>(a.x_out + lin);  // first plane of the work item: nothing was prefetched
+                    else for (int j = 0; j < VEC; ++j) xp.v[j] = th.xp[j];
                     T s0 = T(0), s1 = T(0);
                     for (int j = 0; j < VEC; ++j) {
                         const T dd = xo[j] - xp.v[j];
@@ -273,6 +281,7 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             // peer-memory exchange: the first owned plane of the new primal iterate is the lower neighbour's upper ghost plane
             if (a.peer.dn_u != nullptr && m == 0) pxb_vstore<T, VEC>(a.peer.dn_u + (int64_t)r * g.sR + c, o);
         }
+        if (pre) for (int j = 0; j < VEC; ++j) th.xp[j] = xp_next.v[j];
     }
     // rims: w of the neighbouring tiles' border samples (only on planes this work item updates); the carried z0 of
     // the previous plane is refreshed on every plane

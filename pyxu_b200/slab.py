@@ -212,11 +212,24 @@ class PeerBuffers:
         dist.all_gather_object(everyone, mine)
         opened = {}
 
+        me = torch.cuda.current_device()
+
         def open_rank(r):
+            """Neighbour r's buffers as tensors whose data_ptr() is valid in kernels launched on THIS device: the IPC handle is
+            opened with this device current (argument 6 of torch's rebuild function is the device the mapping is made for;
+            cudaIpcOpenMemHandle then sets up peer access to the exporting GPU by itself), after peer access has been switched
+            on explicitly as well."""
             if r is None:
                 return None
             if r not in opened:
-                opened[r] = {k: fn(*args) for k, (fn, args) in everyone[r].items()}
+                out = {}
+                for k, (fn, args) in everyone[r].items():
+                    args = list(args)
+                    if int(args[6]) != me:
+                        K.check(K.lib().pxb_enable_peer_access(int(args[6])), "pxb_enable_peer_access")
+                        args[6] = me
+                    out[k] = fn(*args)
+                opened[r] = out
             return opened[r]
 
         self.lo, self.hi = open_rank(lo), open_rank(hi)

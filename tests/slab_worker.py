@@ -56,6 +56,7 @@ def main(dev="cuda"):
         results.append(good)
         if rank == 0:
             form = type(eng).__name__ + ("/single-kernel" if getattr(eng, "fused", True) else "/two-sweep")
+            form += ", exchange: " + ("fused into the kernel (peer memory)" if getattr(eng, "p2p", None) is not None else "NCCL send/recv")
             print(f"[slab] world={world} {name} ({form}, overlap={eng.overlap}): rel.err vs reference " + ", ".join(f"{e:.2e}" for e in errs)
                   + f" {'OK' if good else 'FAIL'}", flush=True)
 
@@ -141,6 +142,9 @@ def main(dev="cuda"):
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"[slab] world={world}: {sum(results)}/{len(results)} cases OK", flush=True)
+    del slv
+    slab.release_pool()  # drop the mappings of the neighbours' buffers before anybody's process ends
+    dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if t.item() == 1.0 else 1)
 

@@ -11,6 +11,7 @@ import pytest
 import cases
 import emu_util as E
 import pyxu_b200.operator as pxo
+from pyxu_b200 import _cabi as K
 from conftest import golden
 
 
@@ -79,6 +80,25 @@ def test_rank_one_dense_kernels_take_the_separable_passes():
     assert full._tiled_plan(False)[1][0] == "dense"
     f32 = pxo.Stencil(arg_shape=(40, 64), kernel=np.outer(g9, g9).astype(np.float32), center=(4, 4), mode="constant")
     assert f32._tiled_plan(False)[1][0] == "sep"  # rank 1 at fp32 resolution
+
+
+def test_rank_one_dense_3d_kernels_are_split_into_three_factors():
+    g = [gauss(7, 1.2), gauss(5, 1.0), gauss(7, 1.5)]
+    for dt, tol in ((np.float64, 1e-13), (np.float32, 2e-6)):
+        dense = np.einsum("i,j,k->ijk", *g).astype(dt)
+        op = pxo.Stencil(arg_shape=(12, 20, 32), kernel=dense, center=(3, 2, 3), mode="constant")
+        for adj in (False, True):
+            plan = op._tiled_plan(adj)
+            assert plan is not None and plan[0] is not None and plan[1][0] == "sep"  # a factor along axis 0 + separable in-plane part
+            assert op._desc3d(K.F64 if dt == np.float64 else K.F32, adj, 1) is not None
+        # the three factors multiply back to the kernel
+        fac = [k3.reshape(-1) for k3, _ in op._rank1_split(*op._passes(False)[0])]
+        assert relerr(np.einsum("i,j,k->ijk", *fac), dense) < tol
+        bumped = dense.copy()
+        bumped[1, 2, 3] *= 1.05
+        assert pxo.Stencil(arg_shape=(12, 20, 32), kernel=bumped, center=(3, 2, 3), mode="constant")._tiled_plan(False) is None
+        pair = np.einsum("j,k->jk", g[1], g[2])[None].astype(dt)  # (1, 5, 7): no factor along axis 0, the 2-D rule applies
+        assert pxo.Stencil(arg_shape=(12, 20, 32), kernel=pair, center=(0, 2, 3), mode="constant")._tiled_plan(False)[0] is None
 
 
 def test_tiled_not_applicable():

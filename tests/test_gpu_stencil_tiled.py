@@ -134,6 +134,29 @@ def test_single_pass_3d_and_fast_gradient(dtype, tol):
         assert abs(float(lhs - rhs)) < (1e-10 if dtype == np.float64 else 2e-4) * (1 + abs(float(lhs)))
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 5e-6)])
+def test_dense_3d_psf_that_is_an_outer_product_takes_the_single_pass(dtype, tol):
+    """BASELINE configs[4] names a "7x7x7 Stencil PSF": handed over as a dense array, a Gaussian PSF is recognised as
+    a (x) b (x) c and served by pxb_stencil3d_apply (21 taps per sample); a PSF that is not an outer product keeps the gather kernel."""
+    import pyxu_b200.operator as pxo
+
+    shape = (40, 45, 264)
+    g = [gauss(7, 1.2), gauss(5, 1.0), gauss(7, 1.5)]
+    dense = np.einsum("i,j,k->ijk", *g).astype(dtype)
+    fast = pxo.Stencil(arg_shape=shape, kernel=dense, center=(3, 2, 3), mode="constant")
+    sep = pxo.Stencil(arg_shape=shape, kernel=[k.astype(dtype) for k in g], center=(3, 2, 3), mode="constant")
+    slow = pxo.Stencil(arg_shape=shape, kernel=dense, center=(3, 2, 3), mode="constant")
+    slow._tiled_ok = slow._tiled3d_ok = False
+    x = torch.randn(2, fast.dim, device="cuda", dtype=torch.float64 if dtype == np.float64 else torch.float32)
+    for adj in (False, True):
+        a, b, c = ((o.adjoint(x) if adj else o.apply(x)) for o in (fast, sep, slow))
+        assert fast._tiled3d_ok is True, "the single-pass 3-D kernel did not run"
+        assert rel(a, b) < tol and rel(a, c) < tol, (adj, rel(a, b), rel(a, c))
+    bumped = dense.copy()
+    bumped[0, 0, 0] += 0.01
+    assert pxo.Stencil(arg_shape=shape, kernel=bumped, center=(3, 2, 3), mode="constant")._tiled_plan(False) is None
+
+
 def test_tiled_stencils_random_geometries():
     """Random kernel extents / centres / shapes (degenerate ones included) for every tiled path -- 2-D separable and dense,
     3-D single pass, axis-0 streaming + tiled -- apply and adjoint against the gather kernels."""

@@ -80,8 +80,15 @@ def main():
     else:
         allrows = [row]
     if env.rank == 0:
-        print(json.dumps({"workload": bench.workload_name(n), "n_gpus": env.world, "steps": K, "ranks": allrows}))
+        print(json.dumps({"workload": bench.workload_name(n), "n_gpus": env.world, "steps": K,
+                          "exchange": "peer memory (pxb_pds_iter_p2p)" if (slv._slab is not None and slv._slab.p2p is not None) else "NCCL send/recv",
+                          "ranks": allrows}))
     if env.world > 1:
+        from pyxu_b200 import slab
+
+        del slv
+        slab.release_pool()
+        env.barrier()
         dist.destroy_process_group()
 
 
