@@ -222,6 +222,9 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:  # nvidia-smi takes a moment to start: be sampling before anything is timed
+                time.sleep(0.02)
         except Exception:
             self.proc = None
         return self

@@ -324,24 +324,33 @@ class LinOp(DiffMap):
         return ar.transpose(self)
 
     def estimate_lipschitz(self, **kwargs):
-        """Spectral norm by power iteration on A^T A, run on the device
-        (the reference uses scipy.sparse.linalg.svds, operator.py:1440-1507)."""
+        """Spectral norm by power iteration on A^T A, run on the device (the reference uses scipy.sparse.linalg.svds,
+        operator.py:1440-1507).  Power iteration approaches ||A||^2 from BELOW, and slowly when the top of the spectrum is dense
+        (Gradient, Stencil): it runs until the estimate moves by less than `tol` (default 1e-3, as the reference's svds tol)
+        or `n_iter` (default 500) iterations, and the result is inflated by the last relative change (at least `margin`,
+        default 1 %), so that step-size rules built on it (tau sigma ||K||^2 <= 1) stay on the safe side."""
         import torch
 
-        n_iter = int(kwargs.get("n_iter", 60))
+        n_iter = int(kwargs.get("n_iter", 500))
+        tol = float(kwargs.get("tol", 1e-3))
+        margin = float(kwargs.get("margin", 1e-2))
         dtype = kwargs.get("dtype", torch.float64)
         g = torch.Generator(device="cpu").manual_seed(0)
         x = torch.randn(self.dim, generator=g, dtype=torch.float64).to(device=A.current_device(), dtype=dtype)
-        sig2 = 0.0
-        for _ in range(n_iter):
+        sig2, change = 0.0, 1.0
+        for it in range(n_iter):
             nrm = float(kr.sqnorms(x)[0, 0].sqrt())
             if nrm == 0:
                 return 0.0
             x = kr.lincomb(1.0 / nrm, x)
             y = self.adjoint(self.apply(x))
-            sig2 = float(kr.sqnorms(y)[0, 0].sqrt())
+            new = float(kr.sqnorms(y)[0, 0].sqrt())
+            change = abs(new - sig2) / new if new > 0 else 0.0
+            sig2 = new
             x = y
-        return math.sqrt(sig2)
+            if it >= 5 and change < tol:
+                break
+        return math.sqrt(sig2 * (1.0 + max(margin, change)))
 
     def asarray(self, **kwargs):
         import torch

@@ -139,6 +139,11 @@ class PGD(Solver):
             if self._nx is not None:
                 self._nx = None
                 mst.pop("_fused_norms", None)
+                # The criterion took its first call on the fused branch (it only marked itself started): let it start over on
+                # the generic branch with the current iterate as its reference point, so that the x_1-vs-x_0 test is not skipped.
+                crit = self._astate["stop_crit"]
+                crit.clear()
+                crit.stop(mst)
         x, xp, tau = mst["x"], mst["x_prev"], mst["tau"]
         if self._y is None:
             self._y = A.empty_like(x)
