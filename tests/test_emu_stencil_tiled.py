@@ -104,8 +104,12 @@ def test_rank_one_dense_3d_kernels_are_split_into_three_factors():
 def test_tiled_not_applicable():
     op = pxo.Stencil(arg_shape=(20, 24), kernel=np.ones((3, 3)), center=(1, 1), mode="reflect")
     assert op._tiled_plan(False) is None
+    full = np.ones((3, 3, 3))
+    full[0, 1, 2] = 2.0  # not an outer product
+    op = pxo.Stencil(arg_shape=(6, 20, 24), kernel=full, center=(1, 1, 1), mode="constant")
+    assert op._tiled_plan(False) is None  # dense 3-D kernels of full rank keep the generic path ...
     op = pxo.Stencil(arg_shape=(6, 20, 24), kernel=np.ones((3, 3, 3)), center=(1, 1, 1), mode="constant")
-    assert op._tiled_plan(False) is None  # dense 3-D kernels keep the generic path
+    assert op._tiled_plan(False) is not None  # ... an outer product handed over as an array takes the separable single pass
     op = pxo.Stencil(arg_shape=(20, 22), kernel=np.ones((3, 3), dtype=np.float32), center=(1, 1), mode="constant")
     x = np.zeros(op.dim, dtype=np.float32)
     assert E.stencil_run_tiled(op, x, False) is None  # fp32: the last axis must be a multiple of 4 samples
