@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
+    *os.environ.get("PYXU_B200_NVCC_EXTRA", "").split(),  # e.g. -DPXB_EXPERIMENT for the A/B switches of tools/bench_criterion.py
 ]
 
 

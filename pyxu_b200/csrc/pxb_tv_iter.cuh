@@ -26,6 +26,18 @@
 #pragma once
 #include "pxb_tv_fast.cuh"
 
+// A/B switches for timing experiments (tools/bench_criterion.py --exp): compiled in only with -DPXB_EXPERIMENT, set per process
+// through the environment variable PXB_EXP; PXB_EXP(bit) is the constant 0 in every normal build and on the host emulation.
+#if defined(PXB_EXPERIMENT) && defined(__CUDA_ARCH__)
+static __device__ int pxb_exp_flags;
+#define PXB_EXP(bit) ((pxb_exp_flags & (bit)) != 0)
+#elif defined(PXB_EXPERIMENT) && defined(__CUDACC__)
+static __device__ int pxb_exp_flags;
+#define PXB_EXP(bit) false
+#else
+#define PXB_EXP(bit) false
+#endif
+
 struct PxbIterGeom {
     int nM, nR, nC;       // extents along M, rows (1 when NDIR == 2), columns
     int64_t sM, sR;       // strides in elements (columns: 1)
@@ -429,7 +441,7 @@ PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
         pxb_dual_prox_group<T>(pxb_hkind<S>(q), NDIR, q.lam, q.sigma, grp);
         for (int k = 0; k < NDIR; ++k) {
             const T zn = q.one_m_rho * zo[k][j] + q.rho * grp[k];
-            if (NORMS) {
+            if (NORMS && !PXB_EXP(4)) {
                 const T dd = zn - zo[k][j];
                 a0 += dd * dd;
                 a1 += zo[k][j] * zo[k][j];

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(32 * TY, 2)
     for (int k = 0; k < 3; ++k)
         for (int j = 0; j < VEC; ++j) th.zc[k][j] = th.zprev[k][j] = T(0);
     for (int k = 0; k < 4; ++k) th.acc[k] = 0.0;
-    pxb_tma_prologue<T, VEC, TY, MODES>(q, g, it, a, tid, R.mlo, th);
+    pxb_tma_prologue<T, VEC, TY, MODES, ALGO == PXB_PD3O && NORMS>(q, g, it, a, tid, R.mlo, th);
 
     const int lag = S::SCHEME == PXB_SCHEME_FWD ? 1 : R.lag;
     int s = 0;            // stage of plane m, and the parity of its mbarrier phase
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(32 * TY, 2)
         }
     }
 
-    if (NORMS) {
+    if (NORMS && !PXB_EXP(2)) {
         __shared__ double red[4][C::NT / 32];
         double v[4] = {th.acc[0], th.acc[1], th.acc[2], th.acc[3]};
         for (int o = 16; o > 0; o >>= 1)
@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(32 * TY, 2)
             double s4[4] = {0.0, 0.0, 0.0, 0.0};
             for (int i = 0; i < C::NT / 32; ++i)
                 for (int kk = 0; kk < 4; ++kk) s4[kk] += red[kk][i];
-            if (a.norms_x) { atomicAdd(a.norms_x + 2 * it.b, s4[0]); atomicAdd(a.norms_x + 2 * it.b + 1, s4[1]); }
-            if (a.norms_z) { atomicAdd(a.norms_z + 2 * it.b, s4[2]); atomicAdd(a.norms_z + 2 * it.b + 1, s4[3]); }
+            if (a.norms_x && !PXB_EXP(1)) { atomicAdd(a.norms_x + 2 * it.b, s4[0]); atomicAdd(a.norms_x + 2 * it.b + 1, s4[1]); }
+            if (a.norms_z && !PXB_EXP(1)) { atomicAdd(a.norms_z + 2 * it.b, s4[2]); atomicAdd(a.norms_z + 2 * it.b + 1, s4[3]); }
             pxb_iter_finish(a.stop, a.norms_x, a.norms_z, gridDim.x);
         }
     }
@@ -154,6 +154,14 @@ int run(const pxb_grad_desc& d, const pxb_pds_params& P, const PxbIterPtr<T>& a_
     // specialised instances: forward differences + L21 + shifted squared-l2 data term staged per voxel + g in
     // {positivity, none}; everything else runs the generic instance
     const int spec = pxb_tma_pick_spec<T>(cf, q, tg);
+#ifdef PXB_EXPERIMENT
+    {
+        static int exp_set = -1;
+        const char* e = getenv("PXB_EXP");
+        const int v = e ? atoi(e) : 0;
+        if (v != exp_set) { cudaMemcpyToSymbol(pxb_exp_flags, &v, sizeof(int)); exp_set = v; }
+    }
+#endif
     auto go = [&](auto kern) {
         // (the attribute is per function: set it on every launch path once; cheap enough to repeat)
         cudaError_t e = pxb_smem_attr_once((const void*)kern, (int)C::SMEM);

@@ -187,12 +187,20 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
 
 // z0 of plane mlo-1 at the samples whose previous-plane value this thread carries (start of a work item)
 // (MODES: a rim thread carries the value at the sample its rim cell stands for, see pxb_rim_src)
-template <class T, int VEC, int TY, bool MODES = false>
+// XPREV (PD3O with RelError[x] sums): also the previous x of the first plane the work item updates
+template <class T, int VEC, int TY, bool MODES = false, bool XPREV = false>
 PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid, int mlo,
                              PxbTmaThread<T, VEC>& st) {
     using C = PxbTmaCfg<T, VEC, TY>;
     for (int j = 0; j < VEC; ++j) st.z0p[j] = st.z0p_rim[j] = T(0);
     st.z0p_col = T(0);
+    if (XPREV && a.norms_x != nullptr) {
+        const int rl = tid / C::TXL, r = it.r0 + rl, c = it.c0 + (tid - rl * C::TXL) * VEC;
+        if (r < g.nR && c < g.nC) {
+            const PxbVec<T, VEC> v = pxb_vload<T, VEC>(a.x_out + it.lin_base + (int64_t)it.m0 * g.sM + (int64_t)r * g.sR + c);
+            for (int j = 0; j < VEC; ++j) st.xp[j] = v.v[j];
+        }
+    }
     if (q.cp[0] == T(0)) return;  // (run-time test: executed once per work item)
     const int mp = mlo - 1;
     if (!((mp >= 0 || g.open_lo) && (mp < g.nM || g.open_hi))) return;
@@ -243,24 +251,17 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = keep ? wv[j] : T(0);
         pxb_vstore<T, VEC>(slot + (rl + 1) * R::RS + cl + VEC, o);
-        // previous x of this thread's samples on the NEXT plane (consumed one plane later)
-        PxbVec<T, VEC> xp_next;
-        const bool pre = ALGO == PXB_PD3O && NORMS && a.norms_x != nullptr && m + 1 >= it.m0 && m + 1 < it.m1 && r < g.nR && c < g.nC;
-        if (pre) xp_next = pxb_vload<T, VEC>(a.x_out + it.lin_base + (int64_t)(m + 1) * g.sM + (int64_t)r * g.sR + c);
         if (own && in) {
             const int64_t lin = it.lin_base + (int64_t)m * g.sM + (int64_t)r * g.sR + c;
             if (ALGO == PXB_PD3O) {
                 if (NORMS && a.norms_x) {
                     // partial sums of one vector in the working precision, widened once (fp32: the per-sample fp64
                     // conversions and FMAs made the criterion-carrying instance issue-bound: 9.3 ms instead of 7.5 at 1024^3)
-                    PxbVec<T, VEC> xp;
-                    if (m == it.m0) xp = pxb_vload<T, VEC>(a.x_out + lin);  // first plane of the work item: nothing was prefetched
-                    else for (int j = 0; j < VEC; ++j) xp.v[j] = th.xp[j];
-                    T s0 = T(0), s1 = T(0);
+                    T s0 = T(0), s1 = T(0);  // (th.xp: loaded one plane ahead -- by the prologue for the work item's first plane)
                     for (int j = 0; j < VEC; ++j) {
-                        const T dd = xo[j] - xp.v[j];
+                        const T dd = xo[j] - th.xp[j];
                         s0 += dd * dd;
-                        s1 += xp.v[j] * xp.v[j];
+                        s1 += th.xp[j] * th.xp[j];
                     }
                     th.acc[0] += (double)s0;
                     th.acc[1] += (double)s1;
@@ -281,7 +282,13 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             // peer-memory exchange: the first owned plane of the new primal iterate is the lower neighbour's upper ghost plane
             if (a.peer.dn_u != nullptr && m == 0) pxb_vstore<T, VEC>(a.peer.dn_u + (int64_t)r * g.sR + c, o);
         }
-        if (pre) for (int j = 0; j < VEC; ++j) th.xp[j] = xp_next.v[j];
+        // previous x of this thread's samples on the NEXT plane, consumed one plane later: loaded straight into the registers
+        // the sums above have just released (a load into a temporary moved over afterwards made the move wait for the load:
+        // 9.5 ms instead of 7.3 at 1024^3, long-scoreboard stalls doubled)
+        if (ALGO == PXB_PD3O && NORMS && !PXB_EXP(8) && a.norms_x != nullptr && m + 1 >= it.m0 && m + 1 < it.m1 && r < g.nR && c < g.nC) {
+            const PxbVec<T, VEC> nx = pxb_vload<T, VEC>(a.x_out + it.lin_base + (int64_t)(m + 1) * g.sM + (int64_t)r * g.sR + c);
+            for (int j = 0; j < VEC; ++j) th.xp[j] = nx.v[j];
+        }
     }
     // rims: w of the neighbouring tiles' border samples (only on planes this work item updates); the carried z0 of
     // the previous plane is refreshed on every plane

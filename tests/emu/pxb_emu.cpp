@@ -248,7 +248,7 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
         for (int m = Rg.mlo; m < Rg.mlo + C::NSTAGE && m < mload_hi; ++m) issue(m);
         for (int tid = 0; tid < C::NT; ++tid) {
             std::memset(&th[tid], 0, sizeof(th[tid]));
-            pxb_tma_prologue<T, VEC, TY, MODES>(q, g, it, a, tid, Rg.mlo, th[tid]);
+            pxb_tma_prologue<T, VEC, TY, MODES, ALGO == PXB_PD3O && NORMS>(q, g, it, a, tid, Rg.mlo, th[tid]);
         }
         for (int m = Rg.mlo; m < Rg.mhi; ++m) {
             const int k = m - Rg.mlo;
