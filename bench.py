@@ -656,8 +656,10 @@ def main():
         e2e = {"value": nvox * K / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(2 * 4 * nvox / K),
                "d2h_bytes_per_step": int(4 * nvox / K + 16 * world), "seconds": dt, "parts": runs[1], "first_call": runs[0],
                "what": "per rank: PD3O(...).fit(x0=<pinned host array>, stop_crit=MaxIter(K)|RelError[x]) + solution(): H2D of x0 and of the data y "
-                       "(this rank's planes), K fused iterations with RelError[x] tested after every one of them (1 GPU: on the device, iterations "
-                       "queued back to back, sums read back per batch; N ranks: sums all-reduced and read back every step), D2H of x into a "
+                       "(this rank's planes), K fused iterations with RelError[x] tested after every one of them (1 GPU: x0 and y travel in 16-plane "
+                       "z-chunks and the iterations are queued as a wavefront behind the chunks, the result travels back behind the wave, the "
+                       "criterion is replayed from the sums every iteration left on the device -- SlabTV.run_streamed; N ranks: one upload, "
+                       "sums all-reduced and read back every step), D2H of x into a "
                        "pinned result buffer reserved beforehand (reserve_host_results); wall clock between barriers, max over ranks; second of two "
                        "calls (the first one, which also pays one-off initialisation, is `first_call`)"}
         A_.release_host_results()

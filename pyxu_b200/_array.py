@@ -145,21 +145,30 @@ def _give_back(nbytes, buf):
             _RESULT_POOL[nbytes].append(buf)
 
 
-def _d2h_reserved(t):
-    """Device tensor -> NumPy array backed by a reserved pinned buffer (None when no free buffer of that size exists)."""
+def take_reserved(nbytes):
+    """A free reserved pinned buffer of exactly `nbytes` (uint8 tensor), or None; finish with as_result() or _give_back()."""
+    with _POOL_LOCK:
+        free = _RESULT_POOL.get(int(nbytes))
+        return free.pop() if free else None
+
+
+def as_result(buf, dtype, shape):
+    """The NumPy face of a reserved buffer that holds a result; the buffer returns to the pool when the array is collected."""
     import weakref
 
-    nbytes = t.numel() * t.element_size()
-    with _POOL_LOCK:
-        free = _RESULT_POOL.get(nbytes)
-        buf = free.pop() if free else None
+    out = buf.numpy().view(np_dtype(dtype)).reshape(tuple(shape))
+    weakref.finalize(out, _give_back, buf.numel(), buf)  # views keep `out` alive through .base
+    return out
+
+
+def _d2h_reserved(t):
+    """Device tensor -> NumPy array backed by a reserved pinned buffer (None when no free buffer of that size exists)."""
+    buf = take_reserved(t.numel() * t.element_size())
     if buf is None:
         return None
     buf.view(t.dtype).copy_(t.reshape(-1), non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    out = buf.numpy().view(np_dtype(t.dtype)).reshape(tuple(t.shape))
-    weakref.finalize(out, _give_back, nbytes, buf)  # views keep `out` alive through .base
-    return out
+    return as_result(buf, t.dtype, t.shape)
 
 
 def _d2h_pipelined(t):
@@ -242,6 +251,54 @@ def _h2d_pipelined(arr, want):
     # buffer waits on before a host thread writes into it again
     torch.cuda.current_stream().wait_stream(copy_stream)
     return out if out.dtype == want else out.to(want)
+
+
+_STAGE_NEXT = [0]  # round-robin index of the staging buffers for chunk-wise uploads (h2d_into)
+
+
+def host_flat(arr, dtype):
+    """A host array as a flat, contiguous NumPy array of the torch dtype `dtype` (no copy when it already is one)."""
+    a = arr.numpy() if isinstance(arr, torch.Tensor) else np.asarray(arr)
+    return np.ascontiguousarray(a, dtype=np_dtype(dtype)).reshape(-1)
+
+
+def is_pinned(arr):
+    try:
+        return bool(torch.from_numpy(arr).is_pinned())
+    except Exception:
+        return False
+
+
+def h2d_into(dst, src, pinned=None, pool=None):
+    """Queue the copy of the flat host array `src` into the contiguous device tensor `dst` (same dtype and size) on the CURRENT
+    stream.  Pinned memory: one asynchronous copy.  Pageable memory: through the pinned staging buffers, `pool` threads (a
+    ThreadPoolExecutor) moving each piece in while the previous piece's copy is in flight; returns once the last piece is queued."""
+    flat = dst.reshape(-1)
+    if pinned is None:
+        pinned = is_pinned(src)
+    if pinned or not flat.is_cuda:
+        flat.copy_(torch.from_numpy(src), non_blocking=True)
+        return
+    src_b, dst_b = src.view(np.uint8), flat.view(torch.uint8)
+    nbytes = src_b.size
+    nthreads = pool._max_workers if pool is not None else 1
+    with _STAGE_LOCK:
+        stage = _staging()
+        for lo in range(0, nbytes, _CHUNK):
+            hi = min(nbytes, lo + _CHUNK)
+            k = _STAGE_NEXT[0] % _NSTAGE
+            _STAGE_NEXT[0] += 1
+            _stage_free(k)
+            buf = stage[k].numpy()
+            step = -(-(hi - lo) // nthreads)
+            if pool is None:
+                np.copyto(buf[: hi - lo], src_b[lo:hi])
+            else:
+                for f in [pool.submit(np.copyto, buf[a : min(hi - lo, a + step)], src_b[lo + a : min(hi, lo + a + step)]) for a in range(0, hi - lo, step)]:
+                    f.result()
+            dst_b[lo:hi].copy_(stage[k][: hi - lo], non_blocking=True)
+            _STAGE_EVENTS[k] = torch.cuda.Event()
+            _STAGE_EVENTS[k].record()
 
 
 def restore(t, origin):

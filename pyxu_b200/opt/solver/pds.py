@@ -44,11 +44,15 @@ def _is_null(op):
 class _Plan:
     """Decides how one iteration is executed and owns the descriptors / work buffers."""
 
-    def __init__(self, solver, algo, x0, part=None):
+    def __init__(self, solver, algo, x0, part=None, defer_shift=False):
         """x0: the primal iterate on the device (a slab's planes under a z-slab decomposition; `part` = (volume shape,
-        rank, world) then makes the planner keep only this rank's planes of per-voxel arrays)."""
+        rank, world) then makes the planner keep only this rank's planes of per-voxel arrays).  defer_shift: a per-voxel
+        shift of the data term that lives in host memory stays there (`fshift_host`; the streamed fit uploads it chunk by
+        chunk together with x0) -- x0 may then be a `meta` tensor that only carries shape and dtype."""
         f, g, h, Kop = solver._f, solver._g, solver._h, solver._K
         self.algo = algo
+        self.fshift_host = None
+        self._defer_shift = bool(defer_shift)
         self._x0_like = x0
         self.kind = "generic"
         self.batch = max(1, x0.numel() // x0.shape[-1])
@@ -63,7 +67,11 @@ class _Plan:
             s = f._sql2_spec()
             if s is not None:
                 self.fkind, self.falpha = K.F_SQL2, float(s[0])
-                self.fshift = self._shift_on_device(s[1], x0, part)
+                c = s[1]
+                if self._defer_shift and isinstance(c, np.ndarray) and c.size == x0.numel():
+                    self.fshift_host = A.host_flat(c, x0.dtype)
+                else:
+                    self.fshift = self._shift_on_device(c, x0, part)
                 if self.fshift is not None and x0.numel() % self.fshift.numel() != 0:
                     self.fkind = None
             elif part is not None:
@@ -108,7 +116,7 @@ class _Plan:
         if isinstance(c, float):
             import torch
 
-            return torch.full((1,), c, dtype=x0.dtype, device=x0.device)
+            return torch.full((1,), c, dtype=x0.dtype, device=A.current_device() if x0.device.type == "meta" else x0.device)
         if part is not None:
             from ... import slab
 
@@ -218,8 +226,9 @@ class _PrimalDualSplitting(Solver):
 
         sharded_in = isinstance(x0, slab.ShardedArray)
         ctx = slab.context(True if (sharded_in and distributed is None) else distributed)
+        self._stream_src = None
         if ctx is None:
-            return False
+            return self._m_init_streamed(x0, z0)
         required = distributed is True or sharded_in
         Kop = self._K
         n_in = int(x0.numel()) if hasattr(x0, "numel") else int(np.size(x0))
@@ -269,6 +278,125 @@ class _PrimalDualSplitting(Solver):
         plan.iter_ok = True
         return True
 
+    # -- single GPU, large HOST arrays: iterations as a wavefront behind the upload (slab.SlabTV.run_streamed) ----------
+    _STREAM_MIN_BYTES = 256 << 20  # smaller volumes are uploaded in one go (PYXU_B200_STREAM_MIN_BYTES overrides; 0 = never stream)
+    _STREAM_EPOCH = 32             # iterations run speculatively behind the upload before the criterion's sums are looked at
+    _STREAM_PLANES = 16
+
+    def _m_init_streamed(self, x0, z0):
+        """fit(x0=<large host array>) in BLOCK mode on a fused 3-D TV problem: nothing is uploaded here; _fit_run() streams x0
+        (and a per-voxel data-term shift that also lives in host memory) in z-chunks with the first iterations queued behind
+        the chunks (the host->device transfer is what bounds a 1024^3 solve end to end).  False: the ordinary path."""
+        import os
+
+        import torch
+
+        from ... import slab
+        from ...abc.solver import Mode
+        from ...operator.linop.diff import _DiffStack
+
+        mst, ast, Kop = self._mstate, self._astate, self._K
+        floor = int(os.environ.get("PYXU_B200_STREAM_MIN_BYTES", self._STREAM_MIN_BYTES))
+        if floor <= 0 or z0 is not None or ast["mode"] is not Mode.BLOCK or not isinstance(x0, np.ndarray):
+            return False
+        if x0.dtype not in (np.float32, np.float64) or x0.nbytes < floor:
+            return False
+        if not (isinstance(Kop, _DiffStack) and len(Kop.arg_shape) == 3 and Kop._dirs == (0, 1, 2) and x0.size == Kop.dim):
+            return False
+        vol = Kop.arg_shape
+        if tuple(Kop._mode)[0] != "constant":  # a z-chunk's cut faces are open sides: exact as long as no fold reaches along axis 0
+            return False
+        if vol[0] < 2 * self._STREAM_PLANES or ast["track_objective"] or ast["wb_rate"] is not None or ast["stop_rate"] != 1:
+            return False
+        tdt = A.torch_dtype(x0.dtype)
+        meta = torch.empty(x0.size, dtype=tdt, device="meta")
+        plan = _Plan(self, self._ALGO, meta, part=(vol, 0, 1), defer_shift=True)
+        if plan.kind != "fused" or plan.fkind == K.F_GRADARR:
+            return False
+        crit = ast["stop_crit"]
+        reads = crit._state_vars()
+        self._plan = plan
+        mst["x"] = mst["z"] = None
+        self._setup_fused_norms(device=A.current_device())
+        served = frozenset(k for k in ("x", "z") if k in mst.get("_fused_norms", {}))
+        if reads is None or not (reads <= served) or crit._rank_local():
+            self._plan = None
+            mst.pop("_fused_norms", None)
+            return False
+        ast["origin"], ast["sharded"] = A.HOST, False
+        params = plan._build_params(mst)
+        self._slab = slab.SlabTV(self._ALGO, Kop, params, None, None, plan.fshift, 0, 1, dtype=tdt, shift_streamed=plan.fshift_host is not None)
+        self._stream_src = (A.host_flat(x0, tdt), plan.fshift_host)
+        self._stream_out = None
+        plan.iter_ok = True
+        return True
+
+    def _run_streamed(self):
+        """The solver loop (abc/solver.py:_step) with the first epoch of iterations queued behind the upload.  The criterion is
+        evaluated afterwards from the sums every iteration left behind, exactly as the loop would have: history, log and the
+        iteration at which it stops are those of the one-iteration-at-a-time loop.  Should the criterion turn out to have been met
+        INSIDE the epoch (the wave had already moved on), the solve is redone from the host arrays up to that iteration."""
+        import copy
+
+        import torch
+
+        ast, mst, eng = self._astate, self._mstate, self._slab
+        crit = ast["stop_crit"]
+        x0_host, shift_host = self._stream_src
+        self._stream_src = None
+        planes = self._STREAM_PLANES
+        if not self._pre_step():  # met before the first iteration: upload only, so that solution() / stats() have their arrays
+            eng.run_streamed(x0_host, shift_host, 0, planes=planes)
+            return
+        budget = crit._budget()  # (inf without a MaxIter leaf)
+        E = int(max(1, min(budget, self._STREAM_EPOCH)))
+        final = E == budget  # a MaxIter leaf fires at the test after iteration E: the result can travel back behind the wave
+        use_x, use_z = self._nx is not None, self._nz is not None
+        nrm = torch.zeros((E, 2, 1, 2), dtype=torch.float64, device=eng.dev) if (use_x or use_z) else None
+        out = None
+        if final and "x" in ast["log_var"]:
+            buf = A.take_reserved(eng.local_voxels * eng._pb[0].element_size())
+            out = buf.view(eng.dtype) if buf is not None else None
+        done = eng.run_streamed(x0_host, shift_host, E, nrm, use_x, use_z, out, planes=planes)
+        if done == 0:  # outside the single-kernel envelope: everything is on the device, iterate the ordinary way
+            if out is not None:
+                A._give_back(buf.numel(), buf)
+            ast["idx"] += 1  # (the test that precedes the first iteration was made above)
+            self.m_step()
+            self._loop_steps()
+            return
+        idx0 = ast["idx"]
+        fused = mst.get("_fused_norms")
+        if nrm is None:  # MaxIter / ManualStop only: nothing to look at
+            sums = np.empty((E, 0))
+            stop_at = None
+        else:
+            sums = nrm.cpu().numpy()  # (synchronises: the wave has left the last chunk)
+            dec, _ = copy.deepcopy(crit)._replay(sums[: E - 1]) if E > 1 else (np.zeros(0, bool), None)
+            hit = np.flatnonzero(dec)
+            stop_at = int(hit[0]) if hit.size else None  # the test after iteration stop_at + 1 fires
+        if stop_at is not None:
+            if out is not None:
+                torch.cuda.synchronize()
+                A._give_back(buf.numel(), buf)
+                out = None
+            E = stop_at + 1
+            eng.reset_streamed()
+            eng.run_streamed(x0_host, shift_host, E, None, False, False, None, planes=planes)  # no sums: the recorded ones stand
+        if E > 1:
+            _, info = crit._replay(sums[: E - 1])
+            self._record_block(idx0 + 1, info)
+        ast["idx"] = idx0 + E
+        if fused is not None:
+            fused["_host"], fused["_stamp"] = sums[E - 1], 0  # the test at the top of the loop reads the last iteration's sums
+        if out is not None:
+            self._stream_out = (ast["idx"], buf)
+        self._loop_steps()
+
+    def _loop_steps(self):
+        while self._step():
+            pass
+
     def _step_slab(self):
         self._zero_norms()
         eng = self._slab
@@ -288,12 +416,26 @@ class _PrimalDualSplitting(Solver):
         from ... import slab
 
         eng = self._slab
+        so = getattr(self, "_stream_out", None)
+        if k == "x" and so is not None and not getattr(self, "_in_writeback", False):  # the streamed fit has already brought x back behind the wave
+            self._stream_out = None
+            if so[0] == self._astate["idx"]:
+                A.synchronize()
+                return A.as_result(so[1], eng.dtype, (eng.local_voxels,))
+            A._give_back(so[1].numel(), so[1])
         loc = eng.x_local().unsqueeze(0) if k == "x" else eng.z_local()
         if self._astate.get("sharded"):
             out = A.restore(loc.contiguous().reshape(-1), self._astate["origin"])
             return slab.ShardedArray(out, eng.shape, comps=loc.shape[0], rank=eng.rank, world=eng.world)
         full = slab.gather_planes(loc, eng.shape, eng.world, group=eng.group) if eng.world > 1 else loc.contiguous()
         return A.restore(full.reshape(-1), self._astate["origin"])
+
+    def writeback(self):
+        self._in_writeback = True  # (the checkpoint copies x out of the device; the streamed result stays for solution())
+        try:
+            super().writeback()
+        finally:
+            self._in_writeback = False
 
     def _setup_fused_norms(self, device=None):
         """If the stopping criterion is RelError on x / z evaluated every iteration, let the update kernels
@@ -398,6 +540,14 @@ class _PrimalDualSplitting(Solver):
         return r
 
     def _fit_run(self):
+        if getattr(self, "_stream_src", None) is not None:
+            try:
+                self._run_streamed()
+            except Exception as e:
+                self._on_error(e)
+            self._astate.update(mode=None, active=None, worker=None)
+            self._cleanup_logger()
+            return
         rule = self._batch_rule() if self._plan is not None else None
         if rule is None:  # (False: batches without a device-side rule)
             return super()._fit_run()

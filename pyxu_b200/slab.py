@@ -321,16 +321,20 @@ class SlabTV(_Engine):
     shift   None | this rank's planes of the data-term shift c (n0 * plane samples, device) | a 1-sample tensor
     """
 
-    def __init__(self, algo, Kop, params, x0, z0=None, shift=None, rank=0, world=1, group=None, overlap=True, fused=True, edge=8, p2p=None):
+    def __init__(self, algo, Kop, params, x0, z0=None, shift=None, rank=0, world=1, group=None, overlap=True, fused=True, edge=8, p2p=None,
+                 dtype=None, shift_streamed=False):
+        """x0 = None (with `dtype`; world 1 only): the initial iterate -- and, with `shift_streamed`, the per-voxel shift of the data
+        term -- is still in host memory and arrives through run_streamed()."""
         A.require_cuda()
-        self.algo, self.dtype = algo, x0.dtype
+        self.algo, self.dtype = algo, (x0.dtype if x0 is not None else dtype)
+        assert x0 is not None or (world == 1 and z0 is None), "deferred initial iterate: single z-slab, z0 = K x0"
         modes = tuple(Kop._mode)
         self._geometry(Kop, rank, world, 1, group, periodic=(modes[0] == "wrap"))
         h, n0 = self.H, self.n0
         assert n0 >= 2 * h + 1, "slabs thinner than 3 planes are not supported"
         self.p = _copy_params(params)
-        self._shift_arr = shift is not None and shift.numel() > 1
-        if self._shift_arr:
+        self._shift_arr = bool(shift_streamed) or (shift is not None and shift.numel() > 1)
+        if self._shift_arr and not shift_streamed:
             assert shift.numel() == self.local_voxels, "data-term shift: one sample per voxel of the slab"
         self.fused = bool(fused)  # single-kernel iteration with ping-pong (primal, z) pairs; decided for good on the first step
         self.edge = max(1, min(int(edge), n0 // 2))  # planes of the boundary launches that precede the exchange
@@ -365,8 +369,13 @@ class SlabTV(_Engine):
         self.shift_h = None
         if self._shift_arr:  # shift WITH ghost planes: the single-kernel form evaluates grad f on the ghost plane too
             self.shift_h = self._field()
-            self.shift_h[0, own].copy_(shift.reshape(n0, *self.shape[1:]))
+            if not shift_streamed:
+                self.shift_h[0, own].copy_(shift.reshape(n0, *self.shape[1:]))
         self._shift1 = shift if (shift is not None and not self._shift_arr) else None
+        self._streams = None
+        if x0 is None:  # run_streamed() fills the fields chunk by chunk
+            self.overlap, self.comm = False, None
+            return
         self._pb[0][0, own].copy_(x0.reshape(n0, *self.shape[1:]))
         if self.x is not None:
             self.x[0, own].copy_(self._pb[0][0, own])
@@ -458,6 +467,110 @@ class SlabTV(_Engine):
             K.check(rc, "pxb_pds_iter")
         self._iter_cache["ran"] = True
         return True
+
+    # -- wavefront over z-chunks behind the upload (single z-slab) -----------------------------------------
+    def run_streamed(self, x0_host, shift_host, n_iter, nrm=None, use_x=False, use_z=False, out=None, planes=16):
+        """Uploads the initial iterate (and the data-term shift) chunk by chunk along axis 0 and runs the first `n_iter` iterations
+        as a WAVEFRONT behind the upload: iteration i of chunk c only reads iterate i of chunks c-1, c, c+1 (one plane of each
+        neighbour), so it is queued as soon as chunk c+i+2 has arrived -- the iterations hide under the PCIe transfer instead of
+        waiting for its end.  With `out` (pinned host tensor, one sample per voxel) the result of the last iteration is copied
+        back chunk by chunk behind the wave, i.e. while later chunks are still being uploaded and iterated.
+
+        Task (i, c), i = -1 .. n_iter-1 (i = -1: z0 = K x0 on the chunk), is issued in the order of i + c (ascending i inside a
+        group), which respects every dependency -- (i, c) needs (i-1, c-1), (i-1, c), (i-1, c+1) -- on ONE in-order compute stream;
+        the ping-pong pair a task overwrites holds iterate i-1, whose last readers are exactly those three tasks.
+
+        x0_host, shift_host : flat host arrays of the slab's dtype (shift_host None: the shift is not per-voxel or is on the device)
+        nrm                 : (n_iter, 2, 1, 2) zeroed device doubles -- RelError sums of every iteration ([:, 0] x when use_x,
+                              [:, 1] z when use_z) -- or None
+        Returns the number of iterations carried out: n_iter, or 0 when the single-kernel form declined the problem (everything
+        is uploaded and z0 initialised then; the caller iterates with step())."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        assert self.world == 1 and self.cur == 0
+        h, n0, plane = self.H, self.n0, self.plane
+        lib = K.lib()
+        main = torch.cuda.current_stream()
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        up, dn = self._streams
+        up.wait_stream(main)  # (the fields were zero-filled on the main stream)
+        bounds = [(p, min(n0, p + planes)) for p in range(0, n0, planes)]
+        if len(bounds) > 1 and bounds[-1][1] - bounds[-1][0] < 2:  # no one-plane tail
+            bounds[-2:] = [(bounds[-2][0], n0)]
+        nchunk = len(bounds)
+        pinned = A.is_pinned(x0_host) and (shift_host is None or A.is_pinned(shift_host))
+        pool = None if pinned else ThreadPoolExecutor(A._copy_threads())
+        write_last = True  # PD3O: the last iteration of the wave writes x (4 B/voxel, once) -- no rebuild from the previous pair later
+        declined = [n_iter <= 0]
+        gdesc = {}
+
+        def upload(c):
+            p0, p1 = bounds[c]
+            with torch.cuda.stream(up):
+                A.h2d_into(self._pb[0][0, h + p0 : h + p1], x0_host[p0 * plane : p1 * plane], pinned, pool)
+                if shift_host is not None:
+                    A.h2d_into(self.shift_h[0, h + p0 : h + p1], shift_host[p0 * plane : p1 * plane], pinned, pool)
+                ev = torch.cuda.Event()
+                ev.record()
+            main.wait_event(ev)
+
+        def task(i, c):
+            p0, p1 = bounds[c]
+            if i < 0:
+                d = gdesc.get(c)
+                if d is None:
+                    d = gdesc[c] = self._desc(p0, p1)
+                K.check(lib.pxb_gradient_apply(C.byref(d), self._p(self._pb[0], 0, p0), self._p(self._zb[0], 0, p0), A.stream()), "gradient_apply")
+                if self.x is not None and use_x:  # RelError[x] of the first iteration compares with x0
+                    self.x[0, h + p0 : h + p1].copy_(self._pb[0][0, h + p0 : h + p1])
+                return
+            if declined[0]:
+                return
+            last = i == n_iter - 1
+            nx = nrm[i, 0] if (nrm is not None and use_x) else None
+            nz = nrm[i, 1] if (nrm is not None and use_z) else None
+            if not self._iter(p0, p1, i % 2, 1 - i % 2, use_x or (last and write_last), nx, nz):
+                declined[0] = True  # outside the single-kernel envelope (decided by the first launch): upload only from here on
+                return
+            if last and out is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                dn.wait_event(ev)
+                src = (self.x if self.x is not None else self._pb[n_iter % 2])[0, h + p0 : h + p1]
+                with torch.cuda.stream(dn):
+                    out[p0 * plane : p1 * plane].copy_(src.reshape(-1), non_blocking=True)
+
+        def group(s):
+            for i in range(-1, n_iter):
+                c = s - i
+                if 0 <= c < nchunk:
+                    task(i, c)
+
+        try:
+            for j in range(nchunk):
+                upload(j)
+                if j < nchunk - 1:
+                    group(j - 2)  # (needs chunks up to j: empty for j = 0)
+                else:
+                    for s in range(j - 2, n_iter + nchunk - 1):
+                        group(s)
+        finally:
+            if pool is not None:
+                pool.shutdown()
+        if out is not None:
+            main.wait_stream(dn)
+        done = 0 if declined[0] else n_iter
+        self.cur = done % 2
+        if self.x is not None:
+            self._x_stale = done > 0 and not (use_x or write_last)
+        return done
+
+    def reset_streamed(self):
+        """Back to the state before run_streamed() (the host arrays are uploaded again by the next call)."""
+        torch.cuda.synchronize()
+        self.cur, self._x_stale = 0, False
+        self._iter_cache.pop("ran", None)
 
     def _peer_block(self, dst):
         """pxb_peer for an iteration that writes iterate `dst`: where this slab's new boundary planes go in the neighbours' copies

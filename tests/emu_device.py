@@ -230,6 +230,9 @@ class _Stream:  # stands in for torch.cuda.Stream / Event: the emulated device e
     def wait_stream(self, other):
         pass
 
+    def wait_event(self, ev):
+        pass
+
     def record(self, *a):
         pass
 

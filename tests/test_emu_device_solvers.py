@@ -250,3 +250,138 @@ def test_gpu_tests_of_the_folding_modes_replayed(dev, monkeypatch):
     GM.test_modes_vs_two_sweeps_2d_batched(env, ("reflect", "wrap"), "tile2d", select)
     GM.test_modes_solver_fit_against_reference_fixtures(env, select)
     dev.lib.pxb_set_iter_path(0)
+
+
+@pytest.fixture
+def dev_rt():
+    import pyxu_b200.operator as pxo
+    import pyxu_b200.opt.solver as pxs
+    import pyxu_b200.opt.stop as pxst
+
+    with emulated_device(cuda_runtime=True) as lib:
+        yield types.SimpleNamespace(operator=pxo, solver=pxs, stop=pxst, lib=lib)
+
+
+def _tv3d(dev, shape, y, dtype, algo="PD3O", positivity=True, mode="constant", **kw):
+    pxo, pxs = dev.operator, dev.solver
+    N = int(np.prod(shape))
+    f = 0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y)
+    Kop = pxo.Gradient(arg_shape=shape, dtype=dtype, mode=mode)
+    h = 0.08 * pxo.L21Norm(arg_shape=(3, *shape), l2_axis=(0,))
+    g = pxo.PositiveOrthant(dim=N) if positivity else None
+    return getattr(pxs, algo)(f=f, g=g, h=h, K=Kop, show_progress=False, final_writeback=kw.pop("final_writeback", False), **kw)
+
+
+@pytest.mark.parametrize("case", ["maxiter", "maxiter_or_relerr", "relerr_fires_inside_the_epoch", "longer_than_one_epoch", "cv", "ragged_tail",
+                                  "modes_fold", "modes_edge", "modes_ring", "declined"])
+def test_streamed_fit_equals_the_ordinary_fit(dev_rt, case, monkeypatch):
+    """fit(x0=<large host array>) on one GPU queues the first iterations as a wavefront over z-chunks behind the chunked upload
+    (SlabTV.run_streamed): same iterate, same history, same stopping iteration as the one-upload, one-iteration-at-a-time loop."""
+    dev = dev_rt
+    pxst, PDS = dev.stop, dev.solver.PD3O.__mro__[1]
+    dtype = np.float32
+    shape = {"ragged_tail": (13, 8, 16), "declined": (12, 8, 14)}.get(case, (12, 8, 16))  # 14 columns: outside the single-kernel envelope in fp32
+    y = (np.random.default_rng(3).random(int(np.prod(shape))) - 0.2).astype(dtype)
+    algo = "CondatVu" if case == "cv" else "PD3O"
+    crits = {
+        "maxiter": lambda: pxst.MaxIter(7),
+        "maxiter_or_relerr": lambda: pxst.MaxIter(7) | pxst.RelError(eps=1e-30, var="x"),
+        "relerr_fires_inside_the_epoch": lambda: pxst.MaxIter(40) | (pxst.RelError(eps=2e-2, var="x") & pxst.RelError(eps=2e-2, var="z")),
+        "longer_than_one_epoch": lambda: pxst.MaxIter(9) | pxst.RelError(eps=1e-30, var="z"),
+        "cv": lambda: pxst.MaxIter(6) | pxst.RelError(eps=1e-30, var="x"),
+        "ragged_tail": lambda: pxst.MaxIter(5),
+    }
+    mode = {"modes_fold": ("constant", "symmetric", "wrap"), "modes_edge": ("constant", "edge", "symmetric"), "modes_ring": ("constant", "reflect", "edge")}.get(case, "constant")
+    if case.startswith("modes") or case == "declined":
+        crits[case] = lambda: pxst.MaxIter(6) | pxst.RelError(eps=1e-30, var="x")
+    monkeypatch.setattr(PDS, "_STREAM_MIN_BYTES", 1 << 62)
+    ref = _tv3d(dev, shape, y, dtype, algo, mode=mode)
+    ref.fit(x0=y.copy(), stop_crit=crits[case]())
+    assert ref._astate.get("error") is None and ref._slab is None
+    x_ref, (dref, href) = ref.solution(), ref.stats()
+    monkeypatch.setattr(PDS, "_STREAM_MIN_BYTES", 1)
+    monkeypatch.setattr(PDS, "_STREAM_PLANES", 2)
+    monkeypatch.setattr(PDS, "_STREAM_EPOCH", 4 if case == "longer_than_one_epoch" else 32)
+    calls = []
+    from pyxu_b200 import slab
+
+    real = slab.SlabTV.run_streamed
+    monkeypatch.setattr(slab.SlabTV, "run_streamed", lambda self, *a, **k: (calls.append(a[2]), real(self, *a, **k))[1])
+    slv = _tv3d(dev, shape, y, dtype, algo, mode=mode)
+    slv.fit(x0=y.copy(), stop_crit=crits[case]())
+    assert slv._astate.get("error") is None, slv._astate.get("error")
+    assert slv._slab is not None and len(calls) >= 1
+    x, (d, hist) = slv.solution(), slv.stats()
+    assert isinstance(x, np.ndarray) and x.dtype == dtype
+    assert len(hist) == len(href) and (hist["iteration"] == href["iteration"]).all()
+    if case == "relerr_fires_inside_the_epoch":
+        assert 2 < len(hist) - 1 < 32 and calls == [32, len(hist) - 1]  # speculated 32 iterations, redone up to the stopping one
+    elif case == "longer_than_one_epoch":
+        assert calls == [4] and len(hist) == 10
+    elif case == "declined":
+        assert slv._slab.fused is False and "pds_dual" in dev.lib.log
+    for name in href.dtype.names[1:]:
+        assert np.allclose(hist[name], href[name], rtol=1e-5, atol=1e-12), name
+    # (z: the same kernels on the same numbers; x: written by the wave's last iteration here, rebuilt from the previous pair by the
+    # two-sweep primal kernel when no criterion reads it -- the same formula, contracted differently)
+    assert np.allclose(x, x_ref, rtol=2e-6, atol=1e-7)
+    assert np.array_equal(d["z"], dref["z"])
+    assert sum("Iteration" in ln for ln in open(slv.logfile)) == sum("Iteration" in ln for ln in open(ref.logfile))
+
+
+def test_streamed_fit_is_declined_outside_its_envelope(dev_rt, monkeypatch):
+    """A boundary mode that folds along axis 0, a device-resident x0, MANUAL mode, objective tracking: the ordinary path."""
+    import torch
+
+    from pyxu_b200.abc.solver import Mode
+
+    dev = dev_rt
+    pxst, PDS = dev.stop, dev.solver.PD3O.__mro__[1]
+    monkeypatch.setattr(PDS, "_STREAM_MIN_BYTES", 1)
+    monkeypatch.setattr(PDS, "_STREAM_PLANES", 2)
+    shape, dtype = (12, 8, 16), np.float32
+    y = np.random.default_rng(3).random(int(np.prod(shape))).astype(dtype)
+    for kw, fit_kw, x0 in ((dict(mode=("reflect", "constant", "constant")), {}, y.copy()), ({}, {}, torch.from_numpy(y.copy())),
+                           ({}, dict(mode=Mode.MANUAL), y.copy()), ({}, dict(track_objective=True), y.copy())):
+        slv = _tv3d(dev, shape, y, dtype, **kw)
+        slv.fit(x0=x0, stop_crit=pxst.MaxIter(3), **fit_kw)
+        assert slv._astate.get("error") is None and slv._slab is None and slv._plan.kind == "fused"
+
+
+def test_streamed_fit_brings_the_result_back_behind_the_wave(dev_rt, monkeypatch):
+    """With a reserved pinned result buffer the last iteration's x is copied out chunk by chunk inside fit(); solution() hands that
+    buffer out (once), stats() / a second solution() read the device."""
+    import pyxu_b200
+    from pyxu_b200 import _array as A_
+
+    dev = dev_rt
+    pxst, PDS = dev.stop, dev.solver.PD3O.__mro__[1]
+    shape, dtype = (12, 8, 16), np.float64
+    y = np.random.default_rng(5).random(int(np.prod(shape)))
+    monkeypatch.setattr(PDS, "_STREAM_MIN_BYTES", 1 << 62)
+    ref = _tv3d(dev, shape, y, dtype)
+    ref.fit(x0=y.copy(), stop_crit=pxst.MaxIter(5))
+    x_ref = ref.solution()
+    monkeypatch.setattr(PDS, "_STREAM_MIN_BYTES", 1)
+    monkeypatch.setattr(PDS, "_STREAM_PLANES", 4)
+    import torch
+
+    monkeypatch.setattr(A_, "reserve_host_results", lambda n, count=1: A_._RESULT_POOL.setdefault(int(n), []).extend(
+        torch.empty(int(n), dtype=torch.uint8) for _ in range(count)))
+    A_.reserve_host_results(y.nbytes)
+    try:
+        slv = _tv3d(dev, shape, y, dtype, final_writeback=True)
+        slv.fit(x0=y.copy(), stop_crit=pxst.MaxIter(5))
+        assert slv._astate.get("error") is None, slv._astate.get("error")
+        assert slv._stream_out is not None and not A_._RESULT_POOL[y.nbytes]  # taken; the final writeback did not consume it
+        x = slv.solution()
+        assert slv._stream_out is None and np.allclose(x, x_ref, rtol=1e-13, atol=1e-15)
+        assert np.array_equal(slv.solution(), x)  # second call: from the device
+        assert np.array_equal(np.load(slv.datafile)["x"], x)
+        del x
+        import gc
+
+        gc.collect()
+        assert len(A_._RESULT_POOL[y.nbytes]) == 1  # the buffer is back in the pool
+    finally:
+        A_.release_host_results()

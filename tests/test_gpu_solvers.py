@@ -330,3 +330,77 @@ def test_fast_kernels_equal_generic_kernels_on_device(px):
         tol = 1e-12 if dt == torch.float64 else 2e-5
         for a, b in zip(res[0], res[1]):
             assert float((a - b).norm() / b.norm()) < tol, (shape, mode, dt)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_streamed_fit_against_reference_fixtures(px, pinned, monkeypatch):
+    """fit(x0=<host array>) with the first iterations queued as a wavefront over z-chunks behind the chunked upload
+    (SlabTV.run_streamed; on by default for host arrays >= 256 MiB, forced here on the 32x12x16 fixtures of the real reference):
+    MaxIter run, the reference's default criterion (same iteration count), in-plane folding modes, CondatVu; pageable and pinned
+    host memory; the result copied back behind the wave into a reserved pinned buffer."""
+    from pyxu_b200 import _array as A_
+
+    PDS = px.solver.PD3O.__mro__[1]
+    monkeypatch.setattr(PDS, "_STREAM_MIN_BYTES", 1)
+    monkeypatch.setattr(PDS, "_STREAM_PLANES", 4)
+    gs = golden("slabs.npz")
+    shape = (32, 12, 16)
+    y = gs["y"]
+
+    def host(a):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        if not pinned:
+            return a.copy()
+        t = torch.empty(a.size, dtype=torch.float64, pin_memory=True)
+        t.copy_(torch.from_numpy(a))
+        return t.numpy()
+
+    def build(lam, **kw):
+        pxo = px.operator
+        N = y.size
+        f = 0.5 * pxo.SquaredL2Norm(dim=N).argshift(host(-y))
+        Kop = pxo.Gradient(arg_shape=shape, mode=kw.pop("mode", "constant"))
+        h = lam * pxo.L21Norm(arg_shape=(3, *shape), l2_axis=(0,))
+        g = pxo.PositiveOrthant(dim=N) if kw.pop("positivity", True) else None
+        return getattr(px.solver, kw.pop("solver", "PD3O"))(f=f, g=g, h=h, K=Kop, show_progress=False)
+
+    A_.reserve_host_results(y.nbytes)
+    try:
+        slv = build(0.08)
+        slv.fit(x0=host(y), stop_crit=px.stop.MaxIter(25), rho=1.2)
+        assert slv._slab is not None and slv._slab.fused and slv._stream_out is not None
+        check(slv, gs, "pd3o_tv3d")
+        slv = build(0.3)
+        slv.fit(x0=host(y))  # default criterion: fires inside the first epoch -> redone up to the stopping iteration
+        assert slv._slab is not None
+        check(slv, gs, "pd3o_tv3d/default_stop", tol=1e-9)
+        slv = build(0.08, solver="CondatVu", positivity=False)
+        slv.fit(x0=host(np.zeros(y.size)), stop_crit=px.stop.MaxIter(25))
+        assert slv._slab is not None
+        check(slv, gs, "cv_tv3d")
+    finally:
+        A_.release_host_results()
+
+
+def test_streamed_fit_equals_the_ordinary_fit_fp32(px, monkeypatch):
+    """128 x 64 x 128 fp32, 16-plane chunks (the default), in-plane folding modes: streamed and ordinary fit agree."""
+    PDS = px.solver.PD3O.__mro__[1]
+    shape = (128, 64, 128)
+    N = int(np.prod(shape))
+    y = (np.random.default_rng(11).random(N) - 0.2).astype(np.float32)
+    res = {}
+    for name, floor in (("ordinary", 1 << 62), ("streamed", 1)):
+        monkeypatch.setattr(PDS, "_STREAM_MIN_BYTES", floor)
+        pxo = px.operator
+        f = 0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y)
+        Kop = pxo.Gradient(arg_shape=shape, dtype=np.float32, mode=("constant", "reflect", "wrap"))
+        h = 0.08 * pxo.L21Norm(arg_shape=(3, *shape), l2_axis=(0,))
+        slv = px.solver.PD3O(f=f, g=pxo.PositiveOrthant(dim=N), h=h, K=Kop, show_progress=False)
+        slv.fit(x0=y.copy(), stop_crit=px.stop.MaxIter(40) | px.stop.RelError(eps=1e-30, var="x"))
+        assert slv._astate.get("error") is None, slv._astate.get("error")
+        assert (slv._slab is not None) == (name == "streamed")
+        res[name] = slv.stats()
+    (da, ha), (db, hb) = res["ordinary"], res["streamed"]
+    assert len(ha) == len(hb) == 41
+    assert np.array_equal(da["z"], db["z"]) and np.allclose(da["x"], db["x"], rtol=2e-6, atol=1e-7)
+    assert np.allclose(ha["RelError[x]"], hb["RelError[x]"], rtol=1e-5)
