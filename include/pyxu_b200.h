@@ -235,6 +235,10 @@ typedef struct pxb_stencil3d {
     pxb_slab slab;
 } pxb_stencil3d;
 int pxb_stencil3d_apply(const pxb_stencil3d* d, const void* in, void* out, void* stream);
+/* Which kernel serves pxb_stencil3d_apply: 0 = automatic (K x K x K taps, K in {3, 5, 7, 9}, centred along the rows and a dense or
+ * absent epilogue operand: the fully unrolled instances; anything else: the general marching kernel), 1 = the general kernel
+ * always.  No reference counterpart: for A/B measurements and tests. */
+int pxb_set_stencil3d_path(int path);
 
 /* One accelerated proximal-gradient (FISTA) iteration on f = alpha_f*||A x + shift||^2, g pointwise, A such a stencil
  * (reference: src/pyxu/opt/solver/pgd.py:173-191), as TWO tiled passes instead of five:

@@ -197,6 +197,7 @@ PROTOTYPES = {
     "pxb_pds_iter_chunked": (_i, [_i, _P(GradDesc), _P(PdsParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pxb_set_iter_path": (_i, [_i]),
     "pxb_set_iter_modes": (_i, [_i]),
+    "pxb_set_stencil3d_path": (_i, [_i]),
     "pxb_sqnorms": (_i, [_i, _i64, _i64, _vp, _vp, _vp, _vp]),
 }
 

@@ -3,7 +3,11 @@
 #include "pxb_tma_util.cuh"
 #include "pxb_stencil3d.cuh"
 
+int pxb_st3_fast_try(int dtype, const PxbSt3P& g, const void* in, void* out, cudaStream_t s, cudaError_t* err);  // pxb_stencil3d_fast.cu
+
 namespace {
+
+int g_st3_path = 0;  // pxb_set_stencil3d_path: 0 = the K x K x K instances where they apply, 1 = k_stencil3d always
 
 template <class T, int VEC, int NV, int K0>
 __global__ void __launch_bounds__(256) k_stencil3d(const __grid_constant__ PxbSt3P p, const __grid_constant__ CUtensorMap map, T* __restrict__ out) {
@@ -111,6 +115,7 @@ template <class T>
 int run(PxbSt3P& p, const void* in, void* out, cudaStream_t s, cudaError_t* err) {
     constexpr int VEC = 16 / (int)sizeof(T);
     if (int why = pxb_st3_setup<T, VEC>(p)) return why;
+    if (g_st3_path == 0 && pxb_st3_fast_try(sizeof(T) == 4 ? PXB_F32 : PXB_F64, p, in, out, s, err) == 0) return 0;
     const int64_t s0 = (int64_t)p.s.n1 * p.s.n2;
     const uint64_t dim[4] = {(uint64_t)p.s.n2, (uint64_t)p.s.n1, (uint64_t)(p.n0 + p.lo_planes + p.hi_planes), (uint64_t)p.batch};
     const uint64_t stride[4] = {1, (uint64_t)p.s.n2, (uint64_t)s0, (uint64_t)p.vol};
@@ -135,6 +140,12 @@ int run(PxbSt3P& p, const void* in, void* out, cudaStream_t s, cudaError_t* err)
 }
 
 }  // namespace
+
+extern "C" int pxb_set_stencil3d_path(int path) {
+    if (path < 0 || path > 1) return pxb_fail(PXB_EINVAL, "pxb_set_stencil3d_path: 0 (auto) or 1 (generic kernel)");
+    g_st3_path = path;
+    return 0;
+}
 
 extern "C" int pxb_stencil3d_apply(const pxb_stencil3d* d, const void* in, void* out, void* stream) {
     const char* who = "pxb_stencil3d_apply";

@@ -63,6 +63,9 @@ class EmuLib:
         self.path = p
         return 0
 
+    def pxb_set_stencil3d_path(self, p):
+        return 0 if p in (0, 1) else EINVAL  # (the emulation runs the general kernel's bodies either way)
+
     def pxb_set_iter_modes(self, on):
         if on < -1 or on > 1:
             return EINVAL

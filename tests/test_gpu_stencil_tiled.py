@@ -186,3 +186,37 @@ def test_tiled_stencils_random_geometries():
             den = float(torch.linalg.vector_norm(b.double()))
             err = float(torch.linalg.vector_norm(a.double() - b.double())) / max(den, 1e-30)
             assert err < tol, (trial, shape, ks, cen, adj, err, fast._tiled_ok, fast._tiled3d_ok)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 5e-6)])
+@pytest.mark.parametrize("K", [3, 5, 7, 9])
+def test_single_pass_3d_cubic_instances(dtype, tol, K):
+    """K x K x K PSFs centred along the rows take the fully unrolled instances (k_stencil3d_fast); against the gather kernels and
+    against the general marching kernel (pxb_set_stencil3d_path(1)): apply, adjoint, epilogue operand, ragged tiles, stacks,
+    off-centre taps along axes 0 / 1, chunked volumes."""
+    import pyxu_b200.operator as pxo
+    from pyxu_b200 import _cabi as Kc
+
+    rng = np.random.default_rng(K)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    lib = Kc.lib()
+    for shape, cen in (((70, 45, 264), (K // 2, K // 2, K // 2)), ((150, 16, 128), (K - 1, 0, K // 2)), ((K, 37, 8), (0, K - 1, K // 2))):
+        kern = [rng.standard_normal(K).astype(dtype) for _ in range(3)]
+        fast = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        slow = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        slow._tiled_ok = slow._tiled3d_ok = False
+        x = torch.randn(2, fast.dim, device="cuda", dtype=tdt)
+        y = torch.randn(2, fast.dim, device="cuda", dtype=tdt)
+        for adj in (False, True):
+            n0 = lib.pxb_launch_count()
+            a = fast.adjoint(x) if adj else fast.apply(x)
+            assert fast._tiled3d_ok is True and lib.pxb_launch_count() - n0 == 1, "one marching pass"
+            b = slow.adjoint(x) if adj else slow.apply(x)
+            assert rel(a, b) < tol, (shape, cen, adj, rel(a, b))
+            Kc.check(lib.pxb_set_stencil3d_path(1), "pxb_set_stencil3d_path")
+            try:
+                c = fast.adjoint(x) if adj else fast.apply(x)
+            finally:
+                lib.pxb_set_stencil3d_path(0)
+            assert rel(a, c) < tol, (shape, cen, adj, rel(a, c))
+        assert rel(fast._run_tiled(x, False, alpha=0.5, beta=-1.0, add=y), 0.5 * slow.apply(x) - y) < tol
