@@ -344,6 +344,7 @@ class _PrimalDualSplitting(Solver):
         crit = ast["stop_crit"]
         x0_host, shift_host = self._stream_src
         self._stream_src = None
+        eng.probe = self._probe
         planes = self._STREAM_PLANES
         if not self._pre_step():  # met before the first iteration: upload only, so that solution() / stats() have their arrays
             eng.run_streamed(x0_host, shift_host, 0, planes=planes)
