@@ -124,6 +124,7 @@ class Stencil(pxo.SquareOp):
         self._tiled_ok = None  # TMA-tiled single-pass kernel (pxb_stencil2d_apply): None = not tried yet
         self._tiled3d_ok = None  # single-pass separable 3-D kernel (pxb_stencil3d_apply)
         self._padded_ok = None  # Pad -> tiled stencil / tiled stencil -> Pad^T for folding boundary modes (_run_padded)
+        self._dense3d_ok = None  # dense (full-rank) 3-D kernel as one tiled dense 2-D pass per plane of the kernel (_run_dense3d)
         self._folds = any(m != "constant" for m, p in zip(self._mode, self._pad_width) if p[0] > 0)
         self.lipschitz = self.estimate_lipschitz(__rule=True)
 
@@ -467,11 +468,83 @@ class Stencil(pxo.SquareOp):
         self._padded_ok = True
         return out
 
+    def _run_dense3d(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
+        """A dense 3-D kernel of full rank ('constant' boundaries; e.g. a measured 7x7x7 PSF -- the reference takes any dense kernel,
+        stencil.py:356-461) as K0 passes of the TILED dense 2-D kernel, one per plane of the kernel, accumulated in place through the
+        kernel's epilogue operand:
+            out[z]  =  alpha * sum_a  S2D_{k[a]}( in[z + a - c0] )  +  beta * add[z]          (planes outside the volume are zero)
+        The pass of the centre plane (a = c0) covers every output plane and writes `out` (epilogue operand `add`); the other passes
+        cover the planes whose source plane exists and add onto `out`.  12 B/voxel per pass against the per-sample gather of
+        pxb_stencil_apply (L1-bound: one load per tap and sample).  None when it does not apply."""
+        if self._dense3d_ok is False:
+            return None
+        passes = self._passes(False)
+        ok = (not self._folds and len(passes) == 1 and len(self._arg_shape) == 3 and all(n > 1 for n in passes[0][0].shape)
+              and all(m == "constant" for m in self._mode) and arr.is_contiguous())
+        if ok:
+            k3, c3 = passes[0]
+            vec = 16 // arr.element_size()
+            ok = k3.shape[1] <= 16 and k3.shape[2] <= (13 if vec == 4 else 11) and self._arg_shape[2] % vec == 0 and self._rank1_split(k3, c3) is None
+        if not ok:
+            self._dense3d_ok = False
+            return None
+        if adjoint:  # zero-padded correlation: transpose = correlation with the reversed kernel, mirrored centre
+            k3, c3 = np.ascontiguousarray(np.flip(k3)), np.array(k3.shape) - c3 - 1
+        n0, n1, n2 = self._arg_shape
+        plane = n1 * n2
+        batch = max(1, arr.numel() // self.dim)
+        key = ("dense3d", adjoint, arr.dtype, arr.device)
+        coef = self._dev_coef.get(key)
+        if coef is None:
+            coef, _ = A.asdevice(np.ascontiguousarray(k3.reshape(-1)), dtype=arr.dtype)
+            self._dev_coef[key] = coef
+        es, k12 = arr.element_size(), int(k3.shape[1] * k3.shape[2])
+        out = A.empty_like(arr)
+        src, dst = arr.reshape(batch, n0 * plane), out.reshape(batch, n0 * plane)
+        addf = add.reshape(-1) if add is not None else None
+        c0 = int(c3[0])
+        for a in [c0] + [a for a in range(k3.shape[0]) if a != c0]:
+            sft = a - c0
+            z_lo, z_hi = max(0, -sft), min(n0, n0 - sft)
+            if z_hi <= z_lo:
+                continue
+            for b in range(batch):
+                d = K.Stencil2D()
+                d.dtype, d.nimg, d.dense = A.dcode(arr), z_hi - z_lo, 1
+                d.shape[0], d.shape[1] = n1, n2
+                d.ksize[0], d.ksize[1], d.center[0], d.center[1] = k3.shape[1], k3.shape[2], int(c3[1]), int(c3[2])
+                d.coef = coef.data_ptr() + es * a * k12
+                pin = C.c_void_p(src[b].data_ptr() + es * (z_lo + sft) * plane)
+                pout = C.c_void_p(dst[b].data_ptr() + es * z_lo * plane)
+                if a == c0:
+                    d.alpha, d.beta = float(alpha), float(beta)
+                    if addf is not None:  # out[i] = ... + beta * add[i % period]: the operand of this batch item, rotated to its first sample
+                        per = addf.numel()
+                        if per % (n0 * plane) == 0:
+                            d.add, d.add_period = addf.data_ptr() + es * ((b * n0 * plane) % per), n0 * plane
+                        else:
+                            self._dense3d_ok = False
+                            return None
+                else:
+                    d.alpha, d.beta = float(alpha), 1.0
+                    d.add, d.add_period = pout.value, (z_hi - z_lo) * plane
+                rc = K.lib().pxb_stencil2d_apply(C.byref(d), pin, pout, A.stream())
+                if rc == -3:
+                    self._dense3d_ok = False
+                    return None
+                K.check(rc, "pxb_stencil2d_apply")
+        self._dense3d_ok = True
+        return out
+
     def _run_tiled(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
         """One pass over HBM for the in-plane part (+ one streaming pass when there is a factor along axis 0 that the
         single-pass 3-D kernel does not take).  Returns None when the tiled kernels do not apply."""
         if PADDED_TILED and self._folds:
             return self._run_padded(arr, adjoint, alpha, beta, add)
+        if self._dense3d_ok is not False:
+            out = self._run_dense3d(arr, adjoint, alpha, beta, add)
+            if out is not None:
+                return out
         batch = max(1, arr.numel() // self.dim)
         if self._tiled3d_ok is not False:
             d3 = self._desc3d(A.dcode(arr), adjoint, batch, alpha, beta, add)

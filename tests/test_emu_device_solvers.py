@@ -385,3 +385,46 @@ def test_streamed_fit_brings_the_result_back_behind_the_wave(dev_rt, monkeypatch
         assert len(A_._RESULT_POOL[y.nbytes]) == 1  # the buffer is back in the pool
     finally:
         A_.release_host_results()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_dense_3d_kernel_of_full_rank_runs_as_tiled_passes_per_kernel_plane(dev, dtype):
+    """Stencil with a dense 3-D kernel that is not an outer product ('constant' boundaries): one tiled dense 2-D pass per plane of
+    the kernel, accumulated in place (Stencil._run_dense3d) -- apply, adjoint, stacks, epilogue operand -- against the gather kernels
+    and against the NumPy oracle's correlation."""
+    import torch
+
+    import test_gpu_operators as GO
+    from oracle import pyxu_oracle as orc
+
+    pxo = dev.operator
+    rng = np.random.default_rng(2)
+    tol = 1e-12 if dtype == np.float64 else 2e-5
+    for shape, ks, cen in (((9, 20, 24), (3, 3, 3), (1, 1, 1)), ((7, 12, 16), (5, 3, 4), (0, 2, 3)), ((4, 10, 8), (7, 2, 3), (6, 0, 1))):
+        kern = rng.standard_normal(ks).astype(dtype)
+        fast = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        slow = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        slow._dense3d_ok = False
+        x = torch.from_numpy(rng.standard_normal((2, fast.dim)).astype(dtype))
+        y = torch.from_numpy(rng.standard_normal(fast.dim).astype(dtype))
+        for adj in (False, True):
+            dev.lib.log.clear()
+            a = fast.adjoint(x) if adj else fast.apply(x)
+            c0 = ks[0] - 1 - cen[0] if adj else cen[0]
+            live = sum(1 for a in range(ks[0]) if max(0, c0 - a) < min(shape[0], shape[0] - (a - c0)))  # kernel planes whose source plane exists
+            assert fast._dense3d_ok is True and dev.lib.log.count("stencil2d") == 2 * live and "stencil" not in dev.lib.log
+            b = slow.adjoint(x) if adj else slow.apply(x)
+            assert slow._dense3d_ok is False
+            assert GO.relerr(a.numpy(), b.numpy()) < tol, (shape, ks, adj)
+        oref = orc.Stencil(shape, kern.astype(np.float64), cen, "constant")
+        ref = oref.apply(x.numpy().astype(np.float64))
+        assert GO.relerr(fast.apply(x).numpy(), ref) < tol and GO.relerr(fast.adjoint(x).numpy(), oref.adjoint(x.numpy().astype(np.float64))) < tol
+        got = fast._run_tiled(x, False, alpha=0.5, beta=-1.0, add=y)
+        assert GO.relerr(got.numpy(), 0.5 * ref - y.numpy()) < tol
+    # an outer product keeps the separable single pass; a folding mode keeps the gather kernels
+    sep = pxo.Stencil(arg_shape=(9, 20, 24), kernel=np.ones((3, 3, 3), dtype=dtype), center=(1, 1, 1), mode="constant")
+    sep.apply(torch.zeros(sep.dim, dtype=torch.float64 if dtype == np.float64 else torch.float32))
+    assert sep._dense3d_ok is False and sep._tiled3d_ok is True
+    fold = pxo.Stencil(arg_shape=(9, 20, 24), kernel=rng.standard_normal((3, 3, 3)).astype(dtype), center=(1, 1, 1), mode="reflect")
+    fold.apply(torch.zeros(fold.dim, dtype=torch.float64 if dtype == np.float64 else torch.float32))
+    assert fold._dense3d_ok in (None, False) and fold._tiled_ok is not True

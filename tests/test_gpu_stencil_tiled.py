@@ -220,3 +220,31 @@ def test_single_pass_3d_cubic_instances(dtype, tol, K):
                 lib.pxb_set_stencil3d_path(0)
             assert rel(a, c) < tol, (shape, cen, adj, rel(a, c))
         assert rel(fast._run_tiled(x, False, alpha=0.5, beta=-1.0, add=y), 0.5 * slow.apply(x) - y) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 1e-5)])
+def test_dense_3d_kernel_of_full_rank(dtype, tol):
+    """A dense 3-D PSF that is not an outer product ('constant' boundaries) runs as one tiled dense 2-D pass per plane of the kernel,
+    accumulated in place through the epilogue operand (Stencil._run_dense3d), instead of the per-sample gather kernel."""
+    import pyxu_b200.operator as pxo
+    from pyxu_b200 import _cabi as Kc
+
+    rng = np.random.default_rng(5)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    lib = Kc.lib()
+    for shape, ks, cen in (((40, 45, 264), (7, 7, 7), (3, 3, 3)), ((9, 37, 64), (5, 3, 4), (0, 2, 3)), ((4, 50, 8), (7, 2, 3), (6, 0, 1))):
+        kern = rng.standard_normal(ks).astype(dtype)
+        fast = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        slow = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        slow._dense3d_ok = False
+        x = torch.randn(2, fast.dim, device="cuda", dtype=tdt)
+        y = torch.randn(fast.dim, device="cuda", dtype=tdt)
+        for adj in (False, True):
+            a = fast.adjoint(x) if adj else fast.apply(x)
+            assert fast._dense3d_ok is True
+            b = slow.adjoint(x) if adj else slow.apply(x)
+            assert slow._dense3d_ok is False and rel(a, b) < tol, (shape, ks, adj, rel(a, b))
+        assert rel(fast._run_tiled(x, False, alpha=0.5, beta=-1.0, add=y), 0.5 * slow.apply(x) - y) < tol
+        z = torch.randn(2, fast.dim, device="cuda", dtype=tdt)
+        lhs, rhs = torch.sum(fast.apply(x).double() * z.double()), torch.sum(x.double() * fast.adjoint(z).double())
+        assert abs(float(lhs - rhs)) < (1e-10 if dtype == np.float64 else 2e-4) * (1 + abs(float(lhs)))
