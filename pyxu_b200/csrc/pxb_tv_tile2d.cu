@@ -6,7 +6,7 @@
 namespace {
 
 template <class T, int VEC, int ALGO, bool NORMS, class S, bool MODES = false>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
     k_tv_tile2d(const __grid_constant__ PxbTvP<T> q, const __grid_constant__ PxbT2Geom g, const __grid_constant__ PxbIterPtr<T> a,
                 const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_zr,
                 const __grid_constant__ CUtensorMap map_zc) {

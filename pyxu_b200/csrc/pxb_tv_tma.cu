@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(32 * TY, 2)
     pxb_tma_prologue<T, VEC, TY, MODES, ALGO == PXB_PD3O && NORMS>(q, g, it, a, tid, R.mlo, th);
 
     const int lag = S::SCHEME == PXB_SCHEME_FWD ? 1 : R.lag;
+    const PxbTmaFold fb = MODES ? pxb_tma_fold_setup<T, VEC, TY>(q, g, it) : PxbTmaFold{};
     int s = 0;            // stage of plane m, and the parity of its mbarrier phase
     uint32_t par = 0;
     for (int m = R.mlo; m < R.mhi; ++m) {
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(32 * TY, 2)
             mbar_wait(full + s1, s1 == 0 ? par ^ 1u : par);
             st_next = stages + s1 * C::STAGE;
         }
-        pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring, th);
+        pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring, th, fb);
         __syncthreads();  // w(m) complete; every thread is done with stage s
         if (tid == 0 && m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
         const int mm = m - lag;

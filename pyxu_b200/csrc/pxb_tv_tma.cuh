@@ -98,6 +98,83 @@ inline int pxb_tma_pick_spec(const PxbTvCoef& cf, const PxbTvP<T>& q, const PxbT
     return 0;
 }
 
+// MODES: where the sources of the in-plane fold terms of K^T z (pxb_tv_fold_kz) sit in a work item's staged boxes.  For reflect /
+// symmetric / edge the target sample (n-2 or n-1, resp. 1 or 0) and its source (n-1, resp. 0) lie in the same edge tile, so the term
+// comes out of shared memory; PXB_NOSRC = not in the boxes ('wrap': the other end of the line) -> global memory.  `any_rc`: the tile
+// (with its rim) holds an in-plane fold target at all -- interior tiles skip the fold code with one uniform test per plane.
+// (ncu on 512^3 'reflect': the scalar global load of z[n-1] by the rim-column threads sat in the per-plane critical path -- barrier
+//  stalls 3x those of the 'constant' instance, DRAM throughput 58 % against 81 %.)
+struct PxbTmaFold {
+    int any_rc;
+    int bc_hi2, bc_lo2;  // column in the boxes of z2[.., n2-1] / z2[.., 0]
+    int br_hi1, br_lo1;  // row in the z1 box of z1[n1-1, ..] / z1[0, ..]
+};
+template <class T, int VEC, int TY>
+PXB_HD PxbTmaFold pxb_tma_fold_setup(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterItem& it) {
+    using C = PxbTmaCfg<T, VEC, TY>;
+    PxbTmaFold f;
+    auto hit = [](int t, int lo, int hi) { return t != PXB_NOSRC && t >= lo && t <= hi; };
+    f.any_rc = (hit(q.fold_hi[1], it.r0 - 1, it.r0 + TY) || hit(q.fold_lo[1], it.r0 - 1, it.r0 + TY) || hit(q.fold_hi[2], it.c0 - 1, it.c0 + C::T2) ||
+                hit(q.fold_lo[2], it.c0 - 1, it.c0 + C::T2)) ? 1 : 0;
+    auto pos = [](int src, int start, int extent) { const int b = src - start; return (b >= 0 && b < extent) ? b : PXB_NOSRC; };
+    f.bc_hi2 = pos(g.nC - 1, it.c0 - VEC, C::BW);
+    f.bc_lo2 = pos(0, it.c0 - VEC, C::BW);
+    f.br_hi1 = pos(g.nR - 1, it.r0 - 2, C::BR1);
+    f.br_lo1 = pos(0, it.r0 - 2, C::BR1);
+    return f;
+}
+// pxb_tv_fold_kz for W samples at box position (row br, column bc) = sample (f0, f1, f2): same terms, the in-plane ones out of the
+// staged boxes where `fb` says they are there.
+template <class T, int VEC, int TY, int W, bool LO>
+PXB_HD void pxb_tma_fold_kz(const PxbTvP<T>& q, const PxbTmaFold& fb, const T* __restrict__ st, const T* __restrict__ zimg, int br, int bc, int f0, int f1,
+                            int f2, T* kz) {
+    using C = PxbTmaCfg<T, VEC, TY>;
+    {   // along the row (component 2)
+        const int th = q.fold_hi[2], tl = LO ? q.fold_lo[2] : PXB_NOSRC;
+        const bool hi = th >= f2 && th < f2 + W, lo = LO && tl >= f2 && tl < f2 + W;
+        if (hi || lo) {
+            const T* __restrict__ row = zimg + 2 * q.vol + (int64_t)f0 * q.s0 + (int64_t)f1 * q.s1;
+            if (hi) {
+                const T zf = fb.bc_hi2 != PXB_NOSRC ? st[C::OFF_Z2 + br * C::BW + fb.bc_hi2] : row[q.n2 - 1];
+                for (int j = 0; j < W; ++j)
+                    if (f2 + j == th) kz[j] += q.cp[2] * zf;
+            }
+            if (lo) {
+                const T zf = fb.bc_lo2 != PXB_NOSRC ? st[C::OFF_Z2 + br * C::BW + fb.bc_lo2] : row[0];
+                for (int j = 0; j < W; ++j)
+                    if (f2 + j == tl) kz[j] += q.cm[2] * zf;
+            }
+        }
+    }
+    {   // along the rows (component 1; its box starts one row earlier)
+        const bool hi = f1 == q.fold_hi[1], lo = LO && f1 == q.fold_lo[1];
+        if (hi) {
+            const PxbVec<T, W> f = fb.br_hi1 != PXB_NOSRC ? pxb_vload<T, W>(st + C::OFF_Z1 + fb.br_hi1 * C::BW + bc)
+                                                          : pxb_vload<T, W>(zimg + q.vol + (int64_t)f0 * q.s0 + (int64_t)(q.n1 - 1) * q.s1 + f2);
+            for (int j = 0; j < W; ++j) kz[j] += q.cp[1] * f.v[j];
+        }
+        if (lo) {
+            const PxbVec<T, W> f = fb.br_lo1 != PXB_NOSRC ? pxb_vload<T, W>(st + C::OFF_Z1 + fb.br_lo1 * C::BW + bc)
+                                                          : pxb_vload<T, W>(zimg + q.vol + (int64_t)f0 * q.s0 + f2);
+            for (int j = 0; j < W; ++j) kz[j] += q.cm[1] * f.v[j];
+        }
+    }
+    {   // along the planes (component 0): two planes of the volume, from global memory
+        const bool hi = f0 == q.fold_hi[0], lo = LO && f0 == q.fold_lo[0];
+        if (hi || lo) {
+            const T* __restrict__ line = zimg + (int64_t)f1 * q.s1 + f2;
+            if (hi) {
+                const PxbVec<T, W> f = pxb_vload<T, W>(line + (int64_t)(q.n0 - 1) * q.s0);
+                for (int j = 0; j < W; ++j) kz[j] += q.cp[0] * f.v[j];
+            }
+            if (lo) {
+                const PxbVec<T, W> f = pxb_vload<T, W>(line);
+                for (int j = 0; j < W; ++j) kz[j] += q.cm[0] * f.v[j];
+            }
+        }
+    }
+}
+
 template <class T, int VEC>
 struct PxbTmaThread {
     T zc[3][VEC];     // z_in at this thread's own samples, plane just visited
@@ -116,7 +193,7 @@ struct PxbTmaThread {
 template <class T, int VEC, int TY, int W, int ALGO, class S, bool MODES = false>
 PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restrict__ st, const T* __restrict__ st_next, int br, int bc,
                       const T* z0p, T* wv, T* z0c, T* z1c, T* z2c, T* xo, T* un, T* uold, const T* __restrict__ fold = nullptr, int f0 = 0,
-                      int f1 = 0, int f2 = 0) {
+                      int f1 = 0, int f2 = 0, const PxbTmaFold* fb = nullptr) {
     using C = PxbTmaCfg<T, VEC, TY>;
     const int i = br * C::BW + bc, i1 = (br + 1) * C::BW + bc;
     T kz[W];
@@ -155,7 +232,7 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
             if (pxb_has_cp<S>(q, 2)) kz[j] += q.cp[2] * (j > 0 ? c.v[j > 0 ? j - 1 : 0] : lo);
         }
     }
-    if (MODES && fold) pxb_tv_fold_kz<T, W, 3, S::SCHEME != PXB_SCHEME_FWD>(q, fold, f0, f1, f2, kz);
+    if (MODES && fold) pxb_tma_fold_kz<T, VEC, TY, W, S::SCHEME != PXB_SCHEME_FWD>(q, *fb, st, fold, br, bc, f0, f1, f2, kz);
     const PxbVec<T, W> old = pxb_vload<T, W>(st + C::OFF_U + i);
     PxbVec<T, W> sh;
     for (int j = 0; j < W; ++j) sh.v[j] = T(0);
@@ -229,10 +306,13 @@ PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const Pxb
 // boundary map folds them onto (pxb_tv_w_outside), which K w then reads as the padded array.
 template <class T, int VEC, int TY, int ALGO, bool NORMS, class S = PxbSpecAny, bool MODES = false>
 PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTmaGeom& tg, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid,
-                           int m, const T* __restrict__ st, const T* __restrict__ st_next, T* ring, PxbTmaThread<T, VEC>& th) {
+                           int m, const T* __restrict__ st, const T* __restrict__ st_next, T* ring, PxbTmaThread<T, VEC>& th,
+                           const PxbTmaFold& fb = PxbTmaFold{}) {
     using C = PxbTmaCfg<T, VEC, TY>;
     using R = typename C::Ring;
     T* __restrict__ slot = ring + (m & 3) * R::SLOT;
+    // MODES: the image's z for the fold terms of K^T z, or null when neither this tile nor this plane holds a fold target
+    const T* __restrict__ zfold = (MODES && (fb.any_rc || m == q.fold_hi[0] || m == q.fold_lo[0])) ? a.z_in + it.b * 3 * g.vol : nullptr;
     const bool plane_in = (m >= 0 || g.open_lo) && (m < g.nM || g.open_hi);
     const bool own = m >= it.m0 && m < it.m1;
     const int rl = tid / C::TXL, cl = (tid - rl * C::TXL) * VEC;
@@ -240,9 +320,8 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         const int r = it.r0 + rl, c = it.c0 + cl;
         const bool in = plane_in && r < g.nR && c < g.nC;
         T wv[VEC], z0c[VEC], xo[VEC], un[VEC], uo[VEC];
-        const T* __restrict__ zimg = a.z_in + it.b * 3 * g.vol;
         pxb_tma_w<T, VEC, TY, VEC, ALGO, S, MODES>(q, tg, st, st_next, rl + 1, cl + VEC, th.z0p, wv, z0c, th.zc[1], th.zc[2], xo, un, uo,
-                                                   in ? zimg : nullptr, m, r, c);
+                                                   in ? zfold : nullptr, m, r, c, &fb);
         for (int j = 0; j < VEC; ++j) { th.zc[0][j] = z0c[j]; th.z0p[j] = z0c[j]; }
         // (on the planes of neighbouring chunks / slabs only the tile's own, in-plane-inside cells are read)
         const bool fold = MODES && !in && (own || !plane_in);
@@ -307,7 +386,7 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             if (MODES) {
                 const bool ev = rs != PXB_NOSRC && c < g.nC;
                 if (ev) pxb_tma_w<T, VEC, TY, VEC, ALGO, S, true>(q, tg, st, st_next, brs, cl + VEC, th.z0p_rim, wv, z0c, z1c, z2c, xo, un, uo,
-                                                                  a.z_in + it.b * 3 * g.vol, m, rs, c);
+                                                                  zfold, m, rs, c, &fb);
                 else pxb_tv_w_outside<T, VEC, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);  // a fold onto another tile ('wrap'), or zeros
                 PxbVec<T, VEC> o;
                 for (int j = 0; j < VEC; ++j) o.v[j] = wv[j];
@@ -340,7 +419,7 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             if (MODES) {
                 const bool ev = r < g.nR && cs != PXB_NOSRC;
                 if (ev) pxb_tma_w<T, VEC, TY, 1, ALGO, S, true>(q, tg, st, st_next, hl + 1, bcs, &th.z0p_col, wv, z0c, z1c, z2c, xo, un, uo,
-                                                                a.z_in + it.b * 3 * g.vol, m, r, cs);
+                                                                zfold, m, r, cs, &fb);
                 else pxb_tv_w_outside<T, 1, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);
                 slot[(hl + 1) * R::RS + bc] = wv[0];
             } else {

@@ -246,6 +246,7 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
             emu_tma_box<T>(mz, C::BR1, c1, st + C::OFF_Z1);
         };
         for (int m = Rg.mlo; m < Rg.mlo + C::NSTAGE && m < mload_hi; ++m) issue(m);
+        const PxbTmaFold fbx = MODES ? pxb_tma_fold_setup<T, VEC, TY>(q, g, it) : PxbTmaFold{};
         for (int tid = 0; tid < C::NT; ++tid) {
             std::memset(&th[tid], 0, sizeof(th[tid]));
             pxb_tma_prologue<T, VEC, TY, MODES, ALGO == PXB_PD3O && NORMS>(q, g, it, a, tid, Rg.mlo, th[tid]);
@@ -254,7 +255,7 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
             const int k = m - Rg.mlo;
             const T* st = stages.data() + (k % C::NSTAGE) * C::STAGE;
             const T* st_next = need_next ? stages.data() + ((k + 1) % C::NSTAGE) * C::STAGE : st;
-            for (int tid = 0; tid < C::NT; ++tid) pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring.data(), th[tid]);
+            for (int tid = 0; tid < C::NT; ++tid) pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring.data(), th[tid], fbx);
             if (m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
             const int mm = m - lag;
             for (int tid = 0; tid < C::NT; ++tid) {

@@ -18,6 +18,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--size2d", type=int, default=8192)
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--modes", default="constant,reflect,wrap,symmetric,edge")
+ap.add_argument("--no-two-sweep", action="store_true")
 args = ap.parse_args()
 lib = K.lib()
 
@@ -35,7 +37,7 @@ def timeit(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
-for shape in ((args.size,) * 3, (args.size2d,) * 2):
+for shape in [sh for sh in ((args.size,) * 3, (args.size2d,) * 2) if sh[0] > 0]:
     N, D = int(np.prod(shape)), len(shape)
     y = torch.rand(N, device="cuda")
     shift = -y
@@ -49,7 +51,7 @@ for shape in ((args.size,) * 3, (args.size2d,) * 2):
     u0, u1, w, x = y.clone(), torch.empty_like(y), torch.empty_like(y), torch.empty_like(y)
     z0, z1 = torch.zeros(D * N, device="cuda"), torch.empty(D * N, device="cuda")
     bpv = 4 * (2 * D + 3)
-    for mode in ("constant", "reflect", "wrap", "symmetric", "edge"):
+    for mode in args.modes.split(","):
         d = pxo.Gradient(arg_shape=shape, mode=mode, dtype=np.float32)._desc(1, K.F32)
 
         def one():
@@ -61,6 +63,7 @@ for shape in ((args.size,) * 3, (args.size2d,) * 2):
                 K.check(lib.pxb_pds_primal(K.ALGO_PD3O, C.byref(d), C.byref(P), u0.data_ptr(), z0.data_ptr(), None, x.data_ptr(), w.data_ptr(), None, None), "primal")
                 K.check(lib.pxb_pds_dual(C.byref(d), C.byref(P), w.data_ptr(), z0.data_ptr(), None, None), "dual")
 
-        t1, t2 = timeit(one, args.reps) / 2, timeit(two, args.reps) / 2
+        t1 = timeit(one, args.reps) / 2
+        t2 = float("nan") if args.no_two_sweep else timeit(two, args.reps) / 2
         print(f"{shape} fp32 mode={mode:9s}: single kernel {t1:7.3f} ms ({bpv * N / t1 / 1e6:5.0f} GB/s at {bpv} B/voxel)   two sweeps {t2:7.3f} ms", flush=True)
     del u0, u1, w, x, z0, z1, y, shift
