@@ -156,4 +156,6 @@ int pxb_stencil2d_try(const pxb_stencil2d* d, const void* in, void* out, cudaStr
 int pxb_stencil2d_fista_try(const pxb_stencil2d* d, const pxb_fista_step* f, int which, void* out, cudaStream_t s, cudaError_t* err);
 int pxb_tv_tile2d_try(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* xu_in, const void* z_in, void* xu_out, void* z_out,
                       void* x_out, double* norms_x, double* norms_z, cudaStream_t s, cudaError_t* err, const PxbIterStop* stop = nullptr);
+int pxb_tv_tile2d_loop_try(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, void* xu_a, void* z_a, void* xu_b, void* z_b, void* x_out, double* norms,
+                           int use_x, int use_z, int n, cudaStream_t s, cudaError_t* err, const PxbIterStop* stop);
 bool pxb_tv_try_grad(const pxb_grad_desc* K, bool adjoint, const void* in, void* out, cudaStream_t s, int* rc);

@@ -192,6 +192,22 @@ int pxb_tv_iter_launch_n(int algo, const pxb_grad_desc* K, const pxb_pds_params*
         st.rows = (int32_t)K->batch;
     }
     const int64_t per = 4 * K->batch;
+    // small 2-D problems (every tile resident at once): all n iterations in ONE cooperative launch with grid-wide barriers
+    if (K->ndir == 2 && n >= 2 && pxb_iter_path() != 1) {
+        const void* sh = (p->f.kind == PXB_F_SQL2 && p->f.shift_period > 1) ? p->f.shift : nullptr;
+        const bool ok = aligned16({xu_a, z_a, xu_b, z_b, x_out, sh, p->f.kind == PXB_F_GRADARR ? p->f.garr : nullptr}) &&
+                        !(algo == PXB_PD3O && p->f.kind == PXB_F_GRADARR) && !(algo == PXB_PD3O && rule && rule->eps_x > 0 && !x_out);
+        if (ok) {
+            cudaError_t err = cudaSuccess;
+            const int why = pxb_tv_tile2d_loop_try(algo, K, p, xu_a, z_a, xu_b, z_b, x_out, rule ? norms : nullptr, rule && rule->eps_x > 0, rule && rule->eps_z > 0,
+                                                   n, s, &err, rule ? &st : nullptr);
+            if (why == 0) {
+                if (err != cudaSuccess) return pxb_fail(PXB_ECUDA, "pxb_pds_iter_n (persistent tile2d): %s", cudaGetErrorString(err));
+                pxb_count_launch();  // ONE kernel launch carries the n iterations
+                return 0;
+            }
+        }
+    }
     for (int i = 0; i < n; ++i) {
         double* nx = rule && rule->eps_x > 0 ? norms + (int64_t)i * per : nullptr;
         double* nz = rule && rule->eps_z > 0 ? norms + (int64_t)i * per + 2 * K->batch : nullptr;

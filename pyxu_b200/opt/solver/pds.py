@@ -611,7 +611,7 @@ class _PrimalDualSplitting(Solver):
                     A.synchronize()
                     dt = (time.perf_counter() - t0) / n
                     per_iter = dt if per_iter is None else min(per_iter, dt)
-                    cap = max(2, min(cap * 2, self._BATCH_MAX, int(self._BATCH_SECONDS / max(per_iter, 1e-7))))
+                    cap = max(2, min(self._BATCH_MAX, int(self._BATCH_SECONDS / max(per_iter, 1e-7))))  # (one timed batch is enough: no doubling)
         buf = torch.empty(self._BATCH_MAX * 4 * rows + 2, dtype=torch.float64, device=mst["z"].device)  # sums of every iteration | ctl
         ctl_view = buf[-2:].view(torch.int32)
         fused = mst["_fused_norms"]
@@ -652,7 +652,7 @@ class _PrimalDualSplitting(Solver):
             # the sums of the last iteration wait for the test at the top of the loop
             fused["_host"], fused["_stamp"] = sums[done - 1], 0
             per_iter = dt / done if per_iter is None else min(per_iter, dt / done)
-            cap = max(2, min(cap * 2, self._BATCH_MAX, int(self._BATCH_SECONDS / max(per_iter, 1e-7))))
+            cap = max(2, min(self._BATCH_MAX, int(self._BATCH_SECONDS / max(per_iter, 1e-7))))
 
     def _materialize(self, name):
         """x of PD3O is not written by the single-kernel iteration unless something needs it every step; rebuild it
