@@ -51,7 +51,7 @@ struct PxbIterGeom {
     int ndir;
     int open_lo, open_hi; // slab cuts along M (NDIR == 3): ghost planes hold the neighbour's u, z, shift
     int64_t nblocks;
-    int edge_first;       // peer-memory exchange: the first and the last chunk of every tile come first in the block order
+    int edge_first;       // peer-memory exchange: the first and the last chunk of every tile come early in the block order (1: first, 2: interleaved 1:3)
 };
 
 // Device-side stopping rule of iterations launched back to back without the host in the loop (pxb_pds_iter_n): the last
@@ -176,15 +176,30 @@ PXB_HD PxbIterItem pxb_iter_item(const PxbIterGeom& g, int64_t blk, int ty, int 
     int64_t rem = blk - img * per_img;
     int ch, tR, tC;
     // edge_first: the chunks that hold a slab's first / last plane -- what the neighbours wait for -- before the interior ones
+    // edge_first == 2: ... interleaved with the interior ones, one edge block in four, over the first 4 * (edge blocks) of the grid.
+    // (An A/B switch: all edge blocks at once put 296 blocks' worth of peer stores on NVLink in the first microseconds of the launch;
+    // interleaved, every SM pairs an edge block with an interior one.  Measured on 2 B200s: no difference.)
     const int n_edge = g.edge_first ? (g.nchunk >= 2 ? 2 : 1) : 0;
     const int64_t tiles = (int64_t)g.ntR * g.ntC;
-    if (rem < n_edge * tiles) {
-        const int e = (int)(rem / tiles), t = (int)(rem - (int64_t)e * tiles);
+    const int64_t eb = n_edge * tiles;
+    bool edge = rem < eb;
+    int64_t idx = edge ? rem : rem - eb;
+    if (g.edge_first == 2 && per_img - eb >= 3 * eb) {
+        if (rem < 4 * eb) {
+            edge = (rem & 3) == 0;
+            idx = edge ? (rem >> 2) : rem - (rem >> 2) - 1;
+        } else {
+            edge = false;
+            idx = rem - eb;
+        }
+    }
+    if (edge) {
+        const int e = (int)(idx / tiles), t = (int)(idx - (int64_t)e * tiles);
         ch = e == 0 ? 0 : g.nchunk - 1;
         tR = t / g.ntC;
         tC = t % g.ntC;
     } else {
-        rem -= n_edge * tiles;
+        rem = idx;
         const int nch = g.nchunk - n_edge;
         const int64_t full_band = (int64_t)g.band * g.ntC * nch;
         const int bi = (int)(rem / full_band);

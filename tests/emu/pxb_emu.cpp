@@ -191,6 +191,7 @@ static void emu_tma_box(const PxbTmaBoxDesc& m, uint32_t rows, const int c[5], T
         }
 }
 static const pxb_peer* g_emu_peer = nullptr;  // set by emu_tv_iter_tma_p2p for the duration of one call
+static int g_emu_edge_first = 1;              // block order of the peer-exchange launches (emu_set_edge_first: 1 = edges first, 2 = interleaved)
 template <class T, int ALGO, bool NORMS, class S, bool MODES = false>
 static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbIterPtr<T>& a_in, int chunk, int want_spec) {
     constexpr int VEC = 16 / (int)sizeof(T), TY = 8;
@@ -213,7 +214,7 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
     }
     if (const pxb_peer* peer = g_emu_peer) {  // as run() in pxb_tv_tma.cu
         if (K->batch != 1) return -124;
-        g.edge_first = 1;
+        g.edge_first = g_emu_edge_first;
         a.peer.dn_u = (T*)peer->dn_u; a.peer.dn_z = (T*)peer->dn_z; a.peer.dn_zvol = peer->dn_zvol; a.peer.up_z0 = (T*)peer->up_z0;
         a.peer.dn_flag = peer->dn_flag; a.peer.up_flag = peer->up_flag; a.peer.lo_wait = peer->lo_wait; a.peer.hi_wait = peer->hi_wait;
         a.peer.target = (unsigned)((uint64_t)peer->epoch * (uint64_t)g.ntR * (uint64_t)g.ntC);
@@ -226,7 +227,13 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
         // counter short of its target is a counting error
         if (a.peer.lo_wait && it.m0 == 0 && (int)(*a.peer.lo_wait - a.peer.target) < 0) return -140;
         if (a.peer.hi_wait && it.m1 == g.nM && (int)(*a.peer.hi_wait - a.peer.target) < 0) return -141;
-        if (g.edge_first && blk < (int64_t)(g.nchunk >= 2 ? 2 : 1) * g.ntR * g.ntC && !(it.m0 == 0 || it.m1 == g.nM)) return -142;  // edges first
+        {   // the edge work items come early: all of them first (1), or inside the first 4 x (their number) blocks (2)
+            const int64_t eb = (int64_t)(g.nchunk >= 2 ? 2 : 1) * g.ntR * g.ntC;
+            const bool is_edge = it.m0 == 0 || it.m1 == g.nM;
+            const bool woven = g.edge_first == 2 && (int64_t)g.ntR * g.ntC * g.nchunk - eb >= 3 * eb;
+            if (g.edge_first && !woven && blk < eb && !is_edge) return -142;
+            if (g.edge_first && woven && blk >= 4 * eb && is_edge) return -142;
+        }
         const PxbIterRange Rg = pxb_iter_range<T>(q, it);
         const bool need_next = pxb_has_cm<S>(q, 0);
         const int lag = S::SCHEME == PXB_SCHEME_FWD ? 1 : Rg.lag;
@@ -674,6 +681,11 @@ int emu_tv_iter_tma(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, c
                     void* x_out, double* nx, double* nz, int chunk) {
     if (K->dtype == PXB_F32) return t_tma<float>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);
     return t_tma<double>(algo, K, p, u_in, z_in, u_out, z_out, x_out, nx, nz, chunk);
+}
+int emu_set_edge_first(int v) {
+    if (v != 1 && v != 2) return -1;
+    g_emu_edge_first = v;
+    return 0;
 }
 // the same with the halo exchange fused in (pxb_pds_iter_p2p): `peer` points into the neighbouring ranks' arrays of this process
 int emu_tv_iter_tma_p2p(int algo, const pxb_grad_desc* K, const pxb_pds_params* p, const void* u_in, const void* z_in, void* u_out, void* z_out,

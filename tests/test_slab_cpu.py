@@ -331,8 +331,10 @@ def test_slab_single_kernel_iteration_equals_single_domain(world, form, scheme, 
 
 @pytest.mark.parametrize("mode", ["constant", ("reflect", "symmetric", "edge"), ("wrap", "reflect", "symmetric")], ids=lambda m: m if isinstance(m, str) else "-".join(m))
 @pytest.mark.parametrize("world", [2, 3, 4])
-@pytest.mark.parametrize("shape,chunk", [((26, 6, 8), 3), ((41, 16, 64), 0), ((12, 16, 64), 0)], ids=["ragged-chunk3", "fulltiles", "one-chunk-slabs"])
-def test_slab_iteration_with_the_exchange_fused_into_the_kernel(world, mode, shape, chunk):
+@pytest.mark.parametrize("shape,chunk", [((26, 6, 8), 3), ((41, 16, 64), 0), ((12, 16, 64), 0), ((96, 16, 64), 2)],
+                         ids=["ragged-chunk3", "fulltiles", "one-chunk-slabs", "many-chunks"])
+@pytest.mark.parametrize("order", [1, 2], ids=["edges-first", "edges-interleaved"])
+def test_slab_iteration_with_the_exchange_fused_into_the_kernel(world, mode, shape, chunk, order):
     """pxb_pds_iter_p2p: ONE launch per rank and iteration; the kernel body stores the new boundary planes into the neighbours'
     ghost planes (here: the other simulated ranks' arrays), bumps their counters, and checks the neighbours' counters before
     reading its own ghost planes.  No exchange between iterations; result = the single-domain iteration, bit for bit in
@@ -340,6 +342,7 @@ def test_slab_iteration_with_the_exchange_fused_into_the_kernel(world, mode, sha
     n_iter, lam = 6, 0.08
     tau = sigma = 0.28
     rho = 1.3
+    assert E.lib().emu_set_edge_first(order) == 0  # block order of the launch: the edge work items first (the library's default) / one in four
     y = np.random.default_rng(3).random(shape)
     m0 = mode if isinstance(mode, str) else mode[0]
     periodic = m0 == "wrap" and world > 1
@@ -394,6 +397,7 @@ def test_slab_iteration_with_the_exchange_fused_into_the_kernel(world, mode, sha
     tiles = -(-shape[1] // 8) * -(-shape[2] // 64)
     for r, rk in enumerate(ranks):
         assert flags[r][0] == (n_iter * tiles if rk.has_lo else 0) and flags[r][1] == (n_iter * tiles if rk.has_hi else 0)
+    E.lib().emu_set_edge_first(1)
 
 
 def _worker_many(rank, world, port, q):
