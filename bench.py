@@ -670,10 +670,32 @@ def main():
             tm = slv2._astate["timing"]
             runs.append({"seconds": dt, "build_s": t1 - t0, "fit_s": t2 - t1, "fit_m_init_s": tm["m_init_s"], "fit_iterations_s": tm["run_s"],
                          "solution_s": t3 - t2, "final_barrier_s": time.perf_counter() - t3})
-            del slv2, x_host, x_loc
+            hist_e2e = np.concatenate(slv2._astate["history"])["RelError[x]"].copy()
+            streamed = getattr(slv2, "_slab", None) is not None and world == 1
+            if rep == 0:
+                del x_host, x_loc
+            del slv2
+        # Full-size check of the end-to-end result (outside every timed region): the same K iterations on DEVICE-resident arrays
+        # through the ordinary one-launch-per-iteration / batched path; result and RelError history must agree with what the
+        # host-array run (streamed wavefront on one GPU) brought back.
+        yd = torch.from_numpy(x0_np).to(dev)
+        slvc = tv_solver(shape, sh(-yd))
+        slvc.fit(x0=sh(yd), stop_crit=pxst.MaxIter(K) | pxst.RelError(eps=1e-30, var="x"), **dist_kw)
+        xc = slvc.solution()
+        xc = getattr(xc, "local", xc)
+        xe = torch.from_numpy(x_loc).to(dev)
+        num, den = torch.linalg.vector_norm((xe - xc.reshape(-1)).double()), torch.linalg.vector_norm(xc.double())
+        rel_chk = env.max_over_ranks(float(num / den))
+        hist_c = np.concatenate(slvc._astate["history"])["RelError[x]"]
+        hist_dev = float(np.max(np.abs(hist_e2e[1:] - hist_c[1:]) / np.maximum(np.abs(hist_c[1:]), 1e-30)))
+        assert rel_chk < 1e-5 and hist_dev < 1e-3, (rel_chk, hist_dev)
+        e2e_check = {"rel_err_x_vs_device_resident_run": rel_chk, "max_rel_dev_of_RelError_history": hist_dev, "tol": [1e-5, 1e-3],
+                     "streamed_wavefront": bool(streamed), "voxels_compared": int(local_vox)}
+        del slvc, xc, xe, yd, x_host, x_loc
+        torch.cuda.empty_cache()
         dt = runs[1]["seconds"]
         e2e = {"value": nvox * K / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(2 * 4 * nvox / K),
-               "d2h_bytes_per_step": int(4 * nvox / K + 16 * world), "seconds": dt, "parts": runs[1], "first_call": runs[0],
+               "d2h_bytes_per_step": int(4 * nvox / K + 16 * world), "seconds": dt, "parts": runs[1], "first_call": runs[0], "check": e2e_check,
                "what": "per rank: PD3O(...).fit(x0=<pinned host array>, stop_crit=MaxIter(K)|RelError[x]) + solution(): H2D of x0 and of the data y "
                        "(this rank's planes), K fused iterations with RelError[x] tested after every one of them (1 GPU: x0 and y travel in 16-plane "
                        "z-chunks and the iterations are queued as a wavefront behind the chunks, the result travels back behind the wave, the "
