@@ -704,6 +704,22 @@ def main():
                        "pinned result buffer reserved beforehand (reserve_host_results); wall clock between barriers, max over ranks; second of two "
                        "calls (the first one, which also pays one-off initialisation, is `first_call`)"}
         A_.release_host_results()
+        # What a caller gets who hands over ordinary (pageable) NumPy arrays and has reserved nothing: uploads through the pinned staging
+        # buffers (host threads), the result into a fresh pageable array.  One call, reported beside the pinned number.
+        x0_pg, shift_pg = np.array(x0_np, copy=True), np.array(shift_np, copy=True)
+        env.barrier()
+        t0 = time.perf_counter()
+        slv3 = tv_solver(shape, sh(shift_pg))
+        slv3.fit(x0=sh(x0_pg), stop_crit=pxst.MaxIter(K) | pxst.RelError(eps=1e-30, var="x"), **dist_kw)
+        x_pg = slv3.solution()
+        torch.cuda.synchronize()
+        env.barrier()
+        dt_pg = env.max_over_ranks(time.perf_counter() - t0)
+        x_pg = getattr(x_pg, "local", x_pg)
+        assert isinstance(x_pg, np.ndarray) and np.isfinite(x_pg[:: max(1, local_vox // 1000)]).all()
+        e2e["pageable"] = {"value": nvox * K / dt_pg / 1e9, "unit": UNIT, "seconds": dt_pg,
+                           "what": "the same call with pageable NumPy arrays in and out and no reserved result buffer (staged copies, host threads)"}
+        del slv3, x_pg, x0_pg, shift_pg
         del y_host, shift_host, shift_np, x0_np
         torch.cuda.empty_cache()
 
