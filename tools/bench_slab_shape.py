@@ -23,7 +23,12 @@ ap.add_argument("--n1", type=int, default=1024)
 ap.add_argument("--n2", type=int, default=1024)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--planes", default="64,128,256,512,1024")
+ap.add_argument("--spin", type=int, default=0, help="extra untimed pairs first (keeps the GPUs of a box busy together before the timed ones)")
 args = ap.parse_args()
+# under torchrun: every rank times the same kernel on its own GPU AT THE SAME TIME, no communication -- how much the GPUs of one box
+# differ under simultaneous load is the floor of what a ring of coupled ranks can run at
+rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(rank)
 lib = K.lib()
 out = []
 for n0 in [int(v) for v in args.planes.split(",")]:
@@ -46,7 +51,7 @@ for n0 in [int(v) for v in args.planes.split(",")]:
         K.check(lib.pxb_pds_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), u0.data_ptr(), z0.data_ptr(), u1.data_ptr(), z1.data_ptr(), None, None, None, None), "iter")
         K.check(lib.pxb_pds_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), u1.data_ptr(), z1.data_ptr(), u0.data_ptr(), z0.data_ptr(), None, None, None, None), "iter")
 
-    for _ in range(3):
+    for _ in range(3 + args.spin):
         pair()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -59,4 +64,4 @@ for n0 in [int(v) for v in args.planes.split(",")]:
     out.append({"planes": n0, "ms": ms, "us_per_plane": 1e3 * ms / n0, "GBps": 36 * N / ms / 1e6})
     del y, shift, u0, u1, z0, z1
     torch.cuda.empty_cache()
-print(json.dumps({"shape": f"(n0, {args.n1}, {args.n2}) fp32, single-kernel PD3O-TV iteration, one GPU", "rows": out}))
+print(json.dumps({"shape": f"(n0, {args.n1}, {args.n2}) fp32, single-kernel PD3O-TV iteration, one GPU", "rank": rank, "rows": out}), flush=True)
