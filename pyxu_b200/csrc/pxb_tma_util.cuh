@@ -30,6 +30,9 @@ static __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
+#ifdef PXB_MBAR_BACKOFF
+        __nanosleep(PXB_MBAR_BACKOFF);
+#endif
     }
     __trap();
 }
