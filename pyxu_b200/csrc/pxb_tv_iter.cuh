@@ -146,6 +146,7 @@ struct PxbIterItem {
     int64_t b;         // batch row
     int m0, m1, r0, c0;
     int si;            // image index inside the batch item (NDIR == 2: its axis-0 coordinate)
+    int full;          // the tile lies entirely inside the image (no row / column tests for its own samples)
 };
 
 template <class T, int VEC, int TXL, int TY, int NDIR>
@@ -170,23 +171,25 @@ struct PxbIterThread {
 // hit too.  Hence: a band holds as many tile-rows as there are co-resident CTAs; inside a band the order is tile
 // column, tile row, then chunk.  (Measured at 1024^3: tiles-then-chunks order 5.4 TB/s, banded short chunks > 6 TB/s.)
 PXB_HD PxbIterItem pxb_iter_item(const PxbIterGeom& g, int64_t blk, int ty, int t2) {
+    // (the grid has fewer than 2^31 blocks -- pxb_iter_setup -- so the block arithmetic is 32-bit: the 64-bit divisions of the first
+    //  version were ~1000 warp instructions per thread block)
     PxbIterItem it;
-    const int64_t per_img = (int64_t)g.ntR * g.ntC * g.nchunk;
-    const int64_t img = blk / per_img;
-    int64_t rem = blk - img * per_img;
+    const unsigned per_img = (unsigned)g.ntR * (unsigned)g.ntC * (unsigned)g.nchunk;
+    const unsigned img = (unsigned)blk / per_img;
+    unsigned rem = (unsigned)blk - img * per_img;
     int ch, tR, tC;
     // edge_first: the chunks that hold a slab's first / last plane -- what the neighbours wait for -- before the interior ones
     // edge_first == 2: ... interleaved with the interior ones, one edge block in four, over the first 4 * (edge blocks) of the grid.
     // (An A/B switch: all edge blocks at once put 296 blocks' worth of peer stores on NVLink in the first microseconds of the launch;
     // interleaved, every SM pairs an edge block with an interior one.  Measured on 2 B200s: no difference.)
     const int n_edge = g.edge_first ? (g.nchunk >= 2 ? 2 : 1) : 0;
-    const int64_t tiles = (int64_t)g.ntR * g.ntC;
-    const int64_t eb = n_edge * tiles;
+    const unsigned tiles = (unsigned)g.ntR * (unsigned)g.ntC;
+    const unsigned eb = (unsigned)n_edge * tiles;
     bool edge = rem < eb;
-    int64_t idx = edge ? rem : rem - eb;
-    if (g.edge_first == 2 && per_img - eb >= 3 * eb) {
-        if (rem < 4 * eb) {
-            edge = (rem & 3) == 0;
+    unsigned idx = edge ? rem : rem - eb;
+    if (g.edge_first == 2 && per_img - eb >= 3u * eb) {
+        if (rem < 4u * eb) {
+            edge = (rem & 3u) == 0;
             idx = edge ? (rem >> 2) : rem - (rem >> 2) - 1;
         } else {
             edge = false;
@@ -194,26 +197,27 @@ PXB_HD PxbIterItem pxb_iter_item(const PxbIterGeom& g, int64_t blk, int ty, int 
         }
     }
     if (edge) {
-        const int e = (int)(idx / tiles), t = (int)(idx - (int64_t)e * tiles);
+        const unsigned e = idx / tiles, t = idx - e * tiles;
         ch = e == 0 ? 0 : g.nchunk - 1;
-        tR = t / g.ntC;
-        tC = t % g.ntC;
+        tR = (int)(t / (unsigned)g.ntC);
+        tC = (int)(t - (unsigned)tR * (unsigned)g.ntC);
     } else {
         rem = idx;
-        const int nch = g.nchunk - n_edge;
-        const int64_t full_band = (int64_t)g.band * g.ntC * nch;
-        const int bi = (int)(rem / full_band);
+        const unsigned nch = (unsigned)(g.nchunk - n_edge);
+        const unsigned full_band = (unsigned)g.band * (unsigned)g.ntC * nch;
+        const unsigned bi = rem / full_band;
         rem -= bi * full_band;
-        const int rows_here = g.ntR - bi * g.band < g.band ? g.ntR - bi * g.band : g.band;
-        const int per_chunk = rows_here * g.ntC;
-        ch = (int)(rem / per_chunk);
-        const int r2 = (int)(rem - (int64_t)ch * per_chunk);
-        ch += n_edge ? 1 : 0;
-        tR = bi * g.band + r2 / g.ntC;
-        tC = r2 % g.ntC;
+        const int rows_here = g.ntR - (int)bi * g.band < g.band ? g.ntR - (int)bi * g.band : g.band;
+        const unsigned per_chunk = (unsigned)rows_here * (unsigned)g.ntC;
+        const unsigned chq = rem / per_chunk;
+        const unsigned r2 = rem - chq * per_chunk;
+        ch = (int)chq + (n_edge ? 1 : 0);
+        const unsigned rq = r2 / (unsigned)g.ntC;
+        tR = (int)bi * g.band + (int)rq;
+        tC = (int)(r2 - rq * (unsigned)g.ntC);
     }
-    const int64_t b = img / g.sub;
-    const int si = (int)(img - b * g.sub);
+    const int64_t b = (int64_t)(img / (unsigned)g.sub);
+    const int si = (int)(img - (unsigned)b * (unsigned)g.sub);
     it.b = b;
     it.si = si;
     it.v_base = (int64_t)si * g.sub_stride;
@@ -223,6 +227,7 @@ PXB_HD PxbIterItem pxb_iter_item(const PxbIterGeom& g, int64_t blk, int ty, int 
     it.m1 = it.m0 + g.chunk < g.nM ? it.m0 + g.chunk : g.nM;
     it.r0 = tR * ty;
     it.c0 = tC * t2;
+    it.full = (it.r0 + ty <= g.nR && it.c0 + t2 <= g.nC) ? 1 : 0;
     return it;
 }
 
@@ -403,11 +408,13 @@ PXB_HD void pxb_iter_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
 // ---------------------------------------------------------------------------------------------------------
 template <class T, int VEC, int TXL, int TY, int NDIR, bool NORMS, class S = PxbSpecAny>
 PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid, int mm,
-                            const T* smem, const T (*zo)[VEC], double* acc) {
+                            const T* smem, const T (*zo)[VEC], double* acc, T* zb_at = nullptr) {
+    // zb_at: z_out at this thread's samples on plane mm, component 0, when the caller keeps a running pointer (saves the 64-bit
+    // index arithmetic per plane: 19 of the 463 warp instructions per plane of the TMA form)
     using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
     const int rl = tid / TXL, cx = tid - rl * TXL, cl = cx * VEC;
     const int r = it.r0 + rl, c = it.c0 + cl;
-    if (r >= g.nR || c >= g.nC) return;
+    if (!it.full && (r >= g.nR || c >= g.nC)) return;
     const int cell = (rl + C::R0) * C::RS + cl + VEC;
     const T* __restrict__ s1 = smem + (mm & 3) * C::SLOT + cell;
     const PxbVec<T, VEC> wc = pxb_vload<T, VEC>(s1);
@@ -464,14 +471,16 @@ PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
             p[k][j] = zn;
         }
     }
-    T* __restrict__ zb = a.z_out + it.z_base + (int64_t)mm * g.sM + (int64_t)r * g.sR + c;
+    T* __restrict__ zb = zb_at ? zb_at : a.z_out + it.z_base + (int64_t)mm * g.sM + (int64_t)r * g.sR + c;
+    // peer-memory exchange: the first owned plane of every component goes down, the last one of component 0 goes up
+    // (the plane tests first: they are uniform and almost never true)
+    const bool dn = NDIR == 3 && mm == 0 && a.peer.dn_z != nullptr, up = NDIR == 3 && mm == g.nM - 1 && a.peer.up_z0 != nullptr;
     for (int k = 0; k < NDIR; ++k) {
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = p[k][j];
         pxb_vstore<T, VEC>(zb + k * g.vol, o);
-        // peer-memory exchange: the first owned plane of every component goes down, the last one of component 0 goes up
-        if (NDIR == 3 && a.peer.dn_z != nullptr && mm == 0) pxb_vstore<T, VEC>(a.peer.dn_z + k * a.peer.dn_zvol + (int64_t)r * g.sR + c, o);
-        if (NDIR == 3 && k == 0 && a.peer.up_z0 != nullptr && mm == g.nM - 1) pxb_vstore<T, VEC>(a.peer.up_z0 + (int64_t)r * g.sR + c, o);
+        if (dn) pxb_vstore<T, VEC>(a.peer.dn_z + k * a.peer.dn_zvol + (int64_t)r * g.sR + c, o);
+        if (up && k == 0) pxb_vstore<T, VEC>(a.peer.up_z0 + (int64_t)r * g.sR + c, o);
     }
     if (NORMS) { acc[2] += (double)a0; acc[3] += (double)a1; }
 }

@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(32 * TY, 2)
             T zo[3][VEC];
             for (int kk = 0; kk < 3; ++kk)
                 for (int j = 0; j < VEC; ++j) zo[kk][j] = lag ? th.zprev[kk][j] : th.zc[kk][j];
-            pxb_iter_phaseC<T, VEC, C::TXL, TY, 3, NORMS, S>(q, g, it, a, tid, mm, ring, zo, th.acc);
+            pxb_iter_phaseC<T, VEC, C::TXL, TY, 3, NORMS, S>(q, g, it, a, tid, mm, ring, zo, th.acc, th.pz);
+            th.pz += g.sM;
         }
         for (int kk = 0; kk < 3; ++kk)
             for (int j = 0; j < VEC; ++j) th.zprev[kk][j] = th.zc[kk][j];

@@ -184,6 +184,8 @@ struct PxbTmaThread {
     T z0p_col;        //   ... the rim-column sample (last 2*TY threads)
     T xp[VEC];        // PD3O + RelError[x]: the previous x of the plane phase A visits next, loaded one plane ahead so that
                       // the global-load latency is not in the per-plane critical path (everything else is staged by TMA)
+    int64_t lin;      // offset of this thread's own samples on the plane phase A visits next, in u-like arrays (running: += sM per plane)
+    T* pz;            // z_out (component 0) at this thread's own samples on the plane phase C finishes next (running)
     double acc[4];
 };
 
@@ -271,6 +273,12 @@ PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const Pxb
     using C = PxbTmaCfg<T, VEC, TY>;
     for (int j = 0; j < VEC; ++j) st.z0p[j] = st.z0p_rim[j] = T(0);
     st.z0p_col = T(0);
+    {   // running addresses of the thread's own samples (the per-plane 64-bit index arithmetic was ~30 of 463 warp instructions per plane)
+        const int rl0 = tid / C::TXL, r_ = it.r0 + rl0, c_ = it.c0 + (tid - rl0 * C::TXL) * VEC;
+        const int64_t rc = (int64_t)r_ * g.sR + c_;
+        st.lin = it.lin_base + (int64_t)mlo * g.sM + rc;
+        st.pz = a.z_out + it.z_base + (int64_t)it.m0 * g.sM + rc;
+    }
     if (XPREV && a.norms_x != nullptr) {
         const int rl = tid / C::TXL, r = it.r0 + rl, c = it.c0 + (tid - rl * C::TXL) * VEC;
         if (r < g.nR && c < g.nC) {
@@ -318,7 +326,8 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
     const int rl = tid / C::TXL, cl = (tid - rl * C::TXL) * VEC;
     {
         const int r = it.r0 + rl, c = it.c0 + cl;
-        const bool in = plane_in && r < g.nR && c < g.nC;
+        const bool in_rc = it.full || (r < g.nR && c < g.nC);
+        const bool in = plane_in && in_rc;
         T wv[VEC], z0c[VEC], xo[VEC], un[VEC], uo[VEC];
         pxb_tma_w<T, VEC, TY, VEC, ALGO, S, MODES>(q, tg, st, st_next, rl + 1, cl + VEC, th.z0p, wv, z0c, th.zc[1], th.zc[2], xo, un, uo,
                                                    in ? zfold : nullptr, m, r, c, &fb);
@@ -330,8 +339,9 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = keep ? wv[j] : T(0);
         pxb_vstore<T, VEC>(slot + (rl + 1) * R::RS + cl + VEC, o);
+        const int64_t lin = th.lin;  // (= it.lin_base + m * g.sM + r * g.sR + c)
+        th.lin = lin + g.sM;
         if (own && in) {
-            const int64_t lin = it.lin_base + (int64_t)m * g.sM + (int64_t)r * g.sR + c;
             if (ALGO == PXB_PD3O) {
                 if (NORMS && a.norms_x) {
                     // partial sums of one vector in the working precision, widened once (fp32: the per-sample fp64
@@ -359,13 +369,13 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             for (int j = 0; j < VEC; ++j) o.v[j] = un[j];
             pxb_vstore<T, VEC>(a.u_out + lin, o);
             // peer-memory exchange: the first owned plane of the new primal iterate is the lower neighbour's upper ghost plane
-            if (a.peer.dn_u != nullptr && m == 0) pxb_vstore<T, VEC>(a.peer.dn_u + (int64_t)r * g.sR + c, o);
+            if (m == 0 && a.peer.dn_u != nullptr) pxb_vstore<T, VEC>(a.peer.dn_u + (int64_t)r * g.sR + c, o);
         }
         // previous x of this thread's samples on the NEXT plane, consumed one plane later: loaded straight into the registers
         // the sums above have just released (a load into a temporary moved over afterwards made the move wait for the load:
         // 9.5 ms instead of 7.3 at 1024^3, long-scoreboard stalls doubled)
-        if (ALGO == PXB_PD3O && NORMS && !PXB_EXP(8) && a.norms_x != nullptr && m + 1 >= it.m0 && m + 1 < it.m1 && r < g.nR && c < g.nC) {
-            const PxbVec<T, VEC> nx = pxb_vload<T, VEC>(a.x_out + it.lin_base + (int64_t)(m + 1) * g.sM + (int64_t)r * g.sR + c);
+        if (ALGO == PXB_PD3O && NORMS && !PXB_EXP(8) && a.norms_x != nullptr && m + 1 >= it.m0 && m + 1 < it.m1 && in_rc) {
+            const PxbVec<T, VEC> nx = pxb_vload<T, VEC>(a.x_out + lin + g.sM);
             for (int j = 0; j < VEC; ++j) th.xp[j] = nx.v[j];
         }
     }

@@ -266,8 +266,10 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
             if (m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
             const int mm = m - lag;
             for (int tid = 0; tid < C::NT; ++tid) {
-                if (mm >= it.m0 && mm < it.m1)
-                    pxb_iter_phaseC<T, VEC, C::TXL, TY, 3, NORMS, S>(q, g, it, a, tid, mm, ring.data(), lag ? th[tid].zprev : th[tid].zc, th[tid].acc);
+                if (mm >= it.m0 && mm < it.m1) {
+                    pxb_iter_phaseC<T, VEC, C::TXL, TY, 3, NORMS, S>(q, g, it, a, tid, mm, ring.data(), lag ? th[tid].zprev : th[tid].zc, th[tid].acc, th[tid].pz);
+                    th[tid].pz += g.sM;
+                }
                 std::memcpy(th[tid].zprev, th[tid].zc, sizeof(th[tid].zc));
             }
         }
