@@ -460,7 +460,7 @@ PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
     for (int j = 0; j < VEC; ++j) {
         T grp[PXB_MAX_DIRS];
         for (int k = 0; k < NDIR; ++k) grp[k] = p[k][j];
-        pxb_dual_prox_group<T>(pxb_hkind<S>(q), NDIR, q.lam, q.sigma, grp);
+        if (!PXB_EXP(16)) pxb_dual_prox_group<T>(pxb_hkind<S>(q), NDIR, q.lam, q.sigma, grp);
         for (int k = 0; k < NDIR; ++k) {
             const T zn = q.one_m_rho * zo[k][j] + q.rho * grp[k];
             if (NORMS && !PXB_EXP(4)) {

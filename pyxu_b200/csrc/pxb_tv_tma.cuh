@@ -390,7 +390,7 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             rs = pxb_rim_src(top ? it.r0 - 1 : it.r0 + TY, g.nR, q.mode[1], it.r0, TY, true);
             if (rs != PXB_NOSRC) brs = rs - (it.r0 - 1);
         }
-        if (own && need) {
+        if (own && need && !PXB_EXP(32)) {
             const int r = top ? it.r0 - 1 : it.r0 + TY, c = it.c0 + cl;
             T wv[VEC], z0c[VEC], z1c[VEC], z2c[VEC], xo[VEC], un[VEC], uo[VEC];
             if (MODES) {

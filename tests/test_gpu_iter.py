@@ -304,3 +304,79 @@ def test_iter_random_small_shapes(env, form, iter_path):
         algo = K.ALGO_PD3O if trial % 2 == 0 else K.ALGO_CV
         a, b = both_forms(env, algo, Kop, batch, dtype, P, seed=trial)
         assert_same(env, algo, a, b, 1e-12 if dtype == torch.float64 else 3e-6)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("algo", ["pd3o", "cv"])
+def test_small_2d_batch_is_one_cooperative_launch(env, dtype, algo):
+    """pxb_pds_iter_n on an image whose tiles are all resident at once: ONE launch for the n iterations (k_tv_tile2d_loop, grid-wide
+    barrier between iterations) -- the iterate, the per-iteration RelError sums and the device-side stop are those of n single launches;
+    an image too large for that, and a folding boundary mode, keep one launch per iteration."""
+    K, lib = env.K, env.lib
+    tdt, ndt, kdt = (torch.float64, np.float64, K.F64) if dtype == "f64" else (torch.float32, np.float32, K.F32)
+    A_ = K.ALGO_PD3O if algo == "pd3o" else K.ALGO_CV
+    n = 37
+
+    def problem(shape, mode="constant"):
+        N = int(np.prod(shape))
+        g = torch.Generator(device="cpu").manual_seed(3)
+        y = torch.rand(N, generator=g, dtype=tdt).to(DEV)
+        shift = -y
+        P = params(K, 0.28, 0.28, 1.2, (K.PROX_POS, 0.0, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L21, 0.1)
+        d = env.operator.Gradient(arg_shape=shape, dtype=ndt, mode=mode)._desc(1, kdt)
+        zi = (0.05 * torch.randn(2 * N, generator=g, dtype=tdt)).to(DEV)  # (z0 != 0: with z0 = 0 the first x equals x0 and RelError[x] is met at once)
+        st = lambda: (y.clone(), torch.empty_like(y), zi.clone(), torch.empty(2 * N, device=DEV, dtype=tdt), y.clone())
+        return N, P, d, st, (y, shift)
+
+    N, P, d, st, keep = problem((200, 264))
+    # (a) no rule: n plain iterations
+    u0, u1, z0, z1, x = st()
+    c0 = lib.pxb_launch_count()
+    K.check(lib.pxb_pds_iter_n(A_, C.byref(d), C.byref(P), u0.data_ptr(), z0.data_ptr(), u1.data_ptr(), z1.data_ptr(), None, None, n, None, None, None), "iter_n")
+    assert lib.pxb_launch_count() - c0 == 1, "the batch must be one launch"
+    ra_u, ra_z = (u1, z1) if n % 2 else (u0, z0)
+    v0, v1, w0, w1, _ = st()
+    a, b = (v0, w0), (v1, w1)
+    for _ in range(n):
+        K.check(lib.pxb_pds_iter(A_, C.byref(d), C.byref(P), a[0].data_ptr(), a[1].data_ptr(), b[0].data_ptr(), b[1].data_ptr(), None, None, None, None), "iter")
+        a, b = b, a
+    _sync()
+    assert torch.equal(ra_u, a[0]) and torch.equal(ra_z, a[1])
+    # (b) with the device-side rule: sums of every iteration, stop at the iteration where RelError[z] <= eps
+    rule = K.StopRule()
+    rule.eps_x, rule.eps_z, rule.all_x, rule.all_z = (1e-30 if algo == "pd3o" else 0.0), 0.05, 1, 1
+    rule.table = 0b1110  # bit (2*px + pz): stop when either test holds
+    u0, u1, z0, z1, x = st()
+    sums = torch.zeros(n * 4, device=DEV, dtype=torch.float64)
+    ctl = torch.zeros(4, device=DEV, dtype=torch.int32)
+    c0 = lib.pxb_launch_count()
+    K.check(lib.pxb_pds_iter_n(A_, C.byref(d), C.byref(P), u0.data_ptr(), z0.data_ptr(), u1.data_ptr(), z1.data_ptr(), x.data_ptr() if algo == "pd3o" else None,
+                               sums.data_ptr(), n, C.byref(rule), ctl.data_ptr(), None), "iter_n")
+    assert lib.pxb_launch_count() - c0 == 1
+    _sync()
+    done = int(ctl[1])
+    assert 2 <= done < n and int(ctl[0]) == 1, (done, ctl)
+    S = sums.cpu().numpy().reshape(n, 2, 1, 2)
+    assert np.sqrt(S[done - 1, 1, 0, 0]) <= 0.05 * np.sqrt(S[done - 1, 1, 0, 1]) and np.all(np.sqrt(S[: done - 1, 1, 0, 0]) > 0.05 * np.sqrt(S[: done - 1, 1, 0, 1]))
+    assert not S[done:].any()
+    # the same iterations one launch each, sums per launch
+    v0, v1, w0, w1, xx = st()
+    a, b = (v0, w0), (v1, w1)
+    for i in range(done):
+        nx = torch.zeros(2, device=DEV, dtype=torch.float64)
+        nz = torch.zeros(2, device=DEV, dtype=torch.float64)
+        K.check(lib.pxb_pds_iter(A_, C.byref(d), C.byref(P), a[0].data_ptr(), a[1].data_ptr(), b[0].data_ptr(), b[1].data_ptr(), xx.data_ptr() if algo == "pd3o" else None,
+                                 nx.data_ptr() if rule.eps_x > 0 else None, nz.data_ptr(), None), "iter")
+        a, b = b, a
+        assert np.allclose(nz.cpu().numpy(), S[i, 1, 0], rtol=1e-9 if dtype == "f64" else 1e-5)
+    got_u, got_z = (u1, z1) if done % 2 else (u0, z0)
+    assert torch.equal(got_u, a[0]) and torch.equal(got_z, a[1])
+    if algo == "pd3o":
+        assert torch.equal(x, xx)
+    # (c) too many tiles to be resident at once / a folding mode: one launch per iteration
+    for shape, mode in (((1600, 2048) if dtype == "f64" else (2048, 4096), "constant"), ((200, 264), "reflect")):
+        N2, P2, d2, st2, keep2 = problem(shape, mode)
+        u0, u1, z0, z1, x = st2()
+        c0 = lib.pxb_launch_count()
+        K.check(lib.pxb_pds_iter_n(A_, C.byref(d2), C.byref(P2), u0.data_ptr(), z0.data_ptr(), u1.data_ptr(), z1.data_ptr(), None, None, 4, None, None, None), "iter_n")
+        assert lib.pxb_launch_count() - c0 == 4, (shape, mode)
