@@ -51,6 +51,7 @@ template <class T>
 struct PxbTvP {
     T cm[PXB_MAX_DIRS], c0[PXB_MAX_DIRS], cp[PXB_MAX_DIRS];
     T tau, sigma, rho, one_m_rho, lam, two_alpha, gp0, gp1;
+    int rho1;  // rho == 1 (the reference's default): the relaxation (1-rho) old + rho new IS new -- the tiled forms skip its arithmetic
     int gkind, fkind, hkind, shift_mode;
     const T* shift;
     const T* garr;
@@ -93,7 +94,7 @@ PXB_HD void pxb_tv_prepare(const pxb_grad_desc& d, const PxbTvCoef& cf, const px
     for (int k = 0; k < PXB_MAX_DIRS; ++k) {
         q.cm[k] = T(cf.cm[k]); q.c0[k] = T(cf.c0[k]); q.cp[k] = T(cf.cp[k]);
     }
-    q.tau = T(P.tau); q.sigma = T(P.sigma); q.rho = T(P.rho); q.one_m_rho = T(1) - q.rho;
+    q.tau = T(P.tau); q.sigma = T(P.sigma); q.rho = T(P.rho); q.one_m_rho = T(1) - q.rho; q.rho1 = P.rho == 1.0 ? 1 : 0;
     q.lam = T(P.lam); q.two_alpha = T(2 * P.f.alpha); q.gp0 = T(P.g.p0); q.gp1 = T(P.g.p1);
     q.gkind = P.g.kind; q.fkind = P.f.kind; q.hkind = P.hkind;
     const PxbGeom g = pxb_geom(d.shape);

@@ -461,16 +461,18 @@ PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
         T grp[PXB_MAX_DIRS];
         for (int k = 0; k < NDIR; ++k) grp[k] = p[k][j];
         if (!PXB_EXP(16)) pxb_dual_prox_group<T>(pxb_hkind<S>(q), NDIR, q.lam, q.sigma, grp);
-        for (int k = 0; k < NDIR; ++k) {
-            const T zn = q.one_m_rho * zo[k][j] + q.rho * grp[k];
-            if (NORMS && !PXB_EXP(4)) {
-                const T dd = zn - zo[k][j];
+        for (int k = 0; k < NDIR; ++k) p[k][j] = grp[k];
+    }
+    if (!q.rho1)  // (uniform; rho == 1: (1 - rho) z + rho p is p, bit for bit)
+        for (int k = 0; k < NDIR; ++k)
+            for (int j = 0; j < VEC; ++j) p[k][j] = q.one_m_rho * zo[k][j] + q.rho * p[k][j];
+    if (NORMS && !PXB_EXP(4))
+        for (int k = 0; k < NDIR; ++k)
+            for (int j = 0; j < VEC; ++j) {
+                const T dd = p[k][j] - zo[k][j];
                 a0 += dd * dd;
                 a1 += zo[k][j] * zo[k][j];
             }
-            p[k][j] = zn;
-        }
-    }
     T* __restrict__ zb = zb_at ? zb_at : a.z_out + it.z_base + (int64_t)mm * g.sM + (int64_t)r * g.sR + c;
     // peer-memory exchange: the first owned plane of every component goes down, the last one of component 0 goes up
     // (the plane tests first: they are uniform and almost never true)

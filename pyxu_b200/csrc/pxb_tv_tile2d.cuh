@@ -74,7 +74,7 @@ PXB_HD void pxb_t2_w(const PxbTvP<T>& q, const PxbT2Geom& g, const T* __restrict
             const T gf = (q.fkind == PXB_F_SQL2) ? (x + sh.v[j]) * q.two_alpha : T(0);
             const T ut = x - q.tau * gf;
             wv[j] = x + ut - old.v[j];
-            un[j] = q.one_m_rho * old.v[j] + q.rho * ut;
+            un[j] = ut;
             xo[j] = x;
         } else {
             T gf = T(0);
@@ -82,10 +82,13 @@ PXB_HD void pxb_t2_w(const PxbTvP<T>& q, const PxbT2Geom& g, const T* __restrict
             else if (q.fkind == PXB_F_GRADARR) gf = sh.v[j];
             const T xt = pxb_prox_eval<T>(gk, q.gp0, q.gp1, old.v[j] - q.tau * gf - q.tau * kz[j], q.tau);
             wv[j] = T(2) * xt - old.v[j];
-            un[j] = q.rho * xt + q.one_m_rho * old.v[j];
-            xo[j] = un[j];
+            un[j] = xt;
         }
     }
+    if (!q.rho1)  // (uniform; rho == 1: the relaxed iterate IS the new one, bit for bit)
+        for (int j = 0; j < W; ++j) un[j] = q.one_m_rho * old.v[j] + q.rho * un[j];
+    if (ALGO != PXB_PD3O)
+        for (int j = 0; j < W; ++j) xo[j] = un[j];
 }
 
 struct PxbT2Item {
@@ -237,14 +240,20 @@ PXB_HD void pxb_t2_phaseC(const PxbTvP<T>& q, const PxbT2Geom& g, const PxbT2Ite
         for (int j = 0; j < VEC; ++j) {
             T grp[PXB_MAX_DIRS] = {p[0][j], p[1][j], T(0)};
             pxb_dual_prox_group<T>(pxb_hkind<S>(q), 2, q.lam, q.sigma, grp);
-            o0.v[j] = q.one_m_rho * z0.v[j] + q.rho * grp[0];
-            o1.v[j] = q.one_m_rho * z1.v[j] + q.rho * grp[1];
-            if (NORMS) {
+            o0.v[j] = grp[0];
+            o1.v[j] = grp[1];
+        }
+        if (!q.rho1)  // (uniform; rho == 1: (1 - rho) z + rho p is p, bit for bit)
+            for (int j = 0; j < VEC; ++j) {
+                o0.v[j] = q.one_m_rho * z0.v[j] + q.rho * o0.v[j];
+                o1.v[j] = q.one_m_rho * z1.v[j] + q.rho * o1.v[j];
+            }
+        if (NORMS)
+            for (int j = 0; j < VEC; ++j) {
                 const T d0 = o0.v[j] - z0.v[j], d1 = o1.v[j] - z1.v[j];
                 a0 += d0 * d0 + d1 * d1;
                 a1 += z0.v[j] * z0.v[j] + z1.v[j] * z1.v[j];
             }
-        }
         if (NORMS) { acc[2] += (double)a0; acc[3] += (double)a1; }
         T* __restrict__ zb = a.z_out + it.b * 2 * g.vol + (int64_t)it.i0 * g.s0 + (int64_t)r * g.n2 + c;
         pxb_vstore<T, VEC>(zb, o0);

@@ -248,7 +248,7 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
             const T gf = (S::FK == 1 || q.fkind == PXB_F_SQL2) ? (x + sh.v[j]) * q.two_alpha : T(0);
             const T ut = x - q.tau * gf;
             wv[j] = x + ut - old.v[j];
-            un[j] = q.one_m_rho * old.v[j] + q.rho * ut;
+            un[j] = ut;
             xo[j] = x;
         } else {
             T gf = T(0);
@@ -258,10 +258,13 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
             const T vv = old.v[j] - q.tau * gf - q.tau * kz[j];
             const T xt = pxb_prox_eval<T>(gk, q.gp0, q.gp1, vv, q.tau);
             wv[j] = T(2) * xt - old.v[j];
-            un[j] = q.rho * xt + q.one_m_rho * old.v[j];
-            xo[j] = un[j];
+            un[j] = xt;
         }
     }
+    if (!q.rho1)  // (uniform; rho == 1: the relaxed iterate IS the new one, bit for bit)
+        for (int j = 0; j < W; ++j) un[j] = q.one_m_rho * old.v[j] + q.rho * un[j];
+    if (ALGO != PXB_PD3O)
+        for (int j = 0; j < W; ++j) xo[j] = un[j];
 }
 
 // z0 of plane mlo-1 at the samples whose previous-plane value this thread carries (start of a work item)
