@@ -227,6 +227,10 @@ class _PrimalDualSplitting(Solver):
         sharded_in = isinstance(x0, slab.ShardedArray)
         ctx = slab.context(True if (sharded_in and distributed is None) else distributed)
         self._stream_src = None
+        so = getattr(self, "_stream_out", None)  # a result an earlier streamed fit() of this object brought back and nobody collected
+        if so is not None and not isinstance(so[1], np.ndarray):
+            A._give_back(so[1].numel(), so[1])
+        self._stream_out = None
         if ctx is None:
             return self._m_init_streamed(x0, z0)
         required = distributed is True or sharded_in

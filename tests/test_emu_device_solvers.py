@@ -383,6 +383,18 @@ def test_streamed_fit_brings_the_result_back_behind_the_wave(dev_rt, monkeypatch
 
         gc.collect()
         assert len(A_._RESULT_POOL[y.nbytes]) == 1  # the buffer is back in the pool
+        # a second fit() of the same object: the result of the first one, had it not been collected, must not be handed out again
+        slv.fit(x0=y.copy(), stop_crit=pxst.MaxIter(5))
+        assert slv._stream_out is not None
+        slv.fit(x0=0.5 * y, stop_crit=pxst.MaxIter(5))  # (the uncollected buffer goes back to the pool, a new one is taken)
+        x2 = slv.solution()
+        ref2 = _tv3d(dev, shape, y, dtype)
+        monkeypatch.setattr(PDS, "_STREAM_MIN_BYTES", 1 << 62)
+        ref2.fit(x0=0.5 * y, stop_crit=pxst.MaxIter(5))
+        assert np.allclose(x2, ref2.solution(), rtol=1e-13, atol=1e-15) and not np.allclose(x2, x_ref)
+        del x2
+        gc.collect()
+        assert len(A_._RESULT_POOL[y.nbytes]) == 1
     finally:
         A_.release_host_results()
 
