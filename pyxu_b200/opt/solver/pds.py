@@ -662,6 +662,11 @@ class _PrimalDualSplitting(Solver):
         """x of PD3O is not written by the single-kernel iteration unless something needs it every step; rebuild it
         on demand from the previous iterate: x_k = prox_{tau g}(u_{k-1} - tau K^T z_{k-1})  (pds.py:747-750)."""
         mst = self._mstate
+        eng = getattr(self, "_slab", None)
+        if eng is not None and name in ("x", "z"):  # the iterate lives in the slab engine's buffers
+            if eng.world > 1:
+                raise NotImplementedError("under a z-slab decomposition the iterate is distributed: use stats() / solution() (they gather it)")
+            return eng.x_local().reshape(-1) if name == "x" else eng.z_local().reshape(-1)
         if name == "x" and getattr(self, "_x_stale", False):
             u_prev, z_prev = self._plan.alt
             ktz = self._K.jacobian(u_prev).adjoint(z_prev)

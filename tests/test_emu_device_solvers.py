@@ -383,6 +383,7 @@ def test_streamed_fit_brings_the_result_back_behind_the_wave(dev_rt, monkeypatch
 
         gc.collect()
         assert len(A_._RESULT_POOL[y.nbytes]) == 1  # the buffer is back in the pool
+        assert np.isclose(float(slv.objective_func()), float(ref.objective_func()), rtol=1e-12)  # the public objective on the streamed state
         # a second fit() of the same object: the result of the first one, had it not been collected, must not be handed out again
         slv.fit(x0=y.copy(), stop_crit=pxst.MaxIter(5))
         assert slv._stream_out is not None
