@@ -402,6 +402,72 @@ PXB_HD void pxb_iter_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
 #undef PXB_I1
 }
 
+#if defined(__CUDA_ARCH__)
+// ---------------------------------------------------------------------------------------------------------
+// Packed form of phase C for the headline instances (fp32, 4 samples per thread, three forward differences, L21, rho == 1):
+// the same update on PAIRS of samples -- fma.rn.f32x2 / mul.rn.f32x2 (FFMA2 / FMUL2) -- with sigma folded into the tap
+// coefficients.  Why: the kernel is HBM-bound in bursts but draws the board's power cap when it runs for more than a second; the SM
+// clock then falls to ~1.5 GHz and its ~110 instructions per voxel no longer hide under the memory time (5.8 instead of 6.5 TB/s,
+// tools/probe_sustained.py).  43 % of those instructions are fp32 arithmetic on vectors whose lanes share their coefficients.
+// Results differ from the scalar body in the last bits (sigma * (c0 w + cp w') against (sigma c0) w + (sigma cp) w').
+// ---------------------------------------------------------------------------------------------------------
+template <int TXL, int TY, bool NORMS>
+static __device__ __forceinline__ void pxb_iter_phaseC_f32x2(const PxbTvP<float>& q, const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<float>& a,
+                                                               int tid, int mm, const float* smem, const float (*zo)[4], double* acc, float* zb_at) {
+    using C = PxbIterCfg<float, 4, TXL, TY, 3>;
+    const int rl = tid / TXL, cl = (tid - rl * TXL) * 4;
+    const int r = it.r0 + rl, c = it.c0 + cl;
+    if (!it.full && (r >= g.nR || c >= g.nC)) return;
+    const int cell = (rl + C::R0) * C::RS + cl + 4;
+    const float* __restrict__ s1 = smem + (mm & 3) * C::SLOT + cell;
+    const float4 wc = *reinterpret_cast<const float4*>(s1);
+    const float4 wm = *reinterpret_cast<const float4*>(smem + ((mm + 1) & 3) * C::SLOT + cell);  // next plane
+    const float4 wr = *reinterpret_cast<const float4*>(s1 + C::RS);                               // next row
+    const float hi = s1[4];                                                                      // next column of the last sample
+    const float aM = q.sigma * q.c0[0], bM = q.sigma * q.cp[0], aR = q.sigma * q.c0[1], bR = q.sigma * q.cp[1], aC = q.sigma * q.c0[2], bC = q.sigma * q.cp[2];
+    const float2 aM2 = make_float2(aM, aM), bM2 = make_float2(bM, bM), aR2 = make_float2(aR, aR), bR2 = make_float2(bR, bR), aC2 = make_float2(aC, aC),
+                 bC2 = make_float2(bC, bC);
+    const float2 wcl = make_float2(wc.x, wc.y), wch = make_float2(wc.z, wc.w);
+    float2 p0l = __ffma2_rn(bM2, make_float2(wm.x, wm.y), __ffma2_rn(aM2, wcl, make_float2(zo[0][0], zo[0][1])));
+    float2 p0h = __ffma2_rn(bM2, make_float2(wm.z, wm.w), __ffma2_rn(aM2, wch, make_float2(zo[0][2], zo[0][3])));
+    float2 p1l = __ffma2_rn(bR2, make_float2(wr.x, wr.y), __ffma2_rn(aR2, wcl, make_float2(zo[1][0], zo[1][1])));
+    float2 p1h = __ffma2_rn(bR2, make_float2(wr.z, wr.w), __ffma2_rn(aR2, wch, make_float2(zo[1][2], zo[1][3])));
+    float2 p2l = __ffma2_rn(bC2, make_float2(wc.y, wc.z), __ffma2_rn(aC2, wcl, make_float2(zo[2][0], zo[2][1])));
+    float2 p2h = __ffma2_rn(bC2, make_float2(wc.w, hi), __ffma2_rn(aC2, wch, make_float2(zo[2][2], zo[2][3])));
+    const float2 nl = __ffma2_rn(p2l, p2l, __ffma2_rn(p1l, p1l, __fmul2_rn(p0l, p0l)));
+    const float2 nh = __ffma2_rn(p2h, p2h, __ffma2_rn(p1h, p1h, __fmul2_rn(p0h, p0h)));
+    const float2 sl = make_float2(fminf(1.0f, q.lam * rsqrtf(nl.x)), fminf(1.0f, q.lam * rsqrtf(nl.y)));
+    const float2 sh = make_float2(fminf(1.0f, q.lam * rsqrtf(nh.x)), fminf(1.0f, q.lam * rsqrtf(nh.y)));
+    p0l = __fmul2_rn(p0l, sl); p0h = __fmul2_rn(p0h, sh);
+    p1l = __fmul2_rn(p1l, sl); p1h = __fmul2_rn(p1h, sh);
+    p2l = __fmul2_rn(p2l, sl); p2h = __fmul2_rn(p2h, sh);
+    if (NORMS) {
+        float a0 = 0.f, a1 = 0.f;
+        const float2 pz[3][2] = {{p0l, p0h}, {p1l, p1h}, {p2l, p2h}};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float d0 = pz[k][0].x - zo[k][0], d1 = pz[k][0].y - zo[k][1], d2 = pz[k][1].x - zo[k][2], d3 = pz[k][1].y - zo[k][3];
+            a0 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            a1 += zo[k][0] * zo[k][0] + zo[k][1] * zo[k][1] + zo[k][2] * zo[k][2] + zo[k][3] * zo[k][3];
+        }
+        acc[2] += (double)a0;
+        acc[3] += (double)a1;
+    }
+    float* __restrict__ zb = zb_at ? zb_at : a.z_out + it.z_base + (int64_t)mm * g.sM + (int64_t)r * g.sR + c;
+    const float4 o0 = make_float4(p0l.x, p0l.y, p0h.x, p0h.y), o1 = make_float4(p1l.x, p1l.y, p1h.x, p1h.y), o2 = make_float4(p2l.x, p2l.y, p2h.x, p2h.y);
+    *reinterpret_cast<float4*>(zb) = o0;
+    *reinterpret_cast<float4*>(zb + g.vol) = o1;
+    *reinterpret_cast<float4*>(zb + 2 * g.vol) = o2;
+    if (mm == 0 && a.peer.dn_z != nullptr) {  // peer-memory exchange: the first owned plane of every component goes down ...
+        float* pd = a.peer.dn_z + (int64_t)r * g.sR + c;
+        *reinterpret_cast<float4*>(pd) = o0;
+        *reinterpret_cast<float4*>(pd + a.peer.dn_zvol) = o1;
+        *reinterpret_cast<float4*>(pd + 2 * a.peer.dn_zvol) = o2;
+    }
+    if (mm == g.nM - 1 && a.peer.up_z0 != nullptr) *reinterpret_cast<float4*>(a.peer.up_z0 + (int64_t)r * g.sR + c) = o0;  // ... the last one of component 0 up
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 // phase C of plane mm: z_out(mm) = (1-rho) z + rho prox_{sigma h*}(z + sigma K w) for the tile, w from the ring,
 // z (old) from `zo` (registers).
@@ -412,6 +478,14 @@ PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
     // zb_at: z_out at this thread's samples on plane mm, component 0, when the caller keeps a running pointer (saves the 64-bit
     // index arithmetic per plane: 19 of the 463 warp instructions per plane of the TMA form)
     using C = PxbIterCfg<T, VEC, TXL, TY, NDIR>;
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4 && VEC == 4 && NDIR == 3 && S::SCHEME == PXB_SCHEME_FWD && S::HK == PXB_DUAL_L21) {
+        if (q.rho1 && !PXB_EXP(64)) {  // (uniform)
+            pxb_iter_phaseC_f32x2<TXL, TY, NORMS>(q, g, it, a, tid, mm, smem, zo, acc, zb_at);
+            return;
+        }
+    }
+#endif
     const int rl = tid / TXL, cx = tid - rl * TXL, cl = cx * VEC;
     const int r = it.r0 + rl, c = it.c0 + cl;
     if (!it.full && (r >= g.nR || c >= g.nC)) return;
