@@ -198,6 +198,53 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
                       int f1 = 0, int f2 = 0, const PxbTmaFold* fb = nullptr) {
     using C = PxbTmaCfg<T, VEC, TY>;
     const int i = br * C::BW + bc, i1 = (br + 1) * C::BW + bc;
+#if defined(__CUDA_ARCH__)
+    // Packed form for the headline instances (fp32 vectors of the tile's own samples, PD3O, three forward differences, per-voxel
+    // shifted squared-l2 data term, g = positivity | none, rho == 1): the same arithmetic on pairs of samples (fma / mul / add.f32x2),
+    // -tau folded into the taps of K^T z, and x - tau grad f(x) = (1 - 2 alpha tau) x - 2 alpha tau shift.  See pxb_iter_phaseC_f32x2.
+    if constexpr (sizeof(T) == 4 && W == 4 && VEC == 4 && ALGO == PXB_PD3O && S::SCHEME == PXB_SCHEME_FWD && S::FK == 1 &&
+                  (S::GK == PXB_PROX_POS || S::GK == PXB_PROX_NONE) && !MODES) {
+        if (q.rho1 && !PXB_EXP(64)) {  // (uniform)
+            const float4 c0v = *reinterpret_cast<const float4*>(st + C::OFF_Z0 + i);
+            const float4 c1v = *reinterpret_cast<const float4*>(st + C::OFF_Z1 + i1);
+            const float4 n1v = *reinterpret_cast<const float4*>(st + C::OFF_Z1 + i1 - C::BW);
+            const float4 c2v = *reinterpret_cast<const float4*>(st + C::OFF_Z2 + i);
+            const float lo = st[C::OFF_Z2 + i - 1];
+            const float4 old = *reinterpret_cast<const float4*>(st + C::OFF_U + i);
+            const float4 shv = *reinterpret_cast<const float4*>(st + C::OFF_S + i);
+            const float mt = -q.tau;
+            const float t00 = mt * q.c0[0], t0p = mt * q.cp[0], t10 = mt * q.c0[1], t1p = mt * q.cp[1], t20 = mt * q.c0[2], t2p = mt * q.cp[2];
+            const float a2 = mt * q.two_alpha, a1 = 1.0f + a2;
+            auto d2 = [](float v) { return make_float2(v, v); };
+            float2 vl = __ffma2_rn(d2(t00), make_float2(c0v.x, c0v.y), make_float2(old.x, old.y));
+            float2 vh = __ffma2_rn(d2(t00), make_float2(c0v.z, c0v.w), make_float2(old.z, old.w));
+            vl = __ffma2_rn(d2(t0p), make_float2(z0p[0], z0p[1]), vl);
+            vh = __ffma2_rn(d2(t0p), make_float2(z0p[2], z0p[3]), vh);
+            vl = __ffma2_rn(d2(t10), make_float2(c1v.x, c1v.y), vl);
+            vh = __ffma2_rn(d2(t10), make_float2(c1v.z, c1v.w), vh);
+            vl = __ffma2_rn(d2(t1p), make_float2(n1v.x, n1v.y), vl);
+            vh = __ffma2_rn(d2(t1p), make_float2(n1v.z, n1v.w), vh);
+            vl = __ffma2_rn(d2(t20), make_float2(c2v.x, c2v.y), vl);
+            vh = __ffma2_rn(d2(t20), make_float2(c2v.z, c2v.w), vh);
+            vl = __ffma2_rn(d2(t2p), make_float2(lo, c2v.x), vl);
+            vh = __ffma2_rn(d2(t2p), make_float2(c2v.y, c2v.z), vh);
+            float2 xl = vl, xh = vh;
+            if (S::GK == PXB_PROX_POS) { xl = make_float2(fmaxf(vl.x, 0.f), fmaxf(vl.y, 0.f)); xh = make_float2(fmaxf(vh.x, 0.f), fmaxf(vh.y, 0.f)); }
+            const float2 ul = __ffma2_rn(d2(a1), xl, __fmul2_rn(d2(a2), make_float2(shv.x, shv.y)));
+            const float2 uh = __ffma2_rn(d2(a1), xh, __fmul2_rn(d2(a2), make_float2(shv.z, shv.w)));
+            const float2 wl = __ffma2_rn(d2(-1.0f), make_float2(old.x, old.y), __fadd2_rn(xl, ul));
+            const float2 wh = __ffma2_rn(d2(-1.0f), make_float2(old.z, old.w), __fadd2_rn(xh, uh));
+            wv[0] = wl.x; wv[1] = wl.y; wv[2] = wh.x; wv[3] = wh.y;
+            un[0] = ul.x; un[1] = ul.y; un[2] = uh.x; un[3] = uh.y;
+            xo[0] = xl.x; xo[1] = xl.y; xo[2] = xh.x; xo[3] = xh.y;
+            uold[0] = old.x; uold[1] = old.y; uold[2] = old.z; uold[3] = old.w;
+            z0c[0] = c0v.x; z0c[1] = c0v.y; z0c[2] = c0v.z; z0c[3] = c0v.w;
+            z1c[0] = c1v.x; z1c[1] = c1v.y; z1c[2] = c1v.z; z1c[3] = c1v.w;
+            z2c[0] = c2v.x; z2c[1] = c2v.y; z2c[2] = c2v.z; z2c[3] = c2v.w;
+            return;
+        }
+    }
+#endif
     T kz[W];
     {   // along M: (K^T z)[s] = cm z[s+e] + c0 z[s] + cp z[s-e]
         const PxbVec<T, W> c = pxb_vload<T, W>(st + C::OFF_Z0 + i);
