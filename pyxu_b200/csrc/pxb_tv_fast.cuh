@@ -63,6 +63,10 @@ struct PxbTvP {
     // Folding boundary modes, per AXIS (see pxb_tv_fold_kz): the sample whose K^T z gains cp*z[n-1] (fold_hi) / cm*z[0]
     // (fold_lo) on top of the 'constant' arithmetic; PXB_NOSRC when the axis does not fold or the tap is absent.
     int fold_hi[3], fold_lo[3];
+    // Packed fp32 forms (pxb_iter_phaseC_f32x2, pxb_tma_w): the folded coefficients as (c, c) pairs, read by FFMA2 / FMUL2 as
+    // uniform-register operands straight from the constant bank (computed per call and per thread they were 7 % of the instructions):
+    // [0..2] sigma*c0[k], [3..5] sigma*cp[k], [6..8] -tau*c0[k], [9..11] -tau*cp[k], [12] 1 - 2 alpha tau, [13] -2 alpha tau, [14] -1
+    alignas(8) T pk[15][2];
 };
 
 
@@ -96,6 +100,15 @@ PXB_HD void pxb_tv_prepare(const pxb_grad_desc& d, const PxbTvCoef& cf, const px
     }
     q.tau = T(P.tau); q.sigma = T(P.sigma); q.rho = T(P.rho); q.one_m_rho = T(1) - q.rho; q.rho1 = P.rho == 1.0 ? 1 : 0;
     q.lam = T(P.lam); q.two_alpha = T(2 * P.f.alpha); q.gp0 = T(P.g.p0); q.gp1 = T(P.g.p1);
+    {
+        T v[15];
+        for (int k = 0; k < 3; ++k) {
+            v[k] = q.sigma * q.c0[k]; v[3 + k] = q.sigma * q.cp[k];
+            v[6 + k] = -q.tau * q.c0[k]; v[9 + k] = -q.tau * q.cp[k];
+        }
+        v[13] = -q.tau * q.two_alpha; v[12] = T(1) + v[13]; v[14] = T(-1);
+        for (int i = 0; i < 15; ++i) q.pk[i][0] = q.pk[i][1] = v[i];
+    }
     q.gkind = P.g.kind; q.fkind = P.f.kind; q.hkind = P.hkind;
     const PxbGeom g = pxb_geom(d.shape);
     q.n0 = g.n0; q.n1 = g.n1; q.n2 = g.n2; q.s0 = g.s0; q.s1 = g.s1;

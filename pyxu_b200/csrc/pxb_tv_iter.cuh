@@ -424,9 +424,8 @@ static __device__ __forceinline__ void pxb_iter_phaseC_f32x2(const PxbTvP<float>
     const float4 wm = *reinterpret_cast<const float4*>(smem + ((mm + 1) & 3) * C::SLOT + cell);  // next plane
     const float4 wr = *reinterpret_cast<const float4*>(s1 + C::RS);                               // next row
     const float hi = s1[4];                                                                      // next column of the last sample
-    const float aM = q.sigma * q.c0[0], bM = q.sigma * q.cp[0], aR = q.sigma * q.c0[1], bR = q.sigma * q.cp[1], aC = q.sigma * q.c0[2], bC = q.sigma * q.cp[2];
-    const float2 aM2 = make_float2(aM, aM), bM2 = make_float2(bM, bM), aR2 = make_float2(aR, aR), bR2 = make_float2(bR, bR), aC2 = make_float2(aC, aC),
-                 bC2 = make_float2(bC, bC);
+    auto pk = [&](int i) { return *reinterpret_cast<const float2*>(q.pk[i]); };  // (c, c) pairs folded on the host
+    const float2 aM2 = pk(0), aR2 = pk(1), aC2 = pk(2), bM2 = pk(3), bR2 = pk(4), bC2 = pk(5);
     const float2 wcl = make_float2(wc.x, wc.y), wch = make_float2(wc.z, wc.w);
     float2 p0l = __ffma2_rn(bM2, make_float2(wm.x, wm.y), __ffma2_rn(aM2, wcl, make_float2(zo[0][0], zo[0][1])));
     float2 p0h = __ffma2_rn(bM2, make_float2(wm.z, wm.w), __ffma2_rn(aM2, wch, make_float2(zo[0][2], zo[0][3])));

@@ -212,28 +212,26 @@ PXB_HD void pxb_tma_w(const PxbTvP<T>& q, const PxbTmaGeom& tg, const T* __restr
             const float lo = st[C::OFF_Z2 + i - 1];
             const float4 old = *reinterpret_cast<const float4*>(st + C::OFF_U + i);
             const float4 shv = *reinterpret_cast<const float4*>(st + C::OFF_S + i);
-            const float mt = -q.tau;
-            const float t00 = mt * q.c0[0], t0p = mt * q.cp[0], t10 = mt * q.c0[1], t1p = mt * q.cp[1], t20 = mt * q.c0[2], t2p = mt * q.cp[2];
-            const float a2 = mt * q.two_alpha, a1 = 1.0f + a2;
-            auto d2 = [](float v) { return make_float2(v, v); };
-            float2 vl = __ffma2_rn(d2(t00), make_float2(c0v.x, c0v.y), make_float2(old.x, old.y));
-            float2 vh = __ffma2_rn(d2(t00), make_float2(c0v.z, c0v.w), make_float2(old.z, old.w));
-            vl = __ffma2_rn(d2(t0p), make_float2(z0p[0], z0p[1]), vl);
-            vh = __ffma2_rn(d2(t0p), make_float2(z0p[2], z0p[3]), vh);
-            vl = __ffma2_rn(d2(t10), make_float2(c1v.x, c1v.y), vl);
-            vh = __ffma2_rn(d2(t10), make_float2(c1v.z, c1v.w), vh);
-            vl = __ffma2_rn(d2(t1p), make_float2(n1v.x, n1v.y), vl);
-            vh = __ffma2_rn(d2(t1p), make_float2(n1v.z, n1v.w), vh);
-            vl = __ffma2_rn(d2(t20), make_float2(c2v.x, c2v.y), vl);
-            vh = __ffma2_rn(d2(t20), make_float2(c2v.z, c2v.w), vh);
-            vl = __ffma2_rn(d2(t2p), make_float2(lo, c2v.x), vl);
-            vh = __ffma2_rn(d2(t2p), make_float2(c2v.y, c2v.z), vh);
+            auto pk = [&](int i) { return *reinterpret_cast<const float2*>(q.pk[i]); };  // (c, c) pairs folded on the host
+            const float2 t00 = pk(6), t10 = pk(7), t20 = pk(8), t0p = pk(9), t1p = pk(10), t2p = pk(11), a1 = pk(12), a2 = pk(13), m1 = pk(14);
+            float2 vl = __ffma2_rn(t00, make_float2(c0v.x, c0v.y), make_float2(old.x, old.y));
+            float2 vh = __ffma2_rn(t00, make_float2(c0v.z, c0v.w), make_float2(old.z, old.w));
+            vl = __ffma2_rn(t0p, make_float2(z0p[0], z0p[1]), vl);
+            vh = __ffma2_rn(t0p, make_float2(z0p[2], z0p[3]), vh);
+            vl = __ffma2_rn(t10, make_float2(c1v.x, c1v.y), vl);
+            vh = __ffma2_rn(t10, make_float2(c1v.z, c1v.w), vh);
+            vl = __ffma2_rn(t1p, make_float2(n1v.x, n1v.y), vl);
+            vh = __ffma2_rn(t1p, make_float2(n1v.z, n1v.w), vh);
+            vl = __ffma2_rn(t20, make_float2(c2v.x, c2v.y), vl);
+            vh = __ffma2_rn(t20, make_float2(c2v.z, c2v.w), vh);
+            vl = __ffma2_rn(t2p, make_float2(lo, c2v.x), vl);
+            vh = __ffma2_rn(t2p, make_float2(c2v.y, c2v.z), vh);
             float2 xl = vl, xh = vh;
             if (S::GK == PXB_PROX_POS) { xl = make_float2(fmaxf(vl.x, 0.f), fmaxf(vl.y, 0.f)); xh = make_float2(fmaxf(vh.x, 0.f), fmaxf(vh.y, 0.f)); }
-            const float2 ul = __ffma2_rn(d2(a1), xl, __fmul2_rn(d2(a2), make_float2(shv.x, shv.y)));
-            const float2 uh = __ffma2_rn(d2(a1), xh, __fmul2_rn(d2(a2), make_float2(shv.z, shv.w)));
-            const float2 wl = __ffma2_rn(d2(-1.0f), make_float2(old.x, old.y), __fadd2_rn(xl, ul));
-            const float2 wh = __ffma2_rn(d2(-1.0f), make_float2(old.z, old.w), __fadd2_rn(xh, uh));
+            const float2 ul = __ffma2_rn(a1, xl, __fmul2_rn(a2, make_float2(shv.x, shv.y)));
+            const float2 uh = __ffma2_rn(a1, xh, __fmul2_rn(a2, make_float2(shv.z, shv.w)));
+            const float2 wl = __ffma2_rn(m1, make_float2(old.x, old.y), __fadd2_rn(xl, ul));
+            const float2 wh = __ffma2_rn(m1, make_float2(old.z, old.w), __fadd2_rn(xh, uh));
             wv[0] = wl.x; wv[1] = wl.y; wv[2] = wh.x; wv[3] = wh.y;
             un[0] = ul.x; un[1] = ul.y; un[2] = uh.x; un[3] = uh.y;
             xo[0] = xl.x; xo[1] = xl.y; xo[2] = xh.x; xo[3] = xh.y;
