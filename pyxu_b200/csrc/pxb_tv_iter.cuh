@@ -147,6 +147,8 @@ struct PxbIterItem {
     int m0, m1, r0, c0;
     int si;            // image index inside the batch item (NDIR == 2: its axis-0 coordinate)
     int full;          // the tile lies entirely inside the image (no row / column tests for its own samples)
+    int nopeer;        // 1: the launch carries no peer-memory exchange at all (set by the kernel once per thread block: the per-plane tests
+                       // of the three peer pointers were 4 % of the instructions); 0: test the pointers
 };
 
 template <class T, int VEC, int TXL, int TY, int NDIR>
@@ -228,6 +230,7 @@ PXB_HD PxbIterItem pxb_iter_item(const PxbIterGeom& g, int64_t blk, int ty, int 
     it.r0 = tR * ty;
     it.c0 = tC * t2;
     it.full = (it.r0 + ty <= g.nR && it.c0 + t2 <= g.nC) ? 1 : 0;
+    it.nopeer = 0;
     return it;
 }
 
@@ -457,6 +460,7 @@ static __device__ __forceinline__ void pxb_iter_phaseC_f32x2(const PxbTvP<float>
     *reinterpret_cast<float4*>(zb) = o0;
     *reinterpret_cast<float4*>(zb + g.vol) = o1;
     *reinterpret_cast<float4*>(zb + 2 * g.vol) = o2;
+    if (it.nopeer) return;
     if (mm == 0 && a.peer.dn_z != nullptr) {  // peer-memory exchange: the first owned plane of every component goes down ...
         float* pd = a.peer.dn_z + (int64_t)r * g.sR + c;
         *reinterpret_cast<float4*>(pd) = o0;
@@ -549,7 +553,7 @@ PXB_HD void pxb_iter_phaseC(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbI
     T* __restrict__ zb = zb_at ? zb_at : a.z_out + it.z_base + (int64_t)mm * g.sM + (int64_t)r * g.sR + c;
     // peer-memory exchange: the first owned plane of every component goes down, the last one of component 0 goes up
     // (the plane tests first: they are uniform and almost never true)
-    const bool dn = NDIR == 3 && mm == 0 && a.peer.dn_z != nullptr, up = NDIR == 3 && mm == g.nM - 1 && a.peer.up_z0 != nullptr;
+    const bool dn = NDIR == 3 && !it.nopeer && mm == 0 && a.peer.dn_z != nullptr, up = NDIR == 3 && !it.nopeer && mm == g.nM - 1 && a.peer.up_z0 != nullptr;
     for (int k = 0; k < NDIR; ++k) {
         PxbVec<T, VEC> o;
         for (int j = 0; j < VEC; ++j) o.v[j] = p[k][j];

@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(32 * TY, 2)
     T* ring = reinterpret_cast<T*>(pxb_tma_smem + C::SMEM_STAGES);
     uint64_t* full = reinterpret_cast<uint64_t*>(pxb_tma_smem + C::SMEM_STAGES + C::SMEM_RING);
 
-    const PxbIterItem it = pxb_iter_item(g, (int64_t)blockIdx.x, TY, C::T2);
+    PxbIterItem it = pxb_iter_item(g, (int64_t)blockIdx.x, TY, C::T2);
+    it.nopeer = (a.peer.dn_u == nullptr && a.peer.dn_z == nullptr && a.peer.up_z0 == nullptr) ? 1 : 0;
     const PxbIterRange R = pxb_iter_range<T>(q, it);
     const int tid = threadIdx.x;
     const bool need_next = pxb_has_cm<S>(q, 0);          // phase A of plane m reads z0 of plane m+1

@@ -385,7 +385,9 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
         if (fold) pxb_tv_w_outside<T, VEC, 3, ALGO>(q, a.u_in, a.z_in, it.b, m, r, c, wv);
         const bool keep = fold || in;
         PxbVec<T, VEC> o;
-        for (int j = 0; j < VEC; ++j) o.v[j] = keep ? wv[j] : T(0);
+        for (int j = 0; j < VEC; ++j) o.v[j] = wv[j];
+        if (!keep)  // (never taken on a full tile and an in-domain plane)
+            for (int j = 0; j < VEC; ++j) o.v[j] = T(0);
         pxb_vstore<T, VEC>(slot + (rl + 1) * R::RS + cl + VEC, o);
         const int64_t lin = th.lin;  // (= it.lin_base + m * g.sM + r * g.sR + c)
         th.lin = lin + g.sM;
@@ -417,7 +419,7 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             for (int j = 0; j < VEC; ++j) o.v[j] = un[j];
             pxb_vstore<T, VEC>(a.u_out + lin, o);
             // peer-memory exchange: the first owned plane of the new primal iterate is the lower neighbour's upper ghost plane
-            if (m == 0 && a.peer.dn_u != nullptr) pxb_vstore<T, VEC>(a.peer.dn_u + (int64_t)r * g.sR + c, o);
+            if (!it.nopeer && m == 0 && a.peer.dn_u != nullptr) pxb_vstore<T, VEC>(a.peer.dn_u + (int64_t)r * g.sR + c, o);
         }
         // previous x of this thread's samples on the NEXT plane, consumed one plane later: loaded straight into the registers
         // the sums above have just released (a load into a temporary moved over afterwards made the move wait for the load:
