@@ -175,6 +175,21 @@ PXB_HD void pxb_tma_fold_kz(const PxbTvP<T>& q, const PxbTmaFold& fb, const T* _
     }
 }
 
+// A value loaded from a staged box must have ARRIVED before the thread passes the per-plane barrier: behind it thread 0 re-arms the
+// stage and the TMA unit overwrites the box.  bar.sync orders the load's issue, not its completion; a load whose result is first used
+// in the next plane (the carried z0 of the rims) can sit in the memory-instruction queue behind this thread's global stores -- the
+// kernel is memory-bound -- long enough to read the NEXT contents of the box: one wrong rim cell in ~10^6 thread-block-planes at 1024^3,
+// different from run to run (tools/check_kernel_determinism.py).  Reading the register makes the scoreboard wait.
+template <class T>
+PXB_HD void pxb_landed(T& v) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) asm volatile("mov.b32 %0, %0;" : "+f"(reinterpret_cast<float&>(v)));
+    else asm volatile("mov.b64 %0, %0;" : "+d"(reinterpret_cast<double&>(v)));
+#else
+    (void)v;
+#endif
+}
+
 template <class T, int VEC>
 struct PxbTmaThread {
     T zc[3][VEC];     // z_in at this thread's own samples, plane just visited
@@ -355,6 +370,22 @@ PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const Pxb
     }
 }
 
+// PD3O + RelError[x]: the previous x of this thread's samples on the plane phase A visits NEXT (plane m + 1 after phase A of plane m),
+// loaded one plane ahead straight into th.xp (a load into a temporary moved over afterwards made the move wait for the load: 9.5 ms
+// instead of 7.3 at 1024^3).  Called AFTER the per-plane barrier: issued from inside phase A, ahead of the rim-column code, the packed
+// instances produced sporadic wrong rim cells at 1024^3 (one in ~10^6 thread-block-planes, tools/check_kernel_determinism.py) -- a
+// scheduling-dependent hazard that neither the scalar bodies nor this placement show.
+template <class T, int VEC, int TY, int ALGO, bool NORMS>
+PXB_HD void pxb_tma_xprefetch(const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid, int m, PxbTmaThread<T, VEC>& th) {
+    using C = PxbTmaCfg<T, VEC, TY>;
+    if (!(ALGO == PXB_PD3O && NORMS) || PXB_EXP(8) || a.norms_x == nullptr) return;
+    if (!(m + 1 >= it.m0 && m + 1 < it.m1)) return;
+    const int rl = tid / C::TXL, r = it.r0 + rl, c = it.c0 + (tid - rl * C::TXL) * VEC;
+    if (!(it.full || (r < g.nR && c < g.nC))) return;
+    const PxbVec<T, VEC> nx = pxb_vload<T, VEC>(a.x_out + th.lin);  // (th.lin: already advanced to plane m + 1)
+    for (int j = 0; j < VEC; ++j) th.xp[j] = nx.v[j];
+}
+
 // phase A of plane m out of stage `st` (plane m) and, for two-sided / backward schemes, `st_next` (plane m+1).
 // MODES (folding boundary modes): the staged boxes are zero-filled outside the domain, i.e. they carry the 'constant'
 // extension.  In-domain samples add the fold terms of K^T z (pxb_tv_fold_kz); the cells of the w ring one step outside
@@ -421,13 +452,6 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             // peer-memory exchange: the first owned plane of the new primal iterate is the lower neighbour's upper ghost plane
             if (!it.nopeer && m == 0 && a.peer.dn_u != nullptr) pxb_vstore<T, VEC>(a.peer.dn_u + (int64_t)r * g.sR + c, o);
         }
-        // previous x of this thread's samples on the NEXT plane, consumed one plane later: loaded straight into the registers
-        // the sums above have just released (a load into a temporary moved over afterwards made the move wait for the load:
-        // 9.5 ms instead of 7.3 at 1024^3, long-scoreboard stalls doubled)
-        if (ALGO == PXB_PD3O && NORMS && !PXB_EXP(8) && a.norms_x != nullptr && m + 1 >= it.m0 && m + 1 < it.m1 && in_rc) {
-            const PxbVec<T, VEC> nx = pxb_vload<T, VEC>(a.x_out + lin + g.sM);
-            for (int j = 0; j < VEC; ++j) th.xp[j] = nx.v[j];
-        }
     }
     // rims: w of the neighbouring tiles' border samples (only on planes this work item updates); the carried z0 of
     // the previous plane is refreshed on every plane
@@ -460,7 +484,7 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             }
         }
         const PxbVec<T, VEC> z = pxb_vload<T, VEC>(st + C::OFF_Z0 + (MODES ? brs : br) * C::BW + cl + VEC);
-        for (int j = 0; j < VEC; ++j) th.z0p_rim[j] = z.v[j];
+        for (int j = 0; j < VEC; ++j) { th.z0p_rim[j] = z.v[j]; pxb_landed(th.z0p_rim[j]); }
     }
     if (tid >= C::NT - 2 * TY) {
         const int h = tid - (C::NT - 2 * TY);
@@ -489,5 +513,6 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             }
         }
         th.z0p_col = st[C::OFF_Z0 + (hl + 1) * C::BW + (MODES ? bcs : bc)];
+        pxb_landed(th.z0p_col);
     }
 }
