@@ -67,6 +67,7 @@ struct PxbTvP {
     // uniform-register operands straight from the constant bank (computed per call and per thread they were 7 % of the instructions):
     // [0..2] sigma*c0[k], [3..5] sigma*cp[k], [6..8] -tau*c0[k], [9..11] -tau*cp[k], [12] 1 - 2 alpha tau, [13] -2 alpha tau, [14] -1
     alignas(8) T pk[15][2];
+    T one;  // 1, opaque to the compiler: `v * one` is an exact copy of v that cannot be issued before v's load has landed (pxb_landed)
 };
 
 
@@ -108,6 +109,7 @@ PXB_HD void pxb_tv_prepare(const pxb_grad_desc& d, const PxbTvCoef& cf, const px
         }
         v[13] = -q.tau * q.two_alpha; v[12] = T(1) + v[13]; v[14] = T(-1);
         for (int i = 0; i < 15; ++i) q.pk[i][0] = q.pk[i][1] = v[i];
+        q.one = T(1);
     }
     q.gkind = P.g.kind; q.fkind = P.f.kind; q.hkind = P.hkind;
     const PxbGeom g = pxb_geom(d.shape);

@@ -179,15 +179,11 @@ PXB_HD void pxb_tma_fold_kz(const PxbTvP<T>& q, const PxbTmaFold& fb, const T* _
 // stage and the TMA unit overwrites the box.  bar.sync orders the load's issue, not its completion; a load whose result is first used
 // in the next plane (the carried z0 of the rims) can sit in the memory-instruction queue behind this thread's global stores -- the
 // kernel is memory-bound -- long enough to read the NEXT contents of the box: one wrong rim cell in ~10^6 thread-block-planes at 1024^3,
-// different from run to run (tools/check_kernel_determinism.py).  Reading the register makes the scoreboard wait.
+// different from run to run (tools/check_kernel_determinism.py).  A dependent instruction makes the scoreboard wait (a self-move is
+// dropped by ptxas: SASS showed the LDS directly in front of BAR.SYNC).
 template <class T>
-PXB_HD void pxb_landed(T& v) {
-#if defined(__CUDA_ARCH__)
-    if constexpr (sizeof(T) == 4) asm volatile("mov.b32 %0, %0;" : "+f"(reinterpret_cast<float&>(v)));
-    else asm volatile("mov.b64 %0, %0;" : "+d"(reinterpret_cast<double&>(v)));
-#else
-    (void)v;
-#endif
+PXB_HD T pxb_landed(const PxbTvP<T>& q, T v) {
+    return v * q.one;  // (q.one == 1 comes from the constant bank: the multiplication stays, and it needs v in its register)
 }
 
 template <class T, int VEC>
@@ -372,9 +368,7 @@ PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const Pxb
 
 // PD3O + RelError[x]: the previous x of this thread's samples on the plane phase A visits NEXT (plane m + 1 after phase A of plane m),
 // loaded one plane ahead straight into th.xp (a load into a temporary moved over afterwards made the move wait for the load: 9.5 ms
-// instead of 7.3 at 1024^3).  Called AFTER the per-plane barrier: issued from inside phase A, ahead of the rim-column code, the packed
-// instances produced sporadic wrong rim cells at 1024^3 (one in ~10^6 thread-block-planes, tools/check_kernel_determinism.py) -- a
-// scheduling-dependent hazard that neither the scalar bodies nor this placement show.
+// instead of 7.3 at 1024^3).  Called right after the per-plane barrier.
 template <class T, int VEC, int TY, int ALGO, bool NORMS>
 PXB_HD void pxb_tma_xprefetch(const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid, int m, PxbTmaThread<T, VEC>& th) {
     using C = PxbTmaCfg<T, VEC, TY>;
@@ -484,7 +478,7 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             }
         }
         const PxbVec<T, VEC> z = pxb_vload<T, VEC>(st + C::OFF_Z0 + (MODES ? brs : br) * C::BW + cl + VEC);
-        for (int j = 0; j < VEC; ++j) { th.z0p_rim[j] = z.v[j]; pxb_landed(th.z0p_rim[j]); }
+        for (int j = 0; j < VEC; ++j) th.z0p_rim[j] = pxb_landed(q, z.v[j]);
     }
     if (tid >= C::NT - 2 * TY) {
         const int h = tid - (C::NT - 2 * TY);
@@ -512,7 +506,6 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
                 slot[(hl + 1) * R::RS + bc] = in ? wv[0] : T(0);
             }
         }
-        th.z0p_col = st[C::OFF_Z0 + (hl + 1) * C::BW + (MODES ? bcs : bc)];
-        pxb_landed(th.z0p_col);
+        th.z0p_col = pxb_landed(q, st[C::OFF_Z0 + (hl + 1) * C::BW + (MODES ? bcs : bc)]);
     }
 }
