@@ -82,7 +82,6 @@ __global__ void __launch_bounds__(32 * TY, 2)
         pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring, th, fb);
         __syncthreads();  // w(m) complete; every thread is done with stage s
         if (tid == 0 && m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
-        pxb_tma_xprefetch<T, VEC, TY, ALGO, NORMS>(g, it, a, tid, m, th);
         const int mm = m - lag;
         if (mm >= it.m0 && mm < it.m1) {
             T zo[3][VEC];

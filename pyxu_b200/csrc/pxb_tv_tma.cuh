@@ -368,7 +368,7 @@ PXB_HD void pxb_tma_prologue(const PxbTvP<T>& q, const PxbIterGeom& g, const Pxb
 
 // PD3O + RelError[x]: the previous x of this thread's samples on the plane phase A visits NEXT (plane m + 1 after phase A of plane m),
 // loaded one plane ahead straight into th.xp (a load into a temporary moved over afterwards made the move wait for the load: 9.5 ms
-// instead of 7.3 at 1024^3).  Called right after the per-plane barrier.
+// instead of 7.3 at 1024^3).  Called at the end of phase A's own-sample block.
 template <class T, int VEC, int TY, int ALGO, bool NORMS>
 PXB_HD void pxb_tma_xprefetch(const PxbIterGeom& g, const PxbIterItem& it, const PxbIterPtr<T>& a, int tid, int m, PxbTmaThread<T, VEC>& th) {
     using C = PxbTmaCfg<T, VEC, TY>;
@@ -446,6 +446,7 @@ PXB_HD void pxb_tma_phaseA(const PxbTvP<T>& q, const PxbIterGeom& g, const PxbTm
             // peer-memory exchange: the first owned plane of the new primal iterate is the lower neighbour's upper ghost plane
             if (!it.nopeer && m == 0 && a.peer.dn_u != nullptr) pxb_vstore<T, VEC>(a.peer.dn_u + (int64_t)r * g.sR + c, o);
         }
+        pxb_tma_xprefetch<T, VEC, TY, ALGO, NORMS>(g, it, a, tid, m, th);
     }
     // rims: w of the neighbouring tiles' border samples (only on planes this work item updates); the carried z0 of
     // the previous plane is refreshed on every plane

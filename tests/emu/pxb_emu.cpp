@@ -264,7 +264,6 @@ static int t_tma_run(const pxb_grad_desc* K, const pxb_pds_params* p, const PxbI
             const T* st_next = need_next ? stages.data() + ((k + 1) % C::NSTAGE) * C::STAGE : st;
             for (int tid = 0; tid < C::NT; ++tid) pxb_tma_phaseA<T, VEC, TY, ALGO, NORMS, S, MODES>(q, g, tg, it, a, tid, m, st, st_next, ring.data(), th[tid], fbx);
             if (m + C::NSTAGE < mload_hi) issue(m + C::NSTAGE);
-            for (int tid = 0; tid < C::NT; ++tid) pxb_tma_xprefetch<T, VEC, TY, ALGO, NORMS>(g, it, a, tid, m, th[tid]);
             const int mm = m - lag;
             for (int tid = 0; tid < C::NT; ++tid) {
                 if (mm >= it.m0 && mm < it.m1) {
