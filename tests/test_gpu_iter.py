@@ -380,3 +380,36 @@ def test_small_2d_batch_is_one_cooperative_launch(env, dtype, algo):
         c0 = lib.pxb_launch_count()
         K.check(lib.pxb_pds_iter_n(A_, C.byref(d2), C.byref(P2), u0.data_ptr(), z0.data_ptr(), u1.data_ptr(), z1.data_ptr(), None, None, 4, None, None, None), "iter_n")
         assert lib.pxb_launch_count() - c0 == 4, (shape, mode)
+
+
+def test_criterion_iteration_is_bitwise_reproducible_at_full_size(env):
+    """The headline volume (1024^3 fp32, 131 072 thread blocks): K iterations of the criterion-carrying TMA instance twice from the same
+    state must agree bit for bit.  Guards the one asynchrony bug of round 2 -- a value loaded from a staged box right before the
+    per-plane barrier and first used in the next plane could be read after the TMA unit had refilled the box (one wrong rim cell in ~10^6
+    thread-block-planes, different from run to run).  Before the fix every second pair of runs differed."""
+    K, lib = env.K, env.lib
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70 << 30:
+        pytest.skip("needs ~60 GiB of free device memory")
+    shape = (1024, 1024, 1024)
+    N = int(np.prod(shape))
+    y = torch.rand(N, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
+    shift = -y
+    P = params(K, 0.28, 0.28, 1.0, (K.PROX_POS, 0.0, 0.0), K.F_SQL2, 0.5, shift, None, K.DUAL_L21, 0.08)
+    d = env.operator.Gradient(arg_shape=shape, dtype=np.float32)._desc(1, K.F32)
+    zinit = 0.01 * torch.randn(3 * N, device=DEV, generator=torch.Generator(device=DEV).manual_seed(7))
+    ref = None
+    for rep in range(4):
+        u0, u1, z0, z1, x = y.clone(), torch.zeros_like(y), zinit.clone(), torch.zeros(3 * N, device=DEV), y.clone()
+        nx, nz = torch.zeros(2, device=DEV, dtype=torch.float64), torch.zeros(2, device=DEV, dtype=torch.float64)
+        a, b = (u0, z0), (u1, z1)
+        for _ in range(6):
+            K.check(lib.pxb_pds_iter(K.ALGO_PD3O, C.byref(d), C.byref(P), a[0].data_ptr(), a[1].data_ptr(), b[0].data_ptr(), b[1].data_ptr(),
+                                     x.data_ptr(), nx.data_ptr(), nz.data_ptr(), None), "iter")
+            a, b = b, a
+        _sync()
+        if ref is None:
+            ref = (a[0].clone(), a[1].clone())
+        else:
+            assert torch.equal(ref[0], a[0]) and torch.equal(ref[1], a[1]), f"run {rep} differs from run 0"
+        del u0, u1, z0, z1, x
