@@ -240,6 +240,31 @@ int pxb_stencil3d_apply(const pxb_stencil3d* d, const void* in, void* out, void*
  * always.  No reference counterpart: for A/B measurements and tests. */
 int pxb_set_stencil3d_path(int path);
 
+/* A DENSE (full-rank) 3-D stencil ('constant' boundaries; e.g. a measured 7x7x7 PSF) in ONE pass over HBM.  The reference takes
+ * any dense kernel and evaluates it sample by sample over the padded array (stencil.py:356-461, _stencil.py:232-305); here
+ * thread blocks march along axis 0 and scatter every staged input plane into the register accumulators of the output planes it
+ * contributes to, the coefficients being constant-bank operands of the FMAs (k0*k1*k2 FMAs per sample, 8 B/voxel in fp32).
+ *   out = alpha * S(in) + beta * add[i % add_period]     (add: dense (batch, n0, n1, n2), nullable)
+ * coef: k0*k1*k2 HOST values, row-major; center[]: the kernel's entry on the output sample.  The adjoint of a zero-padded
+ * correlation is the correlation with the reversed kernel and the mirrored centre (the caller passes those).
+ * Envelope: every extent <= 7 and the kernel filling at least half of the enclosing cube of 3, 5 or 7 taps; last axis a multiple
+ * of 4 / 2 samples, 16-byte aligned arrays; PXB_ENOSUP otherwise (use pxb_stencil_apply, or pxb_stencil2d_apply per kernel
+ * plane).  Slab cuts: as pxb_stencil_axis0_apply. */
+typedef struct pxb_stencil3d_dense {
+    int32_t dtype;
+    int32_t _pad;
+    int64_t batch;
+    int64_t shape[3];
+    int32_t ksize[3];
+    int32_t center[3];
+    const double* coef;
+    double alpha, beta;
+    const void* add;
+    int64_t add_period;
+    pxb_slab slab;
+} pxb_stencil3d_dense;
+int pxb_stencil3d_dense_apply(const pxb_stencil3d_dense* d, const void* in, void* out, void* stream);
+
 /* One accelerated proximal-gradient (FISTA) iteration on f = alpha_f*||A x + shift||^2, g pointwise, A such a stencil
  * (reference: src/pyxu/opt/solver/pgd.py:173-191), as TWO tiled passes instead of five:
  *   which == 0:  out = r = d.alpha * A((1+a) x - a x_prev) + d.beta * d.add      (d describes A; the extrapolated point

@@ -96,6 +96,23 @@ class Stencil3D(C.Structure):
     ]
 
 
+class Stencil3DDense(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("_pad", C.c_int32),
+        ("batch", C.c_int64),
+        ("shape", C.c_int64 * 3),
+        ("ksize", C.c_int32 * 3),
+        ("center", C.c_int32 * 3),
+        ("coef", C.POINTER(C.c_double)),
+        ("alpha", C.c_double),
+        ("beta", C.c_double),
+        ("add", C.c_void_p),
+        ("add_period", C.c_int64),
+        ("slab", Slab),
+    ]
+
+
 class GradDesc(C.Structure):
     _fields_ = [
         ("dtype", C.c_int32),
@@ -183,6 +200,7 @@ PROTOTYPES = {
     "pxb_stencil_axis0_apply": (_i, [_i, _i64, _P(C.c_int64), _P(Slab), _i, _i, _P(C.c_double), _vp, _vp, _vp]),
     "pxb_stencil_axis0_fold": (_i, [_i, _i64, _P(C.c_int64), _i, _i, _P(C.c_double), _i, _i, _vp, _vp, _vp]),
     "pxb_stencil3d_apply": (_i, [_P(Stencil3D), _vp, _vp, _vp]),
+    "pxb_stencil3d_dense_apply": (_i, [_P(Stencil3DDense), _vp, _vp, _vp]),
     "pxb_gradient_apply": (_i, [_P(GradDesc), _vp, _vp, _vp]),
     "pxb_gradient_adjoint": (_i, [_P(GradDesc), _vp, _vp, _vp]),
     "pxb_prox_lincomb": (_i, [_i, _P(ProxSpec), _d, _i64, _vp, _d, _vp, _d, _vp, _i64, _d, _vp, _i64, _vp]),

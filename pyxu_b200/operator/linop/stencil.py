@@ -31,6 +31,11 @@ import os as _os
 
 PADDED_TILED = _os.environ.get("PYXU_B200_STENCIL_PADDED", "1") != "0"
 
+# Dense (full-rank) 3-D kernels through the marching kernel (pxb_stencil3d_dense_apply: one pass over HBM, K^3 FMAs per sample with
+# constant-bank coefficients) instead of one tiled dense 2-D pass per plane of the kernel (Stencil._run_dense3d).
+# PYXU_B200_DENSE3D_MARCH=0 / 1 selects the path for A/B runs.
+DENSE3D_MARCH = _os.environ.get("PYXU_B200_DENSE3D_MARCH", "0") != "0"
+
 
 def canonical_mode(mode, ndim):
     """tuple[str] of length ndim (reference: pad.py:190-205)."""
@@ -124,6 +129,7 @@ class Stencil(pxo.SquareOp):
         self._tiled_ok = None  # TMA-tiled single-pass kernel (pxb_stencil2d_apply): None = not tried yet
         self._tiled3d_ok = None  # single-pass separable 3-D kernel (pxb_stencil3d_apply)
         self._padded_ok = None  # Pad -> tiled stencil / tiled stencil -> Pad^T for folding boundary modes (_run_padded)
+        self._march3d_ok = None  # dense (full-rank) 3-D kernel in one marching pass (_run_dense3d_march)
         self._dense3d_ok = None  # dense (full-rank) 3-D kernel as one tiled dense 2-D pass per plane of the kernel (_run_dense3d)
         self._folds = any(m != "constant" for m, p in zip(self._mode, self._pad_width) if p[0] > 0)
         self.lipschitz = self.estimate_lipschitz(__rule=True)
@@ -347,6 +353,55 @@ class Stencil(pxo.SquareOp):
         d.slab = slab if slab is not None else K.Slab(0, 0, 0, 0)
         return d
 
+    def _desc3d_dense(self, dcode, adjoint, batch, alpha=1.0, beta=0.0, add=None, slab=None, shape0=None):
+        """pxb_stencil3d_dense descriptor (marching kernel for a dense 3-D kernel of full rank, 'constant' boundaries), or None when
+        the operator is not one dense 3-D pass inside the kernel's envelope (every extent <= 7, at least half of the enclosing cube
+        of 3 / 5 / 7 taps filled)."""
+        passes = self._passes(False)
+        if self._folds or len(passes) != 1 or len(self._arg_shape) != 3 or any(m != "constant" for m in self._mode):
+            return None
+        k3, c3 = passes[0]
+        m = max(k3.shape)
+        cube = 3 if m <= 3 else 5 if m <= 5 else 7 if m <= 7 else 0
+        if not cube or 2 * k3.size < cube**3 or min(k3.shape) < 2:
+            return None
+        if adjoint:  # zero-padded correlation: transpose = correlation with the reversed kernel, mirrored centre
+            k3, c3 = np.ascontiguousarray(np.flip(k3)), np.array(k3.shape) - c3 - 1
+        d = K.Stencil3DDense()
+        d.dtype, d.batch = dcode, batch
+        n0, n1, n2 = self._arg_shape
+        d.shape[0], d.shape[1], d.shape[2] = (shape0 if shape0 is not None else n0), n1, n2
+        for a in range(3):
+            d.ksize[a], d.center[a] = int(k3.shape[a]), int(c3[a])
+        coef = (C.c_double * k3.size)(*[float(v) for v in k3.reshape(-1)])
+        d.coef = C.cast(coef, C.POINTER(C.c_double))
+        d._keep_coef = coef
+        d.alpha, d.beta = float(alpha), float(beta)
+        if add is not None:
+            d.add, d.add_period = add.data_ptr(), add.numel()
+            d._keep = add
+        d.slab = slab if slab is not None else K.Slab(0, 0, 0, 0)
+        return d
+
+    def _run_dense3d_march(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
+        """A dense 3-D kernel of full rank in one pass (pxb_stencil3d_dense_apply); None outside the kernel's envelope."""
+        if self._march3d_ok is False or self._rank1_split(*self._passes(False)[0]) is not None:
+            return None
+        batch = max(1, arr.numel() // self.dim)
+        addf = add.reshape(-1) if add is not None else None
+        d = self._desc3d_dense(A.dcode(arr), adjoint, batch, alpha, beta, addf)
+        if d is None:
+            self._march3d_ok = False
+            return None
+        out = A.empty_like(arr)
+        rc = K.lib().pxb_stencil3d_dense_apply(C.byref(d), A.ptr(arr), A.ptr(out), A.stream())
+        if rc == -3:
+            self._march3d_ok = False
+            return None
+        K.check(rc, "pxb_stencil3d_dense_apply")
+        self._march3d_ok = True
+        return out
+
     # -- folding boundary modes through the tiled kernel -------------------------------------------------
     def _run_padded(self, arr, adjoint, alpha=1.0, beta=0.0, add=None):
         """Stencil = Trim o S0 o Pad (reference: stencil.py:76-84) with a folding mode on an in-plane axis, as two passes over
@@ -488,6 +543,11 @@ class Stencil(pxo.SquareOp):
         if not ok:
             self._dense3d_ok = False
             return None
+        if DENSE3D_MARCH and self._march3d_ok is not False:
+            out = self._run_dense3d_march(arr, adjoint, alpha, beta, add)
+            if out is not None:
+                self._dense3d_ok = True
+                return out
         if adjoint:  # zero-padded correlation: transpose = correlation with the reversed kernel, mirrored centre
             k3, c3 = np.ascontiguousarray(np.flip(k3)), np.array(k3.shape) - c3 - 1
         n0, n1, n2 = self._arg_shape

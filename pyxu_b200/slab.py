@@ -778,12 +778,18 @@ class SlabDeblurCV(_Engine):
         self._xb[0][0, own].copy_(x0.reshape(n0, *self.shape[1:]))
         self.comm = torch.cuda.Stream(device=self.dev, priority=-1) if world > 1 else None
         Aop._slab_dcode = A.dcode(self.r)
-        self._plans = {adj: Aop._tiled_plan(adj) for adj in (False, True)}
-        if not all(p is not None and p[0] is not None for p in self._plans.values()):
-            raise NotImplementedError("slab decomposition of a Stencil data term: expected a separable 'constant'-mode PSF with a factor along axis 0")
         self._slab = K.Slab(1 if self.hx.lo is not None else 0, 1 if self.hx.hi is not None else 0, H, self._alloc)
         self._cache = {}   # descriptors per (kind, adjoint / parity, p0, p1): built once
-        self.single_pass = Aop._desc3d(A.dcode(self.r), False, 1, slab=self._slab, shape0=n0) is not None
+        self._plans = {adj: Aop._tiled_plan(adj) for adj in (False, True)}
+        # a dense PSF of full rank: the marching kernel reads the ghost planes itself (pxb_stencil3d_dense_apply)
+        from .operator.linop import stencil as _st
+
+        self.dense = (_st.DENSE3D_MARCH and not all(p is not None for p in self._plans.values())
+                      and Aop._desc3d_dense(A.dcode(self.r), False, 1, slab=self._slab, shape0=n0) is not None)
+        if not self.dense and not all(p is not None and p[0] is not None for p in self._plans.values()):
+            raise NotImplementedError("slab decomposition of a Stencil data term: expected a 'constant'-mode PSF that is separable with a factor along "
+                                      "axis 0, or dense with at most 7 taps per axis (PYXU_B200_DENSE3D_MARCH)")
+        self.single_pass = not self.dense and Aop._desc3d(A.dcode(self.r), False, 1, slab=self._slab, shape0=n0) is not None
         self.edge = max(H, min(8, n0 // 4))  # planes of the boundary launches that precede each exchange
         self.overlap = bool(overlap) and world > 1 and n0 >= 4 * self.edge
         self._gdesc = Kop._desc(1, A.dcode(self.r), slab=self._slab, shape0=n0)
@@ -814,6 +820,9 @@ class SlabDeblurCV(_Engine):
             if not adjoint and self.add is not None:
                 add = self.add if self.add.numel() == 1 else self.add[p0 * self.plane : p1 * self.plane]
             al, be = (1.0, 0.0) if adjoint else (self.two_alpha, self.two_alpha if add is not None else 0.0)
+            if self.dense:
+                c = self._cache[key] = (self.Aop._desc3d_dense(A.dcode(self.r), adjoint, 1, al, be, add, slab=slab, shape0=p1 - p0), None, slab, None)
+                return self._stencil(adjoint, src, dst, p0, p1)
             d3 = self.Aop._desc3d(A.dcode(self.r), adjoint, 1, al, be, add, slab=slab, shape0=p1 - p0) if self.single_pass else None
             d2 = None
             if d3 is None:
@@ -824,6 +833,9 @@ class SlabDeblurCV(_Engine):
                     self.tmp = self._field()
             c = self._cache[key] = (d3, d2, slab, self._plans[adjoint][0])
         d3, d2, slab, axis0 = c
+        if self.dense:
+            K.check(K.lib().pxb_stencil3d_dense_apply(C.byref(d3), self._p(src, 0, p0), self._p(dst, 0, p0), A.stream()), "pxb_stencil3d_dense_apply")
+            return
         if d3 is not None:
             rc = K.lib().pxb_stencil3d_apply(C.byref(d3), self._p(src, 0, p0), self._p(dst, 0, p0), A.stream())
             if rc == -3:  # outside the marching kernel's envelope (e.g. an even number of taps along z): two passes from now on

@@ -6,6 +6,7 @@
 // GPU-less build container.  Never loaded by the pyxu_b200 package; pointers here are HOST pointers.
 #include <algorithm>
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 
 static long g_w_global_cells = 0;  // cells of the w tiles evaluated by pxb_tv_w_global (folded rims that left the tile)
@@ -17,8 +18,11 @@ static long g_w_global_cells = 0;  // cells of the w tiles evaluated by pxb_tv_w
 #include "../../pyxu_b200/csrc/pxb_stencil_tma.cuh"
 #include "../../pyxu_b200/csrc/pxb_tv_tile2d.cuh"
 #include "../../pyxu_b200/csrc/pxb_stencil3d.cuh"
+#include "../../pyxu_b200/csrc/pxb_stencil3d_dense.cuh"
 #include "../../pyxu_b200/csrc/pxb_stencil_axis0.cuh"
 #include <vector>
+
+static int g_d3_chunk = 0;  // emu_stencil3d_dense: forced chunk length (0: the launcher's choice)
 
 // folding boundary modes inside the single-kernel iteration forms (pxb_set_iter_modes on the device side)
 static bool g_allow_modes = true;
@@ -588,6 +592,83 @@ static int t_st3(const pxb_stencil3d* d, const void* in, void* out) {
     }
 }
 
+// dense K x K x K marching stencil (pxb_stencil3d_dense.cuh): CTA by CTA, plane by plane, the phases between two barriers of
+// k_stencil3d_dense replayed for all threads in turn; per-thread registers (accumulator slots, fetched window) are arrays
+template <class T, int K>
+static int t_d3_run(const pxb_stencil3d_dense* d, const T* in, T* out) {
+    using C = PxbD3Cfg<T, K>;
+    constexpr int VEC = C::VEC;
+    PxbD3P<T, K> p;
+    p.n0 = (int)d->shape[0]; p.n1 = (int)d->shape[1]; p.n2 = (int)d->shape[2];
+    p.batch = d->batch;
+    const int halo = d->slab.halo;
+    const int alloc = d->slab.plane_alloc > 0 ? d->slab.plane_alloc : p.n0 + 2 * halo;
+    p.vol = (int64_t)alloc * d->shape[1] * d->shape[2];
+    p.c0 = d->center[0]; p.c1 = d->center[1]; p.c2 = d->center[2];
+    p.lo_planes = d->slab.open_lo ? d->center[0] : 0;
+    p.hi_planes = d->slab.open_hi ? d->ksize[0] - 1 - d->center[0] : 0;
+    p.alpha = T(d->alpha); p.beta = T(d->beta);
+    p.add = (const T*)d->add; p.add_period = d->add_period;
+    if (d->add && d->add_period > 0 && d->add_period >= d->batch * d->shape[0] * d->shape[1] * d->shape[2]) p.add_period = 0;
+    for (int a = 0; a < K; ++a)
+        for (int bb = 0; bb < K; ++bb)
+            for (int c = 0; c < K; ++c) {
+                const bool in_k = a < d->ksize[0] && bb < d->ksize[1] && c < d->ksize[2];
+                p.coef[(a * K + bb) * K + c] = in_k ? T(d->coef[((int64_t)a * d->ksize[1] + bb) * d->ksize[2] + c]) : T(0);
+            }
+    if (int why = pxb_d3_setup<T, K>(p)) return -100 - why;
+    if (g_d3_chunk > 0) { p.chunk = std::min(g_d3_chunk, p.n0); p.nchunk = (p.n0 + p.chunk - 1) / p.chunk; }  // tests: several chunks on small volumes
+    const int64_t s0 = (int64_t)p.n1 * p.n2;
+    struct Regs { T acc[K][C::R][VEC]; T pre[C::NROW * C::NCOL]; };
+    std::vector<Regs> regs(C::NT);
+    std::vector<T> box0(C::BOX), box1(C::BOX);
+    T* box[2] = {box0.data(), box1.data()};
+    for (int64_t b = 0; b < p.batch; ++b)
+        for (int ch = 0; ch < p.nchunk; ++ch)
+            for (int ty = 0; ty < p.nty; ++ty)
+                for (int tx = 0; tx < p.ntx; ++tx) {
+                    const int x0 = tx * C::TX, y0 = ty * C::TY;
+                    const int m0 = ch * p.chunk, m1 = std::min(p.n0, m0 + p.chunk);
+                    const int pl_lo = m0 - p.c0, pl_hi = m1 + K - 1 - p.c0;
+                    const int ra = std::max(pl_lo, -p.lo_planes), rb = std::min(pl_hi, p.n0 + p.hi_planes);
+                    const T* vol = in + b * p.vol;
+                    for (auto& r : regs) std::memset(&r, 0, sizeof(r));
+                    std::fill(box0.begin(), box0.end(), T(NAN));  // a read of a cell no thread staged poisons the result
+                    std::fill(box1.begin(), box1.end(), T(NAN));
+                    if (ra < rb)
+                        for (int tid = 0; tid < C::NT; ++tid) {
+                            pxb_d3_fetch<T, K>(p, vol + (int64_t)ra * s0, y0, x0, tid, regs[tid].pre);
+                            pxb_d3_stash<T, K>(regs[tid].pre, box[0], tid);
+                        }
+                    for (int pl = ra; pl < pl_hi; ++pl) {
+                        const bool have = pl < rb, more = pl + 1 < rb;
+                        const int k = pl - ra, q = pl - (K - 1 - p.c0);
+                        for (int tid = 0; tid < C::NT; ++tid) {
+                            Regs& r = regs[tid];
+                            const int xl = (tid & 31) * VEC, yl = (tid >> 5) * C::R;
+                            if (more) pxb_d3_fetch<T, K>(p, vol + (int64_t)(pl + 1) * s0, y0, x0, tid, r.pre);
+                            T addv[C::R][VEC];
+                            if (q >= m0) pxb_d3_load_add<T, K>(p, addv, b, q, y0, x0, yl, xl);
+                            if (have) pxb_d3_accum<T, K>(p.coef, box[k & 1], yl, xl, r.acc);
+                            if (q >= m0) pxb_d3_emit<T, K>(p, out, r.acc[K - 1], addv, b, q, y0, x0, yl, xl);
+                            pxb_d3_shift<T, K>(r.acc);
+                        }
+                        if (more)
+                            for (int tid = 0; tid < C::NT; ++tid) pxb_d3_stash<T, K>(regs[tid].pre, box[(k + 1) & 1], tid);
+                    }
+                }
+    return 0;
+}
+template <class T>
+static int t_d3(const pxb_stencil3d_dense* d, const void* in, void* out) {
+    switch (pxb_d3_cube(d->ksize)) {
+        case 3: return t_d3_run<T, 3>(d, (const T*)in, (T*)out);
+        case 5: return t_d3_run<T, 5>(d, (const T*)in, (T*)out);
+        case 7: return t_d3_run<T, 7>(d, (const T*)in, (T*)out);
+        default: return -101;
+    }
+}
+
 template <class T>
 static void t_pad2d(const pxb_pad2d_desc* d, bool adj, const void* a, void* b, double alpha, double beta, const void* add, int64_t add_period) {
     const int64_t rows = adj ? d->shape[0] : d->ext_shape[0], cols = adj ? d->shape[1] : d->ext_shape[1];
@@ -645,6 +726,10 @@ int emu_stencil_axis0_fold(int dtype, int64_t batch, const int64_t* shape, int k
                            void* out, int chunk) {
     return dtype == PXB_F32 ? t_axis0<float>(batch, shape, k0, c0, coef, mode, adjoint, in, out, chunk)
                             : t_axis0<double>(batch, shape, k0, c0, coef, mode, adjoint, in, out, chunk);
+}
+int emu_stencil3d_dense(const pxb_stencil3d_dense* d, const void* in, void* out, int chunk) {
+    g_d3_chunk = chunk;
+    return d->dtype == PXB_F32 ? t_d3<float>(d, in, out) : t_d3<double>(d, in, out);
 }
 int emu_stencil3d(const pxb_stencil3d* d, const void* in, void* out) {
     return d->dtype == PXB_F32 ? t_st3<float>(d, in, out) : t_st3<double>(d, in, out);

@@ -89,6 +89,10 @@ class EmuLib:
     def pxb_stencil3d_apply(self, d, x, out, stream):
         return self._ok("stencil3d", self.h.emu_stencil3d(d, x, out))
 
+    def pxb_stencil3d_dense_apply(self, d, x, out, stream):
+        # a forced chunk length of 5 planes, so that chunk borders take part on the small volumes of the tests
+        return self._ok("stencil3d_dense", self.h.emu_stencil3d_dense(d, x, out, 5))
+
     def pxb_stencil_axis0_apply(self, *a):
         return ENOSUP  # the streaming kernel's body is not replayed on the host: callers take the gather kernel, as on a GPU outside its envelope
 

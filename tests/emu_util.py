@@ -36,6 +36,7 @@ def lib():
         h.emu_stencil2d_fista.argtypes = [P(K.Stencil2D), P(K.FistaStep), i, vp]
         h.emu_tv_grad.argtypes = [i, i, P(K.GradDesc), vp, vp]
         h.emu_stencil3d.argtypes = [P(K.Stencil3D), vp, vp]
+        h.emu_stencil3d_dense.argtypes = [P(K.Stencil3DDense), vp, vp, i]
         h.emu_stencil_axis0_fold.argtypes = [i, i64, P(C.c_int64), i, i, P(C.c_double), i, i, vp, vp, i]
         h.emu_dual_update.argtypes = [i, i, i64, i64, i64, d, d, d, vp, vp, vp]
         h.emu_prox_l21.argtypes = [i, i64, i64, i64, d, d, vp, vp]
@@ -146,6 +147,21 @@ def stencil3d_run(op, x, adjoint, alpha=1.0, beta=0.0, add=None, slab=None, shap
         return lib().emu_stencil3d(C.byref(d), raw_ptrs[0], raw_ptrs[1])
     out = np.empty_like(x)
     rc = lib().emu_stencil3d(C.byref(d), p(np.ascontiguousarray(x)), p(out))
+    return out if rc == 0 else None
+
+
+def stencil3d_dense_run(op, x, adjoint, alpha=1.0, beta=0.0, add=None, chunk=0, slab=None, shape0=None, raw_ptrs=None):
+    """Dense K x K x K marching kernel (emulated).  chunk > 0 forces the chunk length; raw_ptrs = (in_ptr, out_ptr) for slab buffers."""
+    batch = 1 if raw_ptrs else max(1, x.size // op.dim)
+    d = op._desc3d_dense(dcode(x), adjoint, batch, alpha, beta, None, slab=slab, shape0=shape0)
+    if d is None:
+        return None
+    if add is not None:
+        d.add, d.add_period = add.ctypes.data, add.size
+    if raw_ptrs:
+        return lib().emu_stencil3d_dense(C.byref(d), raw_ptrs[0], raw_ptrs[1], chunk)
+    out = np.empty_like(x)
+    rc = lib().emu_stencil3d_dense(C.byref(d), p(np.ascontiguousarray(x)), p(out), chunk)
     return out if rc == 0 else None
 
 

@@ -229,6 +229,42 @@ def slabs(ns):
     print("slabs.npz", len(out))
 
 
+def dense_psf(ks, seed, skew=0.6):
+    """A dense PSF of FULL RANK (not an outer product): a sheared anisotropic Gaussian plus a small irregular part, normalised to sum 1."""
+    ax = [np.arange(k) - (k - 1) / 2 for k in ks]
+    a, b, c = np.meshgrid(*ax, indexing="ij")
+    q = (a / (0.35 * ks[0])) ** 2 + ((b - skew * a) / (0.3 * ks[1])) ** 2 + ((c + skew * b) / (0.4 * ks[2])) ** 2
+    k = np.exp(-0.5 * q) * (1 + 0.1 * np.random.default_rng(seed).standard_normal(ks))
+    return k / k.sum()
+
+
+def dense3d(ns):
+    """Dense 3-D kernels of full rank (the reference takes any dense kernel: stencil.py:356-461): Stencil apply / adjoint, and CondatVu
+    TV deblurring with such a PSF on a volume tall enough to be cut into z-slabs."""
+    stop = ns.stop
+    out = {}
+    rng = np.random.default_rng(31)
+    for i, (shape, ks, cen) in enumerate((((12, 19, 24), (7, 7, 7), (3, 3, 3)), ((11, 18, 16), (5, 4, 5), (4, 0, 3)), ((6, 20, 24), (3, 3, 3), (1, 1, 1)),
+                                          ((9, 21, 28), (7, 7, 7), (0, 6, 1)))):
+        kern = rng.standard_normal(ks)
+        op = ns.operator.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        x = rng.standard_normal((2, int(np.prod(shape))))
+        out[f"st{i}/shape"], out[f"st{i}/center"], out[f"st{i}/kernel"], out[f"st{i}/x"] = np.array(shape), np.array(cen), kern, x
+        out[f"st{i}/apply"], out[f"st{i}/adjoint"] = np.asarray(op.apply(x)), np.asarray(op.adjoint(x))
+    shape = (32, 12, 16)
+    x3, _ = cases.phantom(shape, seed=32)
+    psf = dense_psf((5, 5, 5), 33)
+    assert np.linalg.svd(psf.reshape(5, 25), compute_uv=False)[1] > 1e-3  # full rank: no separable pass applies
+    slv, A = cases.build_tv_deblur(ns, np.zeros(shape), shape, psf, (2, 2, 2), positivity=True)
+    yb = np.asarray(A.apply(x3.reshape(-1))) + 0.01 * np.random.default_rng(34).standard_normal(x3.size)
+    out["cv_deblur3d_dense/y"], out["cv_deblur3d_dense/psf"] = yb, psf
+    slv, A = cases.build_tv_deblur(ns, yb, shape, psf, (2, 2, 2), lam=0.02, positivity=True)
+    slv.fit(x0=np.zeros(yb.size), stop_crit=stop.MaxIter(15), rho=0.9)
+    _record(slv, "cv_deblur3d_dense", out)
+    np.savez_compressed(os.path.join(HERE, "dense3d.npz"), **out)
+    print("dense3d.npz", len(out))
+
+
 def config0(ns):
     """BASELINE.json configs[0] at full size: 512x512 float64 PD3O TV denoising, 200 iterations.
 
@@ -249,6 +285,6 @@ def config0(ns):
 
 if __name__ == "__main__":
     ns = _ref_import.load()
-    which = sys.argv[1:] or ["stencils", "gradients", "funcs", "solvers", "slabs", "config0"]
+    which = sys.argv[1:] or ["stencils", "gradients", "funcs", "solvers", "slabs", "dense3d", "config0"]
     for w in which:
         globals()[w](ns)

@@ -103,6 +103,16 @@ def main(dev="cuda"):
         slv, Aop = cases.build_tv_deblur(px, yb, shape, psf, cen, lam=0.02, positivity=True)
         slv.fit(x0=np.zeros(yb.size), stop_crit=pxst.MaxIter(15), **kw, **always)
         check_fixture(tag, slv, gs, tag)
+    # -- the same with a DENSE 5x5x5 PSF of full rank (reaches 2 planes across a cut): the dense marching kernel per slab ---------
+    from pyxu_b200.operator.linop import stencil as st_mod
+
+    if st_mod.DENSE3D_MARCH:
+        gd = np.load(os.path.join(ROOT, "tests", "golden", "dense3d.npz"))
+        yd = gd["cv_deblur3d_dense/y"]
+        slv, Aop = cases.build_tv_deblur(px, yd, shape, gd["cv_deblur3d_dense/psf"], (2, 2, 2), lam=0.02, positivity=True)
+        slv.fit(x0=np.zeros(yd.size), stop_crit=pxst.MaxIter(15), rho=0.9, **always)
+        assert slv._slab.dense
+        check_fixture("cv_deblur3d_dense", slv, gd, "cv_deblur3d_dense")
     # -- the small fixtures of the single-GPU suite, when their slabs are thick enough --------------------------------
     if world <= 3:
         y3 = g0["pd3o_tv3d/y"]

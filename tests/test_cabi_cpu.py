@@ -43,6 +43,8 @@ def test_struct_layouts_match_the_c_compiler():
       printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", offsetof(pxb_stencil_desc, coef), offsetof(pxb_grad_desc, coef),
              offsetof(pxb_grad_desc, slab), offsetof(pxb_pds_params, lam), offsetof(pxb_stencil2d, coef), offsetof(pxb_stencil2d, add_period),
              offsetof(pxb_fista_step, norms), offsetof(pxb_stencil2d, origin), offsetof(pxb_pad2d_desc, mode));
+      printf("%zu %zu %zu %zu %zu\n", sizeof(pxb_stencil3d), sizeof(pxb_stencil3d_dense), offsetof(pxb_stencil3d_dense, coef),
+             offsetof(pxb_stencil3d_dense, slab), offsetof(pxb_stencil3d, slab));
       return 0; }
     """
     with tempfile.TemporaryDirectory() as td:
@@ -55,7 +57,8 @@ def test_struct_layouts_match_the_c_compiler():
     sizes = [C.sizeof(s) for s in (K.Slab, K.StencilDesc, K.GradDesc, K.ProxSpec, K.FTerm, K.PdsParams, K.Stencil2D, K.FistaStep, K.Pad2D, K.StopRule, K.IterCtl)]
     offs = [K.StopRule.table.offset, K.IterCtl.ticket.offset, K.StencilDesc.coef.offset, K.GradDesc.coef.offset, K.GradDesc.slab.offset, K.PdsParams.lam.offset, K.Stencil2D.coef.offset,
             K.Stencil2D.add_period.offset, K.FistaStep.norms.offset, K.Stencil2D.origin.offset, K.Pad2D.mode.offset]
-    assert [int(v) for v in out] == sizes + extra + offs
+    st3 = [C.sizeof(K.Stencil3D), C.sizeof(K.Stencil3DDense), K.Stencil3DDense.coef.offset, K.Stencil3DDense.slab.offset, K.Stencil3D.slab.offset]
+    assert [int(v) for v in out] == sizes + extra + offs + st3
 
 
 def test_argument_errors_are_reported_without_a_gpu():

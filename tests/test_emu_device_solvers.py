@@ -72,6 +72,14 @@ def test_cv_deblur3d_and_generic_path(dev):
     G.test_generic_path_equals_fused_path(dev)
 
 
+@pytest.mark.parametrize("march", [False, True], ids=["per_plane_passes", "marching_kernel"])
+def test_dense3d_golden(dev, march, monkeypatch):
+    G.test_dense3d_stencil_golden(dev, march, monkeypatch)
+    dev.lib.log.clear()
+    G.test_cv_deblur3d_dense(dev, march, monkeypatch)
+    assert ("stencil3d_dense" in dev.lib.log) is march and "stencil" not in dev.lib.log
+
+
 @pytest.mark.parametrize("padded", [False, True])
 def test_reflect_mode_blur_through_gather_and_padded_tiled_paths(dev, padded, monkeypatch):
     """PD3O / PGD with a reflect-mode blur in the data term: the gather kernels (default) and Stencil._run_padded
@@ -441,3 +449,45 @@ def test_dense_3d_kernel_of_full_rank_runs_as_tiled_passes_per_kernel_plane(dev,
     fold = pxo.Stencil(arg_shape=(9, 20, 24), kernel=rng.standard_normal((3, 3, 3)).astype(dtype), center=(1, 1, 1), mode="reflect")
     fold.apply(torch.zeros(fold.dim, dtype=torch.float64 if dtype == np.float64 else torch.float32))
     assert fold._dense3d_ok in (None, False) and fold._tiled_ok is not True
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_dense_3d_kernel_of_full_rank_through_the_marching_kernel(dev, dtype, monkeypatch):
+    """The same operators with the marching kernel selected (PYXU_B200_DENSE3D_MARCH): ONE launch per direction inside its envelope,
+    the per-plane passes outside it; results against the gather kernels and the NumPy oracle."""
+    import torch
+
+    import test_gpu_operators as GO
+    from oracle import pyxu_oracle as orc
+    from pyxu_b200.operator.linop import stencil as st_mod
+
+    monkeypatch.setattr(st_mod, "DENSE3D_MARCH", True)
+    pxo = dev.operator
+    rng = np.random.default_rng(4)
+    tol = 1e-12 if dtype == np.float64 else 2e-5
+    for shape, ks, cen, march in (((9, 20, 24), (3, 3, 3), (1, 1, 1), True), ((13, 12, 16), (5, 4, 5), (0, 2, 3), True), ((12, 10, 8), (7, 7, 6), (6, 0, 1), True),
+                                  ((4, 10, 8), (7, 2, 3), (6, 0, 1), False)):
+        kern = rng.standard_normal(ks).astype(dtype)
+        fast = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        slow = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        slow._dense3d_ok = False
+        x = torch.from_numpy(rng.standard_normal((2, fast.dim)).astype(dtype))
+        y = torch.from_numpy(rng.standard_normal(fast.dim).astype(dtype))
+        for adj in (False, True):
+            dev.lib.log.clear()
+            a = fast.adjoint(x) if adj else fast.apply(x)
+            if march:
+                assert fast._march3d_ok is True and dev.lib.log == ["stencil3d_dense"], dev.lib.log
+            else:
+                assert fast._march3d_ok is False and "stencil3d_dense" not in dev.lib.log and "stencil2d" in dev.lib.log
+            b = slow.adjoint(x) if adj else slow.apply(x)
+            assert GO.relerr(a.numpy(), b.numpy()) < tol, (shape, ks, adj)
+        oref = orc.Stencil(shape, kern.astype(np.float64), cen, "constant")
+        ref = oref.apply(x.numpy().astype(np.float64))
+        assert GO.relerr(fast.apply(x).numpy(), ref) < tol and GO.relerr(fast.adjoint(x).numpy(), oref.adjoint(x.numpy().astype(np.float64))) < tol
+        got = fast._run_tiled(x, False, alpha=0.5, beta=-1.0, add=y)
+        assert GO.relerr(got.numpy(), 0.5 * ref - y.numpy()) < tol
+    # an outer product keeps the separable single pass
+    sep = pxo.Stencil(arg_shape=(9, 20, 24), kernel=np.ones((3, 3, 3), dtype=dtype), center=(1, 1, 1), mode="constant")
+    sep.apply(torch.zeros(sep.dim, dtype=torch.float64 if dtype == np.float64 else torch.float32))
+    assert sep._march3d_ok is None and sep._tiled3d_ok is True

@@ -235,6 +235,93 @@ def test_single_pass_3d_slab_cuts():
 
 
 # ---------------------------------------------------------------------------------------------------------
+# Dense (full-rank) 3-D kernels in one marching pass (pxb_stencil3d_dense.cuh): every staged input plane scattered into the
+# register accumulators of the K output planes it contributes to.  Against the gather kernels' bodies and the NumPy oracle.
+# ---------------------------------------------------------------------------------------------------------
+DENSE3D_CASES = [
+    # (arg_shape, kernel extents, center)
+    ((21, 19, 140), (7, 7, 7), (3, 3, 3)),   # the "7x7x7 PSF" of BASELINE configs[4]; ragged tiles in both in-plane directions
+    ((9, 35, 264), (7, 7, 7), (0, 6, 1)),    # off-centre everywhere (windows start at any column); three tiles along the rows
+    ((12, 17, 72), (5, 5, 5), (2, 2, 2)),
+    ((11, 18, 16), (5, 4, 5), (4, 0, 3)),    # embedded in the 5-cube (zero taps behind the kernel's own)
+    ((6, 20, 24), (3, 3, 3), (1, 1, 1)),
+    ((3, 9, 8), (7, 6, 5), (6, 2, 0)),       # fewer planes than taps: most kernel planes never meet a source plane
+    ((10, 16, 12), (2, 3, 3), (1, 0, 2)),    # embedded in the 3-cube
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", range(len(DENSE3D_CASES)))
+def test_dense_3d_marching_kernel(dtype, case):
+    from oracle import pyxu_oracle as orc
+
+    shape, ks, cen = DENSE3D_CASES[case]
+    rng = np.random.default_rng(100 + case)
+    kern = rng.standard_normal(ks).astype(dtype)
+    op = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+    x = rng.standard_normal((2, op.dim)).astype(dtype)
+    y = rng.standard_normal(op.dim).astype(dtype)
+    tol = 1e-13 if dtype == np.float64 else 2e-5
+    oref = orc.Stencil(shape, kern.astype(np.float64), cen, "constant")
+    for adj in (False, True):
+        ref = E.stencil_run(op, x, adj)
+        for chunk in (0, 4):  # the launcher's chunk length (one chunk at these sizes) / several chunks, the last one ragged
+            out = E.stencil3d_dense_run(op, x, adj, chunk=chunk)
+            assert out is not None and not np.isnan(out).any() and relerr(out, ref) < tol, (adj, chunk, relerr(out, ref))
+        oo = oref.adjoint(x.astype(np.float64)) if adj else oref.apply(x.astype(np.float64))
+        assert relerr(out, oo) < tol
+    out = E.stencil3d_dense_run(op, x, False, alpha=0.5, beta=-1.0, add=y, chunk=5)  # the operand of one item serves the stack
+    assert relerr(out, 0.5 * E.stencil_run(op, x, False) - y) < tol
+    # adjoint identity <S x, z> = <x, S^T z> through the marching kernel alone
+    z = rng.standard_normal((2, op.dim)).astype(dtype)
+    lhs = np.sum(E.stencil3d_dense_run(op, x, False).astype(np.float64) * z)
+    rhs = np.sum(x * E.stencil3d_dense_run(op, z, True).astype(np.float64))
+    assert abs(lhs - rhs) < (1e-11 if dtype == np.float64 else 2e-4) * (1 + abs(lhs))
+
+
+def test_dense_3d_marching_kernel_envelope():
+    """Outside the envelope the descriptor is not even built: folding modes, more than 7 taps, kernels that leave most of the cube empty."""
+    rng = np.random.default_rng(0)
+    mk = lambda ks, mode="constant": pxo.Stencil(arg_shape=(12, 16, 16), kernel=rng.standard_normal(ks), center=(0, 0, 0), mode=mode)
+    assert mk((7, 7, 7))._desc3d_dense(1, False, 1) is not None
+    assert mk((3, 3, 3), "reflect")._desc3d_dense(1, False, 1) is None
+    assert mk((9, 3, 3))._desc3d_dense(1, False, 1) is None
+    assert mk((7, 2, 3))._desc3d_dense(1, False, 1) is None     # 42 of 343 taps
+    assert mk((1, 3, 3))._desc3d_dense(1, False, 1) is None     # a 2-D kernel: the tiled 2-D pass
+    # last axis not a multiple of the vector width: the launcher declines (PXB_ENOSUP), callers fall back
+    op = pxo.Stencil(arg_shape=(5, 6, 7), kernel=rng.standard_normal((3, 3, 3)), center=(1, 1, 1), mode="constant")
+    assert E.stencil3d_dense_run(op, rng.standard_normal(op.dim), False) is None
+
+
+def test_dense_3d_marching_kernel_slab_cuts():
+    """z-slab cuts: every slab filtered on its own (ghost planes = the neighbours' planes) == the whole volume."""
+    import ctypes as C
+
+    from pyxu_b200 import _cabi as K
+
+    rng = np.random.default_rng(3)
+    shape = (23, 17, 72)
+    op = pxo.Stencil(arg_shape=shape, kernel=rng.standard_normal((7, 5, 6)), center=(2, 2, 3), mode="constant")
+    x = rng.standard_normal(shape)
+    plane = shape[1] * shape[2]
+    H = 4
+    for adj in (False, True):
+        ref = E.stencil_run(op, x.reshape(-1), adj).reshape(shape)
+        parts, got = [(0, 8), (8, 16), (16, 23)], []
+        for r, (a, b) in enumerate(parts):
+            n0 = b - a
+            buf = np.zeros((n0 + 2 * H,) + shape[1:])
+            lo, hi = max(0, a - H), min(shape[0], b + H)
+            buf[H - (a - lo) : H + n0 + (hi - b)] = x[lo:hi]
+            out = np.full_like(buf, np.nan)
+            slab = K.Slab(1 if r > 0 else 0, 1 if r < len(parts) - 1 else 0, H, n0 + 2 * H)
+            ptr = lambda t: C.c_void_p(t.ctypes.data + 8 * H * plane)
+            assert E.stencil3d_dense_run(op, buf, adj, chunk=3, slab=slab, shape0=n0, raw_ptrs=(ptr(buf), ptr(out))) == 0
+            got.append(out[H : H + n0])
+        assert relerr(np.concatenate(got, axis=0), ref) < 1e-13, adj
+
+
+# ---------------------------------------------------------------------------------------------------------
 # Folding boundary modes through the tiled kernel (Stencil._run_padded): Pad (pxb_pad2d) -> tiled S0 on the padded array /
 # tiled S0^T onto the padded extent -> Pad^T (pxb_pad2d_adjoint).  Against the gather kernels, the fixtures of the real
 # reference and the adjoint identity.

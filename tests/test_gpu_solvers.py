@@ -195,6 +195,37 @@ def test_cv_deblur3d(px):
     check(slv, g, "cv_deblur3d")
 
 
+@pytest.mark.parametrize("march", [False, True], ids=["per_plane_passes", "marching_kernel"])
+def test_dense3d_stencil_golden(px, march, monkeypatch):
+    """Dense 3-D kernels of FULL RANK against the real reference's outputs (tests/golden/dense3d.npz): per-plane tiled passes and the
+    marching kernel (pxb_stencil3d_dense_apply), fp64 and fp32, apply and adjoint."""
+    from pyxu_b200.operator.linop import stencil as st_mod
+
+    monkeypatch.setattr(st_mod, "DENSE3D_MARCH", march)
+    g = golden("dense3d.npz")
+    for i in range(4):
+        shape, cen, kern, x = tuple(int(v) for v in g[f"st{i}/shape"]), tuple(int(v) for v in g[f"st{i}/center"]), g[f"st{i}/kernel"], g[f"st{i}/x"]
+        for dt, tol in ((np.float64, 1e-12), (np.float32, 5e-6)):
+            op = px.operator.Stencil(arg_shape=shape, kernel=kern.astype(dt), center=cen, mode="constant")
+            assert relerr(op.apply(x.astype(dt)), g[f"st{i}/apply"]) < tol, (i, dt)
+            assert relerr(op.adjoint(x.astype(dt)), g[f"st{i}/adjoint"]) < tol, (i, dt)
+            assert op._dense3d_ok is True and op._march3d_ok is (True if march else None)
+
+
+@pytest.mark.parametrize("march", [False, True], ids=["per_plane_passes", "marching_kernel"])
+def test_cv_deblur3d_dense(px, march, monkeypatch):
+    """CondatVu TV deblurring with a dense 5x5x5 PSF of full rank (configs[4] with a measured PSF) against the real reference."""
+    from pyxu_b200.operator.linop import stencil as st_mod
+
+    monkeypatch.setattr(st_mod, "DENSE3D_MARCH", march)
+    g = golden("dense3d.npz")
+    yb, psf = g["cv_deblur3d_dense/y"], g["cv_deblur3d_dense/psf"]
+    slv, A = cases.build_tv_deblur(px, yb, (32, 12, 16), psf, (2, 2, 2), lam=0.02, positivity=True)
+    slv.fit(x0=np.zeros(yb.size), stop_crit=px.stop.MaxIter(15), rho=0.9)
+    check(slv, g, "cv_deblur3d_dense")
+    assert A._dense3d_ok is True and A._march3d_ok is (True if march else None)
+
+
 @pytest.mark.parametrize("acc", [True, False])
 def test_pgd_l1_deconv(px, acc):
     g = golden("solvers.npz")

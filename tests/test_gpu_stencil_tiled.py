@@ -248,3 +248,47 @@ def test_dense_3d_kernel_of_full_rank(dtype, tol):
         z = torch.randn(2, fast.dim, device="cuda", dtype=tdt)
         lhs, rhs = torch.sum(fast.apply(x).double() * z.double()), torch.sum(x.double() * fast.adjoint(z).double())
         assert abs(float(lhs - rhs)) < (1e-10 if dtype == np.float64 else 2e-4) * (1 + abs(float(lhs)))
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 2e-5)])
+def test_dense_3d_marching_kernel(dtype, tol, monkeypatch):
+    """A dense 3-D PSF of full rank in ONE marching pass (pxb_stencil3d_dense_apply, selected by PYXU_B200_DENSE3D_MARCH) against the
+    per-sample gather kernels (which the golden-vector tests pin on the real reference) and the per-plane tiled passes: cubes and
+    embedded kernels, off-centre entries, ragged tiles, several chunks and waves of thread blocks, stacks, epilogue, adjoint identity."""
+    import pyxu_b200.operator as pxo
+    from pyxu_b200.operator.linop import stencil as st_mod
+
+    monkeypatch.setattr(st_mod, "DENSE3D_MARCH", True)
+    rng = np.random.default_rng(6)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    cases = (((40, 45, 264), (7, 7, 7), (3, 3, 3)), ((70, 130, 520), (7, 7, 7), (0, 6, 1)), ((33, 37, 64), (5, 5, 5), (2, 2, 2)), ((19, 50, 136), (5, 4, 5), (4, 0, 3)),
+             ((64, 64, 128), (3, 3, 3), (1, 1, 1)), ((3, 9, 8), (7, 6, 5), (6, 2, 0)))
+    for shape, ks, cen in cases:
+        kern = rng.standard_normal(ks).astype(dtype)
+        fast = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        slow = pxo.Stencil(arg_shape=shape, kernel=kern, center=cen, mode="constant")
+        slow._dense3d_ok = False
+        x = torch.randn(2, fast.dim, device="cuda", dtype=tdt)
+        y = torch.randn(fast.dim, device="cuda", dtype=tdt)
+        for adj in (False, True):
+            a = fast.adjoint(x) if adj else fast.apply(x)
+            assert fast._march3d_ok is True
+            b = slow.adjoint(x) if adj else slow.apply(x)
+            assert slow._dense3d_ok is False and rel(a, b) < tol, (shape, ks, adj, rel(a, b))
+        assert rel(fast._run_tiled(x, False, alpha=0.5, beta=-1.0, add=y), 0.5 * slow.apply(x) - y) < tol
+        z = torch.randn(2, fast.dim, device="cuda", dtype=tdt)
+        lhs, rhs = torch.sum(fast.apply(x).double() * z.double()), torch.sum(x.double() * fast.adjoint(z).double())
+        assert abs(float(lhs - rhs)) < (1e-10 if dtype == np.float64 else 2e-4) * (1 + abs(float(lhs)))
+    # against the per-plane tiled passes at a size with many tiles, chunks and waves
+    monkeypatch.setattr(st_mod, "DENSE3D_MARCH", False)
+    shape = (96, 256, 512)
+    kern = rng.standard_normal((7, 7, 7)).astype(dtype)
+    planes = pxo.Stencil(arg_shape=shape, kernel=kern, center=(3, 3, 3), mode="constant")
+    x = torch.randn(planes.dim, device="cuda", dtype=tdt)
+    ref_f, ref_a = planes.apply(x), planes.adjoint(x)
+    assert planes._dense3d_ok is True and planes._march3d_ok is None
+    monkeypatch.setattr(st_mod, "DENSE3D_MARCH", True)
+    march = pxo.Stencil(arg_shape=shape, kernel=kern, center=(3, 3, 3), mode="constant")
+    got_f, got_a = march.apply(x), march.adjoint(x)
+    assert march._march3d_ok is True and rel(got_f, ref_f) < tol and rel(got_a, ref_a) < tol
+    assert torch.equal(march.apply(x), got_f)  # run-to-run identical

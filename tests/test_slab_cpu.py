@@ -445,10 +445,10 @@ def test_slab_worker_on_the_emulated_device(world):
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PXB_SLAB_WORKER_DEVICE="cpu", OMP_NUM_THREADS="1")
+    env = dict(os.environ, PXB_SLAB_WORKER_DEVICE="cpu", OMP_NUM_THREADS="1", PYXU_B200_DENSE3D_MARCH="1")  # (the dense-PSF case included)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(root, "tests", "slab_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    n = 12 if world <= 3 else 11
+    n = 13 if world <= 3 else 12
     assert f"{n}/{n} cases OK" in r.stdout and "FAIL" not in r.stdout

@@ -63,12 +63,16 @@ for k in [int(v) for v in args.taps.split(",")]:
             rows.append({"taps": k, "kernel": label, "what": what, "ms": ms, "bytes_per_voxel": bpv, "GBps": bpv * N / ms / 1e6})
             print(f"{k}x{k}x{k} {label:8s} {what:10s} {ms:8.3f} ms  {bpv * N / ms / 1e6:7.0f} GB/s ({bpv} B/voxel)", flush=True)
     lib.pxb_set_stencil3d_path(0)
-# a dense PSF of full rank (not an outer product): one tiled dense 2-D pass per kernel plane (Stencil._run_dense3d) against the gather kernel
+# a dense PSF of full rank (not an outer product): the marching kernel (K^3 FMAs per sample, one pass), one tiled dense 2-D pass per kernel
+# plane (Stencil._run_dense3d), the gather kernel
 for k in [int(v) for v in args.taps.split(",") if int(v) <= 7]:
     kern = np.random.default_rng(k).random((k, k, k)).astype(ndt)
-    for label, force in (("tiled", None), ("gather", False)):
-        if args.only and label != "tiled":
+    for label, force in (("march", None), ("tiled", None), ("gather", False)):
+        if args.only and label not in ("tiled", "march"):
             continue
+        from pyxu_b200.operator.linop import stencil as st_mod
+
+        st_mod.DENSE3D_MARCH = label == "march"  # one marching pass (pxb_stencil3d_dense_apply) / one tiled 2-D pass per kernel plane
         op = pxo.Stencil(arg_shape=shape, kernel=kern, center=(k // 2,) * 3, mode="constant")
         op._dense3d_ok = force
         ms = timeit(lambda: op.apply(x), 2 if label == "gather" else args.reps)
