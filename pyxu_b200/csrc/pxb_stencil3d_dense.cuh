@@ -10,7 +10,7 @@
 //     (K x R x VEC per thread) live in registers and shift by one slot per plane; the slot that just received its last
 //     contribution is the finished output plane.  Each staged sample is therefore read from shared memory once per
 //     K*K*K-tap, not once per output plane: per thread and plane (R + K - 1) rows of NV vector loads feed R*VEC*K^3 FMAs
-//     (K = 7, fp32: 24 LDS.128 for 2744 FFMA);
+//     (K = 7, fp32: 42 LDS.128 for 2744 FFMA);
 //   * the K^3 coefficients are a by-value kernel parameter and every loop over taps is unrolled, so each FMA takes its
 //     coefficient as a constant-bank operand: no coefficient loads, no index arithmetic in the tap loops;
 //   * the next plane's window is fetched into registers before the accumulation and stored to the other buffer after it
@@ -25,8 +25,10 @@
 
 #if defined(__CUDACC__)
 #define PXB_UNROLL _Pragma("unroll")
+#define PXB_NOUNROLL _Pragma("unroll 1")
 #else
 #define PXB_UNROLL
+#define PXB_NOUNROLL
 #endif
 
 template <class T, int K>
@@ -38,6 +40,7 @@ struct PxbD3Cfg {
     static constexpr int PITCH = TX + (NV - 1) * VEC;         // columns of the staged window (>= TX + K - 1, multiple of VEC)
     static constexpr int NROW = (BH + 7) / 8, NCOL = (PITCH + 31) / 32;  // fetch: warp w takes rows w + 8i, lane l columns l + 32j
     static constexpr int BOX = (BH * PITCH + 31) / 32 * 32;   // elements of one staging buffer
+    static constexpr int CROW = (K * K + VEC - 1) / VEC * VEC;  // coefficients of one kernel row, padded to whole 16-byte vectors
 };
 
 template <class T, int K>
@@ -51,7 +54,8 @@ struct PxbD3P {            // by-value kernel parameter
     T alpha, beta;
     const T* add;          // dense (batch, n0, n1, n2), nullable
     int64_t add_period;    // 0: as long as the output
-    T coef[K * K * K];     // row-major (axis 0, 1, 2)
+    alignas(16) T coef[K * PxbD3Cfg<T, K>::CROW];  // [axis 1][axis 0][axis 2]: the K*K coefficients of one kernel row are contiguous and
+                           // start on a 16-byte boundary (vector loads from the parameter bank, pxb_d3_accum)
 };
 
 // window of input plane `plane` (pointer to its sample (0, 0)) for the tile at (y0, x0) -> registers; zeros outside the image
@@ -84,16 +88,16 @@ PXB_HD void pxb_d3_stash(const T* pre, T* __restrict__ box, int tid) {
     }
 }
 
-// one staged input plane scattered into the K output planes it contributes to: slot a holds the output plane that takes this
-// input plane with the kernel's plane a (output q = input plane - a + c0)
+// one kernel row (bp) of one staged input plane: window rows bp + r for the R output rows of the thread, every tap along the
+// columns and every kernel plane a.  `cf`: the K*K coefficients k[a][bp][c] of this kernel row, laid out [a][c].
 template <class T, int K>
-PXB_HD void pxb_d3_accum(const T* __restrict__ coef, const T* __restrict__ box, int yl, int xl, T (*acc)[PxbD3Cfg<T, K>::R][PxbD3Cfg<T, K>::VEC]) {
+PXB_HD void pxb_d3_row(const T* __restrict__ cf, const T* __restrict__ box, int yl, int xl, int bp, T (*acc)[PxbD3Cfg<T, K>::R][PxbD3Cfg<T, K>::VEC]) {
     using C = PxbD3Cfg<T, K>;
     constexpr int VEC = C::VEC;
 PXB_UNROLL
-    for (int b = 0; b < C::R + K - 1; ++b) {
+    for (int r = 0; r < C::R; ++r) {
         T v[C::NV * VEC];
-        const T* __restrict__ src = box + (yl + b) * C::PITCH + xl;
+        const T* __restrict__ src = box + (yl + bp + r) * C::PITCH + xl;
 PXB_UNROLL
         for (int n = 0; n < C::NV; ++n) {
             const PxbVec<T, VEC> t = pxb_vload<T, VEC>(src + n * VEC);
@@ -101,18 +105,30 @@ PXB_UNROLL
             for (int j = 0; j < VEC; ++j) v[n * VEC + j] = t.v[j];
         }
 PXB_UNROLL
-        for (int r = 0; r < C::R; ++r) {
-            const int bp = b - r;  // the kernel's row this window row is for output row r
-            if (bp < 0 || bp >= K) continue;
-PXB_UNROLL
-            for (int c = 0; c < K; ++c) {
+        for (int c = 0; c < K; ++c) {
+            PXB_UNROLL
+            for (int j = 0; j < VEC; ++j) {
                 PXB_UNROLL
-                for (int j = 0; j < VEC; ++j) {
-                    PXB_UNROLL
-                    for (int a = 0; a < K; ++a) acc[a][r][j] += coef[(a * K + bp) * K + c] * v[c + j];
-                }
+                for (int a = 0; a < K; ++a) acc[a][r][j] += cf[a * K + c] * v[c + j];
             }
         }
+    }
+}
+
+// one staged input plane scattered into the K output planes it contributes to: slot a holds the output plane that takes this
+// input plane with the kernel's plane a (output q = input plane - a + c0).  `coef` is laid out [kernel row][kernel plane][column].
+// The loop over the kernel's rows stays ROLLED for K > 3: fully unrolled, the 7x7x7 body is 2744 FFMA = 46 KB of code, more than
+// the 32 KB instruction cache an SM's warps share -- ncu on the first version: "no instruction" was the top stall (1.6 per
+// issued instruction, 78 % issue-active); one kernel row is 392 FFMA + 6 LDS + the row's 49 coefficients (uniform loads from the
+// parameter bank at a run-time row offset).
+template <class T, int K>
+PXB_HD void pxb_d3_accum(const T* __restrict__ coef, const T* __restrict__ box, int yl, int xl, T (*acc)[PxbD3Cfg<T, K>::R][PxbD3Cfg<T, K>::VEC]) {
+    if (K <= 3) {
+PXB_UNROLL
+        for (int bp = 0; bp < K; ++bp) pxb_d3_row<T, K>(coef + bp * PxbD3Cfg<T, K>::CROW, box, yl, xl, bp, acc);
+    } else {
+PXB_NOUNROLL
+        for (int bp = 0; bp < K; ++bp) pxb_d3_row<T, K>(coef + bp * PxbD3Cfg<T, K>::CROW, box, yl, xl, bp, acc);
     }
 }
 

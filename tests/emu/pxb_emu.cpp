@@ -610,11 +610,12 @@ static int t_d3_run(const pxb_stencil3d_dense* d, const T* in, T* out) {
     p.alpha = T(d->alpha); p.beta = T(d->beta);
     p.add = (const T*)d->add; p.add_period = d->add_period;
     if (d->add && d->add_period > 0 && d->add_period >= d->batch * d->shape[0] * d->shape[1] * d->shape[2]) p.add_period = 0;
+    for (int i = 0; i < K * C::CROW; ++i) p.coef[i] = T(0);
     for (int a = 0; a < K; ++a)
         for (int bb = 0; bb < K; ++bb)
             for (int c = 0; c < K; ++c) {
                 const bool in_k = a < d->ksize[0] && bb < d->ksize[1] && c < d->ksize[2];
-                p.coef[(a * K + bb) * K + c] = in_k ? T(d->coef[((int64_t)a * d->ksize[1] + bb) * d->ksize[2] + c]) : T(0);
+                p.coef[bb * C::CROW + a * K + c] = in_k ? T(d->coef[((int64_t)a * d->ksize[1] + bb) * d->ksize[2] + c]) : T(0);
             }
     if (int why = pxb_d3_setup<T, K>(p)) return -100 - why;
     if (g_d3_chunk > 0) { p.chunk = std::min(g_d3_chunk, p.n0); p.nchunk = (p.n0 + p.chunk - 1) / p.chunk; }  // tests: several chunks on small volumes

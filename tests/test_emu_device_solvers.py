@@ -409,11 +409,16 @@ def test_streamed_fit_brings_the_result_back_behind_the_wave(dev_rt, monkeypatch
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_dense_3d_kernel_of_full_rank_runs_as_tiled_passes_per_kernel_plane(dev, dtype):
+def test_dense_3d_kernel_of_full_rank_runs_as_tiled_passes_per_kernel_plane(dev, dtype, monkeypatch):
     """Stencil with a dense 3-D kernel that is not an outer product ('constant' boundaries): one tiled dense 2-D pass per plane of
-    the kernel, accumulated in place (Stencil._run_dense3d) -- apply, adjoint, stacks, epilogue operand -- against the gather kernels
-    and against the NumPy oracle's correlation."""
+    the kernel, accumulated in place (Stencil._run_dense3d; what serves the kernels the marching kernel declines, selected here with
+    PYXU_B200_DENSE3D_MARCH = 0) -- apply, adjoint, stacks, epilogue operand -- against the gather kernels and against the NumPy
+    oracle's correlation."""
     import torch
+
+    from pyxu_b200.operator.linop import stencil as st_mod
+
+    monkeypatch.setattr(st_mod, "DENSE3D_MARCH", False)
 
     import test_gpu_operators as GO
     from oracle import pyxu_oracle as orc

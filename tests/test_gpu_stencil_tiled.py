@@ -223,11 +223,15 @@ def test_single_pass_3d_cubic_instances(dtype, tol, K):
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 1e-5)])
-def test_dense_3d_kernel_of_full_rank(dtype, tol):
-    """A dense 3-D PSF that is not an outer product ('constant' boundaries) runs as one tiled dense 2-D pass per plane of the kernel,
-    accumulated in place through the epilogue operand (Stencil._run_dense3d), instead of the per-sample gather kernel."""
+def test_dense_3d_kernel_of_full_rank(dtype, tol, monkeypatch):
+    """A dense 3-D PSF that is not an outer product ('constant' boundaries) as one tiled dense 2-D pass per plane of the kernel,
+    accumulated in place through the epilogue operand (Stencil._run_dense3d: what serves the kernels the marching kernel declines,
+    selected here with PYXU_B200_DENSE3D_MARCH = 0), against the per-sample gather kernel."""
     import pyxu_b200.operator as pxo
     from pyxu_b200 import _cabi as Kc
+    from pyxu_b200.operator.linop import stencil as st_mod
+
+    monkeypatch.setattr(st_mod, "DENSE3D_MARCH", False)
 
     rng = np.random.default_rng(5)
     tdt = torch.float64 if dtype == np.float64 else torch.float32

@@ -22,6 +22,7 @@ ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--only", default=None)
 ap.add_argument("--taps", default="3,5,7,9")
 ap.add_argument("--dtype", default="f32")
+ap.add_argument("--dense-only", action="store_true", help="only the dense (full-rank) kernels")
 args = ap.parse_args()
 lib = K.lib()
 shape = (args.n0, args.n1, args.n2)
@@ -51,7 +52,7 @@ def timeit(fn, reps):
 x = torch.randn(1, N, device="cuda", dtype=tdt)
 y = torch.randn(N, device="cuda", dtype=tdt)
 rows = []
-for k in [int(v) for v in args.taps.split(",")]:
+for k in [] if args.dense_only else [int(v) for v in args.taps.split(",")]:
     op = pxo.Stencil(arg_shape=shape, kernel=[gauss(k, 0.2 * k)] * 3, center=(k // 2,) * 3, mode="constant")
     for label, path in (("fast", 0), ("general", 1)):
         if args.only and label != args.only:
@@ -75,7 +76,14 @@ for k in [int(v) for v in args.taps.split(",") if int(v) <= 7]:
         st_mod.DENSE3D_MARCH = label == "march"  # one marching pass (pxb_stencil3d_dense_apply) / one tiled 2-D pass per kernel plane
         op = pxo.Stencil(arg_shape=shape, kernel=kern, center=(k // 2,) * 3, mode="constant")
         op._dense3d_ok = force
-        ms = timeit(lambda: op.apply(x), 2 if label == "gather" else args.reps)
-        rows.append({"taps": k, "kernel": f"dense {label}", "what": "apply", "ms": ms, "gflops": 2 * k**3 * N / ms / 1e6})
-        print(f"{k}x{k}x{k} dense (full rank) {label:7s} apply {ms:9.3f} ms  {2 * k**3 * N / ms / 1e9:6.2f} TFLOP/s", flush=True)
+        for what, fn in (("apply", lambda: op.apply(x)), ("adjoint", lambda: op.adjoint(x)), ("apply - y", lambda: op._run_tiled(x, False, alpha=1.0, beta=-1.0, add=y))):
+            if label == "gather" and what != "apply":
+                continue
+            ms = timeit(fn, 2 if label == "gather" else args.reps)
+            rows.append({"taps": k, "kernel": f"dense {label}", "what": what, "ms": ms, "tflops": 2 * k**3 * N / ms / 1e9,
+                         "GBps": (3 if what == "apply - y" else 2) * isz * N / ms / 1e6})
+            print(f"{k}x{k}x{k} dense (full rank) {label:7s} {what:10s} {ms:9.3f} ms  {2 * k**3 * N / ms / 1e9:6.2f} TFLOP/s  {(3 if what == 'apply - y' else 2) * isz * N / ms / 1e6:7.0f} GB/s",
+                  flush=True)
+        if label == "march":
+            assert op._march3d_ok is True, "the marching kernel declined"
 print(json.dumps({"shape": f"{shape} {args.dtype}", "rows": rows}))
