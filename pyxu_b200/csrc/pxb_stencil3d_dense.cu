@@ -42,7 +42,11 @@ __global__ void __launch_bounds__(256, 2) k_stencil3d_dense(const __grid_constan
         const int q = pl - (K - 1 - p.c0);
         T addv[C::R][VEC];
         if (q >= m0) pxb_d3_load_add<T, K>(p, addv, b, q, y0, x0, yl, xl);
-        if (have) pxb_d3_accum<T, K>(p.coef, box[k & 1], yl, xl, acc);
+        if (have) {
+            const int a_lo = pl + p.c0 - m1 + 1, a_hi = pl + p.c0 - m0;  // slots whose output plane pl - a + c0 lies in [m0, m1)
+            if (a_lo <= 0 && a_hi >= K - 1) pxb_d3_accum<T, K>(p.coef, box[k & 1], yl, xl, acc);
+            else pxb_d3_accum_some<T, K>(p.coef, box[k & 1], yl, xl, acc, a_lo, a_hi);
+        }
         if (q >= m0) pxb_d3_emit<T, K>(p, out, acc[K - 1], addv, b, q, y0, x0, yl, xl);
         pxb_d3_shift<T, K>(acc);
         if (more) {

@@ -115,21 +115,57 @@ PXB_UNROLL
     }
 }
 
+// the same for the planes at the two ends of a chunk, where only the slots a_lo..a_hi belong to output planes of the chunk (the
+// others would collect sums nobody stores: (K - 1)/chunk of all FMAs): kernel plane outermost, one uniform test per slot
+template <class T, int K>
+PXB_HD void pxb_d3_row_some(const T* __restrict__ cf, const T* __restrict__ box, int yl, int xl, int bp, T (*acc)[PxbD3Cfg<T, K>::R][PxbD3Cfg<T, K>::VEC],
+                            int a_lo, int a_hi) {
+    using C = PxbD3Cfg<T, K>;
+    constexpr int VEC = C::VEC;
+PXB_UNROLL
+    for (int r = 0; r < C::R; ++r) {
+        T v[C::NV * VEC];
+        const T* __restrict__ src = box + (yl + bp + r) * C::PITCH + xl;
+PXB_UNROLL
+        for (int n = 0; n < C::NV; ++n) {
+            const PxbVec<T, VEC> t = pxb_vload<T, VEC>(src + n * VEC);
+PXB_UNROLL
+            for (int j = 0; j < VEC; ++j) v[n * VEC + j] = t.v[j];
+        }
+PXB_UNROLL
+        for (int a = 0; a < K; ++a) {
+            if (a < a_lo || a > a_hi) continue;
+            PXB_UNROLL
+            for (int c = 0; c < K; ++c) {
+                PXB_UNROLL
+                for (int j = 0; j < VEC; ++j) acc[a][r][j] += cf[a * K + c] * v[c + j];
+            }
+        }
+    }
+}
+
 // one staged input plane scattered into the K output planes it contributes to: slot a holds the output plane that takes this
 // input plane with the kernel's plane a (output q = input plane - a + c0).  `coef` is laid out [kernel row][kernel plane][column].
-// The loop over the kernel's rows stays ROLLED for K > 3: fully unrolled, the 7x7x7 body is 2744 FFMA = 46 KB of code, more than
+// The loop over the kernel's rows stays ROLLED for K = 7: fully unrolled, the 7x7x7 body is 2744 FFMA = 46 KB of code, more than
 // the 32 KB instruction cache an SM's warps share -- ncu on the first version: "no instruction" was the top stall (1.6 per
-// issued instruction, 78 % issue-active); one kernel row is 392 FFMA + 6 LDS + the row's 49 coefficients (uniform loads from the
-// parameter bank at a run-time row offset).
+// issued instruction, 78 % issue-active; rolled: 0.08 and 93 %, 4.20 -> 3.60 ms); one kernel row is 392 FFMA + 6 LDS + the row's
+// 49 coefficients (uniform loads from the parameter bank at a run-time row offset).  5x5x5 (1000 FFMA, 16 KB) fits and is faster
+// unrolled (1.59 against 1.9 ms on 256x1024^2).
 template <class T, int K>
 PXB_HD void pxb_d3_accum(const T* __restrict__ coef, const T* __restrict__ box, int yl, int xl, T (*acc)[PxbD3Cfg<T, K>::R][PxbD3Cfg<T, K>::VEC]) {
-    if (K <= 3) {
+    if (K <= 5) {
 PXB_UNROLL
         for (int bp = 0; bp < K; ++bp) pxb_d3_row<T, K>(coef + bp * PxbD3Cfg<T, K>::CROW, box, yl, xl, bp, acc);
     } else {
 PXB_NOUNROLL
         for (int bp = 0; bp < K; ++bp) pxb_d3_row<T, K>(coef + bp * PxbD3Cfg<T, K>::CROW, box, yl, xl, bp, acc);
     }
+}
+template <class T, int K>
+PXB_HD void pxb_d3_accum_some(const T* __restrict__ coef, const T* __restrict__ box, int yl, int xl, T (*acc)[PxbD3Cfg<T, K>::R][PxbD3Cfg<T, K>::VEC],
+                              int a_lo, int a_hi) {
+PXB_NOUNROLL
+    for (int bp = 0; bp < K; ++bp) pxb_d3_row_some<T, K>(coef + bp * PxbD3Cfg<T, K>::CROW, box, yl, xl, bp, acc, a_lo, a_hi);
 }
 
 // the epilogue's `add` samples of output plane q for this thread
@@ -193,8 +229,9 @@ inline int pxb_d3_cube(const int* ksize) {
     return K;
 }
 
-// host: chunk length along the marching axis.  A chunk spends K - 1 planes filling its accumulators (FMAs whose outputs belong
-// to the chunk below); fewer chunks leave the last wave of CTAs (2 per SM) partly empty.  Smallest cost of both.
+// host: chunk length along the marching axis.  A chunk reads K - 1 planes it shares with its neighbours (half of their FMAs
+// belong to the neighbour's outputs and are skipped); fewer chunks leave the last wave of CTAs (2 per SM) partly empty.
+// Smallest cost of both.
 template <class T, int K>
 inline int pxb_d3_setup(PxbD3P<T, K>& p) {
     using C = PxbD3Cfg<T, K>;
@@ -212,7 +249,7 @@ inline int pxb_d3_setup(PxbD3P<T, K>& p) {
         const int64_t ctas = tiles * ((p.n0 + chunk - 1) / chunk);
         const double waves = (double)ctas / slots;
         const double tail = (double)(int64_t)(waves + 0.999999) / waves;
-        const double cost = tail * (1.0 + (double)(K - 1) / chunk);
+        const double cost = tail * (1.0 + 0.5 * (double)(K - 1) / chunk);  // (the end planes run the slots of the chunk only)
         if (cost < best_cost - 1e-9) { best_cost = cost; best = chunk; }
     }
     p.chunk = best;

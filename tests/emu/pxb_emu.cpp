@@ -650,7 +650,11 @@ static int t_d3_run(const pxb_stencil3d_dense* d, const T* in, T* out) {
                             if (more) pxb_d3_fetch<T, K>(p, vol + (int64_t)(pl + 1) * s0, y0, x0, tid, r.pre);
                             T addv[C::R][VEC];
                             if (q >= m0) pxb_d3_load_add<T, K>(p, addv, b, q, y0, x0, yl, xl);
-                            if (have) pxb_d3_accum<T, K>(p.coef, box[k & 1], yl, xl, r.acc);
+                            if (have) {
+                                const int a_lo = pl + p.c0 - m1 + 1, a_hi = pl + p.c0 - m0;
+                                if (a_lo <= 0 && a_hi >= K - 1) pxb_d3_accum<T, K>(p.coef, box[k & 1], yl, xl, r.acc);
+                                else pxb_d3_accum_some<T, K>(p.coef, box[k & 1], yl, xl, r.acc, a_lo, a_hi);
+                            }
                             if (q >= m0) pxb_d3_emit<T, K>(p, out, r.acc[K - 1], addv, b, q, y0, x0, yl, xl);
                             pxb_d3_shift<T, K>(r.acc);
                         }

@@ -23,6 +23,7 @@ ap.add_argument("--only", default=None)
 ap.add_argument("--taps", default="3,5,7,9")
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--dense-only", action="store_true", help="only the dense (full-rank) kernels")
+ap.add_argument("--no-tiled", action="store_true", help="dense kernels: the marching kernel only")
 args = ap.parse_args()
 lib = K.lib()
 shape = (args.n0, args.n1, args.n2)
@@ -69,7 +70,7 @@ for k in [] if args.dense_only else [int(v) for v in args.taps.split(",")]:
 for k in [int(v) for v in args.taps.split(",") if int(v) <= 7]:
     kern = np.random.default_rng(k).random((k, k, k)).astype(ndt)
     for label, force in (("march", None), ("tiled", None), ("gather", False)):
-        if args.only and label not in ("tiled", "march"):
+        if (args.only and label not in ("tiled", "march")) or (args.no_tiled and label == "tiled"):
             continue
         from pyxu_b200.operator.linop import stencil as st_mod
 
