@@ -530,6 +530,33 @@ def secondary_configs(env, peak, K=10, W=3):
                               ms, launches, N, 12 + 8 + 36, world)
     del slv, f, Aop
     torch.cuda.empty_cache()
+
+    if world == 1:
+        # configs[4] with a DENSE 7x7x7 PSF of full rank (a measured PSF; the reference takes any dense kernel, stencil.py:356-461): the two
+        # stencil passes are then 343 FMAs per voxel each (pxb_stencil3d_dense_apply), the iteration is FMA- instead of HBM-bound.
+        # An extra entry: a failure here is reported in the entry and leaves the line intact.
+        try:
+            rng = np.random.default_rng(11)
+            ax = np.arange(7) - 3.0
+            q = (ax[:, None, None] / 2.4) ** 2 + ((ax[None, :, None] - 0.6 * ax[:, None, None]) / 2.1) ** 2 + ((ax[None, None, :] + 0.6 * ax[None, :, None]) / 2.8) ** 2
+            psf = np.exp(-0.5 * q) * (1 + 0.1 * rng.standard_normal((7, 7, 7)))
+            psf = (psf / psf.sum()).astype(np.float32)
+            Aop = pxo.Stencil(arg_shape=shape, kernel=psf, center=(3, 3, 3), mode="constant")
+            y_loc = torch.rand(N, device=env.dev, generator=gen)
+            f = (0.5 * pxo.SquaredL2Norm(dim=N).argshift(-y_loc)) * Aop
+            slv = pxs.CondatVu(f=f, g=pxo.PositiveOrthant(dim=N), h=h, K=pxo.Gradient(arg_shape=shape, dtype=np.float32), beta=float(Aop.lipschitz) ** 2,
+                               show_progress=False)
+            slv.fit(x0=y_loc, mode=Mode.MANUAL, stop_crit=pxst.ManualStop())
+            ms, launches, _ = timed_steps(env, slv.m_step, K, W)
+            flops = 2 * 2 * 343 * N  # two dense passes per iteration
+            out["configs[4] dense PSF"] = entry(f"3-D TV deblurring 2048x2048x{nz} fp32, CondatVu, DENSE 7x7x7 Stencil PSF of full rank + positivity, one GPU",
+                                                ms, launches, N, 12 + 8 + 36, 1, stencil_path="marching kernel" if Aop._march3d_ok else "per-plane tiled passes",
+                                                fp32_TFLOPs_per_s=flops / (ms / K) / 1e9,
+                                                note="FMA-bound: 2 x 343 FMA per voxel and iteration in the two stencil passes; frac (HBM) is not the bound here")
+            del slv, f, Aop, y_loc
+        except Exception as e:  # noqa: BLE001
+            out["configs[4] dense PSF"] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
     return out
 
 
