@@ -554,9 +554,9 @@ def secondary_configs(env, peak, K=10, W=3):
                                                 fp32_TFLOPs_per_s=flops / (ms / K) / 1e9,
                                                 note="FMA-bound: 2 x 343 FMA per voxel and iteration in the two stencil passes; frac (HBM) is not the bound here")
             del slv, f, Aop, y_loc
+            torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
             out["configs[4] dense PSF"] = {"error": f"{type(e).__name__}: {e}"}
-        torch.cuda.empty_cache()
     return out
 
 
